@@ -1,0 +1,214 @@
+"""Physical-consistency pins for the CPU oracle (oracle/fe_oracle.c).
+
+The reference holds no numeric test of the physics ("parity unpinned"), so the oracle is pinned by
+properties any correct restatement of the mj_step pipeline must satisfy."""
+import numpy as np
+import pytest
+
+from furniture_b200 import mjcf
+from oracle.oracle import OracleSim
+
+
+def place_parts(sim, m, dz=0.01):
+    for name in m.meta["part_names"]:
+        q = np.array(m.meta["part_init_qpos"][name], dtype=np.float64)
+        qa = m.jnt_qposadr[m.names["jnt"].index(name)]
+        sim.qpos[qa : qa + 7] = q
+        sim.qpos[qa + 2] += dz
+    nr = len(m.meta["robot_init_qpos"])
+    sim.qpos[:nr] = m.meta["robot_init_qpos"]
+    ng = len(m.meta["gripper_init_qpos"])
+    sim.qpos[nr : nr + ng] = m.meta["gripper_init_qpos"]
+
+
+def test_dimensions_match_survey(sawyer_model):
+    m = sawyer_model
+    assert (m.nq, m.nv, m.nu, m.nbody, m.neq) == (44, 39, 9, 36, 4)
+    assert int(((m.geom_contype != 0) | (m.geom_conaffinity != 0)).sum()) == 27
+    assert m.names["actuator"][7:] == ["gripper_r_gripper_r_finger_joint", "gripper_r_gripper_l_finger_joint"]
+
+
+def test_kinetic_energy_identity(sawyer_model):
+    """0.5 v^T M v (CRBA) == sum_b 0.5 m |v_com|^2 + 0.5 w^T I w (body velocities): ties M to the motion subspaces."""
+    m = sawyer_model
+    sim = OracleSim(m)
+    rng = np.random.RandomState(0)
+    place_parts(sim, m)
+    sim.qpos[:7] += rng.uniform(-0.5, 0.5, 7)
+    sim.qvel[:] = rng.normal(size=m.nv)
+    sim.stage("kinematics")
+    sim.stage("smooth")
+    M = sim.qM.reshape(m.nv, m.nv)
+    T1 = 0.5 * sim.qvel @ M @ sim.qvel
+    T2 = 0.0
+    bv = sim.bvel.reshape(-1, 6)
+    for b in range(1, m.nbody):
+        w, vO = bv[b, :3], bv[b, 3:]
+        c = sim.xipos.reshape(-1, 3)[b]
+        vc = vO + np.cross(w, c)
+        R = sim.ximat.reshape(-1, 3, 3)[b]
+        I = R @ np.diag(m.body_inertia[b]) @ R.T
+        T2 += 0.5 * m.body_mass[b] * vc @ vc + 0.5 * w @ I @ w
+    assert abs(T1 - T2) < 1e-10 * max(1, abs(T2))
+    assert np.allclose(M, M.T) and np.linalg.eigvalsh(M).min() > 0
+
+
+def test_bias_is_gravity_gradient_at_rest(sawyer_model):
+    """qfrc_bias(q, v=0) == dV/dq with V = -sum m g.c  (finite differences over the 7 arm joints)."""
+    m = sawyer_model
+    sim = OracleSim(m)
+    place_parts(sim, m)
+    sim.stage("kinematics"); sim.stage("smooth")
+    bias = sim.qfrc_bias.copy()
+
+    def V():
+        sim.stage("kinematics")
+        return -sum(m.body_mass[b] * m.opt_gravity @ sim.xipos.reshape(-1, 3)[b] for b in range(m.nbody))
+
+    for j in range(7):
+        q0 = sim.qpos[j]
+        sim.qpos[j] = q0 + 1e-6; vp = V()
+        sim.qpos[j] = q0 - 1e-6; vm = V()
+        sim.qpos[j] = q0
+        assert abs((vp - vm) / 2e-6 - bias[j]) < 1e-5 * max(1, abs(bias[j])), j
+
+
+def test_energy_conservation_without_dissipation(sawyer_model):
+    """Arm swinging under gravity with damping/actuators/contacts removed: total energy drift of semi-implicit Euler
+    stays small and shrinks with the time step (checks Coriolis/centrifugal terms of the RNE)."""
+    m = sawyer_model
+    drift = []
+    for h in (0.002, 0.001):
+        mm = mjcf.Model(a=dict(m.a), names=m.names, meta=m.meta)
+        mm.a["dof_damping"] = np.zeros(m.nv)
+        mm.a["actuator_gainprm"] = np.zeros(m.nu); mm.a["actuator_biasprm"] = np.zeros((m.nu, 3))
+        mm.a["geom_contype"] = np.zeros(m.ngeom, np.int32); mm.a["geom_conaffinity"] = np.zeros(m.ngeom, np.int32)
+        mm.a["jnt_limited"] = np.zeros(m.njnt, np.int32)
+        mm.a["opt_timestep"] = h
+        sim = OracleSim(mm)
+        place_parts(sim, mm)
+        sim.qvel[:7] = [0.5, -0.3, 0.4, 0.2, -0.6, 0.3, 0.1]
+
+        def E():
+            sim.stage("kinematics"); sim.stage("smooth")
+            M = sim.qM.reshape(m.nv, m.nv)[:9, :9]
+            T = 0.5 * sim.qvel[:9] @ M @ sim.qvel[:9]
+            Vp = -sum(m.body_mass[b] * m.opt_gravity @ sim.xipos.reshape(-1, 3)[b] for b in range(1, 31))
+            return T + Vp
+
+        e0 = E()
+        sim.step(int(0.2 / h))
+        drift.append(abs(E() - e0))
+    # ~12 J move from potential to kinetic energy; the integrator is first order: drift <1% and halves with h
+    assert drift[0] < 0.15 and 0.45 < drift[1] / drift[0] < 0.55
+
+
+def test_free_fall_and_rest_on_floor():
+    m = mjcf.load_scene("None", "table_lack_0825")
+    sim = OracleSim(m)
+    place_parts(sim, m, dz=0.5)
+    z0 = sim.qpos[2::7].copy()
+    n = 50
+    sim.step(n)
+    h, g = m.opt_timestep, 9.81
+    # semi-implicit Euler with the free-joint damping b=1e-4 (floor_task.py:66) integrated implicitly:
+    # (m + h b) a = -m g - b v ;  v += h a ;  z += h v      (the 1.2 g legs feel it: b/m = 0.085 1/s)
+    b = 1e-4
+    for i, mass in enumerate(m.body_mass[1:]):
+        v, z = 0.0, z0[i]
+        for _ in range(n):
+            a = (-mass * g - b * v) / (mass + h * b)
+            v += h * a
+            z += h * v
+        assert abs(sim.qpos[7 * i + 2] - z) < 1e-9
+    sim.step(1500)
+    assert np.abs(sim.qvel).max() < 1e-3
+    # resting heights: legs lie on a 0.015 half-width side, table top on its 0.02 half-thickness; penetration ~3e-5
+    assert np.allclose(sim.qpos[2:30:7], 0.015, atol=1e-4) and abs(sim.qpos[4 * 7 + 2] - 0.02) < 1e-4
+    f = sim.efc_force
+    assert abs(f[0::3].sum() - m.body_mass.sum() * g) < 1e-6 * m.body_mass.sum() * g  # normal forces carry the weight
+    # leg resting height equals the reference XML's recorded initpos z (0.01497): same soft-contact equilibrium
+    assert abs(sim.qpos[2] - 0.01497) < 2e-5
+
+
+def test_weld_holds_relative_pose():
+    from oracle.assembly_oracle import rel_pose
+
+    m = mjcf.load_scene("None", "table_lack_0825")
+    sim = OracleSim(m)
+    place_parts(sim, m, dz=0.3)
+    e = 0  # weld 0_part0 <-> 4_part4
+    i1 = m.names["jnt"].index(m.names["body"][m.eq_obj1id[e]]); i2 = m.names["jnt"].index(m.names["body"][m.eq_obj2id[e]])
+    q1 = sim.qpos[7 * i1 : 7 * i1 + 7].copy(); q2 = sim.qpos[7 * i2 : 7 * i2 + 7].copy()
+    rel0 = rel_pose(q1, q2)
+    sim.eq_data[7 * e : 7 * e + 7] = rel0  # furniture.py:2772
+    sim.eq_active[e] = 1
+    sim.qvel[6 * i1 : 6 * i1 + 6] = [0.3, -0.2, 0.0, 1.0, 2.0, -1.5]  # kick one part; the pair must move rigidly
+    sim.step(400)
+    rel = rel_pose(sim.qpos[7 * i1 : 7 * i1 + 7], sim.qpos[7 * i2 : 7 * i2 + 7])
+    assert np.abs(rel[:3] - rel0[:3]).max() < 2e-3
+    assert min(np.abs(rel[3:] - rel0[3:]).max(), np.abs(rel[3:] + rel0[3:]).max()) < 5e-3
+
+
+def test_solver_kkt_residual(sawyer_model):
+    """At the Newton solution: M qacc - qfrc_smooth - J^T f == 0 with f the constraint forces of the returned qacc."""
+    m = sawyer_model
+    sim = OracleSim(m)
+    place_parts(sim, m, dz=-0.002)  # slight penetration: active contacts with sliding
+    sim.qvel[9:] = np.random.RandomState(1).normal(size=30) * 0.3
+    sim.forward()
+    assert sim.nefc > 30
+    M = sim.qM.reshape(m.nv, m.nv)
+    J = sim.efc_J.reshape(sim.nefc, m.nv)
+    res = M @ sim.qacc - sim.qfrc_smooth - J.T @ sim.efc_force
+    assert np.abs(res).max() < 1e-6 * max(1.0, np.abs(sim.qfrc_smooth).max())
+    # friction cone: |f_t| <= mu_phys * f_n for every contact (elliptic cone, condim 3)
+    for c in sim.contacts():
+        a = c.efc_address
+        fn, ft = sim.efc_force[a], np.hypot(sim.efc_force[a + 1], sim.efc_force[a + 2])
+        assert fn >= -1e-9 and ft <= c.friction[0] * fn + 1e-7
+
+
+@pytest.mark.parametrize("pair", ["sphere_box", "cyl_box", "box_box_face", "box_box_edge"])
+def test_narrowphase_geometry(pair):
+    """Hand-checkable narrow-phase cases through om_collide_pair on a two-geom model."""
+    xml = """<mujoco><worldbody>
+      <body name="a" pos="0 0 0"><joint type="free"/><geom name="ga" type="%s" size="%s"/></body>
+      <body name="b" pos="0 0 1"><joint type="free"/><geom name="gb" type="%s" size="%s"/></body>
+    </worldbody></mujoco>"""
+    cfg = {
+        "sphere_box": ("sphere", "0.1", "box", "0.2 0.2 0.2", [0, 0, 0.28], [1, 0, 0, 0], -0.02, [0, 0, -1]),
+        "cyl_box": ("cylinder", "0.1 0.3", "box", "0.2 0.2 0.2", [0, 0, 0.48], [1, 0, 0, 0], -0.02, [0, 0, -1]),
+        "box_box_face": ("box", "0.1 0.1 0.1", "box", "0.2 0.2 0.2", [0, 0, 0.29], [1, 0, 0, 0], -0.01, [0, 0, -1]),
+        "box_box_edge": ("box", "0.1 0.1 0.1", "box", "0.1 0.1 0.1", None, None, None, None),
+    }[pair]
+    m = mjcf.compile_mjcf(xml % cfg[:4])
+    sim = OracleSim(m)
+    if pair == "box_box_edge":
+        # b rotated 45deg about x then 45deg about y-ish so that an edge of b meets an edge of a
+        sim.qpos[7:10] = [0.0, 0.0, 0.0]
+        qa = mjcf.q_axis_angle([0, 0, 1], np.pi / 4)
+        sim.qpos[3:7] = qa  # a: edge along z faces +x
+        qb = mjcf.q_mul(mjcf.q_axis_angle([1, 0, 0], np.pi / 2), mjcf.q_axis_angle([0, 0, 1], np.pi / 4))
+        sim.qpos[10:14] = qb  # b: edge along y faces -x
+        sim.qpos[7:10] = [2 * 0.1 * np.sqrt(2) - 0.01, 0, 0]
+        sim.stage("kinematics")
+        cs = sim.collide_pair(0, 1)
+        assert len(cs) == 1 and abs(cs[0].dist + 0.01) < 1e-9
+        assert np.allclose(list(cs[0].frame)[:3], [1, 0, 0], atol=1e-9)
+        assert np.allclose(list(cs[0].pos), [0.1 * np.sqrt(2) - 0.005, 0, 0], atol=1e-9)
+        return
+    sim.qpos[7:10] = cfg[4]
+    sim.qpos[10:14] = cfg[5]
+    sim.stage("kinematics")
+    cs = sim.collide_pair(0, 1)
+    assert len(cs) >= 1
+    for c in cs:
+        assert abs(c.dist - cfg[6]) < 2e-6, (c.dist, cfg[6])
+    g1 = cs[0].geom1
+    nrm = np.array(list(cs[0].frame)[:3])
+    # normal points from geom1 to geom2; geom1 is the lower-type geom (sphere/cylinder first) else 'a'
+    expect = np.array([0, 0, 1.0]) if g1 == 0 else np.array([0, 0, -1.0])
+    assert np.allclose(nrm, expect, atol=1e-5), nrm
+    if pair == "box_box_face":
+        assert len(cs) == 4
