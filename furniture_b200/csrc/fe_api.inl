@@ -1,0 +1,234 @@
+// fe_api.inl -- host side of the C-ABI (include/furniture_b200.h), shared by the CUDA library (fe_cuda.cu) and the
+// lane-emulated test build (tests/emu/fe_emu.cpp).  The including file provides the plat_* functions.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/furniture_b200.h"
+#include "fe_env.h"
+
+struct FeField {
+  std::string name;
+  void* ptr;
+  int dim, elem;
+  bool writable;
+};
+
+struct fe_handle {
+  int N = 0, device = 0;
+  fe_config cfg;
+  FeOpt opt;
+  fe_model hm;
+  fe_scene hs;
+  fe_model* dm = nullptr;
+  fe_scene* ds = nullptr;
+  FeState st;
+  FeDebug dbg;
+  FeEnvState es;
+  int slice_words = 0;
+  std::vector<FeField> fields;
+  std::vector<void*> allocs;
+  std::string err;
+  // staging for fe_env_step_host
+  void *pin_act = nullptr, *pin_out = nullptr, *dev_act = nullptr, *dev_rew = nullptr, *dev_done = nullptr, *dev_info = nullptr;
+  void* plat = nullptr;
+};
+
+static std::string g_create_err;
+
+template <typename T>
+static T* h_alloc(fe_handle* h, size_t count) {
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  void* p = plat_alloc(bytes);
+  if (!p) return nullptr;
+  plat_memset0(p, bytes);
+  h->allocs.push_back(p);
+  return (T*)p;
+}
+static void add_field(fe_handle* h, const char* name, void* ptr, int dim, int elem, bool writable) { h->fields.push_back({name, ptr, dim, elem, writable}); }
+static FeField* find_field(fe_handle* h, const char* name) {
+  for (auto& f : h->fields)
+    if (f.name == name) return &f;
+  return nullptr;
+}
+static int fail(fe_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+extern "C" {
+
+size_t fe_model_sizeof(void) { return sizeof(fe_model); }
+size_t fe_scene_sizeof(void) { return sizeof(fe_scene); }
+size_t fe_config_sizeof(void) { return sizeof(fe_config); }
+int fe_is_cuda(void) { return PLAT_IS_CUDA; }
+
+const char* fe_last_error(const fe_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int fe_num_envs(const fe_handle* h) { return h->N; }
+int fe_obs_dim(const fe_handle* h) { return h->hs.obs_dim; }
+int fe_action_dim(const fe_handle* h) { return h->hs.act_dim; }
+int fe_info_dim(const fe_handle* h) { return FE_INFO_DIM; }
+const float* fe_obs_dev(const fe_handle* h) { return h->es.obs; }
+
+int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob, size_t scene_bytes, const fe_config* cfg, int n_envs, int device,
+              fe_handle** out) {
+  if (!model_blob || model_bytes != sizeof(fe_model)) return fail(nullptr, -1, "fe_create: model blob size mismatch (host/lib layout differ)");
+  if (!cfg || cfg->struct_bytes != (int32_t)sizeof(fe_config)) return fail(nullptr, -1, "fe_create: fe_config size mismatch");
+  if (n_envs <= 0) return fail(nullptr, -1, "fe_create: n_envs must be positive");
+  fe_handle* h = new fe_handle();
+  memcpy(&h->hm, model_blob, sizeof(fe_model));
+  if (h->hm.magic != FE_MODEL_MAGIC || h->hm.struct_bytes != (int32_t)sizeof(fe_model)) { delete h; return fail(nullptr, -1, "fe_create: bad model magic"); }
+  memset(&h->hs, 0, sizeof(fe_scene));
+  if (scene_blob) {
+    if (scene_bytes != sizeof(fe_scene)) { delete h; return fail(nullptr, -1, "fe_create: scene blob size mismatch"); }
+    memcpy(&h->hs, scene_blob, sizeof(fe_scene));
+    if (h->hs.magic != FE_SCENE_MAGIC) { delete h; return fail(nullptr, -1, "fe_create: bad scene magic"); }
+  }
+  h->N = n_envs; h->device = device; h->cfg = *cfg;
+  h->opt.maxcon = cfg->maxcon > 0 ? cfg->maxcon : 48;
+  h->opt.newton_iters = cfg->newton_iters > 0 ? cfg->newton_iters : 8;
+  h->opt.ls_iters = cfg->ls_iters > 0 ? cfg->ls_iters : 12;
+  h->opt.tolerance = cfg->tolerance > 0 ? cfg->tolerance : 1e-6f;
+  if (h->opt.maxcon > 255) { delete h; return fail(nullptr, -1, "fe_create: maxcon must be <= 255"); }
+  if (h->hm.ngeom > 255) { delete h; return fail(nullptr, -1, "fe_create: ngeom must be <= 255"); }
+  int rc = plat_init(h);
+  if (rc) { std::string e = h->err; delete h; return fail(nullptr, rc, e); }
+  const fe_model& m = h->hm;
+  const size_t N = (size_t)n_envs;
+  h->dm = (fe_model*)plat_alloc(sizeof(fe_model));
+  h->ds = (fe_scene*)plat_alloc(sizeof(fe_scene));
+  if (!h->dm || !h->ds) { fe_destroy(h); return fail(nullptr, -2, "fe_create: device allocation failed"); }
+  h->allocs.push_back(h->dm); h->allocs.push_back(h->ds);
+  plat_upload(h->dm, &h->hm, sizeof(fe_model));
+  plat_upload(h->ds, &h->hs, sizeof(fe_scene));
+  FeWarp tmp;
+  h->slice_words = fe_warp_bind(&tmp, nullptr, &h->hm, h->opt);
+  h->slice_words = (h->slice_words + 31) & ~31;
+  FeState& s = h->st;
+  s.N = n_envs;
+  const int mc = h->opt.maxcon;
+#define ALLOC(dst, T, dim, nm, wr) dst = h_alloc<T>(h, N * (size_t)(dim)); if (!dst) { fe_destroy(h); return fail(nullptr, -2, "fe_create: device allocation failed"); } \
+  if (nm) add_field(h, nm, dst, (dim), (int)sizeof(T), wr);
+  ALLOC(s.qpos, float, m.nq, "qpos", true) ALLOC(s.qvel, float, m.nv, "qvel", true) ALLOC(s.warm, float, m.nv, "qacc_warmstart", true)
+  ALLOC(s.ctrl, float, m.nu, "ctrl", true) ALLOC(s.qfrc_applied, float, m.nr, "qfrc_applied", true) ALLOC(s.gravcomp, float, m.npart, "gravcomp", true)
+  ALLOC(s.eq_data, float, 7 * m.neq, "eq_data", true) ALLOC(s.contype, int, m.ngeom, "geom_contype", true) ALLOC(s.conaff, int, m.ngeom, "geom_conaffinity", true)
+  ALLOC(s.eq_active, int, m.neq, "eq_active", true) ALLOC(s.bias, float, m.nr, "qfrc_bias", false)
+  ALLOC(s.lpos, float, 3 * m.nlink, "link_xpos", false) ALLOC(s.lquat, float, 4 * m.nlink, "link_xquat", false) ALLOC(s.lvel, float, 6 * m.nlink, "link_vel", false)
+  ALLOC(s.touch, int, m.npart, "touch", false) ALLOC(s.flags, int, 1, "flags", true) ALLOC(s.ncon, int, 1, "ncon", false) ALLOC(s.niter, int, 1, "niter", false)
+  FeDebug& d = h->dbg;
+  ALLOC(d.Mr, float, m.nr * m.nr, "dbg_Mr", false) ALLOC(d.fs, float, m.nv, "dbg_fs", false) ALLOC(d.as, float, m.nv, "dbg_as", false)
+  ALLOC(d.linert, float, 10 * m.nlink, "dbg_linert", false) ALLOC(d.x, float, m.nv, "dbg_x", false) ALLOC(d.fc, float, m.nv, "dbg_fc", false)
+  ALLOC(d.lmat, float, 9 * m.nlink, "link_xmat", false) ALLOC(d.S, float, 6 * m.nr, "dbg_S", false)
+  ALLOC(d.c_dist, float, mc, "con_dist", false) ALLOC(d.c_pos, float, 3 * mc, "con_pos", false) ALLOC(d.c_frame, float, 9 * mc, "con_frame", false)
+  ALLOC(d.c_aref, float, 3 * mc, "con_aref", false) ALLOC(d.c_D, float, 2 * mc, "con_D", false) ALLOC(d.c_f, float, 3 * mc, "con_force", false)
+  ALLOC(d.c_geom, int, mc, "con_geom", false) ALLOC(d.c_state, int, mc, "con_state", false)
+  FeEnvState& e = h->es;
+  const int nsite = m.nsite > 0 ? m.nsite : 1;
+  ALLOC(e.obs, float, h->hs.obs_dim > 0 ? h->hs.obs_dim : 1, "obs", false) ALLOC(e.group, int, m.npart, "group", true) ALLOC(e.site_connected, int, nsite, "site_connected", true)
+  ALLOC(e.num_connected, int, 1, "num_connected", true) ALLOC(e.prev_num_connected, int, 1, "prev_num_connected", true)
+  ALLOC(e.touched, int, m.npart, "touched", true) ALLOC(e.picked, int, m.npart, "picked", true) ALLOC(e.episode_len, int, 1, "episode_length", true)
+  ALLOC(e.rng, unsigned long long, 1, "rng", true) ALLOC(e.done, int, 1, "done", false) ALLOC(e.robot_contype, int, m.ngeom, nullptr, false)
+  ALLOC(e.robot_conaff, int, m.ngeom, nullptr, false) ALLOC(e.episode_reward, float, 1, "episode_reward", false)
+#undef ALLOC
+  // initial per-env model state: MjSim.reset() semantics (qpos = qpos0 of the XML, masks / welds from the model)
+  {
+    std::vector<int> ct(N * m.ngeom), ca(N * m.ngeom), ea(N * (m.neq > 0 ? m.neq : 1));
+    std::vector<float> ed(N * 7 * (m.neq > 0 ? m.neq : 1));
+    for (size_t n = 0; n < N; ++n) {
+      for (int g = 0; g < m.ngeom; ++g) { ct[n * m.ngeom + g] = m.geom_contype0[g]; ca[n * m.ngeom + g] = m.geom_conaffinity0[g]; }
+      for (int q = 0; q < m.neq; ++q) { ea[n * m.neq + q] = m.eq_active0[q]; for (int k = 0; k < 7; ++k) ed[(n * m.neq + q) * 7 + k] = m.eq_data0[q][k]; }
+    }
+    plat_upload(s.contype, ct.data(), sizeof(int) * N * m.ngeom);
+    plat_upload(s.conaff, ca.data(), sizeof(int) * N * m.ngeom);
+    if (m.neq) { plat_upload(s.eq_active, ea.data(), sizeof(int) * N * m.neq); plat_upload(s.eq_data, ed.data(), sizeof(float) * N * 7 * m.neq); }
+    std::vector<unsigned long long> rng(N);
+    for (size_t n = 0; n < N; ++n) rng[n] = cfg->seed + n;
+    plat_upload(e.rng, rng.data(), sizeof(unsigned long long) * N);
+  }
+  h->dev_act = h_alloc<float>(h, N * (size_t)(h->hs.act_dim > 0 ? h->hs.act_dim : 1));
+  h->dev_rew = h_alloc<float>(h, N);
+  h->dev_done = h_alloc<uint8_t>(h, N);
+  h->dev_info = h_alloc<int32_t>(h, N * FE_INFO_DIM);
+  *out = h;
+  return 0;
+}
+
+void fe_destroy(fe_handle* h) {
+  if (!h) return;
+  plat_fini(h);
+  for (void* p : h->allocs) plat_free(p);
+  delete h;
+}
+
+int fe_field_dim(fe_handle* h, const char* name, int* dim, int* elem_bytes) {
+  FeField* f = find_field(h, name);
+  if (!f) return fail(h, -3, std::string("unknown field ") + name);
+  if (dim) *dim = f->dim;
+  if (elem_bytes) *elem_bytes = f->elem;
+  return 0;
+}
+int fe_get_field(fe_handle* h, const char* name, void* dst, size_t bytes) {
+  FeField* f = find_field(h, name);
+  if (!f) return fail(h, -3, std::string("unknown field ") + name);
+  size_t want = (size_t)h->N * f->dim * f->elem;
+  if (bytes != want) return fail(h, -4, std::string("size mismatch for field ") + name);
+  plat_sync(h);
+  plat_download(dst, f->ptr, bytes);
+  return 0;
+}
+int fe_set_field(fe_handle* h, const char* name, const void* src, size_t bytes) {
+  FeField* f = find_field(h, name);
+  if (!f) return fail(h, -3, std::string("unknown field ") + name);
+  if (!f->writable) return fail(h, -5, std::string("field is read-only: ") + name);
+  size_t want = (size_t)h->N * f->dim * f->elem;
+  if (bytes != want) return fail(h, -4, std::string("size mismatch for field ") + name);
+  plat_sync(h);
+  plat_upload(f->ptr, src, bytes);
+  return 0;
+}
+int fe_get_state(fe_handle* h, float* qpos, float* qvel) {
+  int rc = fe_get_field(h, "qpos", qpos, sizeof(float) * h->N * h->hm.nq);
+  return rc ? rc : fe_get_field(h, "qvel", qvel, sizeof(float) * h->N * h->hm.nv);
+}
+int fe_set_state(fe_handle* h, const float* qpos, const float* qvel) {
+  int rc = fe_set_field(h, "qpos", qpos, sizeof(float) * h->N * h->hm.nq);
+  return rc ? rc : fe_set_field(h, "qvel", qvel, sizeof(float) * h->N * h->hm.nv);
+}
+
+int fe_sim_forward(fe_handle* h, void* stream) { return plat_run_sim(h, 1, 1, stream); }
+int fe_sim_step(fe_handle* h, int nsub, void* stream) {
+  if (nsub <= 0) return fail(h, -1, "fe_sim_step: nsub must be positive");
+  return plat_run_sim(h, nsub, 0, stream);
+}
+
+int fe_env_reset(fe_handle* h, const uint8_t* env_mask_dev, float* obs_dev, void* stream) {
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_env_reset: handle was created without a scene blob");
+  int rc = plat_run_reset(h, env_mask_dev, stream);
+  if (rc) return rc;
+  if (obs_dev) plat_copy_d2d(h, obs_dev, h->es.obs, sizeof(float) * (size_t)h->N * h->hs.obs_dim, stream);
+  return 0;
+}
+int fe_env_step(fe_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, int32_t* info_dev, void* stream) {
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_env_step: handle was created without a scene blob");
+  if (!actions_dev) return fail(h, -1, "fe_env_step: actions is NULL");
+  int rc = plat_run_step(h, actions_dev, reward_dev ? reward_dev : (float*)h->dev_rew, done_dev ? done_dev : (uint8_t*)h->dev_done,
+                         info_dev ? info_dev : (int32_t*)h->dev_info, stream);
+  if (rc) return rc;
+  if (obs_dev) plat_copy_d2d(h, obs_dev, h->es.obs, sizeof(float) * (size_t)h->N * h->hs.obs_dim, stream);
+  return 0;
+}
+int fe_env_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_env_step_host: handle was created without a scene blob");
+  return plat_step_host(h, actions, obs, reward, done, info);
+}
+
+int fe_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles, const int32_t* nangles,
+                  const double* thr, uint8_t* aligned, double* tq) {
+  if (n <= 0) return 0;
+  return plat_is_aligned(h, n, p1, m1, p2, m2, angles, nangles, thr, aligned, tq);
+}
+
+} // extern "C"

@@ -1,0 +1,412 @@
+// fe_collide.h -- narrow-phase primitives (fp32, one lane per candidate pair).
+//
+// Geometry definitions follow MuJoCo's mj_collision for the pair types the furniture scenes contain:
+// analytic plane-{sphere,cylinder,box}, sphere-sphere, sphere-box; Minkowski-portal-refinement (the libccd algorithm
+// MuJoCo 2.0 calls for cylinder pairs) for sphere/cylinder/box vs cylinder; box-box by SAT + reference-face clipping.
+// Contact convention: normal points from geom1 to geom2, dist < 0 is penetration, pos lies mid-way between surfaces.
+#pragma once
+#include "fe_warp.h"
+
+struct FeCon {
+  float dist, pos[3], n[3];
+};
+
+FE_HD void fe_col(float* r, const float* R, int k) { r[0] = R[k]; r[1] = R[3 + k]; r[2] = R[6 + k]; }
+
+FE_HD int fe_plane_sphere(const float* pp, const float* pR, const float* c, float r, FeCon* out) {
+  float n[3], t[3];
+  fe_col(n, pR, 2);
+  v3sub(t, c, pp);
+  float dist = v3dot(t, n) - r;
+  if (dist >= 0.f) return 0;
+  out->dist = dist;
+  v3madd(out->pos, c, n, -(r + 0.5f * dist));
+  v3cpy(out->n, n);
+  return 1;
+}
+
+FE_HD int fe_plane_box(const float* pp, const float* pR, const float* c, const float* R, const float* s, FeCon* out) {
+  float n[3];
+  fe_col(n, pR, 2);
+  int cnt = 0;
+  for (int i = 0; i < 8 && cnt < 4; ++i) {
+    float lx = (i & 1) ? s[0] : -s[0], ly = (i & 2) ? s[1] : -s[1], lz = (i & 4) ? s[2] : -s[2];
+    float corner[3] = {c[0] + R[0] * lx + R[1] * ly + R[2] * lz, c[1] + R[3] * lx + R[4] * ly + R[5] * lz, c[2] + R[6] * lx + R[7] * ly + R[8] * lz};
+    float t[3];
+    v3sub(t, corner, pp);
+    float dist = v3dot(t, n);
+    if (dist >= 0.f) continue;
+    out[cnt].dist = dist;
+    v3madd(out[cnt].pos, corner, n, -0.5f * dist);
+    v3cpy(out[cnt].n, n);
+    ++cnt;
+  }
+  return cnt;
+}
+
+FE_HD int fe_plane_cylinder(const float* pp, const float* pR, const float* c, const float* R, float r, float h, FeCon* out) {
+  float n[3], ax[3], vec[3], p[3], t[3];
+  fe_col(n, pR, 2);
+  fe_col(ax, R, 2);
+  float prj = v3dot(n, ax);
+  if (prj > 0.f) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; prj = -prj; }
+  for (int k = 0; k < 3; ++k) vec[k] = -n[k] + ax[k] * prj;
+  float len = v3norm(vec);
+  if (len < 1e-6f) { fe_col(vec, R, 0); for (int k = 0; k < 3; ++k) vec[k] *= r; }
+  else { float s = r / len; for (int k = 0; k < 3; ++k) vec[k] *= s; }
+  for (int k = 0; k < 3; ++k) p[k] = c[k] + ax[k] * h + vec[k];
+  v3sub(t, p, pp);
+  float dist = v3dot(t, n);
+  if (dist >= 0.f) return 0;
+  int cnt = 0;
+  out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt;
+  for (int k = 0; k < 3; ++k) p[k] = c[k] - ax[k] * h + vec[k];
+  v3sub(t, p, pp);
+  dist = v3dot(t, n);
+  if (dist < 0.f) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
+  float w[3];
+  v3cross(w, vec, ax);
+  for (int sg = -1; sg <= 1; sg += 2) {
+    for (int k = 0; k < 3; ++k) p[k] = c[k] + ax[k] * h - 0.5f * vec[k] + (float)sg * 0.8660254037844386f * w[k];
+    v3sub(t, p, pp);
+    dist = v3dot(t, n);
+    if (dist < 0.f) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
+  }
+  return cnt;
+}
+
+FE_HD int fe_sphere_sphere(const float* c1, float r1, const float* c2, float r2, FeCon* out) {
+  float n[3];
+  v3sub(n, c2, c1);
+  float d = v3norm(n), dist = d - r1 - r2;
+  if (dist >= 0.f) return 0;
+  if (d < 1e-20f) { n[0] = 1.f; n[1] = n[2] = 0.f; } else { float s = 1.f / d; n[0] *= s; n[1] *= s; n[2] *= s; }
+  out->dist = dist;
+  v3madd(out->pos, c1, n, r1 + 0.5f * dist);
+  v3cpy(out->n, n);
+  return 1;
+}
+
+FE_HD int fe_sphere_box(const float* c, float r, const float* bc, const float* R, const float* s, FeCon* out) {
+  float t[3], loc[3], cl[3], n[3];
+  v3sub(t, c, bc);
+  m3tmulv(loc, R, t);
+  bool inside = true;
+  for (int k = 0; k < 3; ++k) {
+    cl[k] = fminf(fmaxf(loc[k], -s[k]), s[k]);
+    if (cl[k] != loc[k]) inside = false;
+  }
+  float dist;
+  if (!inside) {
+    float dl[3] = {cl[0] - loc[0], cl[1] - loc[1], cl[2] - loc[2]};
+    float d = v3norm(dl);
+    dist = d - r;
+    if (dist >= 0.f) return 0;
+    m3mulv(n, R, dl);
+    float inv = 1.f / d;
+    n[0] *= inv; n[1] *= inv; n[2] *= inv;
+  } else {
+    int best = 0;
+    float bd = 1e30f;
+    for (int k = 0; k < 3; ++k) { float dd = s[k] - fabsf(loc[k]); if (dd < bd) { bd = dd; best = k; } }
+    float sg = loc[best] >= 0.f ? 1.f : -1.f;
+    for (int k = 0; k < 3; ++k) n[k] = -sg * R[3 * k + best];
+    dist = -bd - r;
+  }
+  out->dist = dist;
+  v3madd(out->pos, c, n, r + 0.5f * dist);
+  v3cpy(out->n, n);
+  return 1;
+}
+
+// ---- box-box
+FE_HD int fe_clip(float (*poly)[3], int n, const float* cR, const float* ax, float lim, float sgn) {
+  float o[12][3];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* P = poly[i];
+    const float* Q = poly[(i + 1 == n) ? 0 : i + 1];
+    float t[3];
+    v3sub(t, P, cR);
+    float dp = sgn * v3dot(t, ax) - lim;
+    v3sub(t, Q, cR);
+    float dq = sgn * v3dot(t, ax) - lim;
+    if (dp <= 0.f && m < 12) { v3cpy(o[m], P); ++m; }
+    if ((dp <= 0.f) != (dq <= 0.f) && m < 12) {
+      float u = dp / (dp - dq);
+      for (int k = 0; k < 3; ++k) o[m][k] = P[k] + u * (Q[k] - P[k]);
+      ++m;
+    }
+  }
+  for (int i = 0; i < m; ++i) v3cpy(poly[i], o[i]);
+  return m;
+}
+
+FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const float* cB, const float* RB, const float* b, FeCon* out) {
+  float A[3][3], B[3][3], d[3], Cm[3][3], AC[3][3], dA[3], dB[3];
+  for (int k = 0; k < 3; ++k) { fe_col(A[k], RA, k); fe_col(B[k], RB, k); }
+  v3sub(d, cB, cA);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { Cm[i][j] = v3dot(A[i], B[j]); AC[i][j] = fabsf(Cm[i][j]); }
+  for (int i = 0; i < 3; ++i) { dA[i] = v3dot(d, A[i]); dB[i] = v3dot(d, B[i]); }
+  float best_face = -1e30f;
+  int face = -1;
+  for (int i = 0; i < 3; ++i) {
+    float sep = fabsf(dA[i]) - (a[i] + b[0] * AC[i][0] + b[1] * AC[i][1] + b[2] * AC[i][2]);
+    if (sep > 0.f) return 0;
+    if (sep > best_face) { best_face = sep; face = i; }
+  }
+  for (int j = 0; j < 3; ++j) {
+    float sep = fabsf(dB[j]) - (b[j] + a[0] * AC[0][j] + a[1] * AC[1][j] + a[2] * AC[2][j]);
+    if (sep > 0.f) return 0;
+    if (sep > best_face) { best_face = sep; face = 3 + j; }
+  }
+  float best_edge = -1e30f;
+  int ei = -1, ej = -1;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float l2 = 1.f - Cm[i][j] * Cm[i][j];
+      if (l2 < 1e-6f) continue;
+      float l = sqrtf(l2);
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      float dl = dA[i2] * Cm[i1][j] - dA[i1] * Cm[i2][j];
+      float ra = a[i1] * AC[i2][j] + a[i2] * AC[i1][j];
+      float rb = b[j1] * AC[i][j2] + b[j2] * AC[i][j1];
+      float sep = (fabsf(dl) - ra - rb) / l;
+      if (sep > 0.f) return 0;
+      if (sep > best_edge) { best_edge = sep; ei = i; ej = j; }
+    }
+  if (ei >= 0 && -best_edge < 0.95f * (-best_face) - 1e-5f) {
+    float L[3], pa[3], pb[3];
+    v3cross(L, A[ei], B[ej]);
+    v3normalize(L);
+    if (v3dot(L, d) < 0.f) { L[0] = -L[0]; L[1] = -L[1]; L[2] = -L[2]; }
+    v3cpy(pa, cA); v3cpy(pb, cB);
+    for (int k = 0; k < 3; ++k) {
+      if (k != ei) { float sg = v3dot(L, A[k]) > 0.f ? 1.f : -1.f; v3madd(pa, pa, A[k], sg * a[k]); }
+      if (k != ej) { float sg = v3dot(L, B[k]) > 0.f ? -1.f : 1.f; v3madd(pb, pb, B[k], sg * b[k]); }
+    }
+    float w[3];
+    v3sub(w, pa, pb);
+    float uv = Cm[ei][ej], uw = v3dot(A[ei], w), vw = v3dot(B[ej], w);
+    float den = 1.f - uv * uv;
+    float s = (uv * vw - uw) / den, t = (vw - uv * uw) / den;
+    float qa[3], qb[3];
+    v3madd(qa, pa, A[ei], s);
+    v3madd(qb, pb, B[ej], t);
+    out->dist = best_edge;
+    for (int k = 0; k < 3; ++k) out->pos[k] = 0.5f * (qa[k] + qb[k]);
+    v3cpy(out->n, L);
+    return 1;
+  }
+  const float *cR, *cI, *hR, *hI;
+  float(*Rax)[3];
+  float(*Iax)[3];
+  float nref[3];
+  int ri;
+  bool refIsA = face < 3;
+  if (refIsA) { ri = face; cR = cA; cI = cB; hR = a; hI = b; Rax = A; Iax = B; float sg = dA[ri] >= 0.f ? 1.f : -1.f; for (int k = 0; k < 3; ++k) nref[k] = sg * A[ri][k]; }
+  else { ri = face - 3; cR = cB; cI = cA; hR = b; hI = a; Rax = B; Iax = A; float sg = dB[ri] >= 0.f ? -1.f : 1.f; for (int k = 0; k < 3; ++k) nref[k] = sg * B[ri][k]; }
+  int ik = 0;
+  float bestd = -1.f;
+  for (int k = 0; k < 3; ++k) { float v = fabsf(v3dot(Iax[k], nref)); if (v > bestd) { bestd = v; ik = k; } }
+  float sgI = v3dot(Iax[ik], nref) > 0.f ? -1.f : 1.f;
+  int iu = (ik + 1) % 3, iv = (ik + 2) % 3;
+  float fc[3], poly[12][3];
+  v3madd(fc, cI, Iax[ik], sgI * hI[ik]);
+  const float su[4] = {1.f, -1.f, -1.f, 1.f}, sv[4] = {1.f, 1.f, -1.f, -1.f};
+  for (int q = 0; q < 4; ++q)
+    for (int k = 0; k < 3; ++k) poly[q][k] = fc[k] + su[q] * hI[iu] * Iax[iu][k] + sv[q] * hI[iv] * Iax[iv][k];
+  int np = 4, ru = (ri + 1) % 3, rv = (ri + 2) % 3;
+  np = fe_clip(poly, np, cR, Rax[ru], hR[ru], 1.f);
+  if (np) np = fe_clip(poly, np, cR, Rax[ru], hR[ru], -1.f);
+  if (np) np = fe_clip(poly, np, cR, Rax[rv], hR[rv], 1.f);
+  if (np) np = fe_clip(poly, np, cR, Rax[rv], hR[rv], -1.f);
+  int cnt = 0;
+  for (int q = 0; q < np && cnt < 8; ++q) {
+    float t[3];
+    v3sub(t, poly[q], cR);
+    float depth = hR[ri] - v3dot(t, nref);
+    if (depth <= 0.f) continue;
+    out[cnt].dist = -depth;
+    v3madd(out[cnt].pos, poly[q], nref, 0.5f * depth);
+    for (int k = 0; k < 3; ++k) out[cnt].n[k] = refIsA ? nref[k] : -nref[k];
+    ++cnt;
+  }
+  return cnt;
+}
+
+// ---- Minkowski portal refinement on (g1 - g2), v0 = c1 - c2; direction returned points from g1 to g2
+struct FeCvx {
+  int type;
+  const float *pos, *mat, *size;
+};
+FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
+  float l[3], p[3];
+  m3tmulv(l, g.mat, dir);
+  if (g.type == 2) {
+    float n = v3norm(l);
+    float s = n > 1e-20f ? g.size[0] / n : 0.f;
+    p[0] = l[0] * s; p[1] = l[1] * s; p[2] = l[2] * s;
+  } else if (g.type == 6) {
+    p[0] = l[0] >= 0.f ? g.size[0] : -g.size[0];
+    p[1] = l[1] >= 0.f ? g.size[1] : -g.size[1];
+    p[2] = l[2] >= 0.f ? g.size[2] : -g.size[2];
+  } else {
+    float n = sqrtf(l[0] * l[0] + l[1] * l[1]);
+    float s = n > 1e-20f ? g.size[0] / n : 0.f;
+    p[0] = l[0] * s; p[1] = l[1] * s;
+    p[2] = l[2] >= 0.f ? g.size[1] : -g.size[1];
+  }
+  m3mulv(out, g.mat, p);
+  v3add(out, out, g.pos);
+}
+struct FeSup {
+  float v[3], v1[3], v2[3];
+};
+FE_HD void fe_mink(const FeCvx& g1, const FeCvx& g2, const float* dir, FeSup* s) {
+  float nd[3] = {-dir[0], -dir[1], -dir[2]};
+  fe_support(g1, dir, s->v1);
+  fe_support(g2, nd, s->v2);
+  v3sub(s->v, s->v1, s->v2);
+}
+FE_HD float fe_origin_tri(const float* a, const float* b, const float* c, float* w) {
+  float ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]}, bp[3] = {-b[0], -b[1], -b[2]}, cp[3] = {-c[0], -c[1], -c[2]};
+  v3sub(ab, b, a); v3sub(ac, c, a);
+  float d1 = v3dot(ab, ap), d2 = v3dot(ac, ap);
+  if (d1 <= 0.f && d2 <= 0.f) { v3cpy(w, a); return v3dot(w, w); }
+  float d3 = v3dot(ab, bp), d4 = v3dot(ac, bp);
+  if (d3 >= 0.f && d4 <= d3) { v3cpy(w, b); return v3dot(w, w); }
+  float vc = d1 * d4 - d3 * d2;
+  if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { float v = d1 / (d1 - d3); v3madd(w, a, ab, v); return v3dot(w, w); }
+  float d5 = v3dot(ab, cp), d6 = v3dot(ac, cp);
+  if (d6 >= 0.f && d5 <= d6) { v3cpy(w, c); return v3dot(w, w); }
+  float vb = d5 * d2 - d1 * d6;
+  if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { float v = d2 / (d2 - d6); v3madd(w, a, ac, v); return v3dot(w, w); }
+  float va = d3 * d6 - d5 * d4;
+  if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+    float v = (d4 - d3) / ((d4 - d3) + (d5 - d6)), bc[3];
+    v3sub(bc, c, b); v3madd(w, b, bc, v);
+    return v3dot(w, w);
+  }
+  float den = 1.f / (va + vb + vc), v = vb * den, u = vc * den;
+  for (int k = 0; k < 3; ++k) w[k] = a[k] + ab[k] * v + ac[k] * u;
+  return v3dot(w, w);
+}
+FE_HD void fe_portal_dir(const FeSup* p, float* dir) {
+  float e1[3], e2[3];
+  v3sub(e1, p[2].v, p[1].v); v3sub(e2, p[3].v, p[1].v);
+  v3cross(dir, e1, e2);
+  v3normalize(dir);
+}
+FE_HD void fe_expand_portal(FeSup* p, const FeSup& v4) {
+  float x[3];
+  v3cross(x, v4.v, p[0].v);
+  if (v3dot(p[1].v, x) > 0.f) { if (v3dot(p[2].v, x) > 0.f) p[1] = v4; else p[3] = v4; }
+  else { if (v3dot(p[3].v, x) > 0.f) p[2] = v4; else p[1] = v4; }
+}
+FE_HD void fe_find_pos(const FeSup* p, float* pos) {
+  float b[4], t[3];
+  v3cross(t, p[1].v, p[2].v); b[0] = v3dot(t, p[3].v);
+  v3cross(t, p[3].v, p[2].v); b[1] = v3dot(t, p[0].v);
+  v3cross(t, p[0].v, p[1].v); b[2] = v3dot(t, p[3].v);
+  v3cross(t, p[2].v, p[1].v); b[3] = v3dot(t, p[0].v);
+  float sum = b[0] + b[1] + b[2] + b[3];
+  if (sum <= 0.f) {
+    float dir[3];
+    b[0] = 0.f;
+    fe_portal_dir(p, dir);
+    v3cross(t, p[2].v, p[3].v); b[1] = v3dot(t, dir);
+    v3cross(t, p[3].v, p[1].v); b[2] = v3dot(t, dir);
+    v3cross(t, p[1].v, p[2].v); b[3] = v3dot(t, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  float inv = 0.5f / sum;
+  for (int k = 0; k < 3; ++k) {
+    float s = 0.f;
+    for (int i = 0; i < 4; ++i) s += b[i] * (p[i].v1[k] + p[i].v2[k]);
+    pos[k] = s * inv;
+  }
+}
+FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
+  const float tol = 1e-6f, eps = 1e-9f;
+  FeSup p[4], v4;
+  float dir[3], va[3], vb[3];
+  v3sub(p[0].v, g1.pos, g2.pos);
+  v3cpy(p[0].v1, g1.pos); v3cpy(p[0].v2, g2.pos);
+  if (v3norm(p[0].v) < 1e-7f) p[0].v[0] = 1e-5f;
+  dir[0] = -p[0].v[0]; dir[1] = -p[0].v[1]; dir[2] = -p[0].v[2];
+  v3normalize(dir);
+  fe_mink(g1, g2, dir, &p[1]);
+  if (v3dot(p[1].v, dir) <= 0.f) return 0;
+  v3cross(dir, p[0].v, p[1].v);
+  if (v3dot(dir, dir) < eps * eps) {
+    v3cpy(out->n, p[1].v);
+    float depth = v3normalize(out->n);
+    if (!(depth > 0.f)) return 0;
+    out->dist = -depth;
+    for (int k = 0; k < 3; ++k) out->pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]);
+    return 1;
+  }
+  v3normalize(dir);
+  fe_mink(g1, g2, dir, &p[2]);
+  if (v3dot(p[2].v, dir) <= 0.f) return 0;
+  v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v);
+  v3cross(dir, va, vb);
+  v3normalize(dir);
+  if (v3dot(dir, p[0].v) > 0.f) { FeSup t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+  for (int it = 0;; ++it) {
+    if (it > 100) return 0;
+    fe_mink(g1, g2, dir, &p[3]);
+    if (v3dot(p[3].v, dir) <= 0.f) return 0;
+    bool cont = false;
+    v3cross(va, p[1].v, p[3].v);
+    if (v3dot(va, p[0].v) < -eps) { p[2] = p[3]; cont = true; }
+    if (!cont) { v3cross(va, p[3].v, p[2].v); if (v3dot(va, p[0].v) < -eps) { p[1] = p[3]; cont = true; } }
+    if (!cont) break;
+    v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v);
+    v3cross(dir, va, vb);
+    v3normalize(dir);
+  }
+  for (int it = 0;; ++it) {
+    fe_portal_dir(p, dir);
+    if (v3dot(p[1].v, dir) >= 0.f) break;
+    fe_mink(g1, g2, dir, &v4);
+    float dv4 = v3dot(v4.v, dir);
+    float mn = fminf(fminf(dv4 - v3dot(p[1].v, dir), dv4 - v3dot(p[2].v, dir)), dv4 - v3dot(p[3].v, dir));
+    if (dv4 < 0.f || mn <= tol || it > 50) return 0;
+    fe_expand_portal(p, v4);
+  }
+  for (int it = 0;; ++it) {
+    fe_portal_dir(p, dir);
+    fe_mink(g1, g2, dir, &v4);
+    float dv4 = v3dot(v4.v, dir);
+    float mn = fminf(fminf(dv4 - v3dot(p[1].v, dir), dv4 - v3dot(p[2].v, dir)), dv4 - v3dot(p[3].v, dir));
+    if (mn <= tol || it > 50) {
+      float w[3];
+      float depth = sqrtf(fe_origin_tri(p[1].v, p[2].v, p[3].v, w));
+      if (depth < 1e-9f) v3cpy(out->n, dir);
+      else { float s = 1.f / depth; out->n[0] = w[0] * s; out->n[1] = w[1] * s; out->n[2] = w[2] * s; }
+      if (!(depth > 0.f)) return 0;
+      out->dist = -depth;
+      fe_find_pos(p, out->pos);
+      return 1;
+    }
+    fe_expand_portal(p, v4);
+  }
+}
+
+// dispatch on the (ordered) type pair; geometry in world frame. Returns contact count (<= 8).
+FE_HD int fe_narrowphase(int t1, const float* p1, const float* R1, const float* s1, int t2, const float* p2, const float* R2, const float* s2, FeCon* out) {
+  if (t1 == 0) {
+    if (t2 == 2) return fe_plane_sphere(p1, R1, p2, s2[0], out);
+    if (t2 == 5) return fe_plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], out);
+    if (t2 == 6) return fe_plane_box(p1, R1, p2, R2, s2, out);
+    return 0;
+  }
+  if (t1 == 2 && t2 == 2) return fe_sphere_sphere(p1, s1[0], p2, s2[0], out);
+  if (t1 == 2 && t2 == 6) return fe_sphere_box(p1, s1[0], p2, R2, s2, out);
+  if (t1 == 6 && t2 == 6) return fe_box_box(p1, R1, s1, p2, R2, s2, out);
+  FeCvx a = {t1, p1, R1, s1}, b = {t2, p2, R2, s2};
+  return fe_mpr(a, b, out);
+}

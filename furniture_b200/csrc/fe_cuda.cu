@@ -1,0 +1,190 @@
+// fe_cuda.cu -- sm_100a kernels and the CUDA platform layer of the C-ABI (include/furniture_b200.h).
+// One block = one warp = one environment; the warp's working set lives in dynamic shared memory for the whole call
+// (all nsub mj_steps of an env step run without touching HBM except for the model tables, which stay in L1/L2).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define PLAT_IS_CUDA 1
+struct fe_handle;
+static void* plat_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr; }
+static void plat_free(void* p) { cudaFree(p); }
+static void plat_memset0(void* p, size_t n) { cudaMemset(p, 0, n); }
+static void plat_upload(void* d, const void* h, size_t n) { cudaMemcpy(d, h, n, cudaMemcpyHostToDevice); }
+static void plat_download(void* h, const void* d, size_t n) { cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost); }
+static int plat_init(fe_handle* h);
+static void plat_fini(fe_handle* h);
+static void plat_sync(fe_handle* h);
+static int plat_run_sim(fe_handle* h, int nsub, int mode, void* stream);
+static int plat_run_reset(fe_handle* h, const uint8_t* mask, void* stream);
+static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, void* stream);
+static int plat_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info);
+static void plat_copy_d2d(fe_handle* h, void* dst, const void* src, size_t n, void* stream);
+static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles,
+                           const int32_t* nangles, const double* thr, uint8_t* aligned, double* tq);
+
+#include "fe_api.inl"
+
+// ---------------------------------------------------------------- kernels
+extern __shared__ float fe_smem[];
+
+__global__ void __launch_bounds__(32) fe_sim_kernel(FeState s, const fe_model* __restrict__ m, FeOpt opt, int nsub, int mode, FeDebug dbg) {
+  const int env = blockIdx.x;
+  if (env >= s.N) return;
+  fe_run_env(s, m, opt, env, nsub, mode, fe_smem, dbg);
+}
+
+__global__ void __launch_bounds__(32) fe_env_step_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
+                                                         fe_config cfg, FeOpt opt, const float* __restrict__ actions, float* reward, uint8_t* done,
+                                                         int32_t* info, int slice_words) {
+  const int env = blockIdx.x;
+  if (env >= st.N) return;
+  FeEnv e;
+  fe_env_bind(&e, fe_smem, m, sc, &cfg, opt, st, es, env, slice_words);
+  fe_load(&e.w, st, env);
+  fe_env_load_groups(&e);
+  fe_env_step_one(&e, actions, reward, done, info);
+  fe_env_store_groups(&e);
+  fe_store(&e.w, st, env);
+}
+
+__global__ void __launch_bounds__(32) fe_env_reset_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
+                                                          fe_config cfg, FeOpt opt, const uint8_t* __restrict__ mask, int slice_words) {
+  const int env = blockIdx.x;
+  if (env >= st.N) return;
+  if (mask && !mask[env]) return;
+  FeEnv e;
+  fe_env_bind(&e, fe_smem, m, sc, &cfg, opt, st, es, env, slice_words);
+  fe_load(&e.w, st, env);
+  fe_env_load_groups(&e);
+  fe_env_reset_one(&e);
+  fe_env_store_groups(&e);
+  fe_store(&e.w, st, env);
+}
+
+__global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* cs, const double* sn,
+                                     const int32_t* nang, const double* thr, uint8_t* aligned, double* tq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double q[4] = {0, 0, 0, 0};
+  bool set = false;
+  const bool ok = fe_is_aligned_d(p1 + 3 * i, m1 + 9 * i, p2 + 3 * i, m2 + 9 * i, nang[i], cs + 4 * i, sn + 4 * i, thr + 4 * i, q, &set);
+  aligned[i] = ok ? 1 : 0;
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  for (int k = 0; k < 4; ++k) tq[4 * i + k] = set ? q[k] : nanv;
+}
+
+// ---------------------------------------------------------------- platform layer
+struct CudaPlat {
+  size_t smem_sim = 0, smem_env = 0;
+  float* pin_act = nullptr;
+  unsigned char* pin_out = nullptr;
+  size_t out_bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+#define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(h, -10, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
+
+static int plat_init(fe_handle* h) {
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return -10; }
+  h->plat = new CudaPlat();
+  return 0;
+}
+static int plat_prepare(fe_handle* h) {
+  CudaPlat* p = (CudaPlat*)h->plat;
+  if (p->smem_sim) return 0;
+  p->smem_sim = (size_t)h->slice_words * 4;
+  p->smem_env = (size_t)(h->slice_words + FE_ENV_EXTRA_WORDS) * 4;
+  CUDA_OK(cudaFuncSetAttribute(fe_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sim));
+  CUDA_OK(cudaFuncSetAttribute(fe_env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_env));
+  CUDA_OK(cudaFuncSetAttribute(fe_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_env));
+  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  const size_t N = h->N;
+  p->out_bytes = N * (sizeof(float) * h->hs.obs_dim + sizeof(float) + sizeof(int32_t) * FE_INFO_DIM + 1);
+  CUDA_OK(cudaMallocHost((void**)&p->pin_act, sizeof(float) * N * (h->hs.act_dim > 0 ? h->hs.act_dim : 1)));
+  CUDA_OK(cudaMallocHost((void**)&p->pin_out, p->out_bytes + 64));
+  return 0;
+}
+static void plat_fini(fe_handle* h) {
+  CudaPlat* p = (CudaPlat*)h->plat;
+  if (!p) return;
+  cudaDeviceSynchronize();
+  if (p->pin_act) cudaFreeHost(p->pin_act);
+  if (p->pin_out) cudaFreeHost(p->pin_out);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  h->plat = nullptr;
+}
+static void plat_sync(fe_handle* h) { cudaDeviceSynchronize(); }
+static void plat_copy_d2d(fe_handle* h, void* dst, const void* src, size_t n, void* stream) {
+  if (dst != src) cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+static int plat_run_sim(fe_handle* h, int nsub, int mode, void* stream) {
+  int rc = plat_prepare(h);
+  if (rc) return rc;
+  CudaPlat* p = (CudaPlat*)h->plat;
+  fe_sim_kernel<<<h->N, 32, p->smem_sim, (cudaStream_t)stream>>>(h->st, h->dm, h->opt, nsub, mode, h->dbg);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int plat_run_reset(fe_handle* h, const uint8_t* mask, void* stream) {
+  int rc = plat_prepare(h);
+  if (rc) return rc;
+  CudaPlat* p = (CudaPlat*)h->plat;
+  fe_env_reset_kernel<<<h->N, 32, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, mask, h->slice_words);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, void* stream) {
+  int rc = plat_prepare(h);
+  if (rc) return rc;
+  CudaPlat* p = (CudaPlat*)h->plat;
+  fe_env_step_kernel<<<h->N, 32, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int plat_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
+  int rc = plat_prepare(h);
+  if (rc) return rc;
+  CudaPlat* p = (CudaPlat*)h->plat;
+  const size_t N = h->N, ab = sizeof(float) * N * h->hs.act_dim, ob = sizeof(float) * N * h->hs.obs_dim, rb = sizeof(float) * N, ib = sizeof(int32_t) * N * FE_INFO_DIM;
+  memcpy(p->pin_act, actions, ab);
+  CUDA_OK(cudaMemcpyAsync(h->dev_act, p->pin_act, ab, cudaMemcpyHostToDevice, p->stream));
+  fe_env_step_kernel<<<h->N, 32, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
+                                                            (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words);
+  CUDA_OK(cudaGetLastError());
+  unsigned char* o = p->pin_out;
+  CUDA_OK(cudaMemcpyAsync(o, h->es.obs, ob, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaMemcpyAsync(o + ob, h->dev_rew, rb, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaMemcpyAsync(o + ob + rb, h->dev_info, ib, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaMemcpyAsync(o + ob + rb + ib, h->dev_done, N, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaStreamSynchronize(p->stream));
+  if (obs) memcpy(obs, o, ob);
+  if (reward) memcpy(reward, o + ob, rb);
+  if (info) memcpy(info, o + ob + rb, ib);
+  if (done) memcpy(done, o + ob + rb + ib, N);
+  return 0;
+}
+static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles,
+                           const int32_t* nangles, const double* thr, uint8_t* aligned, double* tq) {
+  // cos/sin of the allowed angles are evaluated on the host in float64 (the same libm the reference's numpy uses)
+  std::vector<double> cs(4 * (size_t)n), sn(4 * (size_t)n);
+  for (size_t i = 0; i < 4 * (size_t)n; ++i) { double a = angles[i] / 180 * 3.141592653589793; cs[i] = cos(a); sn[i] = sin(a); }
+  double *d_p1, *d_m1, *d_p2, *d_m2, *d_cs, *d_sn, *d_thr, *d_tq;
+  int32_t* d_na;
+  uint8_t* d_al;
+  const size_t N = n;
+  CUDA_OK(cudaMalloc(&d_p1, 24 * N)); CUDA_OK(cudaMalloc(&d_m1, 72 * N)); CUDA_OK(cudaMalloc(&d_p2, 24 * N)); CUDA_OK(cudaMalloc(&d_m2, 72 * N));
+  CUDA_OK(cudaMalloc(&d_cs, 32 * N)); CUDA_OK(cudaMalloc(&d_sn, 32 * N)); CUDA_OK(cudaMalloc(&d_thr, 32 * N)); CUDA_OK(cudaMalloc(&d_tq, 32 * N));
+  CUDA_OK(cudaMalloc(&d_na, 4 * N)); CUDA_OK(cudaMalloc(&d_al, N));
+  cudaMemcpy(d_p1, p1, 24 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_m1, m1, 72 * N, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_p2, p2, 24 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_m2, m2, 72 * N, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_cs, cs.data(), 32 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_sn, sn.data(), 32 * N, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_thr, thr, 32 * N, cudaMemcpyHostToDevice); cudaMemcpy(d_na, nangles, 4 * N, cudaMemcpyHostToDevice);
+  fe_is_aligned_kernel<<<(n + 127) / 128, 128>>>(n, d_p1, d_m1, d_p2, d_m2, d_cs, d_sn, d_na, d_thr, d_al, d_tq);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(aligned, d_al, N, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(tq, d_tq, 32 * N, cudaMemcpyDeviceToHost));
+  cudaFree(d_p1); cudaFree(d_m1); cudaFree(d_p2); cudaFree(d_m2); cudaFree(d_cs); cudaFree(d_sn); cudaFree(d_thr); cudaFree(d_tq); cudaFree(d_na); cudaFree(d_al);
+  return 0;
+}

@@ -1,0 +1,1182 @@
+// fe_engine.h -- one mj_step for one environment, executed by one warp out of its shared-memory slice.
+//
+// This is the B200-native replacement of the per-env MjSim.step() hot loop (reference call site
+// furniture/env/furniture.py:2878-2879; the arithmetic is MuJoCo's mj_step, see DESIGN.md for the stage map):
+//   fe_kin_smooth : forward kinematics over the fused link tree, link velocities, composite inertia (CRBA) of the
+//                   robot block, spatial inertia of every free part, RNE bias wrench, actuation, qacc_smooth
+//   fe_collide    : geom poses, broad phase over the compile-time pair list with the per-env contype/conaffinity
+//                   masks, narrow phase (fe_collide.h), per-part finger/floor touch flags
+//   fe_assemble   : contact / weld / joint-limit rows (impedance, regularisation R, reference acceleration aref)
+//   fe_solve      : primal Newton solver with exact line search over elliptic friction cones (impratio scaling)
+//   fe_integrate  : semi-implicit Euler with implicit joint damping, quaternion integration
+// Solver coordinates z: robot joint accelerations, then for every free part the world-frame spatial acceleration
+// [alpha; vdot_origin] (a fixed orthogonal change of variables of the part's qacc, so the Newton iterates coincide).
+#pragma once
+#include "fe_collide.h"
+#include "fe_model.h"
+#include "fe_warp.h"
+
+#define FE_MINVAL 1e-15f
+#define FE_MINIMP 0.0001f
+#define FE_MAXIMP 0.9999f
+#define FE_MAXCAND 96
+
+struct FeOpt {
+  int maxcon;       // contact capacity per env
+  int newton_iters; // max Newton iterations
+  int ls_iters;     // max line-search evaluations
+  float tolerance;  // scaled improvement / gradient tolerance (MuJoCo: 1e-8 in double)
+};
+
+// ---- shared-memory layout of one warp (all sizes in 4-byte words)
+struct FeWarp {
+  const fe_model* m;
+  FeOpt opt;
+  // persistent state
+  float *qpos, *qvel, *warm, *ctrl, *qfrc_applied, *gravcomp, *eq_data;
+  int *contype, *conaff, *eq_active;
+  // kinematics / dynamics
+  float *lpos, *lquat, *lmat, *S, *lvel, *lacc, *lfrc, *linert, *lcrb, *Mr, *Lr, *fs, *as, *bias, *lacc2;
+  // collision
+  float *gpos, *gmat;
+  int *cand, *touch;
+  // contacts (SoA, maxcon each)
+  float *c_dist, *c_pos, *c_frame, *c_aref, *c_D, *c_mu, *c_fric, *c_jar, *c_jv, *c_f;
+  int *c_geom, *c_link, *c_state;
+  // welds (neq each) and limits (nr each)
+  float *w_r1, *w_G, *w_aref, *w_D, *w_jar, *w_jv, *w_f;
+  float *l_sign, *l_aref, *l_D, *l_jar, *l_jv, *l_f;
+  // solver
+  float *x, *Ma, *grad, *search, *Mv, *fc, *H, *Jc, *scr;
+  int *first, *iscr, *colmap;
+  // uniform scalars (kept in smem so that both builds see one copy)
+  int* u; // [0]=ncon [1]=ncand [2]=flags [3]=niter
+};
+
+FE_BOTH int fe_tri(int n) { return n * (n + 1) / 2; }
+
+// Carves the slice; returns the number of words used. Pass base = nullptr to only measure.
+FE_BOTH int fe_warp_bind(FeWarp* w, float* base, const fe_model* m, const FeOpt& opt) {
+  int o = 0;
+  const int nq = m->nq, nv = m->nv, nu = m->nu, nl = m->nlink, nr = m->nr, np = m->npart, ng = m->ngeom, ne = m->neq, mc = opt.maxcon;
+#define CARVE_F(field, n) w->field = base ? base + o : nullptr; o += (n);
+#define CARVE_I(field, n) w->field = base ? (int*)(base + o) : nullptr; o += (n);
+  w->m = m; w->opt = opt;
+  CARVE_F(qpos, nq) CARVE_F(qvel, nv) CARVE_F(warm, nv) CARVE_F(ctrl, nu) CARVE_F(qfrc_applied, nr) CARVE_F(gravcomp, np) CARVE_F(eq_data, 7 * ne)
+  CARVE_I(contype, ng) CARVE_I(conaff, ng) CARVE_I(eq_active, ne)
+  CARVE_F(lpos, 3 * nl) CARVE_F(lquat, 4 * nl) CARVE_F(lmat, 9 * nl) CARVE_F(S, 6 * nr) CARVE_F(lvel, 6 * nl) CARVE_F(lacc, 6 * nl) CARVE_F(lfrc, 6 * nl)
+  CARVE_F(linert, 10 * nl) CARVE_F(lcrb, 10 * nr) CARVE_F(Mr, nr * nr) CARVE_F(Lr, fe_tri(nr)) CARVE_F(fs, nv) CARVE_F(as, nv) CARVE_F(bias, nr) CARVE_F(lacc2, 6 * nl)
+  CARVE_I(touch, np)
+  CARVE_F(c_dist, mc) CARVE_F(c_pos, 3 * mc) CARVE_F(c_frame, 9 * mc) CARVE_F(c_aref, 3 * mc) CARVE_F(c_D, 2 * mc) CARVE_F(c_mu, mc) CARVE_F(c_fric, mc)
+  CARVE_F(c_jar, 3 * mc) CARVE_F(c_jv, 3 * mc) CARVE_F(c_f, 3 * mc) CARVE_I(c_geom, mc) CARVE_I(c_link, mc) CARVE_I(c_state, mc)
+  CARVE_F(w_r1, 3 * ne) CARVE_F(w_G, 9 * ne) CARVE_F(w_aref, 6 * ne) CARVE_F(w_D, 6 * ne) CARVE_F(w_jar, 6 * ne) CARVE_F(w_jv, 6 * ne) CARVE_F(w_f, 6 * ne)
+  CARVE_F(l_sign, nr) CARVE_F(l_aref, nr) CARVE_F(l_D, nr) CARVE_F(l_jar, nr) CARVE_F(l_jv, nr) CARVE_F(l_f, nr)
+  CARVE_F(x, nv) CARVE_F(Ma, nv) CARVE_F(grad, nv) CARVE_F(search, nv) CARVE_F(Mv, nv) CARVE_F(fc, nv)
+  CARVE_F(Jc, 3 * 32) CARVE_F(scr, 3 * 32) CARVE_I(first, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 4)
+  // H (solver) and the collision scratch (geom poses, candidate list) are never live together: overlay them
+  int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
+  int big = hwords > cwords ? hwords : cwords;
+  w->H = base ? base + o : nullptr;
+  w->gpos = w->H; w->gmat = base ? base + o + 3 * ng : nullptr; w->cand = base ? (int*)(base + o + 12 * ng) : nullptr;
+  o += big;
+#undef CARVE_F
+#undef CARVE_I
+  return o;
+}
+
+// ---------------------------------------------------------------- 6x6 SPD helpers (packed lower, index i(i+1)/2+j)
+FE_HD void fe_inert_sym6(float* A, const float* I, float diag_add) {
+  const float m = I[0], hx = I[1], hy = I[2], hz = I[3];
+  // rows 0-2: [Io, [h]x]; rows 3-5: [[h]x^T, m 1]
+  A[0] = I[4] + diag_add;
+  A[1] = I[7]; A[2] = I[5] + diag_add;
+  A[3] = I[8]; A[4] = I[9]; A[5] = I[6] + diag_add;
+  // row 3 (v_x): [h]x^T row 0 = (0, hz, -hy)
+  A[6] = 0.f; A[7] = hz; A[8] = -hy; A[9] = m + diag_add;
+  A[10] = -hz; A[11] = 0.f; A[12] = hx; A[13] = 0.f; A[14] = m + diag_add;
+  A[15] = hy; A[16] = -hx; A[17] = 0.f; A[18] = 0.f; A[19] = 0.f; A[20] = m + diag_add;
+}
+FE_HD bool fe_chol6(float* A) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float s = A[k * (k + 1) / 2 + k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) s -= A[k * (k + 1) / 2 + j] * A[k * (k + 1) / 2 + j];
+    if (!(s > 1e-30f)) { ok = false; s = 1e-30f; }
+    float l = sqrtf(s), inv = 1.0f / l;
+    A[k * (k + 1) / 2 + k] = l;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      float t = A[i * (i + 1) / 2 + k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) t -= A[i * (i + 1) / 2 + j] * A[k * (k + 1) / 2 + j];
+      A[i * (i + 1) / 2 + k] = t * inv;
+    }
+  }
+  return ok;
+}
+FE_HD void fe_chol6_solve(const float* L, float* x) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float s = x[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s -= L[i * (i + 1) / 2 + j] * x[j];
+    x[i] = s / L[i * (i + 1) / 2 + i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    float s = x[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) s -= L[j * (j + 1) / 2 + i] * x[j];
+    x[i] = s / L[i * (i + 1) / 2 + i];
+  }
+}
+
+// ---------------------------------------------------------------- cooperative skyline Cholesky (packed lower H)
+// first[i] = first column of row i's envelope. Returns false (uniform) if a pivot is not positive.
+FE_FN bool fe_chol(FeWarp* w, float* H, const int* first, int n) {
+  bool ok = true;
+  for (int k = 0; k < n; ++k) {
+    const int fk = first[k];
+    LANES_BEGIN
+      for (int i = k + lane; i < n; i += 32) {
+        int fi = first[i];
+        if (fi > k) continue;
+        int j0 = fi > fk ? fi : fk;
+        const float* Hi = H + fe_tri(i);
+        const float* Hk = H + fe_tri(k);
+        float s = Hi[k];
+        for (int j = j0; j < k; ++j) s -= Hi[j] * Hk[j];
+        H[fe_tri(i) + k] = s;
+      }
+    LANES_END
+    float pk = H[fe_tri(k) + k];
+    FE_SYNC; // every lane has read the pivot before the row-k lane overwrites it
+    if (!(pk > 1e-30f)) { ok = false; pk = 1e-30f; }
+    const float lkk = sqrtf(pk), inv = 1.0f / lkk;
+    LANES_BEGIN
+      for (int i = k + lane; i < n; i += 32) {
+        if (first[i] > k) continue;
+        if (i == k) H[fe_tri(k) + k] = lkk; else H[fe_tri(i) + k] *= inv;
+      }
+    LANES_END
+  }
+  return ok;
+}
+// x <- (L L^T)^-1 x ; tmp is an n-vector scratch
+FE_FN void fe_chol_solve(FeWarp* w, const float* L, const int* first, int n, float* x, float* tmp) {
+  for (int k = 0; k < n; ++k) { // forward: tmp = L^-1 x
+    const float xk = x[k] / L[fe_tri(k) + k];
+    LANES_BEGIN
+      if (lane == 0) tmp[k] = xk;
+      for (int i = k + 1 + lane; i < n; i += 32)
+        if (first[i] <= k) x[i] -= L[fe_tri(i) + k] * xk;
+    LANES_END
+  }
+  for (int k = n - 1; k >= 0; --k) { // backward: x = L^-T tmp
+    const float xk = tmp[k] / L[fe_tri(k) + k];
+    const int fk = first[k];
+    LANES_BEGIN
+      if (lane == 0) x[k] = xk;
+      for (int j = fk + lane; j < k; j += 32) tmp[j] -= L[fe_tri(k) + j] * xk;
+    LANES_END
+  }
+}
+
+// ---------------------------------------------------------------- kinematics + smooth dynamics
+FE_FN void fe_kin_smooth(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int nl = m->nlink, nr = m->nr, nrl = m->nrlink, nv = m->nv;
+  const float Pr[3] = {m->robot_ref[0], m->robot_ref[1], m->robot_ref[2]};
+  const float g[3] = {m->gravity[0], m->gravity[1], m->gravity[2]};
+  for (int level = 0; level <= m->maxdepth; ++level) {
+    LANES_BEGIN
+      const int l = lane;
+      if (l < nl && m->link_depth[l] == level) {
+        float pos[3], quat[4], R[9], V[6], A[6];
+        const int qa = m->link_qadr[l], da = m->link_dadr[l];
+        if (m->link_jtype[l] == FE_JNT_FREE) {
+          v3cpy(pos, w->qpos + qa);
+          quat[0] = w->qpos[qa + 3]; quat[1] = w->qpos[qa + 4]; quat[2] = w->qpos[qa + 5]; quat[3] = w->qpos[qa + 6];
+          qnormalize(quat);
+          q2mat(R, quat);
+          m3mulv(V, R, w->qvel + da + 3);            // world angular velocity
+          v3cpy(V + 3, w->qvel + da);                // velocity of the link origin (= reference point)
+          float t[3];
+          v3cross(t, V, V + 3);
+          A[0] = A[1] = A[2] = 0.f;
+          A[3] = -t[0] - g[0]; A[4] = -t[1] - g[1]; A[5] = -t[2] - g[2];
+        } else {
+          const int p = m->link_parent[l];
+          float ppos[3] = {0.f, 0.f, 0.f}, pquat[4] = {1.f, 0.f, 0.f, 0.f}, pR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+          float Vp[6] = {0, 0, 0, 0, 0, 0}, Ap[6] = {0, 0, 0, -g[0], -g[1], -g[2]};
+          if (p >= 0) {
+            v3cpy(ppos, w->lpos + 3 * p);
+            for (int k = 0; k < 4; ++k) pquat[k] = w->lquat[4 * p + k];
+            for (int k = 0; k < 9; ++k) pR[k] = w->lmat[9 * p + k];
+            for (int k = 0; k < 6; ++k) { Vp[k] = w->lvel[6 * p + k]; Ap[k] = w->lacc[6 * p + k]; }
+          }
+          float t[3], anchor[3], axis[3];
+          m3mulv(t, pR, m->link_pos[l]);
+          v3add(pos, ppos, t);
+          qmul(quat, pquat, m->link_quat[l]);
+          q2mat(R, quat);
+          m3mulv(t, R, m->link_jpos[l]);
+          v3add(anchor, pos, t);
+          m3mulv(axis, R, m->link_jaxis[l]);
+          const float q = w->qpos[qa], qd = w->qvel[da];
+          float Sd[6];
+          if (m->link_jtype[l] == FE_JNT_HINGE) {
+            float s = sinf(0.5f * q), c = cosf(0.5f * q);
+            float ql[4] = {c, m->link_jaxis[l][0] * s, m->link_jaxis[l][1] * s, m->link_jaxis[l][2] * s}, qn[4];
+            qmul(qn, quat, ql);
+            for (int k = 0; k < 4; ++k) quat[k] = qn[k];
+            qnormalize(quat);
+            q2mat(R, quat);
+            m3mulv(t, R, m->link_jpos[l]);
+            v3sub(pos, anchor, t);
+            v3cpy(Sd, axis);
+            v3sub(t, anchor, Pr);
+            v3cross(Sd + 3, t, axis);
+          } else {
+            v3madd(pos, pos, axis, q);
+            qnormalize(quat);
+            q2mat(R, quat);
+            Sd[0] = Sd[1] = Sd[2] = 0.f;
+            v3cpy(Sd + 3, axis);
+          }
+          float Sdot[6];
+          crossm(Sdot, Vp, Sd);
+          for (int k = 0; k < 6; ++k) { V[k] = Vp[k] + Sd[k] * qd; A[k] = Ap[k] + Sdot[k] * qd; w->S[6 * da + k] = Sd[k]; }
+        }
+        v3cpy(w->lpos + 3 * l, pos);
+        for (int k = 0; k < 4; ++k) w->lquat[4 * l + k] = quat[k];
+        for (int k = 0; k < 9; ++k) w->lmat[9 * l + k] = R[k];
+        for (int k = 0; k < 6; ++k) { w->lvel[6 * l + k] = V[k]; w->lacc[6 * l + k] = A[k]; }
+      }
+    LANES_END
+  }
+  // spatial inertia about the link's reference point (robot_ref for robot links, own origin for parts) + RNE wrench
+  LANES_BEGIN
+    const int l = lane;
+    if (l < nl) {
+      const float* R = w->lmat + 9 * l;
+      float I[10], t[3];
+      I[0] = m->link_mass[l];
+      m3mulv(t, R, m->link_com[l]);
+      if (l < nrl) {
+        float d[3];
+        v3add(d, w->lpos + 3 * l, t);
+        v3sub(d, d, Pr);
+        sym3rot(I + 4, R, m->link_inertia_c[l]);
+        const float mm = I[0], dd = v3dot(d, d);
+        I[4] += mm * (dd - d[0] * d[0]); I[5] += mm * (dd - d[1] * d[1]); I[6] += mm * (dd - d[2] * d[2]);
+        I[7] -= mm * d[0] * d[1]; I[8] -= mm * d[0] * d[2]; I[9] -= mm * d[1] * d[2];
+        I[1] = mm * d[0]; I[2] = mm * d[1]; I[3] = mm * d[2];
+      } else {
+        sym3rot(I + 4, R, m->link_inertia_o[l]);
+        I[1] = I[0] * t[0]; I[2] = I[0] * t[1]; I[3] = I[0] * t[2];
+      }
+      float IA[6], IV[6], X[6];
+      inert_mulv(IA, I, w->lacc + 6 * l);
+      inert_mulv(IV, I, w->lvel + 6 * l);
+      crossf(X, w->lvel + 6 * l, IV);
+      for (int k = 0; k < 10; ++k) w->linert[10 * l + k] = I[k];
+      if (l < nrl) for (int k = 0; k < 10; ++k) w->lcrb[10 * l + k] = I[k];
+      for (int k = 0; k < 6; ++k) w->lfrc[6 * l + k] = IA[k] + X[k];
+    }
+  LANES_END
+  // leaves -> root accumulation of RNE wrench and composite inertia (robot tree)
+  for (int level = m->maxdepth - 1; level >= 0; --level) {
+    LANES_BEGIN
+      const int l = lane;
+      if (l < nrl && m->link_depth[l] == level) {
+        for (int c = l + 1; c < nrl; ++c)
+          if (m->link_parent[c] == l) {
+            for (int k = 0; k < 6; ++k) w->lfrc[6 * l + k] += w->lfrc[6 * c + k];
+            for (int k = 0; k < 10; ++k) w->lcrb[10 * l + k] += w->lcrb[10 * c + k];
+          }
+      }
+    LANES_END
+  }
+  // robot: bias force, joint-space inertia, smooth force
+  LANES_BEGIN
+    const int d = lane;
+    if (d < nr) {
+      const float* Sd = w->S + 6 * d;
+      const float b = dot6(Sd, w->lfrc + 6 * d);
+      w->bias[d] = b;
+      float F[6];
+      inert_mulv(F, w->lcrb + 10 * d, Sd);
+      for (int a = d; a >= 0; a = m->link_parent[a]) {
+        float v = dot6(w->S + 6 * a, F);
+        w->Mr[d * nr + a] = v;
+        w->Mr[a * nr + d] = v;
+      }
+      float f = -m->dof_damping[d] * w->qvel[d] - b + w->qfrc_applied[d];
+      for (int u = 0; u < m->nu; ++u)
+        if (m->act_dof[u] == d) {
+          float c = w->ctrl[u];
+          if (m->act_ctrllimited[u]) c = fminf(fmaxf(c, m->act_ctrlrange[u][0]), m->act_ctrlrange[u][1]);
+          const float gear = m->act_gear[u];
+          float af = m->act_gain[u] * c + m->act_bias[u][0] + m->act_bias[u][1] * gear * w->qpos[m->act_qadr[u]] + m->act_bias[u][2] * gear * w->qvel[d];
+          if (m->act_forcelimited[u]) af = fminf(fmaxf(af, m->act_forcerange[u][0]), m->act_forcerange[u][1]);
+          f += gear * af;
+        }
+      w->fs[d] = f;
+    }
+  LANES_END
+  // zero the entries of Mr between unrelated dofs (branches) -- they are never written above
+  LANES_BEGIN
+    for (int e = lane; e < nr * nr; e += 32) {
+      int i = e / nr, j = e % nr;
+      int lo = i < j ? i : j, hi = i < j ? j : i;
+      if (!((m->link_ancmask[hi] >> lo) & 1)) w->Mr[e] = 0.f;
+    }
+    for (int e = lane; e < nr; e += 32) w->first[e] = 0;
+  LANES_END
+  // parts: smooth wrench and acceleration in z coordinates
+  LANES_BEGIN
+    const int p = lane;
+    if (p < m->npart) {
+      const int l = nrl + p, z = nr + 6 * p, da = m->link_dadr[l];
+      const float* I = w->linert + 10 * l;
+      const float* V = w->lvel + 6 * l;
+      const float damp = m->dof_damping[da];
+      float W[6];
+      for (int k = 0; k < 6; ++k) W[k] = -w->lfrc[6 * l + k] - damp * V[k];
+      const float gc = w->gravcomp[p];
+      if (gc != 0.f) { // xfrc_applied = -gc * gravity * mass at the CoM (furniture.py:2778-2790)
+        float F[3] = {-gc * g[0] * I[0], -gc * g[1] * I[0], -gc * g[2] * I[0]}, r[3] = {I[1] / I[0], I[2] / I[0], I[3] / I[0]}, t[3];
+        v3cross(t, r, F);
+        W[0] += t[0]; W[1] += t[1]; W[2] += t[2]; W[3] += F[0]; W[4] += F[1]; W[5] += F[2];
+      }
+      float A[21], a[6];
+      fe_inert_sym6(A, I, 0.f);
+      if (!fe_chol6(A)) w->u[2] |= 2;
+      for (int k = 0; k < 6; ++k) { w->fs[z + k] = W[k]; a[k] = W[k]; }
+      fe_chol6_solve(A, a);
+      for (int k = 0; k < 6; ++k) w->as[z + k] = a[k];
+    }
+  LANES_END
+  // robot smooth acceleration: Lr = chol(Mr)
+  if (nr > 0) {
+    LANES_BEGIN
+      for (int e = lane; e < fe_tri(nr); e += 32) {
+        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        while (fe_tri(i + 1) <= e) ++i;
+        while (fe_tri(i) > e) --i;
+        w->Lr[e] = w->Mr[i * nr + (e - fe_tri(i))];
+      }
+      for (int e = lane; e < nr; e += 32) w->as[e] = w->fs[e];
+    LANES_END
+    if (!fe_chol(w, w->Lr, w->first, nr)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END }
+    fe_chol_solve(w, w->Lr, w->first, nr, w->as, w->grad);
+  }
+  (void)nv;
+}
+
+// ---------------------------------------------------------------- collision
+#if FE_DEVICE_BUILD
+FE_HD int fe_lane_excl_scan(int n) {
+  int v = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((int)(threadIdx.x & 31u) >= o) v += t;
+  }
+  return v - n;
+}
+#define FE_SCAN(run, n) fe_lane_excl_scan(n)
+#else
+#define FE_SCAN(run, n) ((run += (n)), (run - (n)))
+#endif
+
+FE_FN void fe_collide(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int ng = m->ngeom, npair = m->npair, nrl = m->nrlink, mc = w->opt.maxcon;
+  LANES_BEGIN
+    for (int gi = lane; gi < ng; gi += 32) {
+      const int l = m->geom_link[gi];
+      float* gp = w->gpos + 3 * gi;
+      float* gm = w->gmat + 9 * gi;
+      if (l < 0) { v3cpy(gp, m->geom_pos[gi]); for (int k = 0; k < 9; ++k) gm[k] = m->geom_mat[gi][k]; }
+      else {
+        float t[3];
+        m3mulv(t, w->lmat + 9 * l, m->geom_pos[gi]);
+        v3add(gp, w->lpos + 3 * l, t);
+        m3mul(gm, w->lmat + 9 * l, m->geom_mat[gi]);
+      }
+    }
+    if (lane < m->npart) w->touch[lane] = 0;
+  LANES_END
+  int ncand = 0;
+  for (int base = 0; base < npair; base += 32) {
+    LANES_BEGIN
+      const int k = base + lane;
+      int flag = 0;
+      if (k < npair) {
+        const int g1 = m->pair_g1[k], g2 = m->pair_g2[k];
+        if ((w->contype[g1] & w->conaff[g2]) || (w->contype[g2] & w->conaff[g1])) {
+          float t[3];
+          v3sub(t, w->gpos + 3 * g2, w->gpos + 3 * g1);
+          if (m->geom_type[g1] == FE_GEOM_PLANE) {
+            float n[3];
+            fe_col(n, w->gmat + 9 * g1, 2);
+            flag = v3dot(t, n) <= m->geom_rbound[g2];
+          } else {
+            float bnd = m->geom_rbound[g1] + m->geom_rbound[g2];
+            flag = v3dot(t, t) <= bnd * bnd;
+          }
+        }
+      }
+      w->iscr[lane] = flag;
+    LANES_END
+    const unsigned mask = fe_ballot32(w->iscr);
+    LANES_BEGIN
+      if ((mask >> lane) & 1u) {
+        int idx = ncand + fe_popc(mask & ((1u << lane) - 1u));
+        if (idx < FE_MAXCAND) w->cand[idx] = base + lane;
+      }
+    LANES_END
+    ncand += fe_popc(mask);
+  }
+  if (ncand > FE_MAXCAND) { ncand = FE_MAXCAND; LANES_BEGIN if (lane == 0) w->u[2] |= 1; LANES_END }
+  int ncon = 0;
+  for (int base = 0; base < ncand; base += 32) {
+    int run = 0;
+    (void)run;
+    LANES_BEGIN
+      const int ci = base + lane;
+      FeCon res[8];
+      int n = 0, g1 = 0, g2 = 0;
+      if (ci < ncand) {
+        const int k = w->cand[ci];
+        g1 = m->pair_g1[k]; g2 = m->pair_g2[k];
+        n = fe_narrowphase(m->geom_type[g1], w->gpos + 3 * g1, w->gmat + 9 * g1, m->geom_size[g1], m->geom_type[g2], w->gpos + 3 * g2, w->gmat + 9 * g2,
+                           m->geom_size[g2], res);
+      }
+      const int off = FE_SCAN(run, n);
+      for (int i = 0; i < n; ++i) {
+        const int c = ncon + off + i;
+        if (c < mc) {
+          w->c_dist[c] = res[i].dist;
+          v3cpy(w->c_pos + 3 * c, res[i].pos);
+          v3cpy(w->c_frame + 9 * c, res[i].n);
+          w->c_geom[c] = g1 | (g2 << 8);
+        }
+      }
+      if (lane == 31) w->iscr[0] = off + n;
+    LANES_END
+    ncon += w->iscr[0];
+    LANES_BEGIN LANES_END
+  }
+  if (ncon > mc) { ncon = mc; LANES_BEGIN if (lane == 0) w->u[2] |= 1; LANES_END }
+  // touch flags per part: bit0 left finger, bit1 right finger, bit2 floor (furniture.py:500-520, :1290-1322)
+  LANES_BEGIN
+    const int p = lane;
+    if (p < m->npart) {
+      int bits = 0;
+      for (int c = 0; c < ncon; ++c) {
+        const int g1 = w->c_geom[c] & 255, g2 = w->c_geom[c] >> 8;
+        const int t1 = m->geom_tag[g1], t2 = m->geom_tag[g2];
+        const int p1 = ((t1 >> FE_TAG_PART_SHIFT) & 0xff) - 1, p2 = ((t2 >> FE_TAG_PART_SHIFT) & 0xff) - 1;
+        if (p1 == p) bits |= ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0) | ((t2 & FE_TAG_FLOOR) ? 4 : 0);
+        if (p2 == p) bits |= ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0) | ((t1 & FE_TAG_FLOOR) ? 4 : 0);
+      }
+      w->touch[p] = bits;
+    }
+    if (lane == 0) { w->u[0] = ncon; w->u[1] = ncand; }
+  LANES_END
+  (void)nrl;
+}
+
+// ---------------------------------------------------------------- constraint rows
+FE_HD float fe_impedance(const float* si, float dist_abs) {
+  float d0 = fminf(fmaxf(si[0], FE_MINIMP), FE_MAXIMP), d1 = fminf(fmaxf(si[1], FE_MINIMP), FE_MAXIMP);
+  float width = fmaxf(si[2], FE_MINVAL);
+  if (d0 == d1) return d0;
+  float x = dist_abs / width;
+  if (x >= 1.f) return d1;
+  float y = x <= 0.5f ? 2.f * x * x : 1.f - 2.f * (1.f - x) * (1.f - x); // midpoint 0.5, power 2
+  return d0 + y * (d1 - d0);
+}
+FE_HD void fe_kb(const float* solref, float dmax_in, float h, float* k, float* b) {
+  float tc = solref[0], dr = solref[1];
+  if (tc > 0.f && tc < 2.f * h) tc = 2.f * h; // refsafe
+  float dmax = fminf(fmaxf(dmax_in, FE_MINIMP), FE_MAXIMP);
+  *k = 1.f / (dmax * dmax * tc * tc * dr * dr);
+  *b = 2.f / (dmax * tc);
+}
+// reference point of a link (world)
+FE_HD void fe_link_ref(const FeWarp* w, int l, float* P) {
+  if (l < w->m->nrlink) { P[0] = w->m->robot_ref[0]; P[1] = w->m->robot_ref[1]; P[2] = w->m->robot_ref[2]; }
+  else v3cpy(P, w->lpos + 3 * l);
+}
+// velocity-like quantity of the point p fixed to link l, from per-link spatial vectors X (6*nlink): X.v + X.w x (p - P)
+FE_HD void fe_point_vel(const FeWarp* w, const float* X, int l, const float* p, float* out) {
+  if (l < 0) { out[0] = out[1] = out[2] = 0.f; return; }
+  float P[3], r[3], t[3];
+  fe_link_ref(w, l, P);
+  v3sub(r, p, P);
+  v3cross(t, X + 6 * l, r);
+  out[0] = X[6 * l + 3] + t[0]; out[1] = X[6 * l + 4] + t[1]; out[2] = X[6 * l + 5] + t[2];
+}
+FE_HD void fe_make_frame(float* F) {
+  float* x = F;
+  float* y = F + 3;
+  float* z = F + 6;
+  v3normalize(x);
+  if (fabsf(x[1]) < 0.5f) { y[0] = 0.f; y[1] = 1.f; y[2] = 0.f; } else { y[0] = 0.f; y[1] = 0.f; y[2] = 1.f; }
+  float dt = v3dot(x, y);
+  v3madd(y, y, x, -dt);
+  v3normalize(y);
+  v3cross(z, x, y);
+}
+
+FE_FN void fe_assemble(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int ncon = w->u[0], nr = m->nr, ne = m->neq;
+  const float h = m->timestep;
+  LANES_BEGIN
+    for (int c = lane; c < ncon; c += 32) {
+      const int g1 = w->c_geom[c] & 255, g2 = w->c_geom[c] >> 8;
+      const int A = m->geom_link[g1], B = m->geom_link[g2];
+      w->c_link[c] = (A + 1) | ((B + 1) << 8);
+      float* F = w->c_frame + 9 * c;
+      fe_make_frame(F);
+      const float fric = fmaxf(fmaxf(m->geom_friction[g1], m->geom_friction[g2]), 1e-5f);
+      float sr[2], si[3];
+      const float *s1 = m->geom_solref[g1], *s2 = m->geom_solref[g2];
+      if (s1[0] > 0.f && s2[0] > 0.f) { sr[0] = 0.5f * (s1[0] + s2[0]); sr[1] = 0.5f * (s1[1] + s2[1]); }
+      else { sr[0] = fminf(s1[0], s2[0]); sr[1] = fminf(s1[1], s2[1]); }
+      for (int k = 0; k < 3; ++k) si[k] = 0.5f * (m->geom_solimp[g1][k] + m->geom_solimp[g2][k]);
+      const float dist = w->c_dist[c];
+      const float imp = fe_impedance(si, fabsf(dist));
+      float kk, bb;
+      fe_kb(sr, si[1], h, &kk, &bb);
+      const float diag = fmaxf(m->geom_invweight[g1] + m->geom_invweight[g2], FE_MINVAL);
+      const float R0 = fmaxf((1.f - imp) / imp * diag, FE_MINVAL);
+      const float R1 = fmaxf(R0 / m->impratio, FE_MINVAL);
+      w->c_D[2 * c] = 1.f / R0;
+      w->c_D[2 * c + 1] = 1.f / R1;
+      w->c_mu[c] = fric * sqrtf(R1 / R0);
+      w->c_fric[c] = fric;
+      float vA[3], vB[3], dv[3];
+      fe_point_vel(w, w->lvel, A, w->c_pos + 3 * c, vA);
+      fe_point_vel(w, w->lvel, B, w->c_pos + 3 * c, vB);
+      v3sub(dv, vB, vA);
+      w->c_aref[3 * c] = -bb * v3dot(F, dv) - kk * imp * dist;
+      w->c_aref[3 * c + 1] = -bb * v3dot(F + 3, dv);
+      w->c_aref[3 * c + 2] = -bb * v3dot(F + 6, dv);
+    }
+    // weld rows
+    for (int e = lane; e < ne; e += 32) {
+      if (!w->eq_active[e]) continue;
+      const int A = m->eq_link1[e], B = m->eq_link2[e];
+      const float* data = w->eq_data + 7 * e;
+      float r1[3], p1[3], err[6];
+      m3mulv(r1, w->lmat + 9 * A, data);
+      v3add(p1, w->lpos + 3 * A, r1);
+      v3sub(err, p1, w->lpos + 3 * B);
+      float quat[4], qc[4], qe[4];
+      qmul(quat, w->lquat + 4 * A, data + 3);
+      qc[0] = w->lquat[4 * B]; qc[1] = -w->lquat[4 * B + 1]; qc[2] = -w->lquat[4 * B + 2]; qc[3] = -w->lquat[4 * B + 3];
+      qmul(qe, qc, quat);
+      err[3] = qe[1]; err[4] = qe[2]; err[5] = qe[3];
+      float G[9];
+      for (int j = 0; j < 3; ++j) {
+        float ax[4] = {0.f, j == 0 ? 1.f : 0.f, j == 1 ? 1.f : 0.f, j == 2 ? 1.f : 0.f}, t1[4], t2[4];
+        qmul(t1, qc, ax);
+        qmul(t2, t1, quat);
+        G[0 + j] = 0.5f * t2[1]; G[3 + j] = 0.5f * t2[2]; G[6 + j] = 0.5f * t2[3];
+      }
+      v3cpy(w->w_r1 + 3 * e, r1);
+      for (int k = 0; k < 9; ++k) w->w_G[9 * e + k] = G[k];
+      const float *VA = w->lvel + 6 * A, *VB = w->lvel + 6 * B;
+      float vel[6], t[3], dw[3];
+      v3cross(t, VA, r1);
+      for (int k = 0; k < 3; ++k) vel[k] = VA[3 + k] + t[k] - VB[3 + k];
+      v3sub(dw, VA, VB);
+      m3mulv(vel + 3, G, dw);
+      float kk, bb;
+      fe_kb(m->eq_solref[e], m->eq_solimp[e][1], h, &kk, &bb);
+      for (int k = 0; k < 6; ++k) {
+        const float imp = fe_impedance(m->eq_solimp[e], fabsf(err[k]));
+        const float diag = fmaxf(k < 3 ? m->eq_invw_t[e] : m->eq_invw_r[e], FE_MINVAL);
+        const float R = fmaxf((1.f - imp) / imp * diag, FE_MINVAL);
+        w->w_D[6 * e + k] = 1.f / R;
+        w->w_aref[6 * e + k] = -bb * vel[k] - kk * imp * err[k];
+      }
+    }
+    // joint limits
+    for (int d = lane; d < nr; d += 32) {
+      float sgn = 0.f, dist = 0.f;
+      if (m->rdof_limited[d]) {
+        const float q = w->qpos[d];
+        if (q - m->rdof_range[d][0] < 0.f) { sgn = 1.f; dist = q - m->rdof_range[d][0]; }
+        else if (m->rdof_range[d][1] - q < 0.f) { sgn = -1.f; dist = m->rdof_range[d][1] - q; }
+      }
+      w->l_sign[d] = sgn;
+      if (sgn != 0.f) {
+        const float imp = fe_impedance(m->rdof_solimp[d], fabsf(dist));
+        float kk, bb;
+        fe_kb(m->rdof_solref[d], m->rdof_solimp[d][1], h, &kk, &bb);
+        const float R = fmaxf((1.f - imp) / imp * fmaxf(m->rdof_invweight[d], FE_MINVAL), FE_MINVAL);
+        w->l_D[d] = 1.f / R;
+        w->l_aref[d] = -bb * sgn * w->qvel[d] - kk * imp * dist;
+      } else { w->l_D[d] = 0.f; w->l_aref[d] = 0.f; }
+    }
+  LANES_END
+}
+
+// ---------------------------------------------------------------- solver pieces
+// out = M_z in
+FE_FN void fe_mul_M(FeWarp* w, const float* in, float* out) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, np = m->npart, nrl = m->nrlink;
+  LANES_BEGIN
+    for (int d = lane; d < nr; d += 32) {
+      float s = 0.f;
+      for (int j = 0; j < nr; ++j) s += w->Mr[d * nr + j] * in[j];
+      out[d] = s;
+    }
+    for (int p = lane; p < np; p += 32) inert_mulv(out + nr + 6 * p, w->linert + 10 * (nrl + p), in + nr + 6 * p);
+  LANES_END
+}
+// rows = J_z in  (contacts -> cout[3*c..], welds -> wout[6*e..], limits -> lout[d]); `sub_aref` subtracts aref
+FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float* lout, bool sub_aref) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink, nl = m->nlink, ncon = w->u[0], ne = m->neq;
+  LANES_BEGIN
+    const int l = lane;
+    if (l < nl) {
+      float X[6] = {0, 0, 0, 0, 0, 0};
+      if (l < nrl) {
+        const int mask = m->link_ancmask[l];
+        for (int d = 0; d < nr; ++d)
+          if ((mask >> d) & 1) { const float xd = in[d]; for (int k = 0; k < 6; ++k) X[k] += w->S[6 * d + k] * xd; }
+      } else for (int k = 0; k < 6; ++k) X[k] = in[nr + 6 * (l - nrl) + k];
+      for (int k = 0; k < 6; ++k) w->lacc2[6 * l + k] = X[k];
+    }
+  LANES_END
+  LANES_BEGIN
+    for (int c = lane; c < ncon; c += 32) {
+      const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+      float aA[3], aB[3], da[3];
+      fe_point_vel(w, w->lacc2, A, w->c_pos + 3 * c, aA);
+      fe_point_vel(w, w->lacc2, B, w->c_pos + 3 * c, aB);
+      v3sub(da, aB, aA);
+      const float* F = w->c_frame + 9 * c;
+      for (int k = 0; k < 3; ++k) cout[3 * c + k] = v3dot(F + 3 * k, da) - (sub_aref ? w->c_aref[3 * c + k] : 0.f);
+    }
+    for (int e = lane; e < ne; e += 32) {
+      if (!w->eq_active[e]) continue;
+      const float *XA = w->lacc2 + 6 * m->eq_link1[e], *XB = w->lacc2 + 6 * m->eq_link2[e];
+      float t[3], dw[3], r[6];
+      v3cross(t, XA, w->w_r1 + 3 * e);
+      for (int k = 0; k < 3; ++k) r[k] = XA[3 + k] + t[k] - XB[3 + k];
+      v3sub(dw, XA, XB);
+      m3mulv(r + 3, w->w_G + 9 * e, dw);
+      for (int k = 0; k < 6; ++k) wout[6 * e + k] = r[k] - (sub_aref ? w->w_aref[6 * e + k] : 0.f);
+    }
+    for (int d = lane; d < nr; d += 32) lout[d] = w->l_sign[d] * in[d] - (sub_aref ? w->l_aref[d] : 0.f);
+  LANES_END
+}
+// constraint forces/states from jar; returns the constraint cost
+FE_FN float fe_update(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int ncon = w->u[0], ne = m->neq, nr = m->nr;
+  LANES_BEGIN
+    float cost = 0.f;
+    for (int c = lane; c < ncon; c += 32) {
+      const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
+      const float j0 = w->c_jar[3 * c], j1 = w->c_jar[3 * c + 1], j2 = w->c_jar[3 * c + 2];
+      const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+      int st = 0;
+      if (N >= mu * T || (T <= 0.f && N >= 0.f)) st = 0;
+      else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+        st = 1;
+        f0 = -D0 * j0; f1 = -D1 * j1; f2 = -D1 * j2;
+        cost += 0.5f * (D0 * j0 * j0 + D1 * (j1 * j1 + j2 * j2));
+      } else {
+        st = 2;
+        const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+        cost += 0.5f * Dm * NmT * NmT;
+        f0 = -Dm * NmT * mu;
+        f1 = -f0 / T * U1 * fr;
+        f2 = -f0 / T * U2 * fr;
+      }
+      w->c_f[3 * c] = f0; w->c_f[3 * c + 1] = f1; w->c_f[3 * c + 2] = f2;
+      w->c_state[c] = st;
+    }
+    for (int e = lane; e < ne; e += 32) {
+      if (!w->eq_active[e]) continue;
+      for (int k = 0; k < 6; ++k) {
+        const float D = w->w_D[6 * e + k], j = w->w_jar[6 * e + k];
+        w->w_f[6 * e + k] = -D * j;
+        cost += 0.5f * D * j * j;
+      }
+    }
+    for (int d = lane; d < nr; d += 32) {
+      float f = 0.f;
+      if (w->l_sign[d] != 0.f && w->l_jar[d] < 0.f) { f = -w->l_D[d] * w->l_jar[d]; cost += 0.5f * w->l_D[d] * w->l_jar[d] * w->l_jar[d]; }
+      w->l_f[d] = f;
+    }
+    w->scr[lane] = cost;
+  LANES_END
+  return fe_sum32(w->scr);
+}
+// out = J_z^T force
+FE_FN void fe_mul_JT(FeWarp* w, float* out) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink, nl = m->nlink, ncon = w->u[0], ne = m->neq;
+  LANES_BEGIN
+    const int l = lane;
+    if (l < nl) {
+      float P[3], Wr[6] = {0, 0, 0, 0, 0, 0};
+      fe_link_ref(w, l, P);
+      for (int c = 0; c < ncon; ++c) {
+        if (w->c_state[c] == 0) continue;
+        const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+        if (A != l && B != l) continue;
+        const float sg = (B == l ? 1.f : 0.f) - (A == l ? 1.f : 0.f);
+        if (sg == 0.f) continue;
+        const float* F = w->c_frame + 9 * c;
+        const float *f = w->c_f + 3 * c;
+        float fw[3] = {F[0] * f[0] + F[3] * f[1] + F[6] * f[2], F[1] * f[0] + F[4] * f[1] + F[7] * f[2], F[2] * f[0] + F[5] * f[1] + F[8] * f[2]};
+        float r[3], t[3];
+        v3sub(r, w->c_pos + 3 * c, P);
+        v3cross(t, r, fw);
+        Wr[0] += sg * t[0]; Wr[1] += sg * t[1]; Wr[2] += sg * t[2]; Wr[3] += sg * fw[0]; Wr[4] += sg * fw[1]; Wr[5] += sg * fw[2];
+      }
+      for (int e = 0; e < ne; ++e) {
+        if (!w->eq_active[e]) continue;
+        const int A = m->eq_link1[e], B = m->eq_link2[e];
+        if (A != l && B != l) continue;
+        const float* f = w->w_f + 6 * e;
+        float tq[3], t[3];
+        m3tmulv(tq, w->w_G + 9 * e, f + 3); // G^T f_rot
+        if (A == l) {
+          v3cross(t, w->w_r1 + 3 * e, f);
+          Wr[0] += t[0] + tq[0]; Wr[1] += t[1] + tq[1]; Wr[2] += t[2] + tq[2]; Wr[3] += f[0]; Wr[4] += f[1]; Wr[5] += f[2];
+        } else {
+          Wr[0] -= tq[0]; Wr[1] -= tq[1]; Wr[2] -= tq[2]; Wr[3] -= f[0]; Wr[4] -= f[1]; Wr[5] -= f[2];
+        }
+      }
+      for (int k = 0; k < 6; ++k) w->lacc2[6 * l + k] = Wr[k];
+      if (l >= nrl) for (int k = 0; k < 6; ++k) out[nr + 6 * (l - nrl) + k] = Wr[k];
+    }
+  LANES_END
+  LANES_BEGIN
+    for (int d = lane; d < nr; d += 32) {
+      float s = w->l_sign[d] * w->l_f[d];
+      for (int l = d; l < nrl; ++l)
+        if ((m->link_ancmask[l] >> d) & 1) s += dot6(w->S + 6 * d, w->lacc2 + 6 * l);
+      out[d] = s;
+    }
+  LANES_END
+}
+
+// one 1-D cost evaluation along the search direction: returns p'(alpha), p''(alpha) (uniform)
+FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, float* d2) {
+  const fe_model* m = w->m;
+  const int ncon = w->u[0], ne = m->neq, nr = m->nr;
+  LANES_BEGIN
+    float p1 = 0.f, p2 = 0.f;
+    for (int c = lane; c < ncon; c += 32) {
+      const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
+      const float v0 = w->c_jv[3 * c], v1 = w->c_jv[3 * c + 1], v2 = w->c_jv[3 * c + 2];
+      const float x0 = w->c_jar[3 * c] + alpha * v0, x1 = w->c_jar[3 * c + 1] + alpha * v1, x2 = w->c_jar[3 * c + 2] + alpha * v2;
+      const float N = x0 * mu, U1 = x1 * fr, U2 = x2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+      if (N >= mu * T || (T <= 0.f && N >= 0.f)) {
+      } else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+        p1 += D0 * x0 * v0 + D1 * (x1 * v1 + x2 * v2);
+        p2 += D0 * v0 * v0 + D1 * (v1 * v1 + v2 * v2);
+      } else {
+        const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+        const float N1 = v0 * mu, V1 = v1 * fr, V2 = v2 * fr;
+        const float T1 = (U1 * V1 + U2 * V2) / T, T2 = (V1 * V1 + V2 * V2 - T1 * T1) / T, a = N1 - mu * T1;
+        p1 += Dm * NmT * a;
+        p2 += Dm * (a * a - NmT * mu * T2);
+      }
+    }
+    for (int e = lane; e < ne; e += 32) {
+      if (!w->eq_active[e]) continue;
+      for (int k = 0; k < 6; ++k) {
+        const float D = w->w_D[6 * e + k], v = w->w_jv[6 * e + k], x = w->w_jar[6 * e + k] + alpha * v;
+        p1 += D * x * v; p2 += D * v * v;
+      }
+    }
+    for (int d = lane; d < nr; d += 32) {
+      if (w->l_sign[d] == 0.f) continue;
+      const float v = w->l_jv[d], x = w->l_jar[d] + alpha * v;
+      if (x < 0.f) { p1 += w->l_D[d] * x * v; p2 += w->l_D[d] * v * v; }
+    }
+    w->scr[lane] = p1; w->scr[32 + lane] = p2;
+  LANES_END
+  *d1 = fe_sum32(w->scr) + g1 + 2.f * alpha * g2;
+  *d2 = fe_sum32(w->scr + 32) + 2.f * g2;
+}
+
+// H = M_z + J^T W J  (packed lower, skyline first[])
+FE_FN void fe_build_H(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink, np = m->npart, nv = m->nv, ncon = w->u[0], ne = m->neq;
+  // envelope: a part row starts at its own block unless it is coupled to the robot or to a lower part
+  LANES_BEGIN
+    for (int d = lane; d < nr; d += 32) w->first[d] = 0;
+    for (int p = lane; p < np; p += 32) {
+      const int l = nrl + p;
+      int f = nr + 6 * p;
+      for (int c = 0; c < ncon; ++c) {
+        if (w->c_state[c] == 0) continue;
+        const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+        int o = -2;
+        if (A == l) o = B; else if (B == l) o = A;
+        if (o < 0) continue;
+        const int fo = o < nrl ? 0 : nr + 6 * (o - nrl);
+        if (fo < f) f = fo;
+      }
+      for (int e = 0; e < ne; ++e) {
+        if (!w->eq_active[e]) continue;
+        const int A = m->eq_link1[e], B = m->eq_link2[e];
+        int o = -1;
+        if (A == l) o = B; else if (B == l) o = A;
+        if (o < 0) continue;
+        const int fo = nr + 6 * (o - nrl);
+        if (fo < f) f = fo;
+      }
+      for (int k = 0; k < 6; ++k) w->first[nr + 6 * p + k] = f;
+    }
+  LANES_END
+  // M_z inside the envelope
+  LANES_BEGIN
+    for (int i = lane; i < nv; i += 32) {
+      float* Hi = w->H + fe_tri(i);
+      for (int j = w->first[i]; j <= i; ++j) Hi[j] = 0.f;
+      if (i < nr) { for (int j = 0; j <= i; ++j) Hi[j] = w->Mr[i * nr + j]; if (w->l_sign[i] != 0.f && w->l_jar[i] < 0.f) Hi[i] += w->l_D[i]; }
+      else {
+        const int p = (i - nr) / 6, r = (i - nr) % 6;
+        float A[21];
+        fe_inert_sym6(A, w->linert + 10 * (nrl + p), 0.f);
+        for (int c = 0; c <= r; ++c) Hi[nr + 6 * p + c] = A[fe_tri(r) + c];
+      }
+    }
+  LANES_END
+  // contacts, one at a time: dof-space rows staged in Jc (3 x ncols), then the ncols x ncols outer product
+  for (int c = 0; c < ncon; ++c) {
+    const int st = w->c_state[c];
+    if (st == 0) continue;
+    const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+    const bool robot = (A >= 0 && A < nrl) || (B >= 0 && B < nrl);
+    const int partA = A >= nrl ? A - nrl : -1, partB = B >= nrl ? B - nrl : -1;
+    const int ncols = (robot ? nr : 0) + (partA >= 0 ? 6 : 0) + (partB >= 0 ? 6 : 0);
+    // 3x3 weight: diag(D) in the quadratic zone, cone Hessian in the middle zone
+    float W[9];
+    {
+      const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
+      if (st == 1) { W[0] = D0; W[4] = D1; W[8] = D1; W[1] = W[2] = W[3] = W[5] = W[6] = W[7] = 0.f; }
+      else {
+        const float N = w->c_jar[3 * c] * mu, U[3] = {N, w->c_jar[3 * c + 1] * fr, w->c_jar[3 * c + 2] * fr};
+        const float T = sqrtf(U[1] * U[1] + U[2] * U[2]), Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+        const float sc[3] = {mu, fr, fr};
+        float HU[9];
+        HU[0] = Dm;
+        for (int a = 1; a < 3; ++a) HU[a] = HU[3 * a] = -Dm * mu * U[a] / T;
+        for (int a = 1; a < 3; ++a)
+          for (int b = 1; b < 3; ++b) HU[3 * a + b] = Dm * mu * mu * U[a] * U[b] / (T * T) - Dm * NmT * mu * ((a == b ? 1.f : 0.f) / T - U[a] * U[b] / (T * T * T));
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) W[3 * a + b] = sc[a] * HU[3 * a + b] * sc[b];
+      }
+    }
+    LANES_BEGIN
+      const int j = lane;
+      if (j < ncols) {
+        const float* F = w->c_frame + 9 * c;
+        const float* p = w->c_pos + 3 * c;
+        float col[3] = {0.f, 0.f, 0.f};
+        int z;
+        int jj = j;
+        if (robot && jj < nr) {
+          z = jj;
+          const float sg = ((B >= 0 && B < nrl && ((m->link_ancmask[B] >> jj) & 1)) ? 1.f : 0.f) - ((A >= 0 && A < nrl && ((m->link_ancmask[A] >> jj) & 1)) ? 1.f : 0.f);
+          if (sg != 0.f) {
+            float r[3], t[3], v[3];
+            v3sub(r, p, m->robot_ref);
+            v3cross(t, w->S + 6 * jj, r);
+            v3add(v, w->S + 6 * jj + 3, t);
+            for (int k = 0; k < 3; ++k) col[k] = sg * v3dot(F + 3 * k, v);
+          }
+        } else {
+          if (robot) jj -= nr;
+          int part; float sg;
+          if (partA >= 0 && jj < 6) { part = partA; sg = -1.f; } else { if (partA >= 0) jj -= 6; part = partB; sg = 1.f; }
+          z = nr + 6 * part + jj;
+          float r[3];
+          v3sub(r, p, w->lpos + 3 * (nrl + part));
+          for (int k = 0; k < 3; ++k) {
+            if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * t[jj]; }
+            else col[k] = sg * F[3 * k + (jj - 3)];
+          }
+        }
+        w->Jc[j] = col[0]; w->Jc[32 + j] = col[1]; w->Jc[64 + j] = col[2];
+        w->colmap[j] = z;
+      }
+    LANES_END
+    LANES_BEGIN
+      for (int e = lane; e < fe_tri(ncols); e += 32) {
+        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        while (fe_tri(i + 1) <= e) ++i;
+        while (fe_tri(i) > e) --i;
+        const int j = e - fe_tri(i);
+        float v = 0.f;
+        for (int a = 0; a < 3; ++a) {
+          const float ja = w->Jc[32 * a + i];
+          if (ja == 0.f) continue;
+          v += ja * (W[3 * a] * w->Jc[j] + W[3 * a + 1] * w->Jc[32 + j] + W[3 * a + 2] * w->Jc[64 + j]);
+        }
+        if (v != 0.f) {
+          int zi = w->colmap[i], zj = w->colmap[j];
+          if (zi < zj) { int t = zi; zi = zj; zj = t; }
+          w->H[fe_tri(zi) + zj] += v;
+        }
+      }
+    LANES_END
+  }
+  // welds: 6 rows over the two parts' 12 columns, diagonal weights
+  for (int e = 0; e < ne; ++e) {
+    if (!w->eq_active[e]) continue;
+    const int A = m->eq_link1[e], B = m->eq_link2[e];
+    for (int half = 0; half < 2; ++half) { // rows 0-2 (translation) then 3-5 (rotation), staged 3 at a time
+      LANES_BEGIN
+        const int j = lane;
+        if (j < 12) {
+          const bool sideA = j < 6;
+          const int jj = sideA ? j : j - 6;
+          float col[3] = {0.f, 0.f, 0.f};
+          if (half == 0) { // v_A + w_A x r1 - v_B
+            if (sideA) {
+              if (jj < 3) { // d/dw_A of (w_A x r1)_k = (e_jj x r1)_k
+                float ej[3] = {jj == 0 ? 1.f : 0.f, jj == 1 ? 1.f : 0.f, jj == 2 ? 1.f : 0.f}, t[3];
+                v3cross(t, ej, w->w_r1 + 3 * e);
+                col[0] = t[0]; col[1] = t[1]; col[2] = t[2];
+              } else col[jj - 3] = 1.f;
+            } else if (jj >= 3) col[jj - 3] = -1.f;
+          } else if (jj < 3) {
+            const float sg = sideA ? 1.f : -1.f;
+            for (int k = 0; k < 3; ++k) col[k] = sg * w->w_G[9 * e + 3 * k + jj];
+          }
+          w->Jc[j] = col[0]; w->Jc[32 + j] = col[1]; w->Jc[64 + j] = col[2];
+          w->colmap[j] = nr + 6 * ((sideA ? A : B) - nrl) + jj;
+        }
+      LANES_END
+      LANES_BEGIN
+        for (int en = lane; en < fe_tri(12); en += 32) {
+          int i = (int)((sqrtf(8.f * (float)en + 1.f) - 1.f) * 0.5f);
+          while (fe_tri(i + 1) <= en) ++i;
+          while (fe_tri(i) > en) --i;
+          const int j = en - fe_tri(i);
+          float v = 0.f;
+          for (int a = 0; a < 3; ++a) v += w->w_D[6 * e + 3 * half + a] * w->Jc[32 * a + i] * w->Jc[32 * a + j];
+          if (v != 0.f) {
+            int zi = w->colmap[i], zj = w->colmap[j];
+            if (zi < zj) { int t = zi; zi = zj; zj = t; }
+            w->H[fe_tri(zi) + zj] += v;
+          }
+        }
+      LANES_END
+    }
+  }
+}
+
+FE_FN void fe_solve(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink, np = m->npart, nv = m->nv, ncon = w->u[0], ne = m->neq;
+  // any constraint at all?
+  LANES_BEGIN
+    int any = (lane == 0 && ncon > 0) ? 1 : 0;
+    for (int e = lane; e < ne; e += 32) any |= w->eq_active[e] != 0;
+    for (int d = lane; d < nr; d += 32) any |= w->l_sign[d] != 0.f;
+    w->iscr[lane] = any;
+    for (int i = lane; i < nv; i += 32) w->fc[i] = 0.f;
+  LANES_END
+  if (fe_ballot32(w->iscr) == 0u) {
+    LANES_BEGIN
+      for (int i = lane; i < nv; i += 32) w->x[i] = w->as[i];
+      if (lane == 0) w->u[3] = 0;
+    LANES_END
+    return;
+  }
+  const float scale = 1.0f / (m->meaninertia * (float)(nv > 1 ? nv : 1));
+  // warm start candidate (stored in qacc coordinates) -> z coordinates; pick the cheaper of warm / smooth
+  float best = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    LANES_BEGIN
+      if (pass == 0) {
+        for (int d = lane; d < nr; d += 32) w->x[d] = w->warm[d];
+        for (int p = lane; p < np; p += 32) {
+          const int da = m->link_dadr[nrl + p], z = nr + 6 * p;
+          m3mulv(w->x + z, w->lmat + 9 * (nrl + p), w->warm + da + 3);
+          v3cpy(w->x + z + 3, w->warm + da);
+        }
+      } else for (int i = lane; i < nv; i += 32) w->search[i] = w->as[i];
+    LANES_END
+    float* cand = pass == 0 ? w->x : w->search;
+    fe_mul_M(w, cand, w->Ma);
+    fe_mul_J(w, cand, w->c_jar, w->w_jar, w->l_jar, true);
+    float cost = fe_update(w);
+    LANES_BEGIN
+      float s = 0.f;
+      for (int i = lane; i < nv; i += 32) s += 0.5f * (w->Ma[i] - w->fs[i]) * (cand[i] - w->as[i]);
+      w->scr[lane] = s;
+    LANES_END
+    cost += fe_sum32(w->scr);
+    if (pass == 0) best = cost;
+    else if (cost < best || !(best == best)) { LANES_BEGIN for (int i = lane; i < nv; i += 32) w->x[i] = w->as[i]; LANES_END }
+    else { // keep the warm start: recompute its products
+      fe_mul_M(w, w->x, w->Ma);
+      fe_mul_J(w, w->x, w->c_jar, w->w_jar, w->l_jar, true);
+    }
+  }
+  int iter = 0;
+  float cost = 0.f, oldcost = 0.f;
+  for (;;) {
+    const float ccost = fe_update(w);
+    fe_mul_JT(w, w->fc);
+    LANES_BEGIN
+      float s = 0.f, gsq = 0.f;
+      for (int i = lane; i < nv; i += 32) {
+        const float r = w->Ma[i] - w->fs[i];
+        s += 0.5f * r * (w->x[i] - w->as[i]);
+        const float gi = r - w->fc[i];
+        w->grad[i] = gi;
+        gsq += gi * gi;
+      }
+      w->scr[lane] = s; w->scr[32 + lane] = gsq;
+    LANES_END
+    const float gauss = fe_sum32(w->scr), gnorm = sqrtf(fe_sum32(w->scr + 32));
+    oldcost = cost;
+    cost = gauss + ccost;
+    if (!(cost == cost)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END break; }
+    if (iter > 0) { if (scale * (oldcost - cost) < w->opt.tolerance || scale * gnorm < w->opt.tolerance) break; }
+    else if (scale * gnorm < w->opt.tolerance) break;
+    if (iter >= w->opt.newton_iters) break;
+    fe_build_H(w);
+    if (!fe_chol(w, w->H, w->first, nv)) { LANES_BEGIN if (lane == 0) w->u[2] |= 4; LANES_END }
+    LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search[i] = -w->grad[i]; LANES_END
+    fe_chol_solve(w, w->H, w->first, nv, w->search, w->Mv);
+    fe_mul_M(w, w->search, w->Mv);
+    fe_mul_J(w, w->search, w->c_jv, w->w_jv, w->l_jv, false);
+    LANES_BEGIN
+      float a = 0.f, b = 0.f;
+      for (int i = lane; i < nv; i += 32) { a += w->search[i] * (w->Ma[i] - w->fs[i]); b += 0.5f * w->search[i] * w->Mv[i]; }
+      w->scr[lane] = a; w->scr[32 + lane] = b;
+    LANES_END
+    const float g1 = fe_sum32(w->scr), g2 = fe_sum32(w->scr + 32);
+    // exact line search: safeguarded Newton on p'(alpha) = 0
+    float p1, p2, lo = 0.f, hi = -1.f, alpha;
+    fe_line_eval(w, 0.f, g1, g2, &p1, &p2);
+    if (!(p1 < 0.f) || !(p2 > 0.f)) break;
+    const float p1_0 = p1;
+    alpha = -p1 / p2;
+    for (int ls = 0; ls < w->opt.ls_iters; ++ls) {
+      fe_line_eval(w, alpha, g1, g2, &p1, &p2);
+      if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
+      if (p1 < 0.f) lo = alpha; else hi = alpha;
+      float next = alpha - p1 / p2;
+      if (hi > 0.f && !(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      if (hi < 0.f && !(next > lo)) next = 2.f * alpha;
+      if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
+      alpha = next;
+    }
+    if (!(alpha > 0.f)) break;
+    LANES_BEGIN
+      for (int i = lane; i < nv; i += 32) { w->x[i] += alpha * w->search[i]; w->Ma[i] += alpha * w->Mv[i]; }
+      for (int c = lane; c < 3 * ncon; c += 32) w->c_jar[c] += alpha * w->c_jv[c];
+      for (int e = lane; e < 6 * ne; e += 32) w->w_jar[e] += alpha * w->w_jv[e];
+      for (int d = lane; d < nr; d += 32) w->l_jar[d] += alpha * w->l_jv[d];
+    LANES_END
+    ++iter;
+  }
+  fe_update(w);
+  fe_mul_JT(w, w->fc);
+  LANES_BEGIN if (lane == 0) w->u[3] = iter; LANES_END
+}
+
+// ---------------------------------------------------------------- mj_Euler + mj_advance
+FE_FN void fe_integrate(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink, np = m->npart;
+  const float h = m->timestep;
+  // robot: (Mr + h B) a = fs + fc
+  if (nr > 0) {
+    LANES_BEGIN
+      for (int e = lane; e < fe_tri(nr); e += 32) {
+        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        while (fe_tri(i + 1) <= e) ++i;
+        while (fe_tri(i) > e) --i;
+        const int j = e - fe_tri(i);
+        w->Lr[e] = w->Mr[i * nr + j] + (i == j ? h * m->dof_damping[i] : 0.f);
+      }
+      for (int d = lane; d < nr; d += 32) { w->grad[d] = w->fs[d] + w->fc[d]; w->first[d] = 0; }
+    LANES_END
+    if (!fe_chol(w, w->Lr, w->first, nr)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END }
+    fe_chol_solve(w, w->Lr, w->first, nr, w->grad, w->Mv);
+  }
+  LANES_BEGIN
+    // warm start for the next step = solver solution, stored in qacc coordinates
+    for (int d = lane; d < nr; d += 32) {
+      w->warm[d] = w->x[d];
+      const float v = w->qvel[d] + h * w->grad[d];
+      w->qvel[d] = v;
+      w->qpos[d] += h * v;
+    }
+    for (int p = lane; p < np; p += 32) {
+      const int l = nrl + p, z = nr + 6 * p, da = m->link_dadr[l], qa = m->link_qadr[l];
+      const float* R = w->lmat + 9 * l;
+      float t[3];
+      m3tmulv(t, R, w->x + z);
+      v3cpy(w->warm + da, w->x + z + 3);
+      v3cpy(w->warm + da + 3, t);
+      float A[21], a[6];
+      fe_inert_sym6(A, w->linert + 10 * l, h * m->dof_damping[da]);
+      if (!fe_chol6(A)) w->u[2] |= 2;
+      for (int k = 0; k < 6; ++k) a[k] = w->fs[z + k] + w->fc[z + k];
+      fe_chol6_solve(A, a);
+      m3tmulv(t, R, a);
+      for (int k = 0; k < 3; ++k) { w->qvel[da + k] += h * a[3 + k]; w->qvel[da + 3 + k] += h * t[k]; }
+      for (int k = 0; k < 3; ++k) w->qpos[qa + k] += h * w->qvel[da + k];
+      float wl[3] = {w->qvel[da + 3], w->qvel[da + 4], w->qvel[da + 5]};
+      const float n = v3norm(wl);
+      float* q = w->qpos + qa + 3;
+      if (n * h > 1e-12f) {
+        const float s = sinf(0.5f * n * h) / n, c = cosf(0.5f * n * h);
+        float dq[4] = {c, wl[0] * s, wl[1] * s, wl[2] * s}, qn[4];
+        qmul(qn, q, dq);
+        q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
+      }
+      qnormalize(q);
+    }
+  LANES_END
+  // divergence guard (mj_checkPos / mj_checkVel): NaN or huge values raise bit 3
+  LANES_BEGIN
+    int bad = 0;
+    for (int i = lane; i < m->nq; i += 32) { float v = w->qpos[i]; if (!(v == v) || fabsf(v) > 1e6f) bad = 1; }
+    for (int i = lane; i < m->nv; i += 32) { float v = w->qvel[i]; if (!(v == v) || fabsf(v) > 1e6f) bad = 1; }
+    w->iscr[lane] = bad;
+  LANES_END
+  if (fe_ballot32(w->iscr) != 0u) { LANES_BEGIN if (lane == 0) w->u[2] |= 8; LANES_END }
+}
+
+FE_FN void fe_forward(FeWarp* w) {
+  fe_kin_smooth(w);
+  fe_collide(w);
+  fe_assemble(w);
+  fe_solve(w);
+}
+FE_FN void fe_substep(FeWarp* w) {
+  fe_forward(w);
+  fe_integrate(w);
+}

@@ -1,0 +1,253 @@
+"""ctypes binding of the C-ABI in include/furniture_b200.h plus the env-level scene table (struct fe_scene).
+
+``Engine`` mirrors the part of ``mujoco_py.MjSim`` the reference touches (forward/step, named data views,
+get/set state) for a whole batch of envs, and the batched FurnitureEnv entry points (reset/step).
+The CUDA library is mandatory: if ``libfurniture_b200.so`` is missing or no CUDA device is present the constructor
+raises -- there is no CPU fallback.  (Tests may pass ``lib_path`` to load the lane-emulated harness build.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import mjcf
+from .engine_model import MAXEQ, MAXPART, MAXRDOF, MAXSITE, MAXU, EngineModel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libfurniture_b200.so")
+MAXCONN = 48
+SCENE_MAGIC = 0x46455343
+INFO_DIM = 6
+i32, f32, f64 = C.c_int32, C.c_float, C.c_double
+
+
+class FeConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("maxcon", i32), ("newton_iters", i32), ("ls_iters", i32), ("tolerance", f32), ("nsub", i32),
+        ("max_episode_steps", i32), ("discrete_grip", i32), ("rescale_actions", i32), ("auto_align", i32),
+        ("alignment_pos_dist", f64), ("alignment_rot_dist_up", f64), ("alignment_rot_dist_forward", f64), ("alignment_project_dist", f64),
+        ("ctrl_penalty_coef", f32), ("unstable_penalty_coef", f32), ("success_reward", f32), ("touch_reward", f32), ("pick_reward", f32),
+        ("furn_xyz_rand", f32), ("furn_rot_rand", f32), ("agent_xyz_rand", f32), ("seed", C.c_uint64),
+    ]
+
+
+class FeScene(C.Structure):
+    _fields_ = [
+        ("magic", i32), ("struct_bytes", i32),
+        ("obs_dim", i32), ("act_dim", i32), ("robot_ob_dim", i32), ("nconn", i32), ("npart", i32), ("narm", i32), ("ngrip", i32),
+        ("act_src", i32 * MAXU), ("act_sign", f32 * MAXU), ("grip_action_index", i32), ("connect_action_index", i32),
+        ("conn_site", i32 * MAXCONN), ("conn_part", i32 * MAXCONN), ("conn_a", i32 * MAXCONN), ("conn_b", i32 * MAXCONN), ("conn_nangles", i32 * MAXCONN),
+        ("conn_cos", (f64 * 4) * MAXCONN), ("conn_sin", (f64 * 4) * MAXCONN),
+        ("eq_part1", i32 * MAXEQ), ("eq_part2", i32 * MAXEQ),
+        ("part_site_start", i32 * (MAXPART + 1)), ("part_sites", i32 * MAXSITE),
+        ("eef_site", i32), ("hand_link", i32), ("hand_quat", f32 * 4),
+        ("robot_init_qpos", f32 * MAXRDOF),
+        ("part_init_pos", (f32 * 3) * MAXPART), ("part_init_quat", (f32 * 4) * MAXPART), ("part_radius", f32 * MAXPART),
+    ]
+
+
+def default_config(**kw):
+    """Reference defaults: config/furniture.py:16-312 (control_freq 10 => 50 mj_steps per env step)."""
+    c = FeConfig()
+    c.struct_bytes = C.sizeof(FeConfig)
+    c.maxcon, c.newton_iters, c.ls_iters, c.tolerance = 48, 8, 12, 1e-6
+    c.nsub, c.max_episode_steps = 50, 2000
+    c.discrete_grip, c.rescale_actions, c.auto_align = 1, 1, 1
+    c.alignment_pos_dist, c.alignment_rot_dist_up, c.alignment_rot_dist_forward, c.alignment_project_dist = 0.1, 0.9, 0.9, 0.3
+    c.ctrl_penalty_coef, c.unstable_penalty_coef, c.success_reward, c.touch_reward, c.pick_reward = 1e-3, 100, 100, 10, 100
+    c.furn_xyz_rand, c.furn_rot_rand, c.agent_xyz_rand = 0.02, 3, 0.001
+    c.seed = 123
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
+    return c
+
+
+def build_scene(m: mjcf.Model, em: EngineModel) -> FeScene:
+    """Integer tables for the connect logic, pre-compiled from the site names, the obs layout and the
+    reset placements."""
+    meta = m.meta
+    sc = FeScene()
+    sc.magic, sc.struct_bytes = SCENE_MAGIC, C.sizeof(FeScene)
+    parts = em.part_names
+    npart = len(parts)
+    narm, ngrip = len(meta.get("robot_joints", [])), len(meta.get("gripper_joints", []))
+    sc.npart, sc.narm, sc.ngrip = npart, narm, ngrip
+    has_robot = narm > 0
+    sc.robot_ob_dim = (2 * narm + ngrip + 3 + 4 + 3 + 3) if has_robot else 0  # furniture_sawyer.py:40
+    sc.obs_dim = 7 * npart + sc.robot_ob_dim
+    sc.act_dim = (narm + 2) if has_robot else 1
+    if has_robot:
+        # Sawyer: 7 arm actions, one gripper action fanned out as [g, -g] (two_finger_gripper.py:67-72)
+        assert m.nu == narm + ngrip
+        for u in range(narm):
+            sc.act_src[u], sc.act_sign[u] = u, 1.0
+        for k in range(ngrip):
+            sc.act_src[narm + k], sc.act_sign[narm + k] = narm, (1.0 if k == 0 else -1.0)
+        sc.grip_action_index, sc.connect_action_index = narm, narm + 1
+        assert list(m.actuator_jntid[:narm]) == list(range(narm))
+        init = np.concatenate([meta["robot_init_qpos"], meta["gripper_init_qpos"]])
+        for d, v in enumerate(init):
+            sc.robot_init_qpos[d] = v
+        sc.eef_site = m.names["site"].index(meta["eef_site"])
+        hb = m.names["body"].index(meta["hand_body"])
+        hl = em.weld_link(hb)
+        kin = mjcf.kinematics_np(m, m.qpos0)
+        lb = em.link_body[hl]
+        sc.hand_link = hl
+        sc.hand_quat[:] = list(mjcf.q_norm(mjcf.q_mul(mjcf.q_conj(kin["xquat"][lb]), kin["xquat"][hb])))
+    else:
+        sc.eef_site, sc.hand_link = -1, -1
+        sc.grip_action_index, sc.connect_action_index = 0, 0
+    # connector sites (name contains "conn_site"), model site-id order
+    names = {}
+    conn = [s for s in range(m.nsite) if "conn_site" in m.names["site"][s]]
+    assert len(conn) <= MAXCONN
+    sc.nconn = len(conn)
+    for i, s in enumerate(conn):
+        nm = m.names["site"][s]
+        pair = nm.split(",")[0].split("-")
+        assert len(pair) == 2, nm
+        a, b = (names.setdefault(x, len(names)) for x in pair)
+        angles = [float(x) for x in nm.split(",")[1:-1] if x]
+        assert len(angles) <= 4
+        sc.conn_site[i], sc.conn_a[i], sc.conn_b[i], sc.conn_nangles[i] = s, a, b, len(angles)
+        sc.conn_part[i] = parts.index(m.names["body"][m.site_bodyid[s]])
+        for k, ang in enumerate(angles):
+            r = ang / 180 * np.pi  # transform_utils.py:743
+            sc.conn_cos[i][k], sc.conn_sin[i][k] = float(np.cos(r)), float(np.sin(r))
+    for e in range(m.neq):
+        sc.eq_part1[e] = parts.index(m.names["body"][m.eq_obj1id[e]])
+        sc.eq_part2[e] = parts.index(m.names["body"][m.eq_obj2id[e]])
+    k = 0
+    for p, name in enumerate(parts):
+        sc.part_site_start[p] = k
+        b = m.names["body"].index(name)
+        for s in range(m.nsite):
+            if m.site_bodyid[s] == b:
+                sc.part_sites[k] = s
+                k += 1
+        q = meta.get("part_init_qpos", {}).get(name)
+        if q is None:
+            q = np.concatenate([m.body_pos[b], m.body_quat[b]])
+        sc.part_init_pos[p][:] = list(q[:3])
+        sc.part_init_quat[p][:] = list(q[3:7])
+        sc.part_radius[p] = meta.get("part_radius", {}).get(name, 0.0)
+    sc.part_site_start[npart] = k
+    return sc
+
+
+class Engine:
+    def __init__(self, model: mjcf.Model, n_envs: int, device: int = 0, config: FeConfig | None = None, lib_path: str | None = None):
+        path = lib_path or DEFAULT_LIB
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "furniture_b200: CUDA extension %s not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback" % path
+            )
+        L = C.CDLL(path)
+        self.L = L
+        L.fe_last_error.restype = C.c_char_p
+        L.fe_last_error.argtypes = [C.c_void_p]
+        for f in ("fe_model_sizeof", "fe_scene_sizeof", "fe_config_sizeof"):
+            getattr(L, f).restype = C.c_size_t
+        L.fe_obs_dev.restype = C.c_void_p
+        L.fe_obs_dev.argtypes = [C.c_void_p]
+        self.is_cuda = bool(L.fe_is_cuda())
+        if lib_path is None and not self.is_cuda:
+            raise RuntimeError("furniture_b200: default library is not a CUDA build")
+        self.model = model
+        self.em = EngineModel(model)
+        self.scene = build_scene(model, self.em)
+        self.cfg = config or default_config()
+        for fn, cls in (("fe_model_sizeof", type(self.em.fm)), ("fe_scene_sizeof", FeScene), ("fe_config_sizeof", FeConfig)):
+            if getattr(L, fn)() != C.sizeof(cls):
+                raise RuntimeError("furniture_b200: %s = %d but python layout has %d bytes" % (fn, getattr(L, fn)(), C.sizeof(cls)))
+        self.h = C.c_void_p()
+        rc = L.fe_create(C.byref(self.em.fm), C.c_size_t(C.sizeof(self.em.fm)), C.byref(self.scene), C.c_size_t(C.sizeof(self.scene)), C.byref(self.cfg),
+                         int(n_envs), int(device), C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("fe_create failed (%d): %s" % (rc, L.fe_last_error(None).decode()))
+        self.N = int(n_envs)
+        self.obs_dim, self.act_dim = self.scene.obs_dim, self.scene.act_dim
+        for f in ("fe_env_reset", "fe_env_step"):
+            getattr(L, f).argtypes = None
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.fe_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("furniture_b200 error %d: %s" % (rc, self.L.fe_last_error(self.h).decode()))
+
+    # ---- simulator surface
+    def field_info(self, name):
+        d, e = C.c_int(), C.c_int()
+        self._chk(self.L.fe_field_dim(self.h, name.encode(), C.byref(d), C.byref(e)))
+        return d.value, e.value
+
+    _INT = {"geom_contype", "geom_conaffinity", "eq_active", "touch", "flags", "ncon", "niter", "con_geom", "con_state", "group", "site_connected",
+            "num_connected", "prev_num_connected", "touched", "picked", "episode_length", "done"}
+
+    def get(self, name):
+        dim, eb = self.field_info(name)
+        dt = np.uint64 if eb == 8 else (np.int32 if name in self._INT else np.float32)
+        out = np.empty((self.N, dim), dtype=dt)
+        self._chk(self.L.fe_get_field(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
+        return out
+
+    def set(self, name, value):
+        dim, eb = self.field_info(name)
+        dt = np.uint64 if eb == 8 else (np.int32 if name in self._INT else np.float32)
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), (self.N, dim)))
+        self._chk(self.L.fe_set_field(self.h, name.encode(), v.ctypes.data_as(C.c_void_p), C.c_size_t(v.nbytes)))
+
+    def forward(self, stream=None):
+        self._chk(self.L.fe_sim_forward(self.h, C.c_void_p(stream or 0)))
+
+    def step(self, nsub=1, stream=None):
+        self._chk(self.L.fe_sim_step(self.h, int(nsub), C.c_void_p(stream or 0)))
+
+    # ---- env surface with host buffers (numpy); torch-tensor variants live in furniture_b200/env.py
+    def env_reset(self, mask_dev=None, obs_dev=None, stream=None):
+        self._chk(self.L.fe_env_reset(self.h, C.c_void_p(mask_dev or 0), C.c_void_p(obs_dev or 0), C.c_void_p(stream or 0)))
+
+    def env_step_dev(self, actions_dev, obs_dev, reward_dev, done_dev, info_dev, stream=None):
+        self._chk(self.L.fe_env_step(self.h, C.c_void_p(actions_dev), C.c_void_p(obs_dev or 0), C.c_void_p(reward_dev or 0), C.c_void_p(done_dev or 0),
+                                     C.c_void_p(info_dev or 0), C.c_void_p(stream or 0)))
+
+    def env_step_host(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        assert a.shape == (self.N, self.act_dim), a.shape
+        obs = np.empty((self.N, self.obs_dim), np.float32)
+        rew = np.empty(self.N, np.float32)
+        done = np.empty(self.N, np.uint8)
+        info = np.empty((self.N, INFO_DIM), np.int32)
+        self._chk(self.L.fe_env_step_host(self.h, a.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p), rew.ctypes.data_as(C.c_void_p),
+                                          done.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p)))
+        return obs, rew, done, info
+
+    def obs_dev_ptr(self):
+        return self.L.fe_obs_dev(self.h)
+
+    def is_aligned(self, p1, m1, p2, m2, angles, nangles, thr):
+        n = len(p1)
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (p1, m1, p2, m2, angles, thr)]
+        na = np.ascontiguousarray(nangles, dtype=np.int32)
+        al = np.empty(n, np.uint8)
+        tq = np.empty((n, 4), np.float64)
+        self._chk(self.L.fe_is_aligned(self.h, n, arrs[0].ctypes.data_as(C.c_void_p), arrs[1].ctypes.data_as(C.c_void_p), arrs[2].ctypes.data_as(C.c_void_p),
+                                       arrs[3].ctypes.data_as(C.c_void_p), arrs[4].ctypes.data_as(C.c_void_p), na.ctypes.data_as(C.c_void_p),
+                                       arrs[5].ctypes.data_as(C.c_void_p), al.ctypes.data_as(C.c_void_p), tq.ctypes.data_as(C.c_void_p)))
+        return al.astype(bool), tq

@@ -1,0 +1,94 @@
+/* furniture_b200.h -- C-ABI of the B200-native batched physics backend.
+ *
+ * The reference has no FFI seam of its own: FurnitureEnv drives the closed MuJoCo 2.0 binary through mujoco-py
+ * (SURVEY.md 8b-B2).  This header is the seam a maintainer would bind instead; every entry point names the
+ * reference call it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ *   fe_create        <- load_model_from_xml + MjSim(model)          furniture/env/models/base.py:113-115, furniture.py:1837-1838
+ *   fe_sim_forward   <- sim.forward()   (17 call sites, e.g.)        furniture/env/furniture.py:2877
+ *   fe_sim_step      <- sim.step()      (12 call sites, e.g.)        furniture/env/furniture.py:2878-2879
+ *   fe_set_field/fe_get_field <- sim.data.* / sim.model.* views     furniture.py:1622-1627, :2784-2800, :875-878, :2772-2775
+ *   fe_get_state/fe_set_state <- get_env_state / set_env_state      furniture/env/furniture.py:1781-1803, :3095-3105
+ *   fe_env_reset     <- FurnitureEnv.reset() -> _reset()             furniture/env/furniture.py:318-334, :1406-1663
+ *   fe_env_step      <- FurnitureEnv.step() (incl. _step_continuous, _try_connect/_is_aligned/_connect, _get_obs,
+ *                       _compute_reward, _after_step; VecEnv auto-reset) furniture.py:364-385, :405-449, :1260-1330,
+ *                       :926-1153, :847-924, furniture_sawyer.py:66-155, util/subproc_vec_env.py:16-20
+ *   fe_is_aligned    <- FurnitureEnv._is_aligned on explicit site poses (test hook)  furniture.py:1057-1153
+ *
+ * Conventions: every function returns 0 on success or a negative code and records a message retrievable with
+ * fe_last_error(); a handle is bound to one CUDA device, is not thread-safe, and all work is issued on the stream
+ * passed in (NULL = default stream).  "dev" pointers are device memory, "host" pointers are host memory.  All
+ * per-env arrays at the boundary are env-major and contiguous: (n_envs, dim).
+ */
+#ifndef FURNITURE_B200_H
+#define FURNITURE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fe_handle fe_handle;
+
+typedef struct fe_config {
+  int32_t struct_bytes;      /* sizeof(fe_config), checked */
+  int32_t maxcon;            /* contact capacity per env (MuJoCo: nconmax, base.xml:5) */
+  int32_t newton_iters;      /* max Newton iterations per mj_step (MuJoCo default 100) */
+  int32_t ls_iters;          /* max line-search evaluations per Newton iteration */
+  float tolerance;           /* solver tolerance on scaled improvement / gradient (MuJoCo: 1e-8 in double) */
+  int32_t nsub;              /* mj_steps per env step = int(control_timestep / model_timestep), furniture.py:2878 */
+  int32_t max_episode_steps; /* config/furniture.py:164 */
+  int32_t discrete_grip, rescale_actions, auto_align; /* config/furniture.py:75, :90, :96 */
+  double alignment_pos_dist, alignment_rot_dist_up, alignment_rot_dist_forward, alignment_project_dist; /* :203-226 */
+  float ctrl_penalty_coef, unstable_penalty_coef, success_reward, touch_reward, pick_reward;            /* :291-295 */
+  float furn_xyz_rand, furn_rot_rand, agent_xyz_rand; /* :177-194 */
+  uint64_t seed;             /* per-env streams are derived from seed + env index (env/base.py:77) */
+} fe_config;
+
+/* sizes of the blobs the host packs (furniture_b200/engine_model.py, furniture_b200/scene.py) */
+size_t fe_model_sizeof(void);
+size_t fe_scene_sizeof(void);
+size_t fe_config_sizeof(void);
+/* 1 if this library drives a CUDA device, 0 for the lane-emulated test build (never shipped) */
+int fe_is_cuda(void);
+
+int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob, size_t scene_bytes, const fe_config* cfg, int n_envs,
+              int device, fe_handle** out);
+void fe_destroy(fe_handle* h);
+const char* fe_last_error(const fe_handle* h); /* h may be NULL: last creation error */
+
+int fe_num_envs(const fe_handle* h);
+int fe_obs_dim(const fe_handle* h);    /* robot_ob (29 for Sawyer impedance) + object_ob (7 per part) */
+int fe_action_dim(const fe_handle* h); /* dof: 7 joint velocities + gripper + connect for Sawyer impedance */
+int fe_info_dim(const fe_handle* h);   /* int32 per env: num_connected, success, unstable, episode_length, ncon, solver iters */
+
+/* ---- simulator surface (MjSim) */
+int fe_sim_forward(fe_handle* h, void* stream);
+int fe_sim_step(fe_handle* h, int nsub, void* stream);
+/* named per-env arrays, host side; bytes must equal n_envs * dim * sizeof(elem). Names: qpos qvel ctrl qfrc_applied
+   qacc_warmstart gravcomp eq_data eq_active geom_contype geom_conaffinity (read/write); qfrc_bias link_xpos link_xquat
+   link_xmat link_vel touch ncon niter flags + the debug fields of the last fe_sim_forward (read only) */
+int fe_get_field(fe_handle* h, const char* name, void* dst_host, size_t bytes);
+int fe_set_field(fe_handle* h, const char* name, const void* src_host, size_t bytes);
+int fe_field_dim(fe_handle* h, const char* name, int* dim, int* elem_bytes);
+int fe_get_state(fe_handle* h, float* qpos_host, float* qvel_host);
+int fe_set_state(fe_handle* h, const float* qpos_host, const float* qvel_host);
+
+/* ---- environment surface (FurnitureEnv / VecEnv) */
+int fe_env_reset(fe_handle* h, const uint8_t* env_mask_dev /* NULL = all */, float* obs_dev, void* stream);
+int fe_env_step(fe_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, int32_t* info_dev,
+                void* stream);
+/* same call with host buffers: H2D of the actions and D2H of the results happen inside (pinned staging) */
+int fe_env_step_host(fe_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host, int32_t* info_host);
+/* device pointer of the internal obs buffer after the last step/reset: (n_envs, obs_dim) float32 */
+const float* fe_obs_dev(const fe_handle* h);
+
+/* ---- test hook: the device _is_aligned on explicit site poses (float64), n independent cases */
+int fe_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles /* (n,4) */,
+                  const int32_t* nangles, const double* thr /* (n,4) */, uint8_t* aligned_host, double* target_quat_host /* (n,4) wxyz, NaN if unset */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
