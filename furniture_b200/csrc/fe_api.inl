@@ -89,8 +89,8 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   }
   h->N = n_envs; h->device = device; h->cfg = *cfg;
   h->opt.maxcon = cfg->maxcon > 0 ? cfg->maxcon : 48;
-  h->opt.newton_iters = cfg->newton_iters > 0 ? cfg->newton_iters : 8;
-  h->opt.ls_iters = cfg->ls_iters > 0 ? cfg->ls_iters : 12;
+  h->opt.newton_iters = cfg->newton_iters > 0 ? cfg->newton_iters : 30;
+  h->opt.ls_iters = cfg->ls_iters > 0 ? cfg->ls_iters : 20;
   h->opt.tolerance = cfg->tolerance > 0 ? cfg->tolerance : 1e-6f;
   if (h->opt.maxcon > 255) { delete h; return fail(nullptr, -1, "fe_create: maxcon must be <= 255"); }
   if (h->hm.ngeom > 255) { delete h; return fail(nullptr, -1, "fe_create: ngeom must be <= 255"); }

@@ -1041,7 +1041,7 @@ FE_FN void fe_solve(FeWarp* w) {
     }
   }
   int iter = 0;
-  float cost = 0.f, oldcost = 0.f;
+  float cost = 0.f, impr = 0.f;
   for (;;) {
     const float ccost = fe_update(w);
     fe_mul_JT(w, w->fc);
@@ -1057,10 +1057,11 @@ FE_FN void fe_solve(FeWarp* w) {
       w->scr[lane] = s; w->scr[32 + lane] = gsq;
     LANES_END
     const float gauss = fe_sum32(w->scr), gnorm = sqrtf(fe_sum32(w->scr + 32));
-    oldcost = cost;
     cost = gauss + ccost;
     if (!(cost == cost)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END break; }
-    if (iter > 0) { if (scale * (oldcost - cost) < w->opt.tolerance || scale * gnorm < w->opt.tolerance) break; }
+    // MuJoCo stops on scale*(oldcost - cost) < tol; in fp32 that difference of two large costs is round-off, so the
+    // improvement is taken from the line search instead: -alpha p'(0) / 2 (exact for a quadratic, the Newton decrement)
+    if (iter > 0) { if (scale * impr < w->opt.tolerance || scale * gnorm < w->opt.tolerance) break; }
     else if (scale * gnorm < w->opt.tolerance) break;
     if (iter >= w->opt.newton_iters) break;
     fe_build_H(w);
@@ -1092,6 +1093,7 @@ FE_FN void fe_solve(FeWarp* w) {
       alpha = next;
     }
     if (!(alpha > 0.f)) break;
+    impr = -0.5f * alpha * p1_0;
     LANES_BEGIN
       for (int i = lane; i < nv; i += 32) { w->x[i] += alpha * w->search[i]; w->Ma[i] += alpha * w->Mv[i]; }
       for (int c = lane; c < 3 * ncon; c += 32) w->c_jar[c] += alpha * w->c_jv[c];

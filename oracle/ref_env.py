@@ -1,0 +1,329 @@
+"""CPU ORACLE of the env layer (TEST INFRASTRUCTURE, NOT PRODUCT CODE): a single-env restatement of
+FurnitureSawyerEnv (control_type="impedance") on top of the C physics oracle.
+
+Restates, with reference line cites:
+  reset      FurnitureEnv._reset                      furniture/env/furniture.py:1406-1663
+  step       FurnitureEnv.step/_step/_step_continuous  :364-449, :1260-1330;  FurnitureSawyerEnv._step  furniture_sawyer.py:66-84
+  action     _setup_action                             :3332-3379
+  connect    _try_connect / _is_aligned / _connect     :926-1153, :847-924  (assembly_oracle.py)
+  obs        _get_obs                                  :1344-1387, furniture_sawyer.py:103-155
+  reward     _compute_reward / _after_step             :482-541, :451-480
+Used as the checker for the device env kernels and as the CPU arm of bench.py (`--impl reference`, cpu_baseline).
+Random draws use numpy's RandomState(seed) like the reference (furniture.py:72) but the engine uses its own per-env
+counter RNG, so resets are compared in distribution, not draw by draw.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import assembly_oracle as A
+from .oracle import OracleSim
+
+
+class Cfg:
+    control_freq = 10
+    max_episode_steps = 2000
+    discrete_grip = True
+    rescale_actions = True
+    auto_align = True
+    alignment_pos_dist, alignment_rot_dist_up, alignment_rot_dist_forward, alignment_project_dist = 0.1, 0.9, 0.9, 0.3
+    ctrl_penalty_coef, unstable_penalty_coef, success_reward, touch_reward, pick_reward = 1e-3, 100.0, 100.0, 10.0, 100.0
+    furn_xyz_rand, furn_rot_rand, agent_xyz_rand = 0.02, 3.0, 0.001
+    seed = 123
+
+
+class OracleFurnitureEnv:
+    def __init__(self, model, cfg=None):
+        self.m = model
+        self.cfg = cfg or Cfg()
+        self.sim = OracleSim(model)
+        meta = model.meta
+        self.parts = list(meta["part_names"])
+        self.npart = len(self.parts)
+        self.part_body = [model.names["body"].index(n) for n in self.parts]
+        self.part_qadr = [int(model.jnt_qposadr[model.names["jnt"].index(n)]) for n in self.parts]
+        self.part_dadr = [int(model.jnt_dofadr[model.names["jnt"].index(n)]) for n in self.parts]
+        self.narm, self.ngrip = len(meta["robot_joints"]), len(meta["gripper_joints"])
+        self.nr = self.narm + self.ngrip
+        self.dof = self.narm + 2
+        self.rng = np.random.RandomState(self.cfg.seed)
+        g = model.names["geom"]
+        self.lf = [g.index(n) for n in meta["l_finger_geoms"]]
+        self.rf = [g.index(n) for n in meta["r_finger_geoms"]]
+        self.floor = g.index("FLOOR")
+        self.robot_geoms = [i for i, n in enumerate(g) if n in set(meta["robot_contact_geoms"])]
+        self.part_col_geoms = [i for i, n in enumerate(g) if "collision" in n and model.names["body"][model.geom_bodyid[i]] in self.parts]
+        self.conn_sites = [s for s, n in enumerate(model.names["site"]) if "conn_site" in n]
+        self.eef_site = model.names["site"].index(meta["eef_site"])
+        self.hand_body = model.names["body"].index(meta["hand_body"])
+        self.nsub = int((1.0 / self.cfg.control_freq) / model.opt_timestep)
+        self.group = list(range(self.npart))
+        self.connected_sites = set()
+        self.num_connected = 0
+
+    # ---- helpers
+    def _find(self, i):
+        while self.group[i] != i:
+            i = self.group[i]
+        return i
+
+    def _part_of_body(self, b):
+        return self.part_body.index(b)
+
+    def _qpos(self, p):
+        return self.sim.qpos[self.part_qadr[p] : self.part_qadr[p] + 7].copy()
+
+    def _set_qpos(self, p, pos, quat):
+        self.sim.qpos[self.part_qadr[p] : self.part_qadr[p] + 3] = pos
+        self.sim.qpos[self.part_qadr[p] + 3 : self.part_qadr[p] + 7] = quat
+
+    def _stop(self, p, gravity):  # furniture.py:2778-2800
+        b = self.part_body[p]
+        self.sim.xfrc_applied[6 * b : 6 * b + 6] = [0, 0, -gravity * self.m.opt_gravity[2] * self.m.body_mass[b], 0, 0, 0]
+        self.sim.qvel[self.part_dadr[p] : self.part_dadr[p] + 6] = 0
+        self.sim.qfrc_applied[self.part_dadr[p] : self.part_dadr[p] + 6] = 0
+
+    def _slow(self, p):  # :2821-2842
+        b = self.part_body[p]
+        self.sim.xfrc_applied[6 * b : 6 * b + 6] = [0, 0, -self.m.opt_gravity[2] * self.m.body_mass[b], 0, 0, 0]
+        d = self.part_dadr[p]
+        self.sim.qvel[d : d + 6] = np.clip(self.sim.qvel[d : d + 6], -0.2, 0.2)
+        self.sim.qfrc_applied[d : d + 6] = 0
+
+    def _fwd_step(self):
+        self.sim.forward()
+        self.sim.step()
+
+    def _grav_comp(self):  # :3372-3377
+        self.sim.qfrc_applied[: self.nr] = self.sim.qfrc_bias[: self.nr]
+
+    def _init_robot(self):  # :1761-1779
+        noise = self.rng.uniform(-self.cfg.agent_xyz_rand, self.cfg.agent_xyz_rand, self.narm)
+        self.sim.qpos[: self.narm] = self.m.meta["robot_init_qpos"] + noise
+        self.sim.qpos[self.narm : self.nr] = self.m.meta["gripper_init_qpos"]
+
+    def _site_pose(self, s):  # _site_xpos_xquat :1044-1055
+        b = self.m.site_bodyid[s]
+        bq = self.sim.xquat[4 * b : 4 * b + 4]
+        return np.hstack([self.sim.site_xpos[3 * s : 3 * s + 3], A._qmul(bq, self.m.site_quat[s])])
+
+    # ---- reset
+    def reset(self):
+        sim, m, cfg = self.sim, self.m, self.cfg
+        sim.reset()
+        saved = {g: (sim.geom_contype[g], sim.geom_conaffinity[g]) for g in self.robot_geoms}
+        for g in self.robot_geoms:
+            sim.geom_contype[g] = 0; sim.geom_conaffinity[g] = 0
+        for g in self.part_col_geoms:
+            sim.geom_contype[g] = 1; sim.geom_conaffinity[g] = 1
+        self.group = list(range(self.npart))
+        self.connected_sites = set()
+        self.num_connected = self.prev_num_connected = 0
+        self.touched = [False] * self.npart
+        self.picked = [False] * self.npart
+        sim.eq_active[:] = 0
+        placed = []
+        for p, name in enumerate(self.parts):  # placement_sampler.py:137-190
+            init = m.meta["part_init_qpos"][name]
+            r = m.meta["part_radius"][name]
+            for _ in range(10000):
+                x = init[0] + self.rng.uniform(-cfg.furn_xyz_rand, cfg.furn_xyz_rand)
+                y = init[1] + self.rng.uniform(-cfg.furn_xyz_rand, cfg.furn_xyz_rand)
+                if all(np.hypot(x - px, y - py) > pr + r for px, py, pr in placed):
+                    break
+            self.rng.uniform(cfg.furn_rot_rand, cfg.furn_rot_rand)  # sample_quat draws uniform(high=max, low=max)
+            quat = A.euler_to_quat([cfg.furn_rot_rand, 0, 0], init[3:7])
+            placed.append((x, y, r))
+            self._set_qpos(p, [x, y, init[2] + 0.01], quat)
+        for _ in range(10):
+            for p in range(self.npart):
+                self._stop(p, 0)
+            for _ in range(10):
+                self._fwd_step()
+                for p in range(self.npart):
+                    self._slow(p)
+        self._grav_comp()
+        self._init_robot()
+        self._fwd_step()
+        for g, (ct, ca) in saved.items():
+            sim.geom_contype[g] = ct; sim.geom_conaffinity[g] = ca
+        self._grav_comp()
+        for _ in range(100):
+            self._init_robot()
+            self._fwd_step()
+        sim.ctrl[:] = 0; sim.qfrc_applied[:] = 0; sim.xfrc_applied[:] = 0; sim.qacc[:] = 0; sim.qacc_warmstart[:] = 0
+        sim.forward()
+        self._grav_comp()
+        for _ in range(100):
+            self._fwd_step()
+        self.episode_len = 0
+        self.connected_body1 = None
+        return self.obs()
+
+    # ---- step
+    def touch_bits(self):
+        bits = [0] * self.npart
+        for c in self.sim.contacts():
+            for ga, gb in ((c.geom1, c.geom2), (c.geom2, c.geom1)):
+                b = self.m.geom_bodyid[gb]
+                if b in self.part_body:
+                    p = self.part_body.index(b)
+                    bits[p] |= (1 if ga in self.lf else 0) | (2 if ga in self.rf else 0) | (4 if ga == self.floor else 0)
+        return bits
+
+    def _move_group(self, obj, translation, target_quat, gravity=0):  # :1163-1176
+        base = self._qpos(obj)
+        g = self._find(obj)
+        for i in range(self.npart):
+            if self._find(i) == g:
+                npos, nq = A.transform_to_target_quat(base, self._qpos(i), np.asarray(target_quat, dtype=np.float64))
+                self._set_qpos(i, npos + translation, nq)
+                self._stop(i, gravity)
+
+    def _group_min_z(self, obj):  # _get_bounding_box :749-769 (min starts at 0)
+        g = self._find(obj)
+        mn = 0.0
+        for i in range(self.npart):
+            if self._find(i) == g:
+                for s in range(self.m.nsite):
+                    if self.m.site_bodyid[s] == self.part_body[i]:
+                        mn = min(mn, self.sim.site_xpos[3 * s + 2])
+        return mn
+
+    def _try_connect(self, part1):
+        m, cfg = self.m, self.cfg
+        g1 = self._find(part1)
+        thr = (cfg.alignment_pos_dist, cfg.alignment_rot_dist_up, cfg.alignment_rot_dist_forward, cfg.alignment_project_dist)
+        if m.neq == 0:
+            return False
+        for s1 in self.conn_sites:
+            if self._find(self._part_of_body(m.site_bodyid[s1])) != g1:
+                continue
+            n1 = m.names["site"][s1]
+            for s2 in self.conn_sites:
+                if s1 in self.connected_sites or s2 in self.connected_sites:
+                    continue
+                n2 = m.names["site"][s2]
+                if n1.split(",")[0].split("-") != n2.split(",")[0].split("-")[::-1]:
+                    continue
+                angles = [float(x) for x in n1.split(",")[1:-1] if x]
+                ok, tq = A.is_aligned(self.sim.site_xpos[3 * s1 : 3 * s1 + 3], self.sim.site_xmat[9 * s1 : 9 * s1 + 9], self.sim.site_xpos[3 * s2 : 3 * s2 + 3],
+                                      self.sim.site_xmat[9 * s2 : 9 * s2 + 9], angles, thr)
+                if tq is not None:
+                    self.target_quat = tq
+                if ok:
+                    self._connect(s1, s2)
+                    return True
+        return False
+
+    def _connect(self, s1, s2):  # :847-924
+        m, sim = self.m, self.sim
+        self.connected_sites |= {s1, s2}
+        body1, body2 = self._part_of_body(m.site_bodyid[s1]), self._part_of_body(m.site_bodyid[s2])
+        g1, g2 = self._find(body1), self._find(body2)
+        for g in range(m.ngeom):
+            b = m.geom_bodyid[g]
+            if b in self.part_body and self._find(self.part_body.index(b)) in (g1, g2) and sim.geom_contype[g] != 0:
+                sim.geom_contype[g], sim.geom_conaffinity[g] = A.connect_masks(g1)
+        if self.cfg.auto_align:  # _align_connectors / _move_site_to_target :1224-1250
+            target = self._site_pose(s1)
+            target[3:] = self.target_quat
+            base = self._site_pose(s2)
+            bq = self._qpos(body2)
+            _, nq = A.transform_to_target_quat(base, bq, target[3:])
+            nsp, _ = A.transform_to_target_quat(bq, base, nq)
+            self._move_group(body2, target[:3] - nsp, nq, 0)
+        self._fwd_step()
+        mn = min(self._group_min_z(body1), self._group_min_z(body2))
+        if mn < 0:
+            for obj in (body1, body2):  # _move_rotate_object + _is_inside (one more step each)
+                base = self._qpos(obj)
+                g = self._find(obj)
+                for i in range(self.npart):
+                    if self._find(i) == g:
+                        npos, nq = A.transform_to_target_quat(base, self._qpos(i), base[3:])
+                        self._set_qpos(i, npos + np.array([0, 0, -mn]), nq)
+                self._fwd_step()
+        self._fwd_step()
+        for e in range(m.neq):  # _activate_weld :2761-2776
+            a, b = self._part_of_body(m.eq_obj1id[e]), self._part_of_body(m.eq_obj2id[e])
+            if a in (body1, body2) and b in (body1, body2):
+                sim.eq_data[7 * e : 7 * e + 7] = A.rel_pose(self._qpos(a), self._qpos(b))
+                sim.eq_active[e] = 1
+                self.group[self._find(body1)] = self._find(body2)
+        self.num_connected += 1
+        self.connected_body1 = body1
+        self.connected_pose = self._qpos(body1)
+
+    def obs(self):
+        sim, m = self.sim, self.m
+        ob = []
+        for p in range(self.npart):
+            b = self.part_body[p]
+            ob += list(sim.xpos[3 * b : 3 * b + 3]) + list(sim.xquat[4 * b : 4 * b + 4])
+        ob += list(sim.qpos[: self.narm]) + list(sim.qvel[: self.narm]) + list(sim.qpos[self.narm : self.nr])
+        s = self.eef_site
+        ob += list(sim.site_xpos[3 * s : 3 * s + 3])
+        hq = sim.xquat[4 * self.hand_body : 4 * self.hand_body + 4]
+        ob += [hq[1], hq[2], hq[3], hq[0]]
+        v = sim.site_velocity(s)
+        ob += list(v[:3]) + list(v[3:])
+        return np.array(ob)
+
+    def set_controls(self, action):
+        a = np.asarray(action, dtype=np.float64).copy()
+        if self.cfg.discrete_grip:
+            a[-2] = -1 if a[-2] < 0 else 1
+        act = np.clip(a[:-1], -1, 1) if self.cfg.rescale_actions else a[:-1]
+        full = np.concatenate([act[: self.narm], [act[self.narm], -act[self.narm]]])
+        cr = self.m.actuator_ctrlrange
+        if self.cfg.rescale_actions:
+            full = 0.5 * (cr[:, 1] + cr[:, 0]) + 0.5 * (cr[:, 1] - cr[:, 0]) * full
+        self.sim.ctrl[:] = full
+        self._grav_comp()
+        return a[-1]
+
+    def step(self, action):
+        raw = np.asarray(action, dtype=np.float64)
+        connect = self.set_controls(raw)
+        self.sim.forward()
+        self.sim.step(self.nsub)
+        fail = bool(self.sim.scalar("warning") & 2)
+        if fail:
+            self.sim.L.om_clear_warning(self.sim.d)
+            self.reset()
+        else:
+            if connect > 0:
+                bits = self.touch_bits()
+                for p in range(self.npart):
+                    if bits[p] & 3 == 3:
+                        self._try_connect(p)
+                        break
+            if self.connected_body1 is not None:
+                b1 = self.connected_body1
+                self.sim.forward()
+                self._move_group(b1, self.connected_pose[:3] - self._qpos(b1)[:3], self.connected_pose[3:], 0)
+                self.connected_body1 = None
+                self._fwd_step()
+        ob = self.obs()
+        touch_r = pick_r = 0.0
+        if not fail:
+            bits = self.touch_bits()
+            for p in range(self.npart):
+                if bits[p] & 3 == 3:
+                    if not self.touched[p]:
+                        self.touched[p] = True; touch_r += self.cfg.touch_reward
+                    if not (bits[p] & 4) and not self.picked[p]:
+                        self.picked[p] = True; pick_r += self.cfg.pick_reward
+        success_r = self.cfg.success_reward * (self.num_connected - self.prev_num_connected)
+        self.prev_num_connected = self.num_connected
+        reward = success_r + touch_r + pick_r - self.cfg.ctrl_penalty_coef * float(np.square(raw).sum())
+        success = self.num_connected == self.npart - 1 and self.npart > 1
+        done = success
+        self.episode_len += 1
+        if self.episode_len == self.cfg.max_episode_steps or fail:
+            done = True
+            if fail:
+                reward -= self.cfg.unstable_penalty_coef
+        info = dict(num_connected=self.num_connected, success=int(success), unstable=int(fail), episode_length=self.episode_len)
+        return ob, reward, done, info

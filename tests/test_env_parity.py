@@ -1,0 +1,167 @@
+"""Env-level parity: the device FurnitureEnv logic (fe_env_step / fe_env_reset through the C-ABI) against the CPU
+env oracle (oracle/ref_env.py, a restatement of FurnitureSawyerEnv with control_type="impedance").
+`emu` runs the lane-emulated harness build on CPU, `cuda` the sm_100a library (marked gpu)."""
+import numpy as np
+import pytest
+
+from furniture_b200 import mjcf
+from oracle import assembly_oracle as A
+from oracle.ref_env import Cfg, OracleFurnitureEnv
+from parity_util import make_engine
+
+BACKENDS = [pytest.param(False, id="emu"), pytest.param(True, id="cuda", marks=pytest.mark.gpu)]
+
+
+def _sync_oracle_from_engine(env, eng, i):
+    """copy env i of the engine (state + the per-env model bits the reference mutates) into the oracle env"""
+    sim, m = env.sim, env.m
+    sim.qpos[:] = eng.get("qpos")[i]; sim.qvel[:] = eng.get("qvel")[i]; sim.qacc_warmstart[:] = eng.get("qacc_warmstart")[i]
+    ct, ca = eng.get("geom_contype")[i], eng.get("geom_conaffinity")[i]
+    for k, g in enumerate(eng.em.geom_src):
+        sim.geom_contype[g] = ct[k]; sim.geom_conaffinity[g] = ca[k]
+    sim.eq_active[:] = eng.get("eq_active")[i]
+    sim.eq_data[:] = eng.get("eq_data")[i]
+    sim.forward()
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_reset_settles_like_the_reference_protocol(sawyer_model, gpu):
+    m = sawyer_model
+    n = 8
+    eng = make_engine(m, n, gpu)
+    eng.env_reset()
+    q, v = eng.get("qpos"), eng.get("qvel")
+    assert (eng.get("flags") == 0).all()
+    # parts rest on the floor (leg half-width 0.015, table half-thickness 0.02) within furn_xyz_rand of their XML slots
+    z = q[:, 9 + 2 :: 7]
+    assert np.allclose(z[:, :4], 0.015, atol=2e-4) and np.allclose(z[:, 4], 0.02, atol=2e-4)
+    for p, name in enumerate(m.meta["part_names"]):
+        init = m.meta["part_init_qpos"][name]
+        assert np.abs(q[:, 9 + 7 * p : 11 + 7 * p] - init[:2]).max() < 0.02 + 5e-3
+    assert np.abs(v[:, 9:]).max() < 5e-3
+    # arm stays near init_qpos (it sags a little under the stale gravity compensation, as in the reference), gripper open->0
+    assert np.abs(q[:, :7] - m.meta["robot_init_qpos"]).max() < 0.25
+    # envs got different random placements
+    assert np.abs(q[0, 9:11] - q[1, 9:11]).max() > 1e-4
+    # same protocol on the CPU oracle env: same resting heights, arm sag of the same size
+    env = OracleFurnitureEnv(m)
+    env.reset()
+    assert np.allclose(env.sim.qpos[9 + 2 :: 7][:4], 0.015, atol=2e-4)
+    assert np.abs(env.sim.qpos[:7] - q[:, :7].mean(0)).max() < 0.02
+    # masks restored, welds off, bookkeeping cleared
+    assert np.array_equal(eng.get("geom_contype")[0], np.array([1 if (t & (1 << 30)) else c for t, c in zip(list(eng.em.fm.geom_tag)[: eng.em.fm.ngeom], list(eng.em.fm.geom_contype0)[: eng.em.fm.ngeom])]))
+    assert (eng.get("eq_active") == 0).all() and (eng.get("num_connected") == 0).all()
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_env_step_matches_cpu_env(sawyer_model, gpu):
+    """3 env steps (50 mj_steps each) with random actions: obs / reward / done of the device env equal the CPU env
+    started from the same post-reset state."""
+    m = sawyer_model
+    n = 3
+    eng = make_engine(m, n, gpu)
+    eng.env_reset()
+    envs = [OracleFurnitureEnv(m) for _ in range(n)]
+    for i, e in enumerate(envs):
+        e.reset()  # initialises bookkeeping; the state is overwritten next
+        _sync_oracle_from_engine(e, eng, i)
+        e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[i]  # gravity compensation source = last forward of the reset
+    rng = np.random.RandomState(5)
+    for k in range(3):
+        a = rng.uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
+        a[:, -1] = -0.5
+        obs, rew, done, info = eng.env_step_host(a)
+        for i, e in enumerate(envs):
+            ob, r, d, inf = e.step(a[i].astype(np.float64))
+            assert np.abs(obs[i] - ob).max() < 2e-4, (k, i, np.abs(obs[i] - ob).max())
+            assert abs(rew[i] - r) < 1e-5 and bool(done[i]) == d
+            assert info[i][0] == inf["num_connected"] and info[i][3] == inf["episode_length"]
+
+
+def _grasp_and_align_state(m, env):
+    """state in which leg 0 sits between the finger tips (1 mm interpenetration on both sides) and the table top is
+    placed so that its connector 'table-leg..conn_site1' coincides with the leg's 'leg-table..conn_site1'."""
+    sim = env.sim
+    sim.reset()
+    for p, name in enumerate(env.parts):
+        sim.qpos[env.part_qadr[p] : env.part_qadr[p] + 7] = m.meta["part_init_qpos"][name]
+    sim.qpos[:7] = m.meta["robot_init_qpos"]
+    gl, gr = m.names["geom"].index("l_fingertip_g0"), m.names["geom"].index("r_fingertip_g0")
+
+    def tips(g):
+        sim.qpos[7], sim.qpos[8] = g, -g
+        sim.stage("kinematics")
+        return sim.geom_xpos[3 * gl : 3 * gl + 3].copy(), sim.geom_xpos[3 * gr : 3 * gr + 3].copy()
+
+    lo, hi = 0.0, 0.020833
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        cl, cr = tips(mid)
+        if np.linalg.norm(cr - cl) > 0.036:
+            hi = mid
+        else:
+            lo = mid
+    cl, cr = tips(0.5 * (lo + hi))
+    d = (cr - cl) / np.linalg.norm(cr - cl)
+    zl = np.array([0, 0, -1.0]) - d * (-d[2])
+    zl /= np.linalg.norm(zl)
+    yl = np.cross(zl, d)
+    R = np.stack([d, yl, zl], axis=1)  # leg x along the finger axis, leg z (its top) pointing down
+    leg_q = np.concatenate([0.5 * (cl + cr), mjcf.mat_to_q(R)])
+    s1 = m.names["site"].index("leg-table,0,90,180,270,conn_site1")
+    s2 = m.names["site"].index("table-leg,0,90,180,270,conn_site1")
+    site1_world = leg_q[:3] + R @ m.site_pos[s1]
+    table_q = np.concatenate([site1_world - R @ m.site_pos[s2], mjcf.mat_to_q(R)])
+    sim.qpos[env.part_qadr[0] : env.part_qadr[0] + 7] = leg_q
+    sim.qpos[env.part_qadr[4] : env.part_qadr[4] + 7] = table_q
+    return sim.qpos.copy()
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_connect_path_matches_cpu_env(sawyer_model, gpu):
+    """finger contact scan -> _try_connect -> _is_aligned -> _connect (masks, snap, weld, group merge, re-pin) on the
+    device equals the CPU restatement: same decisions (integers exact), same poses to fp32 tolerance."""
+    m = sawyer_model
+    env = OracleFurnitureEnv(m)
+    env.reset()
+    q = _grasp_and_align_state(m, env)
+    env.nsub = 1
+    env.sim.qvel[:] = 0; env.sim.qacc_warmstart[:] = 0; env.sim.ctrl[:] = 0
+    env.sim.forward()
+    eng = make_engine(m, 2, gpu, nsub=1)
+    eng.env_reset()
+    eng.set("qpos", q); eng.set("qvel", np.zeros(m.nv)); eng.set("qacc_warmstart", np.zeros(m.nv))
+    eng.forward()
+    a = np.zeros((2, eng.act_dim), np.float32)
+    a[:, -2] = 1.0
+    a[0, -1] = 1.0   # env 0 asks to connect, env 1 does not
+    a[1, -1] = -1.0
+    obs, rew, done, info = eng.env_step_host(a)
+    ob, r, d, inf = env.step(a[0].astype(np.float64))
+    assert inf["num_connected"] == 1, "the CPU env did not connect: test state is wrong"
+    assert info[0][0] == 1 and info[1][0] == 0
+    assert abs(rew[0] - r) < 1e-3 and rew[0] > 100  # success_reward for one connection (+ touch reward)
+    # integer model state: exact
+    e = 0  # weld 0_part0 <-> 4_part4
+    assert list(eng.get("eq_active")[0]) == list(env.sim.eq_active) and eng.get("eq_active")[0][e] == 1
+    assert (eng.get("eq_active")[1] == 0).all()
+    ct, ca = eng.get("geom_contype")[0], eng.get("geom_conaffinity")[0]
+    for k, g in enumerate(eng.em.geom_src):
+        assert ct[k] == env.sim.geom_contype[g] and ca[k] == env.sim.geom_conaffinity[g]
+    grp = eng.get("group")[0]
+    assert len({tuple(sorted(p for p in range(5) if _find(grp, p) == _find(grp, r_))) for r_ in range(5)}) == 4  # {0,4} merged
+    assert _find(list(grp), 0) == _find(list(grp), 4)
+    # welded relative pose and the resulting state: fp32 tolerance
+    assert np.abs(eng.get("eq_data")[0].reshape(-1, 7)[e] - env.sim.eq_data[7 * e : 7 * e + 7]).max() < 2e-4
+    assert np.abs(eng.get("qpos")[0] - env.sim.qpos).max() < 5e-4
+    assert np.abs(obs[0] - ob).max() < 1e-3
+    # the weld that was just activated holds: relative pose of the two parts equals the stored eq_data
+    q0 = eng.get("qpos")[0]
+    rel = A.rel_pose(q0[9 + 0 : 9 + 7].astype(np.float64), q0[9 + 28 : 9 + 35].astype(np.float64))
+    assert np.abs(rel[:3] - eng.get("eq_data")[0].reshape(-1, 7)[e][:3]).max() < 2e-3
+
+
+def _find(g, i):
+    while g[i] != i:
+        i = g[i]
+    return i

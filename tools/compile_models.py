@@ -1,0 +1,31 @@
+"""Compile the composed MJCF scenes into flat tables (furniture_b200/compiled/*.npz).
+
+Runs where the reference asset tree is reachable (build container).  The GPU box has no /root/reference, so the
+package falls back to these tables (mjcf.load_scene).  Only derived numeric tables are stored, no reference source."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from furniture_b200 import mjcf  # noqa: E402
+
+SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825")]
+
+
+def main():
+    root = mjcf.default_assets_root()
+    if root is None:
+        print("asset tree not found; nothing compiled")
+        return
+    out = os.path.join(ROOT, "furniture_b200", "compiled")
+    os.makedirs(out, exist_ok=True)
+    for agent, furn in SCENES:
+        xml, meta = mjcf.compose_scene(agent, furn, root)
+        m = mjcf.compile_mjcf(xml, meta)
+        path = os.path.join(out, "%s_%s.npz" % (agent, furn))
+        m.save(path)
+        print("wrote", path, "nq=%d nv=%d" % (m.nq, m.nv))
+
+
+if __name__ == "__main__":
+    main()

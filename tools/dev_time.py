@@ -1,0 +1,26 @@
+"""Developer script: time env steps on the GPU (device-resident actions)."""
+import sys, os, time
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np, torch
+from furniture_b200 import mjcf
+from furniture_b200.engine import Engine, default_config
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+m = mjcf.load_scene("Sawyer", "table_lack_0825")
+eng = Engine(m, N, 0, default_config())
+t = time.time(); eng.env_reset(); torch.cuda.synchronize(); print("reset wall %.3f s" % (time.time() - t), "flags nonzero", int((eng.get("flags") != 0).sum()))
+g = torch.Generator(device="cuda").manual_seed(0)
+act = torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1
+obs = torch.empty((N, eng.obs_dim), device="cuda"); rew = torch.empty(N, device="cuda"); done = torch.empty(N, dtype=torch.uint8, device="cuda"); info = torch.empty((N, 6), dtype=torch.int32, device="cuda")
+for w in range(2):
+    eng.env_step_dev(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for k in range(steps):
+    act = torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1
+    eng.env_step_dev(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print("N=%d  %.3f ms/env-step-batch  => %.0f env-steps/s  (%.2f us per mj_step batch)" % (N, ms, N / ms * 1e3, ms * 1e3 / 50))
+print("mean ncon %.1f mean niter %.2f done %d unstable %d" % (info[:, 4].float().mean().item(), info[:, 5].float().mean().item(), int(done.sum()), int(info[:, 2].sum())))
