@@ -149,6 +149,8 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
   CudaPlat* p = (CudaPlat*)h->plat;
   const size_t N = h->N, ab = sizeof(float) * N * h->hs.act_dim, ob = sizeof(float) * N * h->hs.obs_dim, rb = sizeof(float) * N, ib = sizeof(int32_t) * N * FE_INFO_DIM;
   memcpy(p->pin_act, actions, ab);
+  // the private stream does not order against work the caller issued on other streams (fe_sim_forward, fe_set_field ...)
+  CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpyAsync(h->dev_act, p->pin_act, ab, cudaMemcpyHostToDevice, p->stream));
   fe_env_step_kernel<<<h->N, 32, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
                                                             (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words);

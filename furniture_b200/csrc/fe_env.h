@@ -558,6 +558,7 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
   LANES_END
   for (int i = 0; i < cfg->nsub; ++i) fe_substep(w); // _do_simulation, furniture.py:2877-2879
   int fail = (w->u[2] & 8) ? 1 : 0;                   // MujocoException path, :2889-2897
+  FE_SYNC;
   if (fail) {
     fe_env_reset_one(e);
   } else {
@@ -569,7 +570,9 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
         if (e->ei[0]) fe_connect(e);
       }
     }
-    if (e->ei[1] >= 0) { // furniture.py:426-436: re-pin the merged group at the recorded pose, one more step
+    const int repin = e->ei[1];
+    FE_SYNC; // every lane has read the flag before lane 0 clears it
+    if (repin >= 0) { // furniture.py:426-436: re-pin the merged group at the recorded pose, one more step
       LANES_BEGIN
         if (lane == 0) {
           const int b1 = e->ei[1], qa = m->link_qadr[m->nrlink + b1];

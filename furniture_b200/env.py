@@ -1,0 +1,155 @@
+"""Batched gym/VecEnv-shaped surface over the engine (torch tensors in, torch tensors out).
+
+Mirrors the reference's call surface for the accelerated path:
+  make_vec_env(env_id, num_env, config)   furniture/env/base.py:55-80          -> BatchedFurnitureEnv
+  VecEnv.reset() / step(actions)          furniture/util/vec_env.py:53-162, subproc_vec_env.py:100-113 (auto-reset on done)
+  obs dict {"object_ob", "robot_ob"}      furniture.py:1344-1387, furniture_sawyer.py:103-155 (OrderedDict order kept)
+  get_env_state / set_env_state           furniture.py:1781-1803
+Observations live in one contiguous (N, obs_dim) float32 CUDA tensor written by the step kernel; the dict entries are
+views of it.  ShardedFurnitureEnv adds the multi-GPU form: env shards are independent (one process per GPU), the only
+collective is one NCCL all_gather of the packed [obs | reward | done] tensor per step.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+
+from . import mjcf
+from .engine import INFO_DIM, Engine, default_config
+
+INFO_KEYS = ("num_connected", "episode_success", "episode_unstable", "episode_length", "ncon", "solver_iters")
+ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer"}
+
+
+class BatchedFurnitureEnv:
+    def __init__(self, agent="Sawyer", furniture_name="table_lack_0825", num_envs=1, device=0, **cfg_overrides):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("furniture_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists before the library binds to it
+        self.model = mjcf.load_scene(agent, furniture_name)
+        self.cfg = default_config(**cfg_overrides)
+        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg)
+        self.num_envs = num_envs
+        self.obs_dim, self.act_dim = self.engine.obs_dim, self.engine.act_dim
+        self.n_objects = self.engine.scene.npart
+        self.object_ob_dim = 7 * self.n_objects
+        self.robot_ob_dim = self.engine.scene.robot_ob_dim
+        self.dof = self.act_dim
+        self._obs = torch.empty((num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        self._rew = torch.empty(num_envs, dtype=torch.float32, device=self.device)
+        self._done = torch.empty(num_envs, dtype=torch.uint8, device=self.device)
+        self._info = torch.empty((num_envs, INFO_DIM), dtype=torch.int32, device=self.device)
+        self._act = torch.empty((num_envs, self.act_dim), dtype=torch.float32, device=self.device)
+
+    # spaces, in the reference's terms (furniture.py:215-252, :293-310)
+    @property
+    def observation_space(self):
+        return OrderedDict(object_ob=(self.object_ob_dim,), robot_ob=(self.robot_ob_dim,))
+
+    @property
+    def action_space(self):
+        return OrderedDict(default=(self.act_dim,))
+
+    def _obs_dict(self, obs):
+        return OrderedDict(object_ob=obs[:, : self.object_ob_dim], robot_ob=obs[:, self.object_ob_dim :])
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, mask=None):
+        m = 0
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            m = mask.data_ptr()
+        self.engine.env_reset(mask_dev=m, obs_dev=self._obs.data_ptr(), stream=self._stream())
+        return self._obs_dict(self._obs)
+
+    def step(self, actions):
+        """actions: (N, dof) float tensor (CUDA or CPU) in [-1, 1]; returns (obs dict, rewards, dones, info tensor)."""
+        t = self.torch
+        if isinstance(actions, dict):
+            actions = actions["default"]
+        a = t.as_tensor(actions)
+        if a.device != self.device or a.dtype != t.float32 or not a.is_contiguous():
+            self._act.copy_(a, non_blocking=True)
+            a = self._act
+        assert a.shape == (self.num_envs, self.act_dim), tuple(a.shape)
+        self.engine.env_step_dev(a.data_ptr(), self._obs.data_ptr(), self._rew.data_ptr(), self._done.data_ptr(), self._info.data_ptr(), stream=self._stream())
+        return self._obs_dict(self._obs), self._rew, self._done, self._info
+
+    def step_host(self, actions_np):
+        """numpy in / numpy out through fe_env_step_host (pinned staging, copies inside the call)."""
+        obs, rew, done, info = self.engine.env_step_host(actions_np)
+        return OrderedDict(object_ob=obs[:, : self.object_ob_dim], robot_ob=obs[:, self.object_ob_dim :]), rew, done.astype(bool), info
+
+    def infos(self):
+        info = self._info.cpu().numpy()
+        return tuple({k: int(row[j]) for j, k in enumerate(INFO_KEYS)} for row in info)
+
+    def get_env_state(self):
+        return {"qpos": self.engine.get("qpos"), "qvel": self.engine.get("qvel")}
+
+    def set_env_state(self, state):
+        self.engine.set("qpos", state["qpos"])
+        self.engine.set("qvel", state["qvel"])
+        self.engine.set("ctrl", np.zeros((self.num_envs, self.model.nu), np.float32))
+        self.engine.forward(stream=self._stream())
+
+    def close(self):
+        self.engine.close()
+
+
+def make_vec_env(env_id="IKEASawyer-v0", num_env=1, config=None, device=0):
+    config = dict(config or {})
+    agent = ENV_IDS.get(env_id)
+    if agent is None:
+        raise ValueError("unknown env id %s (this build accelerates %s)" % (env_id, sorted(ENV_IDS)))
+    if config.pop("control_type", "impedance") != "impedance":
+        raise NotImplementedError("only control_type='impedance' is accelerated")
+    furniture = config.pop("furniture_name", "table_lack_0825")
+    return BatchedFurnitureEnv(agent, furniture, num_env, device=device, **config)
+
+
+class ShardedFurnitureEnv:
+    """One process per GPU (torch.distributed, backend nccl). Each rank steps its own contiguous env shard; after the
+    step one all_gather makes the packed [obs | reward | done] of every shard visible on every rank."""
+
+    def __init__(self, envs_per_gpu, agent="Sawyer", furniture_name="table_lack_0825", **cfg_overrides):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        local = int(__import__("os").environ.get("LOCAL_RANK", self.rank))
+        cfg_overrides.setdefault("seed", 123 + self.rank * envs_per_gpu)  # env/base.py:77: seed + rank
+        self.env = BatchedFurnitureEnv(agent, furniture_name, envs_per_gpu, device=local, **cfg_overrides)
+        self.envs_per_gpu = envs_per_gpu
+        self.num_envs = envs_per_gpu * self.world
+        self.pack_dim = self.env.obs_dim + 2
+        self._pack = torch.empty((envs_per_gpu, self.pack_dim), dtype=torch.float32, device=self.env.device)
+        self._all = torch.empty((self.num_envs, self.pack_dim), dtype=torch.float32, device=self.env.device)
+
+    def _gather(self, obs, rew=None, done=None):
+        p = self._pack
+        p[:, : self.env.obs_dim] = obs
+        p[:, self.env.obs_dim] = rew if rew is not None else 0
+        p[:, self.env.obs_dim + 1] = done.float() if done is not None else 0
+        self.dist.all_gather_into_tensor(self._all, p)
+        return self._all
+
+    def reset(self):
+        self.env.reset()
+        allp = self._gather(self.env._obs)
+        return self.env._obs_dict(allp[:, : self.env.obs_dim])
+
+    def step(self, local_actions):
+        _, rew, done, info = self.env.step(local_actions)
+        allp = self._gather(self.env._obs, rew, done)
+        od = self.env.obs_dim
+        return self.env._obs_dict(allp[:, :od]), allp[:, od], allp[:, od + 1] > 0.5, info
