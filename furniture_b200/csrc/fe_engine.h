@@ -42,7 +42,7 @@ struct FeWarp {
   int *cand, *touch;
   // contacts (SoA, maxcon each)
   float *c_dist, *c_pos, *c_frame, *c_aref, *c_D, *c_mu, *c_fric, *c_jar, *c_jv, *c_f;
-  int *c_geom, *c_link, *c_state;
+  int *c_geom, *c_link, *c_state, *c_kind;
   // welds (neq each) and limits (nr each)
   float *w_r1, *w_G, *w_aref, *w_D, *w_jar, *w_jv, *w_f;
   float *l_sign, *l_aref, *l_D, *l_jar, *l_jv, *l_f;
@@ -50,7 +50,9 @@ struct FeWarp {
   float *x, *Ma, *grad, *search, *Mv, *fc, *H, *Jc, *scr;
   int *first, *iscr, *colmap;
   // uniform scalars (kept in smem so that both builds see one copy)
-  int* u; // [0]=ncon [1]=ncand [2]=flags [3]=niter
+  int* u; // [0]=ncon [1]=ncand [2]=flags [3]=niter [4]=coupled
+  // solver scope of the cooperative routines: all dofs (FULL) or the robot block only (FAST, parts solved per lane)
+  int nact, fast;
 };
 
 FE_BOTH int fe_tri(int n) { return n * (n + 1) / 2; }
@@ -61,18 +63,18 @@ FE_BOTH int fe_warp_bind(FeWarp* w, float* base, const fe_model* m, const FeOpt&
   const int nq = m->nq, nv = m->nv, nu = m->nu, nl = m->nlink, nr = m->nr, np = m->npart, ng = m->ngeom, ne = m->neq, mc = opt.maxcon;
 #define CARVE_F(field, n) w->field = base ? base + o : nullptr; o += (n);
 #define CARVE_I(field, n) w->field = base ? (int*)(base + o) : nullptr; o += (n);
-  w->m = m; w->opt = opt;
+  w->m = m; w->opt = opt; w->nact = nv; w->fast = 0;
   CARVE_F(qpos, nq) CARVE_F(qvel, nv) CARVE_F(warm, nv) CARVE_F(ctrl, nu) CARVE_F(qfrc_applied, nr) CARVE_F(gravcomp, np) CARVE_F(eq_data, 7 * ne)
   CARVE_I(contype, ng) CARVE_I(conaff, ng) CARVE_I(eq_active, ne)
   CARVE_F(lpos, 3 * nl) CARVE_F(lquat, 4 * nl) CARVE_F(lmat, 9 * nl) CARVE_F(S, 6 * nr) CARVE_F(lvel, 6 * nl) CARVE_F(lacc, 6 * nl) CARVE_F(lfrc, 6 * nl)
   CARVE_F(linert, 10 * nl) CARVE_F(lcrb, 10 * nr) CARVE_F(Mr, nr * nr) CARVE_F(Lr, fe_tri(nr)) CARVE_F(fs, nv) CARVE_F(as, nv) CARVE_F(bias, nr) CARVE_F(lacc2, 6 * nl)
   CARVE_I(touch, np)
   CARVE_F(c_dist, mc) CARVE_F(c_pos, 3 * mc) CARVE_F(c_frame, 9 * mc) CARVE_F(c_aref, 3 * mc) CARVE_F(c_D, 2 * mc) CARVE_F(c_mu, mc) CARVE_F(c_fric, mc)
-  CARVE_F(c_jar, 3 * mc) CARVE_F(c_jv, 3 * mc) CARVE_F(c_f, 3 * mc) CARVE_I(c_geom, mc) CARVE_I(c_link, mc) CARVE_I(c_state, mc)
+  CARVE_F(c_jar, 3 * mc) CARVE_F(c_jv, 3 * mc) CARVE_F(c_f, 3 * mc) CARVE_I(c_geom, mc) CARVE_I(c_link, mc) CARVE_I(c_state, mc) CARVE_I(c_kind, mc)
   CARVE_F(w_r1, 3 * ne) CARVE_F(w_G, 9 * ne) CARVE_F(w_aref, 6 * ne) CARVE_F(w_D, 6 * ne) CARVE_F(w_jar, 6 * ne) CARVE_F(w_jv, 6 * ne) CARVE_F(w_f, 6 * ne)
   CARVE_F(l_sign, nr) CARVE_F(l_aref, nr) CARVE_F(l_D, nr) CARVE_F(l_jar, nr) CARVE_F(l_jv, nr) CARVE_F(l_f, nr)
   CARVE_F(x, nv) CARVE_F(Ma, nv) CARVE_F(grad, nv) CARVE_F(search, nv) CARVE_F(Mv, nv) CARVE_F(fc, nv)
-  CARVE_F(Jc, 3 * 32) CARVE_F(scr, 3 * 32) CARVE_I(first, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 4)
+  CARVE_F(Jc, 3 * 32) CARVE_F(scr, 3 * 32) CARVE_I(first, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 8)
   // H (solver) and the collision scratch (geom poses, candidate list) are never live together: overlay them
   int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
   int big = hwords > cwords ? hwords : cwords;
@@ -544,6 +546,12 @@ FE_FN void fe_assemble(FeWarp* w) {
       const int g1 = w->c_geom[c] & 255, g2 = w->c_geom[c] >> 8;
       const int A = m->geom_link[g1], B = m->geom_link[g2];
       w->c_link[c] = (A + 1) | ((B + 1) << 8);
+      { // 0: one free part against the static world; 1: robot only; 2: couples two moving blocks
+        const int nrl_ = m->nrlink;
+        const bool pa = A >= nrl_, pb = B >= nrl_, ra = A >= 0 && A < nrl_, rb = B >= 0 && B < nrl_;
+        w->c_kind[c] = ((pa && B < 0) || (pb && A < 0)) ? 0 : ((pa || pb) ? 2 : 1);
+        (void)ra; (void)rb;
+      }
       float* F = w->c_frame + 9 * c;
       fe_make_frame(F);
       const float fric = fmaxf(fmaxf(m->geom_friction[g1], m->geom_friction[g2]), 1e-5f);
@@ -635,7 +643,7 @@ FE_FN void fe_assemble(FeWarp* w) {
 // out = M_z in
 FE_FN void fe_mul_M(FeWarp* w, const float* in, float* out) {
   const fe_model* m = w->m;
-  const int nr = m->nr, np = m->npart, nrl = m->nrlink;
+  const int nr = m->nr, np = w->fast ? 0 : m->npart, nrl = m->nrlink;
   LANES_BEGIN
     for (int d = lane; d < nr; d += 32) {
       float s = 0.f;
@@ -648,7 +656,8 @@ FE_FN void fe_mul_M(FeWarp* w, const float* in, float* out) {
 // rows = J_z in  (contacts -> cout[3*c..], welds -> wout[6*e..], limits -> lout[d]); `sub_aref` subtracts aref
 FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float* lout, bool sub_aref) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, nl = m->nlink, ncon = w->u[0], ne = m->neq;
+  const int nr = m->nr, nrl = m->nrlink, nl = w->fast ? m->nrlink : m->nlink, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const bool fast = w->fast != 0;
   LANES_BEGIN
     const int l = lane;
     if (l < nl) {
@@ -663,6 +672,7 @@ FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float*
   LANES_END
   LANES_BEGIN
     for (int c = lane; c < ncon; c += 32) {
+      if (fast && w->c_kind[c] == 0) continue;
       const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
       float aA[3], aB[3], da[3];
       fe_point_vel(w, w->lacc2, A, w->c_pos + 3 * c, aA);
@@ -687,10 +697,12 @@ FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float*
 // constraint forces/states from jar; returns the constraint cost
 FE_FN float fe_update(FeWarp* w) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], ne = m->neq, nr = m->nr;
+  const int ncon = w->u[0], ne = w->fast ? 0 : m->neq, nr = m->nr;
+  const bool fast = w->fast != 0;
   LANES_BEGIN
     float cost = 0.f;
     for (int c = lane; c < ncon; c += 32) {
+      if (fast && w->c_kind[c] == 0) continue;
       const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
       const float j0 = w->c_jar[3 * c], j1 = w->c_jar[3 * c + 1], j2 = w->c_jar[3 * c + 2];
       const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
@@ -732,13 +744,15 @@ FE_FN float fe_update(FeWarp* w) {
 // out = J_z^T force
 FE_FN void fe_mul_JT(FeWarp* w, float* out) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, nl = m->nlink, ncon = w->u[0], ne = m->neq;
+  const int nr = m->nr, nrl = m->nrlink, nl = w->fast ? m->nrlink : m->nlink, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const bool fast = w->fast != 0;
   LANES_BEGIN
     const int l = lane;
     if (l < nl) {
       float P[3], Wr[6] = {0, 0, 0, 0, 0, 0};
       fe_link_ref(w, l, P);
       for (int c = 0; c < ncon; ++c) {
+        if (fast && w->c_kind[c] == 0) continue;
         if (w->c_state[c] == 0) continue;
         const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
         if (A != l && B != l) continue;
@@ -783,10 +797,12 @@ FE_FN void fe_mul_JT(FeWarp* w, float* out) {
 // one 1-D cost evaluation along the search direction: returns p'(alpha), p''(alpha) (uniform)
 FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, float* d2) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], ne = m->neq, nr = m->nr;
+  const int ncon = w->u[0], ne = w->fast ? 0 : m->neq, nr = m->nr;
+  const bool fast = w->fast != 0;
   LANES_BEGIN
     float p1 = 0.f, p2 = 0.f;
     for (int c = lane; c < ncon; c += 32) {
+      if (fast && w->c_kind[c] == 0) continue;
       const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
       const float v0 = w->c_jv[3 * c], v1 = w->c_jv[3 * c + 1], v2 = w->c_jv[3 * c + 2];
       const float x0 = w->c_jar[3 * c] + alpha * v0, x1 = w->c_jar[3 * c + 1] + alpha * v1, x2 = w->c_jar[3 * c + 2] + alpha * v2;
@@ -824,7 +840,8 @@ FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, f
 // H = M_z + J^T W J  (packed lower, skyline first[])
 FE_FN void fe_build_H(FeWarp* w) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, np = m->npart, nv = m->nv, ncon = w->u[0], ne = m->neq;
+  const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const bool fast = w->fast != 0;
   // envelope: a part row starts at its own block unless it is coupled to the robot or to a lower part
   LANES_BEGIN
     for (int d = lane; d < nr; d += 32) w->first[d] = 0;
@@ -869,7 +886,7 @@ FE_FN void fe_build_H(FeWarp* w) {
   // contacts, one at a time: dof-space rows staged in Jc (3 x ncols), then the ncols x ncols outer product
   for (int c = 0; c < ncon; ++c) {
     const int st = w->c_state[c];
-    if (st == 0) continue;
+    if (st == 0 || (fast && w->c_kind[c] == 0)) continue;
     const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
     const bool robot = (A >= 0 && A < nrl) || (B >= 0 && B < nrl);
     const int partA = A >= nrl ? A - nrl : -1, partB = B >= nrl ? B - nrl : -1;
@@ -991,12 +1008,15 @@ FE_FN void fe_build_H(FeWarp* w) {
   }
 }
 
-FE_FN void fe_solve(FeWarp* w) {
+// cooperative Newton solve over the active scope (w->nact dofs; in FAST scope the free parts are excluded)
+FE_FN void fe_solve_coop(FeWarp* w) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, np = m->npart, nv = m->nv, ncon = w->u[0], ne = m->neq;
+  const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const bool fast = w->fast != 0;
   // any constraint at all?
   LANES_BEGIN
-    int any = (lane == 0 && ncon > 0) ? 1 : 0;
+    int any = 0;
+    for (int c = lane; c < ncon; c += 32) any |= !(fast && w->c_kind[c] == 0);
     for (int e = lane; e < ne; e += 32) any |= w->eq_active[e] != 0;
     for (int d = lane; d < nr; d += 32) any |= w->l_sign[d] != 0.f;
     w->iscr[lane] = any;
@@ -1005,11 +1025,10 @@ FE_FN void fe_solve(FeWarp* w) {
   if (fe_ballot32(w->iscr) == 0u) {
     LANES_BEGIN
       for (int i = lane; i < nv; i += 32) w->x[i] = w->as[i];
-      if (lane == 0) w->u[3] = 0;
     LANES_END
     return;
   }
-  const float scale = 1.0f / (m->meaninertia * (float)(nv > 1 ? nv : 1));
+  const float scale = 1.0f / (m->meaninertia * (float)(m->nv > 1 ? m->nv : 1));
   // warm start candidate (stored in qacc coordinates) -> z coordinates; pick the cheaper of warm / smooth
   float best = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1096,7 +1115,10 @@ FE_FN void fe_solve(FeWarp* w) {
     impr = -0.5f * alpha * p1_0;
     LANES_BEGIN
       for (int i = lane; i < nv; i += 32) { w->x[i] += alpha * w->search[i]; w->Ma[i] += alpha * w->Mv[i]; }
-      for (int c = lane; c < 3 * ncon; c += 32) w->c_jar[c] += alpha * w->c_jv[c];
+      for (int c = lane; c < ncon; c += 32) {
+        if (fast && w->c_kind[c] == 0) continue;
+        for (int k = 0; k < 3; ++k) w->c_jar[3 * c + k] += alpha * w->c_jv[3 * c + k];
+      }
       for (int e = lane; e < 6 * ne; e += 32) w->w_jar[e] += alpha * w->w_jv[e];
       for (int d = lane; d < nr; d += 32) w->l_jar[d] += alpha * w->l_jv[d];
     LANES_END
@@ -1104,7 +1126,212 @@ FE_FN void fe_solve(FeWarp* w) {
   }
   fe_update(w);
   fe_mul_JT(w, w->fc);
-  LANES_BEGIN if (lane == 0) w->u[3] = iter; LANES_END
+  LANES_BEGIN if (lane == 0 && iter > w->u[3]) w->u[3] = iter; LANES_END
+}
+
+
+// ---- single-lane Newton solve of one free part whose contacts are all against the static world (FAST scope).
+// Same cost, cones and exact line search as the cooperative solver, on the part's own 6 unknowns [alpha; vdot]; the
+// blocks are independent in that case, so block-wise Newton converges to the same minimiser as MuJoCo's global iteration.
+struct FeRow3 { float j[3][6]; };
+FE_HD void fe_part_rows(const FeWarp* w, int c, int l, float sgn, FeRow3* R) {
+  const float* F = w->c_frame + 9 * c;
+  float r[3];
+  v3sub(r, w->c_pos + 3 * c, w->lpos + 3 * l);
+  for (int k = 0; k < 3; ++k) {
+    float t[3];
+    v3cross(t, r, F + 3 * k);
+    R->j[k][0] = sgn * t[0]; R->j[k][1] = sgn * t[1]; R->j[k][2] = sgn * t[2];
+    R->j[k][3] = sgn * F[3 * k]; R->j[k][4] = sgn * F[3 * k + 1]; R->j[k][5] = sgn * F[3 * k + 2];
+  }
+}
+// zone logic of one elliptic contact: forces f, cost, and (if W) the 3x3 weight (xx yy zz xy xz yz); returns state
+FE_HD int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
+  const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { f[0] = f[1] = f[2] = 0.f; return 0; }
+  if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+    f[0] = -D0 * j0; f[1] = -D1 * j1; f[2] = -D1 * j2;
+    *cost += 0.5f * (D0 * j0 * j0 + D1 * (j1 * j1 + j2 * j2));
+    if (W) { W[0] = D0; W[1] = D1; W[2] = D1; W[3] = W[4] = W[5] = 0.f; }
+    return 1;
+  }
+  const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+  *cost += 0.5f * Dm * NmT * NmT;
+  f[0] = -Dm * NmT * mu;
+  f[1] = -f[0] / T * U1 * fr;
+  f[2] = -f[0] / T * U2 * fr;
+  if (W) {
+    const float iT = 1.f / T, a = Dm * mu * mu * iT * iT, b = Dm * NmT * mu * iT;
+    const float h11 = a * U1 * U1 - b * (1.f - U1 * U1 * iT * iT), h22 = a * U2 * U2 - b * (1.f - U2 * U2 * iT * iT), h12 = a * U1 * U2 + b * U1 * U2 * iT * iT;
+    const float h01 = -Dm * mu * U1 * iT, h02 = -Dm * mu * U2 * iT;
+    W[0] = mu * mu * Dm; W[1] = fr * fr * h11; W[2] = fr * fr * h22; W[3] = mu * fr * h01; W[4] = mu * fr * h02; W[5] = fr * fr * h12;
+  }
+  return 2;
+}
+FE_HD int fe_solve_part_lane(FeWarp* w, int p) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, l = m->nrlink + p, z = nr + 6 * p, ncon = w->u[0], da = m->link_dadr[l];
+  const float* I = w->linert + 10 * l;
+  // MuJoCo scales cost improvement / gradient by 1/(meaninertia * nv) of the whole model; a 1.2 g leg would then stop
+  // three orders of magnitude early next to the 5 kg arm links, so the block uses its own mean inertia
+  const float scale = 1.0f / (3.f * I[0] + I[4] + I[5] + I[6]), tol = w->opt.tolerance;
+  float fs[6], as[6], x[6];
+  for (int k = 0; k < 6; ++k) { fs[k] = w->fs[z + k]; as[k] = w->as[z + k]; }
+  int mine = 0;
+  for (int c = 0; c < ncon; ++c) {
+    if (w->c_kind[c] != 0) continue;
+    const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+    if (A == l || B == l) ++mine;
+  }
+  if (mine == 0) {
+    for (int k = 0; k < 6; ++k) { w->x[z + k] = as[k]; w->fc[z + k] = 0.f; }
+    return 0;
+  }
+#define FE_FOR_MY_CONTACTS(...)                                                          \
+  for (int c = 0; c < ncon; ++c) {                                                       \
+    if (w->c_kind[c] != 0) continue;                                                     \
+    const int A_ = (w->c_link[c] & 255) - 1, B_ = (w->c_link[c] >> 8) - 1;               \
+    if (A_ != l && B_ != l) continue;                                                    \
+    const float sgn = B_ == l ? 1.f : -1.f;                                              \
+    FeRow3 R;                                                                            \
+    fe_part_rows(w, c, l, sgn, &R);                                                      \
+    const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1]; \
+    const float* aref = w->c_aref + 3 * c;                                               \
+    __VA_ARGS__                                                                          \
+  }
+  // warm start (qacc coordinates -> z) against the unconstrained acceleration: keep the cheaper one
+  float xw[6];
+  m3mulv(xw, w->lmat + 9 * l, w->warm + da + 3);
+  v3cpy(xw + 3, w->warm + da);
+  float cw = 0.f, cs = 0.f;
+  {
+    float Mx[6];
+    inert_mulv(Mx, I, xw);
+    for (int k = 0; k < 6; ++k) cw += 0.5f * (Mx[k] - fs[k]) * (xw[k] - as[k]);
+  }
+  FE_FOR_MY_CONTACTS({
+    float f[3];
+    fe_cone(dot6(R.j[0], xw) - aref[0], dot6(R.j[1], xw) - aref[1], dot6(R.j[2], xw) - aref[2], mu, fr, D0, D1, f, &cw, nullptr);
+    fe_cone(dot6(R.j[0], as) - aref[0], dot6(R.j[1], as) - aref[1], dot6(R.j[2], as) - aref[2], mu, fr, D0, D1, f, &cs, nullptr);
+  })
+  const bool use_warm = !(cs < cw) && (cw == cw);
+  for (int k = 0; k < 6; ++k) x[k] = use_warm ? xw[k] : as[k];
+  int iter = 0;
+  float impr = 0.f;
+  for (;;) {
+    float Mx[6], g[6], H[21], ccost = 0.f;
+    inert_mulv(Mx, I, x);
+    for (int k = 0; k < 6; ++k) g[k] = Mx[k] - fs[k];
+    fe_inert_sym6(H, I, 0.f);
+    FE_FOR_MY_CONTACTS({
+      float f[3], W[6];
+      const int st = fe_cone(dot6(R.j[0], x) - aref[0], dot6(R.j[1], x) - aref[1], dot6(R.j[2], x) - aref[2], mu, fr, D0, D1, f, &ccost, W);
+      if (st != 0) {
+        float WJ[3][6];
+        for (int i = 0; i < 6; ++i) {
+          g[i] -= R.j[0][i] * f[0] + R.j[1][i] * f[1] + R.j[2][i] * f[2];
+          WJ[0][i] = W[0] * R.j[0][i] + W[3] * R.j[1][i] + W[4] * R.j[2][i];
+          WJ[1][i] = W[3] * R.j[0][i] + W[1] * R.j[1][i] + W[5] * R.j[2][i];
+          WJ[2][i] = W[4] * R.j[0][i] + W[5] * R.j[1][i] + W[2] * R.j[2][i];
+        }
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j <= i; ++j) H[i * (i + 1) / 2 + j] += R.j[0][i] * WJ[0][j] + R.j[1][i] * WJ[1][j] + R.j[2][i] * WJ[2][j];
+      }
+    })
+    float gsq = 0.f;
+    for (int k = 0; k < 6; ++k) gsq += g[k] * g[k];
+    const float gnorm = sqrtf(gsq);
+    if (!(gnorm == gnorm)) { w->u[2] |= 2; break; }
+    if (iter > 0) { if (scale * impr < tol || scale * gnorm < tol) break; }
+    else if (scale * gnorm < tol) break;
+    if (iter >= w->opt.newton_iters) break;
+    if (!fe_chol6(H)) w->u[2] |= 4;
+    float sd[6], Ms[6];
+    for (int k = 0; k < 6; ++k) sd[k] = -g[k];
+    fe_chol6_solve(H, sd);
+    inert_mulv(Ms, I, sd);
+    float g1 = 0.f, g2 = 0.f;
+    for (int k = 0; k < 6; ++k) { g1 += sd[k] * (Mx[k] - fs[k]); g2 += 0.5f * sd[k] * Ms[k]; }
+    // exact line search (same safeguarded Newton as the cooperative solver)
+    float alpha = 0.f, lo = 0.f, hi = -1.f, p1_0 = 0.f;
+    bool ok = true;
+    for (int ls = 0; ls <= w->opt.ls_iters; ++ls) {
+      float p1 = g1 + 2.f * alpha * g2, p2 = 2.f * g2;
+      FE_FOR_MY_CONTACTS({
+        const float v0 = dot6(R.j[0], sd), v1 = dot6(R.j[1], sd), v2 = dot6(R.j[2], sd);
+        const float x0 = dot6(R.j[0], x) - aref[0] + alpha * v0, x1 = dot6(R.j[1], x) - aref[1] + alpha * v1, x2 = dot6(R.j[2], x) - aref[2] + alpha * v2;
+        const float N = x0 * mu, U1 = x1 * fr, U2 = x2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+        if (N >= mu * T || (T <= 0.f && N >= 0.f)) {
+        } else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+          p1 += D0 * x0 * v0 + D1 * (x1 * v1 + x2 * v2);
+          p2 += D0 * v0 * v0 + D1 * (v1 * v1 + v2 * v2);
+        } else {
+          const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T, N1 = v0 * mu, V1 = v1 * fr, V2 = v2 * fr;
+          const float T1 = (U1 * V1 + U2 * V2) / T, T2 = (V1 * V1 + V2 * V2 - T1 * T1) / T, a = N1 - mu * T1;
+          p1 += Dm * NmT * a;
+          p2 += Dm * (a * a - NmT * mu * T2);
+        }
+      })
+      if (ls == 0) {
+        if (!(p1 < 0.f) || !(p2 > 0.f)) { ok = false; break; }
+        p1_0 = p1;
+        alpha = -p1 / p2;
+        continue;
+      }
+      if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
+      if (p1 < 0.f) lo = alpha; else hi = alpha;
+      float next = alpha - p1 / p2;
+      if (hi > 0.f && !(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      if (hi < 0.f && !(next > lo)) next = 2.f * alpha;
+      if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
+      alpha = next;
+    }
+    if (!ok || !(alpha > 0.f)) break;
+    impr = -0.5f * alpha * p1_0;
+    for (int k = 0; k < 6; ++k) x[k] += alpha * sd[k];
+    ++iter;
+  }
+  float fc[6] = {0, 0, 0, 0, 0, 0}, dummy = 0.f;
+  FE_FOR_MY_CONTACTS({
+    float f[3];
+    const int st = fe_cone(dot6(R.j[0], x) - aref[0], dot6(R.j[1], x) - aref[1], dot6(R.j[2], x) - aref[2], mu, fr, D0, D1, f, &dummy, nullptr);
+    w->c_state[c] = st;
+    for (int k = 0; k < 3; ++k) w->c_f[3 * c + k] = f[k];
+    for (int i = 0; i < 6; ++i) fc[i] += R.j[0][i] * f[0] + R.j[1][i] * f[1] + R.j[2][i] * f[2];
+  })
+#undef FE_FOR_MY_CONTACTS
+  for (int k = 0; k < 6; ++k) { w->x[z + k] = x[k]; w->fc[z + k] = fc[k]; }
+  return iter;
+}
+
+// mj_fwdConstraint: FAST scope when no constraint couples two moving blocks (every part solved by its own lane, robot
+// block cooperatively), FULL scope otherwise
+FE_FN void fe_solve(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int ncon = w->u[0], ne = m->neq, np = m->npart;
+  LANES_BEGIN
+    int coupled = 0;
+    for (int c = lane; c < ncon; c += 32) coupled |= w->c_kind[c] == 2;
+    for (int e = lane; e < ne; e += 32) coupled |= w->eq_active[e] != 0;
+    w->iscr[lane] = coupled;
+    if (lane == 0) w->u[3] = 0;
+  LANES_END
+  const bool coupled = fe_ballot32(w->iscr) != 0u;
+  w->fast = coupled ? 0 : 1;
+  w->nact = coupled ? m->nv : m->nr;
+  if (!coupled) {
+    LANES_BEGIN
+      int it = 0;
+      if (lane < np) it = fe_solve_part_lane(w, lane);
+      w->iscr[lane] = it;
+    LANES_END
+    LANES_BEGIN
+      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr[p] > mx ? w->iscr[p] : mx; w->u[3] = mx; w->u[4] = 0; }
+    LANES_END
+  } else { LANES_BEGIN if (lane == 0) w->u[4] = 1; LANES_END }
+  fe_solve_coop(w);
+  w->fast = 0;
+  w->nact = m->nv;
 }
 
 // ---------------------------------------------------------------- mj_Euler + mj_advance
