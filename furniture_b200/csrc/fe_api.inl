@@ -1,6 +1,7 @@
 // fe_api.inl -- host side of the C-ABI (include/furniture_b200.h), shared by the CUDA library (fe_cuda.cu) and the
 // lane-emulated test build (tests/emu/fe_emu.cpp).  The including file provides the plat_* functions.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -71,6 +72,7 @@ int fe_num_envs(const fe_handle* h) { return h->N; }
 int fe_obs_dim(const fe_handle* h) { return h->hs.obs_dim; }
 int fe_action_dim(const fe_handle* h) { return h->hs.act_dim; }
 int fe_info_dim(const fe_handle* h) { return FE_INFO_DIM; }
+int fe_smem_bytes_per_env(const fe_handle* h) { return (h->slice_words + FE_ENV_EXTRA_WORDS) * 4; }
 const float* fe_obs_dev(const fe_handle* h) { return h->es.obs; }
 
 int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob, size_t scene_bytes, const fe_config* cfg, int n_envs, int device,
@@ -88,10 +90,12 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
     if (h->hs.magic != FE_SCENE_MAGIC) { delete h; return fail(nullptr, -1, "fe_create: bad scene magic"); }
   }
   h->N = n_envs; h->device = device; h->cfg = *cfg;
-  h->opt.maxcon = cfg->maxcon > 0 ? cfg->maxcon : 48;
+  h->opt.maxcon = cfg->maxcon > 0 ? cfg->maxcon : 40;
   h->opt.newton_iters = cfg->newton_iters > 0 ? cfg->newton_iters : 30;
   h->opt.ls_iters = cfg->ls_iters > 0 ? cfg->ls_iters : 20;
   h->opt.tolerance = cfg->tolerance > 0 ? cfg->tolerance : 1e-6f;
+  h->opt.lockstep = 31;
+  if (const char* e = getenv("FE_LOCKSTEP")) h->opt.lockstep = atoi(e);
   if (h->opt.maxcon > 255) { delete h; return fail(nullptr, -1, "fe_create: maxcon must be <= 255"); }
   if (h->hm.ngeom > 255) { delete h; return fail(nullptr, -1, "fe_create: ngeom must be <= 255"); }
   int rc = plat_init(h);
@@ -117,7 +121,7 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   ALLOC(s.eq_data, float, 7 * m.neq, "eq_data", true) ALLOC(s.contype, int, m.ngeom, "geom_contype", true) ALLOC(s.conaff, int, m.ngeom, "geom_conaffinity", true)
   ALLOC(s.eq_active, int, m.neq, "eq_active", true) ALLOC(s.bias, float, m.nr, "qfrc_bias", false)
   ALLOC(s.lpos, float, 3 * m.nlink, "link_xpos", false) ALLOC(s.lquat, float, 4 * m.nlink, "link_xquat", false) ALLOC(s.lvel, float, 6 * m.nlink, "link_vel", false)
-  ALLOC(s.touch, int, m.npart, "touch", false) ALLOC(s.flags, int, 1, "flags", true) ALLOC(s.ncon, int, 1, "ncon", false) ALLOC(s.niter, int, 1, "niter", false)
+  ALLOC(s.touch, int, m.npart, "touch", false) ALLOC(s.flags, int, 1, "flags", true) ALLOC(s.ncon, int, 1, "ncon", false) ALLOC(s.niter, int, 1, "niter", false) ALLOC(s.stats, int, 4, "stats", false)
   FeDebug& d = h->dbg;
   ALLOC(d.Mr, float, m.nr * m.nr, "dbg_Mr", false) ALLOC(d.fs, float, m.nv, "dbg_fs", false) ALLOC(d.as, float, m.nv, "dbg_as", false)
   ALLOC(d.linert, float, 10 * m.nlink, "dbg_linert", false) ALLOC(d.x, float, m.nv, "dbg_x", false) ALLOC(d.fc, float, m.nv, "dbg_fc", false)

@@ -397,7 +397,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
 }
 
 // dispatch on the (ordered) type pair; geometry in world frame. Returns contact count (<= 8).
-FE_HD int fe_narrowphase(int t1, const float* p1, const float* R1, const float* s1, int t2, const float* p2, const float* R2, const float* s2, FeCon* out) {
+FE_HDN int fe_narrowphase(int t1, const float* p1, const float* R1, const float* s1, int t2, const float* p2, const float* R2, const float* s2, FeCon* out) {
   if (t1 == 0) {
     if (t2 == 2) return fe_plane_sphere(p1, R1, p2, s2[0], out);
     if (t2 == 5) return fe_plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], out);

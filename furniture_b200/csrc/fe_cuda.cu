@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #define PLAT_IS_CUDA 1
 struct fe_handle;
@@ -28,19 +29,20 @@ static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* 
 // ---------------------------------------------------------------- kernels
 extern __shared__ float fe_smem[];
 
-__global__ void __launch_bounds__(32) fe_sim_kernel(FeState s, const fe_model* __restrict__ m, FeOpt opt, int nsub, int mode, FeDebug dbg) {
-  const int env = blockIdx.x;
+#define FE_MAX_WPB 14
+__global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_sim_kernel(FeState s, const fe_model* __restrict__ m, FeOpt opt, int nsub, int mode, FeDebug dbg, int slice_words) {
+  const int wib = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + wib;
   if (env >= s.N) return;
-  fe_run_env(s, m, opt, env, nsub, mode, fe_smem, dbg);
+  fe_run_env(s, m, opt, env, nsub, mode, fe_smem + (size_t)wib * slice_words, dbg);
 }
 
-__global__ void __launch_bounds__(32) fe_env_step_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
+__global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_step_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
                                                          fe_config cfg, FeOpt opt, const float* __restrict__ actions, float* reward, uint8_t* done,
                                                          int32_t* info, int slice_words) {
-  const int env = blockIdx.x;
+  const int wib = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + wib;
   if (env >= st.N) return;
   FeEnv e;
-  fe_env_bind(&e, fe_smem, m, sc, &cfg, opt, st, es, env, slice_words);
+  fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
   fe_load(&e.w, st, env);
   fe_env_load_groups(&e);
   fe_env_step_one(&e, actions, reward, done, info);
@@ -48,13 +50,13 @@ __global__ void __launch_bounds__(32) fe_env_step_kernel(FeState st, FeEnvState 
   fe_store(&e.w, st, env);
 }
 
-__global__ void __launch_bounds__(32) fe_env_reset_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
+__global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
                                                           fe_config cfg, FeOpt opt, const uint8_t* __restrict__ mask, int slice_words) {
-  const int env = blockIdx.x;
+  const int wib = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + wib;
   if (env >= st.N) return;
   if (mask && !mask[env]) return;
   FeEnv e;
-  fe_env_bind(&e, fe_smem, m, sc, &cfg, opt, st, es, env, slice_words);
+  fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
   fe_load(&e.w, st, env);
   fe_env_load_groups(&e);
   fe_env_reset_one(&e);
@@ -77,6 +79,7 @@ __global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, 
 // ---------------------------------------------------------------- platform layer
 struct CudaPlat {
   size_t smem_sim = 0, smem_env = 0;
+  int wpb = 1;
   float* pin_act = nullptr;
   unsigned char* pin_out = nullptr;
   size_t out_bytes = 0;
@@ -93,8 +96,15 @@ static int plat_init(fe_handle* h) {
 static int plat_prepare(fe_handle* h) {
   CudaPlat* p = (CudaPlat*)h->plat;
   if (p->smem_sim) return 0;
-  p->smem_sim = (size_t)h->slice_words * 4;
-  p->smem_env = (size_t)(h->slice_words + FE_ENV_EXTRA_WORDS) * 4;
+  // warps (= envs) per block: as many as fit in 227 KB of shared memory, at most FE_MAX_WPB; FE_WPB overrides
+  const size_t per_env = (size_t)(h->slice_words + FE_ENV_EXTRA_WORDS) * 4;
+  int wpb = (int)((227 * 1024 - 1024) / per_env);
+  if (wpb > FE_MAX_WPB) wpb = FE_MAX_WPB;
+  if (const char* e = getenv("FE_WPB")) { int v = atoi(e); if (v >= 1 && v <= wpb) wpb = v; }
+  if (wpb < 1) return fail(h, -11, "model does not fit in shared memory");
+  p->wpb = wpb;
+  p->smem_sim = (size_t)h->slice_words * 4 * wpb;
+  p->smem_env = per_env * wpb;
   CUDA_OK(cudaFuncSetAttribute(fe_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sim));
   CUDA_OK(cudaFuncSetAttribute(fe_env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_env));
   CUDA_OK(cudaFuncSetAttribute(fe_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_env));
@@ -123,7 +133,7 @@ static int plat_run_sim(fe_handle* h, int nsub, int mode, void* stream) {
   int rc = plat_prepare(h);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
-  fe_sim_kernel<<<h->N, 32, p->smem_sim, (cudaStream_t)stream>>>(h->st, h->dm, h->opt, nsub, mode, h->dbg);
+  fe_sim_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_sim, (cudaStream_t)stream>>>(h->st, h->dm, h->opt, nsub, mode, h->dbg, h->slice_words);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -131,7 +141,7 @@ static int plat_run_reset(fe_handle* h, const uint8_t* mask, void* stream) {
   int rc = plat_prepare(h);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
-  fe_env_reset_kernel<<<h->N, 32, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, mask, h->slice_words);
+  fe_env_reset_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, mask, h->slice_words);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -139,7 +149,7 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
   int rc = plat_prepare(h);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
-  fe_env_step_kernel<<<h->N, 32, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words);
+  fe_env_step_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -152,7 +162,7 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
   // the private stream does not order against work the caller issued on other streams (fe_sim_forward, fe_set_field ...)
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpyAsync(h->dev_act, p->pin_act, ab, cudaMemcpyHostToDevice, p->stream));
-  fe_env_step_kernel<<<h->N, 32, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
+  fe_env_step_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
                                                             (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words);
   CUDA_OK(cudaGetLastError());
   unsigned char* o = p->pin_out;

@@ -26,6 +26,7 @@ struct FeOpt {
   int newton_iters; // max Newton iterations
   int ls_iters;     // max line-search evaluations
   float tolerance;  // scaled improvement / gradient tolerance (MuJoCo: 1e-8 in double)
+  int lockstep;     // bit k: block barrier before phase k of fe_substep_lockstep (instruction-fetch sharing)
 };
 
 // ---- shared-memory layout of one warp (all sizes in 4-byte words)
@@ -42,7 +43,7 @@ struct FeWarp {
   int *cand, *touch;
   // contacts (SoA, maxcon each)
   float *c_dist, *c_pos, *c_frame, *c_aref, *c_D, *c_mu, *c_fric, *c_jar, *c_jv, *c_f;
-  int *c_geom, *c_link, *c_state, *c_kind;
+  int *c_geom, *c_link, *c_state, *c_kind, *plist;
   // welds (neq each) and limits (nr each)
   float *w_r1, *w_G, *w_aref, *w_D, *w_jar, *w_jv, *w_f;
   float *l_sign, *l_aref, *l_D, *l_jar, *l_jv, *l_f;
@@ -67,14 +68,16 @@ FE_BOTH int fe_warp_bind(FeWarp* w, float* base, const fe_model* m, const FeOpt&
   CARVE_F(qpos, nq) CARVE_F(qvel, nv) CARVE_F(warm, nv) CARVE_F(ctrl, nu) CARVE_F(qfrc_applied, nr) CARVE_F(gravcomp, np) CARVE_F(eq_data, 7 * ne)
   CARVE_I(contype, ng) CARVE_I(conaff, ng) CARVE_I(eq_active, ne)
   CARVE_F(lpos, 3 * nl) CARVE_F(lquat, 4 * nl) CARVE_F(lmat, 9 * nl) CARVE_F(S, 6 * nr) CARVE_F(lvel, 6 * nl) CARVE_F(lacc, 6 * nl) CARVE_F(lfrc, 6 * nl)
-  CARVE_F(linert, 10 * nl) CARVE_F(lcrb, 10 * nr) CARVE_F(Mr, nr * nr) CARVE_F(Lr, fe_tri(nr)) CARVE_F(fs, nv) CARVE_F(as, nv) CARVE_F(bias, nr) CARVE_F(lacc2, 6 * nl)
+  w->lacc2 = w->lfrc; /* RNE wrench (smooth stage) and solver link accelerations are never live together */
+  CARVE_F(linert, 10 * nl) CARVE_F(lcrb, (10 * nr > 96 ? 10 * nr : 96)) CARVE_F(Mr, nr * nr) CARVE_F(Lr, fe_tri(nr)) CARVE_F(fs, nv) CARVE_F(as, nv) CARVE_F(bias, nr)
   CARVE_I(touch, np)
   CARVE_F(c_dist, mc) CARVE_F(c_pos, 3 * mc) CARVE_F(c_frame, 9 * mc) CARVE_F(c_aref, 3 * mc) CARVE_F(c_D, 2 * mc) CARVE_F(c_mu, mc) CARVE_F(c_fric, mc)
-  CARVE_F(c_jar, 3 * mc) CARVE_F(c_jv, 3 * mc) CARVE_F(c_f, 3 * mc) CARVE_I(c_geom, mc) CARVE_I(c_link, mc) CARVE_I(c_state, mc) CARVE_I(c_kind, mc)
+  CARVE_F(c_jar, 3 * mc) CARVE_F(c_jv, 3 * mc) CARVE_F(c_f, 3 * mc) CARVE_I(c_geom, mc) CARVE_I(c_link, mc) CARVE_I(c_state, mc) CARVE_I(c_kind, mc) CARVE_I(plist, 9 * np)
   CARVE_F(w_r1, 3 * ne) CARVE_F(w_G, 9 * ne) CARVE_F(w_aref, 6 * ne) CARVE_F(w_D, 6 * ne) CARVE_F(w_jar, 6 * ne) CARVE_F(w_jv, 6 * ne) CARVE_F(w_f, 6 * ne)
   CARVE_F(l_sign, nr) CARVE_F(l_aref, nr) CARVE_F(l_D, nr) CARVE_F(l_jar, nr) CARVE_F(l_jv, nr) CARVE_F(l_f, nr)
   CARVE_F(x, nv) CARVE_F(Ma, nv) CARVE_F(grad, nv) CARVE_F(search, nv) CARVE_F(Mv, nv) CARVE_F(fc, nv)
-  CARVE_F(Jc, 3 * 32) CARVE_F(scr, 3 * 32) CARVE_I(first, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 8)
+  w->Jc = w->lcrb; /* composite inertias (smooth stage) vs row staging of fe_build_H */
+  CARVE_F(scr, 2 * 32) CARVE_I(first, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 8)
   // H (solver) and the collision scratch (geom poses, candidate list) are never live together: overlay them
   int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
   int big = hwords > cwords ? hwords : cwords;
@@ -87,7 +90,7 @@ FE_BOTH int fe_warp_bind(FeWarp* w, float* base, const fe_model* m, const FeOpt&
 }
 
 // ---------------------------------------------------------------- 6x6 SPD helpers (packed lower, index i(i+1)/2+j)
-FE_HD void fe_inert_sym6(float* A, const float* I, float diag_add) {
+FE_HDN void fe_inert_sym6(float* A, const float* I, float diag_add) {
   const float m = I[0], hx = I[1], hy = I[2], hz = I[3];
   // rows 0-2: [Io, [h]x]; rows 3-5: [[h]x^T, m 1]
   A[0] = I[4] + diag_add;
@@ -98,7 +101,7 @@ FE_HD void fe_inert_sym6(float* A, const float* I, float diag_add) {
   A[10] = -hz; A[11] = 0.f; A[12] = hx; A[13] = 0.f; A[14] = m + diag_add;
   A[15] = hy; A[16] = -hx; A[17] = 0.f; A[18] = 0.f; A[19] = 0.f; A[20] = m + diag_add;
 }
-FE_HD bool fe_chol6(float* A) {
+FE_HDN bool fe_chol6(float* A) {
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -118,7 +121,7 @@ FE_HD bool fe_chol6(float* A) {
   }
   return ok;
 }
-FE_HD void fe_chol6_solve(const float* L, float* x) {
+FE_HDN void fe_chol6_solve(const float* L, float* x) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     float s = x[i];
@@ -1028,6 +1031,7 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     LANES_END
     return;
   }
+  LANES_BEGIN if (lane == 0) w->u[6] += 1; LANES_END
   const float scale = 1.0f / (m->meaninertia * (float)(m->nv > 1 ? m->nv : 1));
   // warm start candidate (stored in qacc coordinates) -> z coordinates; pick the cheaper of warm / smooth
   float best = 0.f;
@@ -1126,27 +1130,15 @@ FE_FN void fe_solve_coop(FeWarp* w) {
   }
   fe_update(w);
   fe_mul_JT(w, w->fc);
-  LANES_BEGIN if (lane == 0 && iter > w->u[3]) w->u[3] = iter; LANES_END
+  LANES_BEGIN if (lane == 0) { if (iter > w->u[3]) w->u[3] = iter; w->u[7] += iter; } LANES_END
 }
 
 
 // ---- single-lane Newton solve of one free part whose contacts are all against the static world (FAST scope).
 // Same cost, cones and exact line search as the cooperative solver, on the part's own 6 unknowns [alpha; vdot]; the
 // blocks are independent in that case, so block-wise Newton converges to the same minimiser as MuJoCo's global iteration.
-struct FeRow3 { float j[3][6]; };
-FE_HD void fe_part_rows(const FeWarp* w, int c, int l, float sgn, FeRow3* R) {
-  const float* F = w->c_frame + 9 * c;
-  float r[3];
-  v3sub(r, w->c_pos + 3 * c, w->lpos + 3 * l);
-  for (int k = 0; k < 3; ++k) {
-    float t[3];
-    v3cross(t, r, F + 3 * k);
-    R->j[k][0] = sgn * t[0]; R->j[k][1] = sgn * t[1]; R->j[k][2] = sgn * t[2];
-    R->j[k][3] = sgn * F[3 * k]; R->j[k][4] = sgn * F[3 * k + 1]; R->j[k][5] = sgn * F[3 * k + 2];
-  }
-}
 // zone logic of one elliptic contact: forces f, cost, and (if W) the 3x3 weight (xx yy zz xy xz yz); returns state
-FE_HD int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
+FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
   const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
   if (N >= mu * T || (T <= 0.f && N >= 0.f)) { f[0] = f[1] = f[2] = 0.f; return 0; }
   if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
@@ -1168,151 +1160,238 @@ FE_HD int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, fl
   }
   return 2;
 }
-FE_HD int fe_solve_part_lane(FeWarp* w, int p) {
-  const fe_model* m = w->m;
-  const int nr = m->nr, l = m->nrlink + p, z = nr + 6 * p, ncon = w->u[0], da = m->link_dadr[l];
-  const float* I = w->linert + 10 * l;
-  // MuJoCo scales cost improvement / gradient by 1/(meaninertia * nv) of the whole model; a 1.2 g leg would then stop
-  // three orders of magnitude early next to the 5 kg arm links, so the block uses its own mean inertia
-  const float scale = 1.0f / (3.f * I[0] + I[4] + I[5] + I[6]), tol = w->opt.tolerance;
-  float fs[6], as[6], x[6];
-  for (int k = 0; k < 6; ++k) { fs[k] = w->fs[z + k]; as[k] = w->as[z + k]; }
-  int mine = 0;
-  for (int c = 0; c < ncon; ++c) {
-    if (w->c_kind[c] != 0) continue;
-    const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
-    if (A == l || B == l) ++mine;
+// rows of one part-vs-world contact in the part's coordinates: J[k] = sgn * [(r x F_k), F_k], r = pos - origin
+FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
+  const float* F = w->c_frame + 9 * c;
+  float r[3];
+  v3sub(r, w->c_pos + 3 * c, w->lpos + 3 * l);
+  for (int k = 0; k < 3; ++k) {
+    float t[3];
+    v3cross(t, r, F + 3 * k);
+    J[6 * k + 0] = sgn * t[0]; J[6 * k + 1] = sgn * t[1]; J[6 * k + 2] = sgn * t[2];
+    J[6 * k + 3] = sgn * F[3 * k]; J[6 * k + 4] = sgn * F[3 * k + 1]; J[6 * k + 5] = sgn * F[3 * k + 2];
   }
-  if (mine == 0) {
-    for (int k = 0; k < 6; ++k) { w->x[z + k] = as[k]; w->fc[z + k] = 0.f; }
-    return 0;
-  }
-#define FE_FOR_MY_CONTACTS(...)                                                          \
-  for (int c = 0; c < ncon; ++c) {                                                       \
-    if (w->c_kind[c] != 0) continue;                                                     \
-    const int A_ = (w->c_link[c] & 255) - 1, B_ = (w->c_link[c] >> 8) - 1;               \
-    if (A_ != l && B_ != l) continue;                                                    \
-    const float sgn = B_ == l ? 1.f : -1.f;                                              \
-    FeRow3 R;                                                                            \
-    fe_part_rows(w, c, l, sgn, &R);                                                      \
-    const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1]; \
-    const float* aref = w->c_aref + 3 * c;                                               \
-    __VA_ARGS__                                                                          \
-  }
-  // warm start (qacc coordinates -> z) against the unconstrained acceleration: keep the cheaper one
-  float xw[6];
-  m3mulv(xw, w->lmat + 9 * l, w->warm + da + 3);
-  v3cpy(xw + 3, w->warm + da);
-  float cw = 0.f, cs = 0.f;
-  {
-    float Mx[6];
-    inert_mulv(Mx, I, xw);
-    for (int k = 0; k < 6; ++k) cw += 0.5f * (Mx[k] - fs[k]) * (xw[k] - as[k]);
-  }
-  FE_FOR_MY_CONTACTS({
-    float f[3];
-    fe_cone(dot6(R.j[0], xw) - aref[0], dot6(R.j[1], xw) - aref[1], dot6(R.j[2], xw) - aref[2], mu, fr, D0, D1, f, &cw, nullptr);
-    fe_cone(dot6(R.j[0], as) - aref[0], dot6(R.j[1], as) - aref[1], dot6(R.j[2], as) - aref[2], mu, fr, D0, D1, f, &cs, nullptr);
-  })
-  const bool use_warm = !(cs < cw) && (cw == cw);
-  for (int k = 0; k < 6; ++k) x[k] = use_warm ? xw[k] : as[k];
-  int iter = 0;
-  float impr = 0.f;
-  for (;;) {
-    float Mx[6], g[6], H[21], ccost = 0.f;
-    inert_mulv(Mx, I, x);
-    for (int k = 0; k < 6; ++k) g[k] = Mx[k] - fs[k];
-    fe_inert_sym6(H, I, 0.f);
-    FE_FOR_MY_CONTACTS({
-      float f[3], W[6];
-      const int st = fe_cone(dot6(R.j[0], x) - aref[0], dot6(R.j[1], x) - aref[1], dot6(R.j[2], x) - aref[2], mu, fr, D0, D1, f, &ccost, W);
-      if (st != 0) {
-        float WJ[3][6];
-        for (int i = 0; i < 6; ++i) {
-          g[i] -= R.j[0][i] * f[0] + R.j[1][i] * f[1] + R.j[2][i] * f[2];
-          WJ[0][i] = W[0] * R.j[0][i] + W[3] * R.j[1][i] + W[4] * R.j[2][i];
-          WJ[1][i] = W[3] * R.j[0][i] + W[1] * R.j[1][i] + W[5] * R.j[2][i];
-          WJ[2][i] = W[4] * R.j[0][i] + W[5] * R.j[1][i] + W[2] * R.j[2][i];
-        }
-        for (int i = 0; i < 6; ++i)
-          for (int j = 0; j <= i; ++j) H[i * (i + 1) / 2 + j] += R.j[0][i] * WJ[0][j] + R.j[1][i] * WJ[1][j] + R.j[2][i] * WJ[2][j];
-      }
-    })
-    float gsq = 0.f;
-    for (int k = 0; k < 6; ++k) gsq += g[k] * g[k];
-    const float gnorm = sqrtf(gsq);
-    if (!(gnorm == gnorm)) { w->u[2] |= 2; break; }
-    if (iter > 0) { if (scale * impr < tol || scale * gnorm < tol) break; }
-    else if (scale * gnorm < tol) break;
-    if (iter >= w->opt.newton_iters) break;
-    if (!fe_chol6(H)) w->u[2] |= 4;
-    float sd[6], Ms[6];
-    for (int k = 0; k < 6; ++k) sd[k] = -g[k];
-    fe_chol6_solve(H, sd);
-    inert_mulv(Ms, I, sd);
-    float g1 = 0.f, g2 = 0.f;
-    for (int k = 0; k < 6; ++k) { g1 += sd[k] * (Mx[k] - fs[k]); g2 += 0.5f * sd[k] * Ms[k]; }
-    // exact line search (same safeguarded Newton as the cooperative solver)
-    float alpha = 0.f, lo = 0.f, hi = -1.f, p1_0 = 0.f;
-    bool ok = true;
-    for (int ls = 0; ls <= w->opt.ls_iters; ++ls) {
-      float p1 = g1 + 2.f * alpha * g2, p2 = 2.f * g2;
-      FE_FOR_MY_CONTACTS({
-        const float v0 = dot6(R.j[0], sd), v1 = dot6(R.j[1], sd), v2 = dot6(R.j[2], sd);
-        const float x0 = dot6(R.j[0], x) - aref[0] + alpha * v0, x1 = dot6(R.j[1], x) - aref[1] + alpha * v1, x2 = dot6(R.j[2], x) - aref[2] + alpha * v2;
-        const float N = x0 * mu, U1 = x1 * fr, U2 = x2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
-        if (N >= mu * T || (T <= 0.f && N >= 0.f)) {
-        } else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
-          p1 += D0 * x0 * v0 + D1 * (x1 * v1 + x2 * v2);
-          p2 += D0 * v0 * v0 + D1 * (v1 * v1 + v2 * v2);
-        } else {
-          const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T, N1 = v0 * mu, V1 = v1 * fr, V2 = v2 * fr;
-          const float T1 = (U1 * V1 + U2 * V2) / T, T2 = (V1 * V1 + V2 * V2 - T1 * T1) / T, a = N1 - mu * T1;
-          p1 += Dm * NmT * a;
-          p2 += Dm * (a * a - NmT * mu * T2);
-        }
-      })
-      if (ls == 0) {
-        if (!(p1 < 0.f) || !(p2 > 0.f)) { ok = false; break; }
-        p1_0 = p1;
-        alpha = -p1 / p2;
-        continue;
-      }
-      if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
-      if (p1 < 0.f) lo = alpha; else hi = alpha;
-      float next = alpha - p1 / p2;
-      if (hi > 0.f && !(next > lo && next < hi)) next = 0.5f * (lo + hi);
-      if (hi < 0.f && !(next > lo)) next = 2.f * alpha;
-      if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
-      alpha = next;
-    }
-    if (!ok || !(alpha > 0.f)) break;
-    impr = -0.5f * alpha * p1_0;
-    for (int k = 0; k < 6; ++k) x[k] += alpha * sd[k];
-    ++iter;
-  }
-  float fc[6] = {0, 0, 0, 0, 0, 0}, dummy = 0.f;
-  FE_FOR_MY_CONTACTS({
-    float f[3];
-    const int st = fe_cone(dot6(R.j[0], x) - aref[0], dot6(R.j[1], x) - aref[1], dot6(R.j[2], x) - aref[2], mu, fr, D0, D1, f, &dummy, nullptr);
-    w->c_state[c] = st;
-    for (int k = 0; k < 3; ++k) w->c_f[3 * c + k] = f[k];
-    for (int i = 0; i < 6; ++i) fc[i] += R.j[0][i] * f[0] + R.j[1][i] * f[1] + R.j[2][i] * f[2];
-  })
-#undef FE_FOR_MY_CONTACTS
-  for (int k = 0; k < 6; ++k) { w->x[z + k] = x[k]; w->fc[z + k] = fc[k]; }
-  return iter;
 }
 
-// mj_fwdConstraint: FAST scope when no constraint couples two moving blocks (every part solved by its own lane, robot
+// FAST scope, free parts: 8 lanes per part (4 parts per pass), one lane per contact.  Per Newton iteration each lane
+// evaluates its contact (cone zone, force, 3x3 weight, J^T f and J^T W J), the group sums them with 3 xor-shuffles per
+// value, every lane of the group then factors the same 6x6 Hessian and runs the same exact line search, whose
+// per-contact terms are again group-summed.  Parts are independent blocks here, so block-wise Newton reaches the same
+// minimiser as the global iteration.
+FE_FN void fe_solve_parts_grouped(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink, np = m->npart, maxit = w->opt.newton_iters, maxls = w->opt.ls_iters;
+  const float tol = w->opt.tolerance;
+  for (int pass = 0; pass * 4 < np; ++pass) {
+    FE_PRIV(int, c_); FE_PRIV(int, part_); FE_PRIV(int, act_); FE_PRIV(int, iter_); FE_PRIV(int, lsact_);
+    FE_PRIVA(float, J_, 18); FE_PRIVA(float, par_, 7);
+    FE_PRIVA(float, I_, 10); FE_PRIVA(float, fs_, 6); FE_PRIVA(float, as_, 6); FE_PRIVA(float, x_, 6); FE_PRIVA(float, xw_, 6);
+    FE_PRIVA(float, acc_, 28); FE_PRIVA(float, sd_, 6); FE_PRIVA(float, Mx_, 6); FE_PRIVA(float, jx_, 3); FE_PRIVA(float, jv_, 3);
+    FE_PRIV(float, scale_); FE_PRIV(float, impr_); FE_PRIV(float, g1_); FE_PRIV(float, g2_); FE_PRIV(float, alpha_);
+    FE_PRIV(float, lo_); FE_PRIV(float, hi_); FE_PRIV(float, p10_);
+    LANES_BEGIN
+      const int part = pass * 4 + (lane >> 3), slot = lane & 7;
+      PV(part_) = part < np ? part : -1;
+      PV(c_) = -1; PV(act_) = 0; PV(iter_) = 0; PV(impr_) = 0.f; PV(lsact_) = 0;
+      PV(acc_)[0] = 0.f; PV(acc_)[1] = 0.f;
+      if (part < np) {
+        const int l = nrl + part, z = nr + 6 * part, da = m->link_dadr[l];
+        const int cnt = w->plist[9 * part + 8];
+        if (cnt > 0) PV(act_) = 1;
+        if (slot < cnt) PV(c_) = w->plist[9 * part + slot];
+        for (int k = 0; k < 10; ++k) PV(I_)[k] = w->linert[10 * l + k];
+        for (int k = 0; k < 6; ++k) { PV(fs_)[k] = w->fs[z + k]; PV(as_)[k] = w->as[z + k]; }
+        PV(scale_) = 1.0f / (3.f * PV(I_)[0] + PV(I_)[4] + PV(I_)[5] + PV(I_)[6]);
+        m3mulv(PV(xw_), w->lmat + 9 * l, w->warm + da + 3);
+        v3cpy(PV(xw_) + 3, w->warm + da);
+        const int c = PV(c_);
+        if (c >= 0) {
+          const int B_ = (w->c_link[c] >> 8) - 1;
+          fe_part_rows(w, c, l, B_ == l ? 1.f : -1.f, PV(J_));
+          PV(par_)[0] = w->c_aref[3 * c]; PV(par_)[1] = w->c_aref[3 * c + 1]; PV(par_)[2] = w->c_aref[3 * c + 2];
+          PV(par_)[3] = w->c_D[2 * c]; PV(par_)[4] = w->c_D[2 * c + 1]; PV(par_)[5] = w->c_mu[c]; PV(par_)[6] = w->c_fric[c];
+          float f[3], cw = 0.f, cs = 0.f;
+          const float* J = PV(J_);
+          const float* q = PV(par_);
+          fe_cone(dot6(J, PV(xw_)) - q[0], dot6(J + 6, PV(xw_)) - q[1], dot6(J + 12, PV(xw_)) - q[2], q[5], q[6], q[3], q[4], f, &cw, nullptr);
+          fe_cone(dot6(J, PV(as_)) - q[0], dot6(J + 6, PV(as_)) - q[1], dot6(J + 12, PV(as_)) - q[2], q[5], q[6], q[3], q[4], f, &cs, nullptr);
+          PV(acc_)[0] = cw; PV(acc_)[1] = cs;
+        }
+      }
+    LANES_END
+    FE_GSUM8_ARRN(acc_, 28, 2);
+    LANES_BEGIN
+      if (PV(part_) >= 0) { // warm start vs unconstrained acceleration: keep the cheaper one
+        float Mx[6], cw = PV(acc_)[0];
+        inert_mulv(Mx, PV(I_), PV(xw_));
+        for (int k = 0; k < 6; ++k) cw += 0.5f * (Mx[k] - PV(fs_)[k]) * (PV(xw_)[k] - PV(as_)[k]);
+        const bool use_warm = !(PV(acc_)[1] < cw) && (cw == cw);
+        for (int k = 0; k < 6; ++k) PV(x_)[k] = use_warm ? PV(xw_)[k] : PV(as_)[k];
+      }
+    LANES_END
+    for (int it = 0; it <= maxit; ++it) {
+      if (!FE_ANY(act_)) break;
+      // per-contact terms at the current x
+      LANES_BEGIN
+        for (int k = 0; k < 28; ++k) PV(acc_)[k] = 0.f;
+        const int c = PV(c_);
+        if (PV(act_) && c >= 0) {
+          const float* J = PV(J_);
+          const float* q = PV(par_);
+          float f[3], W[6], cc = 0.f;
+          const int st = fe_cone(dot6(J, PV(x_)) - q[0], dot6(J + 6, PV(x_)) - q[1], dot6(J + 12, PV(x_)) - q[2], q[5], q[6], q[3], q[4], f, &cc, W);
+          if (st != 0) {
+            float WJ[18];
+            for (int i = 0; i < 6; ++i) {
+              PV(acc_)[i] = -(J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2]);
+              WJ[i] = W[0] * J[i] + W[3] * J[6 + i] + W[4] * J[12 + i];
+              WJ[6 + i] = W[3] * J[i] + W[1] * J[6 + i] + W[5] * J[12 + i];
+              WJ[12 + i] = W[4] * J[i] + W[5] * J[6 + i] + W[2] * J[12 + i];
+            }
+            for (int i = 0; i < 6; ++i)
+              for (int j = 0; j <= i; ++j) PV(acc_)[6 + i * (i + 1) / 2 + j] = J[i] * WJ[j] + J[6 + i] * WJ[6 + j] + J[12 + i] * WJ[12 + j];
+          }
+          PV(acc_)[27] = cc;
+        }
+      LANES_END
+      FE_GSUM8_ARR(acc_, 28);
+      // gradient, Hessian, convergence test, Newton direction (identical in the 8 lanes of a group)
+      LANES_BEGIN
+        if (PV(act_)) {
+          float g[6], H[21], gsq = 0.f;
+          inert_mulv(PV(Mx_), PV(I_), PV(x_));
+          fe_inert_sym6(H, PV(I_), 0.f);
+          for (int k = 0; k < 6; ++k) { g[k] = PV(Mx_)[k] - PV(fs_)[k] + PV(acc_)[k]; gsq += g[k] * g[k]; }
+          for (int k = 0; k < 21; ++k) H[k] += PV(acc_)[6 + k];
+          const float gnorm = sqrtf(gsq);
+          bool stop = false;
+          if (!(gnorm == gnorm)) { stop = true; if ((lane & 7) == 0) w->u[2] |= 2; }
+          else if (PV(iter_) > 0) stop = PV(scale_) * PV(impr_) < tol || PV(scale_) * gnorm < tol;
+          else stop = PV(scale_) * gnorm < tol;
+          if (PV(iter_) >= maxit) stop = true;
+          if (stop) PV(act_) = 0;
+          else {
+            if (!fe_chol6(H) && (lane & 7) == 0) w->u[2] |= 4;
+            for (int k = 0; k < 6; ++k) PV(sd_)[k] = -g[k];
+            fe_chol6_solve(H, PV(sd_));
+            float Ms[6], g1 = 0.f, g2 = 0.f;
+            inert_mulv(Ms, PV(I_), PV(sd_));
+            for (int k = 0; k < 6; ++k) { g1 += PV(sd_)[k] * (PV(Mx_)[k] - PV(fs_)[k]); g2 += 0.5f * PV(sd_)[k] * Ms[k]; }
+            PV(g1_) = g1; PV(g2_) = g2; PV(alpha_) = 0.f; PV(lo_) = 0.f; PV(hi_) = -1.f; PV(lsact_) = 1;
+            if (PV(c_) >= 0) {
+              const float* J = PV(J_);
+              for (int k = 0; k < 3; ++k) { PV(jx_)[k] = dot6(J + 6 * k, PV(x_)) - PV(par_)[k]; PV(jv_)[k] = dot6(J + 6 * k, PV(sd_)); }
+            }
+          }
+        }
+        if (!PV(act_)) PV(lsact_) = 0;
+      LANES_END
+      // exact line search; evaluation 0 is at alpha = 0
+      for (int ls = 0; ls <= maxls; ++ls) {
+        if (!FE_ANY(lsact_)) break;
+        LANES_BEGIN
+          float p1 = 0.f, p2 = 0.f;
+          if (PV(lsact_) && PV(c_) >= 0) {
+            const float* q = PV(par_);
+            const float al = PV(alpha_), mu = q[5], fr = q[6], D0 = q[3], D1 = q[4];
+            const float v0 = PV(jv_)[0], v1 = PV(jv_)[1], v2 = PV(jv_)[2];
+            const float x0 = PV(jx_)[0] + al * v0, x1 = PV(jx_)[1] + al * v1, x2 = PV(jx_)[2] + al * v2;
+            const float N = x0 * mu, U1 = x1 * fr, U2 = x2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+            if (N >= mu * T || (T <= 0.f && N >= 0.f)) {
+            } else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+              p1 = D0 * x0 * v0 + D1 * (x1 * v1 + x2 * v2);
+              p2 = D0 * v0 * v0 + D1 * (v1 * v1 + v2 * v2);
+            } else {
+              const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T, N1 = v0 * mu, V1 = v1 * fr, V2 = v2 * fr;
+              const float T1 = (U1 * V1 + U2 * V2) / T, T2 = (V1 * V1 + V2 * V2 - T1 * T1) / T, a = N1 - mu * T1;
+              p1 = Dm * NmT * a;
+              p2 = Dm * (a * a - NmT * mu * T2);
+            }
+          }
+          PV(acc_)[0] = p1; PV(acc_)[1] = p2;
+        LANES_END
+        FE_GSUM8_ARRN(acc_, 28, 2);
+        LANES_BEGIN
+          if (PV(lsact_)) {
+            const float al = PV(alpha_);
+            const float p1 = PV(acc_)[0] + PV(g1_) + 2.f * al * PV(g2_), p2 = PV(acc_)[1] + 2.f * PV(g2_);
+            if (ls == 0) {
+              if (!(p1 < 0.f) || !(p2 > 0.f)) { PV(lsact_) = 0; PV(act_) = 0; PV(alpha_) = 0.f; }
+              else { PV(p10_) = p1; PV(alpha_) = -p1 / p2; }
+            } else if (fabsf(p1) <= 1e-5f * fabsf(PV(p10_))) PV(lsact_) = 0;
+            else {
+              if (p1 < 0.f) PV(lo_) = al; else PV(hi_) = al;
+              float next = al - p1 / p2;
+              if (PV(hi_) > 0.f && !(next > PV(lo_) && next < PV(hi_))) next = 0.5f * (PV(lo_) + PV(hi_));
+              if (PV(hi_) < 0.f && !(next > PV(lo_))) next = 2.f * al;
+              if (fabsf(next - al) <= 1e-6f * fabsf(al)) PV(lsact_) = 0;
+              PV(alpha_) = next;
+            }
+          }
+        LANES_END
+      }
+      LANES_BEGIN
+        if (PV(act_)) {
+          const float al = PV(alpha_);
+          if (!(al > 0.f)) PV(act_) = 0;
+          else {
+            PV(impr_) = -0.5f * al * PV(p10_);
+            for (int k = 0; k < 6; ++k) PV(x_)[k] += al * PV(sd_)[k];
+            PV(iter_) += 1;
+          }
+        }
+        PV(lsact_) = 0;
+      LANES_END
+    }
+    // final forces of this pass' contacts, constraint wrench of each part
+    LANES_BEGIN
+      for (int k = 0; k < 6; ++k) PV(acc_)[k] = 0.f;
+      const int c = PV(c_);
+      if (c >= 0) {
+        const float* J = PV(J_);
+        const float* q = PV(par_);
+        float f[3], dummy = 0.f;
+        const int st = fe_cone(dot6(J, PV(x_)) - q[0], dot6(J + 6, PV(x_)) - q[1], dot6(J + 12, PV(x_)) - q[2], q[5], q[6], q[3], q[4], f, &dummy, nullptr);
+        w->c_state[c] = st;
+        for (int k = 0; k < 3; ++k) w->c_f[3 * c + k] = f[k];
+        for (int i = 0; i < 6; ++i) PV(acc_)[i] = J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2];
+      }
+    LANES_END
+    FE_GSUM8_ARRN(acc_, 28, 6);
+    LANES_BEGIN
+      const int part = PV(part_);
+      if (part >= 0 && (lane & 7) == 0) {
+        const int z = nr + 6 * part;
+        const bool any = w->plist[9 * part + 8] > 0;
+        for (int k = 0; k < 6; ++k) { w->x[z + k] = any ? PV(x_)[k] : PV(as_)[k]; w->fc[z + k] = any ? PV(acc_)[k] : 0.f; }
+        w->iscr[part] = PV(iter_);
+      }
+    LANES_END
+  }
+}
+
+// mj_fwdConstraint: FAST scope when no constraint couples two moving blocks (free parts solved 8 lanes per part, robot
 // block cooperatively), FULL scope otherwise
 FE_FN void fe_solve(FeWarp* w) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], ne = m->neq, np = m->npart;
+  const int ncon = w->u[0], ne = m->neq, np = m->npart, nrl = m->nrlink;
   LANES_BEGIN
     int coupled = 0;
     for (int c = lane; c < ncon; c += 32) coupled |= w->c_kind[c] == 2;
     for (int e = lane; e < ne; e += 32) coupled |= w->eq_active[e] != 0;
+    if (lane < np) { // contacts of part `lane` against the static world (at most 8 handled by the grouped solver)
+      const int l = nrl + lane;
+      int cnt = 0;
+      for (int c = 0; c < ncon; ++c) {
+        if (w->c_kind[c] != 0) continue;
+        const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+        if (A != l && B != l) continue;
+        if (cnt < 8) w->plist[9 * lane + cnt] = c;
+        ++cnt;
+      }
+      w->plist[9 * lane + 8] = cnt;
+      if (cnt > 8) coupled = 1;
+    }
     w->iscr[lane] = coupled;
     if (lane == 0) w->u[3] = 0;
   LANES_END
@@ -1320,15 +1399,11 @@ FE_FN void fe_solve(FeWarp* w) {
   w->fast = coupled ? 0 : 1;
   w->nact = coupled ? m->nv : m->nr;
   if (!coupled) {
-    LANES_BEGIN
-      int it = 0;
-      if (lane < np) it = fe_solve_part_lane(w, lane);
-      w->iscr[lane] = it;
-    LANES_END
+    fe_solve_parts_grouped(w);
     LANES_BEGIN
       if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr[p] > mx ? w->iscr[p] : mx; w->u[3] = mx; w->u[4] = 0; }
     LANES_END
-  } else { LANES_BEGIN if (lane == 0) w->u[4] = 1; LANES_END }
+  } else { LANES_BEGIN if (lane == 0) { w->u[4] = 1; w->u[5] += 1; } LANES_END }
   fe_solve_coop(w);
   w->fast = 0;
   w->nact = m->nv;
@@ -1408,4 +1483,15 @@ FE_FN void fe_forward(FeWarp* w) {
 FE_FN void fe_substep(FeWarp* w) {
   fe_forward(w);
   fe_integrate(w);
+}
+// same step with block barriers between the phases: the warps (= envs) of a block then fetch the same instructions at the
+// same time, which is what keeps the instruction cache effective for this large, mostly straight-line code.  Only legal
+// where every live warp of the block executes the same number of steps (the nsub loop of an env step).
+FE_FN void fe_substep_lockstep(FeWarp* w) {
+  const int ls = w->opt.lockstep;
+  if (ls & 1) { FE_BLOCK_SYNC; } fe_kin_smooth(w);
+  if (ls & 2) { FE_BLOCK_SYNC; } fe_collide(w);
+  if (ls & 4) { FE_BLOCK_SYNC; } fe_assemble(w);
+  if (ls & 8) { FE_BLOCK_SYNC; } fe_solve(w);
+  if (ls & 16) { FE_BLOCK_SYNC; } fe_integrate(w);
 }

@@ -76,7 +76,7 @@ FE_HD void np_unit_vector_f32(double* out, const double* v) {
 FE_HD double np_cos_siml(const double* a, const double* b) { return nddiv(nddiv(npdot(a, b), npnorm(a)), npnorm(b)); }
 FE_HD void np_normed(double* r, const double* a) { double n = npnorm(a); r[0] = nddiv(a[0], n); r[1] = nddiv(a[1], n); r[2] = nddiv(a[2], n); }
 // transform_utils.lookat_to_quat(forward, up) -> xyzw, returned here as wxyz (convert_quat(..., "wxyz"))
-FE_HD void np_lookat_wxyz(double* out, const double* forward, const double* up) {
+FE_HDN void np_lookat_wxyz(double* out, const double* forward, const double* up) {
   double v[3], v2[3], v3[3], t[3], q[4] = {0, 0, 0, 0};
   np_normed(v, forward);
   np_normed(t, up);
@@ -104,7 +104,7 @@ FE_HD void np_lookat_wxyz(double* out, const double* forward, const double* up) 
 }
 // FurnitureEnv._is_aligned (furniture.py:1057-1153). m*: row-major site rotation. cs/sn: cos/sin of the allowed angles.
 // Returns the decision; *tq_set tells whether _target_connector_xquat was assigned, tq its value (wxyz).
-FE_HD bool fe_is_aligned_d(const double* p1, const double* m1, const double* p2, const double* m2, int nang, const double* cs, const double* sn,
+FE_HDN bool fe_is_aligned_d(const double* p1, const double* m1, const double* p2, const double* m2, int nang, const double* cs, const double* sn,
                            const double* thr, double* tq, bool* tq_set) {
   const double up1[3] = {m1[2], m1[5], m1[8]}, up2[3] = {m2[2], m2[5], m2[8]}, f1[3] = {m1[1], m1[4], m1[7]}, f2[3] = {m2[1], m2[4], m2[7]};
   double d12[3] = {ndsub(p1[0], p2[0]), ndsub(p1[1], p2[1]), ndsub(p1[2], p2[2])}, d21[3] = {ndsub(p2[0], p1[0]), ndsub(p2[1], p1[1]), ndsub(p2[2], p1[2])};
@@ -166,7 +166,7 @@ FE_HD void dq_rotate(double* r, const double* q_in, const double* v) {
   r[0] = o[1]; r[1] = o[2]; r[2] = o[3];
 }
 // T.transform_to_target_quat(qpos_base, qpos, target_quat) on 7-vectors (pos, wxyz)
-FE_HD void d_transform_to_target(const double* base, const double* q, const double* target, double* new_pos, double* new_quat) {
+FE_HDN void d_transform_to_target(const double* base, const double* q, const double* target, double* new_pos, double* new_quat) {
   double inv[4], rel[4], d[3] = {q[0] - base[0], q[1] - base[1], q[2] - base[2]}, r[3];
   dq_inv(inv, base + 3);
   dq_mul(rel, target, inv);
@@ -202,7 +202,7 @@ struct FeEnv {
 FE_HD int fe_find(int* g, int i) { while (g[i] != i) i = g[i]; return i; } // path compression does not change results
 
 // site world pose (float64) from the link poses of the last forward pass held in the warp slice
-FE_HD void fe_site_pose_d(const FeWarp* w, int site, double* pos, double* mat, double* quat) {
+FE_HDN void fe_site_pose_d(const FeWarp* w, int site, double* pos, double* mat, double* quat) {
   const fe_model* m = w->m;
   const int l = m->site_link[site];
   float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
@@ -228,7 +228,7 @@ FE_HD void fe_stop_part(FeWarp* w, int p, float gc) {
   for (int k = 0; k < 6; ++k) w->qvel[da + k] = 0.f;
 }
 // _move_objects_translation_quat(obj, translation, target_quat, gravity): rigidly move obj's whole group (furniture.py:1163-1176)
-FE_HD void fe_move_group(FeEnv* e, int obj, const double* translation, const double* target_quat, float gc) {
+FE_HDN void fe_move_group(FeEnv* e, int obj, const double* translation, const double* target_quat, float gc) {
   FeWarp* w = &e->w;
   const fe_model* m = w->m;
   const int qb = m->link_qadr[m->nrlink + obj];
@@ -247,7 +247,7 @@ FE_HD void fe_move_group(FeEnv* e, int obj, const double* translation, const dou
   }
 }
 // min z over every site of every part in obj's group, starting from 0 (furniture.py:749-769)
-FE_HD double fe_group_min_z(FeEnv* e, int obj) {
+FE_HDN double fe_group_min_z(FeEnv* e, int obj) {
   FeWarp* w = &e->w;
   const int g = fe_find(e->group, obj);
   double mn = 0.0;
@@ -556,7 +556,7 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
     for (int d = lane; d < nr; d += 32) w->qfrc_applied[d] = w->bias[d]; // gravity compensation, :3372-3377
     if (lane == 0) { e->ei[0] = 0; e->ei[1] = -1; e->ei[6] = 0; w->u[2] = 0; }
   LANES_END
-  for (int i = 0; i < cfg->nsub; ++i) fe_substep(w); // _do_simulation, furniture.py:2877-2879
+  for (int i = 0; i < cfg->nsub; ++i) fe_substep_lockstep(w); // _do_simulation, furniture.py:2877-2879
   int fail = (w->u[2] & 8) ? 1 : 0;                   // MujocoException path, :2889-2897
   FE_SYNC;
   if (fail) {

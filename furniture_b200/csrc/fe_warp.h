@@ -13,21 +13,25 @@
 #if defined(__CUDACC__) && !defined(FE_EMULATE)
 #define FE_DEVICE_BUILD 1
 #define FE_HD __device__ __forceinline__
-#define FE_FN __device__
+#define FE_FN __device__ __noinline__
+#define FE_HDN __device__ __noinline__
 #define FE_BOTH __host__ __device__ __forceinline__
 #define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u); {
 #define LANES_END } } __syncwarp();
 #define FE_LDG(p) __ldg(p)
 #define FE_SYNC __syncwarp()
+#define FE_BLOCK_SYNC __syncthreads()
 #else
 #define FE_DEVICE_BUILD 0
 #define FE_HD static inline
 #define FE_FN static
+#define FE_HDN static
 #define FE_BOTH static inline
 #define LANES_BEGIN for (int lane = 0; lane < 32; ++lane) { {
 #define LANES_END } }
 #define FE_LDG(p) (*(p))
 #define FE_SYNC ((void)0)
+#define FE_BLOCK_SYNC ((void)0)
 #endif
 
 // sum of scr[0..31] with a fixed butterfly order (identical result on every lane and in the emulation build)
@@ -81,6 +85,35 @@ FE_HD int fe_popc(unsigned x) {
   return __builtin_popcount(x);
 #endif
 }
+
+
+// ---- lane-private values that live across regions (registers on the device, one slot per lane in the emulation),
+// and the collectives applied to them BETWEEN regions
+#if FE_DEVICE_BUILD
+#define FE_PRIV(T, name) T name
+#define FE_PRIVA(T, name, n) T name[n]
+#define PV(name) name
+#define FE_GSUM8(name) do { name += __shfl_xor_sync(0xffffffffu, name, 1); name += __shfl_xor_sync(0xffffffffu, name, 2); name += __shfl_xor_sync(0xffffffffu, name, 4); } while (0)
+#define FE_GSUM8_ARR(name, n) do { _Pragma("unroll") for (int k_ = 0; k_ < (n); ++k_) FE_GSUM8(name[k_]); } while (0)
+#define FE_GSUM8_ARRN(name, n, used) do { _Pragma("unroll") for (int k_ = 0; k_ < (used); ++k_) FE_GSUM8(name[k_]); } while (0)
+#define FE_ANY(name) (__any_sync(0xffffffffu, (name) != 0) != 0)
+#else
+#define FE_PRIV(T, name) T name[32]
+#define FE_PRIVA(T, name, n) T name[32][n]
+#define PV(name) name[lane]
+static inline void fe_emu_gsum8(float* a, int stride) {
+  for (int o = 1; o < 8; o <<= 1) {
+    float t[32];
+    for (int i = 0; i < 32; ++i) t[i] = a[i * stride] + a[(i ^ o) * stride];
+    for (int i = 0; i < 32; ++i) a[i * stride] = t[i];
+  }
+}
+#define FE_GSUM8(name) fe_emu_gsum8(name, 1)
+#define FE_GSUM8_ARR(name, n) do { for (int k_ = 0; k_ < (n); ++k_) fe_emu_gsum8(&name[0][k_], (n)); } while (0)
+#define FE_GSUM8_ARRN(name, n, used) do { for (int k_ = 0; k_ < (used); ++k_) fe_emu_gsum8(&name[0][k_], (n)); } while (0)
+static inline bool fe_emu_any(const int* a) { for (int i = 0; i < 32; ++i) if (a[i]) return true; return false; }
+#define FE_ANY(name) fe_emu_any(name)
+#endif
 
 // ---------------------------------------------------------------- small vector math (fp32)
 FE_HD void v3set(float* r, float a, float b, float c) { r[0] = a; r[1] = b; r[2] = c; }

@@ -53,7 +53,7 @@ def default_config(**kw):
     """Reference defaults: config/furniture.py:16-312 (control_freq 10 => 50 mj_steps per env step)."""
     c = FeConfig()
     c.struct_bytes = C.sizeof(FeConfig)
-    c.maxcon, c.newton_iters, c.ls_iters, c.tolerance = 48, 30, 20, 1e-6
+    c.maxcon, c.newton_iters, c.ls_iters, c.tolerance = 40, 30, 20, 1e-6
     c.nsub, c.max_episode_steps = 50, 2000
     c.discrete_grip, c.rescale_actions, c.auto_align = 1, 1, 1
     c.alignment_pos_dist, c.alignment_rot_dist_up, c.alignment_rot_dist_forward, c.alignment_project_dist = 0.1, 0.9, 0.9, 0.3
@@ -197,7 +197,7 @@ class Engine:
         self._chk(self.L.fe_field_dim(self.h, name.encode(), C.byref(d), C.byref(e)))
         return d.value, e.value
 
-    _INT = {"geom_contype", "geom_conaffinity", "eq_active", "touch", "flags", "ncon", "niter", "con_geom", "con_state", "group", "site_connected",
+    _INT = {"geom_contype", "geom_conaffinity", "eq_active", "touch", "flags", "ncon", "niter", "stats", "con_geom", "con_state", "group", "site_connected",
             "num_connected", "prev_num_connected", "touched", "picked", "episode_length", "done"}
 
     def get(self, name):

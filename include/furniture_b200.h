@@ -62,6 +62,7 @@ int fe_num_envs(const fe_handle* h);
 int fe_obs_dim(const fe_handle* h);    /* robot_ob (29 for Sawyer impedance) + object_ob (7 per part) */
 int fe_action_dim(const fe_handle* h); /* dof: 7 joint velocities + gripper + connect for Sawyer impedance */
 int fe_info_dim(const fe_handle* h);   /* int32 per env: num_connected, success, unstable, episode_length, ncon, solver iters */
+int fe_smem_bytes_per_env(const fe_handle* h); /* shared-memory working set of one env (one warp) */
 
 /* ---- simulator surface (MjSim) */
 int fe_sim_forward(fe_handle* h, void* stream);

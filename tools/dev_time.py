@@ -24,3 +24,7 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print("N=%d  %.3f ms/env-step-batch  => %.0f env-steps/s  (%.2f us per mj_step batch)" % (N, ms, N / ms * 1e3, ms * 1e3 / 50))
 print("mean ncon %.1f mean niter %.2f done %d unstable %d" % (info[:, 4].float().mean().item(), info[:, 5].float().mean().item(), int(done.sum()), int(info[:, 2].sum())))
+st = eng.get("stats")
+print("per env-step (50 substeps): coupled substeps mean %.2f  robot-block solves mean %.2f  coop iterations mean %.2f; envs with any coupled %.1f%%" % (st[:,1].mean(), st[:,2].mean(), st[:,3].mean(), 100*(st[:,1]>0).mean()))
+import numpy as np
+print("coupled histogram", np.bincount(np.minimum(st[:,1], 50)//10, minlength=6), " robot-solve histogram", np.bincount(np.minimum(st[:,2],50)//10, minlength=6))
