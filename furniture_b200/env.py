@@ -120,20 +120,26 @@ class ShardedFurnitureEnv:
     """One process per GPU (torch.distributed, backend nccl). Each rank steps its own contiguous env shard; after the
     step one all_gather makes the packed [obs | reward | done] of every shard visible on every rank."""
 
-    def __init__(self, envs_per_gpu, agent="Sawyer", furniture_name="table_lack_0825", **cfg_overrides):
+    def __init__(self, envs_per_gpu, agent="Sawyer", furniture_name="table_lack_0825", env=None, **cfg_overrides):
         import torch
         import torch.distributed as dist
 
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         local = int(__import__("os").environ.get("LOCAL_RANK", self.rank))
-        cfg_overrides.setdefault("seed", 123 + self.rank * envs_per_gpu)  # env/base.py:77: seed + rank
-        self.env = BatchedFurnitureEnv(agent, furniture_name, envs_per_gpu, device=local, **cfg_overrides)
+        cfg_overrides.setdefault("seed", self.shard_seed(123, self.rank, envs_per_gpu))
+        # `env` lets the host logic be exercised with a stand-in shard (tests/test_sharded_gloo.py)
+        self.env = env if env is not None else BatchedFurnitureEnv(agent, furniture_name, envs_per_gpu, device=local, **cfg_overrides)
         self.envs_per_gpu = envs_per_gpu
         self.num_envs = envs_per_gpu * self.world
         self.pack_dim = self.env.obs_dim + 2
         self._pack = torch.empty((envs_per_gpu, self.pack_dim), dtype=torch.float32, device=self.env.device)
         self._all = torch.empty((self.num_envs, self.pack_dim), dtype=torch.float32, device=self.env.device)
+
+    @staticmethod
+    def shard_seed(seed, rank, envs_per_gpu):
+        """env e of rank r is seeded seed + r * envs_per_gpu + e: the reference's seed + rank per env (env/base.py:77)"""
+        return seed + rank * envs_per_gpu
 
     def _gather(self, obs, rew=None, done=None):
         p = self._pack
