@@ -31,16 +31,18 @@ extern __shared__ float fe_smem[];
 
 #define FE_MAX_WPB 14
 __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_sim_kernel(FeState s, const fe_model* __restrict__ m, FeOpt opt, int nsub, int mode, FeDebug dbg, int slice_words) {
-  const int wib = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (env >= s.N) return;
+  const int wib = threadIdx.x >> 5, slot = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (slot >= s.N) return;
+  const int env = s.order[slot];
   fe_run_env(s, m, opt, env, nsub, mode, fe_smem + (size_t)wib * slice_words, dbg);
 }
 
 __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_step_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
                                                          fe_config cfg, FeOpt opt, const float* __restrict__ actions, float* reward, uint8_t* done,
                                                          int32_t* info, int slice_words) {
-  const int wib = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (env >= st.N) return;
+  const int wib = threadIdx.x >> 5, slot = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (slot >= st.N) return;
+  const int env = st.order[slot];
   FeEnv e;
   fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
   fe_load(&e.w, st, env);
@@ -64,6 +66,34 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState s
   fe_store(&e.w, st, env);
 }
 
+// stable partition of the env ids: envs whose last step used the coupled (FULL) solver scope first.  One block.
+__global__ void __launch_bounds__(1024) fe_order_kernel(int N, const int* __restrict__ stats, int* __restrict__ order) {
+  __shared__ int wsum[32], wsum2[32], tot_slow, base_slow, base_fast;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int cnt = 0;
+  for (int e = tid; e < N; e += 1024) cnt += stats[(size_t)e * 12 + 1] > 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) wsum[wid] = cnt;
+  __syncthreads();
+  if (tid == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; tot_slow = t; base_slow = 0; base_fast = 0; }
+  __syncthreads();
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    const int e = c0 + tid;
+    const int valid = e < N, slow = valid && stats[(size_t)e * 12 + 1] > 0, fast = valid && !slow;
+    const unsigned ms = __ballot_sync(0xffffffffu, slow), mf = __ballot_sync(0xffffffffu, fast);
+    if (lane == 0) { wsum[wid] = __popc(ms); wsum2[wid] = __popc(mf); }
+    __syncthreads();
+    int ps = 0, pf = 0;
+    for (int i = 0; i < wid; ++i) { ps += wsum[i]; pf += wsum2[i]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if (slow) order[base_slow + ps + __popc(ms & lt)] = e;
+    if (fast) order[tot_slow + base_fast + pf + __popc(mf & lt)] = e;
+    __syncthreads();
+    if (tid == 0) { int a = 0, b = 0; for (int i = 0; i < 32; ++i) { a += wsum[i]; b += wsum2[i]; } base_slow += a; base_fast += b; }
+    __syncthreads();
+  }
+}
+
 __global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* cs, const double* sn,
                                      const int32_t* nang, const double* thr, uint8_t* aligned, double* tq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -80,6 +110,7 @@ __global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, 
 struct CudaPlat {
   size_t smem_sim = 0, smem_env = 0;
   int wpb = 1;
+  int reorder = 1;
   float* pin_act = nullptr;
   unsigned char* pin_out = nullptr;
   size_t out_bytes = 0;
@@ -103,6 +134,7 @@ static int plat_prepare(fe_handle* h) {
   if (const char* e = getenv("FE_WPB")) { int v = atoi(e); if (v >= 1 && v <= wpb) wpb = v; }
   if (wpb < 1) return fail(h, -11, "model does not fit in shared memory");
   p->wpb = wpb;
+  if (const char* e = getenv("FE_REORDER")) p->reorder = atoi(e);
   p->smem_sim = (size_t)h->slice_words * 4 * wpb;
   p->smem_env = per_env * wpb;
   CUDA_OK(cudaFuncSetAttribute(fe_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sim));
@@ -151,6 +183,7 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
   CudaPlat* p = (CudaPlat*)h->plat;
   fe_env_step_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words);
   CUDA_OK(cudaGetLastError());
+  if (p->reorder) fe_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->N, h->st.stats, h->st.order);
   return 0;
 }
 static int plat_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
@@ -165,6 +198,7 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
   fe_env_step_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
                                                             (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words);
   CUDA_OK(cudaGetLastError());
+  if (p->reorder) fe_order_kernel<<<1, 1024, 0, p->stream>>>(h->N, h->st.stats, h->st.order);
   unsigned char* o = p->pin_out;
   CUDA_OK(cudaMemcpyAsync(o, h->es.obs, ob, cudaMemcpyDeviceToHost, p->stream));
   CUDA_OK(cudaMemcpyAsync(o + ob, h->dev_rew, rb, cudaMemcpyDeviceToHost, p->stream));

@@ -15,6 +15,10 @@
 #include "fe_collide.h"
 #include "fe_model.h"
 #include "fe_warp.h"
+#if !FE_DEVICE_BUILD
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 #define FE_MINVAL 1e-15f
 #define FE_MINIMP 0.0001f
@@ -49,7 +53,7 @@ struct FeWarp {
   float *l_sign, *l_aref, *l_D, *l_jar, *l_jv, *l_f;
   // solver
   float *x, *Ma, *grad, *search, *Mv, *fc, *H, *Jc, *scr;
-  int *first, *iscr, *colmap;
+  int *first, *iscr, *colmap, *skip;
   // uniform scalars (kept in smem so that both builds see one copy)
   int* u; // [0]=ncon [1]=ncand [2]=flags [3]=niter [4]=coupled
   // solver scope of the cooperative routines: all dofs (FULL) or the robot block only (FAST, parts solved per lane)
@@ -77,7 +81,7 @@ FE_BOTH int fe_warp_bind(FeWarp* w, float* base, const fe_model* m, const FeOpt&
   CARVE_F(l_sign, nr) CARVE_F(l_aref, nr) CARVE_F(l_D, nr) CARVE_F(l_jar, nr) CARVE_F(l_jv, nr) CARVE_F(l_f, nr)
   CARVE_F(x, nv) CARVE_F(Ma, nv) CARVE_F(grad, nv) CARVE_F(search, nv) CARVE_F(Mv, nv) CARVE_F(fc, nv)
   w->Jc = w->lcrb; /* composite inertias (smooth stage) vs row staging of fe_build_H */
-  CARVE_F(scr, 2 * 32) CARVE_I(first, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 8)
+  CARVE_F(scr, 2 * 32) CARVE_I(first, nv) CARVE_I(skip, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 16)
   // H (solver) and the collision scratch (geom poses, candidate list) are never live together: overlay them
   int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
   int big = hwords > cwords ? hwords : cwords;
@@ -140,9 +144,10 @@ FE_HDN void fe_chol6_solve(const float* L, float* x) {
 
 // ---------------------------------------------------------------- cooperative skyline Cholesky (packed lower H)
 // first[i] = first column of row i's envelope. Returns false (uniform) if a pivot is not positive.
-FE_FN bool fe_chol(FeWarp* w, float* H, const int* first, int n) {
+FE_FN bool fe_chol(FeWarp* w, float* H, const int* first, int n, const int* skip = nullptr) {
   bool ok = true;
   for (int k = 0; k < n; ++k) {
+    if (skip && skip[k]) continue; // column of an independent 6x6 block, factored in registers by fe_chol_blocks
     const int fk = first[k];
     LANES_BEGIN
       for (int i = k + lane; i < n; i += 32) {
@@ -170,8 +175,9 @@ FE_FN bool fe_chol(FeWarp* w, float* H, const int* first, int n) {
   return ok;
 }
 // x <- (L L^T)^-1 x ; tmp is an n-vector scratch
-FE_FN void fe_chol_solve(FeWarp* w, const float* L, const int* first, int n, float* x, float* tmp) {
+FE_FN void fe_chol_solve(FeWarp* w, const float* L, const int* first, int n, float* x, float* tmp, const int* skip = nullptr) {
   for (int k = 0; k < n; ++k) { // forward: tmp = L^-1 x
+    if (skip && skip[k]) continue;
     const float xk = x[k] / L[fe_tri(k) + k];
     LANES_BEGIN
       if (lane == 0) tmp[k] = xk;
@@ -180,6 +186,7 @@ FE_FN void fe_chol_solve(FeWarp* w, const float* L, const int* first, int n, flo
     LANES_END
   }
   for (int k = n - 1; k >= 0; --k) { // backward: x = L^-T tmp
+    if (skip && skip[k]) continue;
     const float xk = tmp[k] / L[fe_tri(k) + k];
     const int fk = first[k];
     LANES_BEGIN
@@ -187,6 +194,52 @@ FE_FN void fe_chol_solve(FeWarp* w, const float* L, const int* first, int n, flo
       for (int j = fk + lane; j < k; j += 32) tmp[j] -= L[fe_tri(k) + j] * xk;
     LANES_END
   }
+}
+
+// Free-part blocks whose rows start at their own block and that no later row reaches are independent 6x6 systems:
+// flag their columns (skip) so that the synchronised column loops above leave them to one lane each.
+FE_FN void fe_mark_indep_blocks(FeWarp* w, const int* first, int* skip) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, np = m->npart;
+  LANES_BEGIN
+    for (int d = lane; d < nr; d += 32) skip[d] = 0;
+    for (int p = lane; p < np; p += 32) {
+      const int sp = nr + 6 * p;
+      int indep = first[sp] == sp;
+      for (int q = p + 1; q < np && indep; ++q) if (first[nr + 6 * q] <= sp) indep = 0;
+      for (int k = 0; k < 6; ++k) skip[sp + k] = indep;
+    }
+  LANES_END
+}
+FE_FN void fe_chol_blocks(FeWarp* w, float* H, const int* skip) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, np = m->npart;
+  LANES_BEGIN
+    for (int p = lane; p < np; p += 32) {
+      const int sp = nr + 6 * p;
+      if (skip[sp]) {
+        float A[21];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = H[fe_tri(sp + i) + sp + j];
+        if (!fe_chol6(A)) w->u[2] |= 4;
+        for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) H[fe_tri(sp + i) + sp + j] = A[i * (i + 1) / 2 + j];
+      }
+    }
+  LANES_END
+}
+FE_FN void fe_solve_blocks(FeWarp* w, const float* L, const int* skip, float* x) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, np = m->npart;
+  LANES_BEGIN
+    for (int p = lane; p < np; p += 32) {
+      const int sp = nr + 6 * p;
+      if (skip[sp]) {
+        float A[21], b[6];
+        for (int i = 0; i < 6; ++i) { b[i] = x[sp + i]; for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = L[fe_tri(sp + i) + sp + j]; }
+        fe_chol6_solve(A, b);
+        for (int i = 0; i < 6; ++i) x[sp + i] = b[i];
+      }
+    }
+  LANES_END
 }
 
 // ---------------------------------------------------------------- kinematics + smooth dynamics
@@ -840,6 +893,42 @@ FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, f
   *d2 = fe_sum32(w->scr + 32) + 2.f * g2;
 }
 
+// zone logic of one elliptic contact: forces f, cost, and (if W) the 3x3 weight (xx yy zz xy xz yz); returns state
+FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
+  const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { f[0] = f[1] = f[2] = 0.f; return 0; }
+  if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+    f[0] = -D0 * j0; f[1] = -D1 * j1; f[2] = -D1 * j2;
+    *cost += 0.5f * (D0 * j0 * j0 + D1 * (j1 * j1 + j2 * j2));
+    if (W) { W[0] = D0; W[1] = D1; W[2] = D1; W[3] = W[4] = W[5] = 0.f; }
+    return 1;
+  }
+  const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+  *cost += 0.5f * Dm * NmT * NmT;
+  f[0] = -Dm * NmT * mu;
+  f[1] = -f[0] / T * U1 * fr;
+  f[2] = -f[0] / T * U2 * fr;
+  if (W) {
+    const float iT = 1.f / T, a = Dm * mu * mu * iT * iT, b = Dm * NmT * mu * iT;
+    const float h11 = a * U1 * U1 - b * (1.f - U1 * U1 * iT * iT), h22 = a * U2 * U2 - b * (1.f - U2 * U2 * iT * iT), h12 = a * U1 * U2 + b * U1 * U2 * iT * iT;
+    const float h01 = -Dm * mu * U1 * iT, h02 = -Dm * mu * U2 * iT;
+    W[0] = mu * mu * Dm; W[1] = fr * fr * h11; W[2] = fr * fr * h22; W[3] = mu * fr * h01; W[4] = mu * fr * h02; W[5] = fr * fr * h12;
+  }
+  return 2;
+}
+// rows of one part-vs-world contact in the part's coordinates: J[k] = sgn * [(r x F_k), F_k], r = pos - origin
+FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
+  const float* F = w->c_frame + 9 * c;
+  float r[3];
+  v3sub(r, w->c_pos + 3 * c, w->lpos + 3 * l);
+  for (int k = 0; k < 3; ++k) {
+    float t[3];
+    v3cross(t, r, F + 3 * k);
+    J[6 * k + 0] = sgn * t[0]; J[6 * k + 1] = sgn * t[1]; J[6 * k + 2] = sgn * t[2];
+    J[6 * k + 3] = sgn * F[3 * k]; J[6 * k + 4] = sgn * F[3 * k + 1]; J[6 * k + 5] = sgn * F[3 * k + 2];
+  }
+}
+
 // H = M_z + J^T W J  (packed lower, skyline first[])
 FE_FN void fe_build_H(FeWarp* w) {
   const fe_model* m = w->m;
@@ -886,10 +975,47 @@ FE_FN void fe_build_H(FeWarp* w) {
       }
     }
   LANES_END
-  // contacts, one at a time: dof-space rows staged in Jc (3 x ncols), then the ncols x ncols outer product
+  // FULL scope: contacts of a free part against the static world only touch that part's 6x6 diagonal block; they are
+  // accumulated 8 lanes per part (lane = contact) with group reductions, like the FAST solver does
+  bool grouped = !fast;
+  for (int p = 0; p < m->npart; ++p) if (w->plist[9 * p + 8] > 8) grouped = false;
+  if (grouped) {
+    for (int pass = 0; pass * 4 < m->npart; ++pass) {
+      FE_PRIVA(float, hacc_, 21);
+      LANES_BEGIN
+        for (int k = 0; k < 21; ++k) PV(hacc_)[k] = 0.f;
+        const int part = pass * 4 + (lane >> 3), slot = lane & 7;
+        if (part < m->npart && slot < w->plist[9 * part + 8]) {
+          const int c = w->plist[9 * part + slot];
+          if (w->c_state[c] != 0) {
+            const int l = nrl + part, B_ = (w->c_link[c] >> 8) - 1;
+            float J[18], f[3], W[6], dummy = 0.f, WJ[18];
+            fe_part_rows(w, c, l, B_ == l ? 1.f : -1.f, J);
+            fe_cone(w->c_jar[3 * c], w->c_jar[3 * c + 1], w->c_jar[3 * c + 2], w->c_mu[c], w->c_fric[c], w->c_D[2 * c], w->c_D[2 * c + 1], f, &dummy, W);
+            for (int i = 0; i < 6; ++i) {
+              WJ[i] = W[0] * J[i] + W[3] * J[6 + i] + W[4] * J[12 + i];
+              WJ[6 + i] = W[3] * J[i] + W[1] * J[6 + i] + W[5] * J[12 + i];
+              WJ[12 + i] = W[4] * J[i] + W[5] * J[6 + i] + W[2] * J[12 + i];
+            }
+            for (int i = 0; i < 6; ++i)
+              for (int j = 0; j <= i; ++j) PV(hacc_)[i * (i + 1) / 2 + j] = J[i] * WJ[j] + J[6 + i] * WJ[6 + j] + J[12 + i] * WJ[12 + j];
+          }
+        }
+      LANES_END
+      FE_GSUM8_ARR(hacc_, 21);
+      LANES_BEGIN
+        const int part = pass * 4 + (lane >> 3);
+        if (part < m->npart && (lane & 7) == 0 && w->plist[9 * part + 8] > 0) {
+          const int z = nr + 6 * part;
+          for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) w->H[fe_tri(z + i) + z + j] += PV(hacc_)[i * (i + 1) / 2 + j];
+        }
+      LANES_END
+    }
+  }
+  // remaining contacts, one at a time: dof-space rows staged in Jc (3 x ncols), then the ncols x ncols outer product
   for (int c = 0; c < ncon; ++c) {
     const int st = w->c_state[c];
-    if (st == 0 || (fast && w->c_kind[c] == 0)) continue;
+    if (st == 0 || ((fast || grouped) && w->c_kind[c] == 0)) continue;
     const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
     const bool robot = (A >= 0 && A < nrl) || (B >= 0 && B < nrl);
     const int partA = A >= nrl ? A - nrl : -1, partB = B >= nrl ? B - nrl : -1;
@@ -1081,6 +1207,9 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     LANES_END
     const float gauss = fe_sum32(w->scr), gnorm = sqrtf(fe_sum32(w->scr + 32));
     cost = gauss + ccost;
+#if !FE_DEVICE_BUILD
+    if (getenv("FE_DEBUG_SOLVE")) printf("  coop it %d nact %d cost %.9g gnorm %.4g scaled-g %.3g impr %.3g\n", iter, nv, cost, gnorm, scale * gnorm, scale * impr);
+#endif
     if (!(cost == cost)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END break; }
     // MuJoCo stops on scale*(oldcost - cost) < tol; in fp32 that difference of two large costs is round-off, so the
     // improvement is taken from the line search instead: -alpha p'(0) / 2 (exact for a quadratic, the Newton decrement)
@@ -1088,9 +1217,16 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     else if (scale * gnorm < w->opt.tolerance) break;
     if (iter >= w->opt.newton_iters) break;
     fe_build_H(w);
-    if (!fe_chol(w, w->H, w->first, nv)) { LANES_BEGIN if (lane == 0) w->u[2] |= 4; LANES_END }
+    const int* skip = nullptr;
+    if (!fast) { // FULL scope: independent part blocks are factored / solved by one lane each
+      fe_mark_indep_blocks(w, w->first, w->skip);
+      fe_chol_blocks(w, w->H, w->skip);
+      skip = w->skip;
+    }
+    if (!fe_chol(w, w->H, w->first, nv, skip)) { LANES_BEGIN if (lane == 0) w->u[2] |= 4; LANES_END }
     LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search[i] = -w->grad[i]; LANES_END
-    fe_chol_solve(w, w->H, w->first, nv, w->search, w->Mv);
+    if (skip) fe_solve_blocks(w, w->H, skip, w->search);
+    fe_chol_solve(w, w->H, w->first, nv, w->search, w->Mv, skip);
     fe_mul_M(w, w->search, w->Mv);
     fe_mul_J(w, w->search, w->c_jv, w->w_jv, w->l_jv, false);
     LANES_BEGIN
@@ -1137,42 +1273,6 @@ FE_FN void fe_solve_coop(FeWarp* w) {
 // ---- single-lane Newton solve of one free part whose contacts are all against the static world (FAST scope).
 // Same cost, cones and exact line search as the cooperative solver, on the part's own 6 unknowns [alpha; vdot]; the
 // blocks are independent in that case, so block-wise Newton converges to the same minimiser as MuJoCo's global iteration.
-// zone logic of one elliptic contact: forces f, cost, and (if W) the 3x3 weight (xx yy zz xy xz yz); returns state
-FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
-  const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
-  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { f[0] = f[1] = f[2] = 0.f; return 0; }
-  if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
-    f[0] = -D0 * j0; f[1] = -D1 * j1; f[2] = -D1 * j2;
-    *cost += 0.5f * (D0 * j0 * j0 + D1 * (j1 * j1 + j2 * j2));
-    if (W) { W[0] = D0; W[1] = D1; W[2] = D1; W[3] = W[4] = W[5] = 0.f; }
-    return 1;
-  }
-  const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
-  *cost += 0.5f * Dm * NmT * NmT;
-  f[0] = -Dm * NmT * mu;
-  f[1] = -f[0] / T * U1 * fr;
-  f[2] = -f[0] / T * U2 * fr;
-  if (W) {
-    const float iT = 1.f / T, a = Dm * mu * mu * iT * iT, b = Dm * NmT * mu * iT;
-    const float h11 = a * U1 * U1 - b * (1.f - U1 * U1 * iT * iT), h22 = a * U2 * U2 - b * (1.f - U2 * U2 * iT * iT), h12 = a * U1 * U2 + b * U1 * U2 * iT * iT;
-    const float h01 = -Dm * mu * U1 * iT, h02 = -Dm * mu * U2 * iT;
-    W[0] = mu * mu * Dm; W[1] = fr * fr * h11; W[2] = fr * fr * h22; W[3] = mu * fr * h01; W[4] = mu * fr * h02; W[5] = fr * fr * h12;
-  }
-  return 2;
-}
-// rows of one part-vs-world contact in the part's coordinates: J[k] = sgn * [(r x F_k), F_k], r = pos - origin
-FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
-  const float* F = w->c_frame + 9 * c;
-  float r[3];
-  v3sub(r, w->c_pos + 3 * c, w->lpos + 3 * l);
-  for (int k = 0; k < 3; ++k) {
-    float t[3];
-    v3cross(t, r, F + 3 * k);
-    J[6 * k + 0] = sgn * t[0]; J[6 * k + 1] = sgn * t[1]; J[6 * k + 2] = sgn * t[2];
-    J[6 * k + 3] = sgn * F[3 * k]; J[6 * k + 4] = sgn * F[3 * k + 1]; J[6 * k + 5] = sgn * F[3 * k + 2];
-  }
-}
-
 // FAST scope, free parts: 8 lanes per part (4 parts per pass), one lane per contact.  Per Newton iteration each lane
 // evaluates its contact (cone zone, force, 3x3 weight, J^T f and J^T W J), the group sums them with 3 xor-shuffles per
 // value, every lane of the group then factors the same 6x6 Hessian and runs the same exact line search, whose
@@ -1489,9 +1589,16 @@ FE_FN void fe_substep(FeWarp* w) {
 // where every live warp of the block executes the same number of steps (the nsub loop of an env step).
 FE_FN void fe_substep_lockstep(FeWarp* w) {
   const int ls = w->opt.lockstep;
-  if (ls & 1) { FE_BLOCK_SYNC; } fe_kin_smooth(w);
-  if (ls & 2) { FE_BLOCK_SYNC; } fe_collide(w);
-  if (ls & 4) { FE_BLOCK_SYNC; } fe_assemble(w);
-  if (ls & 8) { FE_BLOCK_SYNC; } fe_solve(w);
-  if (ls & 16) { FE_BLOCK_SYNC; } fe_integrate(w);
+#if FE_DEVICE_BUILD
+#define FE_TICK(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) w->u[slot] += (int)((t1_ - t0_) >> 4); t0_ = t1_; }
+  long long t0_ = clock64();
+#else
+#define FE_TICK(slot)
+#endif
+  if (ls & 1) { FE_BLOCK_SYNC; } FE_TICK(13) fe_kin_smooth(w); FE_TICK(8)
+  if (ls & 2) { FE_BLOCK_SYNC; } FE_TICK(13) fe_collide(w); FE_TICK(9)
+  if (ls & 4) { FE_BLOCK_SYNC; } FE_TICK(13) fe_assemble(w); FE_TICK(10)
+  if (ls & 8) { FE_BLOCK_SYNC; } FE_TICK(13) fe_solve(w); FE_TICK(11)
+  if (ls & 16) { FE_BLOCK_SYNC; } FE_TICK(13) fe_integrate(w); FE_TICK(12)
+#undef FE_TICK
 }

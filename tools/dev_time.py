@@ -6,11 +6,12 @@ from furniture_b200 import mjcf
 from furniture_b200.engine import Engine, default_config
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 m = mjcf.load_scene("Sawyer", "table_lack_0825")
 eng = Engine(m, N, 0, default_config())
 t = time.time(); eng.env_reset(); torch.cuda.synchronize(); print("reset wall %.3f s" % (time.time() - t), "flags nonzero", int((eng.get("flags") != 0).sum()))
 g = torch.Generator(device="cuda").manual_seed(0)
-act = torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1
+act = (torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1) * scale
 obs = torch.empty((N, eng.obs_dim), device="cuda"); rew = torch.empty(N, device="cuda"); done = torch.empty(N, dtype=torch.uint8, device="cuda"); info = torch.empty((N, 6), dtype=torch.int32, device="cuda")
 for w in range(2):
     eng.env_step_dev(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
@@ -18,7 +19,7 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for k in range(steps):
-    act = torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1
+    act = (torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1) * scale
     eng.env_step_dev(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
@@ -28,3 +29,12 @@ st = eng.get("stats")
 print("per env-step (50 substeps): coupled substeps mean %.2f  robot-block solves mean %.2f  coop iterations mean %.2f; envs with any coupled %.1f%%" % (st[:,1].mean(), st[:,2].mean(), st[:,3].mean(), 100*(st[:,1]>0).mean()))
 import numpy as np
 print("coupled histogram", np.bincount(np.minimum(st[:,1], 50)//10, minlength=6), " robot-solve histogram", np.bincount(np.minimum(st[:,2],50)//10, minlength=6))
+names = ["kin_smooth", "collide", "assemble", "solve", "integrate", "barrier_wait"]
+cyc = st[:, 4:10].astype(np.float64) * 16
+tot = cyc.sum(1)
+print("cycles per env-step per warp: total mean %.0f max %.0f" % (tot.mean(), tot.max()))
+for i, nme in enumerate(names): print("  %-13s mean %9.0f (%.1f%%)  p99 %9.0f  max %9.0f" % (nme, cyc[:, i].mean(), 100 * cyc[:, i].mean() / tot.mean(), np.percentile(cyc[:, i], 99), cyc[:, i].max()))
+it = st[:, 3]
+print("coop iterations per env-step: max %d  p99 %d  p90 %d ; envs > 200: %d" % (it.max(), np.percentile(it, 99), np.percentile(it, 90), (it > 200).sum()))
+worst = np.argsort(-cyc[:, 3])[:5]
+for e in worst: print("  env %d: solve cycles %.0f coupled %d robot-solves %d coop-iters %d ncon %d" % (e, cyc[e, 3], st[e, 1], st[e, 2], st[e, 3], info[e, 4].item()))
