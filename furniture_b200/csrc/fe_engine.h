@@ -248,73 +248,161 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
   const int nl = m->nlink, nr = m->nr, nrl = m->nrlink, nv = m->nv;
   const float Pr[3] = {m->robot_ref[0], m->robot_ref[1], m->robot_ref[2]};
   const float g[3] = {m->gravity[0], m->gravity[1], m->gravity[2]};
-  for (int level = 0; level <= m->maxdepth; ++level) {
-    LANES_BEGIN
-      const int l = lane;
-      if (l < nl && m->link_depth[l] == level) {
-        float pos[3], quat[4], R[9], V[6], A[6];
-        const int qa = m->link_qadr[l], da = m->link_dadr[l];
-        if (m->link_jtype[l] == FE_JNT_FREE) {
-          v3cpy(pos, w->qpos + qa);
-          quat[0] = w->qpos[qa + 3]; quat[1] = w->qpos[qa + 4]; quat[2] = w->qpos[qa + 5]; quat[3] = w->qpos[qa + 6];
-          qnormalize(quat);
-          q2mat(R, quat);
-          m3mulv(V, R, w->qvel + da + 3);            // world angular velocity
-          v3cpy(V + 3, w->qvel + da);                // velocity of the link origin (= reference point)
-          float t[3];
-          v3cross(t, V, V + 3);
-          A[0] = A[1] = A[2] = 0.f;
-          A[3] = -t[0] - g[0]; A[4] = -t[1] - g[1]; A[5] = -t[2] - g[2];
-        } else {
-          const int p = m->link_parent[l];
-          float ppos[3] = {0.f, 0.f, 0.f}, pquat[4] = {1.f, 0.f, 0.f, 0.f}, pR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-          float Vp[6] = {0, 0, 0, 0, 0, 0}, Ap[6] = {0, 0, 0, -g[0], -g[1], -g[2]};
-          if (p >= 0) {
-            v3cpy(ppos, w->lpos + 3 * p);
-            for (int k = 0; k < 4; ++k) pquat[k] = w->lquat[4 * p + k];
-            for (int k = 0; k < 9; ++k) pR[k] = w->lmat[9 * p + k];
-            for (int k = 0; k < 6; ++k) { Vp[k] = w->lvel[6 * p + k]; Ap[k] = w->lacc[6 * p + k]; }
-          }
-          float t[3], anchor[3], axis[3];
-          m3mulv(t, pR, m->link_pos[l]);
-          v3add(pos, ppos, t);
-          qmul(quat, pquat, m->link_quat[l]);
-          q2mat(R, quat);
-          m3mulv(t, R, m->link_jpos[l]);
-          v3add(anchor, pos, t);
-          m3mulv(axis, R, m->link_jaxis[l]);
-          const float q = w->qpos[qa], qd = w->qvel[da];
-          float Sd[6];
-          if (m->link_jtype[l] == FE_JNT_HINGE) {
-            float s = sinf(0.5f * q), c = cosf(0.5f * q);
-            float ql[4] = {c, m->link_jaxis[l][0] * s, m->link_jaxis[l][1] * s, m->link_jaxis[l][2] * s}, qn[4];
-            qmul(qn, quat, ql);
-            for (int k = 0; k < 4; ++k) quat[k] = qn[k];
-            qnormalize(quat);
-            q2mat(R, quat);
-            m3mulv(t, R, m->link_jpos[l]);
-            v3sub(pos, anchor, t);
-            v3cpy(Sd, axis);
-            v3sub(t, anchor, Pr);
-            v3cross(Sd + 3, t, axis);
-          } else {
-            v3madd(pos, pos, axis, q);
-            qnormalize(quat);
-            q2mat(R, quat);
-            Sd[0] = Sd[1] = Sd[2] = 0.f;
-            v3cpy(Sd + 3, axis);
-          }
-          float Sdot[6];
-          crossm(Sdot, Vp, Sd);
-          for (int k = 0; k < 6; ++k) { V[k] = Vp[k] + Sd[k] * qd; A[k] = Ap[k] + Sdot[k] * qd; w->S[6 * da + k] = Sd[k]; }
-        }
+  FE_PRIVA(float, Atmp_, 6);
+  // Forward pass without a per-level loop: every robot link first builds its own joint transform, then world poses,
+  // velocities and bias accelerations are obtained by pointer jumping up the tree (log2(depth) short regions).
+  int nsteps = 0;
+  while ((1 << nsteps) <= m->maxdepth) ++nsteps;
+  float* const bufp[2] = {w->lpos, w->lacc};   // position (3 of 6 words per link in the scratch buffer)
+  float* const bufq[2] = {w->lquat, w->lfrc};  // quaternion (4 of 6 words)
+  int* const bufa[2] = {w->iscr, w->colmap};   // ancestor pointer
+  const int strp[2] = {3, 6}, strq[2] = {4, 6};
+  LANES_BEGIN
+    const int l = lane;
+    if (l < nl) {
+      const int qa = m->link_qadr[l], da = m->link_dadr[l];
+      if (m->link_jtype[l] == FE_JNT_FREE) { // pose straight from qpos; V, A in closed form about the link origin
+        float pos[3], quat[4], R[9], V[6], A[6], t[3];
+        v3cpy(pos, w->qpos + qa);
+        quat[0] = w->qpos[qa + 3]; quat[1] = w->qpos[qa + 4]; quat[2] = w->qpos[qa + 5]; quat[3] = w->qpos[qa + 6];
+        qnormalize(quat);
+        q2mat(R, quat);
+        m3mulv(V, R, w->qvel + da + 3);
+        v3cpy(V + 3, w->qvel + da);
+        v3cross(t, V, V + 3);
+        A[0] = A[1] = A[2] = 0.f;
+        A[3] = -t[0] - g[0]; A[4] = -t[1] - g[1]; A[5] = -t[2] - g[2];
         v3cpy(w->lpos + 3 * l, pos);
         for (int k = 0; k < 4; ++k) w->lquat[4 * l + k] = quat[k];
         for (int k = 0; k < 9; ++k) w->lmat[9 * l + k] = R[k];
-        for (int k = 0; k < 6; ++k) { w->lvel[6 * l + k] = V[k]; w->lacc[6 * l + k] = A[k]; }
+        for (int k = 0; k < 6; ++k) { w->lvel[6 * l + k] = V[k]; w->lacc2[6 * l + k] = A[k]; }
+      } else { // joint transform in the parent link frame
+        float p0[3], q0[4], R0[9], t[3], pos[3], quat[4];
+        v3cpy(p0, m->link_pos[l]);
+        for (int k = 0; k < 4; ++k) q0[k] = m->link_quat[l][k];
+        const float q = w->qpos[qa];
+        if (m->link_jtype[l] == FE_JNT_HINGE) {
+          const float sn = sinf(0.5f * q), cs = cosf(0.5f * q);
+          const float ql[4] = {cs, m->link_jaxis[l][0] * sn, m->link_jaxis[l][1] * sn, m->link_jaxis[l][2] * sn};
+          float R1[9], t1[3];
+          qmul(quat, q0, ql);
+          qnormalize(quat);
+          q2mat(R0, q0);
+          q2mat(R1, quat);
+          m3mulv(t, R0, m->link_jpos[l]);
+          m3mulv(t1, R1, m->link_jpos[l]);
+          for (int k = 0; k < 3; ++k) pos[k] = p0[k] + t[k] - t1[k];
+        } else {
+          q2mat(R0, q0);
+          m3mulv(t, R0, m->link_jaxis[l]);
+          v3madd(pos, p0, t, q);
+          for (int k = 0; k < 4; ++k) quat[k] = q0[k];
+        }
+        const int s0 = nsteps & 1; // start buffer chosen so that the result lands in lpos / lquat
+        v3cpy(bufp[s0] + strp[s0] * l, pos);
+        for (int k = 0; k < 4; ++k) bufq[s0][strq[s0] * l + k] = quat[k];
+        bufa[s0][l] = m->link_parent[l];
+      }
+    }
+  LANES_END
+  for (int st = 0; st < nsteps; ++st) {
+    const int cur = (nsteps - st) & 1, nxt = cur ^ 1;
+    LANES_BEGIN
+      const int l = lane;
+      if (l < nrl) {
+        const int a = bufa[cur][l];
+        float pos[3], quat[4];
+        v3cpy(pos, bufp[cur] + strp[cur] * l);
+        for (int k = 0; k < 4; ++k) quat[k] = bufq[cur][strq[cur] * l + k];
+        int an = a;
+        if (a >= 0) { // compose with the transform accumulated at the ancestor
+          float qa_[4], Ra[9], t[3], qn[4];
+          for (int k = 0; k < 4; ++k) qa_[k] = bufq[cur][strq[cur] * a + k];
+          q2mat(Ra, qa_);
+          m3mulv(t, Ra, pos);
+          v3add(pos, bufp[cur] + strp[cur] * a, t);
+          qmul(qn, qa_, quat);
+          for (int k = 0; k < 4; ++k) quat[k] = qn[k];
+          an = bufa[cur][a];
+        }
+        v3cpy(bufp[nxt] + strp[nxt] * l, pos);
+        for (int k = 0; k < 4; ++k) bufq[nxt][strq[nxt] * l + k] = quat[k];
+        bufa[nxt][l] = an;
       }
     LANES_END
   }
+  // world rotation, joint motion subspace S (about robot_ref), own velocity term
+  float* const bufv[2] = {w->lvel, w->lacc};
+  LANES_BEGIN
+    const int l = lane;
+    if (l < nrl) {
+      float quat[4], R[9], t[3], anchor[3], axis[3], Sd[6];
+      for (int k = 0; k < 4; ++k) quat[k] = w->lquat[4 * l + k];
+      qnormalize(quat);
+      for (int k = 0; k < 4; ++k) w->lquat[4 * l + k] = quat[k];
+      q2mat(R, quat);
+      for (int k = 0; k < 9; ++k) w->lmat[9 * l + k] = R[k];
+      m3mulv(t, R, m->link_jpos[l]);
+      v3add(anchor, w->lpos + 3 * l, t);
+      m3mulv(axis, R, m->link_jaxis[l]);
+      if (m->link_jtype[l] == FE_JNT_HINGE) { v3cpy(Sd, axis); v3sub(t, anchor, Pr); v3cross(Sd + 3, t, axis); }
+      else { Sd[0] = Sd[1] = Sd[2] = 0.f; v3cpy(Sd + 3, axis); }
+      const int da = m->link_dadr[l];
+      const float qd = w->qvel[da];
+      const int s0 = nsteps & 1;
+      for (int k = 0; k < 6; ++k) { w->S[6 * da + k] = Sd[k]; bufv[s0][6 * l + k] = Sd[k] * qd; }
+      bufa[s0][l] = m->link_parent[l];
+    }
+  LANES_END
+  for (int st = 0; st < nsteps; ++st) { // V_l = sum over ancestors of S_d qd
+    const int cur = (nsteps - st) & 1, nxt = cur ^ 1;
+    LANES_BEGIN
+      const int l = lane;
+      if (l < nrl) {
+        const int a = bufa[cur][l];
+        for (int k = 0; k < 6; ++k) bufv[nxt][6 * l + k] = bufv[cur][6 * l + k] + (a >= 0 ? bufv[cur][6 * a + k] : 0.f);
+        bufa[nxt][l] = a >= 0 ? bufa[cur][a] : -1;
+      }
+    LANES_END
+  }
+  // bias acceleration: A_l = [0; -g] + sum over ancestors of (V_parent(d) x_m S_d) qd
+  float* const bufc[2] = {w->lfrc, w->lacc};
+  LANES_BEGIN
+    const int l = lane;
+    if (l < nrl) {
+      const int p = m->link_parent[l], da = m->link_dadr[l];
+      float Vp[6] = {0, 0, 0, 0, 0, 0}, Sdot[6];
+      if (p >= 0) for (int k = 0; k < 6; ++k) Vp[k] = w->lvel[6 * p + k];
+      crossm(Sdot, Vp, w->S + 6 * da);
+      const float qd = w->qvel[da];
+      const int s0 = nsteps & 1;
+      for (int k = 0; k < 6; ++k) bufc[s0][6 * l + k] = Sdot[k] * qd;
+      bufa[s0][l] = p;
+    }
+  LANES_END
+  for (int st = 0; st < nsteps; ++st) {
+    const int cur = (nsteps - st) & 1, nxt = cur ^ 1;
+    LANES_BEGIN
+      const int l = lane;
+      if (l < nrl) {
+        const int a = bufa[cur][l];
+        for (int k = 0; k < 6; ++k) bufc[nxt][6 * l + k] = bufc[cur][6 * l + k] + (a >= 0 ? bufc[cur][6 * a + k] : 0.f);
+        bufa[nxt][l] = a >= 0 ? bufa[cur][a] : -1;
+      }
+    LANES_END
+  }
+  LANES_BEGIN // result of the scan is in lfrc; move it (plus the gravity term) to lacc, where the parts already wrote theirs via lacc2
+    const int l = lane;
+    float A[6];
+    if (l < nl) {
+      if (l < nrl) { for (int k = 0; k < 6; ++k) A[k] = w->lfrc[6 * l + k]; A[3] -= g[0]; A[4] -= g[1]; A[5] -= g[2]; }
+      else for (int k = 0; k < 6; ++k) A[k] = w->lacc2[6 * l + k];
+    }
+    PV(Atmp_)[0] = A[0]; PV(Atmp_)[1] = A[1]; PV(Atmp_)[2] = A[2]; PV(Atmp_)[3] = A[3]; PV(Atmp_)[4] = A[4]; PV(Atmp_)[5] = A[5];
+  LANES_END
+  LANES_BEGIN
+    if (lane < nl) for (int k = 0; k < 6; ++k) w->lacc[6 * lane + k] = PV(Atmp_)[k];
+  LANES_END
   // spatial inertia about the link's reference point (robot_ref for robot links, own origin for parts) + RNE wrench
   LANES_BEGIN
     const int l = lane;
@@ -345,28 +433,22 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
       for (int k = 0; k < 6; ++k) w->lfrc[6 * l + k] = IA[k] + X[k];
     }
   LANES_END
-  // leaves -> root accumulation of RNE wrench and composite inertia (robot tree)
-  for (int level = m->maxdepth - 1; level >= 0; --level) {
-    LANES_BEGIN
-      const int l = lane;
-      if (l < nrl && m->link_depth[l] == level) {
-        for (int c = l + 1; c < nrl; ++c)
-          if (m->link_parent[c] == l) {
-            for (int k = 0; k < 6; ++k) w->lfrc[6 * l + k] += w->lfrc[6 * c + k];
-            for (int k = 0; k < 10; ++k) w->lcrb[10 * l + k] += w->lcrb[10 * c + k];
-          }
-      }
-    LANES_END
-  }
-  // robot: bias force, joint-space inertia, smooth force
+  // robot: each dof sums the RNE wrench and the spatial inertia of its subtree (links whose ancestor mask holds it),
+  // then bias force, joint-space inertia row (CRBA) and smooth force
   LANES_BEGIN
     const int d = lane;
     if (d < nr) {
       const float* Sd = w->S + 6 * d;
-      const float b = dot6(Sd, w->lfrc + 6 * d);
+      float Fs[6] = {0, 0, 0, 0, 0, 0}, Ic[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = d; c < nrl; ++c)
+        if ((m->link_ancmask[c] >> d) & 1) {
+          for (int k = 0; k < 6; ++k) Fs[k] += w->lfrc[6 * c + k];
+          for (int k = 0; k < 10; ++k) Ic[k] += w->lcrb[10 * c + k];
+        }
+      const float b = dot6(Sd, Fs);
       w->bias[d] = b;
       float F[6];
-      inert_mulv(F, w->lcrb + 10 * d, Sd);
+      inert_mulv(F, Ic, Sd);
       for (int a = d; a >= 0; a = m->link_parent[a]) {
         float v = dot6(w->S + 6 * a, F);
         w->Mr[d * nr + a] = v;
@@ -469,36 +551,44 @@ FE_FN void fe_collide(FeWarp* w) {
     }
     if (lane < m->npart) w->touch[lane] = 0;
   LANES_END
+  // broad phase: every lane tests a contiguous range of the pair list (order preserved), one scan compacts the hits
   int ncand = 0;
-  for (int base = 0; base < npair; base += 32) {
+  {
+    const int per = (npair + 31) / 32;
+    int run = 0;
+    (void)run;
     LANES_BEGIN
-      const int k = base + lane;
-      int flag = 0;
-      if (k < npair) {
+      unsigned long long hits = 0ull;
+      const int k0 = lane * per, k1 = (k0 + per < npair) ? k0 + per : npair;
+      for (int k = k0; k < k1; ++k) {
         const int g1 = m->pair_g1[k], g2 = m->pair_g2[k];
         if ((w->contype[g1] & w->conaff[g2]) || (w->contype[g2] & w->conaff[g1])) {
           float t[3];
           v3sub(t, w->gpos + 3 * g2, w->gpos + 3 * g1);
+          bool hit;
           if (m->geom_type[g1] == FE_GEOM_PLANE) {
             float n[3];
             fe_col(n, w->gmat + 9 * g1, 2);
-            flag = v3dot(t, n) <= m->geom_rbound[g2];
+            hit = v3dot(t, n) <= m->geom_rbound[g2];
           } else {
-            float bnd = m->geom_rbound[g1] + m->geom_rbound[g2];
-            flag = v3dot(t, t) <= bnd * bnd;
+            const float bnd = m->geom_rbound[g1] + m->geom_rbound[g2];
+            hit = v3dot(t, t) <= bnd * bnd;
           }
+          if (hit) hits |= 1ull << (k - k0);
         }
       }
-      w->iscr[lane] = flag;
+#if FE_DEVICE_BUILD
+      const int n = __popcll(hits);
+#else
+      const int n = __builtin_popcountll(hits);
+#endif
+      int off = FE_SCAN(run, n);
+      for (int k = k0; k < k1; ++k)
+        if ((hits >> (k - k0)) & 1ull) { if (off < FE_MAXCAND) w->cand[off] = k; ++off; }
+      if (lane == 31) w->iscr[0] = off;
     LANES_END
-    const unsigned mask = fe_ballot32(w->iscr);
-    LANES_BEGIN
-      if ((mask >> lane) & 1u) {
-        int idx = ncand + fe_popc(mask & ((1u << lane) - 1u));
-        if (idx < FE_MAXCAND) w->cand[idx] = base + lane;
-      }
-    LANES_END
-    ncand += fe_popc(mask);
+    ncand = w->iscr[0];
+    LANES_BEGIN LANES_END
   }
   if (ncand > FE_MAXCAND) { ncand = FE_MAXCAND; LANES_BEGIN if (lane == 0) w->u[2] |= 1; LANES_END }
   int ncon = 0;

@@ -107,6 +107,12 @@ def _grasp_and_align_state(m, env):
     zl /= np.linalg.norm(zl)
     yl = np.cross(zl, d)
     R = np.stack([d, yl, zl], axis=1)  # leg x along the finger axis, leg z (its top) pointing down
+    # a slight tilt keeps the pad / leg faces from being exactly parallel: with parallel faces the choice of box-box
+    # contact points is decided by rounding, and the fp32 and fp64 pipelines would then follow different (equally valid) paths
+    ty, tz = 0.011, 0.007
+    Ry = np.array([[np.cos(ty), 0, np.sin(ty)], [0, 1, 0], [-np.sin(ty), 0, np.cos(ty)]])
+    Rz = np.array([[np.cos(tz), -np.sin(tz), 0], [np.sin(tz), np.cos(tz), 0], [0, 0, 1]])
+    R = R @ Ry @ Rz
     leg_q = np.concatenate([0.5 * (cl + cr), mjcf.mat_to_q(R)])
     s1 = m.names["site"].index("leg-table,0,90,180,270,conn_site1")
     s2 = m.names["site"].index("table-leg,0,90,180,270,conn_site1")
