@@ -29,6 +29,7 @@ struct fe_handle {
   FeDebug dbg;
   FeEnvState es;
   int slice_words = 0;
+  FeLayout lay;       // where each array of an env's slice starts (same for every env of the handle)
   std::vector<FeField> fields;
   std::vector<void*> allocs;
   std::string err;
@@ -108,8 +109,7 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   h->allocs.push_back(h->dm); h->allocs.push_back(h->ds);
   plat_upload(h->dm, &h->hm, sizeof(fe_model));
   plat_upload(h->ds, &h->hs, sizeof(fe_scene));
-  FeWarp tmp;
-  h->slice_words = fe_warp_bind(&tmp, nullptr, &h->hm, h->opt);
+  h->slice_words = fe_layout_build(&h->lay, &h->hm, h->opt);
   h->slice_words = (h->slice_words + 31) & ~31;
   FeState& s = h->st;
   s.N = n_envs;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define PLAT_IS_CUDA 1
 struct fe_handle;
@@ -45,11 +46,11 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_step_kernel(FeState st
   const int env = st.order[slot];
   FeEnv e;
   fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
-  fe_load(&e.w, st, env);
+  fe_load(e.w, st, env);
   fe_env_load_groups(&e);
   fe_env_step_one(&e, actions, reward, done, info);
   fe_env_store_groups(&e);
-  fe_store(&e.w, st, env);
+  fe_store(e.w, st, env);
 }
 
 __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
@@ -59,11 +60,11 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState s
   if (mask && !mask[env]) return;
   FeEnv e;
   fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
-  fe_load(&e.w, st, env);
+  fe_load(e.w, st, env);
   fe_env_load_groups(&e);
   fe_env_reset_one(&e);
   fe_env_store_groups(&e);
-  fe_store(&e.w, st, env);
+  fe_store(e.w, st, env);
 }
 
 // stable partition of the env ids: envs whose last step used the coupled (FULL) solver scope first.  One block.
@@ -124,8 +125,21 @@ static int plat_init(fe_handle* h) {
   h->plat = new CudaPlat();
   return 0;
 }
+// The slice layout table is one __constant__ object per process: (re)upload it when the handle about to launch uses a
+// different layout than the one resident (several handles with different models alive at once, as in the tests).
+static FeLayout g_resident_lay;
+static bool g_resident_valid = false;
+static int plat_use_layout(fe_handle* h) {
+  if (g_resident_valid && memcmp(&g_resident_lay, &h->lay, sizeof(FeLayout)) == 0) return 0;
+  CUDA_OK(cudaDeviceSynchronize()); // kernels of the previous layout's handle must have drained
+  CUDA_OK(cudaMemcpyToSymbol(fe_c_lay, &h->lay, sizeof(FeLayout)));
+  g_resident_lay = h->lay;
+  g_resident_valid = true;
+  return 0;
+}
 static int plat_prepare(fe_handle* h) {
   CudaPlat* p = (CudaPlat*)h->plat;
+  if (int rc = plat_use_layout(h)) return rc;
   if (p->smem_sim) return 0;
   // warps (= envs) per block: as many as fit in 227 KB of shared memory, at most FE_MAX_WPB; FE_WPB overrides
   const size_t per_env = (size_t)(h->slice_words + FE_ENV_EXTRA_WORDS) * 4;

@@ -23,30 +23,30 @@ struct FeDebug {
 
 FE_FN void fe_load(FeWarp* w, const FeState& s, int env) {
   const fe_model* m = w->m;
-#define LD(field, n) for (int i = lane; i < (n); i += 32) w->field[i] = s.field[(size_t)env * (n) + i];
+#define LD(field, n) for (int i = lane; i < (n); i += 32) w->field()[i] = s.field[(size_t)env * (n) + i];
   LANES_BEGIN
     LD(qpos, m->nq) LD(qvel, m->nv) LD(warm, m->nv) LD(ctrl, m->nu) LD(qfrc_applied, m->nr) LD(gravcomp, m->npart) LD(eq_data, 7 * m->neq)
     LD(contype, m->ngeom) LD(conaff, m->ngeom) LD(eq_active, m->neq) LD(bias, m->nr)
-    if (lane < 16) w->u[lane] = 0;
+    if (lane < 16) w->u()[lane] = 0;
   LANES_END
 #undef LD
 }
 FE_FN void fe_store(FeWarp* w, const FeState& s, int env) {
   const fe_model* m = w->m;
-#define ST(field, n) for (int i = lane; i < (n); i += 32) s.field[(size_t)env * (n) + i] = w->field[i];
+#define ST(field, n) for (int i = lane; i < (n); i += 32) s.field[(size_t)env * (n) + i] = w->field()[i];
   LANES_BEGIN
     ST(qpos, m->nq) ST(qvel, m->nv) ST(warm, m->nv) ST(ctrl, m->nu) ST(qfrc_applied, m->nr) ST(gravcomp, m->npart) ST(eq_data, 7 * m->neq)
     ST(contype, m->ngeom) ST(conaff, m->ngeom) ST(eq_active, m->neq)
     ST(bias, m->nr) ST(lpos, 3 * m->nlink) ST(lquat, 4 * m->nlink) ST(lvel, 6 * m->nlink) ST(touch, m->npart)
-    if (lane == 0) { s.flags[env] |= w->u[2]; s.ncon[env] = w->u[0]; s.niter[env] = w->u[3]; }
-    if (lane < 12) s.stats[(size_t)env * 12 + lane] = w->u[4 + lane];
+    if (lane == 0) { s.flags[env] |= w->u()[2]; s.ncon[env] = w->u()[0]; s.niter[env] = w->u()[3]; }
+    if (lane < 12) s.stats[(size_t)env * 12 + lane] = w->u()[4 + lane];
   LANES_END
 #undef ST
 }
 FE_FN void fe_dump(FeWarp* w, const FeDebug& d, int env) {
   const fe_model* m = w->m;
   const int mc = w->opt.maxcon;
-#define DP(field, n) if (d.field) for (int i = lane; i < (n); i += 32) d.field[(size_t)env * (n) + i] = w->field[i];
+#define DP(field, n) if (d.field) for (int i = lane; i < (n); i += 32) d.field[(size_t)env * (n) + i] = w->field()[i];
   LANES_BEGIN
     DP(Mr, m->nr * m->nr) DP(fs, m->nv) DP(as, m->nv) DP(linert, 10 * m->nlink) DP(x, m->nv) DP(fc, m->nv) DP(lmat, 9 * m->nlink) DP(S, 6 * m->nr)
     DP(c_dist, mc) DP(c_pos, 3 * mc) DP(c_frame, 9 * mc) DP(c_aref, 3 * mc) DP(c_D, 2 * mc) DP(c_f, 3 * mc) DP(c_geom, mc) DP(c_state, mc)
@@ -56,10 +56,9 @@ FE_FN void fe_dump(FeWarp* w, const FeDebug& d, int env) {
 
 // nsub mj_steps of one env. mode 0: step; mode 1: forward only (mj_forward, no integration), with optional dump.
 FE_FN void fe_run_env(const FeState& s, const fe_model* m, const FeOpt& opt, int env, int nsub, int mode, float* slice, const FeDebug& dbg) {
-  FeWarp w;
-  fe_warp_bind(&w, slice, m, opt);
-  fe_load(&w, s, env);
-  if (mode == 1) { fe_forward(&w); fe_dump(&w, dbg, env); }
-  else for (int i = 0; i < nsub; ++i) fe_substep_lockstep(&w);
-  fe_store(&w, s, env);
+  FeWarp* w = fe_warp_bind(slice, m, opt);
+  fe_load(w, s, env);
+  if (mode == 1) { fe_forward(w); fe_dump(w, dbg, env); }
+  else for (int i = 0; i < nsub; ++i) fe_substep_lockstep(w);
+  fe_store(w, s, env);
 }

@@ -33,68 +33,95 @@ struct FeOpt {
   int lockstep;     // bit k: block barrier before phase k of fe_substep_lockstep (instruction-fetch sharing)
 };
 
-// ---- shared-memory layout of one warp (all sizes in 4-byte words)
-struct FeWarp {
+// ---- shared-memory slice of one warp (= one env).  All sizes in 4-byte words.
+// The slice starts with a small header (FeWarp) followed by the arrays below.  Where each array starts depends only on
+// the model and the contact capacity, so the offsets live in one FeLayout table -- __constant__ memory on the device,
+// where every thread reads the same entry -- and `w->qpos()` is header address + table entry: no per-thread pointer
+// table, no local-memory traffic to reach the slice.
+#define FE_SLICE_F(X) /* float arrays */ \
+  X(qpos) X(qvel) X(warm) X(ctrl) X(qfrc_applied) X(gravcomp) X(eq_data) /* persistent state */ \
+  X(lpos) X(lquat) X(lmat) X(S) X(lvel) X(lacc) X(lfrc) X(linert) X(lcrb) X(Mr) X(Lr) X(fs) X(as) X(bias) X(lacc2) /* kinematics / dynamics */ \
+  X(gpos) X(gmat) /* collision */ \
+  X(c_dist) X(c_pos) X(c_frame) X(c_aref) X(c_D) X(c_mu) X(c_fric) X(c_jar) X(c_jv) X(c_f) /* contacts (SoA, maxcon each) */ \
+  X(w_r1) X(w_G) X(w_aref) X(w_D) X(w_jar) X(w_jv) X(w_f) /* welds (neq each) */ \
+  X(l_sign) X(l_aref) X(l_D) X(l_jar) X(l_jv) X(l_f) /* joint limits (nr each) */ \
+  X(x) X(Ma) X(grad) X(search) X(Mv) X(fc) X(H) X(Jc) X(scr) /* solver */
+#define FE_SLICE_I(X) /* int arrays */ \
+  X(contype) X(conaff) X(eq_active) X(cand) X(touch) X(c_geom) X(c_link) X(c_state) X(c_kind) X(plist) X(first) X(iscr) X(colmap) X(skip) \
+  X(u) /* uniform scalars: [0]=ncon [1]=ncand [2]=flags [3]=niter [4..]=per-call statistics */
+
+struct FeLayout {
+#define X(f) int f;
+  FE_SLICE_F(X) FE_SLICE_I(X)
+#undef X
+};
+static FeLayout fe_h_lay; // host copy: what the lane-emulated build reads, and what the CUDA build uploads
+#if FE_DEVICE_BUILD
+__constant__ FeLayout fe_c_lay;
+#define FE_ACC __host__ __device__ __forceinline__
+#else
+#define FE_ACC inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define FE_LAY fe_c_lay
+#else
+#define FE_LAY fe_h_lay
+#endif
+
+#define FE_WARP_HDR_WORDS 16
+struct FeWarp { // header at word 0 of the slice
   const fe_model* m;
   FeOpt opt;
-  // persistent state
-  float *qpos, *qvel, *warm, *ctrl, *qfrc_applied, *gravcomp, *eq_data;
-  int *contype, *conaff, *eq_active;
-  // kinematics / dynamics
-  float *lpos, *lquat, *lmat, *S, *lvel, *lacc, *lfrc, *linert, *lcrb, *Mr, *Lr, *fs, *as, *bias, *lacc2;
-  // collision
-  float *gpos, *gmat;
-  int *cand, *touch;
-  // contacts (SoA, maxcon each)
-  float *c_dist, *c_pos, *c_frame, *c_aref, *c_D, *c_mu, *c_fric, *c_jar, *c_jv, *c_f;
-  int *c_geom, *c_link, *c_state, *c_kind, *plist;
-  // welds (neq each) and limits (nr each)
-  float *w_r1, *w_G, *w_aref, *w_D, *w_jar, *w_jv, *w_f;
-  float *l_sign, *l_aref, *l_D, *l_jar, *l_jv, *l_f;
-  // solver
-  float *x, *Ma, *grad, *search, *Mv, *fc, *H, *Jc, *scr;
-  int *first, *iscr, *colmap, *skip;
-  // uniform scalars (kept in smem so that both builds see one copy)
-  int* u; // [0]=ncon [1]=ncand [2]=flags [3]=niter [4]=coupled
-  // solver scope of the cooperative routines: all dofs (FULL) or the robot block only (FAST, parts solved per lane)
+  // solver scope of the cooperative routines: all dofs (FULL) or the robot block only (FAST, parts solved per lane group)
   int nact, fast;
+#define X(f) FE_ACC float* f() const { return (float*)this + FE_LAY.f; }
+  FE_SLICE_F(X)
+#undef X
+#define X(f) FE_ACC int* f() const { return (int*)this + FE_LAY.f; }
+  FE_SLICE_I(X)
+#undef X
 };
+static_assert(sizeof(FeWarp) <= 4 * FE_WARP_HDR_WORDS, "slice header too small");
 
 FE_BOTH int fe_tri(int n) { return n * (n + 1) / 2; }
 
-// Carves the slice; returns the number of words used. Pass base = nullptr to only measure.
-FE_BOTH int fe_warp_bind(FeWarp* w, float* base, const fe_model* m, const FeOpt& opt) {
-  int o = 0;
+// Lays the slice out; returns the number of words used.
+FE_BOTH int fe_layout_build(FeLayout* L, const fe_model* m, const FeOpt& opt) {
+  int o = FE_WARP_HDR_WORDS;
   const int nq = m->nq, nv = m->nv, nu = m->nu, nl = m->nlink, nr = m->nr, np = m->npart, ng = m->ngeom, ne = m->neq, mc = opt.maxcon;
-#define CARVE_F(field, n) w->field = base ? base + o : nullptr; o += (n);
-#define CARVE_I(field, n) w->field = base ? (int*)(base + o) : nullptr; o += (n);
-  w->m = m; w->opt = opt; w->nact = nv; w->fast = 0;
-  CARVE_F(qpos, nq) CARVE_F(qvel, nv) CARVE_F(warm, nv) CARVE_F(ctrl, nu) CARVE_F(qfrc_applied, nr) CARVE_F(gravcomp, np) CARVE_F(eq_data, 7 * ne)
-  CARVE_I(contype, ng) CARVE_I(conaff, ng) CARVE_I(eq_active, ne)
-  CARVE_F(lpos, 3 * nl) CARVE_F(lquat, 4 * nl) CARVE_F(lmat, 9 * nl) CARVE_F(S, 6 * nr) CARVE_F(lvel, 6 * nl) CARVE_F(lacc, 6 * nl) CARVE_F(lfrc, 6 * nl)
-  w->lacc2 = w->lfrc; /* RNE wrench (smooth stage) and solver link accelerations are never live together */
-  CARVE_F(linert, 10 * nl) CARVE_F(lcrb, (10 * nr > 96 ? 10 * nr : 96)) CARVE_F(Mr, nr * nr) CARVE_F(Lr, fe_tri(nr)) CARVE_F(fs, nv) CARVE_F(as, nv) CARVE_F(bias, nr)
-  CARVE_I(touch, np)
-  CARVE_F(c_dist, mc) CARVE_F(c_pos, 3 * mc) CARVE_F(c_frame, 9 * mc) CARVE_F(c_aref, 3 * mc) CARVE_F(c_D, 2 * mc) CARVE_F(c_mu, mc) CARVE_F(c_fric, mc)
-  CARVE_F(c_jar, 3 * mc) CARVE_F(c_jv, 3 * mc) CARVE_F(c_f, 3 * mc) CARVE_I(c_geom, mc) CARVE_I(c_link, mc) CARVE_I(c_state, mc) CARVE_I(c_kind, mc) CARVE_I(plist, 9 * np)
-  CARVE_F(w_r1, 3 * ne) CARVE_F(w_G, 9 * ne) CARVE_F(w_aref, 6 * ne) CARVE_F(w_D, 6 * ne) CARVE_F(w_jar, 6 * ne) CARVE_F(w_jv, 6 * ne) CARVE_F(w_f, 6 * ne)
-  CARVE_F(l_sign, nr) CARVE_F(l_aref, nr) CARVE_F(l_D, nr) CARVE_F(l_jar, nr) CARVE_F(l_jv, nr) CARVE_F(l_f, nr)
-  CARVE_F(x, nv) CARVE_F(Ma, nv) CARVE_F(grad, nv) CARVE_F(search, nv) CARVE_F(Mv, nv) CARVE_F(fc, nv)
-  w->Jc = w->lcrb; /* composite inertias (smooth stage) vs row staging of fe_build_H */
-  CARVE_F(scr, 2 * 32) CARVE_I(first, nv) CARVE_I(skip, nv) CARVE_I(iscr, 32) CARVE_I(colmap, 32) CARVE_I(u, 16)
+#define CARVE(field, n) L->field = o; o += (n);
+  CARVE(qpos, nq) CARVE(qvel, nv) CARVE(warm, nv) CARVE(ctrl, nu) CARVE(qfrc_applied, nr) CARVE(gravcomp, np) CARVE(eq_data, 7 * ne)
+  CARVE(contype, ng) CARVE(conaff, ng) CARVE(eq_active, ne)
+  CARVE(lpos, 3 * nl) CARVE(lquat, 4 * nl) CARVE(lmat, 9 * nl) CARVE(S, 6 * nr) CARVE(lvel, 6 * nl) CARVE(lacc, 6 * nl) CARVE(lfrc, 6 * nl)
+  L->lacc2 = L->lfrc; /* RNE wrench (smooth stage) and solver link accelerations are never live together */
+  CARVE(linert, 10 * nl) CARVE(lcrb, (10 * nr > 96 ? 10 * nr : 96)) CARVE(Mr, nr * nr) CARVE(Lr, fe_tri(nr)) CARVE(fs, nv) CARVE(as, nv) CARVE(bias, nr)
+  CARVE(touch, np)
+  CARVE(c_dist, mc) CARVE(c_pos, 3 * mc) CARVE(c_frame, 9 * mc) CARVE(c_aref, 3 * mc) CARVE(c_D, 2 * mc) CARVE(c_mu, mc) CARVE(c_fric, mc)
+  CARVE(c_jar, 3 * mc) CARVE(c_jv, 3 * mc) CARVE(c_f, 3 * mc) CARVE(c_geom, mc) CARVE(c_link, mc) CARVE(c_state, mc) CARVE(c_kind, mc) CARVE(plist, 9 * np)
+  CARVE(w_r1, 3 * ne) CARVE(w_G, 9 * ne) CARVE(w_aref, 6 * ne) CARVE(w_D, 6 * ne) CARVE(w_jar, 6 * ne) CARVE(w_jv, 6 * ne) CARVE(w_f, 6 * ne)
+  CARVE(l_sign, nr) CARVE(l_aref, nr) CARVE(l_D, nr) CARVE(l_jar, nr) CARVE(l_jv, nr) CARVE(l_f, nr)
+  CARVE(x, nv) CARVE(Ma, nv) CARVE(grad, nv) CARVE(search, nv) CARVE(Mv, nv) CARVE(fc, nv)
+  L->Jc = L->lcrb; /* composite inertias (smooth stage) vs row staging of fe_build_H */
+  CARVE(scr, 2 * 32) CARVE(first, nv) CARVE(skip, nv) CARVE(iscr, 32) CARVE(colmap, 32) CARVE(u, 16)
   // H (solver) and the collision scratch (geom poses, candidate list) are never live together: overlay them
-  int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
-  int big = hwords > cwords ? hwords : cwords;
-  w->H = base ? base + o : nullptr;
-  w->gpos = w->H; w->gmat = base ? base + o + 3 * ng : nullptr; w->cand = base ? (int*)(base + o + 12 * ng) : nullptr;
-  o += big;
-#undef CARVE_F
-#undef CARVE_I
+  const int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
+  L->H = o; L->gpos = o; L->gmat = o + 3 * ng; L->cand = o + 12 * ng;
+  o += hwords > cwords ? hwords : cwords;
+#undef CARVE
   return o;
 }
 
+// Writes the slice header; the arrays are reached through the layout table.
+FE_FN FeWarp* fe_warp_bind(float* slice, const fe_model* m, const FeOpt& opt) {
+  FeWarp* w = (FeWarp*)slice;
+  LANES_BEGIN
+    if (lane == 0) { w->m = m; w->opt = opt; w->nact = m->nv; w->fast = 0; }
+  LANES_END
+  return w;
+}
+
 // ---------------------------------------------------------------- 6x6 SPD helpers (packed lower, index i(i+1)/2+j)
-FE_HDN void fe_inert_sym6(float* A, const float* I, float diag_add) {
+FE_HD void fe_inert_sym6(float* A, const float* I, float diag_add) {
   const float m = I[0], hx = I[1], hy = I[2], hz = I[3];
   // rows 0-2: [Io, [h]x]; rows 3-5: [[h]x^T, m 1]
   A[0] = I[4] + diag_add;
@@ -105,7 +132,7 @@ FE_HDN void fe_inert_sym6(float* A, const float* I, float diag_add) {
   A[10] = -hz; A[11] = 0.f; A[12] = hx; A[13] = 0.f; A[14] = m + diag_add;
   A[15] = hy; A[16] = -hx; A[17] = 0.f; A[18] = 0.f; A[19] = 0.f; A[20] = m + diag_add;
 }
-FE_HDN bool fe_chol6(float* A) {
+FE_HD bool fe_chol6(float* A) {
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -125,7 +152,7 @@ FE_HDN bool fe_chol6(float* A) {
   }
   return ok;
 }
-FE_HDN void fe_chol6_solve(const float* L, float* x) {
+FE_HD void fe_chol6_solve(const float* L, float* x) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     float s = x[i];
@@ -220,7 +247,7 @@ FE_FN void fe_chol_blocks(FeWarp* w, float* H, const int* skip) {
       if (skip[sp]) {
         float A[21];
         for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = H[fe_tri(sp + i) + sp + j];
-        if (!fe_chol6(A)) w->u[2] |= 4;
+        if (!fe_chol6(A)) w->u()[2] |= 4;
         for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) H[fe_tri(sp + i) + sp + j] = A[i * (i + 1) / 2 + j];
       }
     }
@@ -253,9 +280,9 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
   // velocities and bias accelerations are obtained by pointer jumping up the tree (log2(depth) short regions).
   int nsteps = 0;
   while ((1 << nsteps) <= m->maxdepth) ++nsteps;
-  float* const bufp[2] = {w->lpos, w->lacc};   // position (3 of 6 words per link in the scratch buffer)
-  float* const bufq[2] = {w->lquat, w->lfrc};  // quaternion (4 of 6 words)
-  int* const bufa[2] = {w->iscr, w->colmap};   // ancestor pointer
+  float* const bufp[2] = {w->lpos(), w->lacc()};   // position (3 of 6 words per link in the scratch buffer)
+  float* const bufq[2] = {w->lquat(), w->lfrc()};  // quaternion (4 of 6 words)
+  int* const bufa[2] = {w->iscr(), w->colmap()};   // ancestor pointer
   const int strp[2] = {3, 6}, strq[2] = {4, 6};
   LANES_BEGIN
     const int l = lane;
@@ -263,24 +290,24 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
       const int qa = m->link_qadr[l], da = m->link_dadr[l];
       if (m->link_jtype[l] == FE_JNT_FREE) { // pose straight from qpos; V, A in closed form about the link origin
         float pos[3], quat[4], R[9], V[6], A[6], t[3];
-        v3cpy(pos, w->qpos + qa);
-        quat[0] = w->qpos[qa + 3]; quat[1] = w->qpos[qa + 4]; quat[2] = w->qpos[qa + 5]; quat[3] = w->qpos[qa + 6];
+        v3cpy(pos, w->qpos() + qa);
+        quat[0] = w->qpos()[qa + 3]; quat[1] = w->qpos()[qa + 4]; quat[2] = w->qpos()[qa + 5]; quat[3] = w->qpos()[qa + 6];
         qnormalize(quat);
         q2mat(R, quat);
-        m3mulv(V, R, w->qvel + da + 3);
-        v3cpy(V + 3, w->qvel + da);
+        m3mulv(V, R, w->qvel() + da + 3);
+        v3cpy(V + 3, w->qvel() + da);
         v3cross(t, V, V + 3);
         A[0] = A[1] = A[2] = 0.f;
         A[3] = -t[0] - g[0]; A[4] = -t[1] - g[1]; A[5] = -t[2] - g[2];
-        v3cpy(w->lpos + 3 * l, pos);
-        for (int k = 0; k < 4; ++k) w->lquat[4 * l + k] = quat[k];
-        for (int k = 0; k < 9; ++k) w->lmat[9 * l + k] = R[k];
-        for (int k = 0; k < 6; ++k) { w->lvel[6 * l + k] = V[k]; w->lacc2[6 * l + k] = A[k]; }
+        v3cpy(w->lpos() + 3 * l, pos);
+        for (int k = 0; k < 4; ++k) w->lquat()[4 * l + k] = quat[k];
+        for (int k = 0; k < 9; ++k) w->lmat()[9 * l + k] = R[k];
+        for (int k = 0; k < 6; ++k) { w->lvel()[6 * l + k] = V[k]; w->lacc2()[6 * l + k] = A[k]; }
       } else { // joint transform in the parent link frame
         float p0[3], q0[4], R0[9], t[3], pos[3], quat[4];
         v3cpy(p0, m->link_pos[l]);
         for (int k = 0; k < 4; ++k) q0[k] = m->link_quat[l][k];
-        const float q = w->qpos[qa];
+        const float q = w->qpos()[qa];
         if (m->link_jtype[l] == FE_JNT_HINGE) {
           const float sn = sinf(0.5f * q), cs = cosf(0.5f * q);
           const float ql[4] = {cs, m->link_jaxis[l][0] * sn, m->link_jaxis[l][1] * sn, m->link_jaxis[l][2] * sn};
@@ -332,25 +359,25 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
     LANES_END
   }
   // world rotation, joint motion subspace S (about robot_ref), own velocity term
-  float* const bufv[2] = {w->lvel, w->lacc};
+  float* const bufv[2] = {w->lvel(), w->lacc()};
   LANES_BEGIN
     const int l = lane;
     if (l < nrl) {
       float quat[4], R[9], t[3], anchor[3], axis[3], Sd[6];
-      for (int k = 0; k < 4; ++k) quat[k] = w->lquat[4 * l + k];
+      for (int k = 0; k < 4; ++k) quat[k] = w->lquat()[4 * l + k];
       qnormalize(quat);
-      for (int k = 0; k < 4; ++k) w->lquat[4 * l + k] = quat[k];
+      for (int k = 0; k < 4; ++k) w->lquat()[4 * l + k] = quat[k];
       q2mat(R, quat);
-      for (int k = 0; k < 9; ++k) w->lmat[9 * l + k] = R[k];
+      for (int k = 0; k < 9; ++k) w->lmat()[9 * l + k] = R[k];
       m3mulv(t, R, m->link_jpos[l]);
-      v3add(anchor, w->lpos + 3 * l, t);
+      v3add(anchor, w->lpos() + 3 * l, t);
       m3mulv(axis, R, m->link_jaxis[l]);
       if (m->link_jtype[l] == FE_JNT_HINGE) { v3cpy(Sd, axis); v3sub(t, anchor, Pr); v3cross(Sd + 3, t, axis); }
       else { Sd[0] = Sd[1] = Sd[2] = 0.f; v3cpy(Sd + 3, axis); }
       const int da = m->link_dadr[l];
-      const float qd = w->qvel[da];
+      const float qd = w->qvel()[da];
       const int s0 = nsteps & 1;
-      for (int k = 0; k < 6; ++k) { w->S[6 * da + k] = Sd[k]; bufv[s0][6 * l + k] = Sd[k] * qd; }
+      for (int k = 0; k < 6; ++k) { w->S()[6 * da + k] = Sd[k]; bufv[s0][6 * l + k] = Sd[k] * qd; }
       bufa[s0][l] = m->link_parent[l];
     }
   LANES_END
@@ -366,15 +393,15 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
     LANES_END
   }
   // bias acceleration: A_l = [0; -g] + sum over ancestors of (V_parent(d) x_m S_d) qd
-  float* const bufc[2] = {w->lfrc, w->lacc};
+  float* const bufc[2] = {w->lfrc(), w->lacc()};
   LANES_BEGIN
     const int l = lane;
     if (l < nrl) {
       const int p = m->link_parent[l], da = m->link_dadr[l];
       float Vp[6] = {0, 0, 0, 0, 0, 0}, Sdot[6];
-      if (p >= 0) for (int k = 0; k < 6; ++k) Vp[k] = w->lvel[6 * p + k];
-      crossm(Sdot, Vp, w->S + 6 * da);
-      const float qd = w->qvel[da];
+      if (p >= 0) for (int k = 0; k < 6; ++k) Vp[k] = w->lvel()[6 * p + k];
+      crossm(Sdot, Vp, w->S() + 6 * da);
+      const float qd = w->qvel()[da];
       const int s0 = nsteps & 1;
       for (int k = 0; k < 6; ++k) bufc[s0][6 * l + k] = Sdot[k] * qd;
       bufa[s0][l] = p;
@@ -395,25 +422,25 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
     const int l = lane;
     float A[6];
     if (l < nl) {
-      if (l < nrl) { for (int k = 0; k < 6; ++k) A[k] = w->lfrc[6 * l + k]; A[3] -= g[0]; A[4] -= g[1]; A[5] -= g[2]; }
-      else for (int k = 0; k < 6; ++k) A[k] = w->lacc2[6 * l + k];
+      if (l < nrl) { for (int k = 0; k < 6; ++k) A[k] = w->lfrc()[6 * l + k]; A[3] -= g[0]; A[4] -= g[1]; A[5] -= g[2]; }
+      else for (int k = 0; k < 6; ++k) A[k] = w->lacc2()[6 * l + k];
     }
     PV(Atmp_)[0] = A[0]; PV(Atmp_)[1] = A[1]; PV(Atmp_)[2] = A[2]; PV(Atmp_)[3] = A[3]; PV(Atmp_)[4] = A[4]; PV(Atmp_)[5] = A[5];
   LANES_END
   LANES_BEGIN
-    if (lane < nl) for (int k = 0; k < 6; ++k) w->lacc[6 * lane + k] = PV(Atmp_)[k];
+    if (lane < nl) for (int k = 0; k < 6; ++k) w->lacc()[6 * lane + k] = PV(Atmp_)[k];
   LANES_END
   // spatial inertia about the link's reference point (robot_ref for robot links, own origin for parts) + RNE wrench
   LANES_BEGIN
     const int l = lane;
     if (l < nl) {
-      const float* R = w->lmat + 9 * l;
+      const float* R = w->lmat() + 9 * l;
       float I[10], t[3];
       I[0] = m->link_mass[l];
       m3mulv(t, R, m->link_com[l]);
       if (l < nrl) {
         float d[3];
-        v3add(d, w->lpos + 3 * l, t);
+        v3add(d, w->lpos() + 3 * l, t);
         v3sub(d, d, Pr);
         sym3rot(I + 4, R, m->link_inertia_c[l]);
         const float mm = I[0], dd = v3dot(d, d);
@@ -425,12 +452,12 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
         I[1] = I[0] * t[0]; I[2] = I[0] * t[1]; I[3] = I[0] * t[2];
       }
       float IA[6], IV[6], X[6];
-      inert_mulv(IA, I, w->lacc + 6 * l);
-      inert_mulv(IV, I, w->lvel + 6 * l);
-      crossf(X, w->lvel + 6 * l, IV);
-      for (int k = 0; k < 10; ++k) w->linert[10 * l + k] = I[k];
-      if (l < nrl) for (int k = 0; k < 10; ++k) w->lcrb[10 * l + k] = I[k];
-      for (int k = 0; k < 6; ++k) w->lfrc[6 * l + k] = IA[k] + X[k];
+      inert_mulv(IA, I, w->lacc() + 6 * l);
+      inert_mulv(IV, I, w->lvel() + 6 * l);
+      crossf(X, w->lvel() + 6 * l, IV);
+      for (int k = 0; k < 10; ++k) w->linert()[10 * l + k] = I[k];
+      if (l < nrl) for (int k = 0; k < 10; ++k) w->lcrb()[10 * l + k] = I[k];
+      for (int k = 0; k < 6; ++k) w->lfrc()[6 * l + k] = IA[k] + X[k];
     }
   LANES_END
   // robot: each dof sums the RNE wrench and the spatial inertia of its subtree (links whose ancestor mask holds it),
@@ -438,33 +465,33 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
   LANES_BEGIN
     const int d = lane;
     if (d < nr) {
-      const float* Sd = w->S + 6 * d;
+      const float* Sd = w->S() + 6 * d;
       float Fs[6] = {0, 0, 0, 0, 0, 0}, Ic[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int c = d; c < nrl; ++c)
         if ((m->link_ancmask[c] >> d) & 1) {
-          for (int k = 0; k < 6; ++k) Fs[k] += w->lfrc[6 * c + k];
-          for (int k = 0; k < 10; ++k) Ic[k] += w->lcrb[10 * c + k];
+          for (int k = 0; k < 6; ++k) Fs[k] += w->lfrc()[6 * c + k];
+          for (int k = 0; k < 10; ++k) Ic[k] += w->lcrb()[10 * c + k];
         }
       const float b = dot6(Sd, Fs);
-      w->bias[d] = b;
+      w->bias()[d] = b;
       float F[6];
       inert_mulv(F, Ic, Sd);
       for (int a = d; a >= 0; a = m->link_parent[a]) {
-        float v = dot6(w->S + 6 * a, F);
-        w->Mr[d * nr + a] = v;
-        w->Mr[a * nr + d] = v;
+        float v = dot6(w->S() + 6 * a, F);
+        w->Mr()[d * nr + a] = v;
+        w->Mr()[a * nr + d] = v;
       }
-      float f = -m->dof_damping[d] * w->qvel[d] - b + w->qfrc_applied[d];
+      float f = -m->dof_damping[d] * w->qvel()[d] - b + w->qfrc_applied()[d];
       for (int u = 0; u < m->nu; ++u)
         if (m->act_dof[u] == d) {
-          float c = w->ctrl[u];
+          float c = w->ctrl()[u];
           if (m->act_ctrllimited[u]) c = fminf(fmaxf(c, m->act_ctrlrange[u][0]), m->act_ctrlrange[u][1]);
           const float gear = m->act_gear[u];
-          float af = m->act_gain[u] * c + m->act_bias[u][0] + m->act_bias[u][1] * gear * w->qpos[m->act_qadr[u]] + m->act_bias[u][2] * gear * w->qvel[d];
+          float af = m->act_gain[u] * c + m->act_bias[u][0] + m->act_bias[u][1] * gear * w->qpos()[m->act_qadr[u]] + m->act_bias[u][2] * gear * w->qvel()[d];
           if (m->act_forcelimited[u]) af = fminf(fmaxf(af, m->act_forcerange[u][0]), m->act_forcerange[u][1]);
           f += gear * af;
         }
-      w->fs[d] = f;
+      w->fs()[d] = f;
     }
   LANES_END
   // zero the entries of Mr between unrelated dofs (branches) -- they are never written above
@@ -472,21 +499,21 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
     for (int e = lane; e < nr * nr; e += 32) {
       int i = e / nr, j = e % nr;
       int lo = i < j ? i : j, hi = i < j ? j : i;
-      if (!((m->link_ancmask[hi] >> lo) & 1)) w->Mr[e] = 0.f;
+      if (!((m->link_ancmask[hi] >> lo) & 1)) w->Mr()[e] = 0.f;
     }
-    for (int e = lane; e < nr; e += 32) w->first[e] = 0;
+    for (int e = lane; e < nr; e += 32) w->first()[e] = 0;
   LANES_END
   // parts: smooth wrench and acceleration in z coordinates
   LANES_BEGIN
     const int p = lane;
     if (p < m->npart) {
       const int l = nrl + p, z = nr + 6 * p, da = m->link_dadr[l];
-      const float* I = w->linert + 10 * l;
-      const float* V = w->lvel + 6 * l;
+      const float* I = w->linert() + 10 * l;
+      const float* V = w->lvel() + 6 * l;
       const float damp = m->dof_damping[da];
       float W[6];
-      for (int k = 0; k < 6; ++k) W[k] = -w->lfrc[6 * l + k] - damp * V[k];
-      const float gc = w->gravcomp[p];
+      for (int k = 0; k < 6; ++k) W[k] = -w->lfrc()[6 * l + k] - damp * V[k];
+      const float gc = w->gravcomp()[p];
       if (gc != 0.f) { // xfrc_applied = -gc * gravity * mass at the CoM (furniture.py:2778-2790)
         float F[3] = {-gc * g[0] * I[0], -gc * g[1] * I[0], -gc * g[2] * I[0]}, r[3] = {I[1] / I[0], I[2] / I[0], I[3] / I[0]}, t[3];
         v3cross(t, r, F);
@@ -494,10 +521,10 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
       }
       float A[21], a[6];
       fe_inert_sym6(A, I, 0.f);
-      if (!fe_chol6(A)) w->u[2] |= 2;
-      for (int k = 0; k < 6; ++k) { w->fs[z + k] = W[k]; a[k] = W[k]; }
+      if (!fe_chol6(A)) w->u()[2] |= 2;
+      for (int k = 0; k < 6; ++k) { w->fs()[z + k] = W[k]; a[k] = W[k]; }
       fe_chol6_solve(A, a);
-      for (int k = 0; k < 6; ++k) w->as[z + k] = a[k];
+      for (int k = 0; k < 6; ++k) w->as()[z + k] = a[k];
     }
   LANES_END
   // robot smooth acceleration: Lr = chol(Mr)
@@ -507,12 +534,12 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
         int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
         while (fe_tri(i + 1) <= e) ++i;
         while (fe_tri(i) > e) --i;
-        w->Lr[e] = w->Mr[i * nr + (e - fe_tri(i))];
+        w->Lr()[e] = w->Mr()[i * nr + (e - fe_tri(i))];
       }
-      for (int e = lane; e < nr; e += 32) w->as[e] = w->fs[e];
+      for (int e = lane; e < nr; e += 32) w->as()[e] = w->fs()[e];
     LANES_END
-    if (!fe_chol(w, w->Lr, w->first, nr)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END }
-    fe_chol_solve(w, w->Lr, w->first, nr, w->as, w->grad);
+    if (!fe_chol(w, w->Lr(), w->first(), nr)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END }
+    fe_chol_solve(w, w->Lr(), w->first(), nr, w->as(), w->grad());
   }
   (void)nv;
 }
@@ -539,17 +566,17 @@ FE_FN void fe_collide(FeWarp* w) {
   LANES_BEGIN
     for (int gi = lane; gi < ng; gi += 32) {
       const int l = m->geom_link[gi];
-      float* gp = w->gpos + 3 * gi;
-      float* gm = w->gmat + 9 * gi;
+      float* gp = w->gpos() + 3 * gi;
+      float* gm = w->gmat() + 9 * gi;
       if (l < 0) { v3cpy(gp, m->geom_pos[gi]); for (int k = 0; k < 9; ++k) gm[k] = m->geom_mat[gi][k]; }
       else {
         float t[3];
-        m3mulv(t, w->lmat + 9 * l, m->geom_pos[gi]);
-        v3add(gp, w->lpos + 3 * l, t);
-        m3mul(gm, w->lmat + 9 * l, m->geom_mat[gi]);
+        m3mulv(t, w->lmat() + 9 * l, m->geom_pos[gi]);
+        v3add(gp, w->lpos() + 3 * l, t);
+        m3mul(gm, w->lmat() + 9 * l, m->geom_mat[gi]);
       }
     }
-    if (lane < m->npart) w->touch[lane] = 0;
+    if (lane < m->npart) w->touch()[lane] = 0;
   LANES_END
   // broad phase: every lane tests a contiguous range of the pair list (order preserved), one scan compacts the hits
   int ncand = 0;
@@ -562,13 +589,13 @@ FE_FN void fe_collide(FeWarp* w) {
       const int k0 = lane * per, k1 = (k0 + per < npair) ? k0 + per : npair;
       for (int k = k0; k < k1; ++k) {
         const int g1 = m->pair_g1[k], g2 = m->pair_g2[k];
-        if ((w->contype[g1] & w->conaff[g2]) || (w->contype[g2] & w->conaff[g1])) {
+        if ((w->contype()[g1] & w->conaff()[g2]) || (w->contype()[g2] & w->conaff()[g1])) {
           float t[3];
-          v3sub(t, w->gpos + 3 * g2, w->gpos + 3 * g1);
+          v3sub(t, w->gpos() + 3 * g2, w->gpos() + 3 * g1);
           bool hit;
           if (m->geom_type[g1] == FE_GEOM_PLANE) {
             float n[3];
-            fe_col(n, w->gmat + 9 * g1, 2);
+            fe_col(n, w->gmat() + 9 * g1, 2);
             hit = v3dot(t, n) <= m->geom_rbound[g2];
           } else {
             const float bnd = m->geom_rbound[g1] + m->geom_rbound[g2];
@@ -584,13 +611,13 @@ FE_FN void fe_collide(FeWarp* w) {
 #endif
       int off = FE_SCAN(run, n);
       for (int k = k0; k < k1; ++k)
-        if ((hits >> (k - k0)) & 1ull) { if (off < FE_MAXCAND) w->cand[off] = k; ++off; }
-      if (lane == 31) w->iscr[0] = off;
+        if ((hits >> (k - k0)) & 1ull) { if (off < FE_MAXCAND) w->cand()[off] = k; ++off; }
+      if (lane == 31) w->iscr()[0] = off;
     LANES_END
-    ncand = w->iscr[0];
+    ncand = w->iscr()[0];
     LANES_BEGIN LANES_END
   }
-  if (ncand > FE_MAXCAND) { ncand = FE_MAXCAND; LANES_BEGIN if (lane == 0) w->u[2] |= 1; LANES_END }
+  if (ncand > FE_MAXCAND) { ncand = FE_MAXCAND; LANES_BEGIN if (lane == 0) w->u()[2] |= 1; LANES_END }
   int ncon = 0;
   for (int base = 0; base < ncand; base += 32) {
     int run = 0;
@@ -600,42 +627,42 @@ FE_FN void fe_collide(FeWarp* w) {
       FeCon res[8];
       int n = 0, g1 = 0, g2 = 0;
       if (ci < ncand) {
-        const int k = w->cand[ci];
+        const int k = w->cand()[ci];
         g1 = m->pair_g1[k]; g2 = m->pair_g2[k];
-        n = fe_narrowphase(m->geom_type[g1], w->gpos + 3 * g1, w->gmat + 9 * g1, m->geom_size[g1], m->geom_type[g2], w->gpos + 3 * g2, w->gmat + 9 * g2,
+        n = fe_narrowphase(m->geom_type[g1], w->gpos() + 3 * g1, w->gmat() + 9 * g1, m->geom_size[g1], m->geom_type[g2], w->gpos() + 3 * g2, w->gmat() + 9 * g2,
                            m->geom_size[g2], res);
       }
       const int off = FE_SCAN(run, n);
       for (int i = 0; i < n; ++i) {
         const int c = ncon + off + i;
         if (c < mc) {
-          w->c_dist[c] = res[i].dist;
-          v3cpy(w->c_pos + 3 * c, res[i].pos);
-          v3cpy(w->c_frame + 9 * c, res[i].n);
-          w->c_geom[c] = g1 | (g2 << 8);
+          w->c_dist()[c] = res[i].dist;
+          v3cpy(w->c_pos() + 3 * c, res[i].pos);
+          v3cpy(w->c_frame() + 9 * c, res[i].n);
+          w->c_geom()[c] = g1 | (g2 << 8);
         }
       }
-      if (lane == 31) w->iscr[0] = off + n;
+      if (lane == 31) w->iscr()[0] = off + n;
     LANES_END
-    ncon += w->iscr[0];
+    ncon += w->iscr()[0];
     LANES_BEGIN LANES_END
   }
-  if (ncon > mc) { ncon = mc; LANES_BEGIN if (lane == 0) w->u[2] |= 1; LANES_END }
+  if (ncon > mc) { ncon = mc; LANES_BEGIN if (lane == 0) w->u()[2] |= 1; LANES_END }
   // touch flags per part: bit0 left finger, bit1 right finger, bit2 floor (furniture.py:500-520, :1290-1322)
   LANES_BEGIN
     const int p = lane;
     if (p < m->npart) {
       int bits = 0;
       for (int c = 0; c < ncon; ++c) {
-        const int g1 = w->c_geom[c] & 255, g2 = w->c_geom[c] >> 8;
+        const int g1 = w->c_geom()[c] & 255, g2 = w->c_geom()[c] >> 8;
         const int t1 = m->geom_tag[g1], t2 = m->geom_tag[g2];
         const int p1 = ((t1 >> FE_TAG_PART_SHIFT) & 0xff) - 1, p2 = ((t2 >> FE_TAG_PART_SHIFT) & 0xff) - 1;
         if (p1 == p) bits |= ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0) | ((t2 & FE_TAG_FLOOR) ? 4 : 0);
         if (p2 == p) bits |= ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0) | ((t1 & FE_TAG_FLOOR) ? 4 : 0);
       }
-      w->touch[p] = bits;
+      w->touch()[p] = bits;
     }
-    if (lane == 0) { w->u[0] = ncon; w->u[1] = ncand; }
+    if (lane == 0) { w->u()[0] = ncon; w->u()[1] = ncand; }
   LANES_END
   (void)nrl;
 }
@@ -660,7 +687,7 @@ FE_HD void fe_kb(const float* solref, float dmax_in, float h, float* k, float* b
 // reference point of a link (world)
 FE_HD void fe_link_ref(const FeWarp* w, int l, float* P) {
   if (l < w->m->nrlink) { P[0] = w->m->robot_ref[0]; P[1] = w->m->robot_ref[1]; P[2] = w->m->robot_ref[2]; }
-  else v3cpy(P, w->lpos + 3 * l);
+  else v3cpy(P, w->lpos() + 3 * l);
 }
 // velocity-like quantity of the point p fixed to link l, from per-link spatial vectors X (6*nlink): X.v + X.w x (p - P)
 FE_HD void fe_point_vel(const FeWarp* w, const float* X, int l, const float* p, float* out) {
@@ -685,20 +712,20 @@ FE_HD void fe_make_frame(float* F) {
 
 FE_FN void fe_assemble(FeWarp* w) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], nr = m->nr, ne = m->neq;
+  const int ncon = w->u()[0], nr = m->nr, ne = m->neq;
   const float h = m->timestep;
   LANES_BEGIN
     for (int c = lane; c < ncon; c += 32) {
-      const int g1 = w->c_geom[c] & 255, g2 = w->c_geom[c] >> 8;
+      const int g1 = w->c_geom()[c] & 255, g2 = w->c_geom()[c] >> 8;
       const int A = m->geom_link[g1], B = m->geom_link[g2];
-      w->c_link[c] = (A + 1) | ((B + 1) << 8);
+      w->c_link()[c] = (A + 1) | ((B + 1) << 8);
       { // 0: one free part against the static world; 1: robot only; 2: couples two moving blocks
         const int nrl_ = m->nrlink;
         const bool pa = A >= nrl_, pb = B >= nrl_, ra = A >= 0 && A < nrl_, rb = B >= 0 && B < nrl_;
-        w->c_kind[c] = ((pa && B < 0) || (pb && A < 0)) ? 0 : ((pa || pb) ? 2 : 1);
+        w->c_kind()[c] = ((pa && B < 0) || (pb && A < 0)) ? 0 : ((pa || pb) ? 2 : 1);
         (void)ra; (void)rb;
       }
-      float* F = w->c_frame + 9 * c;
+      float* F = w->c_frame() + 9 * c;
       fe_make_frame(F);
       const float fric = fmaxf(fmaxf(m->geom_friction[g1], m->geom_friction[g2]), 1e-5f);
       float sr[2], si[3];
@@ -706,37 +733,37 @@ FE_FN void fe_assemble(FeWarp* w) {
       if (s1[0] > 0.f && s2[0] > 0.f) { sr[0] = 0.5f * (s1[0] + s2[0]); sr[1] = 0.5f * (s1[1] + s2[1]); }
       else { sr[0] = fminf(s1[0], s2[0]); sr[1] = fminf(s1[1], s2[1]); }
       for (int k = 0; k < 3; ++k) si[k] = 0.5f * (m->geom_solimp[g1][k] + m->geom_solimp[g2][k]);
-      const float dist = w->c_dist[c];
+      const float dist = w->c_dist()[c];
       const float imp = fe_impedance(si, fabsf(dist));
       float kk, bb;
       fe_kb(sr, si[1], h, &kk, &bb);
       const float diag = fmaxf(m->geom_invweight[g1] + m->geom_invweight[g2], FE_MINVAL);
       const float R0 = fmaxf((1.f - imp) / imp * diag, FE_MINVAL);
       const float R1 = fmaxf(R0 / m->impratio, FE_MINVAL);
-      w->c_D[2 * c] = 1.f / R0;
-      w->c_D[2 * c + 1] = 1.f / R1;
-      w->c_mu[c] = fric * sqrtf(R1 / R0);
-      w->c_fric[c] = fric;
+      w->c_D()[2 * c] = 1.f / R0;
+      w->c_D()[2 * c + 1] = 1.f / R1;
+      w->c_mu()[c] = fric * sqrtf(R1 / R0);
+      w->c_fric()[c] = fric;
       float vA[3], vB[3], dv[3];
-      fe_point_vel(w, w->lvel, A, w->c_pos + 3 * c, vA);
-      fe_point_vel(w, w->lvel, B, w->c_pos + 3 * c, vB);
+      fe_point_vel(w, w->lvel(), A, w->c_pos() + 3 * c, vA);
+      fe_point_vel(w, w->lvel(), B, w->c_pos() + 3 * c, vB);
       v3sub(dv, vB, vA);
-      w->c_aref[3 * c] = -bb * v3dot(F, dv) - kk * imp * dist;
-      w->c_aref[3 * c + 1] = -bb * v3dot(F + 3, dv);
-      w->c_aref[3 * c + 2] = -bb * v3dot(F + 6, dv);
+      w->c_aref()[3 * c] = -bb * v3dot(F, dv) - kk * imp * dist;
+      w->c_aref()[3 * c + 1] = -bb * v3dot(F + 3, dv);
+      w->c_aref()[3 * c + 2] = -bb * v3dot(F + 6, dv);
     }
     // weld rows
     for (int e = lane; e < ne; e += 32) {
-      if (!w->eq_active[e]) continue;
+      if (!w->eq_active()[e]) continue;
       const int A = m->eq_link1[e], B = m->eq_link2[e];
-      const float* data = w->eq_data + 7 * e;
+      const float* data = w->eq_data() + 7 * e;
       float r1[3], p1[3], err[6];
-      m3mulv(r1, w->lmat + 9 * A, data);
-      v3add(p1, w->lpos + 3 * A, r1);
-      v3sub(err, p1, w->lpos + 3 * B);
+      m3mulv(r1, w->lmat() + 9 * A, data);
+      v3add(p1, w->lpos() + 3 * A, r1);
+      v3sub(err, p1, w->lpos() + 3 * B);
       float quat[4], qc[4], qe[4];
-      qmul(quat, w->lquat + 4 * A, data + 3);
-      qc[0] = w->lquat[4 * B]; qc[1] = -w->lquat[4 * B + 1]; qc[2] = -w->lquat[4 * B + 2]; qc[3] = -w->lquat[4 * B + 3];
+      qmul(quat, w->lquat() + 4 * A, data + 3);
+      qc[0] = w->lquat()[4 * B]; qc[1] = -w->lquat()[4 * B + 1]; qc[2] = -w->lquat()[4 * B + 2]; qc[3] = -w->lquat()[4 * B + 3];
       qmul(qe, qc, quat);
       err[3] = qe[1]; err[4] = qe[2]; err[5] = qe[3];
       float G[9];
@@ -746,9 +773,9 @@ FE_FN void fe_assemble(FeWarp* w) {
         qmul(t2, t1, quat);
         G[0 + j] = 0.5f * t2[1]; G[3 + j] = 0.5f * t2[2]; G[6 + j] = 0.5f * t2[3];
       }
-      v3cpy(w->w_r1 + 3 * e, r1);
-      for (int k = 0; k < 9; ++k) w->w_G[9 * e + k] = G[k];
-      const float *VA = w->lvel + 6 * A, *VB = w->lvel + 6 * B;
+      v3cpy(w->w_r1() + 3 * e, r1);
+      for (int k = 0; k < 9; ++k) w->w_G()[9 * e + k] = G[k];
+      const float *VA = w->lvel() + 6 * A, *VB = w->lvel() + 6 * B;
       float vel[6], t[3], dw[3];
       v3cross(t, VA, r1);
       for (int k = 0; k < 3; ++k) vel[k] = VA[3 + k] + t[k] - VB[3 + k];
@@ -760,27 +787,27 @@ FE_FN void fe_assemble(FeWarp* w) {
         const float imp = fe_impedance(m->eq_solimp[e], fabsf(err[k]));
         const float diag = fmaxf(k < 3 ? m->eq_invw_t[e] : m->eq_invw_r[e], FE_MINVAL);
         const float R = fmaxf((1.f - imp) / imp * diag, FE_MINVAL);
-        w->w_D[6 * e + k] = 1.f / R;
-        w->w_aref[6 * e + k] = -bb * vel[k] - kk * imp * err[k];
+        w->w_D()[6 * e + k] = 1.f / R;
+        w->w_aref()[6 * e + k] = -bb * vel[k] - kk * imp * err[k];
       }
     }
     // joint limits
     for (int d = lane; d < nr; d += 32) {
       float sgn = 0.f, dist = 0.f;
       if (m->rdof_limited[d]) {
-        const float q = w->qpos[d];
+        const float q = w->qpos()[d];
         if (q - m->rdof_range[d][0] < 0.f) { sgn = 1.f; dist = q - m->rdof_range[d][0]; }
         else if (m->rdof_range[d][1] - q < 0.f) { sgn = -1.f; dist = m->rdof_range[d][1] - q; }
       }
-      w->l_sign[d] = sgn;
+      w->l_sign()[d] = sgn;
       if (sgn != 0.f) {
         const float imp = fe_impedance(m->rdof_solimp[d], fabsf(dist));
         float kk, bb;
         fe_kb(m->rdof_solref[d], m->rdof_solimp[d][1], h, &kk, &bb);
         const float R = fmaxf((1.f - imp) / imp * fmaxf(m->rdof_invweight[d], FE_MINVAL), FE_MINVAL);
-        w->l_D[d] = 1.f / R;
-        w->l_aref[d] = -bb * sgn * w->qvel[d] - kk * imp * dist;
-      } else { w->l_D[d] = 0.f; w->l_aref[d] = 0.f; }
+        w->l_D()[d] = 1.f / R;
+        w->l_aref()[d] = -bb * sgn * w->qvel()[d] - kk * imp * dist;
+      } else { w->l_D()[d] = 0.f; w->l_aref()[d] = 0.f; }
     }
   LANES_END
 }
@@ -793,16 +820,16 @@ FE_FN void fe_mul_M(FeWarp* w, const float* in, float* out) {
   LANES_BEGIN
     for (int d = lane; d < nr; d += 32) {
       float s = 0.f;
-      for (int j = 0; j < nr; ++j) s += w->Mr[d * nr + j] * in[j];
+      for (int j = 0; j < nr; ++j) s += w->Mr()[d * nr + j] * in[j];
       out[d] = s;
     }
-    for (int p = lane; p < np; p += 32) inert_mulv(out + nr + 6 * p, w->linert + 10 * (nrl + p), in + nr + 6 * p);
+    for (int p = lane; p < np; p += 32) inert_mulv(out + nr + 6 * p, w->linert() + 10 * (nrl + p), in + nr + 6 * p);
   LANES_END
 }
 // rows = J_z in  (contacts -> cout[3*c..], welds -> wout[6*e..], limits -> lout[d]); `sub_aref` subtracts aref
 FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float* lout, bool sub_aref) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, nl = w->fast ? m->nrlink : m->nlink, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const int nr = m->nr, nrl = m->nrlink, nl = w->fast ? m->nrlink : m->nlink, ncon = w->u()[0], ne = w->fast ? 0 : m->neq;
   const bool fast = w->fast != 0;
   LANES_BEGIN
     const int l = lane;
@@ -811,46 +838,46 @@ FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float*
       if (l < nrl) {
         const int mask = m->link_ancmask[l];
         for (int d = 0; d < nr; ++d)
-          if ((mask >> d) & 1) { const float xd = in[d]; for (int k = 0; k < 6; ++k) X[k] += w->S[6 * d + k] * xd; }
+          if ((mask >> d) & 1) { const float xd = in[d]; for (int k = 0; k < 6; ++k) X[k] += w->S()[6 * d + k] * xd; }
       } else for (int k = 0; k < 6; ++k) X[k] = in[nr + 6 * (l - nrl) + k];
-      for (int k = 0; k < 6; ++k) w->lacc2[6 * l + k] = X[k];
+      for (int k = 0; k < 6; ++k) w->lacc2()[6 * l + k] = X[k];
     }
   LANES_END
   LANES_BEGIN
     for (int c = lane; c < ncon; c += 32) {
-      if (fast && w->c_kind[c] == 0) continue;
-      const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+      if (fast && w->c_kind()[c] == 0) continue;
+      const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
       float aA[3], aB[3], da[3];
-      fe_point_vel(w, w->lacc2, A, w->c_pos + 3 * c, aA);
-      fe_point_vel(w, w->lacc2, B, w->c_pos + 3 * c, aB);
+      fe_point_vel(w, w->lacc2(), A, w->c_pos() + 3 * c, aA);
+      fe_point_vel(w, w->lacc2(), B, w->c_pos() + 3 * c, aB);
       v3sub(da, aB, aA);
-      const float* F = w->c_frame + 9 * c;
-      for (int k = 0; k < 3; ++k) cout[3 * c + k] = v3dot(F + 3 * k, da) - (sub_aref ? w->c_aref[3 * c + k] : 0.f);
+      const float* F = w->c_frame() + 9 * c;
+      for (int k = 0; k < 3; ++k) cout[3 * c + k] = v3dot(F + 3 * k, da) - (sub_aref ? w->c_aref()[3 * c + k] : 0.f);
     }
     for (int e = lane; e < ne; e += 32) {
-      if (!w->eq_active[e]) continue;
-      const float *XA = w->lacc2 + 6 * m->eq_link1[e], *XB = w->lacc2 + 6 * m->eq_link2[e];
+      if (!w->eq_active()[e]) continue;
+      const float *XA = w->lacc2() + 6 * m->eq_link1[e], *XB = w->lacc2() + 6 * m->eq_link2[e];
       float t[3], dw[3], r[6];
-      v3cross(t, XA, w->w_r1 + 3 * e);
+      v3cross(t, XA, w->w_r1() + 3 * e);
       for (int k = 0; k < 3; ++k) r[k] = XA[3 + k] + t[k] - XB[3 + k];
       v3sub(dw, XA, XB);
-      m3mulv(r + 3, w->w_G + 9 * e, dw);
-      for (int k = 0; k < 6; ++k) wout[6 * e + k] = r[k] - (sub_aref ? w->w_aref[6 * e + k] : 0.f);
+      m3mulv(r + 3, w->w_G() + 9 * e, dw);
+      for (int k = 0; k < 6; ++k) wout[6 * e + k] = r[k] - (sub_aref ? w->w_aref()[6 * e + k] : 0.f);
     }
-    for (int d = lane; d < nr; d += 32) lout[d] = w->l_sign[d] * in[d] - (sub_aref ? w->l_aref[d] : 0.f);
+    for (int d = lane; d < nr; d += 32) lout[d] = w->l_sign()[d] * in[d] - (sub_aref ? w->l_aref()[d] : 0.f);
   LANES_END
 }
 // constraint forces/states from jar; returns the constraint cost
 FE_FN float fe_update(FeWarp* w) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], ne = w->fast ? 0 : m->neq, nr = m->nr;
+  const int ncon = w->u()[0], ne = w->fast ? 0 : m->neq, nr = m->nr;
   const bool fast = w->fast != 0;
   LANES_BEGIN
     float cost = 0.f;
     for (int c = lane; c < ncon; c += 32) {
-      if (fast && w->c_kind[c] == 0) continue;
-      const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
-      const float j0 = w->c_jar[3 * c], j1 = w->c_jar[3 * c + 1], j2 = w->c_jar[3 * c + 2];
+      if (fast && w->c_kind()[c] == 0) continue;
+      const float mu = w->c_mu()[c], fr = w->c_fric()[c], D0 = w->c_D()[2 * c], D1 = w->c_D()[2 * c + 1];
+      const float j0 = w->c_jar()[3 * c], j1 = w->c_jar()[3 * c + 1], j2 = w->c_jar()[3 * c + 2];
       const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
       float f0 = 0.f, f1 = 0.f, f2 = 0.f;
       int st = 0;
@@ -867,30 +894,30 @@ FE_FN float fe_update(FeWarp* w) {
         f1 = -f0 / T * U1 * fr;
         f2 = -f0 / T * U2 * fr;
       }
-      w->c_f[3 * c] = f0; w->c_f[3 * c + 1] = f1; w->c_f[3 * c + 2] = f2;
-      w->c_state[c] = st;
+      w->c_f()[3 * c] = f0; w->c_f()[3 * c + 1] = f1; w->c_f()[3 * c + 2] = f2;
+      w->c_state()[c] = st;
     }
     for (int e = lane; e < ne; e += 32) {
-      if (!w->eq_active[e]) continue;
+      if (!w->eq_active()[e]) continue;
       for (int k = 0; k < 6; ++k) {
-        const float D = w->w_D[6 * e + k], j = w->w_jar[6 * e + k];
-        w->w_f[6 * e + k] = -D * j;
+        const float D = w->w_D()[6 * e + k], j = w->w_jar()[6 * e + k];
+        w->w_f()[6 * e + k] = -D * j;
         cost += 0.5f * D * j * j;
       }
     }
     for (int d = lane; d < nr; d += 32) {
       float f = 0.f;
-      if (w->l_sign[d] != 0.f && w->l_jar[d] < 0.f) { f = -w->l_D[d] * w->l_jar[d]; cost += 0.5f * w->l_D[d] * w->l_jar[d] * w->l_jar[d]; }
-      w->l_f[d] = f;
+      if (w->l_sign()[d] != 0.f && w->l_jar()[d] < 0.f) { f = -w->l_D()[d] * w->l_jar()[d]; cost += 0.5f * w->l_D()[d] * w->l_jar()[d] * w->l_jar()[d]; }
+      w->l_f()[d] = f;
     }
-    w->scr[lane] = cost;
+    w->scr()[lane] = cost;
   LANES_END
-  return fe_sum32(w->scr);
+  return fe_sum32(w->scr());
 }
 // out = J_z^T force
 FE_FN void fe_mul_JT(FeWarp* w, float* out) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, nl = w->fast ? m->nrlink : m->nlink, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const int nr = m->nr, nrl = m->nrlink, nl = w->fast ? m->nrlink : m->nlink, ncon = w->u()[0], ne = w->fast ? 0 : m->neq;
   const bool fast = w->fast != 0;
   LANES_BEGIN
     const int l = lane;
@@ -898,43 +925,43 @@ FE_FN void fe_mul_JT(FeWarp* w, float* out) {
       float P[3], Wr[6] = {0, 0, 0, 0, 0, 0};
       fe_link_ref(w, l, P);
       for (int c = 0; c < ncon; ++c) {
-        if (fast && w->c_kind[c] == 0) continue;
-        if (w->c_state[c] == 0) continue;
-        const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+        if (fast && w->c_kind()[c] == 0) continue;
+        if (w->c_state()[c] == 0) continue;
+        const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
         if (A != l && B != l) continue;
         const float sg = (B == l ? 1.f : 0.f) - (A == l ? 1.f : 0.f);
         if (sg == 0.f) continue;
-        const float* F = w->c_frame + 9 * c;
-        const float *f = w->c_f + 3 * c;
+        const float* F = w->c_frame() + 9 * c;
+        const float *f = w->c_f() + 3 * c;
         float fw[3] = {F[0] * f[0] + F[3] * f[1] + F[6] * f[2], F[1] * f[0] + F[4] * f[1] + F[7] * f[2], F[2] * f[0] + F[5] * f[1] + F[8] * f[2]};
         float r[3], t[3];
-        v3sub(r, w->c_pos + 3 * c, P);
+        v3sub(r, w->c_pos() + 3 * c, P);
         v3cross(t, r, fw);
         Wr[0] += sg * t[0]; Wr[1] += sg * t[1]; Wr[2] += sg * t[2]; Wr[3] += sg * fw[0]; Wr[4] += sg * fw[1]; Wr[5] += sg * fw[2];
       }
       for (int e = 0; e < ne; ++e) {
-        if (!w->eq_active[e]) continue;
+        if (!w->eq_active()[e]) continue;
         const int A = m->eq_link1[e], B = m->eq_link2[e];
         if (A != l && B != l) continue;
-        const float* f = w->w_f + 6 * e;
+        const float* f = w->w_f() + 6 * e;
         float tq[3], t[3];
-        m3tmulv(tq, w->w_G + 9 * e, f + 3); // G^T f_rot
+        m3tmulv(tq, w->w_G() + 9 * e, f + 3); // G^T f_rot
         if (A == l) {
-          v3cross(t, w->w_r1 + 3 * e, f);
+          v3cross(t, w->w_r1() + 3 * e, f);
           Wr[0] += t[0] + tq[0]; Wr[1] += t[1] + tq[1]; Wr[2] += t[2] + tq[2]; Wr[3] += f[0]; Wr[4] += f[1]; Wr[5] += f[2];
         } else {
           Wr[0] -= tq[0]; Wr[1] -= tq[1]; Wr[2] -= tq[2]; Wr[3] -= f[0]; Wr[4] -= f[1]; Wr[5] -= f[2];
         }
       }
-      for (int k = 0; k < 6; ++k) w->lacc2[6 * l + k] = Wr[k];
+      for (int k = 0; k < 6; ++k) w->lacc2()[6 * l + k] = Wr[k];
       if (l >= nrl) for (int k = 0; k < 6; ++k) out[nr + 6 * (l - nrl) + k] = Wr[k];
     }
   LANES_END
   LANES_BEGIN
     for (int d = lane; d < nr; d += 32) {
-      float s = w->l_sign[d] * w->l_f[d];
+      float s = w->l_sign()[d] * w->l_f()[d];
       for (int l = d; l < nrl; ++l)
-        if ((m->link_ancmask[l] >> d) & 1) s += dot6(w->S + 6 * d, w->lacc2 + 6 * l);
+        if ((m->link_ancmask[l] >> d) & 1) s += dot6(w->S() + 6 * d, w->lacc2() + 6 * l);
       out[d] = s;
     }
   LANES_END
@@ -943,15 +970,15 @@ FE_FN void fe_mul_JT(FeWarp* w, float* out) {
 // one 1-D cost evaluation along the search direction: returns p'(alpha), p''(alpha) (uniform)
 FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, float* d2) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], ne = w->fast ? 0 : m->neq, nr = m->nr;
+  const int ncon = w->u()[0], ne = w->fast ? 0 : m->neq, nr = m->nr;
   const bool fast = w->fast != 0;
   LANES_BEGIN
     float p1 = 0.f, p2 = 0.f;
     for (int c = lane; c < ncon; c += 32) {
-      if (fast && w->c_kind[c] == 0) continue;
-      const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
-      const float v0 = w->c_jv[3 * c], v1 = w->c_jv[3 * c + 1], v2 = w->c_jv[3 * c + 2];
-      const float x0 = w->c_jar[3 * c] + alpha * v0, x1 = w->c_jar[3 * c + 1] + alpha * v1, x2 = w->c_jar[3 * c + 2] + alpha * v2;
+      if (fast && w->c_kind()[c] == 0) continue;
+      const float mu = w->c_mu()[c], fr = w->c_fric()[c], D0 = w->c_D()[2 * c], D1 = w->c_D()[2 * c + 1];
+      const float v0 = w->c_jv()[3 * c], v1 = w->c_jv()[3 * c + 1], v2 = w->c_jv()[3 * c + 2];
+      const float x0 = w->c_jar()[3 * c] + alpha * v0, x1 = w->c_jar()[3 * c + 1] + alpha * v1, x2 = w->c_jar()[3 * c + 2] + alpha * v2;
       const float N = x0 * mu, U1 = x1 * fr, U2 = x2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
       if (N >= mu * T || (T <= 0.f && N >= 0.f)) {
       } else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
@@ -966,21 +993,21 @@ FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, f
       }
     }
     for (int e = lane; e < ne; e += 32) {
-      if (!w->eq_active[e]) continue;
+      if (!w->eq_active()[e]) continue;
       for (int k = 0; k < 6; ++k) {
-        const float D = w->w_D[6 * e + k], v = w->w_jv[6 * e + k], x = w->w_jar[6 * e + k] + alpha * v;
+        const float D = w->w_D()[6 * e + k], v = w->w_jv()[6 * e + k], x = w->w_jar()[6 * e + k] + alpha * v;
         p1 += D * x * v; p2 += D * v * v;
       }
     }
     for (int d = lane; d < nr; d += 32) {
-      if (w->l_sign[d] == 0.f) continue;
-      const float v = w->l_jv[d], x = w->l_jar[d] + alpha * v;
-      if (x < 0.f) { p1 += w->l_D[d] * x * v; p2 += w->l_D[d] * v * v; }
+      if (w->l_sign()[d] == 0.f) continue;
+      const float v = w->l_jv()[d], x = w->l_jar()[d] + alpha * v;
+      if (x < 0.f) { p1 += w->l_D()[d] * x * v; p2 += w->l_D()[d] * v * v; }
     }
-    w->scr[lane] = p1; w->scr[32 + lane] = p2;
+    w->scr()[lane] = p1; w->scr()[32 + lane] = p2;
   LANES_END
-  *d1 = fe_sum32(w->scr) + g1 + 2.f * alpha * g2;
-  *d2 = fe_sum32(w->scr + 32) + 2.f * g2;
+  *d1 = fe_sum32(w->scr()) + g1 + 2.f * alpha * g2;
+  *d2 = fe_sum32(w->scr() + 32) + 2.f * g2;
 }
 
 // zone logic of one elliptic contact: forces f, cost, and (if W) the 3x3 weight (xx yy zz xy xz yz); returns state
@@ -1008,9 +1035,9 @@ FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, f
 }
 // rows of one part-vs-world contact in the part's coordinates: J[k] = sgn * [(r x F_k), F_k], r = pos - origin
 FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
-  const float* F = w->c_frame + 9 * c;
+  const float* F = w->c_frame() + 9 * c;
   float r[3];
-  v3sub(r, w->c_pos + 3 * c, w->lpos + 3 * l);
+  v3sub(r, w->c_pos() + 3 * c, w->lpos() + 3 * l);
   for (int k = 0; k < 3; ++k) {
     float t[3];
     v3cross(t, r, F + 3 * k);
@@ -1022,17 +1049,17 @@ FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
 // H = M_z + J^T W J  (packed lower, skyline first[])
 FE_FN void fe_build_H(FeWarp* w) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u()[0], ne = w->fast ? 0 : m->neq;
   const bool fast = w->fast != 0;
   // envelope: a part row starts at its own block unless it is coupled to the robot or to a lower part
   LANES_BEGIN
-    for (int d = lane; d < nr; d += 32) w->first[d] = 0;
+    for (int d = lane; d < nr; d += 32) w->first()[d] = 0;
     for (int p = lane; p < np; p += 32) {
       const int l = nrl + p;
       int f = nr + 6 * p;
       for (int c = 0; c < ncon; ++c) {
-        if (w->c_state[c] == 0) continue;
-        const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+        if (w->c_state()[c] == 0) continue;
+        const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
         int o = -2;
         if (A == l) o = B; else if (B == l) o = A;
         if (o < 0) continue;
@@ -1040,7 +1067,7 @@ FE_FN void fe_build_H(FeWarp* w) {
         if (fo < f) f = fo;
       }
       for (int e = 0; e < ne; ++e) {
-        if (!w->eq_active[e]) continue;
+        if (!w->eq_active()[e]) continue;
         const int A = m->eq_link1[e], B = m->eq_link2[e];
         int o = -1;
         if (A == l) o = B; else if (B == l) o = A;
@@ -1048,19 +1075,19 @@ FE_FN void fe_build_H(FeWarp* w) {
         const int fo = nr + 6 * (o - nrl);
         if (fo < f) f = fo;
       }
-      for (int k = 0; k < 6; ++k) w->first[nr + 6 * p + k] = f;
+      for (int k = 0; k < 6; ++k) w->first()[nr + 6 * p + k] = f;
     }
   LANES_END
   // M_z inside the envelope
   LANES_BEGIN
     for (int i = lane; i < nv; i += 32) {
-      float* Hi = w->H + fe_tri(i);
-      for (int j = w->first[i]; j <= i; ++j) Hi[j] = 0.f;
-      if (i < nr) { for (int j = 0; j <= i; ++j) Hi[j] = w->Mr[i * nr + j]; if (w->l_sign[i] != 0.f && w->l_jar[i] < 0.f) Hi[i] += w->l_D[i]; }
+      float* Hi = w->H() + fe_tri(i);
+      for (int j = w->first()[i]; j <= i; ++j) Hi[j] = 0.f;
+      if (i < nr) { for (int j = 0; j <= i; ++j) Hi[j] = w->Mr()[i * nr + j]; if (w->l_sign()[i] != 0.f && w->l_jar()[i] < 0.f) Hi[i] += w->l_D()[i]; }
       else {
         const int p = (i - nr) / 6, r = (i - nr) % 6;
         float A[21];
-        fe_inert_sym6(A, w->linert + 10 * (nrl + p), 0.f);
+        fe_inert_sym6(A, w->linert() + 10 * (nrl + p), 0.f);
         for (int c = 0; c <= r; ++c) Hi[nr + 6 * p + c] = A[fe_tri(r) + c];
       }
     }
@@ -1068,20 +1095,20 @@ FE_FN void fe_build_H(FeWarp* w) {
   // FULL scope: contacts of a free part against the static world only touch that part's 6x6 diagonal block; they are
   // accumulated 8 lanes per part (lane = contact) with group reductions, like the FAST solver does
   bool grouped = !fast;
-  for (int p = 0; p < m->npart; ++p) if (w->plist[9 * p + 8] > 8) grouped = false;
+  for (int p = 0; p < m->npart; ++p) if (w->plist()[9 * p + 8] > 8) grouped = false;
   if (grouped) {
     for (int pass = 0; pass * 4 < m->npart; ++pass) {
       FE_PRIVA(float, hacc_, 21);
       LANES_BEGIN
         for (int k = 0; k < 21; ++k) PV(hacc_)[k] = 0.f;
         const int part = pass * 4 + (lane >> 3), slot = lane & 7;
-        if (part < m->npart && slot < w->plist[9 * part + 8]) {
-          const int c = w->plist[9 * part + slot];
-          if (w->c_state[c] != 0) {
-            const int l = nrl + part, B_ = (w->c_link[c] >> 8) - 1;
+        if (part < m->npart && slot < w->plist()[9 * part + 8]) {
+          const int c = w->plist()[9 * part + slot];
+          if (w->c_state()[c] != 0) {
+            const int l = nrl + part, B_ = (w->c_link()[c] >> 8) - 1;
             float J[18], f[3], W[6], dummy = 0.f, WJ[18];
             fe_part_rows(w, c, l, B_ == l ? 1.f : -1.f, J);
-            fe_cone(w->c_jar[3 * c], w->c_jar[3 * c + 1], w->c_jar[3 * c + 2], w->c_mu[c], w->c_fric[c], w->c_D[2 * c], w->c_D[2 * c + 1], f, &dummy, W);
+            fe_cone(w->c_jar()[3 * c], w->c_jar()[3 * c + 1], w->c_jar()[3 * c + 2], w->c_mu()[c], w->c_fric()[c], w->c_D()[2 * c], w->c_D()[2 * c + 1], f, &dummy, W);
             for (int i = 0; i < 6; ++i) {
               WJ[i] = W[0] * J[i] + W[3] * J[6 + i] + W[4] * J[12 + i];
               WJ[6 + i] = W[3] * J[i] + W[1] * J[6 + i] + W[5] * J[12 + i];
@@ -1095,28 +1122,28 @@ FE_FN void fe_build_H(FeWarp* w) {
       FE_GSUM8_ARR(hacc_, 21);
       LANES_BEGIN
         const int part = pass * 4 + (lane >> 3);
-        if (part < m->npart && (lane & 7) == 0 && w->plist[9 * part + 8] > 0) {
+        if (part < m->npart && (lane & 7) == 0 && w->plist()[9 * part + 8] > 0) {
           const int z = nr + 6 * part;
-          for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) w->H[fe_tri(z + i) + z + j] += PV(hacc_)[i * (i + 1) / 2 + j];
+          for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) w->H()[fe_tri(z + i) + z + j] += PV(hacc_)[i * (i + 1) / 2 + j];
         }
       LANES_END
     }
   }
   // remaining contacts, one at a time: dof-space rows staged in Jc (3 x ncols), then the ncols x ncols outer product
   for (int c = 0; c < ncon; ++c) {
-    const int st = w->c_state[c];
-    if (st == 0 || ((fast || grouped) && w->c_kind[c] == 0)) continue;
-    const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+    const int st = w->c_state()[c];
+    if (st == 0 || ((fast || grouped) && w->c_kind()[c] == 0)) continue;
+    const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
     const bool robot = (A >= 0 && A < nrl) || (B >= 0 && B < nrl);
     const int partA = A >= nrl ? A - nrl : -1, partB = B >= nrl ? B - nrl : -1;
     const int ncols = (robot ? nr : 0) + (partA >= 0 ? 6 : 0) + (partB >= 0 ? 6 : 0);
     // 3x3 weight: diag(D) in the quadratic zone, cone Hessian in the middle zone
     float W[9];
     {
-      const float mu = w->c_mu[c], fr = w->c_fric[c], D0 = w->c_D[2 * c], D1 = w->c_D[2 * c + 1];
+      const float mu = w->c_mu()[c], fr = w->c_fric()[c], D0 = w->c_D()[2 * c], D1 = w->c_D()[2 * c + 1];
       if (st == 1) { W[0] = D0; W[4] = D1; W[8] = D1; W[1] = W[2] = W[3] = W[5] = W[6] = W[7] = 0.f; }
       else {
-        const float N = w->c_jar[3 * c] * mu, U[3] = {N, w->c_jar[3 * c + 1] * fr, w->c_jar[3 * c + 2] * fr};
+        const float N = w->c_jar()[3 * c] * mu, U[3] = {N, w->c_jar()[3 * c + 1] * fr, w->c_jar()[3 * c + 2] * fr};
         const float T = sqrtf(U[1] * U[1] + U[2] * U[2]), Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
         const float sc[3] = {mu, fr, fr};
         float HU[9];
@@ -1130,8 +1157,8 @@ FE_FN void fe_build_H(FeWarp* w) {
     LANES_BEGIN
       const int j = lane;
       if (j < ncols) {
-        const float* F = w->c_frame + 9 * c;
-        const float* p = w->c_pos + 3 * c;
+        const float* F = w->c_frame() + 9 * c;
+        const float* p = w->c_pos() + 3 * c;
         float col[3] = {0.f, 0.f, 0.f};
         int z;
         int jj = j;
@@ -1141,8 +1168,8 @@ FE_FN void fe_build_H(FeWarp* w) {
           if (sg != 0.f) {
             float r[3], t[3], v[3];
             v3sub(r, p, m->robot_ref);
-            v3cross(t, w->S + 6 * jj, r);
-            v3add(v, w->S + 6 * jj + 3, t);
+            v3cross(t, w->S() + 6 * jj, r);
+            v3add(v, w->S() + 6 * jj + 3, t);
             for (int k = 0; k < 3; ++k) col[k] = sg * v3dot(F + 3 * k, v);
           }
         } else {
@@ -1151,14 +1178,14 @@ FE_FN void fe_build_H(FeWarp* w) {
           if (partA >= 0 && jj < 6) { part = partA; sg = -1.f; } else { if (partA >= 0) jj -= 6; part = partB; sg = 1.f; }
           z = nr + 6 * part + jj;
           float r[3];
-          v3sub(r, p, w->lpos + 3 * (nrl + part));
+          v3sub(r, p, w->lpos() + 3 * (nrl + part));
           for (int k = 0; k < 3; ++k) {
             if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * t[jj]; }
             else col[k] = sg * F[3 * k + (jj - 3)];
           }
         }
-        w->Jc[j] = col[0]; w->Jc[32 + j] = col[1]; w->Jc[64 + j] = col[2];
-        w->colmap[j] = z;
+        w->Jc()[j] = col[0]; w->Jc()[32 + j] = col[1]; w->Jc()[64 + j] = col[2];
+        w->colmap()[j] = z;
       }
     LANES_END
     LANES_BEGIN
@@ -1169,21 +1196,21 @@ FE_FN void fe_build_H(FeWarp* w) {
         const int j = e - fe_tri(i);
         float v = 0.f;
         for (int a = 0; a < 3; ++a) {
-          const float ja = w->Jc[32 * a + i];
+          const float ja = w->Jc()[32 * a + i];
           if (ja == 0.f) continue;
-          v += ja * (W[3 * a] * w->Jc[j] + W[3 * a + 1] * w->Jc[32 + j] + W[3 * a + 2] * w->Jc[64 + j]);
+          v += ja * (W[3 * a] * w->Jc()[j] + W[3 * a + 1] * w->Jc()[32 + j] + W[3 * a + 2] * w->Jc()[64 + j]);
         }
         if (v != 0.f) {
-          int zi = w->colmap[i], zj = w->colmap[j];
+          int zi = w->colmap()[i], zj = w->colmap()[j];
           if (zi < zj) { int t = zi; zi = zj; zj = t; }
-          w->H[fe_tri(zi) + zj] += v;
+          w->H()[fe_tri(zi) + zj] += v;
         }
       }
     LANES_END
   }
   // welds: 6 rows over the two parts' 12 columns, diagonal weights
   for (int e = 0; e < ne; ++e) {
-    if (!w->eq_active[e]) continue;
+    if (!w->eq_active()[e]) continue;
     const int A = m->eq_link1[e], B = m->eq_link2[e];
     for (int half = 0; half < 2; ++half) { // rows 0-2 (translation) then 3-5 (rotation), staged 3 at a time
       LANES_BEGIN
@@ -1196,16 +1223,16 @@ FE_FN void fe_build_H(FeWarp* w) {
             if (sideA) {
               if (jj < 3) { // d/dw_A of (w_A x r1)_k = (e_jj x r1)_k
                 float ej[3] = {jj == 0 ? 1.f : 0.f, jj == 1 ? 1.f : 0.f, jj == 2 ? 1.f : 0.f}, t[3];
-                v3cross(t, ej, w->w_r1 + 3 * e);
+                v3cross(t, ej, w->w_r1() + 3 * e);
                 col[0] = t[0]; col[1] = t[1]; col[2] = t[2];
               } else col[jj - 3] = 1.f;
             } else if (jj >= 3) col[jj - 3] = -1.f;
           } else if (jj < 3) {
             const float sg = sideA ? 1.f : -1.f;
-            for (int k = 0; k < 3; ++k) col[k] = sg * w->w_G[9 * e + 3 * k + jj];
+            for (int k = 0; k < 3; ++k) col[k] = sg * w->w_G()[9 * e + 3 * k + jj];
           }
-          w->Jc[j] = col[0]; w->Jc[32 + j] = col[1]; w->Jc[64 + j] = col[2];
-          w->colmap[j] = nr + 6 * ((sideA ? A : B) - nrl) + jj;
+          w->Jc()[j] = col[0]; w->Jc()[32 + j] = col[1]; w->Jc()[64 + j] = col[2];
+          w->colmap()[j] = nr + 6 * ((sideA ? A : B) - nrl) + jj;
         }
       LANES_END
       LANES_BEGIN
@@ -1215,11 +1242,11 @@ FE_FN void fe_build_H(FeWarp* w) {
           while (fe_tri(i) > en) --i;
           const int j = en - fe_tri(i);
           float v = 0.f;
-          for (int a = 0; a < 3; ++a) v += w->w_D[6 * e + 3 * half + a] * w->Jc[32 * a + i] * w->Jc[32 * a + j];
+          for (int a = 0; a < 3; ++a) v += w->w_D()[6 * e + 3 * half + a] * w->Jc()[32 * a + i] * w->Jc()[32 * a + j];
           if (v != 0.f) {
-            int zi = w->colmap[i], zj = w->colmap[j];
+            int zi = w->colmap()[i], zj = w->colmap()[j];
             if (zi < zj) { int t = zi; zi = zj; zj = t; }
-            w->H[fe_tri(zi) + zj] += v;
+            w->H()[fe_tri(zi) + zj] += v;
           }
         }
       LANES_END
@@ -1230,77 +1257,77 @@ FE_FN void fe_build_H(FeWarp* w) {
 // cooperative Newton solve over the active scope (w->nact dofs; in FAST scope the free parts are excluded)
 FE_FN void fe_solve_coop(FeWarp* w) {
   const fe_model* m = w->m;
-  const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u[0], ne = w->fast ? 0 : m->neq;
+  const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u()[0], ne = w->fast ? 0 : m->neq;
   const bool fast = w->fast != 0;
   // any constraint at all?
   LANES_BEGIN
     int any = 0;
-    for (int c = lane; c < ncon; c += 32) any |= !(fast && w->c_kind[c] == 0);
-    for (int e = lane; e < ne; e += 32) any |= w->eq_active[e] != 0;
-    for (int d = lane; d < nr; d += 32) any |= w->l_sign[d] != 0.f;
-    w->iscr[lane] = any;
-    for (int i = lane; i < nv; i += 32) w->fc[i] = 0.f;
+    for (int c = lane; c < ncon; c += 32) any |= !(fast && w->c_kind()[c] == 0);
+    for (int e = lane; e < ne; e += 32) any |= w->eq_active()[e] != 0;
+    for (int d = lane; d < nr; d += 32) any |= w->l_sign()[d] != 0.f;
+    w->iscr()[lane] = any;
+    for (int i = lane; i < nv; i += 32) w->fc()[i] = 0.f;
   LANES_END
-  if (fe_ballot32(w->iscr) == 0u) {
+  if (fe_ballot32(w->iscr()) == 0u) {
     LANES_BEGIN
-      for (int i = lane; i < nv; i += 32) w->x[i] = w->as[i];
+      for (int i = lane; i < nv; i += 32) w->x()[i] = w->as()[i];
     LANES_END
     return;
   }
-  LANES_BEGIN if (lane == 0) w->u[6] += 1; LANES_END
+  LANES_BEGIN if (lane == 0) w->u()[6] += 1; LANES_END
   const float scale = 1.0f / (m->meaninertia * (float)(m->nv > 1 ? m->nv : 1));
   // warm start candidate (stored in qacc coordinates) -> z coordinates; pick the cheaper of warm / smooth
   float best = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
     LANES_BEGIN
       if (pass == 0) {
-        for (int d = lane; d < nr; d += 32) w->x[d] = w->warm[d];
+        for (int d = lane; d < nr; d += 32) w->x()[d] = w->warm()[d];
         for (int p = lane; p < np; p += 32) {
           const int da = m->link_dadr[nrl + p], z = nr + 6 * p;
-          m3mulv(w->x + z, w->lmat + 9 * (nrl + p), w->warm + da + 3);
-          v3cpy(w->x + z + 3, w->warm + da);
+          m3mulv(w->x() + z, w->lmat() + 9 * (nrl + p), w->warm() + da + 3);
+          v3cpy(w->x() + z + 3, w->warm() + da);
         }
-      } else for (int i = lane; i < nv; i += 32) w->search[i] = w->as[i];
+      } else for (int i = lane; i < nv; i += 32) w->search()[i] = w->as()[i];
     LANES_END
-    float* cand = pass == 0 ? w->x : w->search;
-    fe_mul_M(w, cand, w->Ma);
-    fe_mul_J(w, cand, w->c_jar, w->w_jar, w->l_jar, true);
+    float* cand = pass == 0 ? w->x() : w->search();
+    fe_mul_M(w, cand, w->Ma());
+    fe_mul_J(w, cand, w->c_jar(), w->w_jar(), w->l_jar(), true);
     float cost = fe_update(w);
     LANES_BEGIN
       float s = 0.f;
-      for (int i = lane; i < nv; i += 32) s += 0.5f * (w->Ma[i] - w->fs[i]) * (cand[i] - w->as[i]);
-      w->scr[lane] = s;
+      for (int i = lane; i < nv; i += 32) s += 0.5f * (w->Ma()[i] - w->fs()[i]) * (cand[i] - w->as()[i]);
+      w->scr()[lane] = s;
     LANES_END
-    cost += fe_sum32(w->scr);
+    cost += fe_sum32(w->scr());
     if (pass == 0) best = cost;
-    else if (cost < best || !(best == best)) { LANES_BEGIN for (int i = lane; i < nv; i += 32) w->x[i] = w->as[i]; LANES_END }
+    else if (cost < best || !(best == best)) { LANES_BEGIN for (int i = lane; i < nv; i += 32) w->x()[i] = w->as()[i]; LANES_END }
     else { // keep the warm start: recompute its products
-      fe_mul_M(w, w->x, w->Ma);
-      fe_mul_J(w, w->x, w->c_jar, w->w_jar, w->l_jar, true);
+      fe_mul_M(w, w->x(), w->Ma());
+      fe_mul_J(w, w->x(), w->c_jar(), w->w_jar(), w->l_jar(), true);
     }
   }
   int iter = 0;
   float cost = 0.f, impr = 0.f;
   for (;;) {
     const float ccost = fe_update(w);
-    fe_mul_JT(w, w->fc);
+    fe_mul_JT(w, w->fc());
     LANES_BEGIN
       float s = 0.f, gsq = 0.f;
       for (int i = lane; i < nv; i += 32) {
-        const float r = w->Ma[i] - w->fs[i];
-        s += 0.5f * r * (w->x[i] - w->as[i]);
-        const float gi = r - w->fc[i];
-        w->grad[i] = gi;
+        const float r = w->Ma()[i] - w->fs()[i];
+        s += 0.5f * r * (w->x()[i] - w->as()[i]);
+        const float gi = r - w->fc()[i];
+        w->grad()[i] = gi;
         gsq += gi * gi;
       }
-      w->scr[lane] = s; w->scr[32 + lane] = gsq;
+      w->scr()[lane] = s; w->scr()[32 + lane] = gsq;
     LANES_END
-    const float gauss = fe_sum32(w->scr), gnorm = sqrtf(fe_sum32(w->scr + 32));
+    const float gauss = fe_sum32(w->scr()), gnorm = sqrtf(fe_sum32(w->scr() + 32));
     cost = gauss + ccost;
 #if !FE_DEVICE_BUILD
     if (getenv("FE_DEBUG_SOLVE")) printf("  coop it %d nact %d cost %.9g gnorm %.4g scaled-g %.3g impr %.3g\n", iter, nv, cost, gnorm, scale * gnorm, scale * impr);
 #endif
-    if (!(cost == cost)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END break; }
+    if (!(cost == cost)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END break; }
     // MuJoCo stops on scale*(oldcost - cost) < tol; in fp32 that difference of two large costs is round-off, so the
     // improvement is taken from the line search instead: -alpha p'(0) / 2 (exact for a quadratic, the Newton decrement)
     if (iter > 0) { if (scale * impr < w->opt.tolerance || scale * gnorm < w->opt.tolerance) break; }
@@ -1309,22 +1336,22 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     fe_build_H(w);
     const int* skip = nullptr;
     if (!fast) { // FULL scope: independent part blocks are factored / solved by one lane each
-      fe_mark_indep_blocks(w, w->first, w->skip);
-      fe_chol_blocks(w, w->H, w->skip);
-      skip = w->skip;
+      fe_mark_indep_blocks(w, w->first(), w->skip());
+      fe_chol_blocks(w, w->H(), w->skip());
+      skip = w->skip();
     }
-    if (!fe_chol(w, w->H, w->first, nv, skip)) { LANES_BEGIN if (lane == 0) w->u[2] |= 4; LANES_END }
-    LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search[i] = -w->grad[i]; LANES_END
-    if (skip) fe_solve_blocks(w, w->H, skip, w->search);
-    fe_chol_solve(w, w->H, w->first, nv, w->search, w->Mv, skip);
-    fe_mul_M(w, w->search, w->Mv);
-    fe_mul_J(w, w->search, w->c_jv, w->w_jv, w->l_jv, false);
+    if (!fe_chol(w, w->H(), w->first(), nv, skip)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 4; LANES_END }
+    LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search()[i] = -w->grad()[i]; LANES_END
+    if (skip) fe_solve_blocks(w, w->H(), skip, w->search());
+    fe_chol_solve(w, w->H(), w->first(), nv, w->search(), w->Mv(), skip);
+    fe_mul_M(w, w->search(), w->Mv());
+    fe_mul_J(w, w->search(), w->c_jv(), w->w_jv(), w->l_jv(), false);
     LANES_BEGIN
       float a = 0.f, b = 0.f;
-      for (int i = lane; i < nv; i += 32) { a += w->search[i] * (w->Ma[i] - w->fs[i]); b += 0.5f * w->search[i] * w->Mv[i]; }
-      w->scr[lane] = a; w->scr[32 + lane] = b;
+      for (int i = lane; i < nv; i += 32) { a += w->search()[i] * (w->Ma()[i] - w->fs()[i]); b += 0.5f * w->search()[i] * w->Mv()[i]; }
+      w->scr()[lane] = a; w->scr()[32 + lane] = b;
     LANES_END
-    const float g1 = fe_sum32(w->scr), g2 = fe_sum32(w->scr + 32);
+    const float g1 = fe_sum32(w->scr()), g2 = fe_sum32(w->scr() + 32);
     // exact line search: safeguarded Newton on p'(alpha) = 0
     float p1, p2, lo = 0.f, hi = -1.f, alpha;
     fe_line_eval(w, 0.f, g1, g2, &p1, &p2);
@@ -1344,19 +1371,19 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     if (!(alpha > 0.f)) break;
     impr = -0.5f * alpha * p1_0;
     LANES_BEGIN
-      for (int i = lane; i < nv; i += 32) { w->x[i] += alpha * w->search[i]; w->Ma[i] += alpha * w->Mv[i]; }
+      for (int i = lane; i < nv; i += 32) { w->x()[i] += alpha * w->search()[i]; w->Ma()[i] += alpha * w->Mv()[i]; }
       for (int c = lane; c < ncon; c += 32) {
-        if (fast && w->c_kind[c] == 0) continue;
-        for (int k = 0; k < 3; ++k) w->c_jar[3 * c + k] += alpha * w->c_jv[3 * c + k];
+        if (fast && w->c_kind()[c] == 0) continue;
+        for (int k = 0; k < 3; ++k) w->c_jar()[3 * c + k] += alpha * w->c_jv()[3 * c + k];
       }
-      for (int e = lane; e < 6 * ne; e += 32) w->w_jar[e] += alpha * w->w_jv[e];
-      for (int d = lane; d < nr; d += 32) w->l_jar[d] += alpha * w->l_jv[d];
+      for (int e = lane; e < 6 * ne; e += 32) w->w_jar()[e] += alpha * w->w_jv()[e];
+      for (int d = lane; d < nr; d += 32) w->l_jar()[d] += alpha * w->l_jv()[d];
     LANES_END
     ++iter;
   }
   fe_update(w);
-  fe_mul_JT(w, w->fc);
-  LANES_BEGIN if (lane == 0) { if (iter > w->u[3]) w->u[3] = iter; w->u[7] += iter; } LANES_END
+  fe_mul_JT(w, w->fc());
+  LANES_BEGIN if (lane == 0) { if (iter > w->u()[3]) w->u()[3] = iter; w->u()[7] += iter; } LANES_END
 }
 
 
@@ -1386,20 +1413,20 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
       PV(acc_)[0] = 0.f; PV(acc_)[1] = 0.f;
       if (part < np) {
         const int l = nrl + part, z = nr + 6 * part, da = m->link_dadr[l];
-        const int cnt = w->plist[9 * part + 8];
+        const int cnt = w->plist()[9 * part + 8];
         if (cnt > 0) PV(act_) = 1;
-        if (slot < cnt) PV(c_) = w->plist[9 * part + slot];
-        for (int k = 0; k < 10; ++k) PV(I_)[k] = w->linert[10 * l + k];
-        for (int k = 0; k < 6; ++k) { PV(fs_)[k] = w->fs[z + k]; PV(as_)[k] = w->as[z + k]; }
+        if (slot < cnt) PV(c_) = w->plist()[9 * part + slot];
+        for (int k = 0; k < 10; ++k) PV(I_)[k] = w->linert()[10 * l + k];
+        for (int k = 0; k < 6; ++k) { PV(fs_)[k] = w->fs()[z + k]; PV(as_)[k] = w->as()[z + k]; }
         PV(scale_) = 1.0f / (3.f * PV(I_)[0] + PV(I_)[4] + PV(I_)[5] + PV(I_)[6]);
-        m3mulv(PV(xw_), w->lmat + 9 * l, w->warm + da + 3);
-        v3cpy(PV(xw_) + 3, w->warm + da);
+        m3mulv(PV(xw_), w->lmat() + 9 * l, w->warm() + da + 3);
+        v3cpy(PV(xw_) + 3, w->warm() + da);
         const int c = PV(c_);
         if (c >= 0) {
-          const int B_ = (w->c_link[c] >> 8) - 1;
+          const int B_ = (w->c_link()[c] >> 8) - 1;
           fe_part_rows(w, c, l, B_ == l ? 1.f : -1.f, PV(J_));
-          PV(par_)[0] = w->c_aref[3 * c]; PV(par_)[1] = w->c_aref[3 * c + 1]; PV(par_)[2] = w->c_aref[3 * c + 2];
-          PV(par_)[3] = w->c_D[2 * c]; PV(par_)[4] = w->c_D[2 * c + 1]; PV(par_)[5] = w->c_mu[c]; PV(par_)[6] = w->c_fric[c];
+          PV(par_)[0] = w->c_aref()[3 * c]; PV(par_)[1] = w->c_aref()[3 * c + 1]; PV(par_)[2] = w->c_aref()[3 * c + 2];
+          PV(par_)[3] = w->c_D()[2 * c]; PV(par_)[4] = w->c_D()[2 * c + 1]; PV(par_)[5] = w->c_mu()[c]; PV(par_)[6] = w->c_fric()[c];
           float f[3], cw = 0.f, cs = 0.f;
           const float* J = PV(J_);
           const float* q = PV(par_);
@@ -1455,13 +1482,13 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
           for (int k = 0; k < 21; ++k) H[k] += PV(acc_)[6 + k];
           const float gnorm = sqrtf(gsq);
           bool stop = false;
-          if (!(gnorm == gnorm)) { stop = true; if ((lane & 7) == 0) w->u[2] |= 2; }
+          if (!(gnorm == gnorm)) { stop = true; if ((lane & 7) == 0) w->u()[2] |= 2; }
           else if (PV(iter_) > 0) stop = PV(scale_) * PV(impr_) < tol || PV(scale_) * gnorm < tol;
           else stop = PV(scale_) * gnorm < tol;
           if (PV(iter_) >= maxit) stop = true;
           if (stop) PV(act_) = 0;
           else {
-            if (!fe_chol6(H) && (lane & 7) == 0) w->u[2] |= 4;
+            if (!fe_chol6(H) && (lane & 7) == 0) w->u()[2] |= 4;
             for (int k = 0; k < 6; ++k) PV(sd_)[k] = -g[k];
             fe_chol6_solve(H, PV(sd_));
             float Ms[6], g1 = 0.f, g2 = 0.f;
@@ -1542,8 +1569,8 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
         const float* q = PV(par_);
         float f[3], dummy = 0.f;
         const int st = fe_cone(dot6(J, PV(x_)) - q[0], dot6(J + 6, PV(x_)) - q[1], dot6(J + 12, PV(x_)) - q[2], q[5], q[6], q[3], q[4], f, &dummy, nullptr);
-        w->c_state[c] = st;
-        for (int k = 0; k < 3; ++k) w->c_f[3 * c + k] = f[k];
+        w->c_state()[c] = st;
+        for (int k = 0; k < 3; ++k) w->c_f()[3 * c + k] = f[k];
         for (int i = 0; i < 6; ++i) PV(acc_)[i] = J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2];
       }
     LANES_END
@@ -1552,9 +1579,9 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
       const int part = PV(part_);
       if (part >= 0 && (lane & 7) == 0) {
         const int z = nr + 6 * part;
-        const bool any = w->plist[9 * part + 8] > 0;
-        for (int k = 0; k < 6; ++k) { w->x[z + k] = any ? PV(x_)[k] : PV(as_)[k]; w->fc[z + k] = any ? PV(acc_)[k] : 0.f; }
-        w->iscr[part] = PV(iter_);
+        const bool any = w->plist()[9 * part + 8] > 0;
+        for (int k = 0; k < 6; ++k) { w->x()[z + k] = any ? PV(x_)[k] : PV(as_)[k]; w->fc()[z + k] = any ? PV(acc_)[k] : 0.f; }
+        w->iscr()[part] = PV(iter_);
       }
     LANES_END
   }
@@ -1564,36 +1591,36 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
 // block cooperatively), FULL scope otherwise
 FE_FN void fe_solve(FeWarp* w) {
   const fe_model* m = w->m;
-  const int ncon = w->u[0], ne = m->neq, np = m->npart, nrl = m->nrlink;
+  const int ncon = w->u()[0], ne = m->neq, np = m->npart, nrl = m->nrlink;
   LANES_BEGIN
     int coupled = 0;
-    for (int c = lane; c < ncon; c += 32) coupled |= w->c_kind[c] == 2;
-    for (int e = lane; e < ne; e += 32) coupled |= w->eq_active[e] != 0;
+    for (int c = lane; c < ncon; c += 32) coupled |= w->c_kind()[c] == 2;
+    for (int e = lane; e < ne; e += 32) coupled |= w->eq_active()[e] != 0;
     if (lane < np) { // contacts of part `lane` against the static world (at most 8 handled by the grouped solver)
       const int l = nrl + lane;
       int cnt = 0;
       for (int c = 0; c < ncon; ++c) {
-        if (w->c_kind[c] != 0) continue;
-        const int A = (w->c_link[c] & 255) - 1, B = (w->c_link[c] >> 8) - 1;
+        if (w->c_kind()[c] != 0) continue;
+        const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
         if (A != l && B != l) continue;
-        if (cnt < 8) w->plist[9 * lane + cnt] = c;
+        if (cnt < 8) w->plist()[9 * lane + cnt] = c;
         ++cnt;
       }
-      w->plist[9 * lane + 8] = cnt;
+      w->plist()[9 * lane + 8] = cnt;
       if (cnt > 8) coupled = 1;
     }
-    w->iscr[lane] = coupled;
-    if (lane == 0) w->u[3] = 0;
+    w->iscr()[lane] = coupled;
+    if (lane == 0) w->u()[3] = 0;
   LANES_END
-  const bool coupled = fe_ballot32(w->iscr) != 0u;
+  const bool coupled = fe_ballot32(w->iscr()) != 0u;
   w->fast = coupled ? 0 : 1;
   w->nact = coupled ? m->nv : m->nr;
   if (!coupled) {
     fe_solve_parts_grouped(w);
     LANES_BEGIN
-      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr[p] > mx ? w->iscr[p] : mx; w->u[3] = mx; w->u[4] = 0; }
+      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] = 0; }
     LANES_END
-  } else { LANES_BEGIN if (lane == 0) { w->u[4] = 1; w->u[5] += 1; } LANES_END }
+  } else { LANES_BEGIN if (lane == 0) { w->u()[4] = 1; w->u()[5] += 1; } LANES_END }
   fe_solve_coop(w);
   w->fast = 0;
   w->nact = m->nv;
@@ -1612,39 +1639,39 @@ FE_FN void fe_integrate(FeWarp* w) {
         while (fe_tri(i + 1) <= e) ++i;
         while (fe_tri(i) > e) --i;
         const int j = e - fe_tri(i);
-        w->Lr[e] = w->Mr[i * nr + j] + (i == j ? h * m->dof_damping[i] : 0.f);
+        w->Lr()[e] = w->Mr()[i * nr + j] + (i == j ? h * m->dof_damping[i] : 0.f);
       }
-      for (int d = lane; d < nr; d += 32) { w->grad[d] = w->fs[d] + w->fc[d]; w->first[d] = 0; }
+      for (int d = lane; d < nr; d += 32) { w->grad()[d] = w->fs()[d] + w->fc()[d]; w->first()[d] = 0; }
     LANES_END
-    if (!fe_chol(w, w->Lr, w->first, nr)) { LANES_BEGIN if (lane == 0) w->u[2] |= 2; LANES_END }
-    fe_chol_solve(w, w->Lr, w->first, nr, w->grad, w->Mv);
+    if (!fe_chol(w, w->Lr(), w->first(), nr)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END }
+    fe_chol_solve(w, w->Lr(), w->first(), nr, w->grad(), w->Mv());
   }
   LANES_BEGIN
     // warm start for the next step = solver solution, stored in qacc coordinates
     for (int d = lane; d < nr; d += 32) {
-      w->warm[d] = w->x[d];
-      const float v = w->qvel[d] + h * w->grad[d];
-      w->qvel[d] = v;
-      w->qpos[d] += h * v;
+      w->warm()[d] = w->x()[d];
+      const float v = w->qvel()[d] + h * w->grad()[d];
+      w->qvel()[d] = v;
+      w->qpos()[d] += h * v;
     }
     for (int p = lane; p < np; p += 32) {
       const int l = nrl + p, z = nr + 6 * p, da = m->link_dadr[l], qa = m->link_qadr[l];
-      const float* R = w->lmat + 9 * l;
+      const float* R = w->lmat() + 9 * l;
       float t[3];
-      m3tmulv(t, R, w->x + z);
-      v3cpy(w->warm + da, w->x + z + 3);
-      v3cpy(w->warm + da + 3, t);
+      m3tmulv(t, R, w->x() + z);
+      v3cpy(w->warm() + da, w->x() + z + 3);
+      v3cpy(w->warm() + da + 3, t);
       float A[21], a[6];
-      fe_inert_sym6(A, w->linert + 10 * l, h * m->dof_damping[da]);
-      if (!fe_chol6(A)) w->u[2] |= 2;
-      for (int k = 0; k < 6; ++k) a[k] = w->fs[z + k] + w->fc[z + k];
+      fe_inert_sym6(A, w->linert() + 10 * l, h * m->dof_damping[da]);
+      if (!fe_chol6(A)) w->u()[2] |= 2;
+      for (int k = 0; k < 6; ++k) a[k] = w->fs()[z + k] + w->fc()[z + k];
       fe_chol6_solve(A, a);
       m3tmulv(t, R, a);
-      for (int k = 0; k < 3; ++k) { w->qvel[da + k] += h * a[3 + k]; w->qvel[da + 3 + k] += h * t[k]; }
-      for (int k = 0; k < 3; ++k) w->qpos[qa + k] += h * w->qvel[da + k];
-      float wl[3] = {w->qvel[da + 3], w->qvel[da + 4], w->qvel[da + 5]};
+      for (int k = 0; k < 3; ++k) { w->qvel()[da + k] += h * a[3 + k]; w->qvel()[da + 3 + k] += h * t[k]; }
+      for (int k = 0; k < 3; ++k) w->qpos()[qa + k] += h * w->qvel()[da + k];
+      float wl[3] = {w->qvel()[da + 3], w->qvel()[da + 4], w->qvel()[da + 5]};
       const float n = v3norm(wl);
-      float* q = w->qpos + qa + 3;
+      float* q = w->qpos() + qa + 3;
       if (n * h > 1e-12f) {
         const float s = sinf(0.5f * n * h) / n, c = cosf(0.5f * n * h);
         float dq[4] = {c, wl[0] * s, wl[1] * s, wl[2] * s}, qn[4];
@@ -1657,11 +1684,11 @@ FE_FN void fe_integrate(FeWarp* w) {
   // divergence guard (mj_checkPos / mj_checkVel): NaN or huge values raise bit 3
   LANES_BEGIN
     int bad = 0;
-    for (int i = lane; i < m->nq; i += 32) { float v = w->qpos[i]; if (!(v == v) || fabsf(v) > 1e6f) bad = 1; }
-    for (int i = lane; i < m->nv; i += 32) { float v = w->qvel[i]; if (!(v == v) || fabsf(v) > 1e6f) bad = 1; }
-    w->iscr[lane] = bad;
+    for (int i = lane; i < m->nq; i += 32) { float v = w->qpos()[i]; if (!(v == v) || fabsf(v) > 1e6f) bad = 1; }
+    for (int i = lane; i < m->nv; i += 32) { float v = w->qvel()[i]; if (!(v == v) || fabsf(v) > 1e6f) bad = 1; }
+    w->iscr()[lane] = bad;
   LANES_END
-  if (fe_ballot32(w->iscr) != 0u) { LANES_BEGIN if (lane == 0) w->u[2] |= 8; LANES_END }
+  if (fe_ballot32(w->iscr()) != 0u) { LANES_BEGIN if (lane == 0) w->u()[2] |= 8; LANES_END }
 }
 
 FE_FN void fe_forward(FeWarp* w) {
@@ -1680,7 +1707,7 @@ FE_FN void fe_substep(FeWarp* w) {
 FE_FN void fe_substep_lockstep(FeWarp* w) {
   const int ls = w->opt.lockstep;
 #if FE_DEVICE_BUILD
-#define FE_TICK(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) w->u[slot] += (int)((t1_ - t0_) >> 4); t0_ = t1_; }
+#define FE_TICK(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) w->u()[slot] += (int)((t1_ - t0_) >> 4); t0_ = t1_; }
   long long t0_ = clock64();
 #else
 #define FE_TICK(slot)

@@ -187,7 +187,7 @@ FE_HD float fe_rand(unsigned long long* s, float lo, float hi) {
 
 // ---------------------------------------------------------------- env context of one warp
 struct FeEnv {
-  FeWarp w;
+  FeWarp* w;      // header of the env's slice
   const fe_scene* sc;
   const fe_config* cfg;
   FeState st;
@@ -206,7 +206,7 @@ FE_HDN void fe_site_pose_d(const FeWarp* w, int site, double* pos, double* mat, 
   const fe_model* m = w->m;
   const int l = m->site_link[site];
   float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
-  if (l >= 0) { for (int k = 0; k < 9; ++k) R[k] = w->lmat[9 * l + k]; v3cpy(P, w->lpos + 3 * l); for (int k = 0; k < 4; ++k) Q[k] = w->lquat[4 * l + k]; }
+  if (l >= 0) { for (int k = 0; k < 9; ++k) R[k] = w->lmat()[9 * l + k]; v3cpy(P, w->lpos() + 3 * l); for (int k = 0; k < 4; ++k) Q[k] = w->lquat()[4 * l + k]; }
   const float* sp = m->site_pos[site];
   const float* sq = m->site_quat[site];
   for (int i = 0; i < 3; ++i) pos[i] = (double)P[i] + (double)R[3 * i] * sp[0] + (double)R[3 * i + 1] * sp[1] + (double)R[3 * i + 2] * sp[2];
@@ -224,31 +224,31 @@ FE_HDN void fe_site_pose_d(const FeWarp* w, int site, double* pos, double* mat, 
 // _stop_object(obj, gravity=gc): xfrc_applied -> gravity-compensation factor, qvel = 0 (furniture.py:2778-2800)
 FE_HD void fe_stop_part(FeWarp* w, int p, float gc) {
   const int da = w->m->link_dadr[w->m->nrlink + p];
-  w->gravcomp[p] = gc;
-  for (int k = 0; k < 6; ++k) w->qvel[da + k] = 0.f;
+  w->gravcomp()[p] = gc;
+  for (int k = 0; k < 6; ++k) w->qvel()[da + k] = 0.f;
 }
 // _move_objects_translation_quat(obj, translation, target_quat, gravity): rigidly move obj's whole group (furniture.py:1163-1176)
 FE_HDN void fe_move_group(FeEnv* e, int obj, const double* translation, const double* target_quat, float gc) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const fe_model* m = w->m;
   const int qb = m->link_qadr[m->nrlink + obj];
   double base[7];
-  for (int k = 0; k < 7; ++k) base[k] = (double)w->qpos[qb + k];
+  for (int k = 0; k < 7; ++k) base[k] = (double)w->qpos()[qb + k];
   const int g = fe_find(e->group, obj);
   for (int i = 0; i < m->npart; ++i) {
     if (fe_find(e->group, i) != g) continue;
     const int qa = m->link_qadr[m->nrlink + i];
     double q[7], np_[3], nq[4];
-    for (int k = 0; k < 7; ++k) q[k] = (double)w->qpos[qa + k];
+    for (int k = 0; k < 7; ++k) q[k] = (double)w->qpos()[qa + k];
     d_transform_to_target(base, q, target_quat, np_, nq);
-    for (int k = 0; k < 3; ++k) w->qpos[qa + k] = (float)(np_[k] + translation[k]);
-    for (int k = 0; k < 4; ++k) w->qpos[qa + 3 + k] = (float)nq[k];
+    for (int k = 0; k < 3; ++k) w->qpos()[qa + k] = (float)(np_[k] + translation[k]);
+    for (int k = 0; k < 4; ++k) w->qpos()[qa + 3 + k] = (float)nq[k];
     fe_stop_part(w, i, gc);
   }
 }
 // min z over every site of every part in obj's group, starting from 0 (furniture.py:749-769)
 FE_HDN double fe_group_min_z(FeEnv* e, int obj) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const int g = fe_find(e->group, obj);
   double mn = 0.0;
   for (int i = 0; i < w->m->npart; ++i) {
@@ -263,12 +263,12 @@ FE_HDN double fe_group_min_z(FeEnv* e, int obj) {
 }
 
 // forward + step as the reference issues them (the extra sim.forward() has no effect on the state)
-FE_FN void fe_fwd_step(FeEnv* e) { fe_substep(&e->w); }
+FE_FN void fe_fwd_step(FeEnv* e) { fe_substep(e->w); }
 
 // _try_connect(part1) for arm agents (part2 = None, _num_connect_steps = 0), furniture.py:926-1042.
 // Runs on lane 0; leaves the aligned pair in ei[2..5] and the target quat in ed[0..3]; ei[0] = 1 if aligned.
 FE_FN void fe_try_connect_scan(FeEnv* e, int part1) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const fe_scene* sc = e->sc;
   const fe_config* cfg = e->cfg;
   LANES_BEGIN
@@ -299,7 +299,7 @@ FE_FN void fe_try_connect_scan(FeEnv* e, int part1) {
 
 // _connect(site1, site2) (furniture.py:847-924) for arm agents
 FE_FN void fe_connect(FeEnv* e) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const fe_model* m = w->m;
   const fe_scene* sc = e->sc;
   const int s1 = e->ei[2], s2 = e->ei[3], body1 = sc->conn_part[e->ei[4]], body2 = sc->conn_part[e->ei[5]];
@@ -312,7 +312,7 @@ FE_FN void fe_connect(FeEnv* e) {
         const int p = ((m->geom_tag[g] >> FE_TAG_PART_SHIFT) & 0xff) - 1;
         if (p < 0) continue;
         const int gp = fe_find(e->group, p);
-        if ((gp == g1 || gp == g2) && w->contype[g] != 0) { w->contype[g] = (1 << 30) - 1 - (1 << (g1 + 1)); w->conaff[g] = 1 << (g1 + 1); }
+        if ((gp == g1 || gp == g2) && w->contype()[g] != 0) { w->contype()[g] = (1 << 30) - 1 - (1 << (g1 + 1)); w->conaff()[g] = 1 << (g1 + 1); }
       }
       if (e->cfg->auto_align) { // _align_connectors -> _move_site_to_target (furniture.py:1224-1250)
         double target[7], base[7], sp[3], sq[4];
@@ -324,7 +324,7 @@ FE_FN void fe_connect(FeEnv* e) {
         for (int k = 0; k < 4; ++k) base[3 + k] = sq[k];
         const int qa = m->link_qadr[m->nrlink + body2];
         double bq[7], np_[3], nq[4], nsp[3], nsq[4], nb[7];
-        for (int k = 0; k < 7; ++k) bq[k] = (double)w->qpos[qa + k];
+        for (int k = 0; k < 7; ++k) bq[k] = (double)w->qpos()[qa + k];
         d_transform_to_target(base, bq, target + 3, np_, nq);
         for (int k = 0; k < 3; ++k) nb[k] = bq[k];
         for (int k = 0; k < 4; ++k) nb[3 + k] = bq[3 + k];
@@ -352,20 +352,20 @@ FE_FN void fe_connect(FeEnv* e) {
         if (lane == 0) {
           const int obj = which == 0 ? body1 : body2;
           const int qa = m->link_qadr[m->nrlink + obj];
-          double tq[4] = {(double)w->qpos[qa + 3], (double)w->qpos[qa + 4], (double)w->qpos[qa + 5], (double)w->qpos[qa + 6]};
+          double tq[4] = {(double)w->qpos()[qa + 3], (double)w->qpos()[qa + 4], (double)w->qpos()[qa + 5], (double)w->qpos()[qa + 6]};
           double tr[3] = {0, 0, -lift};
           // note: _move_rotate_object does not stop the parts (no _stop_object call): keep velocities / gravcomp
           const int g = fe_find(e->group, obj);
           double base[7];
-          for (int k = 0; k < 7; ++k) base[k] = (double)w->qpos[qa + k];
+          for (int k = 0; k < 7; ++k) base[k] = (double)w->qpos()[qa + k];
           for (int i = 0; i < m->npart; ++i) {
             if (fe_find(e->group, i) != g) continue;
             const int qi = m->link_qadr[m->nrlink + i];
             double q[7], np_[3], nq[4];
-            for (int k = 0; k < 7; ++k) q[k] = (double)w->qpos[qi + k];
+            for (int k = 0; k < 7; ++k) q[k] = (double)w->qpos()[qi + k];
             d_transform_to_target(base, q, tq, np_, nq);
-            for (int k = 0; k < 3; ++k) w->qpos[qi + k] = (float)(np_[k] + tr[k]);
-            for (int k = 0; k < 4; ++k) w->qpos[qi + 3 + k] = (float)nq[k];
+            for (int k = 0; k < 3; ++k) w->qpos()[qi + k] = (float)(np_[k] + tr[k]);
+            for (int k = 0; k < 4; ++k) w->qpos()[qi + 3 + k] = (float)nq[k];
           }
         }
       LANES_END
@@ -380,14 +380,14 @@ FE_FN void fe_connect(FeEnv* e) {
         if ((a == body1 || a == body2) && (b == body1 || b == body2)) {
           const int qa = m->link_qadr[m->nrlink + a], qb = m->link_qadr[m->nrlink + b];
           double q1[7], q2[7], inv[4], d[3], r[3], rq[4];
-          for (int k = 0; k < 7; ++k) { q1[k] = (double)w->qpos[qa + k]; q2[k] = (double)w->qpos[qb + k]; }
+          for (int k = 0; k < 7; ++k) { q1[k] = (double)w->qpos()[qa + k]; q2[k] = (double)w->qpos()[qb + k]; }
           dq_inv(inv, q1 + 3);
           dq_mul(rq, inv, q2 + 3);
           d[0] = q2[0] - q1[0]; d[1] = q2[1] - q1[1]; d[2] = q2[2] - q1[2];
           dq_rotate(r, inv, d);
-          for (int k = 0; k < 3; ++k) w->eq_data[7 * q + k] = (float)r[k];
-          for (int k = 0; k < 4; ++k) w->eq_data[7 * q + 3 + k] = (float)rq[k];
-          w->eq_active[q] = 1;
+          for (int k = 0; k < 3; ++k) w->eq_data()[7 * q + k] = (float)r[k];
+          for (int k = 0; k < 4; ++k) w->eq_data()[7 * q + 3 + k] = (float)rq[k];
+          w->eq_active()[q] = 1;
           const int p1 = fe_find(e->group, body1), p2 = fe_find(e->group, body2);
           e->group[p1] = p2;
         }
@@ -395,45 +395,45 @@ FE_FN void fe_connect(FeEnv* e) {
       e->es.num_connected[e->env] += 1;
       e->ei[1] = body1; // _connected_body1 and its pose
       const int qa = m->link_qadr[m->nrlink + body1];
-      for (int k = 0; k < 7; ++k) e->ed[4 + k] = (double)w->qpos[qa + k];
+      for (int k = 0; k < 7; ++k) e->ed[4 + k] = (double)w->qpos()[qa + k];
     }
   LANES_END
 }
 
 // _get_obs: object_ob (7 per part, XML order) then robot_ob (furniture.py:1344-1387, furniture_sawyer.py:103-155)
 FE_FN void fe_write_obs(FeEnv* e) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const fe_model* m = w->m;
   const fe_scene* sc = e->sc;
   float* ob = e->es.obs + (size_t)e->env * sc->obs_dim;
   const int nrl = m->nrlink, np = m->npart;
   LANES_BEGIN
     for (int p = lane; p < np; p += 32) {
-      for (int k = 0; k < 3; ++k) ob[7 * p + k] = w->lpos[3 * (nrl + p) + k];
-      for (int k = 0; k < 4; ++k) ob[7 * p + 3 + k] = w->lquat[4 * (nrl + p) + k];
+      for (int k = 0; k < 3; ++k) ob[7 * p + k] = w->lpos()[3 * (nrl + p) + k];
+      for (int k = 0; k < 4; ++k) ob[7 * p + 3 + k] = w->lquat()[4 * (nrl + p) + k];
     }
     float* rb = ob + 7 * np;
     const int na = sc->narm, ngr = sc->ngrip;
-    for (int d = lane; d < na; d += 32) { rb[d] = w->qpos[d]; rb[na + d] = w->qvel[d]; }
-    for (int d = lane; d < ngr; d += 32) rb[2 * na + d] = w->qpos[na + d];
+    for (int d = lane; d < na; d += 32) { rb[d] = w->qpos()[d]; rb[na + d] = w->qvel()[d]; }
+    for (int d = lane; d < ngr; d += 32) rb[2 * na + d] = w->qpos()[na + d];
     if (lane == 0 && sc->eef_site >= 0) {
       float* o = rb + 2 * na + ngr;
       const int s = sc->eef_site, l = m->site_link[s], hl = sc->hand_link;
       float t[3], sp[3], q[4];
-      m3mulv(t, w->lmat + 9 * l, m->site_pos[s]);
-      v3add(sp, w->lpos + 3 * l, t);
+      m3mulv(t, w->lmat() + 9 * l, m->site_pos[s]);
+      v3add(sp, w->lpos() + 3 * l, t);
       v3cpy(o, sp);
-      qmul(q, w->lquat + 4 * hl, sc->hand_quat);
+      qmul(q, w->lquat() + 4 * hl, sc->hand_quat);
       o[3] = q[1]; o[4] = q[2]; o[5] = q[3]; o[6] = q[0]; // xyzw
-      fe_point_vel(w, w->lvel, l, sp, o + 7);
-      v3cpy(o + 10, w->lvel + 6 * l);
+      fe_point_vel(w, w->lvel(), l, sp, o + 7);
+      v3cpy(o + 10, w->lvel() + 6 * l);
     }
   LANES_END
 }
 
 // FurnitureEnv._reset (furniture.py:1406-1663); the warp slice is (re)initialised here, caller stores it
 FE_FN void fe_env_reset_one(FeEnv* e) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const fe_model* m = w->m;
   const fe_scene* sc = e->sc;
   const fe_config* cfg = e->cfg;
@@ -442,21 +442,21 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
   int* rca = e->es.robot_conaff + (size_t)e->env * ng;
   LANES_BEGIN
     // sim.reset(): data only (model arrays such as masks / eq_data persist)
-    for (int i = lane; i < m->nq; i += 32) w->qpos[i] = 0.f;
-    for (int i = lane; i < m->nv; i += 32) { w->qvel[i] = 0.f; w->warm[i] = 0.f; }
-    for (int i = lane; i < m->nu; i += 32) w->ctrl[i] = 0.f;
-    for (int i = lane; i < nr; i += 32) w->qfrc_applied[i] = 0.f;
-    for (int i = lane; i < np; i += 32) { w->gravcomp[i] = 0.f; e->group[i] = i; e->es.touched[(size_t)e->env * np + i] = 0; e->es.picked[(size_t)e->env * np + i] = 0; }
+    for (int i = lane; i < m->nq; i += 32) w->qpos()[i] = 0.f;
+    for (int i = lane; i < m->nv; i += 32) { w->qvel()[i] = 0.f; w->warm()[i] = 0.f; }
+    for (int i = lane; i < m->nu; i += 32) w->ctrl()[i] = 0.f;
+    for (int i = lane; i < nr; i += 32) w->qfrc_applied()[i] = 0.f;
+    for (int i = lane; i < np; i += 32) { w->gravcomp()[i] = 0.f; e->group[i] = i; e->es.touched[(size_t)e->env * np + i] = 0; e->es.picked[(size_t)e->env * np + i] = 0; }
     for (int g = lane; g < ng; g += 32) {
       const int tag = m->geom_tag[g];
-      if (tag & FE_TAG_ROBOT) { rct[g] = w->contype[g]; rca[g] = w->conaff[g]; w->contype[g] = 0; w->conaff[g] = 0; } // furniture.py:1441-1453
-      if (tag & (1 << 30)) { w->contype[g] = 1; w->conaff[g] = 1; }                                                    // :1456-1461
+      if (tag & FE_TAG_ROBOT) { rct[g] = w->contype()[g]; rca[g] = w->conaff()[g]; w->contype()[g] = 0; w->conaff()[g] = 0; } // furniture.py:1441-1453
+      if (tag & (1 << 30)) { w->contype()[g] = 1; w->conaff()[g] = 1; }                                                    // :1456-1461
     }
-    for (int q = lane; q < m->neq; q += 32) w->eq_active[q] = 0; // :1501-1503
+    for (int q = lane; q < m->neq; q += 32) w->eq_active()[q] = 0; // :1501-1503
     for (int s = lane; s < m->nsite; s += 32) e->es.site_connected[(size_t)e->env * m->nsite + s] = 0;
     if (lane == 0) {
       e->es.num_connected[e->env] = 0; e->es.prev_num_connected[e->env] = 0; e->es.episode_len[e->env] = 0; e->es.episode_reward[e->env] = 0.f;
-      w->u[2] = 0;
+      w->u()[2] = 0;
     }
   LANES_END
   LANES_BEGIN
@@ -472,16 +472,16 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
           bool valid = true;
           for (int o = 0; o < p; ++o) {
             const int qo = m->link_qadr[nrl + o];
-            const float dx = x - w->qpos[qo], dy = y - w->qpos[qo + 1];
+            const float dx = x - w->qpos()[qo], dy = y - w->qpos()[qo + 1];
             if (sqrtf(dx * dx + dy * dy) <= sc->part_radius[o] + sc->part_radius[p]) { valid = false; break; }
           }
           if (valid) break;
         }
         const int qa = m->link_qadr[nrl + p];
-        w->qpos[qa] = x; w->qpos[qa + 1] = y; w->qpos[qa + 2] = sc->part_init_pos[p][2] + 0.01f;
+        w->qpos()[qa] = x; w->qpos()[qa + 1] = y; w->qpos()[qa + 2] = sc->part_init_pos[p][2] + 0.01f;
         double q0[4] = {sc->part_init_quat[p][0], sc->part_init_quat[p][1], sc->part_init_quat[p][2], sc->part_init_quat[p][3]}, q[4];
         dq_mul(q, q0, qx);
-        for (int k = 0; k < 4; ++k) w->qpos[qa + 3 + k] = (float)q[k];
+        for (int k = 0; k < 4; ++k) w->qpos()[qa + 3 + k] = (float)q[k];
       }
       e->es.rng[e->env] = rs;
     }
@@ -494,8 +494,8 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
       LANES_BEGIN
         for (int p = lane; p < np; p += 32) { // _slow_object: full gravity compensation + velocity clip (furniture.py:2821-2842)
           const int da = m->link_dadr[nrl + p];
-          w->gravcomp[p] = 1.f;
-          for (int k = 0; k < 6; ++k) w->qvel[da + k] = fminf(fmaxf(w->qvel[da + k], -0.2f), 0.2f);
+          w->gravcomp()[p] = 1.f;
+          for (int k = 0; k < 6; ++k) w->qvel()[da + k] = fminf(fmaxf(w->qvel()[da + k], -0.2f), 0.2f);
         }
       LANES_END
     }
@@ -503,12 +503,12 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
   // gravity compensation, robot pose, one step with robot collisions still off (furniture.py:1569-1584)
   for (int phase = 0; phase < 101; ++phase) {
     LANES_BEGIN
-      if (phase <= 1) for (int d = lane; d < nr; d += 32) w->qfrc_applied[d] = w->bias[d];
-      if (phase == 1) for (int g = lane; g < ng; g += 32) if (m->geom_tag[g] & FE_TAG_ROBOT) { w->contype[g] = rct[g]; w->conaff[g] = rca[g]; } // :1586-1595
+      if (phase <= 1) for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d];
+      if (phase == 1) for (int g = lane; g < ng; g += 32) if (m->geom_tag[g] & FE_TAG_ROBOT) { w->contype()[g] = rct[g]; w->conaff()[g] = rca[g]; } // :1586-1595
       if (lane == 0) { // _initialize_robot_pos (furniture.py:1761-1779): fresh noise on every call
         unsigned long long rs = e->es.rng[e->env];
-        for (int d = 0; d < sc->narm; ++d) w->qpos[d] = sc->robot_init_qpos[d] + fe_rand(&rs, -cfg->agent_xyz_rand, cfg->agent_xyz_rand);
-        for (int d = sc->narm; d < sc->narm + sc->ngrip; ++d) w->qpos[d] = sc->robot_init_qpos[d];
+        for (int d = 0; d < sc->narm; ++d) w->qpos()[d] = sc->robot_init_qpos[d] + fe_rand(&rs, -cfg->agent_xyz_rand, cfg->agent_xyz_rand);
+        for (int d = sc->narm; d < sc->narm + sc->ngrip; ++d) w->qpos()[d] = sc->robot_init_qpos[d];
         e->es.rng[e->env] = rs;
       }
     LANES_END
@@ -516,23 +516,23 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
   }
   // sync (furniture.py:1621-1628), gravity compensation from that forward pass, 100 settle steps (:1639-1641)
   LANES_BEGIN
-    for (int i = lane; i < m->nu; i += 32) w->ctrl[i] = 0.f;
-    for (int i = lane; i < nr; i += 32) w->qfrc_applied[i] = 0.f;
-    for (int i = lane; i < np; i += 32) w->gravcomp[i] = 0.f;
-    for (int i = lane; i < m->nv; i += 32) w->warm[i] = 0.f;
+    for (int i = lane; i < m->nu; i += 32) w->ctrl()[i] = 0.f;
+    for (int i = lane; i < nr; i += 32) w->qfrc_applied()[i] = 0.f;
+    for (int i = lane; i < np; i += 32) w->gravcomp()[i] = 0.f;
+    for (int i = lane; i < m->nv; i += 32) w->warm()[i] = 0.f;
   LANES_END
-  fe_forward(&e->w);
-  LANES_BEGIN for (int d = lane; d < nr; d += 32) w->qfrc_applied[d] = w->bias[d]; LANES_END
+  fe_forward(e->w);
+  LANES_BEGIN for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d]; LANES_END
   for (int i = 0; i < 100; ++i) fe_fwd_step(e);
   LANES_BEGIN
-    if (lane == 0) { e->es.done[e->env] = 0; if (w->u[2] & 8) { /* a reset that diverges is reported, not hidden */ } }
+    if (lane == 0) { e->es.done[e->env] = 0; if (w->u()[2] & 8) { /* a reset that diverges is reported, not hidden */ } }
   LANES_END
   fe_write_obs(e);
 }
 
 // FurnitureEnv.step for one env; writes reward / done / info; auto-resets when done (subproc_vec_env.py:16-20)
 FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uint8_t* done_out, int32_t* info_out) {
-  FeWarp* w = &e->w;
+  FeWarp* w = e->w;
   const fe_model* m = w->m;
   const fe_scene* sc = e->sc;
   const fe_config* cfg = e->cfg;
@@ -551,20 +551,20 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
         const float lo = m->act_ctrlrange[u][0], hi = m->act_ctrlrange[u][1];
         v = 0.5f * (hi + lo) + 0.5f * (hi - lo) * v;
       }
-      w->ctrl[u] = v;
+      w->ctrl()[u] = v;
     }
-    for (int d = lane; d < nr; d += 32) w->qfrc_applied[d] = w->bias[d]; // gravity compensation, :3372-3377
-    if (lane == 0) { e->ei[0] = 0; e->ei[1] = -1; e->ei[6] = 0; w->u[2] = 0; }
+    for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d]; // gravity compensation, :3372-3377
+    if (lane == 0) { e->ei[0] = 0; e->ei[1] = -1; e->ei[6] = 0; w->u()[2] = 0; }
   LANES_END
   for (int i = 0; i < cfg->nsub; ++i) fe_substep_lockstep(w); // _do_simulation, furniture.py:2877-2879
-  int fail = (w->u[2] & 8) ? 1 : 0;                   // MujocoException path, :2889-2897
+  int fail = (w->u()[2] & 8) ? 1 : 0;                   // MujocoException path, :2889-2897
   FE_SYNC;
   if (fail) {
     fe_env_reset_one(e);
   } else {
     if (connect > 0.f) { // furniture.py:1290-1322
       int part = -1;
-      for (int p = 0; p < np; ++p) if ((w->touch[p] & 3) == 3) { part = p; break; }
+      for (int p = 0; p < np; ++p) if ((w->touch()[p] & 3) == 3) { part = p; break; }
       if (part >= 0) {
         fe_try_connect_scan(e, part);
         if (e->ei[0]) fe_connect(e);
@@ -576,13 +576,13 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       LANES_BEGIN
         if (lane == 0) {
           const int b1 = e->ei[1], qa = m->link_qadr[m->nrlink + b1];
-          double tr[3] = {e->ed[4] - (double)w->qpos[qa], e->ed[5] - (double)w->qpos[qa + 1], e->ed[6] - (double)w->qpos[qa + 2]};
+          double tr[3] = {e->ed[4] - (double)w->qpos()[qa], e->ed[5] - (double)w->qpos()[qa + 1], e->ed[6] - (double)w->qpos()[qa + 2]};
           fe_move_group(e, b1, tr, e->ed + 7, 0.f);
           e->ei[1] = -1;
         }
       LANES_END
       fe_fwd_step(e);
-      if (w->u[2] & 8) { fail = 1; fe_env_reset_one(e); }
+      if (w->u()[2] & 8) { fail = 1; fe_env_reset_one(e); }
     }
   }
   // reward (furniture.py:482-541), termination (:440-445, :451-480)
@@ -593,7 +593,7 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       int* picked = e->es.picked + (size_t)env * np;
       if (!fail)
         for (int p = 0; p < np; ++p) {
-          const int t = w->touch[p];
+          const int t = w->touch()[p];
           if ((t & 3) == 3) {
             if (!touched[p]) { touched[p] = 1; touch_r += cfg->touch_reward; }
             if (!(t & 4) && !picked[p]) { picked[p] = 1; pick_r += cfg->pick_reward; }
@@ -614,7 +614,7 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       reward_out[env] = reward;
       done_out[env] = (uint8_t)done;
       int32_t* info = info_out + (size_t)env * FE_INFO_DIM;
-      info[0] = nc; info[1] = success; info[2] = fail; info[3] = len; info[4] = w->u[0]; info[5] = w->u[3];
+      info[0] = nc; info[1] = success; info[2] = fail; info[3] = len; info[4] = w->u()[0]; info[5] = w->u()[3];
       e->es.done[env] = done;
       e->ei[6] = done && !fail; // the unstable path has already reset the env
     }
@@ -625,7 +625,7 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
 // per-env context set-up shared by the CUDA kernels and the emulation loop
 FE_FN void fe_env_bind(FeEnv* e, float* slice, const fe_model* m, const fe_scene* sc, const fe_config* cfg, const FeOpt& opt, const FeState& st,
                        const FeEnvState& es, int env, int slice_words_physics) {
-  fe_warp_bind(&e->w, slice, m, opt);
+  e->w = fe_warp_bind(slice, m, opt);
   e->sc = sc; e->cfg = cfg; e->st = st; e->es = es; e->env = env;
   float* extra = slice + slice_words_physics;
   e->ed = (double*)extra;            // 16 doubles (8-byte aligned: slices are multiples of 32 words)
@@ -634,10 +634,10 @@ FE_FN void fe_env_bind(FeEnv* e, float* slice, const fe_model* m, const fe_scene
 }
 #define FE_ENV_EXTRA_WORDS 64
 FE_FN void fe_env_load_groups(FeEnv* e) {
-  const int np = e->w.m->npart;
+  const int np = e->w->m->npart;
   LANES_BEGIN for (int p = lane; p < np; p += 32) e->group[p] = e->es.group[(size_t)e->env * np + p]; LANES_END
 }
 FE_FN void fe_env_store_groups(FeEnv* e) {
-  const int np = e->w.m->npart;
+  const int np = e->w->m->npart;
   LANES_BEGIN for (int p = lane; p < np; p += 32) e->es.group[(size_t)e->env * np + p] = e->group[p]; LANES_END
 }

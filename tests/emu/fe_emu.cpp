@@ -29,34 +29,37 @@ static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* 
 #include "../../furniture_b200/csrc/fe_api.inl"
 
 static int plat_run_sim(fe_handle* h, int nsub, int mode, void*) {
+  fe_h_lay = h->lay;
   std::vector<float> slice(h->slice_words + FE_ENV_EXTRA_WORDS);
   for (int env = 0; env < h->N; ++env) fe_run_env(h->st, h->dm, h->opt, env, nsub, mode, slice.data(), h->dbg);
   return 0;
 }
 static int plat_run_reset(fe_handle* h, const uint8_t* mask, void*) {
+  fe_h_lay = h->lay;
   std::vector<double> slice((h->slice_words + FE_ENV_EXTRA_WORDS) / 2 + 8);
   for (int env = 0; env < h->N; ++env) {
     if (mask && !mask[env]) continue;
     FeEnv e;
     fe_env_bind(&e, (float*)slice.data(), h->dm, h->ds, &h->cfg, h->opt, h->st, h->es, env, h->slice_words);
-    fe_load(&e.w, h->st, env);
+    fe_load(e.w, h->st, env);
     fe_env_load_groups(&e);
     fe_env_reset_one(&e);
     fe_env_store_groups(&e);
-    fe_store(&e.w, h->st, env);
+    fe_store(e.w, h->st, env);
   }
   return 0;
 }
 static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, void*) {
+  fe_h_lay = h->lay;
   std::vector<double> slice((h->slice_words + FE_ENV_EXTRA_WORDS) / 2 + 8);
   for (int env = 0; env < h->N; ++env) {
     FeEnv e;
     fe_env_bind(&e, (float*)slice.data(), h->dm, h->ds, &h->cfg, h->opt, h->st, h->es, env, h->slice_words);
-    fe_load(&e.w, h->st, env);
+    fe_load(e.w, h->st, env);
     fe_env_load_groups(&e);
     fe_env_step_one(&e, actions, reward, done, info);
     fe_env_store_groups(&e);
-    fe_store(&e.w, h->st, env);
+    fe_store(e.w, h->st, env);
   }
   return 0;
 }
