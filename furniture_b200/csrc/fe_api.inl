@@ -121,7 +121,7 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   ALLOC(s.eq_data, float, 7 * m.neq, "eq_data", true) ALLOC(s.contype, int, m.ngeom, "geom_contype", true) ALLOC(s.conaff, int, m.ngeom, "geom_conaffinity", true)
   ALLOC(s.eq_active, int, m.neq, "eq_active", true) ALLOC(s.bias, float, m.nr, "qfrc_bias", false)
   ALLOC(s.lpos, float, 3 * m.nlink, "link_xpos", false) ALLOC(s.lquat, float, 4 * m.nlink, "link_xquat", false) ALLOC(s.lvel, float, 6 * m.nlink, "link_vel", false)
-  ALLOC(s.touch, int, m.npart, "touch", false) ALLOC(s.flags, int, 1, "flags", true) ALLOC(s.ncon, int, 1, "ncon", false) ALLOC(s.niter, int, 1, "niter", false) ALLOC(s.stats, int, 12, "stats", false) ALLOC(s.order, int, 1, "order", true)
+  ALLOC(s.touch, int, m.npart, "touch", false) ALLOC(s.flags, int, 1, "flags", true) ALLOC(s.ncon, int, 1, "ncon", false) ALLOC(s.niter, int, 1, "niter", false) ALLOC(s.stats, int, FE_NSTAT, "stats", false) ALLOC(s.order, int, 1, "order", true)
   FeDebug& d = h->dbg;
   ALLOC(d.Mr, float, m.nr * m.nr, "dbg_Mr", false) ALLOC(d.fs, float, m.nv, "dbg_fs", false) ALLOC(d.as, float, m.nv, "dbg_as", false)
   ALLOC(d.linert, float, 10 * m.nlink, "dbg_linert", false) ALLOC(d.x, float, m.nv, "dbg_x", false) ALLOC(d.fc, float, m.nv, "dbg_fc", false)

@@ -67,32 +67,27 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState s
   fe_store(e.w, st, env);
 }
 
-// stable partition of the env ids: envs whose last step used the coupled (FULL) solver scope first.  One block.
+// Orders the env ids by the work their last step took (cycles in the five phases, barrier waits excluded), heaviest
+// first: the warps of a block run in lockstep, so a block is as slow as its slowest env, and blocks of like envs launched
+// heaviest-first pack the SMs best.  Counting sort on a log-scale key (16 buckets per octave); one block.
+#define FE_ORDER_BUCKETS 256
 __global__ void __launch_bounds__(1024) fe_order_kernel(int N, const int* __restrict__ stats, int* __restrict__ order) {
-  __shared__ int wsum[32], wsum2[32], tot_slow, base_slow, base_fast;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int cnt = 0;
-  for (int e = tid; e < N; e += 1024) cnt += stats[(size_t)e * 12 + 1] > 0;
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) wsum[wid] = cnt;
+  __shared__ int hist[FE_ORDER_BUCKETS], start[FE_ORDER_BUCKETS];
+  const int tid = threadIdx.x;
+  if (tid < FE_ORDER_BUCKETS) hist[tid] = 0;
   __syncthreads();
-  if (tid == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; tot_slow = t; base_slow = 0; base_fast = 0; }
+  auto bucket_of = [&](int e) {
+    const int* st = stats + (size_t)e * FE_NSTAT;
+    const float work = (float)st[4] + (float)st[5] + (float)st[6] + (float)st[7] + (float)st[8]; // cycles / 16
+    int b = (int)(16.f * log2f(fmaxf(work, 1.f) * (1.f / 1024.f)));                               // bucket 0 below 16k cycles
+    b = b < 0 ? 0 : (b > FE_ORDER_BUCKETS - 1 ? FE_ORDER_BUCKETS - 1 : b);
+    return FE_ORDER_BUCKETS - 1 - b; // heaviest first
+  };
+  for (int e = tid; e < N; e += 1024) atomicAdd(&hist[bucket_of(e)], 1);
   __syncthreads();
-  for (int c0 = 0; c0 < N; c0 += 1024) {
-    const int e = c0 + tid;
-    const int valid = e < N, slow = valid && stats[(size_t)e * 12 + 1] > 0, fast = valid && !slow;
-    const unsigned ms = __ballot_sync(0xffffffffu, slow), mf = __ballot_sync(0xffffffffu, fast);
-    if (lane == 0) { wsum[wid] = __popc(ms); wsum2[wid] = __popc(mf); }
-    __syncthreads();
-    int ps = 0, pf = 0;
-    for (int i = 0; i < wid; ++i) { ps += wsum[i]; pf += wsum2[i]; }
-    const unsigned lt = (1u << lane) - 1u;
-    if (slow) order[base_slow + ps + __popc(ms & lt)] = e;
-    if (fast) order[tot_slow + base_fast + pf + __popc(mf & lt)] = e;
-    __syncthreads();
-    if (tid == 0) { int a = 0, b = 0; for (int i = 0; i < 32; ++i) { a += wsum[i]; b += wsum2[i]; } base_slow += a; base_fast += b; }
-    __syncthreads();
-  }
+  if (tid == 0) { int acc = 0; for (int b = 0; b < FE_ORDER_BUCKETS; ++b) { start[b] = acc; acc += hist[b]; } }
+  __syncthreads();
+  for (int e = tid; e < N; e += 1024) order[atomicAdd(&start[bucket_of(e)], 1)] = e;
 }
 
 __global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* cs, const double* sn,

@@ -12,7 +12,7 @@ struct FeState {
   int *touch;                                                           // [N][npart]
   int *flags, *ncon, *niter;                                            // [N]
   int* order;                                                           // [N] slot -> env: envs that were in the coupled (slow) solver scope last step come first and share blocks
-  int* stats;                                                           // [N][12] per call: -, coupled substeps, robot-block solves, coop iterations, cycles/16 in kin, collide, assemble, solve, integrate, barrier wait
+  int* stats;                                                           // [N][FE_NSTAT] per call: parts-solver iterations, coupled substeps, robot-block solves, coop iterations, cycles/16 in kin, collide, assemble, solve, integrate, all barriers, robot-contact substeps, slowest solve, wait at each of the 5 barriers
 };
 
 // optional dump of one forward pass (all nullable, [N][dim])
@@ -27,7 +27,7 @@ FE_FN void fe_load(FeWarp* w, const FeState& s, int env) {
   LANES_BEGIN
     LD(qpos, m->nq) LD(qvel, m->nv) LD(warm, m->nv) LD(ctrl, m->nu) LD(qfrc_applied, m->nr) LD(gravcomp, m->npart) LD(eq_data, 7 * m->neq)
     LD(contype, m->ngeom) LD(conaff, m->ngeom) LD(eq_active, m->neq) LD(bias, m->nr)
-    if (lane < 16) w->u()[lane] = 0;
+    w->u()[lane] = 0; // 4 + FE_NSTAT <= 32
   LANES_END
 #undef LD
 }
@@ -39,7 +39,7 @@ FE_FN void fe_store(FeWarp* w, const FeState& s, int env) {
     ST(contype, m->ngeom) ST(conaff, m->ngeom) ST(eq_active, m->neq)
     ST(bias, m->nr) ST(lpos, 3 * m->nlink) ST(lquat, 4 * m->nlink) ST(lvel, 6 * m->nlink) ST(touch, m->npart)
     if (lane == 0) { s.flags[env] |= w->u()[2]; s.ncon[env] = w->u()[0]; s.niter[env] = w->u()[3]; }
-    if (lane < 12) s.stats[(size_t)env * 12 + lane] = w->u()[4 + lane];
+    if (lane < FE_NSTAT) s.stats[(size_t)env * FE_NSTAT + lane] = w->u()[4 + lane];
   LANES_END
 #undef ST
 }

@@ -50,6 +50,7 @@ struct FeOpt {
   X(contype) X(conaff) X(eq_active) X(cand) X(touch) X(c_geom) X(c_link) X(c_state) X(c_kind) X(plist) X(first) X(iscr) X(colmap) X(skip) \
   X(u) /* uniform scalars: [0]=ncon [1]=ncand [2]=flags [3]=niter [4..]=per-call statistics */
 
+#define FE_NSTAT 28 /* per-call statistics kept behind the 4 scalars of u */
 struct FeLayout {
 #define X(f) int f;
   FE_SLICE_F(X) FE_SLICE_I(X)
@@ -68,7 +69,7 @@ __constant__ FeLayout fe_c_lay;
 #define FE_LAY fe_h_lay
 #endif
 
-#define FE_WARP_HDR_WORDS 16
+#define FE_WARP_HDR_WORDS 10
 struct FeWarp { // header at word 0 of the slice
   const fe_model* m;
   FeOpt opt;
@@ -102,7 +103,7 @@ FE_BOTH int fe_layout_build(FeLayout* L, const fe_model* m, const FeOpt& opt) {
   CARVE(l_sign, nr) CARVE(l_aref, nr) CARVE(l_D, nr) CARVE(l_jar, nr) CARVE(l_jv, nr) CARVE(l_f, nr)
   CARVE(x, nv) CARVE(Ma, nv) CARVE(grad, nv) CARVE(search, nv) CARVE(Mv, nv) CARVE(fc, nv)
   L->Jc = L->lcrb; /* composite inertias (smooth stage) vs row staging of fe_build_H */
-  CARVE(scr, 2 * 32) CARVE(first, nv) CARVE(skip, nv) CARVE(iscr, 32) CARVE(colmap, 32) CARVE(u, 16)
+  CARVE(scr, 2 * 32) CARVE(first, nv) CARVE(skip, nv) CARVE(iscr, 32) CARVE(colmap, 32) CARVE(u, 4 + FE_NSTAT)
   // H (solver) and the collision scratch (geom poses, candidate list) are never live together: overlay them
   const int hwords = fe_tri(nv), cwords = 12 * ng + FE_MAXCAND;
   L->H = o; L->gpos = o; L->gmat = o + 3 * ng; L->cand = o + 12 * ng;
@@ -221,6 +222,54 @@ FE_FN void fe_chol_solve(FeWarp* w, const float* L, const int* first, int n, flo
       for (int j = fk + lane; j < k; j += 32) tmp[j] -= L[fe_tri(k) + j] * xk;
     LANES_END
   }
+}
+
+// The same factorisation and solves done by lane 0 alone in tight loops (envelope-aware, 4 partial sums to pipeline the
+// slice loads).  For the small systems of this solver the barriers and per-column regions of the cooperative version cost
+// more than the arithmetic they spread, and a short loop stays in the instruction cache.
+FE_FN bool fe_chol_serial(FeWarp* w, float* H, const int* first, int n, const int* skip, float* x, float* tmp) {
+  int ok = 1;
+  LANES_BEGIN
+    if (lane == 0) {
+      for (int i = 0; i < n; ++i) {
+        if (skip && skip[i]) continue;
+        float* Hi = H + fe_tri(i);
+        const int fi = first[i];
+        for (int k = fi; k <= i; ++k) {
+          if (skip && skip[k]) { continue; }
+          const float* Hk = H + fe_tri(k);
+          const int fk = first[k], j0 = fi > fk ? fi : fk;
+          float s0 = Hi[k], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = j0;
+          for (; j + 3 < k; j += 4) { s0 -= Hi[j] * Hk[j]; s1 -= Hi[j + 1] * Hk[j + 1]; s2 -= Hi[j + 2] * Hk[j + 2]; s3 -= Hi[j + 3] * Hk[j + 3]; }
+          for (; j < k; ++j) s0 -= Hi[j] * Hk[j];
+          float s = (s0 + s1) + (s2 + s3);
+          if (k < i) Hi[k] = s / Hk[k];
+          else { if (!(s > 1e-30f)) { ok = 0; s = 1e-30f; } Hi[i] = sqrtf(s); }
+        }
+      }
+      // forward: tmp = L^-1 x
+      for (int i = 0; i < n; ++i) {
+        if (skip && skip[i]) continue;
+        const float* Hi = H + fe_tri(i);
+        float s0 = x[i], s1 = 0.f;
+        int j = first[i];
+        for (; j + 1 < i; j += 2) { s0 -= Hi[j] * tmp[j]; s1 -= Hi[j + 1] * tmp[j + 1]; }
+        for (; j < i; ++j) s0 -= Hi[j] * tmp[j];
+        tmp[i] = (s0 + s1) / Hi[i];
+      }
+      // backward: x = L^-T tmp (column sweep)
+      for (int i = n - 1; i >= 0; --i) {
+        if (skip && skip[i]) continue;
+        const float* Hi = H + fe_tri(i);
+        const float xi = tmp[i] / Hi[i];
+        x[i] = xi;
+        for (int j = first[i]; j < i; ++j) tmp[j] -= Hi[j] * xi;
+      }
+      w->iscr()[0] = ok;
+    }
+  LANES_END
+  return w->iscr()[0] != 0;
 }
 
 // Free-part blocks whose rows start at their own block and that no later row reaches are independent 6x6 systems:
@@ -1046,8 +1095,56 @@ FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
   }
 }
 
-// H = M_z + J^T W J  (packed lower, skyline first[])
-FE_FN void fe_build_H(FeWarp* w) {
+// 3x3 weight of an active contact: diag(D) in the quadratic zone (st 1), cone Hessian in the middle zone (st 2)
+FE_HD void fe_contact_weight(const FeWarp* w, int c, int st, float* W) {
+  const float mu = w->c_mu()[c], fr = w->c_fric()[c], D0 = w->c_D()[2 * c], D1 = w->c_D()[2 * c + 1];
+  if (st == 1) { W[0] = D0; W[4] = D1; W[8] = D1; W[1] = W[2] = W[3] = W[5] = W[6] = W[7] = 0.f; }
+  else {
+    const float N = w->c_jar()[3 * c] * mu, U[3] = {N, w->c_jar()[3 * c + 1] * fr, w->c_jar()[3 * c + 2] * fr};
+    const float T = sqrtf(U[1] * U[1] + U[2] * U[2]), Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+    const float sc[3] = {mu, fr, fr};
+    float HU[9];
+    HU[0] = Dm;
+    for (int a = 1; a < 3; ++a) HU[a] = HU[3 * a] = -Dm * mu * U[a] / T;
+    for (int a = 1; a < 3; ++a)
+      for (int b = 1; b < 3; ++b) HU[3 * a + b] = Dm * mu * mu * U[a] * U[b] / (T * T) - Dm * NmT * mu * ((a == b ? 1.f : 0.f) / T - U[a] * U[b] / (T * T * T));
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) W[3 * a + b] = sc[a] * HU[3 * a + b] * sc[b];
+  }
+}
+// column z of the 3-row contact Jacobian (contact frame; B side minus A side), z in solver coordinates
+FE_HD void fe_contact_col(const FeWarp* w, int c, int z, int A, int B, float* col) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, nrl = m->nrlink;
+  const float* F = w->c_frame() + 9 * c;
+  const float* p = w->c_pos() + 3 * c;
+  col[0] = col[1] = col[2] = 0.f;
+  if (z < 0) return;
+  if (z < nr) {
+    const float sg = ((B >= 0 && B < nrl && ((m->link_ancmask[B] >> z) & 1)) ? 1.f : 0.f) - ((A >= 0 && A < nrl && ((m->link_ancmask[A] >> z) & 1)) ? 1.f : 0.f);
+    if (sg != 0.f) {
+      float r[3], t[3], v[3];
+      v3sub(r, p, m->robot_ref);
+      v3cross(t, w->S() + 6 * z, r);
+      v3add(v, w->S() + 6 * z + 3, t);
+      for (int k = 0; k < 3; ++k) col[k] = sg * v3dot(F + 3 * k, v);
+    }
+  } else {
+    const int part = (z - nr) / 6, jj = (z - nr) % 6, l = nrl + part;
+    const float sg = l == B ? 1.f : (l == A ? -1.f : 0.f);
+    if (sg != 0.f) {
+      float r[3];
+      v3sub(r, p, w->lpos() + 3 * l);
+      for (int k = 0; k < 3; ++k) {
+        if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * t[jj]; }
+        else col[k] = sg * F[3 * k + (jj - 3)];
+      }
+    }
+  }
+}
+
+// H = M_z + J^T W J  (packed lower, skyline first[]).  With regs set, the contacts that couple moving blocks are left to
+// fe_newton_regs (they are added to the register-resident rows there).
+FE_FN void fe_build_H(FeWarp* w, bool regs = false) {
   const fe_model* m = w->m;
   const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u()[0], ne = w->fast ? 0 : m->neq;
   const bool fast = w->fast != 0;
@@ -1130,30 +1227,15 @@ FE_FN void fe_build_H(FeWarp* w) {
     }
   }
   // remaining contacts, one at a time: dof-space rows staged in Jc (3 x ncols), then the ncols x ncols outer product
-  for (int c = 0; c < ncon; ++c) {
+  for (int c = 0; c < ncon && !regs; ++c) {
     const int st = w->c_state()[c];
     if (st == 0 || ((fast || grouped) && w->c_kind()[c] == 0)) continue;
     const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
     const bool robot = (A >= 0 && A < nrl) || (B >= 0 && B < nrl);
     const int partA = A >= nrl ? A - nrl : -1, partB = B >= nrl ? B - nrl : -1;
     const int ncols = (robot ? nr : 0) + (partA >= 0 ? 6 : 0) + (partB >= 0 ? 6 : 0);
-    // 3x3 weight: diag(D) in the quadratic zone, cone Hessian in the middle zone
     float W[9];
-    {
-      const float mu = w->c_mu()[c], fr = w->c_fric()[c], D0 = w->c_D()[2 * c], D1 = w->c_D()[2 * c + 1];
-      if (st == 1) { W[0] = D0; W[4] = D1; W[8] = D1; W[1] = W[2] = W[3] = W[5] = W[6] = W[7] = 0.f; }
-      else {
-        const float N = w->c_jar()[3 * c] * mu, U[3] = {N, w->c_jar()[3 * c + 1] * fr, w->c_jar()[3 * c + 2] * fr};
-        const float T = sqrtf(U[1] * U[1] + U[2] * U[2]), Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
-        const float sc[3] = {mu, fr, fr};
-        float HU[9];
-        HU[0] = Dm;
-        for (int a = 1; a < 3; ++a) HU[a] = HU[3 * a] = -Dm * mu * U[a] / T;
-        for (int a = 1; a < 3; ++a)
-          for (int b = 1; b < 3; ++b) HU[3 * a + b] = Dm * mu * mu * U[a] * U[b] / (T * T) - Dm * NmT * mu * ((a == b ? 1.f : 0.f) / T - U[a] * U[b] / (T * T * T));
-        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) W[3 * a + b] = sc[a] * HU[3 * a + b] * sc[b];
-      }
-    }
+    fe_contact_weight(w, c, st, W);
     LANES_BEGIN
       const int j = lane;
       if (j < ncols) {
@@ -1208,7 +1290,7 @@ FE_FN void fe_build_H(FeWarp* w) {
       }
     LANES_END
   }
-  // welds: 6 rows over the two parts' 12 columns, diagonal weights
+  // welds: 6 rows over the two parts' 12 columns, diagonal weights (column map staged in iscr: colmap holds the active-dof list)
   for (int e = 0; e < ne; ++e) {
     if (!w->eq_active()[e]) continue;
     const int A = m->eq_link1[e], B = m->eq_link2[e];
@@ -1232,7 +1314,7 @@ FE_FN void fe_build_H(FeWarp* w) {
             for (int k = 0; k < 3; ++k) col[k] = sg * w->w_G()[9 * e + 3 * k + jj];
           }
           w->Jc()[j] = col[0]; w->Jc()[32 + j] = col[1]; w->Jc()[64 + j] = col[2];
-          w->colmap()[j] = nr + 6 * ((sideA ? A : B) - nrl) + jj;
+          w->iscr()[j] = nr + 6 * ((sideA ? A : B) - nrl) + jj;
         }
       LANES_END
       LANES_BEGIN
@@ -1244,7 +1326,7 @@ FE_FN void fe_build_H(FeWarp* w) {
           float v = 0.f;
           for (int a = 0; a < 3; ++a) v += w->w_D()[6 * e + 3 * half + a] * w->Jc()[32 * a + i] * w->Jc()[32 * a + j];
           if (v != 0.f) {
-            int zi = w->colmap()[i], zj = w->colmap()[j];
+            int zi = w->iscr()[i], zj = w->iscr()[j];
             if (zi < zj) { int t = zi; zi = zj; zj = t; }
             w->H()[fe_tri(zi) + zj] += v;
           }
@@ -1254,8 +1336,101 @@ FE_FN void fe_build_H(FeWarp* w) {
   }
 }
 
+// Newton direction of the active dofs (robot + coupled parts, at most 32): lane i owns row i of the lower triangle of H in
+// registers.  Rows start from the slice copy (M_z, static-world contacts of the parts, welds, limits); the contacts that
+// couple blocks are added as rank-3 updates whose columns travel by shuffle; the factorisation is right-looking
+// (pivot column broadcast by shuffle), the two triangular solves likewise.  No slice traffic, no barriers inside.
+// NMAX (16 / 24 / 32) bounds the unrolled loops; rows and columns beyond nA are padded with the identity.
+template <int NMAX>
+FE_FN void fe_newton_regs(FeWarp* w, int nA) {
+  const int ncon = w->u()[0];
+  FE_PRIVA(float, row_, NMAX);
+  FE_PRIV(float, c0_); FE_PRIV(float, c1_); FE_PRIV(float, c2_); FE_PRIV(float, t0_); FE_PRIV(float, t1_); FE_PRIV(float, t2_);
+  FE_PRIV(float, s0_); FE_PRIV(float, s1_); FE_PRIV(float, s2_); FE_PRIV(float, b_); FE_PRIV(float, dinv_); FE_PRIV(float, q_);
+  FE_PRIV(int, z_); FE_PRIV(int, bad_);
+  REGS_BEGIN
+    const int i = lane, zi = i < nA ? w->colmap()[i] : -1;
+    PV(z_) = zi; PV(bad_) = 0; PV(dinv_) = 1.f;
+    const int fi = zi >= 0 ? w->first()[zi] : 0;
+    const float* Hi = w->H() + fe_tri(zi >= 0 ? zi : 0);
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      float v = (j == i) ? 1.f : 0.f;
+      if (j <= i && i < nA) { const int zj = w->colmap()[j]; v = zj >= fi ? Hi[zj] : 0.f; }
+      PV(row_)[j] = v;
+    }
+    PV(b_) = zi >= 0 ? -w->grad()[zi] : 0.f;
+  REGS_END
+  for (int c = 0; c < ncon; ++c) {
+    const int st = w->c_state()[c];
+    if (st == 0 || w->c_kind()[c] == 0) continue;
+    const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
+    float W[9];
+    fe_contact_weight(w, c, st, W);
+    REGS_BEGIN
+      float col[3];
+      fe_contact_col(w, c, PV(z_), A, B, col);
+      PV(c0_) = col[0]; PV(c1_) = col[1]; PV(c2_) = col[2];
+      PV(t0_) = W[0] * col[0] + W[1] * col[1] + W[2] * col[2];
+      PV(t1_) = W[3] * col[0] + W[4] * col[1] + W[5] * col[2];
+      PV(t2_) = W[6] * col[0] + W[7] * col[1] + W[8] * col[2];
+    REGS_END
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      FE_SHFL(s0_, c0_, j); FE_SHFL(s1_, c1_, j); FE_SHFL(s2_, c2_, j);
+      REGS_BEGIN PV(row_)[j] += PV(t0_) * PV(s0_) + PV(t1_) * PV(s1_) + PV(t2_) * PV(s2_); REGS_END
+    }
+  }
+  // right-looking Cholesky
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    FE_SHFLA(s0_, row_, k, k);
+    REGS_BEGIN
+      float pk = PV(s0_);
+      if (!(pk > 1e-30f)) { PV(bad_) = 1; pk = 1e-30f; }
+      const float lkk = sqrtf(pk), inv = 1.0f / lkk;
+      const float lik = lane > k ? PV(row_)[k] * inv : (lane == k ? lkk : 0.f);
+      PV(row_)[k] = lik;
+      PV(q_) = lik;
+      if (lane == k) PV(dinv_) = inv;
+    REGS_END
+#pragma unroll
+    for (int j = k + 1; j < NMAX; ++j) {
+      FE_SHFL(s1_, q_, j);
+      REGS_BEGIN PV(row_)[j] -= PV(q_) * PV(s1_); REGS_END
+    }
+  }
+  // forward substitution: y = L^-1 b
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    REGS_BEGIN PV(q_) = PV(b_) * PV(dinv_); REGS_END
+    FE_SHFL(s0_, q_, k);
+    REGS_BEGIN
+      if (lane > k) PV(b_) -= PV(row_)[k] * PV(s0_);
+      else if (lane == k) PV(b_) = PV(s0_);
+    REGS_END
+  }
+  // backward substitution: x = L^-T y (column k of L is spread over the lanes: one butterfly sum per unknown)
+#pragma unroll
+  for (int k = NMAX - 1; k >= 0; --k) {
+    REGS_BEGIN PV(q_) = (lane > k && lane < NMAX) ? PV(row_)[k] * PV(b_) : 0.f; REGS_END
+    FE_WSUM(q_);
+    REGS_BEGIN if (lane == k) PV(b_) = (PV(b_) - PV(q_)) * PV(dinv_); REGS_END
+  }
+  LANES_BEGIN
+    if (PV(z_) >= 0) w->search()[PV(z_)] = PV(b_);
+    if (PV(bad_) && lane == 0) w->u()[2] |= 4;
+  LANES_END
+}
+
 // cooperative Newton solve over the active scope (w->nact dofs; in FAST scope the free parts are excluded)
 FE_FN void fe_solve_coop(FeWarp* w) {
+#if FE_DEVICE_BUILD
+#define FE_CTICK(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) w->u()[slot] += (int)((t1_ - t0_) >> 4); t0_ = t1_; }
+  long long t0_ = clock64();
+#else
+#define FE_CTICK(slot)
+#endif
   const fe_model* m = w->m;
   const int nr = m->nr, nrl = m->nrlink, np = w->fast ? 0 : m->npart, nv = w->nact, ncon = w->u()[0], ne = w->fast ? 0 : m->neq;
   const bool fast = w->fast != 0;
@@ -1306,11 +1481,44 @@ FE_FN void fe_solve_coop(FeWarp* w) {
       fe_mul_J(w, w->x(), w->c_jar(), w->w_jar(), w->l_jar(), true);
     }
   }
+  // active set of the register-resident Newton direction: the robot dofs plus every part that a constraint couples to
+  // another moving block (decided by constraint kind, not by contact state, so it is fixed for the whole solve); the
+  // remaining parts are independent 6x6 blocks (skip[] = 1)
+  LANES_BEGIN
+    if (lane < np) {
+      const int l = nrl + lane;
+      int cpl = w->plist()[9 * lane + 8] > 8;
+      for (int c = 0; c < ncon && !cpl; ++c)
+        if (w->c_kind()[c] == 2) { const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1; cpl = A == l || B == l; }
+      for (int e = 0; e < ne && !cpl; ++e) if (w->eq_active()[e]) cpl = m->eq_link1[e] == l || m->eq_link2[e] == l;
+      w->iscr()[lane] = cpl;
+    }
+  LANES_END
+  LANES_BEGIN
+    if (lane == 0) {
+      int n = 0;
+      for (int d = 0; d < nr; ++d) { w->skip()[d] = 0; if (n < 32) w->colmap()[n] = d; ++n; }
+      for (int p = 0; p < np; ++p) {
+        const int cpl = w->iscr()[p];
+        for (int k = 0; k < 6; ++k) { w->skip()[nr + 6 * p + k] = !cpl; if (cpl) { if (n < 32) w->colmap()[n] = nr + 6 * p + k; ++n; } }
+      }
+      w->iscr()[32 - 1] = n;
+    }
+  LANES_END
+  const int nA = w->iscr()[31];
+#if !FE_DEVICE_BUILD
+  if (getenv("FE_DEBUG_SOLVE")) { printf("  coupled flags:"); for (int p = 0; p < np; ++p) printf(" %d(cnt %d)", w->iscr()[p], w->plist()[9 * p + 8]); printf(" kinds:"); for (int c = 0; c < ncon; ++c) printf(" %d", w->c_kind()[c]); printf("\n"); }
+#endif
+  bool regs = nA <= 32 && !(w->opt.lockstep & 512);
+  const bool serial = (w->opt.lockstep & 256) != 0;
+  if (!fast) for (int p = 0; p < m->npart; ++p) if (w->plist()[9 * p + 8] > 8) regs = false; // needs the grouped static-contact path
   int iter = 0;
   float cost = 0.f, impr = 0.f;
+  FE_CTICK(25)
   for (;;) {
     const float ccost = fe_update(w);
     fe_mul_JT(w, w->fc());
+    FE_CTICK(26)
     LANES_BEGIN
       float s = 0.f, gsq = 0.f;
       for (int i = lane; i < nv; i += 32) {
@@ -1325,7 +1533,7 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     const float gauss = fe_sum32(w->scr()), gnorm = sqrtf(fe_sum32(w->scr() + 32));
     cost = gauss + ccost;
 #if !FE_DEVICE_BUILD
-    if (getenv("FE_DEBUG_SOLVE")) printf("  coop it %d nact %d cost %.9g gnorm %.4g scaled-g %.3g impr %.3g\n", iter, nv, cost, gnorm, scale * gnorm, scale * impr);
+    if (getenv("FE_DEBUG_SOLVE")) printf("  coop it %d nact %d active %d regs %d cost %.9g gnorm %.4g scaled-g %.3g impr %.3g\n", iter, nv, nA, (int)regs, cost, gnorm, scale * gnorm, scale * impr);
 #endif
     if (!(cost == cost)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END break; }
     // MuJoCo stops on scale*(oldcost - cost) < tol; in fp32 that difference of two large costs is round-off, so the
@@ -1333,17 +1541,33 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     if (iter > 0) { if (scale * impr < w->opt.tolerance || scale * gnorm < w->opt.tolerance) break; }
     else if (scale * gnorm < w->opt.tolerance) break;
     if (iter >= w->opt.newton_iters) break;
-    fe_build_H(w);
-    const int* skip = nullptr;
-    if (!fast) { // FULL scope: independent part blocks are factored / solved by one lane each
-      fe_mark_indep_blocks(w, w->first(), w->skip());
-      fe_chol_blocks(w, w->H(), w->skip());
-      skip = w->skip();
+    FE_CTICK(27)
+    fe_build_H(w, regs);
+    FE_CTICK(28)
+    if (regs) {
+      LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search()[i] = -w->grad()[i]; LANES_END
+      if (!fast) { fe_chol_blocks(w, w->H(), w->skip()); fe_solve_blocks(w, w->H(), w->skip(), w->search()); }
+      FE_CTICK(29)
+      if (nA <= 16) fe_newton_regs<16>(w, nA); else if (nA <= 24) fe_newton_regs<24>(w, nA); else fe_newton_regs<32>(w, nA);
+    } else {
+      const int* skip = nullptr;
+      if (!fast) { // FULL scope: independent part blocks are factored / solved by one lane each
+        fe_mark_indep_blocks(w, w->first(), w->skip());
+        fe_chol_blocks(w, w->H(), w->skip());
+        skip = w->skip();
+      }
+      LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search()[i] = -w->grad()[i]; LANES_END
+      if (skip) fe_solve_blocks(w, w->H(), skip, w->search());
+      if (serial) {
+        if (!fe_chol_serial(w, w->H(), w->first(), nv, skip, w->search(), w->Mv())) { LANES_BEGIN if (lane == 0) w->u()[2] |= 4; LANES_END }
+        FE_CTICK(29)
+      } else {
+        if (!fe_chol(w, w->H(), w->first(), nv, skip)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 4; LANES_END }
+        FE_CTICK(29)
+        fe_chol_solve(w, w->H(), w->first(), nv, w->search(), w->Mv(), skip);
+      }
     }
-    if (!fe_chol(w, w->H(), w->first(), nv, skip)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 4; LANES_END }
-    LANES_BEGIN for (int i = lane; i < nv; i += 32) w->search()[i] = -w->grad()[i]; LANES_END
-    if (skip) fe_solve_blocks(w, w->H(), skip, w->search());
-    fe_chol_solve(w, w->H(), w->first(), nv, w->search(), w->Mv(), skip);
+    FE_CTICK(30)
     fe_mul_M(w, w->search(), w->Mv());
     fe_mul_J(w, w->search(), w->c_jv(), w->w_jv(), w->l_jv(), false);
     LANES_BEGIN
@@ -1368,6 +1592,7 @@ FE_FN void fe_solve_coop(FeWarp* w) {
       if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
       alpha = next;
     }
+    FE_CTICK(31)
     if (!(alpha > 0.f)) break;
     impr = -0.5f * alpha * p1_0;
     LANES_BEGIN
@@ -1384,6 +1609,8 @@ FE_FN void fe_solve_coop(FeWarp* w) {
   fe_update(w);
   fe_mul_JT(w, w->fc());
   LANES_BEGIN if (lane == 0) { if (iter > w->u()[3]) w->u()[3] = iter; w->u()[7] += iter; } LANES_END
+  FE_CTICK(25)
+#undef FE_CTICK
 }
 
 
@@ -1587,6 +1814,120 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
   }
 }
 
+// ---- FAST scope, robot block whose only constraint rows are joint limits (no robot contact): the common case, e.g. the
+// gripper fingers resting on their stops.  Lane d owns dof d in registers; M products are 9 shuffles + 9 FMAs per lane,
+// reductions are xor-butterflies, only the small Cholesky goes through the slice.  Same cost function, stop tests and exact
+// line search as fe_solve_coop.
+FE_FN void fe_solve_robot_limits(FeWarp* w) {
+  const fe_model* m = w->m;
+  const int nr = m->nr, maxit = w->opt.newton_iters, maxls = w->opt.ls_iters;
+  const float tol = w->opt.tolerance, scale = 1.0f / (m->meaninertia * (float)(m->nv > 1 ? m->nv : 1));
+  FE_PRIV(float, x_); FE_PRIV(float, as_); FE_PRIV(float, sg_); FE_PRIV(float, ar_); FE_PRIV(float, D_);
+  FE_PRIV(float, t_); FE_PRIV(float, u_); FE_PRIV(float, r_); FE_PRIV(float, s_); FE_PRIV(float, Ms_); FE_PRIV(float, f_);
+  FE_PRIV(float, a_); FE_PRIV(float, b_); FE_PRIV(int, any_);
+  REGS_BEGIN
+    const bool on = lane < nr;
+    PV(x_) = on ? w->warm()[lane] : 0.f; PV(as_) = on ? w->as()[lane] : 0.f;
+    PV(sg_) = on ? w->l_sign()[lane] : 0.f; PV(ar_) = on ? w->l_aref()[lane] : 0.f; PV(D_) = on ? w->l_D()[lane] : 0.f;
+    PV(any_) = PV(sg_) != 0.f;
+    PV(u_) = PV(x_) - PV(as_); PV(r_) = 0.f; PV(f_) = 0.f;
+  REGS_END
+  if (!FE_ANY(any_)) {
+    LANES_BEGIN if (lane < nr) { w->x()[lane] = PV(as_); w->fc()[lane] = 0.f; w->l_f()[lane] = 0.f; } LANES_END
+    return;
+  }
+  LANES_BEGIN if (lane == 0) w->u()[6] += 1; LANES_END
+  // r = M (warm - as); warm start kept only if it is cheaper than the unconstrained acceleration
+  for (int j = 0; j < nr; ++j) {
+    FE_SHFL(t_, u_, j);
+    REGS_BEGIN if (lane < nr) PV(r_) += w->Mr()[lane * nr + j] * PV(t_); REGS_END
+  }
+  REGS_BEGIN
+    const float jw = PV(sg_) * PV(x_) - PV(ar_), js = PV(sg_) * PV(as_) - PV(ar_);
+    PV(a_) = 0.5f * PV(u_) * PV(r_) + ((PV(sg_) != 0.f && jw < 0.f) ? 0.5f * PV(D_) * jw * jw : 0.f);
+    PV(b_) = (PV(sg_) != 0.f && js < 0.f) ? 0.5f * PV(D_) * js * js : 0.f;
+  REGS_END
+  FE_WSUM(a_); FE_WSUM(b_);
+  if (!(FE_UNI(a_) <= FE_UNI(b_))) { REGS_BEGIN PV(x_) = PV(as_); PV(r_) = 0.f; REGS_END }
+  int iter = 0;
+  float impr = 0.f;
+  for (;;) {
+    REGS_BEGIN
+      const float jar = PV(sg_) * PV(x_) - PV(ar_);
+      const bool act = PV(sg_) != 0.f && jar < 0.f;
+      PV(f_) = act ? -PV(D_) * jar : 0.f;
+      const float gi = PV(r_) - PV(sg_) * PV(f_);
+      PV(t_) = gi;       // gradient
+      PV(a_) = gi * gi;
+      PV(u_) = act ? PV(D_) : 0.f;
+    REGS_END
+    FE_WSUM(a_);
+    const float gnorm = sqrtf(FE_UNI(a_));
+    if (!(gnorm == gnorm)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END break; }
+    if (iter > 0) { if (scale * impr < tol || scale * gnorm < tol) break; }
+    else if (scale * gnorm < tol) break;
+    if (iter >= maxit) break;
+    LANES_BEGIN
+      if (lane < nr) {
+        float* Hi = w->H() + fe_tri(lane);
+        for (int j = 0; j <= lane; ++j) Hi[j] = w->Mr()[lane * nr + j];
+        Hi[lane] += PV(u_);
+        w->search()[lane] = -PV(t_);
+        w->first()[lane] = 0;
+      }
+    LANES_END
+    if (!fe_chol(w, w->H(), w->first(), nr)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 4; LANES_END }
+    fe_chol_solve(w, w->H(), w->first(), nr, w->search(), w->Mv());
+    REGS_BEGIN PV(s_) = lane < nr ? w->search()[lane] : 0.f; PV(Ms_) = 0.f; REGS_END
+    for (int j = 0; j < nr; ++j) {
+      FE_SHFL(t_, s_, j);
+      REGS_BEGIN if (lane < nr) PV(Ms_) += w->Mr()[lane * nr + j] * PV(t_); REGS_END
+    }
+    REGS_BEGIN PV(a_) = PV(s_) * PV(r_); PV(b_) = 0.5f * PV(s_) * PV(Ms_); REGS_END
+    FE_WSUM(a_); FE_WSUM(b_);
+    const float g1 = FE_UNI(a_), g2 = FE_UNI(b_);
+    // exact line search: safeguarded Newton on p'(alpha) = 0
+    float p1 = 0.f, p2 = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f, p1_0 = 0.f;
+    bool fail = false;
+    for (int ls = -1; ls < maxls; ++ls) {
+      REGS_BEGIN
+        const float jv = PV(sg_) * PV(s_), xx = PV(sg_) * PV(x_) - PV(ar_) + alpha * jv;
+        const bool act = PV(sg_) != 0.f && xx < 0.f;
+        PV(a_) = act ? PV(D_) * xx * jv : 0.f;
+        PV(b_) = act ? PV(D_) * jv * jv : 0.f;
+      REGS_END
+      FE_WSUM(a_); FE_WSUM(b_);
+      p1 = g1 + 2.f * g2 * alpha + FE_UNI(a_);
+      p2 = 2.f * g2 + FE_UNI(b_);
+      if (ls < 0) {
+        if (!(p1 < 0.f) || !(p2 > 0.f)) { fail = true; break; }
+        p1_0 = p1;
+        alpha = -p1 / p2;
+        continue;
+      }
+      if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
+      if (p1 < 0.f) lo = alpha; else hi = alpha;
+      float next = alpha - p1 / p2;
+      if (hi > 0.f && !(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      if (hi < 0.f && !(next > lo)) next = 2.f * alpha;
+      if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
+      alpha = next;
+    }
+    if (fail || !(alpha > 0.f)) break;
+    impr = -0.5f * alpha * p1_0;
+    REGS_BEGIN PV(x_) += alpha * PV(s_); PV(r_) += alpha * PV(Ms_); REGS_END
+    ++iter;
+  }
+  LANES_BEGIN
+    if (lane < nr) {
+      const float jar = PV(sg_) * PV(x_) - PV(ar_);
+      const float f = (PV(sg_) != 0.f && jar < 0.f) ? -PV(D_) * jar : 0.f;
+      w->x()[lane] = PV(x_); w->fc()[lane] = PV(sg_) * f; w->l_f()[lane] = f; w->l_jar()[lane] = jar;
+    }
+    if (lane == 0) { if (iter > w->u()[3]) w->u()[3] = iter; w->u()[7] += iter; }
+  LANES_END
+}
+
 // mj_fwdConstraint: FAST scope when no constraint couples two moving blocks (free parts solved 8 lanes per part, robot
 // block cooperatively), FULL scope otherwise
 FE_FN void fe_solve(FeWarp* w) {
@@ -1594,7 +1935,8 @@ FE_FN void fe_solve(FeWarp* w) {
   const int ncon = w->u()[0], ne = m->neq, np = m->npart, nrl = m->nrlink;
   LANES_BEGIN
     int coupled = 0;
-    for (int c = lane; c < ncon; c += 32) coupled |= w->c_kind()[c] == 2;
+    int rcon = 0;
+    for (int c = lane; c < ncon; c += 32) { coupled |= w->c_kind()[c] == 2; rcon |= w->c_kind()[c] == 1; }
     for (int e = lane; e < ne; e += 32) coupled |= w->eq_active()[e] != 0;
     if (lane < np) { // contacts of part `lane` against the static world (at most 8 handled by the grouped solver)
       const int l = nrl + lane;
@@ -1609,21 +1951,32 @@ FE_FN void fe_solve(FeWarp* w) {
       w->plist()[9 * lane + 8] = cnt;
       if (cnt > 8) coupled = 1;
     }
-    w->iscr()[lane] = coupled;
+    w->iscr()[lane] = coupled | (rcon << 1);
     if (lane == 0) w->u()[3] = 0;
   LANES_END
-  const bool coupled = fe_ballot32(w->iscr()) != 0u;
-  w->fast = coupled ? 0 : 1;
-  w->nact = coupled ? m->nv : m->nr;
+  bool coupled = false, robot_contact = false;
+  { // one ballot for both flags
+    LANES_BEGIN w->colmap()[lane] = w->iscr()[lane] & 2; w->iscr()[lane] &= 1; LANES_END
+    coupled = fe_ballot32(w->iscr()) != 0u;
+    robot_contact = fe_ballot32(w->colmap()) != 0u;
+#if !FE_DEVICE_BUILD
+    if (getenv("FE_NO_RLIM")) robot_contact = true;
+#endif
+  }
+  LANES_BEGIN if (lane == 0) { w->fast = coupled ? 0 : 1; w->nact = coupled ? m->nv : m->nr; } LANES_END
   if (!coupled) {
     fe_solve_parts_grouped(w);
     LANES_BEGIN
-      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] = 0; }
+      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] += mx; if (robot_contact) w->u()[14] += 1; }
     LANES_END
-  } else { LANES_BEGIN if (lane == 0) { w->u()[4] = 1; w->u()[5] += 1; } LANES_END }
+    if (!robot_contact) {
+      fe_solve_robot_limits(w);
+      LANES_BEGIN if (lane == 0) { w->fast = 0; w->nact = m->nv; } LANES_END
+      return;
+    }
+  } else { LANES_BEGIN if (lane == 0) w->u()[5] += 1; LANES_END }
   fe_solve_coop(w);
-  w->fast = 0;
-  w->nact = m->nv;
+  LANES_BEGIN if (lane == 0) { w->fast = 0; w->nact = m->nv; } LANES_END
 }
 
 // ---------------------------------------------------------------- mj_Euler + mj_advance
@@ -1708,14 +2061,21 @@ FE_FN void fe_substep_lockstep(FeWarp* w) {
   const int ls = w->opt.lockstep;
 #if FE_DEVICE_BUILD
 #define FE_TICK(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) w->u()[slot] += (int)((t1_ - t0_) >> 4); t0_ = t1_; }
+#define FE_TICKB(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) { w->u()[13] += (int)((t1_ - t0_) >> 4); w->u()[slot] += (int)((t1_ - t0_) >> 4); } t0_ = t1_; }
   long long t0_ = clock64();
 #else
 #define FE_TICK(slot)
+#define FE_TICKB(slot)
 #endif
-  if (ls & 1) { FE_BLOCK_SYNC; } FE_TICK(13) fe_kin_smooth(w); FE_TICK(8)
-  if (ls & 2) { FE_BLOCK_SYNC; } FE_TICK(13) fe_collide(w); FE_TICK(9)
-  if (ls & 4) { FE_BLOCK_SYNC; } FE_TICK(13) fe_assemble(w); FE_TICK(10)
-  if (ls & 8) { FE_BLOCK_SYNC; } FE_TICK(13) fe_solve(w); FE_TICK(11)
-  if (ls & 16) { FE_BLOCK_SYNC; } FE_TICK(13) fe_integrate(w); FE_TICK(12)
+  if (ls & 1) { FE_BLOCK_SYNC; } FE_TICKB(16) fe_kin_smooth(w); FE_TICK(8)
+  if (ls & 2) { FE_BLOCK_SYNC; } FE_TICKB(17) fe_collide(w); FE_TICK(9)
+  if (ls & 4) { FE_BLOCK_SYNC; } FE_TICKB(18) fe_assemble(w); FE_TICK(10)
+  if (ls & 8) { FE_BLOCK_SYNC; } FE_TICKB(19) fe_solve(w);
+#if FE_DEVICE_BUILD
+  { const int d_ = (int)((clock64() - t0_) >> 4); if ((threadIdx.x & 31u) == 0 && d_ > w->u()[15]) w->u()[15] = d_; }
+#endif
+  FE_TICK(11)
+  if (ls & 16) { FE_BLOCK_SYNC; } FE_TICKB(20) fe_integrate(w); FE_TICK(12)
 #undef FE_TICK
+#undef FE_TICKB
 }

@@ -18,6 +18,9 @@
 #define FE_BOTH __host__ __device__ __forceinline__
 #define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u); {
 #define LANES_END } } __syncwarp();
+// register-only region: touches lane-private values only, so no barrier is needed after it
+#define REGS_BEGIN { const int lane = (int)(threadIdx.x & 31u); {
+#define REGS_END } }
 #define FE_LDG(p) __ldg(p)
 #define FE_SYNC __syncwarp()
 #define FE_BLOCK_SYNC __syncthreads()
@@ -29,6 +32,8 @@
 #define FE_BOTH static inline
 #define LANES_BEGIN for (int lane = 0; lane < 32; ++lane) { {
 #define LANES_END } }
+#define REGS_BEGIN LANES_BEGIN
+#define REGS_END LANES_END
 #define FE_LDG(p) (*(p))
 #define FE_SYNC ((void)0)
 #define FE_BLOCK_SYNC ((void)0)
@@ -97,6 +102,10 @@ FE_HD int fe_popc(unsigned x) {
 #define FE_GSUM8_ARR(name, n) do { _Pragma("unroll") for (int k_ = 0; k_ < (n); ++k_) FE_GSUM8(name[k_]); } while (0)
 #define FE_GSUM8_ARRN(name, n, used) do { _Pragma("unroll") for (int k_ = 0; k_ < (used); ++k_) FE_GSUM8(name[k_]); } while (0)
 #define FE_ANY(name) (__any_sync(0xffffffffu, (name) != 0) != 0)
+#define FE_WSUM(name) do { _Pragma("unroll") for (int o_ = 16; o_ > 0; o_ >>= 1) name += __shfl_xor_sync(0xffffffffu, name, o_); } while (0)
+#define FE_SHFL(dst, src, idx) do { dst = __shfl_sync(0xffffffffu, src, (idx)); } while (0)
+#define FE_SHFLA(dst, arr, elem, idx) do { dst = __shfl_sync(0xffffffffu, arr[elem], (idx)); } while (0)
+#define FE_UNI(name) (name) /* a private value known to be equal on all lanes (after a collective) */
 #else
 #define FE_PRIV(T, name) T name[32]
 #define FE_PRIVA(T, name, n) T name[32][n]
@@ -113,6 +122,17 @@ static inline void fe_emu_gsum8(float* a, int stride) {
 #define FE_GSUM8_ARRN(name, n, used) do { for (int k_ = 0; k_ < (used); ++k_) fe_emu_gsum8(&name[0][k_], (n)); } while (0)
 static inline bool fe_emu_any(const int* a) { for (int i = 0; i < 32; ++i) if (a[i]) return true; return false; }
 #define FE_ANY(name) fe_emu_any(name)
+static inline void fe_emu_wsum(float* a) {
+  for (int o = 16; o > 0; o >>= 1) {
+    float t[32];
+    for (int i = 0; i < 32; ++i) t[i] = a[i] + a[i ^ o];
+    for (int i = 0; i < 32; ++i) a[i] = t[i];
+  }
+}
+#define FE_WSUM(name) fe_emu_wsum(name)
+#define FE_SHFL(dst, src, idx) do { const float t_shfl_ = src[(idx)]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = t_shfl_; } while (0)
+#define FE_SHFLA(dst, arr, elem, idx) do { const float t_shfl_ = arr[(idx)][(elem)]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = t_shfl_; } while (0)
+#define FE_UNI(name) (name[0])
 #endif
 
 // ---------------------------------------------------------------- small vector math (fp32)

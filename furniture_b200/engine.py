@@ -197,7 +197,7 @@ class Engine:
         self._chk(self.L.fe_field_dim(self.h, name.encode(), C.byref(d), C.byref(e)))
         return d.value, e.value
 
-    _INT = {"geom_contype", "geom_conaffinity", "eq_active", "touch", "flags", "ncon", "niter", "stats", "con_geom", "con_state", "group", "site_connected",
+    _INT = {"order", "geom_contype", "geom_conaffinity", "eq_active", "touch", "flags", "ncon", "niter", "stats", "con_geom", "con_state", "group", "site_connected",
             "num_connected", "prev_num_connected", "touched", "picked", "episode_length", "done"}
 
     def get(self, name):

@@ -125,6 +125,33 @@ def test_trajectory_matches_oracle(sawyer_model, gpu):
 
 
 @pytest.mark.parametrize("gpu", BACKENDS)
+def test_joint_limit_rows_match_oracle(sawyer_model, gpu):
+    """gripper fingers pushed past their stops (the everyday case: the robot block then has joint-limit rows only and is
+    solved by the dedicated per-lane Newton): constrained robot acceleration equals the oracle's."""
+    m = sawyer_model
+    eng = make_engine(m, 4, gpu)
+    sim = OracleSim(m)
+    qs, vs, cs, ref = [], [], [], []
+    for seed in range(4):
+        q = settled_state(m, seed, dz=0.01)
+        rng = np.random.RandomState(seed)
+        q[7] = 0.0210 + 0.0002 * seed   # range (-0.0115, 0.020833)
+        q[8] = -0.0211                  # range (-0.020833, 0.0115)
+        v = rng.normal(size=m.nv) * 0.3
+        c = rng.uniform(-1, 1, m.nu)
+        sim.qpos[:] = q; sim.qvel[:] = v; sim.ctrl[:] = c; sim.qacc_warmstart[:] = 0
+        sim.forward()
+        qs.append(q); vs.append(v); cs.append(c); ref.append(sim.qacc[:9].copy())
+    eng.set("qpos", np.array(qs)); eng.set("qvel", np.array(vs)); eng.set("ctrl", np.array(cs)); eng.set("qacc_warmstart", np.zeros((4, m.nv)))
+    eng.forward()
+    x = eng.get("dbg_x")
+    st = eng.get("stats")
+    for e in range(4):
+        assert st[e][2] == 1  # the robot block did need a constraint solve
+        assert np.abs(x[e][:9] - ref[e]).max() < 2e-5 * max(1.0, np.abs(ref[e]).max()), (e, np.abs(x[e][:9] - ref[e]).max())
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
 def test_weld_constraint_matches_oracle(gpu):
     from oracle.assembly_oracle import rel_pose
 

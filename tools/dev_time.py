@@ -38,3 +38,22 @@ it = st[:, 3]
 print("coop iterations per env-step: max %d  p99 %d  p90 %d ; envs > 200: %d" % (it.max(), np.percentile(it, 99), np.percentile(it, 90), (it > 200).sum()))
 worst = np.argsort(-cyc[:, 3])[:5]
 for e in worst: print("  env %d: solve cycles %.0f coupled %d robot-solves %d coop-iters %d ncon %d" % (e, cyc[e, 3], st[e, 1], st[e, 2], st[e, 3], info[e, 4].item()))
+print("parts-solver iterations (max over parts, summed over 50 substeps): mean %.1f p99 %d max %d" % (st[:,0].mean(), np.percentile(st[:,0],99), st[:,0].max()))
+print("FAST substeps with a robot contact (general solver on the robot block): mean %.2f, envs with any %.1f%%, hist" % (st[:,10].mean(), 100*(st[:,10]>0).mean()), np.bincount(np.minimum(st[:,10],50)//10, minlength=6))
+mx = st[:,11].astype(np.float64)*16
+print("slowest single-substep solve per env: mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f cycles" % (mx.mean(), np.percentile(mx,50), np.percentile(mx,90), np.percentile(mx,99), mx.max()))
+fastenv = st[:,1]==0
+print("never-coupled envs: solve cycles mean %.0f p50 %.0f p90 %.0f p99 %.0f ; slowest substep p50 %.0f p90 %.0f p99 %.0f" % (cyc[fastenv,3].mean(), np.percentile(cyc[fastenv,3],50), np.percentile(cyc[fastenv,3],90), np.percentile(cyc[fastenv,3],99), np.percentile(mx[fastenv],50), np.percentile(mx[fastenv],90), np.percentile(mx[fastenv],99)))
+print("never-coupled envs with no robot contact: solve mean %.0f, with: %.0f" % (cyc[fastenv & (st[:,10]==0),3].mean(), cyc[fastenv & (st[:,10]>0),3].mean()))
+bw = st[:, 12:17].astype(np.float64) * 16
+print("wait at the barrier before kin/collide/assemble/solve/integrate: mean", " ".join("%.0f" % v for v in bw.mean(0)), "| never-coupled:", " ".join("%.0f" % v for v in bw[fastenv].mean(0)))
+heavy = np.argsort(-cyc[:, 3])[:40]
+cc = st[heavy][:, 21:28].astype(np.float64) * 16
+its = st[heavy][:, 3].astype(np.float64)
+print("40 heaviest envs: coop iterations mean %.0f; cycles per iteration: setup+final %.0f update+JT %.0f grad/stop %.0f build_H %.0f chol %.0f chol_solve %.0f M,J,linesearch %.0f" % ((its.mean(),) + tuple((cc.sum(0) / its.sum()))))
+if os.environ.get("FE_DUMP_STATS"):
+    order_k = eng.get("order")  # the order the next step will run with
+    act = (torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1) * scale
+    eng.env_step_dev(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+    torch.cuda.synchronize()
+    np.savez(os.environ["FE_DUMP_STATS"], st_prev=st, order=order_k, st=eng.get("stats"))
