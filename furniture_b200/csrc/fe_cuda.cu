@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #define PLAT_IS_CUDA 1
 struct fe_handle;
@@ -34,16 +35,16 @@ extern __shared__ float fe_smem[];
 __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_sim_kernel(FeState s, const fe_model* __restrict__ m, FeOpt opt, int nsub, int mode, FeDebug dbg, int slice_words) {
   const int wib = threadIdx.x >> 5, slot = blockIdx.x * (blockDim.x >> 5) + wib;
   if (slot >= s.N) return;
-  const int env = s.order[slot];
+  const int env = slot;
   fe_run_env(s, m, opt, env, nsub, mode, fe_smem + (size_t)wib * slice_words, dbg);
 }
 
 __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_step_kernel(FeState st, FeEnvState es, const fe_model* __restrict__ m, const fe_scene* __restrict__ sc,
                                                          fe_config cfg, FeOpt opt, const float* __restrict__ actions, float* reward, uint8_t* done,
-                                                         int32_t* info, int slice_words) {
+                                                         int32_t* info, int slice_words, const int* __restrict__ slots) {
   const int wib = threadIdx.x >> 5, slot = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (slot >= st.N) return;
-  const int env = st.order[slot];
+  const int env = slots[slot];
+  if (env < 0) return; // unused slot (blocks of heavy envs are deliberately left partly empty)
   FeEnv e;
   fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
   fe_load(e.w, st, env);
@@ -67,12 +68,16 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState s
   fe_store(e.w, st, env);
 }
 
-// Orders the env ids by the work their last step took (cycles in the five phases, barrier waits excluded), heaviest
-// first: the warps of a block run in lockstep, so a block is as slow as its slowest env, and blocks of like envs launched
-// heaviest-first pack the SMs best.  Counting sort on a log-scale key (16 buckets per octave); one block.
+// Packs the envs into blocks for the next step from the work their last step took (cycles in the five phases, barrier
+// waits excluded).  Counting sort on a log-scale key (16 buckets per octave), heaviest first, into order[].  The warps of a
+// block run in lockstep, so like goes with like; and the few envs far heavier than the median (robot coupled to a part:
+// the big Newton solve) bound the whole step by their own latency, which is lowest when few warps share the SM: they get
+// blocks with only `heavy_k` of the warp slots used, launched first, while the light envs fill the other SMs.
 #define FE_ORDER_BUCKETS 256
-__global__ void __launch_bounds__(1024) fe_order_kernel(int N, const int* __restrict__ stats, int* __restrict__ order) {
-  __shared__ int hist[FE_ORDER_BUCKETS], start[FE_ORDER_BUCKETS];
+#define FE_EXTRA_BLOCKS 148
+__global__ void __launch_bounds__(1024) fe_order_kernel(int N, const int* __restrict__ stats, int* __restrict__ order, int* __restrict__ slots, int nslots,
+                                                        int wpb, int heavy_k, int heavy_shift) {
+  __shared__ int hist[FE_ORDER_BUCKETS], start[FE_ORDER_BUCKETS], nheavy;
   const int tid = threadIdx.x;
   if (tid < FE_ORDER_BUCKETS) hist[tid] = 0;
   __syncthreads();
@@ -85,9 +90,24 @@ __global__ void __launch_bounds__(1024) fe_order_kernel(int N, const int* __rest
   };
   for (int e = tid; e < N; e += 1024) atomicAdd(&hist[bucket_of(e)], 1);
   __syncthreads();
-  if (tid == 0) { int acc = 0; for (int b = 0; b < FE_ORDER_BUCKETS; ++b) { start[b] = acc; acc += hist[b]; } }
+  if (tid == 0) {
+    int acc = 0, med = -1;
+    for (int b = 0; b < FE_ORDER_BUCKETS; ++b) { start[b] = acc; acc += hist[b]; if (med < 0 && 2 * acc >= N) med = b; }
+    // heavy: at least heavy_shift buckets (sixteenths of an octave) above the median bucket
+    const int hb = med - heavy_shift; // last heavy bucket (buckets are in heaviest-first order)
+    const int H = (heavy_k > 0 && heavy_k < wpb && hb >= 0) ? start[hb] + hist[hb] : 0;
+    const int cap = heavy_k * FE_EXTRA_BLOCKS;
+    nheavy = H > cap ? cap : H;
+  }
   __syncthreads();
   for (int e = tid; e < N; e += 1024) order[atomicAdd(&start[bucket_of(e)], 1)] = e;
+  for (int i = tid; i < nslots; i += 1024) slots[i] = -1;
+  __syncthreads();
+  const int H = nheavy, HB = heavy_k > 0 ? (H + heavy_k - 1) / heavy_k : 0;
+  for (int r = tid; r < N; r += 1024) {
+    const int slot = r < H ? (r / heavy_k) * wpb + r % heavy_k : HB * wpb + (r - H);
+    slots[slot] = order[r];
+  }
 }
 
 __global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* cs, const double* sn,
@@ -106,7 +126,9 @@ __global__ void fe_is_aligned_kernel(int n, const double* p1, const double* m1, 
 struct CudaPlat {
   size_t smem_sim = 0, smem_env = 0;
   int wpb = 1;
-  int reorder = 1;
+  int reorder = 1, heavy_k = 7, heavy_shift = 18; // heavy: 2^(18/16) = 2.2x the median work; 7 of the 14 warp slots used
+  int* slots = nullptr;  // block slot -> env (or -1)
+  int nblocks = 0;
   float* pin_act = nullptr;
   unsigned char* pin_out = nullptr;
   size_t out_bytes = 0;
@@ -144,6 +166,15 @@ static int plat_prepare(fe_handle* h) {
   if (wpb < 1) return fail(h, -11, "model does not fit in shared memory");
   p->wpb = wpb;
   if (const char* e = getenv("FE_REORDER")) p->reorder = atoi(e);
+  if (const char* e = getenv("FE_HEAVY_K")) p->heavy_k = atoi(e);
+  if (const char* e = getenv("FE_HEAVY_SHIFT")) p->heavy_shift = atoi(e);
+  p->nblocks = (h->N + wpb - 1) / wpb + FE_EXTRA_BLOCKS;
+  {
+    std::vector<int> init((size_t)p->nblocks * wpb, -1);
+    for (int i = 0; i < h->N; ++i) init[i] = i;
+    CUDA_OK(cudaMalloc((void**)&p->slots, sizeof(int) * init.size()));
+    CUDA_OK(cudaMemcpy(p->slots, init.data(), sizeof(int) * init.size(), cudaMemcpyHostToDevice));
+  }
   p->smem_sim = (size_t)h->slice_words * 4 * wpb;
   p->smem_env = per_env * wpb;
   CUDA_OK(cudaFuncSetAttribute(fe_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sim));
@@ -162,6 +193,7 @@ static void plat_fini(fe_handle* h) {
   cudaDeviceSynchronize();
   if (p->pin_act) cudaFreeHost(p->pin_act);
   if (p->pin_out) cudaFreeHost(p->pin_out);
+  if (p->slots) cudaFree(p->slots);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
   h->plat = nullptr;
@@ -190,9 +222,9 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
   int rc = plat_prepare(h);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
-  fe_env_step_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words);
+  fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words, p->slots);
   CUDA_OK(cudaGetLastError());
-  if (p->reorder) fe_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->N, h->st.stats, h->st.order);
+  if (p->reorder) fe_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift);
   return 0;
 }
 static int plat_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
@@ -204,10 +236,10 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
   // the private stream does not order against work the caller issued on other streams (fe_sim_forward, fe_set_field ...)
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpyAsync(h->dev_act, p->pin_act, ab, cudaMemcpyHostToDevice, p->stream));
-  fe_env_step_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
-                                                            (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words);
+  fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
+                                                            (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words, p->slots);
   CUDA_OK(cudaGetLastError());
-  if (p->reorder) fe_order_kernel<<<1, 1024, 0, p->stream>>>(h->N, h->st.stats, h->st.order);
+  if (p->reorder) fe_order_kernel<<<1, 1024, 0, p->stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift);
   unsigned char* o = p->pin_out;
   CUDA_OK(cudaMemcpyAsync(o, h->es.obs, ob, cudaMemcpyDeviceToHost, p->stream));
   CUDA_OK(cudaMemcpyAsync(o + ob, h->dev_rew, rb, cudaMemcpyDeviceToHost, p->stream));
