@@ -76,14 +76,19 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_reset_kernel(FeState s
 #define FE_ORDER_BUCKETS 256
 #define FE_EXTRA_BLOCKS 148
 __global__ void __launch_bounds__(1024) fe_order_kernel(int N, const int* __restrict__ stats, int* __restrict__ order, int* __restrict__ slots, int nslots,
-                                                        int wpb, int heavy_k, int heavy_shift) {
+                                                        int wpb, int heavy_k, int heavy_shift, float* __restrict__ pred, float decay) {
   __shared__ int hist[FE_ORDER_BUCKETS], start[FE_ORDER_BUCKETS], nheavy;
   const int tid = threadIdx.x;
   if (tid < FE_ORDER_BUCKETS) hist[tid] = 0;
-  __syncthreads();
-  auto bucket_of = [&](int e) {
+  // predicted work of the next step: the last step's, but an env that was heavy a few steps ago is still suspect
+  for (int e = tid; e < N; e += 1024) {
     const int* st = stats + (size_t)e * FE_NSTAT;
     const float work = (float)st[4] + (float)st[5] + (float)st[6] + (float)st[7] + (float)st[8]; // cycles / 16
+    pred[e] = fmaxf(work, decay * pred[e]);
+  }
+  __syncthreads();
+  auto bucket_of = [&](int e) {
+    const float work = pred[e];
     int b = (int)(16.f * log2f(fmaxf(work, 1.f) * (1.f / 1024.f)));                               // bucket 0 below 16k cycles
     b = b < 0 ? 0 : (b > FE_ORDER_BUCKETS - 1 ? FE_ORDER_BUCKETS - 1 : b);
     return FE_ORDER_BUCKETS - 1 - b; // heaviest first
@@ -128,6 +133,8 @@ struct CudaPlat {
   int wpb = 1;
   int reorder = 1, heavy_k = 7, heavy_shift = 18; // heavy: 2^(18/16) = 2.2x the median work; 7 of the 14 warp slots used
   int* slots = nullptr;  // block slot -> env (or -1)
+  float* pred = nullptr; // per env: predicted work of the next step
+  float decay = 0.85f;
   int nblocks = 0;
   float* pin_act = nullptr;
   unsigned char* pin_out = nullptr;
@@ -172,6 +179,9 @@ static int plat_prepare(fe_handle* h) {
   {
     std::vector<int> init((size_t)p->nblocks * wpb, -1);
     for (int i = 0; i < h->N; ++i) init[i] = i;
+    if (const char* e = getenv("FE_PRED_DECAY")) p->decay = 0.01f * (float)atoi(e);
+    CUDA_OK(cudaMalloc((void**)&p->pred, sizeof(float) * (size_t)h->N));
+    CUDA_OK(cudaMemset(p->pred, 0, sizeof(float) * (size_t)h->N));
     CUDA_OK(cudaMalloc((void**)&p->slots, sizeof(int) * init.size()));
     CUDA_OK(cudaMemcpy(p->slots, init.data(), sizeof(int) * init.size(), cudaMemcpyHostToDevice));
   }
@@ -194,6 +204,7 @@ static void plat_fini(fe_handle* h) {
   if (p->pin_act) cudaFreeHost(p->pin_act);
   if (p->pin_out) cudaFreeHost(p->pin_out);
   if (p->slots) cudaFree(p->slots);
+  if (p->pred) cudaFree(p->pred);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
   h->plat = nullptr;
@@ -224,7 +235,7 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
   CudaPlat* p = (CudaPlat*)h->plat;
   fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words, p->slots);
   CUDA_OK(cudaGetLastError());
-  if (p->reorder) fe_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift);
+  if (p->reorder) fe_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift, p->pred, p->decay);
   return 0;
 }
 static int plat_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
@@ -239,7 +250,7 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
   fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->smem_env, p->stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, (const float*)h->dev_act, (float*)h->dev_rew,
                                                             (uint8_t*)h->dev_done, (int32_t*)h->dev_info, h->slice_words, p->slots);
   CUDA_OK(cudaGetLastError());
-  if (p->reorder) fe_order_kernel<<<1, 1024, 0, p->stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift);
+  if (p->reorder) fe_order_kernel<<<1, 1024, 0, p->stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift, p->pred, p->decay);
   unsigned char* o = p->pin_out;
   CUDA_OK(cudaMemcpyAsync(o, h->es.obs, ob, cudaMemcpyDeviceToHost, p->stream));
   CUDA_OK(cudaMemcpyAsync(o + ob, h->dev_rew, rb, cudaMemcpyDeviceToHost, p->stream));
