@@ -191,7 +191,7 @@ def run_ours(args):
         ev[k][0].record()
         env.step(acts[W + k])
         ev[k][1].record()
-        launches += 1
+        launches += 2  # fe_env_step_kernel + fe_order_kernel (block packing for the next step)
     barrier()
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]

@@ -152,6 +152,44 @@ def test_joint_limit_rows_match_oracle(sawyer_model, gpu):
 
 
 @pytest.mark.parametrize("gpu", BACKENDS)
+def test_grasped_part_coupled_solve_matches_oracle(sawyer_model, gpu):
+    """a leg pinched between the finger pads couples the robot block to a free part (FULL solver scope: cooperative Newton
+    with the register-resident direction for the coupled dofs, independent 6x6 blocks for the parts left on the floor):
+    constrained accelerations and a short trajectory follow the oracle."""
+    from oracle.ref_env import OracleFurnitureEnv
+    from test_env_parity import _grasp_and_align_state
+
+    m = sawyer_model
+    env = OracleFurnitureEnv(m)
+    env.reset()
+    q = _grasp_and_align_state(m, env)
+    qs = settled_state(m, 0, dz=0.0)
+    q2 = qs.copy()
+    q2[:9] = q[:9]       # robot pose of the grasp
+    q2[9:16] = q[9:16]   # leg 0 between the pads; the other parts rest on the floor
+    eng = make_engine(m, 2, gpu)
+    em = eng.em
+    sim = OracleSim(m)
+    v = np.random.RandomState(3).normal(size=m.nv) * 0.05
+    sim.qpos[:] = q2; sim.qvel[:] = v; sim.qacc_warmstart[:] = 0
+    sim.forward()
+    eng.set("qpos", q2); eng.set("qvel", v); eng.set("qacc_warmstart", np.zeros(m.nv))
+    eng.forward()
+    assert eng.get("stats")[0][1] == 1  # the coupled scope was taken
+    assert int(eng.get("ncon")[0][0]) == sim.ncon
+    _, _, xm = oracle_link_poses(sim, em)
+    zs = to_z(m, em, xm, sim.qacc)
+    x = eng.get("dbg_x")[0]
+    # stiff pinch (|qacc| ~ 5e2): 5e-5 relative on the coupled dofs
+    assert np.abs(x - zs).max() < 5e-5 * np.abs(zs).max(), np.abs(x - zs).max()
+    for _ in range(5):
+        sim.step()
+        eng.step(1)
+    assert np.abs(eng.get("qpos")[0] - sim.qpos).max() < 5e-6
+    assert np.abs(eng.get("qvel")[0] - sim.qvel).max() < 2e-3  # |qvel| ~ 1 after the pinch relaxes
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
 def test_weld_constraint_matches_oracle(gpu):
     from oracle.assembly_oracle import rel_pose
 
