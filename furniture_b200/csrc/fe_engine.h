@@ -133,6 +133,14 @@ FE_HD void fe_inert_sym6(float* A, const float* I, float diag_add) {
   A[10] = -hz; A[11] = 0.f; A[12] = hx; A[13] = 0.f; A[14] = m + diag_add;
   A[15] = hy; A[16] = -hx; A[17] = 0.f; A[18] = 0.f; A[19] = 0.f; A[20] = m + diag_add;
 }
+// A += the same matrix (for a Hessian accumulated in place on top of contact terms)
+FE_HD void fe_inert_sym6_add(float* A, const float* I) {
+  const float m = I[0], hx = I[1], hy = I[2], hz = I[3];
+  A[0] += I[4]; A[1] += I[7]; A[2] += I[5]; A[3] += I[8]; A[4] += I[9]; A[5] += I[6];
+  A[7] += hz; A[8] -= hy; A[9] += m;
+  A[10] -= hz; A[12] += hx; A[14] += m;
+  A[15] += hy; A[16] -= hx; A[20] += m;
+}
 FE_HD bool fe_chol6(float* A) {
   bool ok = true;
 #pragma unroll
@@ -1627,10 +1635,12 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
   const int nr = m->nr, nrl = m->nrlink, np = m->npart, maxit = w->opt.newton_iters, maxls = w->opt.ls_iters;
   const float tol = w->opt.tolerance;
   for (int pass = 0; pass * 4 < np; ++pass) {
+    // lane-private state that lives across regions is kept small (the Jacobian rows, the reduction buffer, the iterate):
+    // inertia, smooth force / acceleration and the contact's reference acceleration are re-read from the slice where used
     FE_PRIV(int, c_); FE_PRIV(int, part_); FE_PRIV(int, act_); FE_PRIV(int, iter_); FE_PRIV(int, lsact_);
-    FE_PRIVA(float, J_, 18); FE_PRIVA(float, par_, 7);
-    FE_PRIVA(float, I_, 10); FE_PRIVA(float, fs_, 6); FE_PRIVA(float, as_, 6); FE_PRIVA(float, x_, 6); FE_PRIVA(float, xw_, 6);
-    FE_PRIVA(float, acc_, 28); FE_PRIVA(float, sd_, 6); FE_PRIVA(float, Mx_, 6); FE_PRIVA(float, jx_, 3); FE_PRIVA(float, jv_, 3);
+    FE_PRIVA(float, J_, 18); FE_PRIVA(float, par_, 4); // par_: D0, D1, mu, friction scale
+    FE_PRIVA(float, x_, 6);
+    FE_PRIVA(float, acc_, 28); FE_PRIVA(float, sd_, 6); FE_PRIVA(float, jx_, 3); FE_PRIVA(float, jv_, 3);
     FE_PRIV(float, scale_); FE_PRIV(float, impr_); FE_PRIV(float, g1_); FE_PRIV(float, g2_); FE_PRIV(float, alpha_);
     FE_PRIV(float, lo_); FE_PRIV(float, hi_); FE_PRIV(float, p10_);
     LANES_BEGIN
@@ -1643,22 +1653,23 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
         const int cnt = w->plist()[9 * part + 8];
         if (cnt > 0) PV(act_) = 1;
         if (slot < cnt) PV(c_) = w->plist()[9 * part + slot];
-        for (int k = 0; k < 10; ++k) PV(I_)[k] = w->linert()[10 * l + k];
-        for (int k = 0; k < 6; ++k) { PV(fs_)[k] = w->fs()[z + k]; PV(as_)[k] = w->as()[z + k]; }
-        PV(scale_) = 1.0f / (3.f * PV(I_)[0] + PV(I_)[4] + PV(I_)[5] + PV(I_)[6]);
-        m3mulv(PV(xw_), w->lmat() + 9 * l, w->warm() + da + 3);
-        v3cpy(PV(xw_) + 3, w->warm() + da);
+        const float* I = w->linert() + 10 * l;
+        PV(scale_) = 1.0f / (3.f * I[0] + I[4] + I[5] + I[6]);
         const int c = PV(c_);
         if (c >= 0) {
+          float xw[6];
+          m3mulv(xw, w->lmat() + 9 * l, w->warm() + da + 3);
+          v3cpy(xw + 3, w->warm() + da);
           const int B_ = (w->c_link()[c] >> 8) - 1;
           fe_part_rows(w, c, l, B_ == l ? 1.f : -1.f, PV(J_));
-          PV(par_)[0] = w->c_aref()[3 * c]; PV(par_)[1] = w->c_aref()[3 * c + 1]; PV(par_)[2] = w->c_aref()[3 * c + 2];
-          PV(par_)[3] = w->c_D()[2 * c]; PV(par_)[4] = w->c_D()[2 * c + 1]; PV(par_)[5] = w->c_mu()[c]; PV(par_)[6] = w->c_fric()[c];
+          PV(par_)[0] = w->c_D()[2 * c]; PV(par_)[1] = w->c_D()[2 * c + 1]; PV(par_)[2] = w->c_mu()[c]; PV(par_)[3] = w->c_fric()[c];
           float f[3], cw = 0.f, cs = 0.f;
           const float* J = PV(J_);
           const float* q = PV(par_);
-          fe_cone(dot6(J, PV(xw_)) - q[0], dot6(J + 6, PV(xw_)) - q[1], dot6(J + 12, PV(xw_)) - q[2], q[5], q[6], q[3], q[4], f, &cw, nullptr);
-          fe_cone(dot6(J, PV(as_)) - q[0], dot6(J + 6, PV(as_)) - q[1], dot6(J + 12, PV(as_)) - q[2], q[5], q[6], q[3], q[4], f, &cs, nullptr);
+          const float* ar = w->c_aref() + 3 * c;
+          const float* as = w->as() + z;
+          fe_cone(dot6(J, xw) - ar[0], dot6(J + 6, xw) - ar[1], dot6(J + 12, xw) - ar[2], q[2], q[3], q[0], q[1], f, &cw, nullptr);
+          fe_cone(dot6(J, as) - ar[0], dot6(J + 6, as) - ar[1], dot6(J + 12, as) - ar[2], q[2], q[3], q[0], q[1], f, &cs, nullptr);
           PV(acc_)[0] = cw; PV(acc_)[1] = cs;
         }
       }
@@ -1666,11 +1677,14 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
     FE_GSUM8_ARRN(acc_, 28, 2);
     LANES_BEGIN
       if (PV(part_) >= 0) { // warm start vs unconstrained acceleration: keep the cheaper one
-        float Mx[6], cw = PV(acc_)[0];
-        inert_mulv(Mx, PV(I_), PV(xw_));
-        for (int k = 0; k < 6; ++k) cw += 0.5f * (Mx[k] - PV(fs_)[k]) * (PV(xw_)[k] - PV(as_)[k]);
+        const int l = nrl + PV(part_), z = nr + 6 * PV(part_), da = m->link_dadr[l];
+        float xw[6], Mx[6], cw = PV(acc_)[0];
+        m3mulv(xw, w->lmat() + 9 * l, w->warm() + da + 3);
+        v3cpy(xw + 3, w->warm() + da);
+        inert_mulv(Mx, w->linert() + 10 * l, xw);
+        for (int k = 0; k < 6; ++k) cw += 0.5f * (Mx[k] - w->fs()[z + k]) * (xw[k] - w->as()[z + k]);
         const bool use_warm = !(PV(acc_)[1] < cw) && (cw == cw);
-        for (int k = 0; k < 6; ++k) PV(x_)[k] = use_warm ? PV(xw_)[k] : PV(as_)[k];
+        for (int k = 0; k < 6; ++k) PV(x_)[k] = use_warm ? xw[k] : w->as()[z + k];
       }
     LANES_END
     for (int it = 0; it <= maxit; ++it) {
@@ -1682,18 +1696,20 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
         if (PV(act_) && c >= 0) {
           const float* J = PV(J_);
           const float* q = PV(par_);
+          const float* ar = w->c_aref() + 3 * c;
           float f[3], W[6], cc = 0.f;
-          const int st = fe_cone(dot6(J, PV(x_)) - q[0], dot6(J + 6, PV(x_)) - q[1], dot6(J + 12, PV(x_)) - q[2], q[5], q[6], q[3], q[4], f, &cc, W);
+          PV(jx_)[0] = dot6(J, PV(x_)) - ar[0]; PV(jx_)[1] = dot6(J + 6, PV(x_)) - ar[1]; PV(jx_)[2] = dot6(J + 12, PV(x_)) - ar[2];
+          const int st = fe_cone(PV(jx_)[0], PV(jx_)[1], PV(jx_)[2], q[2], q[3], q[0], q[1], f, &cc, W);
           if (st != 0) {
-            float WJ[18];
-            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { // column i of W J, then row i of the lower triangle of J^T W J (W symmetric)
               PV(acc_)[i] = -(J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2]);
-              WJ[i] = W[0] * J[i] + W[3] * J[6 + i] + W[4] * J[12 + i];
-              WJ[6 + i] = W[3] * J[i] + W[1] * J[6 + i] + W[5] * J[12 + i];
-              WJ[12 + i] = W[4] * J[i] + W[5] * J[6 + i] + W[2] * J[12 + i];
+              const float w0 = W[0] * J[i] + W[3] * J[6 + i] + W[4] * J[12 + i];
+              const float w1 = W[3] * J[i] + W[1] * J[6 + i] + W[5] * J[12 + i];
+              const float w2 = W[4] * J[i] + W[5] * J[6 + i] + W[2] * J[12 + i];
+#pragma unroll
+              for (int j = 0; j <= i; ++j) PV(acc_)[6 + i * (i + 1) / 2 + j] = w0 * J[j] + w1 * J[6 + j] + w2 * J[12 + j];
             }
-            for (int i = 0; i < 6; ++i)
-              for (int j = 0; j <= i; ++j) PV(acc_)[6 + i * (i + 1) / 2 + j] = J[i] * WJ[j] + J[6 + i] * WJ[6 + j] + J[12 + i] * WJ[12 + j];
           }
           PV(acc_)[27] = cc;
         }
@@ -1702,11 +1718,13 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
       // gradient, Hessian, convergence test, Newton direction (identical in the 8 lanes of a group)
       LANES_BEGIN
         if (PV(act_)) {
-          float g[6], H[21], gsq = 0.f;
-          inert_mulv(PV(Mx_), PV(I_), PV(x_));
-          fe_inert_sym6(H, PV(I_), 0.f);
-          for (int k = 0; k < 6; ++k) { g[k] = PV(Mx_)[k] - PV(fs_)[k] + PV(acc_)[k]; gsq += g[k] * g[k]; }
-          for (int k = 0; k < 21; ++k) H[k] += PV(acc_)[6 + k];
+          const int l = nrl + PV(part_), z = nr + 6 * PV(part_);
+          const float* I = w->linert() + 10 * l;
+          float g[6], Mx[6], gsq = 0.f;
+          float* H = PV(acc_) + 6; // the group-summed J^T W J becomes the Hessian in place
+          inert_mulv(Mx, I, PV(x_));
+          fe_inert_sym6_add(H, I);
+          for (int k = 0; k < 6; ++k) { Mx[k] -= w->fs()[z + k]; g[k] = Mx[k] + PV(acc_)[k]; gsq += g[k] * g[k]; }
           const float gnorm = sqrtf(gsq);
           bool stop = false;
           if (!(gnorm == gnorm)) { stop = true; if ((lane & 7) == 0) w->u()[2] |= 2; }
@@ -1719,12 +1737,12 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
             for (int k = 0; k < 6; ++k) PV(sd_)[k] = -g[k];
             fe_chol6_solve(H, PV(sd_));
             float Ms[6], g1 = 0.f, g2 = 0.f;
-            inert_mulv(Ms, PV(I_), PV(sd_));
-            for (int k = 0; k < 6; ++k) { g1 += PV(sd_)[k] * (PV(Mx_)[k] - PV(fs_)[k]); g2 += 0.5f * PV(sd_)[k] * Ms[k]; }
+            inert_mulv(Ms, I, PV(sd_));
+            for (int k = 0; k < 6; ++k) { g1 += PV(sd_)[k] * Mx[k]; g2 += 0.5f * PV(sd_)[k] * Ms[k]; }
             PV(g1_) = g1; PV(g2_) = g2; PV(alpha_) = 0.f; PV(lo_) = 0.f; PV(hi_) = -1.f; PV(lsact_) = 1;
             if (PV(c_) >= 0) {
               const float* J = PV(J_);
-              for (int k = 0; k < 3; ++k) { PV(jx_)[k] = dot6(J + 6 * k, PV(x_)) - PV(par_)[k]; PV(jv_)[k] = dot6(J + 6 * k, PV(sd_)); }
+              for (int k = 0; k < 3; ++k) PV(jv_)[k] = dot6(J + 6 * k, PV(sd_));
             }
           }
         }
@@ -1737,7 +1755,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
           float p1 = 0.f, p2 = 0.f;
           if (PV(lsact_) && PV(c_) >= 0) {
             const float* q = PV(par_);
-            const float al = PV(alpha_), mu = q[5], fr = q[6], D0 = q[3], D1 = q[4];
+            const float al = PV(alpha_), mu = q[2], fr = q[3], D0 = q[0], D1 = q[1];
             const float v0 = PV(jv_)[0], v1 = PV(jv_)[1], v2 = PV(jv_)[2];
             const float x0 = PV(jx_)[0] + al * v0, x1 = PV(jx_)[1] + al * v1, x2 = PV(jx_)[2] + al * v2;
             const float N = x0 * mu, U1 = x1 * fr, U2 = x2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
@@ -1794,8 +1812,9 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
       if (c >= 0) {
         const float* J = PV(J_);
         const float* q = PV(par_);
+        const float* ar = w->c_aref() + 3 * c;
         float f[3], dummy = 0.f;
-        const int st = fe_cone(dot6(J, PV(x_)) - q[0], dot6(J + 6, PV(x_)) - q[1], dot6(J + 12, PV(x_)) - q[2], q[5], q[6], q[3], q[4], f, &dummy, nullptr);
+        const int st = fe_cone(dot6(J, PV(x_)) - ar[0], dot6(J + 6, PV(x_)) - ar[1], dot6(J + 12, PV(x_)) - ar[2], q[2], q[3], q[0], q[1], f, &dummy, nullptr);
         w->c_state()[c] = st;
         for (int k = 0; k < 3; ++k) w->c_f()[3 * c + k] = f[k];
         for (int i = 0; i < 6; ++i) PV(acc_)[i] = J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2];
@@ -1807,7 +1826,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
       if (part >= 0 && (lane & 7) == 0) {
         const int z = nr + 6 * part;
         const bool any = w->plist()[9 * part + 8] > 0;
-        for (int k = 0; k < 6; ++k) { w->x()[z + k] = any ? PV(x_)[k] : PV(as_)[k]; w->fc()[z + k] = any ? PV(acc_)[k] : 0.f; }
+        for (int k = 0; k < 6; ++k) { w->x()[z + k] = any ? PV(x_)[k] : w->as()[z + k]; w->fc()[z + k] = any ? PV(acc_)[k] : 0.f; }
         w->iscr()[part] = PV(iter_);
       }
     LANES_END
