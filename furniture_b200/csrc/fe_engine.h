@@ -1634,17 +1634,34 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
   const fe_model* m = w->m;
   const int nr = m->nr, nrl = m->nrlink, np = m->npart, maxit = w->opt.newton_iters, maxls = w->opt.ls_iters;
   const float tol = w->opt.tolerance;
-  for (int pass = 0; pass * 4 < np; ++pass) {
+  // Lanes are handed out in units of 4: a part with up to 4 contacts against the static world takes one unit, one with 5-8
+  // takes an aligned pair of units; parts are placed in order until the 8 units are used up, the rest wait for the next pass
+  // (five parts with <= 4 contacts each, the resting state of this furniture, fit in one pass).
+  for (int p0 = 0; p0 < np;) {
+    int p_end = p0;
     // lane-private state that lives across regions is kept small (the Jacobian rows, the reduction buffer, the iterate):
     // inertia, smooth force / acceleration and the contact's reference acceleration are re-read from the slice where used
-    FE_PRIV(int, c_); FE_PRIV(int, part_); FE_PRIV(int, act_); FE_PRIV(int, iter_); FE_PRIV(int, lsact_);
+    FE_PRIV(int, c_); FE_PRIV(int, part_); FE_PRIV(int, act_); FE_PRIV(int, iter_); FE_PRIV(int, lsact_); FE_PRIV(int, wide_); FE_PRIV(int, lead_);
     FE_PRIVA(float, J_, 18); FE_PRIVA(float, par_, 4); // par_: D0, D1, mu, friction scale
     FE_PRIVA(float, x_, 6);
     FE_PRIVA(float, acc_, 28); FE_PRIVA(float, sd_, 6); FE_PRIVA(float, jx_, 3); FE_PRIVA(float, jv_, 3);
     FE_PRIV(float, scale_); FE_PRIV(float, impr_); FE_PRIV(float, g1_); FE_PRIV(float, g2_); FE_PRIV(float, alpha_);
     FE_PRIV(float, lo_); FE_PRIV(float, hi_); FE_PRIV(float, p10_);
     LANES_BEGIN
-      const int part = pass * 4 + (lane >> 3), slot = lane & 7;
+      int part = np, slot = 0;
+      PV(wide_) = 0; PV(lead_) = 0;
+      {
+        const int unit = lane >> 2;
+        int nu = 0, p = p0;
+        for (; p < np; ++p) {
+          const int need = w->plist()[9 * p + 8] > 4 ? 2 : 1;
+          if (need == 2 && (nu & 1)) ++nu;
+          if (nu + need > 8) break;
+          if (unit >= nu && unit < nu + need) { part = p; slot = (lane & 3) + 4 * (unit - nu); PV(wide_) = need == 2; PV(lead_) = (unit == nu) && (lane & 3) == 0; }
+          nu += need;
+        }
+        p_end = p;
+      }
       PV(part_) = part < np ? part : -1;
       PV(c_) = -1; PV(act_) = 0; PV(iter_) = 0; PV(impr_) = 0.f; PV(lsact_) = 0;
       PV(acc_)[0] = 0.f; PV(acc_)[1] = 0.f;
@@ -1674,7 +1691,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
         }
       }
     LANES_END
-    FE_GSUM8_ARRN(acc_, 28, 2);
+    FE_GSUMV_ARRN(acc_, 28, 2, PV_ALL(wide_));
     LANES_BEGIN
       if (PV(part_) >= 0) { // warm start vs unconstrained acceleration: keep the cheaper one
         const int l = nrl + PV(part_), z = nr + 6 * PV(part_), da = m->link_dadr[l];
@@ -1714,7 +1731,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
           PV(acc_)[27] = cc;
         }
       LANES_END
-      FE_GSUM8_ARR(acc_, 28);
+      FE_GSUMV_ARRN(acc_, 28, 28, PV_ALL(wide_));
       // gradient, Hessian, convergence test, Newton direction (identical in the 8 lanes of a group)
       LANES_BEGIN
         if (PV(act_)) {
@@ -1727,13 +1744,13 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
           for (int k = 0; k < 6; ++k) { Mx[k] -= w->fs()[z + k]; g[k] = Mx[k] + PV(acc_)[k]; gsq += g[k] * g[k]; }
           const float gnorm = sqrtf(gsq);
           bool stop = false;
-          if (!(gnorm == gnorm)) { stop = true; if ((lane & 7) == 0) w->u()[2] |= 2; }
+          if (!(gnorm == gnorm)) { stop = true; if (PV(lead_)) w->u()[2] |= 2; }
           else if (PV(iter_) > 0) stop = PV(scale_) * PV(impr_) < tol || PV(scale_) * gnorm < tol;
           else stop = PV(scale_) * gnorm < tol;
           if (PV(iter_) >= maxit) stop = true;
           if (stop) PV(act_) = 0;
           else {
-            if (!fe_chol6(H) && (lane & 7) == 0) w->u()[2] |= 4;
+            if (!fe_chol6(H) && PV(lead_)) w->u()[2] |= 4;
             for (int k = 0; k < 6; ++k) PV(sd_)[k] = -g[k];
             fe_chol6_solve(H, PV(sd_));
             float Ms[6], g1 = 0.f, g2 = 0.f;
@@ -1772,7 +1789,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
           }
           PV(acc_)[0] = p1; PV(acc_)[1] = p2;
         LANES_END
-        FE_GSUM8_ARRN(acc_, 28, 2);
+        FE_GSUMV_ARRN(acc_, 28, 2, PV_ALL(wide_));
         LANES_BEGIN
           if (PV(lsact_)) {
             const float al = PV(alpha_);
@@ -1820,16 +1837,17 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
         for (int i = 0; i < 6; ++i) PV(acc_)[i] = J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2];
       }
     LANES_END
-    FE_GSUM8_ARRN(acc_, 28, 6);
+    FE_GSUMV_ARRN(acc_, 28, 6, PV_ALL(wide_));
     LANES_BEGIN
       const int part = PV(part_);
-      if (part >= 0 && (lane & 7) == 0) {
+      if (part >= 0 && PV(lead_)) {
         const int z = nr + 6 * part;
         const bool any = w->plist()[9 * part + 8] > 0;
         for (int k = 0; k < 6; ++k) { w->x()[z + k] = any ? PV(x_)[k] : w->as()[z + k]; w->fc()[z + k] = any ? PV(acc_)[k] : 0.f; }
         w->iscr()[part] = PV(iter_);
       }
     LANES_END
+    p0 = p_end;
   }
 }
 

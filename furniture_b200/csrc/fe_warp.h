@@ -98,10 +98,15 @@ FE_HD int fe_popc(unsigned x) {
 #define FE_PRIV(T, name) T name
 #define FE_PRIVA(T, name, n) T name[n]
 #define PV(name) name
+#define PV_ALL(name) name /* the private value as a collective operand */
 #define FE_GSUM8(name) do { name += __shfl_xor_sync(0xffffffffu, name, 1); name += __shfl_xor_sync(0xffffffffu, name, 2); name += __shfl_xor_sync(0xffffffffu, name, 4); } while (0)
 #define FE_GSUM8_ARR(name, n) do { _Pragma("unroll") for (int k_ = 0; k_ < (n); ++k_) FE_GSUM8(name[k_]); } while (0)
 #define FE_GSUM8_ARRN(name, n, used) do { _Pragma("unroll") for (int k_ = 0; k_ < (used); ++k_) FE_GSUM8(name[k_]); } while (0)
 #define FE_ANY(name) (__any_sync(0xffffffffu, (name) != 0) != 0)
+// sums over the lane's 4-lane unit, or over its 8-lane pair of units where `wide` is set (per-lane flag, equal within a group)
+#define FE_GSUMV(name, wide) do { name += __shfl_xor_sync(0xffffffffu, name, 1); name += __shfl_xor_sync(0xffffffffu, name, 2); \
+    const float t_gs_ = __shfl_xor_sync(0xffffffffu, name, 4); if (wide) name += t_gs_; } while (0)
+#define FE_GSUMV_ARRN(name, n, used, wide) do { _Pragma("unroll") for (int k_ = 0; k_ < (used); ++k_) FE_GSUMV(name[k_], wide); } while (0)
 #define FE_WSUM(name) do { _Pragma("unroll") for (int o_ = 16; o_ > 0; o_ >>= 1) name += __shfl_xor_sync(0xffffffffu, name, o_); } while (0)
 #define FE_SHFL(dst, src, idx) do { dst = __shfl_sync(0xffffffffu, src, (idx)); } while (0)
 #define FE_SHFLA(dst, arr, elem, idx) do { dst = __shfl_sync(0xffffffffu, arr[elem], (idx)); } while (0)
@@ -110,6 +115,7 @@ FE_HD int fe_popc(unsigned x) {
 #define FE_PRIV(T, name) T name[32]
 #define FE_PRIVA(T, name, n) T name[32][n]
 #define PV(name) name[lane]
+#define PV_ALL(name) name
 static inline void fe_emu_gsum8(float* a, int stride) {
   for (int o = 1; o < 8; o <<= 1) {
     float t[32];
@@ -118,6 +124,14 @@ static inline void fe_emu_gsum8(float* a, int stride) {
   }
 }
 #define FE_GSUM8(name) fe_emu_gsum8(name, 1)
+static inline void fe_emu_gsumv(float* a, int stride, const int* wide) {
+  for (int o = 1; o < 8; o <<= 1) {
+    float t[32];
+    for (int i = 0; i < 32; ++i) t[i] = (o < 4 || wide[i]) ? a[i * stride] + a[(i ^ o) * stride] : a[i * stride];
+    for (int i = 0; i < 32; ++i) a[i * stride] = t[i];
+  }
+}
+#define FE_GSUMV_ARRN(name, n, used, wide) do { for (int k_ = 0; k_ < (used); ++k_) fe_emu_gsumv(&name[0][k_], (n), wide); } while (0)
 #define FE_GSUM8_ARR(name, n) do { for (int k_ = 0; k_ < (n); ++k_) fe_emu_gsum8(&name[0][k_], (n)); } while (0)
 #define FE_GSUM8_ARRN(name, n, used) do { for (int k_ = 0; k_ < (used); ++k_) fe_emu_gsum8(&name[0][k_], (n)); } while (0)
 static inline bool fe_emu_any(const int* a) { for (int i = 0; i < 32; ++i) if (a[i]) return true; return false; }
