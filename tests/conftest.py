@@ -35,3 +35,11 @@ def sawyer_model():
     from furniture_b200 import mjcf
 
     return mjcf.load_scene("Sawyer", "table_lack_0825")
+
+
+@pytest.fixture(scope="session")
+def swivel_model():
+    """Sawyer + swivel_chair_0700: cylinders, so cylinder-plane / cylinder-box / cylinder-cylinder pairs"""
+    from furniture_b200 import mjcf
+
+    return mjcf.load_scene("Sawyer", "swivel_chair_0700")

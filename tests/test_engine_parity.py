@@ -125,6 +125,37 @@ def test_trajectory_matches_oracle(sawyer_model, gpu):
 
 
 @pytest.mark.parametrize("gpu", BACKENDS)
+def test_trajectory_matches_oracle_swivel_chair(swivel_model, gpu):
+    """second furniture (cylinder parts: the MPR pairs): parts dropped from 3 mm settle on the floor while the arm moves
+    under constant controls; 150 mj_steps stay within 5e-6 of the oracle."""
+    m = swivel_model
+    eng = make_engine(m, 2, gpu)
+    sims = [OracleSim(m) for _ in range(2)]
+    rng = np.random.RandomState(1)
+    for i, s in enumerate(sims):
+        q = settled_state(m, i, robot_noise=0.0, dz=0.003)
+        c = rng.uniform(-0.3, 0.3, m.nu)
+        s.qpos[:] = q; s.qvel[:] = 0; s.ctrl[:] = c
+        s.forward()
+        if i == 0:
+            Q, U = [q], [c]
+        else:
+            Q.append(q); U.append(c)
+    eng.set("qpos", np.array(Q)); eng.set("qvel", np.zeros((2, m.nv))); eng.set("ctrl", np.array(U))
+    eng.forward()
+    for _ in range(3):
+        for s in sims:
+            s.step(50)
+        eng.step(50)
+        qe, ve = eng.get("qpos"), eng.get("qvel")
+        for i, s in enumerate(sims):
+            assert int(eng.get("ncon")[i][0]) == s.ncon
+            assert np.abs(qe[i] - s.qpos).max() < 5e-6, np.abs(qe[i] - s.qpos).max()
+            assert np.abs(ve[i] - s.qvel).max() < 1e-4, np.abs(ve[i] - s.qvel).max()
+    assert (eng.get("flags") == 0).all()
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
 def test_joint_limit_rows_match_oracle(sawyer_model, gpu):
     """gripper fingers pushed past their stops (the everyday case: the robot block then has joint-limit rows only and is
     solved by the dedicated per-lane Newton): constrained robot acceleration equals the oracle's."""

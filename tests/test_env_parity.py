@@ -78,6 +78,34 @@ def test_env_step_matches_cpu_env(sawyer_model, gpu):
             assert info[i][0] == inf["num_connected"] and info[i][3] == inf["episode_length"]
 
 
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_env_reset_and_step_swivel_chair(swivel_model, gpu):
+    """the env path on a second furniture (3 parts, 2 welds, obs_dim 50): reset settles the parts at their resting heights
+    (chair base z = 0.007, the value the reference's own demo recording shows) and env steps follow the
+    CPU env."""
+    m = swivel_model
+    n = 2
+    eng = make_engine(m, n, gpu)
+    eng.env_reset()
+    assert (eng.get("flags") == 0).all()
+    q = eng.get("qpos")
+    assert np.allclose(q[:, 9 + 2], 0.007, atol=3e-4), q[:, 9 + 2]
+    envs = [OracleFurnitureEnv(m) for _ in range(n)]
+    for i, e in enumerate(envs):
+        e.reset()
+        _sync_oracle_from_engine(e, eng, i)
+        e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[i]
+    rng = np.random.RandomState(7)
+    for k in range(2):
+        a = rng.uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
+        a[:, -1] = -0.5
+        obs, rew, done, info = eng.env_step_host(a)
+        for i, e in enumerate(envs):
+            ob, r, d, inf = e.step(a[i].astype(np.float64))
+            assert obs.shape[1] == 50 and np.abs(obs[i] - ob).max() < 2e-4, (k, i, np.abs(obs[i] - ob).max())
+            assert abs(rew[i] - r) < 1e-5 and bool(done[i]) == d
+
+
 def _grasp_and_align_state(m, env):
     """state in which leg 0 sits between the finger tips (1 mm interpenetration on both sides) and the table top is
     placed so that its connector 'table-leg..conn_site1' coincides with the leg's 'leg-table..conn_site1'."""

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from furniture_b200 import mjcf  # noqa: E402
 
-SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825")]
+SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer", "swivel_chair_0700")]
 
 
 def main():
