@@ -221,3 +221,37 @@ def test_every_env_is_stepped_exactly_once_under_block_packing(sawyer_model):
     for a in acts:
         eng2.env_step_host(a[:8])
     assert np.array_equal(eng2.get("qpos"), q_all[:8])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,n", [("table_lack_0825", 4096), ("swivel_chair_0700", 8192)])
+def test_full_size_batches_through_size_independent_properties(scene, n):
+    """BASELINE.json's full sizes (4096 envs of Sawyer+table_lack, 8192 of Sawyer+swivel_chair on one GPU), checked through
+    properties that do not need the oracle at that size: no divergence flag, unit quaternions, parts at rest stay at rest
+    under zero arm action, every env advances one step per call, and the first 8 envs are bit-identical to the same envs
+    stepped in a batch of 8 (which is the size the oracle parity tests run at)."""
+    m = mjcf.load_scene("Sawyer", scene)
+    eng = make_engine(m, n, True)
+    eng.env_reset()
+    assert (eng.get("flags") == 0).all()
+    q0 = eng.get("qpos")
+    assert np.isfinite(q0).all()
+    np_ = len(m.meta["part_names"])
+    for p in range(np_):
+        quat = q0[:, 9 + 7 * p + 3 : 9 + 7 * p + 7]
+        assert np.abs(np.linalg.norm(quat, axis=1) - 1).max() < 1e-5
+    a = np.zeros((n, eng.act_dim), np.float32)
+    a[:, -2] = -1.0  # gripper open
+    a[:, -1] = -1.0  # no connect
+    for k in range(2):
+        obs, rew, done, info = eng.env_step_host(a)
+        assert (info[:, 3] == k + 1).all() and not done.any() and (info[:, 2] == 0).all()
+    q1 = eng.get("qpos")
+    assert (eng.get("flags") == 0).all()
+    assert np.abs(q1[:, 9:] - q0[:, 9:]).max() < 2e-4, "settled parts must stay where they are"
+    small = make_engine(m, 8, True)
+    small.env_reset()
+    assert np.array_equal(small.get("qpos"), q0[:8])
+    for k in range(2):
+        small.env_step_host(a[:8])
+    assert np.array_equal(small.get("qpos"), q1[:8])
