@@ -14,7 +14,7 @@
 #define FE_MAXDOF 116 /* FE_MAXRDOF + 6 * FE_MAXPART */
 #define FE_MAXGEOM 96
 #define FE_MAXPAIR 2048
-#define FE_MAXSITE 192
+#define FE_MAXSITE 256
 #define FE_MAXEQ 40
 #define FE_MAXU 20
 

@@ -53,7 +53,7 @@ def default_config(**kw):
     """Reference defaults: config/furniture.py:16-312 (control_freq 10 => 50 mj_steps per env step)."""
     c = FeConfig()
     c.struct_bytes = C.sizeof(FeConfig)
-    c.maxcon, c.newton_iters, c.ls_iters, c.tolerance = 40, 30, 20, 1e-6
+    c.maxcon, c.newton_iters, c.ls_iters, c.tolerance = 0, 30, 20, 1e-6  # maxcon 0: sized from the model (auto_maxcon)
     c.nsub, c.max_episode_steps = 50, 2000
     c.discrete_grip, c.rescale_actions, c.auto_align = 1, 1, 1
     c.alignment_pos_dist, c.alignment_rot_dist_up, c.alignment_rot_dist_forward, c.alignment_project_dist = 0.1, 0.9, 0.9, 0.3
@@ -65,6 +65,16 @@ def default_config(**kw):
             raise KeyError(k)
         setattr(c, k, v)
     return c
+
+
+def auto_maxcon(em: EngineModel) -> int:
+    """Contact capacity per env when the config leaves it open.  The reference runs with nconmax=5000 (base.xml:5), i.e.
+    never full; the engine keeps contacts in the env's shared-memory slice, so capacity is sized from the scene: four
+    contacts per colliding part geom (a box resting on a face) plus 16 for the robot, at least 40, at most 128.  An env
+    that still overflows raises bit 0 of its `flags` field (never silently dropped)."""
+    fm = em.fm
+    part_geoms = sum(1 for g in range(fm.ngeom) if (fm.geom_tag[g] >> 8) & 0x3FFFFF)
+    return int(min(128, max(40, 4 * part_geoms + 16)))
 
 
 def build_scene(m: mjcf.Model, em: EngineModel) -> FeScene:
@@ -163,6 +173,8 @@ class Engine:
         self.em = EngineModel(model)
         self.scene = build_scene(model, self.em)
         self.cfg = config or default_config()
+        if self.cfg.maxcon <= 0:
+            self.cfg.maxcon = auto_maxcon(self.em)
         for fn, cls in (("fe_model_sizeof", type(self.em.fm)), ("fe_scene_sizeof", FeScene), ("fe_config_sizeof", FeConfig)):
             if getattr(L, fn)() != C.sizeof(cls):
                 raise RuntimeError("furniture_b200: %s = %d but python layout has %d bytes" % (fn, getattr(L, fn)(), C.sizeof(cls)))

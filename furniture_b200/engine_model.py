@@ -18,7 +18,7 @@ import numpy as np
 
 from . import mjcf
 
-MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU = 32, 20, 16, 116, 96, 2048, 192, 40, 20
+MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU = 32, 20, 16, 116, 96, 2048, 256, 40, 20
 MAGIC = 0x46453031
 TAG_FLOOR, TAG_LFINGER, TAG_RFINGER, TAG_ROBOT, TAG_PART_SHIFT = 1, 2, 4, 8, 8
 

@@ -176,7 +176,33 @@ SAWYER_BOTTOM_OFFSET = np.array([0.0, 0.0, -0.913])  # robots/sawyer_robot.py:17
 GRIPPER_INIT_QPOS = np.array([0.020833, -0.020833])  # grippers/two_finger_gripper.py:22-23
 
 
-def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, use_torque=False):
+def place_unlisted_parts(part_names, listed, radii, seed):
+    """Base placement of the parts whose XML carries no `<name>_initpos` numeric (5 of the shipped furniture models).
+    Restates UniformRandomSampler.setup (models/tasks/placement_sampler.py:68-104 with the (0.7, 0.7, 0) table of
+    floor_task.py:37): such a part starts from Qpos(0, 0, 0, identity) and is drawn once, at construction, uniformly in
+    +-0.35 m in x and y, 0.01 above, rejecting draws whose horizontal-radius disc overlaps a part already placed
+    (the XML-listed parts count as placed).  Every reset then jitters around that base like any listed part.
+    The reference draws from the env's numpy RandomState at construction; here the draw is part of scene composition
+    (one RandomState(seed) per composed scene) so that engine, oracle and tests see the same base poses."""
+    rng = np.random.RandomState(int(seed) & 0x7FFFFFFF)
+    placed = [(q[0], q[1], radii.get(n, 0.0)) for n, q in listed.items()]
+    out = {}
+    for name in part_names:
+        if name in listed:
+            continue
+        r = radii.get(name, 0.0)
+        for _ in range(10000):
+            x, y = rng.uniform(-0.35, 0.35), rng.uniform(-0.35, 0.35)
+            if all(np.hypot(x - px, y - py) > pr + r for px, py, pr in placed):
+                break
+        else:
+            raise RuntimeError("cannot place all parts on the floor")  # RandomizationError, placement_sampler.py:187
+        placed.append((x, y, r))
+        out[name] = np.array([x, y, 0.01, 1.0, 0.0, 0.0, 0.0])
+    return out
+
+
+def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, use_torque=False, placement_seed=123):
     """Returns (xml_string, meta). meta carries what the env layer needs beyond the XML:
     part names in XML document order, *_initpos numerics, horizontal radii, robot/gripper joint names."""
     assets_root = assets_root or default_assets_root()
@@ -261,6 +287,7 @@ def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None,
     for eq in list(_section(obj, "equality")):
         _section(world, "equality").append(eq)
     meta["part_names"] = part_names
+    init_qpos.update(place_unlisted_parts(part_names, init_qpos, radii, placement_seed))
     meta["part_init_qpos"] = init_qpos
     meta["part_radius"] = radii
     with io.StringIO() as s:

@@ -48,7 +48,8 @@ def settled_state(model, seed=0, robot_noise=0.3, dz=0.01):
     q[nr : nr + ng] = meta["gripper_init_qpos"]
     for name in meta["part_names"]:
         qa = model.jnt_qposadr[model.names["jnt"].index(name)]
-        q[qa : qa + 7] = meta["part_init_qpos"][name]
+        if name in meta["part_init_qpos"]:
+            q[qa : qa + 7] = meta["part_init_qpos"][name]  # else: the XML body pose (already in qpos0)
         q[qa + 2] += dz
     return q
 
