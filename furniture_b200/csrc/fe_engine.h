@@ -1590,14 +1590,19 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     if (!(p1 < 0.f) || !(p2 > 0.f)) break;
     const float p1_0 = p1;
     alpha = -p1 / p2;
+    // p' is only piecewise smooth (rows change cone zone along the ray): a Newton step is kept only while it at least
+    // halves the previous one (rtsafe rule), otherwise bisect -- else the iterates can hop between the two ends of the
+    // bracket and shrink it by almost nothing
+    float dxold = alpha;
     for (int ls = 0; ls < w->opt.ls_iters; ++ls) {
       fe_line_eval(w, alpha, g1, g2, &p1, &p2);
       if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
       if (p1 < 0.f) lo = alpha; else hi = alpha;
       float next = alpha - p1 / p2;
-      if (hi > 0.f && !(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      if (hi > 0.f && (!(next > lo && next < hi) || fabsf(2.f * p1) > fabsf(dxold * p2))) next = 0.5f * (lo + hi);
       if (hi < 0.f && !(next > lo)) next = 2.f * alpha;
       if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
+      dxold = fabsf(next - alpha);
       alpha = next;
     }
     FE_CTICK(31)
@@ -1646,7 +1651,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
     FE_PRIVA(float, x_, 6);
     FE_PRIVA(float, acc_, 28); FE_PRIVA(float, sd_, 6); FE_PRIVA(float, jx_, 3); FE_PRIVA(float, jv_, 3);
     FE_PRIV(float, scale_); FE_PRIV(float, impr_); FE_PRIV(float, g1_); FE_PRIV(float, g2_); FE_PRIV(float, alpha_);
-    FE_PRIV(float, lo_); FE_PRIV(float, hi_); FE_PRIV(float, p10_);
+    FE_PRIV(float, lo_); FE_PRIV(float, hi_); FE_PRIV(float, p10_); FE_PRIV(float, dx_);
     LANES_BEGIN
       int part = np, slot = 0;
       PV(wide_) = 0; PV(lead_) = 0;
@@ -1756,7 +1761,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
             float Ms[6], g1 = 0.f, g2 = 0.f;
             inert_mulv(Ms, I, PV(sd_));
             for (int k = 0; k < 6; ++k) { g1 += PV(sd_)[k] * Mx[k]; g2 += 0.5f * PV(sd_)[k] * Ms[k]; }
-            PV(g1_) = g1; PV(g2_) = g2; PV(alpha_) = 0.f; PV(lo_) = 0.f; PV(hi_) = -1.f; PV(lsact_) = 1;
+            PV(g1_) = g1; PV(g2_) = g2; PV(alpha_) = 0.f; PV(lo_) = 0.f; PV(hi_) = -1.f; PV(dx_) = 0.f; PV(lsact_) = 1;
             if (PV(c_) >= 0) {
               const float* J = PV(J_);
               for (int k = 0; k < 3; ++k) PV(jv_)[k] = dot6(J + 6 * k, PV(sd_));
@@ -1796,14 +1801,15 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
             const float p1 = PV(acc_)[0] + PV(g1_) + 2.f * al * PV(g2_), p2 = PV(acc_)[1] + 2.f * PV(g2_);
             if (ls == 0) {
               if (!(p1 < 0.f) || !(p2 > 0.f)) { PV(lsact_) = 0; PV(act_) = 0; PV(alpha_) = 0.f; }
-              else { PV(p10_) = p1; PV(alpha_) = -p1 / p2; }
+              else { PV(p10_) = p1; PV(alpha_) = -p1 / p2; PV(dx_) = PV(alpha_); }
             } else if (fabsf(p1) <= 1e-5f * fabsf(PV(p10_))) PV(lsact_) = 0;
             else {
               if (p1 < 0.f) PV(lo_) = al; else PV(hi_) = al;
               float next = al - p1 / p2;
-              if (PV(hi_) > 0.f && !(next > PV(lo_) && next < PV(hi_))) next = 0.5f * (PV(lo_) + PV(hi_));
+              if (PV(hi_) > 0.f && (!(next > PV(lo_) && next < PV(hi_)) || fabsf(2.f * p1) > fabsf(PV(dx_) * p2))) next = 0.5f * (PV(lo_) + PV(hi_)); // rtsafe rule
               if (PV(hi_) < 0.f && !(next > PV(lo_))) next = 2.f * al;
               if (fabsf(next - al) <= 1e-6f * fabsf(al)) PV(lsact_) = 0;
+              PV(dx_) = fabsf(next - al);
               PV(alpha_) = next;
             }
           }
@@ -1924,7 +1930,7 @@ FE_FN void fe_solve_robot_limits(FeWarp* w) {
     FE_WSUM(a_); FE_WSUM(b_);
     const float g1 = FE_UNI(a_), g2 = FE_UNI(b_);
     // exact line search: safeguarded Newton on p'(alpha) = 0
-    float p1 = 0.f, p2 = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f, p1_0 = 0.f;
+    float p1 = 0.f, p2 = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f, p1_0 = 0.f, dxold = 0.f;
     bool fail = false;
     for (int ls = -1; ls < maxls; ++ls) {
       REGS_BEGIN
@@ -1940,14 +1946,16 @@ FE_FN void fe_solve_robot_limits(FeWarp* w) {
         if (!(p1 < 0.f) || !(p2 > 0.f)) { fail = true; break; }
         p1_0 = p1;
         alpha = -p1 / p2;
+        dxold = alpha;
         continue;
       }
       if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
       if (p1 < 0.f) lo = alpha; else hi = alpha;
       float next = alpha - p1 / p2;
-      if (hi > 0.f && !(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      if (hi > 0.f && (!(next > lo && next < hi) || fabsf(2.f * p1) > fabsf(dxold * p2))) next = 0.5f * (lo + hi); // rtsafe rule
       if (hi < 0.f && !(next > lo)) next = 2.f * alpha;
       if (fabsf(next - alpha) <= 1e-6f * fabsf(alpha)) { alpha = next; break; }
+      dxold = fabsf(next - alpha);
       alpha = next;
     }
     if (fail || !(alpha > 0.f)) break;

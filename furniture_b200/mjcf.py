@@ -177,7 +177,7 @@ GRIPPER_INIT_QPOS = np.array([0.020833, -0.020833])  # grippers/two_finger_gripp
 
 
 def place_unlisted_parts(part_names, listed, radii, seed):
-    """Base placement of the parts whose XML carries no `<name>_initpos` numeric (5 of the shipped furniture models).
+    """Base placement of the parts whose XML carries no `<name>_initpos` numeric (6 of the shipped furniture models).
     Restates UniformRandomSampler.setup (models/tasks/placement_sampler.py:68-104 with the (0.7, 0.7, 0) table of
     floor_task.py:37): such a part starts from Qpos(0, 0, 0, identity) and is drawn once, at construction, uniformly in
     +-0.35 m in x and y, 0.01 above, rejecting draws whose horizontal-radius disc overlaps a part already placed

@@ -787,14 +787,19 @@ void om_solve(const om_model* m, om_data* d) {
     if (!(p1 < 0) || !(p2 > 0)) break;
     alpha = -p1 / p2;
     double gtol = 1e-14 * (fabs(plo) > 1 ? fabs(plo) : 1) + 1e-12 * fabs(plo);
-    for (int ls = 0; ls < 60; ls++) {
+    /* p' is piecewise smooth (rows enter and leave the cone zones along the ray), so a Newton step taken from one side of
+       the root can land next to the other end of the bracket and back again, shrinking it by almost nothing; the step is
+       therefore accepted only while it at least halves the previous one (the rtsafe rule), otherwise bisect */
+    double dxold = alpha;
+    for (int ls = 0; ls < 100; ls++) {
       line_eval(&c, alpha, quadGauss, &p0, &p1, &p2);
       if (fabs(p1) <= gtol) break;
       if (p1 < 0) lo = alpha; else hi = alpha;
       double next = alpha - p1 / p2;
-      if (hi > 0 && !(next > lo && next < hi)) next = 0.5 * (lo + hi);
+      if (hi > 0 && (!(next > lo && next < hi) || fabs(2 * p1) > fabs(dxold * p2))) next = 0.5 * (lo + hi);
       if (hi < 0 && !(next > lo)) next = 2 * alpha;
       if (fabs(next - alpha) <= 1e-15 * fabs(alpha)) { alpha = next; break; }
+      dxold = fabs(next - alpha);
       alpha = next;
     }
     if (!(alpha > 0)) break;

@@ -1,0 +1,83 @@
+"""The mixed-furniture case (BASELINE.json config 5): FurnitureSawyerEnv over every furniture XML whose
+colliders the engine supports (57 of the 64 shipped models; the other 7 need mesh colliders) -- ragged nq/nv/nefc, 2 to 14
+parts, 1 to 37 welds, boxes and cylinders.  For each model: device reset (settle protocol of furniture.py:1406-1663), then
+env steps with random actions compared with the CPU env oracle started from the same post-reset state.
+
+`emu` = lane-emulated harness build of the kernel source (CPU); `cuda` = the sm_100a library (marked gpu, a subset that
+spans the shapes: most parts, most geoms, cylinders, smallest)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from furniture_b200 import mjcf
+from oracle.ref_env import OracleFurnitureEnv
+from parity_util import make_engine
+from test_env_parity import _sync_oracle_from_engine
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+COMPILED = os.path.join(os.path.dirname(HERE), "furniture_b200", "compiled")
+NAMES = sorted(os.path.basename(p)[len("Sawyer_") : -len(".npz")] for p in glob.glob(os.path.join(COMPILED, "Sawyer_*.npz")))
+
+# Six models carry no `*_initpos` numerics: the reference drops those parts at z = 0.01 wherever the sampler puts them
+# (placement_sampler.py:68-104), i.e. large panels start half inside the floor and are pushed out during the reset.  Three of
+# them start with more simultaneous contacts than the engine's per-env capacity (the reference runs with nconmax=5000) and
+# raise the overflow flag; all six come out of the reset still moving, so steps are compared loosely (chaotic contact).
+UNLISTED = {"bookcase_billy_0191", "bookcase_grevback_0484", "cabinet_akurum_0021", "chair_agam_0005", "table_hemnes_0539", "table_klubbo_0740"}
+OVERFLOW = {"bookcase_billy_0191", "bookcase_grevback_0484", "table_hemnes_0539"}
+GPU_SUBSET = ["bookcase_expedit_0376", "chair_ingolf_0650", "table_dockstra_0279", "toy_table_flip", "three_blocks_peg", "bookcase_hensvik_0565"]
+
+
+def _run(name, gpu, n=2, steps=2):
+    m = mjcf.load_scene("Sawyer", name)
+    eng = make_engine(m, n, gpu)
+    assert eng.obs_dim == 7 * len(m.meta["part_names"]) + 29
+    eng.env_reset()
+    flags = eng.get("flags")[:, 0]
+    q = eng.get("qpos")
+    assert np.isfinite(q).all()
+    if name in OVERFLOW:
+        assert ((flags & ~1) == 0).all(), flags  # only the capacity bit
+        eng.close()
+        return
+    assert (flags == 0).all(), flags
+    assert np.allclose(np.linalg.norm(q[:, 9:].reshape(n, -1, 7)[:, :, 3:], axis=2), 1, atol=1e-5)  # unit quaternions
+    if name not in UNLISTED:
+        assert np.abs(eng.get("qvel")[:, 9:]).max() < 0.5  # parts (nearly) at rest after the settle phase
+    envs = [OracleFurnitureEnv(m) for _ in range(n)]
+    for i, e in enumerate(envs):
+        e.reset()
+        _sync_oracle_from_engine(e, eng, i)
+        e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[i]
+    rng = np.random.RandomState(5)
+    # analytic pairs (plane/sphere/box) agree to fp32 round-off; cylinder pairs go through MPR (portal tolerance), as in
+    # test_engine_parity; parts still in motion after the reset amplify round-off through contact (loose bound)
+    has_cyl = bool((np.asarray(m.geom_type) == 5).any())
+    tol = 2e-2 if name in UNLISTED else (1e-3 if has_cyl else 5e-5)
+    for k in range(steps):
+        a = rng.uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
+        a[:, -1] = -0.5
+        obs, rew, done, info = eng.env_step_host(a)
+        assert (eng.get("flags")[:, 0] == 0).all()
+        for i, e in enumerate(envs):
+            ob, r, d, inf = e.step(a[i].astype(np.float64))
+            assert np.abs(obs[i] - ob).max() < tol, (name, k, i, np.abs(obs[i] - ob).max())
+            assert abs(rew[i] - r) < 1e-5 and bool(done[i]) == d
+            assert info[i][0] == inf["num_connected"] and info[i][3] == inf["episode_length"]
+    eng.close()
+
+
+def test_compiled_tables_cover_the_supported_models():
+    assert len(NAMES) == 57 and "table_lack_0825" in NAMES and "swivel_chair_0700" in NAMES
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_env_parity_every_furniture_emu(name):
+    _run(name, False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GPU_SUBSET)
+def test_env_parity_mixed_furniture_cuda(name):
+    _run(name, True, n=4)

@@ -10,6 +10,7 @@ sys.path.insert(0, ROOT)
 from furniture_b200 import mjcf  # noqa: E402
 
 SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer", "swivel_chair_0700")]
+MIXED = True  # plus Sawyer + every furniture XML whose colliders the engine supports (BASELINE.json config 5, the mixed batch)
 
 
 def main():
@@ -19,12 +20,22 @@ def main():
         return
     out = os.path.join(ROOT, "furniture_b200", "compiled")
     os.makedirs(out, exist_ok=True)
-    for agent, furn in SCENES:
+    scenes = list(SCENES)
+    if MIXED:
+        scenes += [("Sawyer", n) for n in mjcf.furniture_names(root) if ("Sawyer", n) not in scenes]
+    skipped = []
+    for agent, furn in scenes:
         xml, meta = mjcf.compose_scene(agent, furn, root)
-        m = mjcf.compile_mjcf(xml, meta)
+        try:
+            m = mjcf.compile_mjcf(xml, meta)
+        except NotImplementedError as e:  # mesh colliders (7 of the 64 furniture models)
+            skipped.append((furn, str(e)))
+            continue
         path = os.path.join(out, "%s_%s.npz" % (agent, furn))
         m.save(path)
         print("wrote", path, "nq=%d nv=%d" % (m.nq, m.nv))
+    for furn, why in skipped:
+        print("skipped", furn, "--", why)
 
 
 if __name__ == "__main__":

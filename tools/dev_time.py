@@ -8,7 +8,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 m = mjcf.load_scene("Sawyer", "table_lack_0825")
-eng = Engine(m, N, 0, default_config())
+eng = Engine(m, N, 0, default_config(maxcon=int(os.environ.get("FE_MAXCON", "0"))))
 t = time.time(); eng.env_reset(); torch.cuda.synchronize(); print("reset wall %.3f s" % (time.time() - t), "flags nonzero", int((eng.get("flags") != 0).sum()))
 g = torch.Generator(device="cuda").manual_seed(0)
 act = (torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1) * scale
