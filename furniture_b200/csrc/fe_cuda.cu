@@ -140,30 +140,54 @@ struct CudaPlat {
   unsigned char* pin_out = nullptr;
   size_t out_bytes = 0;
   cudaStream_t stream = nullptr;
+  FeLayout* lay_pin = nullptr;
 };
 #define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(h, -10, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
 
 static int plat_init(fe_handle* h) {
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return -10; }
-  h->plat = new CudaPlat();
+  CudaPlat* p = new CudaPlat();
+  h->plat = p;
+  e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking); // private stream of fe_env_step_host
+  if (e != cudaSuccess) { h->err = std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(e); delete p; h->plat = nullptr; return -10; }
   return 0;
 }
 // The slice layout table is one __constant__ object per process: (re)upload it when the handle about to launch uses a
-// different layout than the one resident (several handles with different models alive at once, as in the tests).
+// different layout than the one resident (several handles with different models alive at once: the tests, a mixed-furniture
+// batch).  If every launch since the last upload went to the stream of this launch, the switch is one stream-ordered
+// cudaMemcpyToSymbolAsync from the handle's pinned copy (kernels of the old layout are ahead of it in the same stream);
+// otherwise the device is drained first.
 static FeLayout g_resident_lay;
 static bool g_resident_valid = false;
-static int plat_use_layout(fe_handle* h) {
-  if (g_resident_valid && memcmp(&g_resident_lay, &h->lay, sizeof(FeLayout)) == 0) return 0;
-  CUDA_OK(cudaDeviceSynchronize()); // kernels of the previous layout's handle must have drained
-  CUDA_OK(cudaMemcpyToSymbol(fe_c_lay, &h->lay, sizeof(FeLayout)));
-  g_resident_lay = h->lay;
-  g_resident_valid = true;
+static std::vector<cudaStream_t> g_resident_streams; // streams that received launches under the resident layout
+static int plat_use_layout(fe_handle* h, cudaStream_t stream) {
+  CudaPlat* p = (CudaPlat*)h->plat;
+  const bool same = g_resident_valid && memcmp(&g_resident_lay, &h->lay, sizeof(FeLayout)) == 0;
+  if (!same) {
+    const bool ordered = g_resident_valid && p->lay_pin && g_resident_streams.size() == 1 && g_resident_streams[0] == stream;
+    if (ordered) {
+      CUDA_OK(cudaMemcpyToSymbolAsync(fe_c_lay, p->lay_pin, sizeof(FeLayout), 0, cudaMemcpyHostToDevice, stream));
+    } else {
+      CUDA_OK(cudaDeviceSynchronize()); // kernels of the previous layout's handle must have drained
+      CUDA_OK(cudaMemcpyToSymbol(fe_c_lay, &h->lay, sizeof(FeLayout)));
+    }
+    g_resident_lay = h->lay;
+    g_resident_valid = true;
+    g_resident_streams.clear();
+  }
+  bool seen = false;
+  for (cudaStream_t s : g_resident_streams) seen |= s == stream;
+  if (!seen) g_resident_streams.push_back(stream);
   return 0;
 }
-static int plat_prepare(fe_handle* h) {
+static int plat_prepare(fe_handle* h, cudaStream_t stream) {
   CudaPlat* p = (CudaPlat*)h->plat;
-  if (int rc = plat_use_layout(h)) return rc;
+  if (!p->lay_pin) { // pinned copy of the layout: source of the stream-ordered switch
+    CUDA_OK(cudaMallocHost((void**)&p->lay_pin, sizeof(FeLayout)));
+    *p->lay_pin = h->lay;
+  }
+  if (int rc = plat_use_layout(h, stream)) return rc;
   if (p->smem_sim) return 0;
   // warps (= envs) per block: as many as fit in 227 KB of shared memory, at most FE_MAX_WPB; FE_WPB overrides
   const size_t per_env = (size_t)(h->slice_words + FE_ENV_EXTRA_WORDS) * 4;
@@ -187,10 +211,11 @@ static int plat_prepare(fe_handle* h) {
   }
   p->smem_sim = (size_t)h->slice_words * 4 * wpb;
   p->smem_env = per_env * wpb;
-  CUDA_OK(cudaFuncSetAttribute(fe_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sim));
-  CUDA_OK(cudaFuncSetAttribute(fe_env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_env));
-  CUDA_OK(cudaFuncSetAttribute(fe_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_env));
-  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  // the opt-in limit is an attribute of the kernel, not of the handle: always the hardware maximum (227 KB), so that handles
+  // with different slice sizes can be alive together (a smaller value set by a later handle would fail the earlier one's launches)
+  CUDA_OK(cudaFuncSetAttribute(fe_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(fe_env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(fe_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const size_t N = h->N;
   p->out_bytes = N * (sizeof(float) * h->hs.obs_dim + sizeof(float) + sizeof(int32_t) * FE_INFO_DIM + 1);
   CUDA_OK(cudaMallocHost((void**)&p->pin_act, sizeof(float) * N * (h->hs.act_dim > 0 ? h->hs.act_dim : 1)));
@@ -201,6 +226,7 @@ static void plat_fini(fe_handle* h) {
   CudaPlat* p = (CudaPlat*)h->plat;
   if (!p) return;
   cudaDeviceSynchronize();
+  if (p->lay_pin) cudaFreeHost(p->lay_pin);
   if (p->pin_act) cudaFreeHost(p->pin_act);
   if (p->pin_out) cudaFreeHost(p->pin_out);
   if (p->slots) cudaFree(p->slots);
@@ -214,7 +240,7 @@ static void plat_copy_d2d(fe_handle* h, void* dst, const void* src, size_t n, vo
   if (dst != src) cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
 }
 static int plat_run_sim(fe_handle* h, int nsub, int mode, void* stream) {
-  int rc = plat_prepare(h);
+  int rc = plat_prepare(h, (cudaStream_t)stream);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
   fe_sim_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_sim, (cudaStream_t)stream>>>(h->st, h->dm, h->opt, nsub, mode, h->dbg, h->slice_words);
@@ -222,7 +248,7 @@ static int plat_run_sim(fe_handle* h, int nsub, int mode, void* stream) {
   return 0;
 }
 static int plat_run_reset(fe_handle* h, const uint8_t* mask, void* stream) {
-  int rc = plat_prepare(h);
+  int rc = plat_prepare(h, (cudaStream_t)stream);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
   fe_env_reset_kernel<<<(h->N + p->wpb - 1) / p->wpb, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, mask, h->slice_words);
@@ -230,7 +256,7 @@ static int plat_run_reset(fe_handle* h, const uint8_t* mask, void* stream) {
   return 0;
 }
 static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, void* stream) {
-  int rc = plat_prepare(h);
+  int rc = plat_prepare(h, (cudaStream_t)stream);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
   fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words, p->slots);
@@ -239,9 +265,9 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
   return 0;
 }
 static int plat_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
-  int rc = plat_prepare(h);
-  if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
+  int rc = plat_prepare(h, p->stream);
+  if (rc) return rc;
   const size_t N = h->N, ab = sizeof(float) * N * h->hs.act_dim, ob = sizeof(float) * N * h->hs.obs_dim, rb = sizeof(float) * N, ib = sizeof(int32_t) * N * FE_INFO_DIM;
   memcpy(p->pin_act, actions, ab);
   // the private stream does not order against work the caller issued on other streams (fe_sim_forward, fe_set_field ...)

@@ -97,7 +97,7 @@ FE_BOTH int fe_layout_build(FeLayout* L, const fe_model* m, const FeOpt& opt) {
   L->lacc2 = L->lfrc; /* RNE wrench (smooth stage) and solver link accelerations are never live together */
   CARVE(linert, 10 * nl) CARVE(lcrb, (10 * nr > 96 ? 10 * nr : 96)) CARVE(Mr, nr * nr) CARVE(Lr, fe_tri(nr)) CARVE(fs, nv) CARVE(as, nv) CARVE(bias, nr)
   CARVE(touch, np)
-  CARVE(c_dist, mc) CARVE(c_pos, 3 * mc) CARVE(c_frame, 9 * mc) CARVE(c_aref, 3 * mc) CARVE(c_D, 2 * mc) CARVE(c_mu, mc) CARVE(c_fric, mc)
+  CARVE(c_dist, mc) CARVE(c_pos, 3 * mc) CARVE(c_frame, 6 * mc) CARVE(c_aref, 3 * mc) CARVE(c_D, 2 * mc) CARVE(c_mu, mc) CARVE(c_fric, mc)
   CARVE(c_jar, 3 * mc) CARVE(c_jv, 3 * mc) CARVE(c_f, 3 * mc) CARVE(c_geom, mc) CARVE(c_link, mc) CARVE(c_state, mc) CARVE(c_kind, mc) CARVE(plist, 9 * np)
   CARVE(w_r1, 3 * ne) CARVE(w_G, 9 * ne) CARVE(w_aref, 6 * ne) CARVE(w_D, 6 * ne) CARVE(w_jar, 6 * ne) CARVE(w_jv, 6 * ne) CARVE(w_f, 6 * ne)
   CARVE(l_sign, nr) CARVE(l_aref, nr) CARVE(l_D, nr) CARVE(l_jar, nr) CARVE(l_jv, nr) CARVE(l_f, nr)
@@ -695,7 +695,7 @@ FE_FN void fe_collide(FeWarp* w) {
         if (c < mc) {
           w->c_dist()[c] = res[i].dist;
           v3cpy(w->c_pos() + 3 * c, res[i].pos);
-          v3cpy(w->c_frame() + 9 * c, res[i].n);
+          v3cpy(w->c_frame() + 6 * c, res[i].n);
           w->c_geom()[c] = g1 | (g2 << 8);
         }
       }
@@ -767,6 +767,15 @@ FE_HD void fe_make_frame(float* F) {
   v3cross(z, x, y);
 }
 
+// The slice keeps the normal and the first tangent of a contact frame (6 words); the second tangent is their cross product
+// (fe_make_frame builds it exactly so), recomputed where the frame is read: 3 words per contact buy 4 more contacts of capacity.
+FE_HD void fe_frame_load(const FeWarp* w, int c, float* F) {
+  const float* s = w->c_frame() + 6 * c;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) F[k] = s[k];
+  v3cross(F + 6, F, F + 3);
+}
+
 FE_FN void fe_assemble(FeWarp* w) {
   const fe_model* m = w->m;
   const int ncon = w->u()[0], nr = m->nr, ne = m->neq;
@@ -782,8 +791,10 @@ FE_FN void fe_assemble(FeWarp* w) {
         w->c_kind()[c] = ((pa && B < 0) || (pb && A < 0)) ? 0 : ((pa || pb) ? 2 : 1);
         (void)ra; (void)rb;
       }
-      float* F = w->c_frame() + 9 * c;
+      float F[9];
+      v3cpy(F, w->c_frame() + 6 * c);
       fe_make_frame(F);
+      for (int k = 0; k < 6; ++k) w->c_frame()[6 * c + k] = F[k];
       const float fric = fmaxf(fmaxf(m->geom_friction[g1], m->geom_friction[g2]), 1e-5f);
       float sr[2], si[3];
       const float *s1 = m->geom_solref[g1], *s2 = m->geom_solref[g2];
@@ -908,7 +919,8 @@ FE_FN void fe_mul_J(FeWarp* w, const float* in, float* cout, float* wout, float*
       fe_point_vel(w, w->lacc2(), A, w->c_pos() + 3 * c, aA);
       fe_point_vel(w, w->lacc2(), B, w->c_pos() + 3 * c, aB);
       v3sub(da, aB, aA);
-      const float* F = w->c_frame() + 9 * c;
+      float F[9];
+      fe_frame_load(w, c, F);
       for (int k = 0; k < 3; ++k) cout[3 * c + k] = v3dot(F + 3 * k, da) - (sub_aref ? w->c_aref()[3 * c + k] : 0.f);
     }
     for (int e = lane; e < ne; e += 32) {
@@ -988,7 +1000,8 @@ FE_FN void fe_mul_JT(FeWarp* w, float* out) {
         if (A != l && B != l) continue;
         const float sg = (B == l ? 1.f : 0.f) - (A == l ? 1.f : 0.f);
         if (sg == 0.f) continue;
-        const float* F = w->c_frame() + 9 * c;
+        float F[9];
+      fe_frame_load(w, c, F);
         const float *f = w->c_f() + 3 * c;
         float fw[3] = {F[0] * f[0] + F[3] * f[1] + F[6] * f[2], F[1] * f[0] + F[4] * f[1] + F[7] * f[2], F[2] * f[0] + F[5] * f[1] + F[8] * f[2]};
         float r[3], t[3];
@@ -1092,7 +1105,8 @@ FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, f
 }
 // rows of one part-vs-world contact in the part's coordinates: J[k] = sgn * [(r x F_k), F_k], r = pos - origin
 FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
-  const float* F = w->c_frame() + 9 * c;
+  float F[9];
+      fe_frame_load(w, c, F);
   float r[3];
   v3sub(r, w->c_pos() + 3 * c, w->lpos() + 3 * l);
   for (int k = 0; k < 3; ++k) {
@@ -1123,7 +1137,8 @@ FE_HD void fe_contact_weight(const FeWarp* w, int c, int st, float* W) {
 FE_HD void fe_contact_col(const FeWarp* w, int c, int z, int A, int B, float* col) {
   const fe_model* m = w->m;
   const int nr = m->nr, nrl = m->nrlink;
-  const float* F = w->c_frame() + 9 * c;
+  float F[9];
+      fe_frame_load(w, c, F);
   const float* p = w->c_pos() + 3 * c;
   col[0] = col[1] = col[2] = 0.f;
   if (z < 0) return;
@@ -1143,8 +1158,8 @@ FE_HD void fe_contact_col(const FeWarp* w, int c, int z, int A, int B, float* co
       float r[3];
       v3sub(r, p, w->lpos() + 3 * l);
       for (int k = 0; k < 3; ++k) {
-        if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * t[jj]; }
-        else col[k] = sg * F[3 * k + (jj - 3)];
+        if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * (jj == 0 ? t[0] : (jj == 1 ? t[1] : t[2])); }
+        else col[k] = sg * (jj == 3 ? F[3 * k] : (jj == 4 ? F[3 * k + 1] : F[3 * k + 2])); // selects keep F in registers
       }
     }
   }
@@ -1247,7 +1262,8 @@ FE_FN void fe_build_H(FeWarp* w, bool regs = false) {
     LANES_BEGIN
       const int j = lane;
       if (j < ncols) {
-        const float* F = w->c_frame() + 9 * c;
+        float F[9];
+      fe_frame_load(w, c, F);
         const float* p = w->c_pos() + 3 * c;
         float col[3] = {0.f, 0.f, 0.f};
         int z;
@@ -1270,8 +1286,8 @@ FE_FN void fe_build_H(FeWarp* w, bool regs = false) {
           float r[3];
           v3sub(r, p, w->lpos() + 3 * (nrl + part));
           for (int k = 0; k < 3; ++k) {
-            if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * t[jj]; }
-            else col[k] = sg * F[3 * k + (jj - 3)];
+            if (jj < 3) { float t[3]; v3cross(t, r, F + 3 * k); col[k] = sg * (jj == 0 ? t[0] : (jj == 1 ? t[1] : t[2])); }
+            else col[k] = sg * (jj == 3 ? F[3 * k] : (jj == 4 ? F[3 * k + 1] : F[3 * k + 2])); // selects keep F in registers
           }
         }
         w->Jc()[j] = col[0]; w->Jc()[32 + j] = col[1]; w->Jc()[64 + j] = col[2];

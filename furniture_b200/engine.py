@@ -70,11 +70,11 @@ def default_config(**kw):
 def auto_maxcon(em: EngineModel) -> int:
     """Contact capacity per env when the config leaves it open.  The reference runs with nconmax=5000 (base.xml:5), i.e.
     never full; the engine keeps contacts in the env's shared-memory slice, so capacity is sized from the scene: four
-    contacts per colliding part geom (a box resting on a face) plus 16 for the robot, at least 40, at most 128.  An env
+    contacts per colliding part geom (a box resting on a face) plus 16 for the robot, at least 44, at most 128.  An env
     that still overflows raises bit 0 of its `flags` field (never silently dropped)."""
     fm = em.fm
     part_geoms = sum(1 for g in range(fm.ngeom) if (fm.geom_tag[g] >> 8) & 0x3FFFFF)
-    return int(min(128, max(40, 4 * part_geoms + 16)))
+    return int(min(128, max(44, 4 * part_geoms + 16)))
 
 
 def build_scene(m: mjcf.Model, em: EngineModel) -> FeScene:

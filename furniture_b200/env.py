@@ -116,6 +116,83 @@ def make_vec_env(env_id="IKEASawyer-v0", num_env=1, config=None, device=0):
     return BatchedFurnitureEnv(agent, furniture, num_env, device=device, **config)
 
 
+class MixedFurnitureEnv:
+    """A batch over several furniture models at once (BASELINE.json config 5; the reference reaches other furniture through
+    `furniture_name` / `furniture_id`, config/furniture.py:43-55, one model per env process).  Envs are bucketed by
+    furniture ("bucket by furniture id first"): one engine handle per model, all stepped from the same CUDA
+    stream, so switching the slice layout between buckets is a stream-ordered constant upload, not a device sync.
+    nq / nv / obs_dim differ per bucket; `object_ob` is returned zero-padded to the widest model, `robot_ob` is common.
+
+      env = MixedFurnitureEnv(["table_lack_0825", "chair_ingolf_0650"], envs_per_model=64)
+      obs = env.reset(); obs, rew, done, info = env.step(actions)          # actions: (num_envs, dof)
+    """
+
+    def __init__(self, furniture_names, envs_per_model, agent="Sawyer", device=0, **cfg_overrides):
+        import torch
+
+        self.torch = torch
+        self.names = list(furniture_names)
+        counts = [envs_per_model] * len(self.names) if isinstance(envs_per_model, int) else list(envs_per_model)
+        assert len(counts) == len(self.names)
+        seed = cfg_overrides.pop("seed", 123)
+        self.buckets, self.offsets, off = [], [], 0
+        for name, n in zip(self.names, counts):
+            self.buckets.append(BatchedFurnitureEnv(agent, name, n, device=device, seed=seed + off, **cfg_overrides))
+            self.offsets.append(off)
+            off += n
+        self.num_envs = off
+        b0 = self.buckets[0]
+        self.device, self.act_dim, self.dof, self.robot_ob_dim = b0.device, b0.act_dim, b0.act_dim, b0.robot_ob_dim
+        assert all(b.act_dim == self.act_dim and b.robot_ob_dim == self.robot_ob_dim for b in self.buckets)
+        self.object_ob_dim = max(b.object_ob_dim for b in self.buckets)
+        self._object_ob = torch.zeros((off, self.object_ob_dim), dtype=torch.float32, device=self.device)
+        self._robot_ob = torch.empty((off, self.robot_ob_dim), dtype=torch.float32, device=self.device)
+        self._rew = torch.empty(off, dtype=torch.float32, device=self.device)
+        self._done = torch.empty(off, dtype=torch.uint8, device=self.device)
+        self._info = torch.empty((off, INFO_DIM), dtype=torch.int32, device=self.device)
+        self._act = torch.empty((off, self.act_dim), dtype=torch.float32, device=self.device)
+
+    def bucket_of(self, env_index):
+        """(furniture name, index inside its bucket) of a global env index"""
+        for name, off, b in zip(self.names, self.offsets, self.buckets):
+            if off <= env_index < off + b.num_envs:
+                return name, env_index - off
+        raise IndexError(env_index)
+
+    def _collect(self, b, off, od):
+        sl = slice(off, off + b.num_envs)
+        self._object_ob[sl, : b.object_ob_dim].copy_(od["object_ob"])
+        self._robot_ob[sl].copy_(od["robot_ob"])
+        return sl
+
+    def _obs(self):
+        return OrderedDict(object_ob=self._object_ob, robot_ob=self._robot_ob)
+
+    def reset(self):
+        for b, off in zip(self.buckets, self.offsets):
+            self._collect(b, off, b.reset())
+        return self._obs()
+
+    def step(self, actions):
+        t = self.torch
+        if isinstance(actions, dict):
+            actions = actions["default"]
+        a = t.as_tensor(actions)
+        if a.device != self.device or a.dtype != t.float32 or not a.is_contiguous():
+            self._act.copy_(a, non_blocking=True)
+            a = self._act
+        assert a.shape == (self.num_envs, self.act_dim), tuple(a.shape)
+        for b, off in zip(self.buckets, self.offsets):
+            od, rew, done, info = b.step(a[off : off + b.num_envs])
+            sl = self._collect(b, off, od)
+            self._rew[sl].copy_(rew); self._done[sl].copy_(done); self._info[sl].copy_(info)
+        return self._obs(), self._rew, self._done, self._info
+
+    def close(self):
+        for b in self.buckets:
+            b.close()
+
+
 class ShardedFurnitureEnv:
     """One process per GPU (torch.distributed, backend nccl). Each rank steps its own contiguous env shard; after the
     step one all_gather makes the packed [obs | reward | done] of every shard visible on every rank."""
