@@ -134,7 +134,7 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   ALLOC(e.obs, float, h->hs.obs_dim > 0 ? h->hs.obs_dim : 1, "obs", false) ALLOC(e.group, int, m.npart, "group", true) ALLOC(e.site_connected, int, nsite, "site_connected", true)
   ALLOC(e.num_connected, int, 1, "num_connected", true) ALLOC(e.prev_num_connected, int, 1, "prev_num_connected", true)
   ALLOC(e.touched, int, m.npart, "touched", true) ALLOC(e.picked, int, m.npart, "picked", true) ALLOC(e.episode_len, int, 1, "episode_length", true)
-  ALLOC(e.rng, unsigned long long, 1, "rng", true) ALLOC(e.done, int, 1, "done", false) ALLOC(e.robot_contype, int, m.ngeom, nullptr, false)
+  ALLOC(e.mt, uint32_t, 624, "mt_state", true) ALLOC(e.mt_pos, int, 1, "mt_pos", true) ALLOC(e.done, int, 1, "done", false) ALLOC(e.robot_contype, int, m.ngeom, nullptr, false)
   ALLOC(e.robot_conaff, int, m.ngeom, nullptr, false) ALLOC(e.episode_reward, float, 1, "episode_reward", false)
 #undef ALLOC
   // initial per-env model state: MjSim.reset() semantics (qpos = qpos0 of the XML, masks / welds from the model)
@@ -151,9 +151,16 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
     std::vector<int> ord(N);
     for (size_t n = 0; n < N; ++n) ord[n] = (int)n;
     plat_upload(s.order, ord.data(), sizeof(int) * N);
-    std::vector<unsigned long long> rng(N);
-    for (size_t n = 0; n < N; ++n) rng[n] = cfg->seed + n;
-    plat_upload(e.rng, rng.data(), sizeof(unsigned long long) * N);
+    // numpy RandomState(seed + env): init_genrand (Knuth), position at the end of the state so that the first draw regenerates it
+    std::vector<uint32_t> mt(N * 624);
+    std::vector<int> mpos(N, 624);
+    for (size_t n = 0; n < N; ++n) {
+      uint32_t* s = mt.data() + n * 624;
+      s[0] = (uint32_t)((cfg->seed + n) & 0xffffffffu);
+      for (uint32_t i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + i;
+    }
+    plat_upload(e.mt, mt.data(), sizeof(uint32_t) * N * 624);
+    plat_upload(e.mt_pos, mpos.data(), sizeof(int) * N);
   }
   h->dev_act = h_alloc<float>(h, N * (size_t)(h->hs.act_dim > 0 ? h->hs.act_dim : 1));
   h->dev_rew = h_alloc<float>(h, N);

@@ -35,7 +35,8 @@ struct FeEnvState {
   float* obs;                                  // [N][obs_dim]
   int *group, *site_connected;                 // [N][npart], [N][nsite]
   int *num_connected, *prev_num_connected, *touched, *picked, *episode_len, *done;
-  unsigned long long* rng;                     // [N]
+  uint32_t* mt;                                // [N][624] MT19937 state of the env's numpy RandomState(seed + env)
+  int* mt_pos;                                 // [N] position in the state (624 = regenerate before the next draw)
   int *robot_contype, *robot_conaff;           // [N][ngeom] saved robot masks during reset
   float* episode_reward;
 };
@@ -175,15 +176,32 @@ FE_HDN void d_transform_to_target(const double* base, const double* q, const dou
   dq_mul(new_quat, rel, q + 3);
 }
 
-// ---------------------------------------------------------------- per-env RNG (splitmix64), uniform in [lo, hi)
-FE_HD float fe_rand(unsigned long long* s, float lo, float hi) {
-  unsigned long long z = (*s += 0x9E3779B97F4A7C15ULL);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-  z ^= z >> 31;
-  float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return lo + (hi - lo) * u;
+// ---------------------------------------------------------------- per-env RNG: the reference's own generator.
+// Every reference env draws from numpy's RandomState(config.seed) (furniture.py:72; seed + rank per VecEnv worker,
+// env/base.py:77): MT19937 seeded by init_genrand, doubles as (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53, and
+// uniform(low, high) = low + (high - low) * double, two roundings (numpy legacy distributions).  The state lives in HBM
+// (2.5 KB per env) and only lane 0 touches it, in reset.
+#define FE_MT_N 624
+#define FE_MT_M 397
+FE_HD void fe_mt_twist(uint32_t* mt) {
+  int i = 0;
+  for (; i < FE_MT_N - FE_MT_M; ++i) { const uint32_t y = (mt[i] & 0x80000000u) | (mt[i + 1] & 0x7fffffffu); mt[i] = mt[i + FE_MT_M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+  for (; i < FE_MT_N - 1; ++i) { const uint32_t y = (mt[i] & 0x80000000u) | (mt[i + 1] & 0x7fffffffu); mt[i] = mt[i + (FE_MT_M - FE_MT_N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+  const uint32_t y = (mt[FE_MT_N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+  mt[FE_MT_N - 1] = mt[FE_MT_M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
+FE_HD uint32_t fe_mt_u32(uint32_t* mt, int* pos) {
+  if (*pos >= FE_MT_N) { fe_mt_twist(mt); *pos = 0; }
+  uint32_t y = mt[(*pos)++];
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+FE_HD double fe_mt_double(uint32_t* mt, int* pos) {
+  const uint32_t a = fe_mt_u32(mt, pos) >> 5, b = fe_mt_u32(mt, pos) >> 6;
+  return nddiv(ndadd(ndmul((double)a, 67108864.0), (double)b), 9007199254740992.0);
+}
+// RandomState.uniform(low, high): low + (high - low) * random_sample()
+FE_HD double fe_mt_uniform(uint32_t* mt, int* pos, double lo, double hi) { return ndadd(lo, ndmul(ndsub(hi, lo), fe_mt_double(mt, pos))); }
 
 // ---------------------------------------------------------------- env context of one warp
 struct FeEnv {
@@ -461,29 +479,33 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
   LANES_END
   LANES_BEGIN
     if (lane == 0) { // UniformRandomSampler.sample (placement_sampler.py:137-190): xy noise, z + 0.01, +furn_rot_rand deg about x
-      unsigned long long rs = e->es.rng[e->env];
+      uint32_t* mt = e->es.mt + (size_t)e->env * FE_MT_N;
+      int pos = e->es.mt_pos[e->env];
       const double half = 0.5 * (double)cfg->furn_rot_rand * 3.14159265358979323846 / 180.0;
       const double qx[4] = {cos(half), sin(half), 0.0, 0.0};
+      const double r_xy = (double)cfg->furn_xyz_rand, r_rot = (double)cfg->furn_rot_rand;
+      double px[FE_MAXPART], py[FE_MAXPART]; // placed so far, in double like the sampler's Qpos list
       for (int p = 0; p < np; ++p) {
-        float x = 0, y = 0;
-        for (int tries = 0; tries < 10000; ++tries) {
-          x = sc->part_init_pos[p][0] + fe_rand(&rs, -cfg->furn_xyz_rand, cfg->furn_xyz_rand);
-          y = sc->part_init_pos[p][1] + fe_rand(&rs, -cfg->furn_xyz_rand, cfg->furn_xyz_rand);
+        double x = 0, y = 0;
+        for (int tries = 0; tries < 10000; ++tries) { // draw order of the reference: x, y per try; the rotation draw after a valid try
+          x = ndadd((double)sc->part_init_pos[p][0], fe_mt_uniform(mt, &pos, -r_xy, r_xy));
+          y = ndadd((double)sc->part_init_pos[p][1], fe_mt_uniform(mt, &pos, -r_xy, r_xy));
           bool valid = true;
           for (int o = 0; o < p; ++o) {
-            const int qo = m->link_qadr[nrl + o];
-            const float dx = x - w->qpos()[qo], dy = y - w->qpos()[qo + 1];
-            if (sqrtf(dx * dx + dy * dy) <= sc->part_radius[o] + sc->part_radius[p]) { valid = false; break; }
+            const double dx = x - px[o], dy = y - py[o];
+            if (ndsqrt(ndadd(ndmul(dx, dx), ndmul(dy, dy))) <= (double)sc->part_radius[o] + (double)sc->part_radius[p]) { valid = false; break; } // np.linalg.norm
           }
           if (valid) break;
         }
+        (void)fe_mt_uniform(mt, &pos, r_rot, r_rot); // sample_quat: rng.uniform(high=max, low=max), a draw whose value is always max
+        px[p] = x; py[p] = y;
         const int qa = m->link_qadr[nrl + p];
-        w->qpos()[qa] = x; w->qpos()[qa + 1] = y; w->qpos()[qa + 2] = sc->part_init_pos[p][2] + 0.01f;
+        w->qpos()[qa] = (float)x; w->qpos()[qa + 1] = (float)y; w->qpos()[qa + 2] = sc->part_init_pos[p][2] + 0.01f;
         double q0[4] = {sc->part_init_quat[p][0], sc->part_init_quat[p][1], sc->part_init_quat[p][2], sc->part_init_quat[p][3]}, q[4];
         dq_mul(q, q0, qx);
         for (int k = 0; k < 4; ++k) w->qpos()[qa + 3 + k] = (float)q[k];
       }
-      e->es.rng[e->env] = rs;
+      e->es.mt_pos[e->env] = pos;
     }
   LANES_END
   // stabilise furniture: 10 x { stop(gravity=0); 10 x { forward; step; slow } }  (furniture.py:1535-1540)
@@ -506,10 +528,12 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
       if (phase <= 1) for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d];
       if (phase == 1) for (int g = lane; g < ng; g += 32) if (m->geom_tag[g] & FE_TAG_ROBOT) { w->contype()[g] = rct[g]; w->conaff()[g] = rca[g]; } // :1586-1595
       if (lane == 0) { // _initialize_robot_pos (furniture.py:1761-1779): fresh noise on every call
-        unsigned long long rs = e->es.rng[e->env];
-        for (int d = 0; d < sc->narm; ++d) w->qpos()[d] = sc->robot_init_qpos[d] + fe_rand(&rs, -cfg->agent_xyz_rand, cfg->agent_xyz_rand);
+        uint32_t* mt = e->es.mt + (size_t)e->env * FE_MT_N;
+        int pos = e->es.mt_pos[e->env];
+        const double r = (double)cfg->agent_xyz_rand; // _init_random(shape, "agent") = rng.uniform(-r, r, size=7), furniture.py:336-349
+        for (int d = 0; d < sc->narm; ++d) w->qpos()[d] = (float)ndadd((double)sc->robot_init_qpos[d], fe_mt_uniform(mt, &pos, -r, r));
         for (int d = sc->narm; d < sc->narm + sc->ngrip; ++d) w->qpos()[d] = sc->robot_init_qpos[d];
-        e->es.rng[e->env] = rs;
+        e->es.mt_pos[e->env] = pos;
       }
     LANES_END
     fe_fwd_step(e);

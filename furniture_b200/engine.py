@@ -210,18 +210,18 @@ class Engine:
         return d.value, e.value
 
     _INT = {"order", "geom_contype", "geom_conaffinity", "eq_active", "touch", "flags", "ncon", "niter", "stats", "con_geom", "con_state", "group", "site_connected",
-            "num_connected", "prev_num_connected", "touched", "picked", "episode_length", "done"}
+            "num_connected", "prev_num_connected", "touched", "picked", "episode_length", "done", "mt_pos"}
 
     def get(self, name):
         dim, eb = self.field_info(name)
-        dt = np.uint64 if eb == 8 else (np.int32 if name in self._INT else np.float32)
+        dt = np.uint64 if eb == 8 else (np.uint32 if name == "mt_state" else (np.int32 if name in self._INT else np.float32))
         out = np.empty((self.N, dim), dtype=dt)
         self._chk(self.L.fe_get_field(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
         return out
 
     def set(self, name, value):
         dim, eb = self.field_info(name)
-        dt = np.uint64 if eb == 8 else (np.int32 if name in self._INT else np.float32)
+        dt = np.uint64 if eb == 8 else (np.uint32 if name == "mt_state" else (np.int32 if name in self._INT else np.float32))
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), (self.N, dim)))
         self._chk(self.L.fe_set_field(self.h, name.encode(), v.ctypes.data_as(C.c_void_p), C.c_size_t(v.nbytes)))
 

@@ -9,8 +9,9 @@ Restates, with reference line cites:
   obs        _get_obs                                  :1344-1387, furniture_sawyer.py:103-155
   reward     _compute_reward / _after_step             :482-541, :451-480
 Used as the checker for the device env kernels and as the CPU arm of bench.py (`--impl reference`, cpu_baseline).
-Random draws use numpy's RandomState(seed) like the reference (furniture.py:72) but the engine uses its own per-env
-counter RNG, so resets are compared in distribution, not draw by draw.
+Random draws use numpy's RandomState(seed) like the reference (furniture.py:72), in the reference's order; the placement
+is pinned to the reference's own sampler code (tests/golden/placement.npz) and the engine runs the same MT19937 stream per
+env, so resets are compared draw for draw (tests/test_reset_rng.py).
 """
 from __future__ import annotations
 
@@ -108,6 +109,27 @@ class OracleFurnitureEnv:
         return np.hstack([self.sim.site_xpos[3 * s : 3 * s + 3], A._qmul(bq, self.m.site_quat[s])])
 
     # ---- reset
+    def place(self):
+        """UniformRandomSampler.sample (placement_sampler.py:137-190): per part, in XML order, x and y uniform around the XML
+        init pose until no horizontal-radius disc overlaps a part placed before, z + 0.01, then one draw for the rotation
+        noise whose value is always furn_rot_rand (uniform(high=max, low=max), :127-135).  Pinned draw for draw to the
+        reference's own sampler by tests/golden/placement.npz."""
+        m, cfg = self.m, self.cfg
+        placed, out = [], []
+        for p, name in enumerate(self.parts):
+            init = m.meta["part_init_qpos"][name]
+            r = m.meta["part_radius"][name]
+            for _ in range(10000):
+                x = init[0] + self.rng.uniform(-cfg.furn_xyz_rand, cfg.furn_xyz_rand)
+                y = init[1] + self.rng.uniform(-cfg.furn_xyz_rand, cfg.furn_xyz_rand)
+                if all(np.linalg.norm([x - px, y - py], 2) > pr + r for px, py, pr in placed):
+                    break
+            rot = self.rng.uniform(high=cfg.furn_rot_rand, low=cfg.furn_rot_rand)
+            quat = A.euler_to_quat([rot, 0, 0], init[3:7])
+            placed.append((x, y, r))
+            out.append((np.array([x, y, init[2] + 0.01]), np.asarray(quat, dtype=np.float64)))
+        return out
+
     def reset(self):
         sim, m, cfg = self.sim, self.m, self.cfg
         sim.reset()
@@ -122,19 +144,8 @@ class OracleFurnitureEnv:
         self.touched = [False] * self.npart
         self.picked = [False] * self.npart
         sim.eq_active[:] = 0
-        placed = []
-        for p, name in enumerate(self.parts):  # placement_sampler.py:137-190
-            init = m.meta["part_init_qpos"][name]
-            r = m.meta["part_radius"][name]
-            for _ in range(10000):
-                x = init[0] + self.rng.uniform(-cfg.furn_xyz_rand, cfg.furn_xyz_rand)
-                y = init[1] + self.rng.uniform(-cfg.furn_xyz_rand, cfg.furn_xyz_rand)
-                if all(np.hypot(x - px, y - py) > pr + r for px, py, pr in placed):
-                    break
-            self.rng.uniform(cfg.furn_rot_rand, cfg.furn_rot_rand)  # sample_quat draws uniform(high=max, low=max)
-            quat = A.euler_to_quat([cfg.furn_rot_rand, 0, 0], init[3:7])
-            placed.append((x, y, r))
-            self._set_qpos(p, [x, y, init[2] + 0.01], quat)
+        for p, (pos, quat) in enumerate(self.place()):
+            self._set_qpos(p, pos, quat)
         for _ in range(10):
             for p in range(self.npart):
                 self._stop(p, 0)

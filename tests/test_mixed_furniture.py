@@ -23,7 +23,7 @@ NAMES = sorted(os.path.basename(p)[len("Sawyer_") : -len(".npz")] for p in glob.
 # Six models carry no `*_initpos` numerics: the reference drops those parts at z = 0.01 wherever the sampler puts them
 # (placement_sampler.py:68-104), i.e. large panels start half inside the floor and are pushed out during the reset.  Three of
 # them start with more simultaneous contacts than the engine's per-env capacity (the reference runs with nconmax=5000) and
-# raise the overflow flag; all six come out of the reset still moving, so steps are compared loosely (chaotic contact).
+# always raise the overflow flag (the others may, depending on the draw); all six come out of the reset still moving, so steps are compared loosely (chaotic contact).
 UNLISTED = {"bookcase_billy_0191", "bookcase_grevback_0484", "cabinet_akurum_0021", "chair_agam_0005", "table_hemnes_0539", "table_klubbo_0740"}
 OVERFLOW = {"bookcase_billy_0191", "bookcase_grevback_0484", "table_hemnes_0539"}
 GPU_SUBSET = ["bookcase_expedit_0376", "chair_ingolf_0650", "table_dockstra_0279", "toy_table_flip", "three_blocks_peg", "bookcase_hensvik_0565"]
@@ -37,10 +37,11 @@ def _run(name, gpu, n=2, steps=2):
     flags = eng.get("flags")[:, 0]
     q = eng.get("qpos")
     assert np.isfinite(q).all()
-    if name in OVERFLOW:
-        assert ((flags & ~1) == 0).all(), flags  # only the capacity bit
-        eng.close()
-        return
+    if name in UNLISTED:
+        assert ((flags & ~1) == 0).all(), flags  # at most the capacity bit
+        if name in OVERFLOW or (flags != 0).any():  # how deep the panels start inside the floor depends on the draw
+            eng.close()
+            return
     assert (flags == 0).all(), flags
     assert np.allclose(np.linalg.norm(q[:, 9:].reshape(n, -1, 7)[:, :, 3:], axis=2), 1, atol=1e-5)  # unit quaternions
     if name not in UNLISTED:
