@@ -177,7 +177,7 @@ GRIPPER_INIT_QPOS = np.array([0.020833, -0.020833])  # grippers/two_finger_gripp
 
 
 def place_unlisted_parts(part_names, listed, radii, seed):
-    """Base placement of the parts whose XML carries no `<name>_initpos` numeric (6 of the shipped furniture models).
+    """Base placement of the parts whose XML carries no `<name>_initpos` numeric (7 of the shipped furniture models).
     Restates UniformRandomSampler.setup (models/tasks/placement_sampler.py:68-104 with the (0.7, 0.7, 0) table of
     floor_task.py:37): such a part starts from Qpos(0, 0, 0, identity) and is drawn once, at construction, uniformly in
     +-0.35 m in x and y, 0.01 above, rejecting draws whose horizontal-radius disc overlaps a part already placed
@@ -258,6 +258,8 @@ def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None,
     part_names = [b.get("name") for b in obj.iter("body")]  # base.py:159-167 (root.iter => document order)
     dst_asset = _section(world, "asset")
     for a in list(_section(obj, "asset")):
+        if a.get("file") is not None:  # MujocoXML.resolve_asset_dependency, models/base.py:55-62
+            a.set("file", os.path.join(assets_root, "objects", a.get("file")))
         nm = a.get("name")
         if nm is None or dst_asset.find("./{}[@name='{}']".format(a.tag, nm)) is None:
             dst_asset.append(a)
@@ -419,6 +421,35 @@ def _geom_mass_inertia(gtype, size, density):
     return m, I
 
 
+def load_stl(path):
+    """triangles (n, 3, 3) of a binary STL (the furniture meshes are Rhino binary exports)"""
+    raw = open(path, "rb").read()
+    n = int(np.frombuffer(raw[80:84], dtype="<u4")[0])
+    if len(raw) != 84 + 50 * n:
+        raise NotImplementedError("not a binary STL: " + path)
+    rec = np.frombuffer(raw[84:], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=n)
+    return rec["v"].astype(np.float64)
+
+
+def mesh_mass_properties(tri, density):
+    """mass, centre of mass and inertia tensor about it (mesh frame) of the solid bounded by a closed triangle mesh: exact
+    volume integrals over the signed tetrahedra (origin, v0, v1, v2).  MuJoCo 2.0 sums pyramids from the faces to the
+    mesh centroid, which is the same number for the closed, consistently oriented meshes shipped with the furniture."""
+    a, b, c = tri[:, 0], tri[:, 1], tri[:, 2]
+    vol6 = np.einsum("ij,ij->i", a, np.cross(b, c))  # 6 x signed volume
+    V = vol6.sum() / 6.0
+    sgn = 1.0 if V >= 0 else -1.0
+    com = (vol6[:, None] * (a + b + c)).sum(0) / (24.0 * V)
+    # second moment: for a tetrahedron (0, a, b, c), integral of x x^T dV = det / 120 * (s s^T + a a^T + b b^T + c c^T), s = a + b + c
+    sm = a + b + c
+    S = sum(np.einsum("i,ij,ik->jk", vol6, u, u) for u in (sm, a, b, c)) / 120.0
+    mass = density * abs(V)
+    S = S * sgn * density                       # density-weighted second moment about the origin
+    S -= mass * np.outer(com, com)              # ... about the centre of mass
+    I = np.trace(S) * np.eye(3) - S
+    return mass, com, I
+
+
 def compile_mjcf(xml_string, meta=None):
     root = ET.fromstring(xml_string)
     comp = root.find("compiler")
@@ -438,6 +469,13 @@ def compile_mjcf(xml_string, meta=None):
     J = dict(type=[], body=[], pos=[], axis=[], limited=[], range=[], damping=[], name=[], solref=[], solimp=[], armature=[])
     G = dict(type=[], body=[], pos=[], quat=[], size=[], contype=[], conaffinity=[], condim=[], friction=[], solref=[], solimp=[], margin=[], gap=[], name=[], density=[])
     S = dict(body=[], pos=[], quat=[], name=[])
+    meshes = {}
+    asset = root.find("asset")
+    if asset is not None:
+        for me in asset.findall("mesh"):
+            nm = me.get("name") or os.path.splitext(os.path.basename(me.get("file", "")))[0]
+            meshes[nm] = dict(file=me.get("file"), scale=_floats(me.get("scale"), 3, [1, 1, 1]))
+    mesh_inertia = {}  # body id -> [(mass, com in the body frame, inertia about it in the body frame)] of non-colliding mesh geoms
 
     def add_body(el, parent, childclass):
         attr = el.attrib
@@ -498,10 +536,19 @@ def compile_mjcf(xml_string, meta=None):
                 conaff = int(a.get("conaffinity", 1))
                 density = float(a.get("density", 1000))
                 if tname == "mesh":
-                    # visual meshes in these scenes carry contype=conaffinity=0 and density 0 (A.1);
-                    # mesh *colliders* (3 furniture models) are out of scope this round.
-                    if contype != 0 or conaff != 0 or (density != 0 and inert is None):
-                        raise NotImplementedError("mesh collider/inertia geom '%s'" % a.get("name"))
+                    # visual meshes carry contype=conaffinity=0; with density 0 they are ignored (A.1), with a density
+                    # they still add their mass and inertia to the body (4 furniture models).  Mesh *colliders*
+                    # (3 furniture models: convex hull + MPR in MuJoCo) are not implemented.
+                    if contype != 0 or conaff != 0:
+                        raise NotImplementedError("mesh collider geom '%s'" % a.get("name"))
+                    if density != 0 and inert is None:
+                        mesh = meshes.get(a.get("mesh"))
+                        if mesh is None:
+                            raise NotImplementedError("mesh asset '%s' of geom '%s' not found" % (a.get("mesh"), a.get("name")))
+                        tri = load_stl(mesh["file"]) * mesh["scale"]
+                        m_, c_, I_ = mesh_mass_properties(tri, density)
+                        Rg = q_to_mat(_orient(a))
+                        mesh_inertia.setdefault(bid, []).append((m_, _floats(a.get("pos"), 3, [0, 0, 0]) + Rg @ c_, Rg @ I_ @ Rg.T))
                     continue
                 if tname not in GEOM_TYPES:
                     raise NotImplementedError("geom type " + tname)
@@ -557,7 +604,7 @@ def compile_mjcf(xml_string, meta=None):
         if B["explicit"][b]:
             continue
         gs = [i for i in range(ngeom) if G["body"][i] == b and G["density"][i] > 0 and G["type"][i] != GEOM_PLANE]
-        if not gs:
+        if not gs and b not in mesh_inertia:
             continue
         ms, cs, Is = [], [], []
         for i in gs:
@@ -566,6 +613,10 @@ def compile_mjcf(xml_string, meta=None):
             ms.append(m)
             cs.append(G["pos"][i])
             Is.append(R @ np.diag(I) @ R.T)
+        for m, c, I in mesh_inertia.get(b, []):
+            ms.append(m)
+            cs.append(np.asarray(c, dtype=np.float64))
+            Is.append(I)
         M = sum(ms)
         if M <= 0:
             continue

@@ -1,5 +1,5 @@
 """The mixed-furniture case (BASELINE.json config 5): FurnitureSawyerEnv over every furniture XML whose
-colliders the engine supports (57 of the 64 shipped models; the other 7 need mesh colliders) -- ragged nq/nv/nefc, 2 to 14
+colliders the engine supports (61 of the 64 shipped models; the other 3 have mesh colliders) -- ragged nq/nv/nefc, 2 to 14
 parts, 1 to 37 welds, boxes and cylinders.  For each model: device reset (settle protocol of furniture.py:1406-1663), then
 env steps with random actions compared with the CPU env oracle started from the same post-reset state.
 
@@ -20,12 +20,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 COMPILED = os.path.join(os.path.dirname(HERE), "furniture_b200", "compiled")
 NAMES = sorted(os.path.basename(p)[len("Sawyer_") : -len(".npz")] for p in glob.glob(os.path.join(COMPILED, "Sawyer_*.npz")))
 
-# Six models carry no `*_initpos` numerics: the reference drops those parts at z = 0.01 wherever the sampler puts them
+# Seven models carry no `*_initpos` numerics: the reference drops those parts at z = 0.01 wherever the sampler puts them
 # (placement_sampler.py:68-104), i.e. large panels start half inside the floor and are pushed out during the reset.  Three of
 # them start with more simultaneous contacts than the engine's per-env capacity (the reference runs with nconmax=5000) and
-# always raise the overflow flag (the others may, depending on the draw); all six come out of the reset still moving, so steps are compared loosely (chaotic contact).
-UNLISTED = {"bookcase_billy_0191", "bookcase_grevback_0484", "cabinet_akurum_0021", "chair_agam_0005", "table_hemnes_0539", "table_klubbo_0740"}
-OVERFLOW = {"bookcase_billy_0191", "bookcase_grevback_0484", "table_hemnes_0539"}
+# always raise the overflow flag (the others may, depending on the draw); all seven come out of the reset still moving, so steps are compared loosely (chaotic contact).
+UNLISTED = {"bookcase_billy_0191", "bookcase_grevback_0484", "cabinet_akurum_0021", "chair_agam_0005", "table_hemnes_0539", "table_klubbo_0740", "table_liden_0921"}
+OVERFLOW = {"bookcase_billy_0191", "bookcase_grevback_0484", "table_hemnes_0539", "table_liden_0921"}
 GPU_SUBSET = ["bookcase_expedit_0376", "chair_ingolf_0650", "table_dockstra_0279", "toy_table_flip", "three_blocks_peg", "bookcase_hensvik_0565"]
 
 
@@ -70,7 +70,7 @@ def _run(name, gpu, n=2, steps=2):
 
 
 def test_compiled_tables_cover_the_supported_models():
-    assert len(NAMES) == 57 and "table_lack_0825" in NAMES and "swivel_chair_0700" in NAMES
+    assert len(NAMES) == 61 and "toy_table" in NAMES and "table_lack_0825" in NAMES and "swivel_chair_0700" in NAMES
 
 
 @pytest.mark.parametrize("name", NAMES)
