@@ -255,3 +255,39 @@ def test_full_size_batches_through_size_independent_properties(scene, n):
     for k in range(2):
         small.env_step_host(a[:8])
     assert np.array_equal(small.get("qpos"), q1[:8])
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_episode_end_and_auto_reset_follow_the_vecenv_worker(sawyer_model, gpu):
+    """SubprocVecEnv's worker resets an env as soon as it reports done and returns the reset observation with the
+    terminal reward (subproc_vec_env.py:16-20).  With max_episode_steps = 2 every second step ends an episode: the
+    device env must report done / reward / episode_length like the CPU env, and hand back the observation of a reset
+    that continues the env's numpy random stream (same placements as the oracle env seeded the same way)."""
+    m = sawyer_model
+    n, seed = 2, 321
+    eng = make_engine(m, n, gpu, seed=seed, max_episode_steps=2, nsub=10)
+    eng.env_reset()
+    envs = []
+    for i in range(n):
+        cfg = Cfg()
+        cfg.seed, cfg.max_episode_steps = seed + i, 2
+        e = OracleFurnitureEnv(m, cfg)
+        e.nsub = 10
+        e.reset()
+        envs.append(e)
+    assert np.abs(eng.get("qpos") - np.array([e.sim.qpos for e in envs])).max() < 1e-5
+    rng = np.random.RandomState(11)
+    dones = []
+    for k in range(5):
+        a = rng.uniform(-1.3, 1.3, (n, eng.act_dim)).astype(np.float32)  # beyond [-1, 1]: clipped by _setup_action
+        a[:, -1] = -0.5
+        obs, rew, done, info = eng.env_step_host(a)
+        for i, e in enumerate(envs):
+            ob, r, d, inf = e.step(a[i].astype(np.float64))
+            if d:
+                ob = e.reset()  # the worker's auto-reset
+            assert bool(done[i]) == d and abs(rew[i] - r) < 1e-5
+            assert info[i][3] == inf["episode_length"]
+            assert np.abs(obs[i] - ob).max() < 2e-4, (k, i, np.abs(obs[i] - ob).max())
+        dones.append(done.copy())
+    assert [bool(d[0]) for d in dones] == [False, True, False, True, False]
