@@ -16,10 +16,10 @@
 #define FE_FN __device__ __noinline__
 #define FE_HDN __device__ __noinline__
 #define FE_BOTH __host__ __device__ __forceinline__
-#define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u); {
+#define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u); (void)lane; {
 #define LANES_END } } __syncwarp();
 // register-only region: touches lane-private values only, so no barrier is needed after it
-#define REGS_BEGIN { const int lane = (int)(threadIdx.x & 31u); {
+#define REGS_BEGIN { const int lane = (int)(threadIdx.x & 31u); (void)lane; {
 #define REGS_END } }
 #define FE_LDG(p) __ldg(p)
 #define FE_SYNC __syncwarp()

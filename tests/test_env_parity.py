@@ -291,3 +291,31 @@ def test_episode_end_and_auto_reset_follow_the_vecenv_worker(sawyer_model, gpu):
             assert np.abs(obs[i] - ob).max() < 2e-4, (k, i, np.abs(obs[i] - ob).max())
         dones.append(done.copy())
     assert [bool(d[0]) for d in dones] == [False, True, False, True, False]
+
+
+@pytest.mark.gpu
+def test_long_random_rollout_stays_physical():
+    """1024 envs x 40 env steps (2000 mj_steps each) of uniform random actions, the bench workload: observations stay
+    finite, no part sinks through the floor or flies off, quaternions stay unit, no solver failure bit is raised, at most
+    the (rare, flagged) contact-capacity bit; envs the engine reports unstable are reset and counted, not hidden."""
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    n = 1024
+    eng = make_engine(m, n, True, seed=7)
+    eng.env_reset()
+    rng = np.random.RandomState(0)
+    unstable = 0
+    for k in range(40):
+        a = rng.uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
+        obs, rew, done, info = eng.env_step_host(a)
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+        unstable += int(info[:, 2].sum())
+        assert (info[:, 3] == k + 1)[~done.astype(bool)].all()
+    q = eng.get("qpos")
+    parts = q[:, 9:].reshape(n, 5, 7)
+    assert parts[:, :, 2].min() > -0.01 and parts[:, :, 2].max() < 1.5, (parts[:, :, 2].min(), parts[:, :, 2].max())
+    assert np.abs(parts[:, :, :2]).max() < 3.0
+    assert np.abs(np.linalg.norm(parts[:, :, 3:], axis=2) - 1).max() < 1e-4
+    flags = eng.get("flags")[:, 0]
+    assert ((flags & ~1) == 0).all(), np.unique(flags)
+    assert (flags & 1).mean() < 0.01
+    assert unstable <= n // 100
