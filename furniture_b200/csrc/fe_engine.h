@@ -1475,20 +1475,20 @@ FE_FN void fe_solve_coop(FeWarp* w) {
   }
   LANES_BEGIN if (lane == 0) w->u()[6] += 1; LANES_END
   const float scale = 1.0f / (m->meaninertia * (float)(m->nv > 1 ? m->nv : 1));
-  // warm start candidate (stored in qacc coordinates) -> z coordinates; pick the cheaper of warm / smooth
-  float best = 0.f;
+  // warm start candidate (stored in qacc coordinates) -> z coordinates; pick the cheaper of warm / smooth.  The smooth
+  // candidate is costed first: the warm start usually wins, and its products (Ma, jar) are then already in place.
+  LANES_BEGIN
+    for (int i = lane; i < nv; i += 32) w->search()[i] = w->as()[i];
+    for (int d = lane; d < nr; d += 32) w->x()[d] = w->warm()[d];
+    for (int p = lane; p < np; p += 32) {
+      const int da = m->link_dadr[nrl + p], z = nr + 6 * p;
+      m3mulv(w->x() + z, w->lmat() + 9 * (nrl + p), w->warm() + da + 3);
+      v3cpy(w->x() + z + 3, w->warm() + da);
+    }
+  LANES_END
+  float cost_smooth = 0.f, cost_warm = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
-    LANES_BEGIN
-      if (pass == 0) {
-        for (int d = lane; d < nr; d += 32) w->x()[d] = w->warm()[d];
-        for (int p = lane; p < np; p += 32) {
-          const int da = m->link_dadr[nrl + p], z = nr + 6 * p;
-          m3mulv(w->x() + z, w->lmat() + 9 * (nrl + p), w->warm() + da + 3);
-          v3cpy(w->x() + z + 3, w->warm() + da);
-        }
-      } else for (int i = lane; i < nv; i += 32) w->search()[i] = w->as()[i];
-    LANES_END
-    float* cand = pass == 0 ? w->x() : w->search();
+    float* cand = pass == 0 ? w->search() : w->x();
     fe_mul_M(w, cand, w->Ma());
     fe_mul_J(w, cand, w->c_jar(), w->w_jar(), w->l_jar(), true);
     float cost = fe_update(w);
@@ -1498,12 +1498,12 @@ FE_FN void fe_solve_coop(FeWarp* w) {
       w->scr()[lane] = s;
     LANES_END
     cost += fe_sum32(w->scr());
-    if (pass == 0) best = cost;
-    else if (cost < best || !(best == best)) { LANES_BEGIN for (int i = lane; i < nv; i += 32) w->x()[i] = w->as()[i]; LANES_END }
-    else { // keep the warm start: recompute its products
-      fe_mul_M(w, w->x(), w->Ma());
-      fe_mul_J(w, w->x(), w->c_jar(), w->w_jar(), w->l_jar(), true);
-    }
+    if (pass == 0) cost_smooth = cost; else cost_warm = cost;
+  }
+  if (cost_smooth < cost_warm || !(cost_warm == cost_warm)) { // the unconstrained acceleration is the better start: redo its products
+    LANES_BEGIN for (int i = lane; i < nv; i += 32) w->x()[i] = w->as()[i]; LANES_END
+    fe_mul_M(w, w->x(), w->Ma());
+    fe_mul_J(w, w->x(), w->c_jar(), w->w_jar(), w->l_jar(), true);
   }
   // active set of the register-resident Newton direction: the robot dofs plus every part that a constraint couples to
   // another moving block (decided by constraint kind, not by contact state, so it is fixed for the whole solve); the
