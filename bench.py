@@ -27,6 +27,11 @@ B_ENV = 58700  # algorithmic bytes per env-step, SURVEY.md 8d: 50 * 4*(2 nq + 5 
 WORKLOAD = "FurnitureSawyerEnv + table_lack_0825, control_type=impedance, 50 mj_steps per env-step, random actions U(-1,1)"
 
 
+def b_env(model, obs_dim, act_dim, nsub=50):
+    """B_sub = 4 (2 nq + 5 nv + nu) per mj_step; B_env = nsub B_sub + 4 (obs + act) + 8"""
+    return nsub * 4 * (2 * model.nq + 5 * model.nv + model.nu) + 4 * (obs_dim + act_dim) + 8
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -164,14 +169,18 @@ def run_ours(args):
 
     n_local = args.envs_per_gpu
     if world > 1:
-        env = ShardedFurnitureEnv(n_local)
+        env = ShardedFurnitureEnv(n_local, furniture_name=args.furniture)
         benv = env.env
     else:
-        env = benv = BatchedFurnitureEnv("Sawyer", "table_lack_0825", n_local, device=local, seed=123)
+        env = benv = BatchedFurnitureEnv("Sawyer", args.furniture, n_local, device=local, seed=123)
     env.reset()
     gen = torch.Generator(device=dev).manual_seed(rank)
     K, W = args.steps, args.warmup
     acts = [torch.rand((n_local, benv.act_dim), device=dev, generator=gen) * 2 - 1 for _ in range(K + W)]
+    if args.actions == "settled":  # SURVEY.md 8d "settled" variant: zero arm action, gripper open, no connect request
+        for a in acts:
+            a.zero_()
+            a[:, -2:] = -1.0
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2 (126 MB)
 
     def barrier():
@@ -226,24 +235,30 @@ def run_ours(args):
     if rank == 0:
         peaks, peak_src = load_peaks()
         kernel_ms = total_ms / K  # one env-step = one launch of fe_env_step_kernel (+ the all_gather when N > 1)
-        achieved = B_ENV * n_local / (kernel_ms * 1e-3) / 1e9
+        benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim)
+        assert args.furniture != "table_lack_0825" or benv_bytes == B_ENV
+        achieved = benv_bytes * n_local / (kernel_ms * 1e-3) / 1e9
+        workload = WORKLOAD if (args.furniture == "table_lack_0825" and args.actions == "random") else (
+            "FurnitureSawyerEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.furniture, "random actions U(-1,1)" if args.actions == "random" else "settled (zero arm action, gripper open)"))
+        default_case = args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and default_case:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+            "metric": METRIC if default_case else "aggregate env-steps/sec, Sawyer+%s @%d envs/GPU (%s actions)" % (args.furniture, n_local, args.actions),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n_local, "global_envs": n_local * world, "parallelism": "env-shards x%d" % world,
+            "config": {"workload": workload, "envs_per_gpu": n_local, "global_envs": n_local * world, "parallelism": "env-shards x%d" % world,
                        "l2": "flushed between timed steps (256 MiB write)", "timing": "CUDA events per step on the launch stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                         "kernel": "fe_env_step_kernel", "algorithmic_bytes_per_launch": B_ENV * n_local, "peak_source": peak_src,
+                         "kernel": "fe_env_step_kernel", "algorithmic_bytes_per_launch": benv_bytes * n_local, "peak_source": peak_src,
                          "note": "state stays in shared memory for the 50 mj_steps of a launch; the path is latency/issue bound, not HBM bound (DESIGN.md)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and default_case:
             v, n = cpu_env_rate(args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": "%d env.step() of one CPU oracle env (oracle/ref_env.py over oracle/fe_oracle.c) in %.0f s" % (n, args.cpu_seconds)}
@@ -262,6 +277,8 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--furniture", default="table_lack_0825", help="other furniture = parity-test configs timed for DESIGN.md, not the bench line")
+    ap.add_argument("--actions", default="random", choices=["random", "settled"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
