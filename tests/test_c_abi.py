@@ -1,0 +1,66 @@
+"""The drop-in boundary: furniture_b200/libfurniture_b200.so must load without a GPU and export every entry point that
+include/furniture_b200.h declares; blob sizes must agree with the Python-side struct layouts; the error path of
+fe_create must answer with a code and a message instead of crashing (no device work is attempted on the CPU box)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "furniture_b200.h")
+LIB = os.path.join(ROOT, "furniture_b200", "libfurniture_b200.so")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fe_[a-z_0-9]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        pytest.fail("CUDA library not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    return C.CDLL(LIB)
+
+
+def test_every_declared_entry_point_is_exported(lib):
+    names = declared_functions()
+    assert len(names) >= 20 and "fe_env_step" in names and "fe_create" in names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_blob_sizes_match_the_python_layouts(lib):
+    from furniture_b200.engine import FeConfig, FeScene
+    from furniture_b200.engine_model import FeModel
+
+    for fn, cls in (("fe_model_sizeof", FeModel), ("fe_scene_sizeof", FeScene), ("fe_config_sizeof", FeConfig)):
+        f = getattr(lib, fn)
+        f.restype = C.c_size_t
+        assert f() == C.sizeof(cls), fn
+    assert lib.fe_is_cuda() == 1  # the shipped library is the CUDA build, not the lane-emulated harness
+
+
+def test_create_rejects_bad_blobs_with_a_message(lib):
+    from furniture_b200.engine import default_config
+
+    lib.fe_last_error.restype = C.c_char_p
+    lib.fe_last_error.argtypes = [C.c_void_p]
+    h = C.c_void_p()
+    cfg = default_config()
+    junk = (C.c_char * 64)()
+    rc = lib.fe_create(junk, C.c_size_t(64), None, C.c_size_t(0), C.byref(cfg), 4, 0, C.byref(h))
+    assert rc < 0 and not h.value
+    assert len(lib.fe_last_error(None)) > 0
+
+
+def test_engine_refuses_to_run_without_the_cuda_library(tmp_path):
+    """no CPU fallback: a missing library is an error, not a silent switch to another path"""
+    from furniture_b200 import mjcf
+    from furniture_b200.engine import Engine
+
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    with pytest.raises(RuntimeError):
+        Engine(m, 2, lib_path=str(tmp_path / "nope.so"))
