@@ -33,7 +33,7 @@ typedef struct fe_handle fe_handle;
 
 typedef struct fe_config {
   int32_t struct_bytes;      /* sizeof(fe_config), checked */
-  int32_t maxcon;            /* contact capacity per env (MuJoCo: nconmax, base.xml:5) */
+  int32_t maxcon;            /* contact capacity per env (MuJoCo: nconmax, base.xml:5); an env that overflows raises bit 0 of `flags` */
   int32_t newton_iters;      /* max Newton iterations per mj_step (MuJoCo default 100) */
   int32_t ls_iters;          /* max line-search evaluations per Newton iteration */
   float tolerance;           /* solver tolerance on scaled improvement / gradient (MuJoCo: 1e-8 in double) */
@@ -43,7 +43,8 @@ typedef struct fe_config {
   double alignment_pos_dist, alignment_rot_dist_up, alignment_rot_dist_forward, alignment_project_dist; /* :203-226 */
   float ctrl_penalty_coef, unstable_penalty_coef, success_reward, touch_reward, pick_reward;            /* :291-295 */
   float furn_xyz_rand, furn_rot_rand, agent_xyz_rand; /* :177-194 */
-  uint64_t seed;             /* per-env streams are derived from seed + env index (env/base.py:77) */
+  uint64_t seed;             /* env i draws its resets from numpy's RandomState(seed + i) stream: MT19937 state per env
+                                (fields mt_state / mt_pos), the reference's draw order (furniture.py:72, env/base.py:77) */
 } fe_config;
 
 /* sizes of the blobs the host packs (furniture_b200/engine_model.py, furniture_b200/scene.py) */
@@ -68,7 +69,7 @@ int fe_smem_bytes_per_env(const fe_handle* h); /* shared-memory working set of o
 int fe_sim_forward(fe_handle* h, void* stream);
 int fe_sim_step(fe_handle* h, int nsub, void* stream);
 /* named per-env arrays, host side; bytes must equal n_envs * dim * sizeof(elem). Names: qpos qvel ctrl qfrc_applied
-   qacc_warmstart gravcomp eq_data eq_active geom_contype geom_conaffinity (read/write); qfrc_bias link_xpos link_xquat
+   qacc_warmstart gravcomp eq_data eq_active geom_contype geom_conaffinity mt_state (624 x uint32) mt_pos (read/write); qfrc_bias link_xpos link_xquat
    link_xmat link_vel touch ncon niter flags + the debug fields of the last fe_sim_forward (read only) */
 int fe_get_field(fe_handle* h, const char* name, void* dst_host, size_t bytes);
 int fe_set_field(fe_handle* h, const char* name, const void* src_host, size_t bytes);
