@@ -1385,24 +1385,122 @@ FE_FN void fe_newton_regs(FeWarp* w, int nA) {
     }
     PV(b_) = zi >= 0 ? -w->grad()[zi] : 0.f;
   REGS_END
-  for (int c = 0; c < ncon; ++c) {
-    const int st = w->c_state()[c];
-    if (st == 0 || w->c_kind()[c] == 0) continue;
-    const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
-    float W[9];
-    fe_contact_weight(w, c, st, W);
-    REGS_BEGIN
-      float col[3];
-      fe_contact_col(w, c, PV(z_), A, B, col);
-      PV(c0_) = col[0]; PV(c1_) = col[1]; PV(c2_) = col[2];
-      PV(t0_) = W[0] * col[0] + W[1] * col[1] + W[2] * col[2];
-      PV(t1_) = W[3] * col[0] + W[4] * col[1] + W[5] * col[2];
-      PV(t2_) = W[6] * col[0] + W[7] * col[1] + W[8] * col[2];
-    REGS_END
+  // Coupling contacts, grouped by the pair of links they join.  A contact row is G_c d, with d the 6-vector [angular; linear at
+  // p0] that a unit of the dof contributes to the relative motion of the two links (B side minus A side) and
+  // G_c = [(r_c x F_k)^T, F_k^T] (3 x 6, r_c = p_c - p0, p0 = the first contact point of the pair).  So the contacts of one
+  // pair add d_i^T K d_j to H with ONE 6x6 matrix K = sum_c G_c^T W_c G_c: lane = contact builds its term, a warp sum per
+  // entry of K, then a rank-6 update of the rows (6 shuffles per column) instead of a rank-3 update per contact.
+  {
+    const fe_model* m = w->m;
+    const int nr = m->nr, nrl = m->nrlink;
+    FE_PRIVA(float, kq_, 21);
+    FE_PRIVA(float, d_, 6); FE_PRIVA(float, u_, 6);
+    FE_PRIV(float, px_); FE_PRIV(float, py_); FE_PRIV(float, pz_); FE_PRIV(float, ox_); FE_PRIV(float, oy_); FE_PRIV(float, oz_);
+    FE_PRIV(float, ks_); FE_PRIV(float, kf_);
+    FE_PRIV(int, key_); FE_PRIV(int, lead_); FE_PRIV(int, isl_);
+    for (int base = 0; base < ncon; base += 32) {
+      REGS_BEGIN
+        const int c = base + lane;
+        int key = -1 - lane; // lanes without a coupling contact: keys that match nobody
+        PV(px_) = PV(py_) = PV(pz_) = 0.f;
+        if (c < ncon && w->c_state()[c] != 0 && w->c_kind()[c] != 0) {
+          key = w->c_link()[c];
+          PV(px_) = w->c_pos()[3 * c]; PV(py_) = w->c_pos()[3 * c + 1]; PV(pz_) = w->c_pos()[3 * c + 2];
+        }
+        PV(key_) = key;
+      REGS_END
+      FE_MATCH_LEADER(lead_, PV_ALL(key_));
+      FE_SHFLV(ox_, PV_ALL(px_), PV_ALL(lead_)); FE_SHFLV(oy_, PV_ALL(py_), PV_ALL(lead_)); FE_SHFLV(oz_, PV_ALL(pz_), PV_ALL(lead_));
+      REGS_BEGIN
+        const int c = base + lane;
 #pragma unroll
-    for (int j = 0; j < NMAX; ++j) {
-      FE_SHFL(s0_, c0_, j); FE_SHFL(s1_, c1_, j); FE_SHFL(s2_, c2_, j);
-      REGS_BEGIN PV(row_)[j] += PV(t0_) * PV(s0_) + PV(t1_) * PV(s1_) + PV(t2_) * PV(s2_); REGS_END
+        for (int k = 0; k < 21; ++k) PV(kq_)[k] = 0.f;
+        PV(isl_) = (PV(key_) >= 0 && PV(lead_) == lane) ? 1 : 0;
+        if (PV(key_) >= 0) {
+          float F[9], W[9], G[18], WG[18];
+          fe_frame_load(w, c, F);
+          fe_contact_weight(w, c, w->c_state()[c], W);
+          const float r[3] = {PV(px_) - PV(ox_), PV(py_) - PV(oy_), PV(pz_) - PV(oz_)};
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { v3cross(G + 6 * k, r, F + 3 * k); G[6 * k + 3] = F[3 * k]; G[6 * k + 4] = F[3 * k + 1]; G[6 * k + 5] = F[3 * k + 2]; }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            WG[i] = W[0] * G[i] + W[1] * G[6 + i] + W[2] * G[12 + i];
+            WG[6 + i] = W[3] * G[i] + W[4] * G[6 + i] + W[5] * G[12 + i];
+            WG[12 + i] = W[6] * G[i] + W[7] * G[6 + i] + W[8] * G[12 + i];
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) PV(kq_)[i * (i + 1) / 2 + j] = G[i] * WG[j] + G[6 + i] * WG[6 + j] + G[12 + i] * WG[12 + j];
+        }
+      REGS_END
+      unsigned todo = FE_BALLOTP(PV_ALL(isl_));
+      while (todo) {
+        int g = 0;
+        while (!((todo >> g) & 1u)) ++g;
+        todo &= todo - 1u;
+        // uniform description of the pair: key, reference point
+        FE_SHFL(ks_, PV_ALL(px_), g); const float p0x = FE_UNI(ks_);
+        FE_SHFL(ks_, PV_ALL(py_), g); const float p0y = FE_UNI(ks_);
+        FE_SHFL(ks_, PV_ALL(pz_), g); const float p0z = FE_UNI(ks_);
+        REGS_BEGIN PV(kf_) = (float)PV(key_); REGS_END // link ids fit a float exactly (two bytes)
+        FE_SHFL(ks_, PV_ALL(kf_), g);
+        const int gkey = (int)FE_UNI(ks_), A = (gkey & 255) - 1, B = (gkey >> 8) - 1;
+        // this lane's dof: its unit contribution to the relative twist of the pair, at p0
+        REGS_BEGIN
+          const int z = PV(z_);
+          float d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (z >= 0 && z < nr) {
+            const float sg = ((B >= 0 && B < nrl && ((m->link_ancmask[B] >> z) & 1)) ? 1.f : 0.f) - ((A >= 0 && A < nrl && ((m->link_ancmask[A] >> z) & 1)) ? 1.f : 0.f);
+            if (sg != 0.f) {
+              const float* S = w->S() + 6 * z;
+              const float r[3] = {p0x - m->robot_ref[0], p0y - m->robot_ref[1], p0z - m->robot_ref[2]};
+              float t[3];
+              v3cross(t, S, r);
+              d[0] = sg * S[0]; d[1] = sg * S[1]; d[2] = sg * S[2]; d[3] = sg * (S[3] + t[0]); d[4] = sg * (S[4] + t[1]); d[5] = sg * (S[5] + t[2]);
+            }
+          } else if (z >= nr) {
+            const int part = (z - nr) / 6, jj = (z - nr) % 6, l = nrl + part;
+            const float sg = l == B ? 1.f : (l == A ? -1.f : 0.f);
+            if (sg != 0.f) {
+              if (jj < 3) {
+                const float e[3] = {jj == 0 ? 1.f : 0.f, jj == 1 ? 1.f : 0.f, jj == 2 ? 1.f : 0.f};
+                const float r[3] = {p0x - w->lpos()[3 * l], p0y - w->lpos()[3 * l + 1], p0z - w->lpos()[3 * l + 2]};
+                float t[3];
+                v3cross(t, e, r);
+                d[0] = sg * e[0]; d[1] = sg * e[1]; d[2] = sg * e[2]; d[3] = sg * t[0]; d[4] = sg * t[1]; d[5] = sg * t[2];
+              } else d[jj] = sg;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) PV(d_)[k] = d[k];
+        REGS_END
+        // K d_i: entry by entry, K[a][b] = warp sum of the members' terms
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { REGS_BEGIN PV(u_)[k] = 0.f; REGS_END }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            REGS_BEGIN PV(ks_) = ((float)PV(key_) == (float)gkey) ? PV(kq_)[a * (a + 1) / 2 + b] : 0.f; REGS_END
+            FE_WSUM(ks_);
+            REGS_BEGIN
+              PV(u_)[a] += PV(ks_) * PV(d_)[b];
+              if (a != b) PV(u_)[b] += PV(ks_) * PV(d_)[a];
+            REGS_END
+          }
+        }
+        // rank-6 update: row_i[j] += u_i . d_j
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            FE_SHFLA(ks_, d_, k, j);
+            REGS_BEGIN PV(row_)[j] += PV(u_)[k] * PV(ks_); REGS_END
+          }
+        }
+      }
     }
   }
   // right-looking Cholesky

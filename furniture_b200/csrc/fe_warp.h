@@ -111,6 +111,11 @@ FE_HD int fe_popc(unsigned x) {
 #define FE_SHFL(dst, src, idx) do { dst = __shfl_sync(0xffffffffu, src, (idx)); } while (0)
 #define FE_SHFLA(dst, arr, elem, idx) do { dst = __shfl_sync(0xffffffffu, arr[elem], (idx)); } while (0)
 #define FE_UNI(name) (name) /* a private value known to be equal on all lanes (after a collective) */
+// lane-indexed shuffle (every lane names its own source lane), ballot of a private predicate, and for every lane the lowest
+// lane that holds the same key
+#define FE_SHFLV(dst, src, idx) do { dst = __shfl_sync(0xffffffffu, src, (idx)); } while (0)
+#define FE_BALLOTP(name) __ballot_sync(0xffffffffu, (name) != 0)
+#define FE_MATCH_LEADER(dst, key) do { dst = __ffs(__match_any_sync(0xffffffffu, (key))) - 1; } while (0)
 #else
 #define FE_PRIV(T, name) T name[32]
 #define FE_PRIVA(T, name, n) T name[32][n]
@@ -147,6 +152,10 @@ static inline void fe_emu_wsum(float* a) {
 #define FE_SHFL(dst, src, idx) do { const float t_shfl_ = src[(idx)]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = t_shfl_; } while (0)
 #define FE_SHFLA(dst, arr, elem, idx) do { const float t_shfl_ = arr[(idx)][(elem)]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = t_shfl_; } while (0)
 #define FE_UNI(name) (name[0])
+#define FE_SHFLV(dst, src, idx) do { float t_sv_[32]; for (int i_ = 0; i_ < 32; ++i_) t_sv_[i_] = src[idx[i_] & 31]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = t_sv_[i_]; } while (0)
+static inline unsigned fe_emu_ballotp(const int* a) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= (a[i] != 0 ? 1u : 0u) << i; return r; }
+#define FE_BALLOTP(name) fe_emu_ballotp(name)
+#define FE_MATCH_LEADER(dst, key) do { for (int i_ = 0; i_ < 32; ++i_) { int l_ = i_; for (int j_ = 0; j_ < i_; ++j_) if (key[j_] == key[i_]) { l_ = j_; break; } dst[i_] = l_; } } while (0)
 #endif
 
 // ---------------------------------------------------------------- small vector math (fp32)
