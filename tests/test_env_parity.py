@@ -319,3 +319,37 @@ def test_long_random_rollout_stays_physical():
     assert ((flags & ~1) == 0).all(), np.unique(flags)
     assert (flags & 1).mean() < 0.01
     assert unstable <= n // 100
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_last_connection_ends_the_episode_with_success(sawyer_model, gpu):
+    """success test of FurnitureEnv._step (furniture.py:440-445): with three of the four welds already counted, the
+    connection made in this step brings num_connected to npart - 1: success reward, done, info.success, and -- as a
+    VecEnv worker does -- the observation handed back is that of the reset that follows."""
+    m = sawyer_model
+    seed = 77
+    cfg = Cfg()
+    cfg.seed = seed
+    env = OracleFurnitureEnv(m, cfg)
+    env.reset()
+    q = _grasp_and_align_state(m, env)
+    env.nsub = 1
+    env.sim.qvel[:] = 0; env.sim.qacc_warmstart[:] = 0; env.sim.ctrl[:] = 0
+    env.sim.forward()
+    env.num_connected = env.prev_num_connected = 3
+    eng = make_engine(m, 1, gpu, nsub=1, seed=seed)
+    eng.env_reset()
+    eng.set("qpos", q); eng.set("qvel", np.zeros(m.nv)); eng.set("qacc_warmstart", np.zeros(m.nv))
+    eng.set("num_connected", 3); eng.set("prev_num_connected", 3)
+    eng.forward()
+    a = np.zeros((1, eng.act_dim), np.float32)
+    a[:, -2] = 1.0
+    a[:, -1] = 1.0
+    obs, rew, done, info = eng.env_step_host(a)
+    ob, r, d, inf = env.step(a[0].astype(np.float64))
+    assert d and inf["success"] == 1 and inf["num_connected"] == 4, "the CPU env did not finish: test state is wrong"
+    assert bool(done[0]) and info[0][1] == 1 and info[0][0] == 4
+    assert abs(rew[0] - r) < 1e-3 and rew[0] > cfg.success_reward
+    ob = env.reset()  # the worker's auto-reset; the device env has done the same inside the step
+    assert np.abs(obs[0] - ob).max() < 2e-4
+    assert (eng.get("num_connected") == 0).all() and (eng.get("eq_active") == 0).all()
