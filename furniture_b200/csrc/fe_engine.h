@@ -1369,8 +1369,7 @@ template <int NMAX>
 FE_FN void fe_newton_regs(FeWarp* w, int nA) {
   const int ncon = w->u()[0];
   FE_PRIVA(float, row_, NMAX);
-  FE_PRIV(float, c0_); FE_PRIV(float, c1_); FE_PRIV(float, c2_); FE_PRIV(float, t0_); FE_PRIV(float, t1_); FE_PRIV(float, t2_);
-  FE_PRIV(float, s0_); FE_PRIV(float, s1_); FE_PRIV(float, s2_); FE_PRIV(float, b_); FE_PRIV(float, dinv_); FE_PRIV(float, q_);
+  FE_PRIV(float, s0_); FE_PRIV(float, s1_); FE_PRIV(float, b_); FE_PRIV(float, dinv_); FE_PRIV(float, q_);
   FE_PRIV(int, z_); FE_PRIV(int, bad_);
   REGS_BEGIN
     const int i = lane, zi = i < nA ? w->colmap()[i] : -1;
