@@ -193,6 +193,23 @@ class MixedFurnitureEnv:
             b.close()
 
 
+def shard_furniture(names, envs_per_model, world, nv=None):
+    """Whole furniture buckets per GPU for a mixed batch ("bucket by furniture id first so each GPU gets
+    whole buckets, balance by sum nv^3"): longest-processing-time greedy on envs * nv^3 (nv from the compiled tables unless
+    given).  Returns, per rank, the list of (name, envs) it owns; every rank computes the same answer."""
+    counts = [envs_per_model] * len(names) if isinstance(envs_per_model, int) else list(envs_per_model)
+    if nv is None:
+        nv = [mjcf.load_scene("Sawyer", n).nv for n in names]
+    cost = [c * float(v) ** 3 for c, v in zip(counts, nv)]
+    order = sorted(range(len(names)), key=lambda i: (-cost[i], names[i]))
+    load, owned = [0.0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += cost[i]
+        owned[r].append((names[i], counts[i]))
+    return owned
+
+
 class ShardedFurnitureEnv:
     """One process per GPU (torch.distributed, backend nccl). Each rank steps its own contiguous env shard; after the
     step one all_gather makes the packed [obs | reward | done] of every shard visible on every rank."""

@@ -119,3 +119,17 @@ def test_mixed_batch_buckets_are_independent_and_layout_switching_is_ordered():
         alone.close()
         off += n
     env.close()
+
+
+def test_furniture_buckets_are_spread_over_ranks_by_cost():
+    """mixed batch over several GPUs: whole buckets per rank, balanced by envs * nv^3, same answer on every rank"""
+    from furniture_b200.env import shard_furniture
+
+    nv = {n: mjcf.load_scene("Sawyer", n).nv for n in NAMES}
+    owned = shard_furniture(NAMES, 128, 8, nv=[nv[n] for n in NAMES])
+    assert sorted(n for r in owned for n, _ in r) == NAMES and all(c == 128 for r in owned for _, c in r)
+    load = [sum(c * nv[n] ** 3 for n, c in r) for r in owned]
+    assert max(load) < 1.15 * (sum(load) / 8)  # LPT keeps the heaviest rank within 15 % of the mean here
+    assert owned == shard_furniture(NAMES, 128, 8, nv=[nv[n] for n in NAMES])
+    one = shard_furniture(["table_lack_0825", "toy_table"], [10, 20], 1, nv=[39, 39])
+    assert one == [[("toy_table", 20), ("table_lack_0825", 10)]]
