@@ -9,8 +9,11 @@
  *
  * PARITY UNPINNED for the physics: the reference holds no golden vector / known-answer test for any qpos/qvel/contact
  * value and no MuJoCo binary exists in this container, so this oracle is pinned only by its own
- * physical-consistency tests (tests/test_oracle_physics.py).  The assembly logic (_is_aligned/_connect) IS pinned
- * bit-exactly against the reference's own Python (oracle/assembly_oracle.py, tests/golden/).
+ * physical-consistency tests (tests/test_oracle_physics.py) and by two numbers MuJoCo itself produced: the height and the
+ * tilt at which the swivel-chair base rests in the reference's demo recordings (demos/Sawyer_7.pkl, Cursor_7.pkl ->
+ * tests/golden/demo_facts.json), which the oracle's reset reproduces to 4e-8 m and 1e-7 -- an equilibrium of the soft-contact
+ * model, not a trajectory.  The assembly logic (_is_aligned/_connect) and the reset placement sampler ARE pinned bit-exactly
+ * against the reference's own Python (oracle/assembly_oracle.py, oracle/ref_env.py place(), tests/golden/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
  */

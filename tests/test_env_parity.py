@@ -90,6 +90,10 @@ def test_env_reset_and_step_swivel_chair(swivel_model, gpu):
     assert (eng.get("flags") == 0).all()
     q = eng.get("qpos")
     assert np.allclose(q[:, 9 + 2], 0.007, atol=3e-4), q[:, 9 + 2]
+    if not gpu:  # the reference's own MuJoCo recording has the base at rest at 0.0069975 (tests/golden/demo_facts.json)
+        import json, os
+        z_demo = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "demo_facts.json")))["swivel_chair_base_rest_z"]
+        assert np.abs(q[:, 9 + 2] - z_demo).max() < 2e-7, (q[:, 9 + 2], z_demo)
     envs = [OracleFurnitureEnv(m) for _ in range(n)]
     for i, e in enumerate(envs):
         e.reset()

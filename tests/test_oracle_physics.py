@@ -212,3 +212,26 @@ def test_narrowphase_geometry(pair):
     assert np.allclose(nrm, expect, atol=1e-5), nrm
     if pair == "box_box_face":
         assert len(cs) == 4
+
+
+def test_chair_base_rests_where_the_reference_recording_has_it():
+    """demos/Sawyer_7.pkl (a MuJoCo run of FurnitureSawyerEnv + swivel_chair_0700 recorded by the reference's authors) has the chair
+    base at rest at z = 0.0069975: 2.5 micrometres of equilibrium penetration of five cylinders lying on the floor.  The value
+    depends on the geom masses (density x volume), gravity, the cylinder-plane contact points and the solref / solimp impedance
+    of the soft-contact model -- the oracle's reset protocol must land on it (tests/golden/demo_facts.json, 1e-7)."""
+    import json
+    import os
+
+    from furniture_b200 import mjcf
+    from oracle.ref_env import OracleFurnitureEnv
+
+    z_demo = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "demo_facts.json")))["swivel_chair_base_rest_z"]
+    m = mjcf.load_scene("Sawyer", "swivel_chair_0700")
+    env = OracleFurnitureEnv(m)
+    env.reset()
+    assert abs(env._qpos(0)[2] - z_demo) < 1e-7, (env._qpos(0)[2], z_demo)
+    # ... leaning by the same 0.028 degrees about its x axis (the five cylinders are not symmetric about the centre of mass)
+    facts = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "demo_facts.json")))
+    qx_demo, qy_demo = facts["swivel_chair_base_rest_quat"][1], facts["swivel_chair_base_rest_quat"][2]
+    quat = env._qpos(0)[3:]
+    assert abs(quat[1] - qx_demo) < 2e-6 and abs(quat[2] - qy_demo) < 2e-6, (quat, qx_demo, qy_demo)

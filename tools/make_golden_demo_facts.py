@@ -1,0 +1,37 @@
+"""Physical facts read off the reference's own demo recording (demos/Sawyer_7.pkl: states logged from a real MuJoCo run of
+FurnitureSawyerEnv + swivel_chair_0700; legacy format, qpos only): the height at which the chair base rests on the floor and
+the small tilt it rests with (Cursor_7.pkl, same furniture).
+That number is an equilibrium of the soft-contact model (geom masses from density, gravity, cylinder-plane contacts, solref /
+solimp impedance), so it pins those parts of the physics oracle against MuJoCo itself.  The assembled relative poses at the
+end of the recording are NOT usable: they match neither the current XML sites nor its weld data (older model version).
+Needs /root/reference; writes tests/golden/demo_facts.json."""
+import json
+import os
+import pickle
+
+import numpy as np
+
+REF = "/root/reference/demos/Sawyer_7.pkl"
+REF2 = "/root/reference/demos/Cursor_7.pkl"  # same furniture driven by the cursor agent; the base starts with no yaw
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "demo_facts.json")
+
+
+def main():
+    q = pickle.load(open(REF, "rb"))["qpos"]
+    z = np.array([s["1_chair_base"][2] for s in q])
+    rest = z[:10]  # the base has not been touched yet in the first steps
+    assert rest.std() < 1e-7
+    facts = {"source": "demos/Sawyer_7.pkl of the reference, key 1_chair_base, first 10 recorded states (tools/make_golden_demo_facts.py)",
+             "swivel_chair_base_rest_z": float(rest.mean()), "swivel_chair_base_rest_z_std": float(rest.std()), "n_states": int(len(q))}
+    q2 = pickle.load(open(REF2, "rb"))["qpos"]
+    base = np.array([s["1_chair_base"] for s in q2[:10]])
+    assert base.std(0).max() < 1e-7 and abs(base[0, 2] - rest.mean()) < 1e-7  # same rest height in both recordings
+    # at rest the base leans by 0.028 degrees about its x axis (its five cylinders are not arranged symmetrically about the
+    # centre of mass): quaternion x component; the z component (yaw) is where it happened to be put
+    facts["swivel_chair_base_rest_quat"] = [float(v) for v in base[:, 3:].mean(0)]
+    json.dump(facts, open(OUT, "w"), indent=1)
+    print(facts)
+
+
+if __name__ == "__main__":
+    main()
