@@ -9,9 +9,9 @@
  *
  * PARITY UNPINNED for the physics: the reference holds no golden vector / known-answer test for any qpos/qvel/contact
  * value and no MuJoCo binary exists in this container, so this oracle is pinned only by its own
- * physical-consistency tests (tests/test_oracle_physics.py) and by two numbers MuJoCo itself produced: the height and the
- * tilt at which the swivel-chair base rests in the reference's demo recordings (demos/Sawyer_7.pkl, Cursor_7.pkl ->
- * tests/golden/demo_facts.json), which the oracle's reset reproduces to 4e-8 m and 1e-7 -- an equilibrium of the soft-contact
+ * physical-consistency tests (tests/test_oracle_physics.py) and by rest states MuJoCo itself produced: the poses at which the
+ * swivel-chair parts and the two blocks stand untouched in the reference's demo recordings (demos/*.pkl ->
+ * tests/golden/demo_facts.json) are equilibria of this oracle to 1e-7 m over 2000 steps -- equilibria of the soft-contact
  * model, not a trajectory.  The assembly logic (_is_aligned/_connect) and the reset placement sampler ARE pinned bit-exactly
  * against the reference's own Python (oracle/assembly_oracle.py, oracle/ref_env.py place(), tests/golden/).
  *

@@ -266,3 +266,25 @@ def test_is_aligned_bit_exact_vs_reference_goldens(sawyer_model, gpu):
     assert withang.sum() > 2000 and noang.sum() > 500
     assert np.array_equal(tq[withang], z["tq"][sl][withang])
     assert np.abs(tq[noang] - z["tq"][sl][noang]).max() < 5e-16
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+@pytest.mark.parametrize("furn,key,ncon", [("swivel_chair_0700", "cursor7_rest_state", 14), ("block", "baxter0_rest_state", 8)])
+def test_state_recorded_from_mujoco_is_an_equilibrium_of_the_engine(furn, key, ncon, gpu):
+    """the rest states MuJoCo itself left in the reference's demo recordings (tests/golden/demo_facts.json, see
+    test_oracle_physics.py) planted in the fp32 engine: after 2000 mj_steps nothing has moved (5e-6 m, 5e-6 in the quaternion)"""
+    from test_oracle_physics import _planted_rest_state
+
+    m = mjcf.load_scene("Sawyer", furn)
+    q, facts = _planted_rest_state(m, key)
+    eng = make_engine(m, 2, gpu)
+    eng.set("qpos", q)
+    eng.forward()
+    eng.set("qfrc_applied", eng.get("qfrc_bias"))
+    eng.step(2000)
+    qe = eng.get("qpos")
+    assert (eng.get("flags") == 0).all() and (eng.get("ncon")[:, 0] == ncon).all()
+    for n in m.meta["part_names"]:
+        qa = m.jnt_qposadr[m.names["jnt"].index(n)]
+        assert np.abs(qe[:, qa : qa + 3] - np.array(facts[n][:3])).max() < 5e-6, n
+        assert np.abs(qe[:, qa + 3 : qa + 7] - np.array(facts[n][3:])).max() < 5e-6, n

@@ -235,3 +235,63 @@ def test_chair_base_rests_where_the_reference_recording_has_it():
     qx_demo, qy_demo = facts["swivel_chair_base_rest_quat"][1], facts["swivel_chair_base_rest_quat"][2]
     quat = env._qpos(0)[3:]
     assert abs(quat[1] - qx_demo) < 2e-6 and abs(quat[2] - qy_demo) < 2e-6, (quat, qx_demo, qy_demo)
+
+
+def _planted_rest_state(m, key="cursor7_rest_state"):
+    import json
+    import os
+
+    facts = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "demo_facts.json")))[key]
+    q = m.qpos0.copy()
+    q[:7] = m.meta["robot_init_qpos"]
+    q[7:9] = m.meta["gripper_init_qpos"]
+    for n in m.meta["part_names"]:
+        qa = m.jnt_qposadr[m.names["jnt"].index(n)]
+        q[qa : qa + 7] = facts[n]
+    return q, facts
+
+
+def test_state_recorded_from_mujoco_is_an_equilibrium_of_the_oracle():
+    """demos/Cursor_7.pkl opens with the three swivel-chair parts standing untouched on the floor (base flat, column and seat
+    upright), as MuJoCo left them: heights with micrometres of penetration, the seat leaning by 0.008 degrees.  Planted in the
+    oracle, that state must not move: after 2000 mj_steps (4 s) every part is within 1e-7 m and 5e-7 (quaternion) of the recorded
+    values -- three shapes, 14 contacts, pinned to MuJoCo's own equilibrium to seven digits."""
+    from furniture_b200 import mjcf
+    from oracle.oracle import OracleSim
+
+    m = mjcf.load_scene("Sawyer", "swivel_chair_0700")
+    q, facts = _planted_rest_state(m)
+    sim = OracleSim(m)
+    sim.reset()
+    sim.qpos[:] = q
+    sim.forward()
+    sim.qfrc_applied[:9] = sim.qfrc_bias[:9]  # arm held by its gravity compensation, away from the parts
+    sim.step(2000)
+    assert len(sim.contacts()) == 14
+    for n in m.meta["part_names"]:
+        qa = m.jnt_qposadr[m.names["jnt"].index(n)]
+        assert np.abs(sim.qpos[qa : qa + 3] - facts[n][:3]).max() < 1e-7, n
+        assert np.abs(sim.qpos[qa + 3 : qa + 7] - facts[n][3:]).max() < 5e-7, n
+    assert np.abs(sim.qvel[9:]).max() < 1e-5
+
+
+def test_recorded_rest_state_of_the_blocks_is_an_equilibrium_of_the_oracle():
+    """demos/Baxter_0.pkl opens with the two boxes of the `block` furniture at rest at z = 0.0499699 (30 micrometres into the
+    floor: 80 g boxes whose solref time constant 0.001 is below two time steps, so MuJoCo's refsafe clamp sets the stiffness).
+    Same check as for the chair: planted in the oracle the recorded state stays put to 1e-7."""
+    from furniture_b200 import mjcf
+    from oracle.oracle import OracleSim
+
+    m = mjcf.load_scene("Sawyer", "block")
+    q, facts = _planted_rest_state(m, "baxter0_rest_state")
+    sim = OracleSim(m)
+    sim.reset()
+    sim.qpos[:] = q
+    sim.forward()
+    sim.qfrc_applied[:9] = sim.qfrc_bias[:9]
+    sim.step(2000)
+    for n in m.meta["part_names"]:
+        qa = m.jnt_qposadr[m.names["jnt"].index(n)]
+        assert abs(sim.qpos[qa + 2] - facts[n][2]) < 1e-7, n  # height (in the recording x / y creep by 2e-7 per step: not compared tightly)
+        assert np.abs(sim.qpos[qa : qa + 2] - facts[n][:2]).max() < 1e-5, n
+        assert np.abs(sim.qpos[qa + 3 : qa + 7] - facts[n][3:]).max() < 5e-7, n

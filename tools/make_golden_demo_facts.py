@@ -29,6 +29,13 @@ def main():
     # at rest the base leans by 0.028 degrees about its x axis (its five cylinders are not arranged symmetrically about the
     # centre of mass): quaternion x component; the z component (yaw) is where it happened to be put
     facts["swivel_chair_base_rest_quat"] = [float(v) for v in base[:, 3:].mean(0)]
+    # the whole first state of the Cursor recording: all three parts standing untouched (base flat, column and seat upright)
+    facts["cursor7_rest_state"] = {k: [float(v) for v in np.mean([s[k] for s in q2[:10]], axis=0)] for k in ("1_chair_base", "2_chair_column", "3_chair_seat")}
+    # demos/Baxter_0.pkl: the two boxes of the `block` furniture at rest (solref 0.001 < 2 h: the refsafe clamp is in play)
+    q3 = pickle.load(open("/root/reference/demos/Baxter_0.pkl", "rb"))["qpos"]
+    blocks = {k: np.array([s[k] for s in q3[:10]]) for k in ("1_block_l", "2_block_r")}
+    assert all(v[:, 2:].std(0).max() < 1e-7 for v in blocks.values())  # height and orientation are still; x / y creep by 2e-7 per recorded step
+    facts["baxter0_rest_state"] = {k: [float(x) for x in v[0]] for k, v in blocks.items()}
     json.dump(facts, open(OUT, "w"), indent=1)
     print(facts)
 
