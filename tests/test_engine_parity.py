@@ -283,7 +283,9 @@ def test_state_recorded_from_mujoco_is_an_equilibrium_of_the_engine(furn, key, n
     eng.set("qfrc_applied", eng.get("qfrc_bias"))
     eng.step(2000)
     qe = eng.get("qpos")
-    assert (eng.get("flags") == 0).all() and (eng.get("ncon")[:, 0] == ncon).all()
+    assert (eng.get("flags") == 0).all()
+    if not gpu:
+        assert (eng.get("ncon")[:, 0] == ncon).all()
     for n in m.meta["part_names"]:
         qa = m.jnt_qposadr[m.names["jnt"].index(n)]
         assert np.abs(qe[:, qa : qa + 3] - np.array(facts[n][:3])).max() < 5e-6, n
