@@ -79,3 +79,29 @@ def test_reset_equals_the_oracle_env_seeded_the_same_way(furn, gpu):
             assert np.abs(v[i] - e.sim.qvel).max() < 2e-4
     assert np.abs(q[0, 9:11] - q[1, 9:11]).max() > 1e-4  # different envs, different placements
     eng.close()
+
+
+def test_masked_reset_touches_only_the_selected_envs():
+    """fe_env_reset(mask): the envs whose mask byte is set are reset (their random stream continues: second reset of the
+    oracle env seeded the same way), the others keep state, bookkeeping and generator untouched (lane-emulated build: the
+    mask pointer is a host pointer there, a device pointer for the CUDA library)."""
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    n, seed = 3, 900
+    eng = make_engine(m, n, False, seed=seed, nsub=5)
+    eng.env_reset()
+    a = np.random.RandomState(1).uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
+    a[:, -1] = -1
+    eng.env_step_host(a)
+    q1, mt1, len1 = eng.get("qpos").copy(), eng.get("mt_state").copy(), eng.get("episode_length").copy()
+    mask = np.array([1, 0, 1], dtype=np.uint8)
+    eng.env_reset(mask_dev=mask.ctypes.data)
+    q2, len2 = eng.get("qpos"), eng.get("episode_length")
+    assert np.array_equal(q2[1], q1[1]) and np.array_equal(eng.get("mt_state")[1], mt1[1]) and len2[1, 0] == len1[1, 0] == 1
+    assert len2[0, 0] == 0 and len2[2, 0] == 0
+    for i in (0, 2):
+        cfg = Cfg()
+        cfg.seed = seed + i
+        e = OracleFurnitureEnv(m, cfg)
+        e.reset()
+        e.reset()
+        assert np.abs(q2[i] - e.sim.qpos).max() < 1e-5, i
