@@ -225,6 +225,19 @@ class Engine:
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), (self.N, dim)))
         self._chk(self.L.fe_set_field(self.h, name.encode(), v.ctypes.data_as(C.c_void_p), C.c_size_t(v.nbytes)))
 
+    def get_state(self):
+        """(qpos, qvel) of every env through fe_get_state: get_env_state, furniture.py:1781-1792"""
+        q = np.empty((self.N, self.model.nq), np.float32)
+        v = np.empty((self.N, self.model.nv), np.float32)
+        self._chk(self.L.fe_get_state(self.h, q.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
+        return q, v
+
+    def set_state(self, qpos, qvel):
+        """fe_set_state: set_env_state / sim.set_state, furniture.py:1794-1803, :3095-3105 (call forward() afterwards, as the reference does)"""
+        q = np.ascontiguousarray(np.broadcast_to(np.asarray(qpos, np.float32), (self.N, self.model.nq)))
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(qvel, np.float32), (self.N, self.model.nv)))
+        self._chk(self.L.fe_set_state(self.h, q.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
+
     def forward(self, stream=None):
         self._chk(self.L.fe_sim_forward(self.h, C.c_void_p(stream or 0)))
 

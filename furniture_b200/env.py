@@ -93,11 +93,11 @@ class BatchedFurnitureEnv:
         return tuple({k: int(row[j]) for j, k in enumerate(INFO_KEYS)} for row in info)
 
     def get_env_state(self):
-        return {"qpos": self.engine.get("qpos"), "qvel": self.engine.get("qvel")}
+        q, v = self.engine.get_state()
+        return {"qpos": q, "qvel": v}
 
     def set_env_state(self, state):
-        self.engine.set("qpos", state["qpos"])
-        self.engine.set("qvel", state["qvel"])
+        self.engine.set_state(state["qpos"], state["qvel"])
         self.engine.set("ctrl", np.zeros((self.num_envs, self.model.nu), np.float32))
         self.engine.forward(stream=self._stream())
 
