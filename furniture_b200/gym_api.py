@@ -1,0 +1,119 @@
+"""Single-environment gym-shaped surface (numpy in / numpy out) over the engine: the call surface of the reference's
+`FurnitureGym` (furniture/env/furniture_gym.py:11-80) and of `FurnitureEnv.step()/reset()` behind it.
+
+  env = FurnitureGymB200(name="FurnitureSawyerEnv", furniture_name="table_lack_0825", seed=123)
+  ob = env.reset()                                  # OrderedDict(object_ob (7 n_objects,), robot_ob (29,))
+  ob, reward, done, info = env.step(action)         # action: (dof,) array or {"default": array}
+
+It is the batched engine with one env (the batch entry point `furniture_b200.env.make_vec_env` is the one to use for
+throughput).  Differences from the reference, all consequences of the step kernel resetting a finished env on the
+device like a `SubprocVecEnv` worker does (subproc_vec_env.py:16-20):
+  * the observation returned together with `done=True` is the first observation of the next episode, not the terminal one;
+  * the `reset()` the caller issues after `done` returns that same observation and does not reset a second time, so the
+    env consumes exactly one reset's worth of numpy random draws per episode, like the reference (furniture.py:72).
+`info` carries the reference's episode keys at the end of an episode (`_after_step`, furniture.py:451-480).
+"""
+from __future__ import annotations
+
+import time
+from collections import OrderedDict
+
+import numpy as np
+
+from . import mjcf
+from .engine import Engine, default_config
+
+AGENTS = {"FurnitureSawyerEnv": "Sawyer", "IKEASawyer-v0": "Sawyer", "Sawyer": "Sawyer"}
+
+
+class FurnitureGymB200:
+    metadata = {"render.modes": []}
+
+    def __init__(self, name="FurnitureSawyerEnv", furniture_name="table_lack_0825", device=0, lib_path=None, control_type="impedance", **config):
+        if name not in AGENTS:
+            raise ValueError("unknown env %s (this build accelerates %s)" % (name, sorted(AGENTS)))
+        if control_type != "impedance":
+            raise NotImplementedError("only control_type='impedance' is accelerated")
+        self.model = mjcf.load_scene(AGENTS[name], furniture_name)
+        self.cfg = default_config(**config)
+        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path)
+        self.n_objects = self.engine.scene.npart
+        self.object_ob_dim = 7 * self.n_objects
+        self.robot_ob_dim = self.engine.scene.robot_ob_dim
+        self.dof = self.engine.act_dim
+        self._max_episode_steps = self.cfg.max_episode_steps
+        self._pending_ob = None  # observation of an episode the device has already started
+        self._episode_reward = 0.0
+        self._episode_time = time.time()
+
+    # ---- spaces (furniture.py:215-252, :293-310): plain shape / bound records, gym.spaces objects when gym is installed
+    @property
+    def observation_space(self):
+        shapes = OrderedDict(object_ob=(self.object_ob_dim,), robot_ob=(self.robot_ob_dim,))
+        try:
+            import gym.spaces as sp
+
+            return sp.Dict(OrderedDict((k, sp.Box(low=-np.inf, high=np.inf, shape=v)) for k, v in shapes.items()))
+        except Exception:
+            return shapes
+
+    @property
+    def action_space(self):
+        try:
+            import gym.spaces as sp
+
+            return sp.Dict([("default", sp.Box(shape=(self.dof,), low=-1, high=1, dtype=np.float32))])
+        except Exception:
+            return OrderedDict(default=dict(shape=(self.dof,), low=-1.0, high=1.0))
+
+    def _ob(self, obs_row):
+        return OrderedDict(object_ob=obs_row[: self.object_ob_dim].astype(np.float64), robot_ob=obs_row[self.object_ob_dim :].astype(np.float64))
+
+    def reset(self):
+        if self._pending_ob is not None:
+            ob, self._pending_ob = self._pending_ob, None
+        else:
+            self.engine.env_reset()
+            ob = self._ob(self.engine.get("obs")[0])
+        self._episode_reward = 0.0
+        self._episode_time = time.time()
+        return ob
+
+    def step(self, action):
+        if isinstance(action, dict):
+            action = np.concatenate([np.asarray(v, dtype=np.float32).ravel() for v in action.values()])
+        a = np.asarray(action, dtype=np.float32).reshape(1, self.dof)
+        obs, rew, done, info = self.engine.env_step_host(a)
+        reward, done = float(rew[0]), bool(done[0])
+        self._episode_reward += reward
+        out = OrderedDict()
+        ob = self._ob(obs[0])
+        if done:
+            unstable = int(info[0][2])
+            out["episode_success"] = int(info[0][1])
+            out["episode_reward"] = self._episode_reward
+            out["episode_length"] = int(info[0][3])
+            out["episode_time"] = time.time() - self._episode_time
+            out["episode_unstable"] = -float(self.cfg.unstable_penalty_coef) if unstable else 0
+            out["episode_num_connected"] = int(info[0][0])
+            self._pending_ob = ob
+        return ob, reward, done, out
+
+    # ---- pass-throughs of FurnitureGym (furniture_gym.py:35-50)
+    def set_max_episode_steps(self, max_episode_steps):
+        raise NotImplementedError("max_episode_steps is fixed at construction (fe_config.max_episode_steps)")
+
+    def get_env_state(self):
+        q, v = self.engine.get_state()
+        return {"qpos": q[0].astype(np.float64), "qvel": v[0].astype(np.float64)}
+
+    def set_env_state(self, state):
+        self.engine.set_state(np.asarray(state["qpos"])[None], np.asarray(state["qvel"])[None])
+        self.engine.set("ctrl", np.zeros((1, self.model.nu), np.float32))
+        self.engine.forward()
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is outside the accelerated path")
+
+    def close(self):
+        self.engine.close()

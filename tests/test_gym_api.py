@@ -1,0 +1,39 @@
+"""Single-env gym surface (FurnitureGym, furniture_gym.py:11-80) over the engine, on the lane-emulated build: observation dict
+layout, reward / done as Python scalars, the reference's episode keys in `info` at episode end, and one reset's worth of numpy
+draws per episode (the env equals the oracle env seeded the same way across an episode boundary)."""
+import numpy as np
+
+from furniture_b200.gym_api import FurnitureGymB200
+from oracle.ref_env import Cfg, OracleFurnitureEnv
+from parity_util import build_emu
+
+
+def test_gym_surface_follows_the_reference_env_across_an_episode_boundary():
+    seed = 41
+    env = FurnitureGymB200(name="FurnitureSawyerEnv", furniture_name="table_lack_0825", lib_path=build_emu(), seed=seed, max_episode_steps=3, nsub=10)
+    cfg = Cfg()
+    cfg.seed, cfg.max_episode_steps = seed, 3
+    ref = OracleFurnitureEnv(env.model, cfg)
+    ref.nsub = 10
+    ob = env.reset()
+    rob = ref.reset()
+    assert list(ob.keys()) == ["object_ob", "robot_ob"] and ob["object_ob"].shape == (35,) and ob["robot_ob"].shape == (29,)
+    assert np.abs(np.concatenate(list(ob.values())) - rob).max() < 2e-4
+    rng = np.random.RandomState(3)
+    for ep in range(2):
+        for k in range(3):
+            a = rng.uniform(-1, 1, env.dof)
+            a[-1] = -1
+            ob, rew, done, info = env.step({"default": a})
+            rob, r, d, inf = ref.step(a)
+            assert isinstance(rew, float) and isinstance(done, bool) and done == d and abs(rew - r) < 1e-5
+            if not done:
+                assert info == {} and np.abs(np.concatenate(list(ob.values())) - rob).max() < 2e-4
+        assert done and info["episode_length"] == 3 and info["episode_success"] == 0 and info["episode_unstable"] == 0
+        assert set(info) == {"episode_success", "episode_reward", "episode_length", "episode_time", "episode_unstable", "episode_num_connected"}
+        ob = env.reset()  # hands back the episode the device has already started: no second reset, no extra draws
+        rob = ref.reset()
+        assert np.abs(np.concatenate(list(ob.values())) - rob).max() < 2e-4, ep
+    st = env.get_env_state()
+    assert st["qpos"].shape == (env.model.nq,) and st["qvel"].shape == (env.model.nv,)
+    env.close()
