@@ -270,28 +270,30 @@ FE_HD void fe_mink(const FeCvx& g1, const FeCvx& g2, const float* dir, FeSup* s)
   fe_support(g2, nd, s->v2);
   v3sub(s->v, s->v1, s->v2);
 }
-FE_HD float fe_origin_tri(const float* a, const float* b, const float* c, float* w) {
-  float ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]}, bp[3] = {-b[0], -b[1], -b[2]}, cp[3] = {-c[0], -c[1], -c[2]};
-  v3sub(ab, b, a); v3sub(ac, c, a);
-  float d1 = v3dot(ab, ap), d2 = v3dot(ac, ap);
-  if (d1 <= 0.f && d2 <= 0.f) { v3cpy(w, a); return v3dot(w, w); }
-  float d3 = v3dot(ab, bp), d4 = v3dot(ac, bp);
-  if (d3 >= 0.f && d4 <= d3) { v3cpy(w, b); return v3dot(w, w); }
-  float vc = d1 * d4 - d3 * d2;
-  if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { float v = d1 / (d1 - d3); v3madd(w, a, ab, v); return v3dot(w, w); }
-  float d5 = v3dot(ab, cp), d6 = v3dot(ac, cp);
-  if (d6 >= 0.f && d5 <= d6) { v3cpy(w, c); return v3dot(w, w); }
-  float vb = d5 * d2 - d1 * d6;
-  if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { float v = d2 / (d2 - d6); v3madd(w, a, ac, v); return v3dot(w, w); }
-  float va = d3 * d6 - d5 * d4;
-  if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
-    float v = (d4 - d3) / ((d4 - d3) + (d5 - d6)), bc[3];
-    v3sub(bc, c, b); v3madd(w, b, bc, v);
-    return v3dot(w, w);
-  }
-  float den = 1.f / (va + vb + vc), v = vb * den, u = vc * den;
-  for (int k = 0; k < 3; ++k) w[k] = a[k] + ab[k] * v + ac[k] * u;
-  return v3dot(w, w);
+// Closest point of triangle (a, b, c) to the origin (Ericson's region tests); returns its squared distance.  Evaluated in
+// float64: the final MPR portal is a tiny triangle (1e-4) some 1e-3 away from the origin, and the region tests are products of
+// differences of nearly equal numbers -- in fp32 they misclassify the region and the witness lands off the triangle (seen: a
+// normal 40 degrees off for a 0.5 mm cylinder-box penetration).  One call per MPR contact: the cost is nil.
+FE_HD float fe_origin_tri(const float* af, const float* bf, const float* cf, float* w) {
+  const double a[3] = {af[0], af[1], af[2]}, b[3] = {bf[0], bf[1], bf[2]}, c[3] = {cf[0], cf[1], cf[2]};
+  const double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+#define FE_D3(x, y) ((x)[0] * (y)[0] + (x)[1] * (y)[1] + (x)[2] * (y)[2])
+  double r[3];
+  const double d1 = -FE_D3(ab, a), d2 = -FE_D3(ac, a);
+  const double d3 = -FE_D3(ab, b), d4 = -FE_D3(ac, b);
+  const double d5 = -FE_D3(ab, c), d6 = -FE_D3(ac, c);
+  const double vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+  if (d1 <= 0.0 && d2 <= 0.0) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+  else if (d3 >= 0.0 && d4 <= d3) { r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; }
+  else if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) { const double v = d1 / (d1 - d3); for (int k = 0; k < 3; ++k) r[k] = a[k] + ab[k] * v; }
+  else if (d6 >= 0.0 && d5 <= d6) { r[0] = c[0]; r[1] = c[1]; r[2] = c[2]; }
+  else if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { const double v = d2 / (d2 - d6); for (int k = 0; k < 3; ++k) r[k] = a[k] + ac[k] * v; }
+  else if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) { const double v = (d4 - d3) / ((d4 - d3) + (d5 - d6)); for (int k = 0; k < 3; ++k) r[k] = b[k] + (c[k] - b[k]) * v; }
+  else { const double den = 1.0 / (va + vb + vc), v = vb * den, u = vc * den; for (int k = 0; k < 3; ++k) r[k] = a[k] + ab[k] * v + ac[k] * u; }
+  const double dd = FE_D3(r, r);
+#undef FE_D3
+  w[0] = (float)r[0]; w[1] = (float)r[1]; w[2] = (float)r[2];
+  return (float)dd;
 }
 FE_HD void fe_portal_dir(const FeSup* p, float* dir) {
   float e1[3], e2[3];

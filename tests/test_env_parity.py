@@ -357,3 +357,46 @@ def test_last_connection_ends_the_episode_with_success(sawyer_model, gpu):
     ob = env.reset()  # the worker's auto-reset; the device env has done the same inside the step
     assert np.abs(obs[0] - ob).max() < 2e-4
     assert (eng.get("num_connected") == 0).all() and (eng.get("eq_active") == 0).all()
+
+
+def test_single_step_parity_along_a_drifting_rollout():
+    """16 envs x 25 env steps of uniform random actions (the bench workload: arms flail, hit parts, pin them to the floor).
+    Before every step the CPU env is re-synchronised to the device env's state, so each comparison is one env step (50
+    mj_steps) from identical states, but over states no hand-made test reaches.  Found with it: the fp32 closest-point test at
+    the end of MPR put the contact normal of a 0.5 mm cylinder-box penetration 40 degrees off (fixed: evaluated in float64).
+    What is left is the MPR portal tolerance (normals to ~1e-3) amplified by stiff contact: a few steps in a thousand above 1e-3."""
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    n, steps = 16, 25
+    eng = make_engine(m, n, False, seed=1000)
+    eng.env_reset()
+    envs = []
+    for i in range(n):
+        cfg = Cfg()
+        cfg.seed = 1000 + i
+        e = OracleFurnitureEnv(m, cfg)
+        e.reset()
+        envs.append(e)
+    rng = np.random.RandomState(0)
+    worst, above = 0.0, 0
+    for k in range(steps):
+        bias, tb, pk, nc, ln = eng.get("qfrc_bias"), eng.get("touched"), eng.get("picked"), eng.get("num_connected"), eng.get("episode_length")
+        for i, e in enumerate(envs):
+            _sync_oracle_from_engine(e, eng, i)
+            e.sim.qfrc_bias[: e.nr] = bias[i]
+            e.touched = [bool(x) for x in tb[i]]
+            e.picked = [bool(x) for x in pk[i]]
+            e.num_connected = e.prev_num_connected = int(nc[i, 0])
+            e.episode_len = int(ln[i, 0])
+        a = rng.uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
+        obs, rew, done, info = eng.env_step_host(a)
+        assert (eng.get("flags")[:, 0] & ~1 == 0).all()
+        for i, e in enumerate(envs):
+            ob, r, d, inf = e.step(a[i].astype(np.float64))
+            assert bool(done[i]) == d
+            if d:
+                continue
+            err = np.abs(obs[i] - ob).max()
+            worst = max(worst, err)
+            above += err > 1e-3
+            assert abs(rew[i] - r) < 1e-4
+    assert worst < 2e-2 and above <= 8, (worst, above)
