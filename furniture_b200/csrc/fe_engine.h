@@ -24,6 +24,12 @@
 #define FE_MINIMP 0.0001f
 #define FE_MAXIMP 0.9999f
 #define FE_MAXCAND 96
+// Line search: stop when |p'(alpha)| <= FE_LS_TOL |p'(0)|.  MuJoCo's default ls_tolerance is 0.01; the Newton loop's own
+// stopping test decides the final accuracy.  (1e-5 was below the fp32 noise of p' for a resting part: every line search of the
+// grouped part solver ran all 20 evaluations for bit-identical steps -- 20.0 passes per call against 4.0, measured on the
+// emulated build over 64 envs x 20 env steps; the cooperative solver went from 6.1 to 3.2 evaluations per Newton iteration
+// with the same number of iterations.)
+#define FE_LS_TOL 1e-2f
 
 struct FeOpt {
   int maxcon;       // contact capacity per env
@@ -1709,7 +1715,7 @@ FE_FN void fe_solve_coop(FeWarp* w) {
     float dxold = alpha;
     for (int ls = 0; ls < w->opt.ls_iters; ++ls) {
       fe_line_eval(w, alpha, g1, g2, &p1, &p2);
-      if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
+      if (fabsf(p1) <= FE_LS_TOL * fabsf(p1_0)) break;
       if (p1 < 0.f) lo = alpha; else hi = alpha;
       float next = alpha - p1 / p2;
       if (hi > 0.f && (!(next > lo && next < hi) || fabsf(2.f * p1) > fabsf(dxold * p2))) next = 0.5f * (lo + hi);
@@ -1915,7 +1921,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
             if (ls == 0) {
               if (!(p1 < 0.f) || !(p2 > 0.f)) { PV(lsact_) = 0; PV(act_) = 0; PV(alpha_) = 0.f; }
               else { PV(p10_) = p1; PV(alpha_) = -p1 / p2; PV(dx_) = PV(alpha_); }
-            } else if (fabsf(p1) <= 1e-5f * fabsf(PV(p10_))) PV(lsact_) = 0;
+            } else if (fabsf(p1) <= FE_LS_TOL * fabsf(PV(p10_))) PV(lsact_) = 0;
             else {
               if (p1 < 0.f) PV(lo_) = al; else PV(hi_) = al;
               float next = al - p1 / p2;
@@ -2062,7 +2068,7 @@ FE_FN void fe_solve_robot_limits(FeWarp* w) {
         dxold = alpha;
         continue;
       }
-      if (fabsf(p1) <= 1e-5f * fabsf(p1_0)) break;
+      if (fabsf(p1) <= FE_LS_TOL * fabsf(p1_0)) break;
       if (p1 < 0.f) lo = alpha; else hi = alpha;
       float next = alpha - p1 / p2;
       if (hi > 0.f && (!(next > lo && next < hi) || fabsf(2.f * p1) > fabsf(dxold * p2))) next = 0.5f * (lo + hi); // rtsafe rule
