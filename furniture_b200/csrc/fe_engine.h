@@ -1737,6 +1737,9 @@ FE_FN void fe_solve_coop(FeWarp* w) {
       for (int d = lane; d < nr; d += 32) w->l_jar()[d] += alpha * w->l_jv()[d];
     LANES_END
     ++iter;
+    // the top of the next iteration would stop on this same test after recomputing forces, J^T f and the gradient: stop now
+    // (the forces of the final iterate are computed once, below)
+    if (scale * impr < w->opt.tolerance) break;
   }
   fe_update(w);
   fe_mul_JT(w, w->fc());
@@ -1942,6 +1945,9 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
             PV(impr_) = -0.5f * al * PV(p10_);
             for (int k = 0; k < 6; ++k) PV(x_)[k] += al * PV(sd_)[k];
             PV(iter_) += 1;
+            // the next pass would stop on this same test before doing anything with its gradient: stop now and spare the
+            // pass (per-contact terms, the 28-value group reduction); the final forces are computed after the loop either way
+            if (PV(scale_) * PV(impr_) < tol) PV(act_) = 0;
           }
         }
         PV(lsact_) = 0;
