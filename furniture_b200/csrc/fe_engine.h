@@ -333,6 +333,74 @@ FE_FN void fe_solve_blocks(FeWarp* w, const float* L, const int* skip, float* x)
 }
 
 // ---------------------------------------------------------------- kinematics + smooth dynamics
+// x = (Mr + hdamp * diag(dof_damping) + diag(dadd))^-1 b for the robot block (nr <= NMAX; dadd may be null): lane i owns row i of the lower triangle in
+// registers, the factorisation is right-looking with the pivot column broadcast by shuffle, the two triangular solves likewise
+// (the scheme of fe_newton_regs).  Two lane regions in all, against some forty for the cooperative slice version (a region per
+// column step of fe_chol and per unknown of fe_chol_solve): the smooth acceleration of fe_kin_smooth and the implicit-damping
+// solve of fe_integrate were mostly barriers.  b and x may alias.  Rows and columns beyond nr are padded with the identity.
+template <int NMAX>
+FE_FN void fe_robot_solve_regs(FeWarp* w, float hdamp, const float* dadd, const float* b, float* x, int flagbit) {
+  const fe_model* m = w->m;
+  const int nr = m->nr;
+  FE_PRIVA(float, row_, NMAX);
+  FE_PRIV(float, s0_); FE_PRIV(float, s1_); FE_PRIV(float, b_); FE_PRIV(float, dinv_); FE_PRIV(float, q_);
+  FE_PRIV(int, bad_);
+  REGS_BEGIN
+    const int i = lane;
+    PV(bad_) = 0; PV(dinv_) = 1.f;
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      float v = (j == i) ? 1.f : 0.f;
+      if (i < nr && j <= i) v = w->Mr()[i * nr + j] + (j == i ? hdamp * m->dof_damping[i] + (dadd ? dadd[i] : 0.f) : 0.f);
+      PV(row_)[j] = v;
+    }
+    PV(b_) = i < nr ? b[i] : 0.f;
+  REGS_END
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    FE_SHFLA(s0_, row_, k, k);
+    REGS_BEGIN
+      float pk = PV(s0_);
+      if (!(pk > 1e-30f)) { PV(bad_) = 1; pk = 1e-30f; }
+      const float lkk = sqrtf(pk), inv = 1.0f / lkk;
+      const float lik = lane > k ? PV(row_)[k] * inv : (lane == k ? lkk : 0.f);
+      PV(row_)[k] = lik;
+      PV(q_) = lik;
+      if (lane == k) PV(dinv_) = inv;
+    REGS_END
+#pragma unroll
+    for (int j = k + 1; j < NMAX; ++j) {
+      FE_SHFL(s1_, q_, j);
+      REGS_BEGIN PV(row_)[j] -= PV(q_) * PV(s1_); REGS_END
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) { // y = L^-1 b
+    REGS_BEGIN PV(q_) = PV(b_) * PV(dinv_); REGS_END
+    FE_SHFL(s0_, q_, k);
+    REGS_BEGIN
+      if (lane > k) PV(b_) -= PV(row_)[k] * PV(s0_);
+      else if (lane == k) PV(b_) = PV(s0_);
+    REGS_END
+  }
+#pragma unroll
+  for (int k = NMAX - 1; k >= 0; --k) { // x = L^-T y
+    REGS_BEGIN PV(q_) = (lane > k && lane < NMAX) ? PV(row_)[k] * PV(b_) : 0.f; REGS_END
+    FE_WSUM(q_);
+    REGS_BEGIN if (lane == k) PV(b_) = (PV(b_) - PV(q_)) * PV(dinv_); REGS_END
+  }
+  LANES_BEGIN
+    if (lane < nr) x[lane] = PV(b_);
+    if (PV(bad_) && lane == 0) w->u()[2] |= flagbit;
+  LANES_END
+}
+FE_FN void fe_robot_solve(FeWarp* w, float hdamp, const float* dadd, const float* b, float* x, int flagbit) {
+  const int nr = w->m->nr;
+  if (nr <= 12) fe_robot_solve_regs<12>(w, hdamp, dadd, b, x, flagbit);
+  else if (nr <= 16) fe_robot_solve_regs<16>(w, hdamp, dadd, b, x, flagbit);
+  else fe_robot_solve_regs<24>(w, hdamp, dadd, b, x, flagbit);
+}
+
 FE_FN void fe_kin_smooth(FeWarp* w) {
   const fe_model* m = w->m;
   const int nl = m->nlink, nr = m->nr, nrl = m->nrlink, nv = m->nv;
@@ -590,19 +658,9 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
       for (int k = 0; k < 6; ++k) w->as()[z + k] = a[k];
     }
   LANES_END
-  // robot smooth acceleration: Lr = chol(Mr)
+  // robot smooth acceleration: as = Mr^-1 fs
   if (nr > 0) {
-    LANES_BEGIN
-      for (int e = lane; e < fe_tri(nr); e += 32) {
-        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-        while (fe_tri(i + 1) <= e) ++i;
-        while (fe_tri(i) > e) --i;
-        w->Lr()[e] = w->Mr()[i * nr + (e - fe_tri(i))];
-      }
-      for (int e = lane; e < nr; e += 32) w->as()[e] = w->fs()[e];
-    LANES_END
-    if (!fe_chol(w, w->Lr(), w->first(), nr)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END }
-    fe_chol_solve(w, w->Lr(), w->first(), nr, w->as(), w->grad());
+    fe_robot_solve(w, 0.f, nullptr, w->fs(), w->as(), 2);
   }
   (void)nv;
 }
@@ -2036,16 +2094,9 @@ FE_FN void fe_solve_robot_limits(FeWarp* w) {
     else if (scale * gnorm < tol) break;
     if (iter >= maxit) break;
     LANES_BEGIN
-      if (lane < nr) {
-        float* Hi = w->H() + fe_tri(lane);
-        for (int j = 0; j <= lane; ++j) Hi[j] = w->Mr()[lane * nr + j];
-        Hi[lane] += PV(u_);
-        w->search()[lane] = -PV(t_);
-        w->first()[lane] = 0;
-      }
+      if (lane < nr) { w->Mv()[lane] = PV(u_); w->search()[lane] = -PV(t_); } // H = Mr + diag(D of the active limit rows)
     LANES_END
-    if (!fe_chol(w, w->H(), w->first(), nr)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 4; LANES_END }
-    fe_chol_solve(w, w->H(), w->first(), nr, w->search(), w->Mv());
+    fe_robot_solve(w, 0.f, w->Mv(), w->search(), w->search(), 4);
     REGS_BEGIN PV(s_) = lane < nr ? w->search()[lane] : 0.f; PV(Ms_) = 0.f; REGS_END
     for (int j = 0; j < nr; ++j) {
       FE_SHFL(t_, s_, j);
@@ -2157,17 +2208,9 @@ FE_FN void fe_integrate(FeWarp* w) {
   // robot: (Mr + h B) a = fs + fc
   if (nr > 0) {
     LANES_BEGIN
-      for (int e = lane; e < fe_tri(nr); e += 32) {
-        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-        while (fe_tri(i + 1) <= e) ++i;
-        while (fe_tri(i) > e) --i;
-        const int j = e - fe_tri(i);
-        w->Lr()[e] = w->Mr()[i * nr + j] + (i == j ? h * m->dof_damping[i] : 0.f);
-      }
-      for (int d = lane; d < nr; d += 32) { w->grad()[d] = w->fs()[d] + w->fc()[d]; w->first()[d] = 0; }
+      for (int d = lane; d < nr; d += 32) w->grad()[d] = w->fs()[d] + w->fc()[d];
     LANES_END
-    if (!fe_chol(w, w->Lr(), w->first(), nr)) { LANES_BEGIN if (lane == 0) w->u()[2] |= 2; LANES_END }
-    fe_chol_solve(w, w->Lr(), w->first(), nr, w->grad(), w->Mv());
+    fe_robot_solve(w, h, nullptr, w->grad(), w->grad(), 2);
   }
   LANES_BEGIN
     // warm start for the next step = solver solution, stored in qacc coordinates
