@@ -400,3 +400,47 @@ def test_single_step_parity_along_a_drifting_rollout():
             above += err > 1e-3
             assert abs(rew[i] - r) < 1e-4
     assert worst < 2e-2 and above <= 8, (worst, above)
+
+
+def test_connect_decisions_over_perturbed_alignments():
+    """48 variations of the grasp-and-align state: the table top displaced (up to a few cm) and rotated (up to 25 degrees) away from
+    the aligned pose, so that some requests connect and others must not.  Every decision (num_connected, weld activation), reward and
+    post-connect state of the device env equals the CPU env's (lane-emulated build)."""
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    env0 = OracleFurnitureEnv(m)
+    env0.reset()
+    q0 = _grasp_and_align_state(m, env0)
+    rng = np.random.RandomState(0)
+    n = 48
+    Q = np.tile(q0, (n, 1))
+    ta = env0.part_qadr[4]
+    for i in range(n):
+        dp = rng.normal(size=3) * (0.03 if i % 2 else 0.008)
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        ang = np.deg2rad(rng.uniform(0, 25 if i % 3 else 6))
+        Q[i, ta : ta + 3] += dp
+        Q[i, ta + 3 : ta + 7] = mjcf.q_mul(np.concatenate([[np.cos(ang / 2)], ax * np.sin(ang / 2)]), Q[i, ta + 3 : ta + 7])
+    eng = make_engine(m, n, False, nsub=1)
+    eng.env_reset()
+    eng.set("qpos", Q); eng.set("qvel", np.zeros(m.nv)); eng.set("qacc_warmstart", np.zeros(m.nv))
+    eng.forward()
+    a = np.zeros((n, eng.act_dim), np.float32)
+    a[:, -2] = 1.0
+    a[:, -1] = 1.0
+    obs, rew, done, info = eng.env_step_host(a)
+    qe, ea = eng.get("qpos"), eng.get("eq_active")
+    connected = 0
+    for i in range(n):
+        e = OracleFurnitureEnv(m)
+        e.reset()
+        e.nsub = 1
+        e.sim.qpos[:] = Q[i]; e.sim.qvel[:] = 0; e.sim.qacc_warmstart[:] = 0; e.sim.ctrl[:] = 0
+        e.sim.forward()
+        ob, r, d, inf = e.step(a[i].astype(np.float64))
+        assert inf["num_connected"] == info[i][0] and list(e.sim.eq_active) == list(ea[i]), i
+        assert abs(rew[i] - r) < 1e-3, i
+        if inf["num_connected"]:
+            assert np.abs(qe[i] - e.sim.qpos).max() < 2e-3, i
+        connected += inf["num_connected"]
+    assert 10 <= connected <= n - 5  # both outcomes are exercised
