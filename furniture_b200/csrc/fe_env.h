@@ -640,10 +640,14 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       int32_t* info = info_out + (size_t)env * FE_INFO_DIM;
       info[0] = nc; info[1] = success; info[2] = fail; info[3] = len; info[4] = w->u()[0]; info[5] = w->u()[3];
       e->es.done[env] = done;
-      e->ei[6] = done && !fail; // the unstable path has already reset the env
+      // An unstable episode resets twice, as the reference does: once inside _do_simulation's except branch
+      // (furniture.py:2889-2897) and once more by the VecEnv worker because the step returned done (subproc_vec_env.py:16-20).
+      // The second reset zeroes the episode length that _after_step just incremented and consumes its own random draws,
+      // so the env's generator stays draw-for-draw on the reference's stream.
+      e->ei[6] = done;
     }
   LANES_END
-  if (e->ei[6]) fe_env_reset_one(e); else if (!fail) fe_write_obs(e);
+  if (e->ei[6]) fe_env_reset_one(e); else fe_write_obs(e);
 }
 
 // per-env context set-up shared by the CUDA kernels and the emulation loop

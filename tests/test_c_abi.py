@@ -66,8 +66,9 @@ def test_engine_refuses_to_run_without_the_cuda_library(tmp_path):
         Engine(m, 2, lib_path=str(tmp_path / "nope.so"))
 
 
-def test_get_and_set_state_round_trip():
-    """fe_get_state / fe_set_state (get_env_state / set_env_state, furniture.py:1781-1803) on the lane-emulated build:
+@pytest.mark.parametrize("gpu", [pytest.param(False, id="emu"), pytest.param(True, id="cuda", marks=pytest.mark.gpu)])
+def test_get_and_set_state_round_trip(gpu):
+    """fe_get_state / fe_set_state (get_env_state / set_env_state, furniture.py:1781-1803) on the lane-emulated build and on the sm_100a library:
     the state planted comes back bit for bit, and stepping from it equals stepping from the same state planted field by field"""
     import sys
 
@@ -78,14 +79,14 @@ def test_get_and_set_state_round_trip():
     from parity_util import make_engine, settled_state
 
     m = mjcf.load_scene("Sawyer", "table_lack_0825")
-    eng = make_engine(m, 3, False)
+    eng = make_engine(m, 3, gpu)
     Q = np.array([settled_state(m, i, robot_noise=0.2) for i in range(3)], np.float32)
     V = np.random.RandomState(0).normal(size=(3, m.nv)).astype(np.float32) * 0.1
     eng.set_state(Q, V)
     q, v = eng.get_state()
     assert np.array_equal(q, Q) and np.array_equal(v, V)
     eng.forward(); eng.step(5)
-    other = make_engine(m, 3, False)
+    other = make_engine(m, 3, gpu)
     other.set("qpos", Q); other.set("qvel", V)
     other.forward(); other.step(5)
     assert np.array_equal(eng.get_state()[0], other.get("qpos")) and np.array_equal(eng.get_state()[1], other.get("qvel"))

@@ -105,3 +105,37 @@ def test_masked_reset_touches_only_the_selected_envs():
         e.reset()
         e.reset()
         assert np.abs(q2[i] - e.sim.qpos).max() < 1e-5, i
+
+
+def test_unstable_episode_resets_twice_like_the_reference_worker():
+    """MujocoException path (furniture.py:2889-2897): the env resets inside the step, _after_step counts the step and ends the
+    episode with the unstable penalty, and the VecEnv worker resets once more (subproc_vec_env.py:16-20).  So after the step
+    the episode length is 0 and the env's generator has consumed two more resets' worth of draws; the next step is step 1 of a
+    fresh episode.  The divergence guard (|qvel| > 1e6, mj_checkVel) is tripped by planting a huge velocity."""
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    n, seed = 2, 321
+    eng = make_engine(m, n, False, seed=seed, nsub=2)
+    eng.env_reset()
+    v = eng.get("qvel").copy()
+    v[1, 0] = 1e8
+    eng.set("qvel", v)
+    a = np.zeros((n, eng.act_dim), np.float32)
+    a[:, -1] = -1
+    obs, rew, done, info = eng.env_step_host(a)
+    assert not done[0] and done[1] and info[1][2] == 1 and info[0][2] == 0
+    assert rew[1] < -50  # unstable_penalty_coef = 100 (config/furniture.py)
+    ln, pos, st = eng.get("episode_length")[:, 0], eng.get("mt_pos")[:, 0], eng.get("mt_state")
+    assert ln[0] == 1 and ln[1] == 0
+    for i, nreset in ((0, 1), (1, 3)):
+        cfg = Cfg()
+        cfg.seed = seed + i
+        e = OracleFurnitureEnv(m, cfg)
+        for _ in range(nreset):
+            e.place()
+            for _ in range(101):
+                e.rng.uniform(-cfg.agent_xyz_rand, cfg.agent_xyz_rand, e.narm)
+        s = e.rng.get_state()
+        assert s[2] == pos[i] and np.array_equal(s[1], st[i]), i
+    assert np.isfinite(obs).all() and (eng.get("flags")[:, 0] & 8 == 0).all()
+    obs, rew, done, info = eng.env_step_host(a)
+    assert info[1][3] == 1 and info[0][3] == 2 and not done.any()
