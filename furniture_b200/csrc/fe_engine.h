@@ -849,11 +849,10 @@ FE_FN void fe_assemble(FeWarp* w) {
       const int g1 = w->c_geom()[c] & 255, g2 = w->c_geom()[c] >> 8;
       const int A = m->geom_link[g1], B = m->geom_link[g2];
       w->c_link()[c] = (A + 1) | ((B + 1) << 8);
-      { // 0: one free part against the static world; 1: robot only; 2: couples two moving blocks
+      { // 0: one free part against the static world; 1: robot only; 2: robot against a part; 3: part against part (2, 3 couple moving blocks)
         const int nrl_ = m->nrlink;
-        const bool pa = A >= nrl_, pb = B >= nrl_, ra = A >= 0 && A < nrl_, rb = B >= 0 && B < nrl_;
-        w->c_kind()[c] = ((pa && B < 0) || (pb && A < 0)) ? 0 : ((pa || pb) ? 2 : 1);
-        (void)ra; (void)rb;
+        const bool pa = A >= nrl_, pb = B >= nrl_;
+        w->c_kind()[c] = ((pa && B < 0) || (pb && A < 0)) ? 0 : ((pa && pb) ? 3 : ((pa || pb) ? 2 : 1));
       }
       float F[9];
       v3cpy(F, w->c_frame() + 6 * c);
@@ -1674,7 +1673,7 @@ FE_FN void fe_solve_coop(FeWarp* w) {
       const int l = nrl + lane;
       int cpl = w->plist()[9 * lane + 8] > 8;
       for (int c = 0; c < ncon && !cpl; ++c)
-        if (w->c_kind()[c] == 2) { const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1; cpl = A == l || B == l; }
+        if (w->c_kind()[c] >= 2) { const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1; cpl = A == l || B == l; }
       for (int e = 0; e < ne && !cpl; ++e) if (w->eq_active()[e]) cpl = m->eq_link1[e] == l || m->eq_link2[e] == l;
       w->iscr()[lane] = cpl;
     }
@@ -1815,7 +1814,7 @@ FE_FN void fe_solve_coop(FeWarp* w) {
 // value, every lane of the group then factors the same 6x6 Hessian and runs the same exact line search, whose
 // per-contact terms are again group-summed.  Parts are independent blocks here, so block-wise Newton reaches the same
 // minimiser as the global iteration.
-FE_FN void fe_solve_parts_grouped(FeWarp* w) {
+FE_FN void fe_solve_parts_grouped(FeWarp* w, unsigned skipmask) {
   const fe_model* m = w->m;
   const int nr = m->nr, nrl = m->nrlink, np = m->npart, maxit = w->opt.newton_iters, maxls = w->opt.ls_iters;
   const float tol = w->opt.tolerance;
@@ -1839,6 +1838,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w) {
         const int unit = lane >> 2;
         int nu = 0, p = p0;
         for (; p < np; ++p) {
+          if ((skipmask >> p) & 1u) continue; // part of the coupled component: solved there
           const int need = w->plist()[9 * p + 8] > 4 ? 2 : 1;
           if (need == 2 && (nu & 1)) ++nu;
           if (nu + need > 8) break;
@@ -2149,53 +2149,99 @@ FE_FN void fe_solve_robot_limits(FeWarp* w) {
   LANES_END
 }
 
-// mj_fwdConstraint: FAST scope when no constraint couples two moving blocks (free parts solved 8 lanes per part, robot
-// block cooperatively), FULL scope otherwise
+#include "fe_solve_comp.h"
+
+// mj_fwdConstraint.  The constraint set of this mj_step is split into independent pieces (the cost is separable over them):
+// free parts that only touch the static world (8 lanes per part, fe_solve_parts_grouped), the robot block when its only
+// rows are joint limits (fe_solve_robot_limits), and the coupled component -- robot block with contacts, parts in contact
+// with the robot or each other, welded parts -- solved by fe_solve_comp with its rows in registers.  A component beyond 32
+// dofs or 32 contacts falls back to the cooperative shared-memory solver over all dofs (fe_solve_coop).
 FE_FN void fe_solve(FeWarp* w) {
   const fe_model* m = w->m;
-  const int ncon = w->u()[0], ne = m->neq, np = m->npart, nrl = m->nrlink;
+  const int ncon = w->u()[0], ne = m->neq, np = m->npart, nrl = m->nrlink, nr = m->nr;
   LANES_BEGIN
-    int coupled = 0;
-    int rcon = 0;
-    for (int c = lane; c < ncon; c += 32) { coupled |= w->c_kind()[c] == 2; rcon |= w->c_kind()[c] == 1; }
-    for (int e = lane; e < ne; e += 32) coupled |= w->eq_active()[e] != 0;
-    if (lane < np) { // contacts of part `lane` against the static world (at most 8 handled by the grouped solver)
+    int rcon = 0, cpl = 0;
+    for (int c = lane; c < ncon; c += 32) { const int k = w->c_kind()[c]; rcon |= (k == 1 || k == 2); }
+    if (lane < np) { // contacts of part `lane`: against the static world (at most 8 handled by the grouped solver) or coupling
       const int l = nrl + lane;
       int cnt = 0;
       for (int c = 0; c < ncon; ++c) {
-        if (w->c_kind()[c] != 0) continue;
         const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1;
         if (A != l && B != l) continue;
+        if (w->c_kind()[c] != 0) { cpl = 1; continue; }
         if (cnt < 8) w->plist()[9 * lane + cnt] = c;
         ++cnt;
       }
       w->plist()[9 * lane + 8] = cnt;
-      if (cnt > 8) coupled = 1;
+      if (cnt > 8) cpl = 1;
+      for (int e = 0; e < ne; ++e) if (w->eq_active()[e] && (m->eq_link1[e] == l || m->eq_link2[e] == l)) cpl = 1;
     }
-    w->iscr()[lane] = coupled | (rcon << 1);
+    w->iscr()[lane] = cpl; w->colmap()[lane] = rcon;
     if (lane == 0) w->u()[3] = 0;
   LANES_END
-  bool coupled = false, robot_contact = false;
-  { // one ballot for both flags
-    LANES_BEGIN w->colmap()[lane] = w->iscr()[lane] & 2; w->iscr()[lane] &= 1; LANES_END
-    coupled = fe_ballot32(w->iscr()) != 0u;
-    robot_contact = fe_ballot32(w->colmap()) != 0u;
+  const unsigned cplmask = fe_ballot32(w->iscr());
+  bool robot_in = fe_ballot32(w->colmap()) != 0u;
 #if !FE_DEVICE_BUILD
-    if (getenv("FE_NO_RLIM")) robot_contact = true;
+  if (getenv("FE_NO_RLIM")) robot_in = true;
 #endif
+  if (cplmask == 0u && !robot_in) { // nothing couples two moving blocks and the robot touches nothing
+    fe_solve_parts_grouped(w, 0u);
+    LANES_BEGIN
+      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] += mx; }
+    LANES_END
+    fe_solve_robot_limits(w);
+    return;
   }
+  // active dofs of the component (robot dofs first, then the coupled parts in order) and its contacts
+  int* const ccl = (int*)w->Jc();
+  LANES_BEGIN
+    if (lane == 0) {
+      int n = 0;
+      if (robot_in) for (int d = 0; d < nr; ++d) { if (n < 32) w->colmap()[n] = d; ++n; }
+      for (int p = 0; p < np; ++p)
+        if ((cplmask >> p) & 1u) for (int k = 0; k < 6; ++k) { if (n < 32) w->colmap()[n] = nr + 6 * p + k; ++n; }
+      w->iscr()[31] = n;
+      if (cplmask) w->u()[5] += 1; else w->u()[14] += 1;
+    }
+  LANES_END
+  const int nA = w->iscr()[31];
+  int ncc = 0;
+  for (int base = 0; base < ncon; base += 32) {
+    int run = 0;
+    (void)run;
+    LANES_BEGIN
+      const int c = base + lane;
+      int in = 0;
+      if (c < ncon) {
+        if (w->c_kind()[c] != 0) in = 1;
+        else { const int A = (w->c_link()[c] & 255) - 1, B = (w->c_link()[c] >> 8) - 1; in = (int)((cplmask >> ((A > B ? A : B) - nrl)) & 1u); }
+      }
+      const int off = FE_SCAN(run, in);
+      if (in && ncc + off < 32) ccl[ncc + off] = c;
+      if (lane == 31) w->iscr()[30] = off + in;
+    LANES_END
+    ncc += w->iscr()[30];
+    LANES_BEGIN LANES_END
+  }
+  if (nA <= 32 && ncc <= 32 && !(w->opt.lockstep & 1024)) {
+    fe_solve_parts_grouped(w, cplmask);
+    LANES_BEGIN
+      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) if (!((cplmask >> p) & 1u)) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] += mx; }
+    LANES_END
+    if (!robot_in) fe_solve_robot_limits(w);
+    if (nA <= 16) fe_solve_comp<16>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
+    else fe_solve_comp<32>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
+    return;
+  }
+  // fallback: cooperative solver in shared memory (all dofs when something couples, else the robot block)
+  const bool coupled = cplmask != 0u;
   LANES_BEGIN if (lane == 0) { w->fast = coupled ? 0 : 1; w->nact = coupled ? m->nv : m->nr; } LANES_END
   if (!coupled) {
-    fe_solve_parts_grouped(w);
+    fe_solve_parts_grouped(w, 0u);
     LANES_BEGIN
-      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] += mx; if (robot_contact) w->u()[14] += 1; }
+      if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] += mx; }
     LANES_END
-    if (!robot_contact) {
-      fe_solve_robot_limits(w);
-      LANES_BEGIN if (lane == 0) { w->fast = 0; w->nact = m->nv; } LANES_END
-      return;
-    }
-  } else { LANES_BEGIN if (lane == 0) w->u()[5] += 1; LANES_END }
+  }
   fe_solve_coop(w);
   LANES_BEGIN if (lane == 0) { w->fast = 0; w->nact = m->nv; } LANES_END
 }
