@@ -64,6 +64,7 @@ struct FeLayout {
 };
 static FeLayout fe_h_lay; // host copy: what the lane-emulated build reads, and what the CUDA build uploads
 #if FE_DEVICE_BUILD
+extern __shared__ float fe_smem[];
 __constant__ FeLayout fe_c_lay;
 #define FE_ACC __host__ __device__ __forceinline__
 #else
@@ -81,10 +82,18 @@ struct FeWarp { // header at word 0 of the slice
   FeOpt opt;
   // solver scope of the cooperative routines: all dofs (FULL) or the robot block only (FAST, parts solved per lane group)
   int nact, fast;
-#define X(f) FE_ACC float* f() const { return (float*)this + FE_LAY.f; }
+  // Device: the slice address is rebuilt from the dynamic shared-memory symbol plus the warp's byte offset, so that the compiler
+  // sees a shared-memory pointer and emits LDS / STS with 32-bit addresses (through the generic `this` every slice access was
+  // a generic LD.E / ST.E with a 64-bit address pair).
+#if defined(__CUDA_ARCH__)
+  __device__ __forceinline__ char* base_() const { return (char*)fe_smem + (unsigned)(__cvta_generic_to_shared(this) - __cvta_generic_to_shared(fe_smem)); }
+#else
+  FE_ACC char* base_() const { return (char*)this; }
+#endif
+#define X(f) FE_ACC float* f() const { return (float*)base_() + FE_LAY.f; }
   FE_SLICE_F(X)
 #undef X
-#define X(f) FE_ACC int* f() const { return (int*)this + FE_LAY.f; }
+#define X(f) FE_ACC int* f() const { return (int*)base_() + FE_LAY.f; }
   FE_SLICE_I(X)
 #undef X
 };
@@ -2159,6 +2168,12 @@ FE_FN void fe_solve_robot_limits(FeWarp* w) {
 FE_FN void fe_solve(FeWarp* w) {
   const fe_model* m = w->m;
   const int ncon = w->u()[0], ne = m->neq, np = m->npart, nrl = m->nrlink, nr = m->nr;
+#if FE_DEVICE_BUILD
+#define FE_STICK(slot) { long long t1_ = clock64(); if ((threadIdx.x & 31u) == 0) w->u()[slot] += (int)((t1_ - t0_) >> 4); t0_ = t1_; }
+  long long t0_ = clock64();
+#else
+#define FE_STICK(slot)
+#endif
   LANES_BEGIN
     int rcon = 0, cpl = 0;
     for (int c = lane; c < ncon; c += 32) { const int k = w->c_kind()[c]; rcon |= (k == 1 || k == 2); }
@@ -2224,13 +2239,16 @@ FE_FN void fe_solve(FeWarp* w) {
     LANES_BEGIN LANES_END
   }
   if (nA <= 32 && ncc <= 32 && !(w->opt.lockstep & 1024)) {
+    FE_STICK(21)
     fe_solve_parts_grouped(w, cplmask);
     LANES_BEGIN
       if (lane == 0) { int mx = 0; for (int p = 0; p < np; ++p) if (!((cplmask >> p) & 1u)) mx = w->iscr()[p] > mx ? w->iscr()[p] : mx; w->u()[3] = mx; w->u()[4] += mx; }
     LANES_END
     if (!robot_in) fe_solve_robot_limits(w);
+    FE_STICK(22)
     if (nA <= 16) fe_solve_comp<16>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
     else fe_solve_comp<32>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
+    FE_STICK(23)
     return;
   }
   // fallback: cooperative solver in shared memory (all dofs when something couples, else the robot block)
@@ -2244,6 +2262,7 @@ FE_FN void fe_solve(FeWarp* w) {
   }
   fe_solve_coop(w);
   LANES_BEGIN if (lane == 0) { w->fast = 0; w->nact = m->nv; } LANES_END
+#undef FE_STICK
 }
 
 // ---------------------------------------------------------------- mj_Euler + mj_advance

@@ -50,7 +50,9 @@ print("wait at the barrier before kin/collide/assemble/solve/integrate: mean", "
 heavy = np.argsort(-cyc[:, 3])[:40]
 cc = st[heavy][:, 21:28].astype(np.float64) * 16
 its = st[heavy][:, 3].astype(np.float64)
-print("40 heaviest envs: coop iterations mean %.0f; cycles per iteration: setup+final %.0f update+JT %.0f grad/stop %.0f build_H %.0f chol %.0f chol_solve %.0f M,J,linesearch %.0f" % ((its.mean(),) + tuple((cc.sum(0) / its.sum()))))
+pre = st[heavy][:, 17:20].astype(np.float64) * 16
+nsol = st[heavy][:, 2].astype(np.float64)
+print("40 heaviest envs: component solves %.0f, Newton iterations mean %.0f; cycles per solve: preamble %.0f grouped+limits %.0f component %.0f | inside the component solver, per solve: setup %.0f candidates %.0f ; per iteration: forces+JTf+grad %.0f H rows+pairs %.0f cholesky+solves %.0f M s, J s %.0f line search %.0f" % ((nsol.mean(), its.mean()) + tuple(pre.sum(0) / nsol.sum()) + tuple(cc[:, :2].sum(0) / nsol.sum()) + tuple(cc[:, 2:].sum(0) / its.sum())))
 if os.environ.get("FE_DUMP_STATS"):
     order_k = eng.get("order")  # the order the next step will run with
     act = (torch.rand((N, eng.act_dim), device="cuda", generator=g) * 2 - 1) * scale
