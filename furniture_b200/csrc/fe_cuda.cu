@@ -45,6 +45,15 @@ __global__ void __launch_bounds__(32 * FE_MAX_WPB) fe_env_step_kernel(FeState st
   const int wib = threadIdx.x >> 5, slot = blockIdx.x * (blockDim.x >> 5) + wib;
   const int env = slots[slot];
   if (env < 0) return; // unused slot (blocks of heavy envs are deliberately left partly empty)
+#ifdef FE_EXP_MODEL_SMEM
+  if (blockDim.x == 32) { // experiment: one warp per block, model tables staged in shared memory behind the slice
+    float* ms = fe_smem + (slice_words + FE_ENV_EXTRA_WORDS);
+    const float* src = (const float*)m;
+    for (int i = threadIdx.x; i < (int)(sizeof(fe_model) / 4); i += 32) ms[i] = src[i];
+    __syncwarp();
+    m = (const fe_model*)ms;
+  }
+#endif
   FeEnv e;
   fe_env_bind(&e, fe_smem + (size_t)wib * (slice_words + FE_ENV_EXTRA_WORDS), m, sc, &cfg, opt, st, es, env, slice_words);
   fe_load(e.w, st, env);
@@ -259,7 +268,11 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
   int rc = plat_prepare(h, (cudaStream_t)stream);
   if (rc) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
+#ifdef FE_EXP_MODEL_SMEM
+  fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->wpb == 1 ? p->smem_env + sizeof(fe_model) : p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words, p->slots);
+#else
   fe_env_step_kernel<<<p->nblocks, 32 * p->wpb, p->smem_env, (cudaStream_t)stream>>>(h->st, h->es, h->dm, h->ds, h->cfg, h->opt, actions, reward, done, info, h->slice_words, p->slots);
+#endif
   CUDA_OK(cudaGetLastError());
   if (p->reorder) fe_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->N, h->st.stats, h->st.order, p->slots, p->nblocks * p->wpb, p->wpb, p->heavy_k, p->heavy_shift, p->pred, p->decay);
   return 0;

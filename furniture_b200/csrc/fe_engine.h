@@ -2247,6 +2247,7 @@ FE_FN void fe_solve(FeWarp* w) {
     if (!robot_in) fe_solve_robot_limits(w);
     FE_STICK(22)
     if (nA <= 16) fe_solve_comp<16>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
+    else if (nA <= 24) fe_solve_comp<24>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
     else fe_solve_comp<32>(w, nA, ncc, cplmask, robot_in ? 1 : 0);
     FE_STICK(23)
     return;

@@ -74,7 +74,14 @@ FE_FN void fe_solve_comp(FeWarp* w, int nA, int ncc, unsigned cplmask, int robot
   int run = 0;
   (void)run;
   LANES_BEGIN
-    for (int e = lane; e < fe_tri(nv); e += 32) Hm[e] = 0.f;
+    // rows of the coupled parts start with zeros left of their own block (M is block diagonal; weld terms are added below)
+    for (int p = 0; p < np; ++p)
+      if ((cplmask >> p) & 1u) {
+        const int z = nr + 6 * p;
+        for (int j = lane; j < z; j += 32)
+#pragma unroll
+          for (int i = 0; i < 6; ++i) Hm[fe_tri(z + i) + j] = 0.f;
+      }
     // warm start (stored in qacc coordinates) -> solver coordinates, staged in x()
     if (robot_in) for (int d = lane; d < nr; d += 32) w->x()[d] = w->warm()[d];
     for (int p = lane; p < np; p += 32)
@@ -451,7 +458,7 @@ FE_FN void fe_solve_comp(FeWarp* w, int nA, int ncc, unsigned cplmask, int robot
                 float t[3];
                 v3cross(t, e, r);
                 d[0] = sg * e[0]; d[1] = sg * e[1]; d[2] = sg * e[2]; d[3] = sg * t[0]; d[4] = sg * t[1]; d[5] = sg * t[2];
-              } else d[jj] = sg;
+              } else { d[3] = jj == 3 ? sg : 0.f; d[4] = jj == 4 ? sg : 0.f; d[5] = jj == 5 ? sg : 0.f; } // selects keep d in registers
             }
           }
 #pragma unroll
