@@ -78,6 +78,40 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def build_id():
+    """identifies the kernel build a profile belongs to: sha256 over the kernel sources and the nvcc flags"""
+    import hashlib
+
+    import __graft_entry__ as ge
+
+    h = hashlib.sha256(" ".join(ge.NVCC_FLAGS).encode())
+    csrc = os.path.join(ROOT, "furniture_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + ["../../include/furniture_b200.h"]:
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def host_cores():
+    """cores this process may really use: the affinity mask capped by the cgroup CPU quota (a 128-thread box with
+    cpu.max = '1600000 100000' gives 16: running 128 busy processes there measures the scheduler, not the code)"""
+    aff = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        a, b = open("/sys/fs/cgroup/cpu.max").read().split()
+        if a != "max":
+            quota = float(a) / float(b)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    cores = aff if quota is None else max(1, min(aff, int(quota)))
+    return cores, aff, quota
+
+
 def cpu_env_rate(seconds, seed=0):
     """env-steps/s of the CPU oracle env on ONE core for about `seconds` of work (reset excluded, like fps.py:119-127)"""
     import numpy as np
@@ -98,26 +132,29 @@ def cpu_env_rate(seconds, seed=0):
     return n / (time.perf_counter() - t0), n
 
 
-def _ref_worker(args):
-    seed, nsteps = args
+def _ref_worker(idx, nrounds, slice_s, start, finish, counts):
+    """one reference env per process (make_vec_env / SubprocVecEnv, env/base.py:55-80): free-running for `slice_s` seconds per
+    bench step, so that a bench step is not a barrier on the slowest worker's fixed chunk"""
     import numpy as np
 
     from furniture_b200 import mjcf
     from oracle.ref_env import OracleFurnitureEnv
 
-    global _REF_ENV
-    if "_REF_ENV" not in globals():
-        m = mjcf.load_scene("Sawyer", "table_lack_0825")
-        _REF_ENV = OracleFurnitureEnv(m)
-        _REF_ENV.cfg.seed = 123 + seed
-        _REF_ENV.reset()
-        _REF_ENV._rng_act = np.random.RandomState(seed)
-    env = _REF_ENV
-    for _ in range(nsteps):
-        _, _, done, _ = env.step(env._rng_act.uniform(-1, 1, env.dof))
-        if done:
-            env.reset()
-    return nsteps
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    env = OracleFurnitureEnv(m)
+    env.cfg.seed = 123 + idx
+    env.reset()
+    rng = np.random.RandomState(idx)
+    for r in range(nrounds):
+        start.wait()
+        n, t_end = 0, time.perf_counter() + slice_s
+        while time.perf_counter() < t_end:
+            _, _, done, _ = env.step(rng.uniform(-1, 1, env.dof))
+            if done:
+                env.reset()
+            n += 1
+        counts[idx] = n
+        finish.wait()
 
 
 def run_reference(args):
@@ -126,32 +163,45 @@ def run_reference(args):
         return
     import multiprocessing as mp
 
-    cores = len(os.sched_getaffinity(0))
-    chunk = 10  # env.step() calls per worker per bench "step"
+    for v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"  # one thread per env process, as a SubprocVecEnv worker (inherited by the spawned workers)
+    cores, aff, quota = host_cores()
+    one_core, _ = cpu_env_rate(4.0)
+    slice_s = args.ref_slice
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        for _ in range(max(args.warmup, 1)):
-            pool.map(_ref_worker, [(i, chunk) for i in range(cores)], chunksize=1)
+    start, finish = ctx.Barrier(cores + 1), ctx.Barrier(cores + 1)
+    counts = ctx.Array("l", cores)
+    W, K = max(args.warmup, 1), args.steps
+    procs = [ctx.Process(target=_ref_worker, args=(i, W + K, slice_s, start, finish, counts), daemon=True) for i in range(cores)]
+    for p in procs:
+        p.start()
+    total, dt = 0, 0.0
+    for r in range(W + K):
+        start.wait()
         t0 = time.perf_counter()
-        total = 0
-        for _ in range(args.steps):
-            total += sum(pool.map(_ref_worker, [(i, chunk) for i in range(cores)], chunksize=1))
-        dt = time.perf_counter() - t0
+        finish.wait()
+        t1 = time.perf_counter()
+        if r >= W:
+            total += sum(counts[:])
+            dt += t1 - t0
+    for p in procs:
+        p.join(timeout=10)
     value = total / dt
-    sample = "%d processes x %d env.step() per bench step (spawned workers keep their env alive; reset excluded)" % (cores, chunk)
+    sample = ("%d processes (affinity %d, cgroup quota %s), one env each, free-running %.1f s per bench step; %d env.step() in %.1f s; "
+              "reset excluded" % (cores, aff, "none" if quota is None else "%.1f cpus" % quota, slice_s, total, dt))
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs": cores, "note": "CPU restatement of the reference loop (mujoco-py/MuJoCo 2.0 absent): oracle/ref_env.py over oracle/fe_oracle.c; "
                    "published anchor 225 env-steps/s on one Xeon 6154 core (docs/more_info.md:35)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "per_core": value / cores, "one_core_alone": one_core,
+                         "parallel_efficiency": value / cores / one_core},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
 
 
 def run_ours(args):
-    import numpy as np
     import torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,19 +218,28 @@ def run_ours(args):
     from furniture_b200.env import BatchedFurnitureEnv, ShardedFurnitureEnv
 
     n_local = args.envs_per_gpu
-    if world > 1:
-        env = ShardedFurnitureEnv(n_local, furniture_name=args.furniture)
-        benv = env.env
-    else:
-        env = benv = BatchedFurnitureEnv("Sawyer", args.furniture, n_local, device=local, seed=123)
-    env.reset()
-    gen = torch.Generator(device=dev).manual_seed(rank)
     K, W = args.steps, args.warmup
-    acts = [torch.rand((n_local, benv.act_dim), device=dev, generator=gen) * 2 - 1 for _ in range(K + W)]
+
+    def make_env():
+        # the two timed legs (device-resident `value`, host-buffer `e2e`) run on two envs built alike -- same seeds, same
+        # reset draws, same actions, same step range -- so that their numbers are comparable
+        if world > 1:
+            e = ShardedFurnitureEnv(n_local, agent=args.agent, furniture_name=args.furniture)
+            return e, e.env
+        e = BatchedFurnitureEnv(args.agent, args.furniture, n_local, device=local, seed=123)
+        return e, e
+
+    env, benv = make_env()
+    env2, benv2 = make_env()
+    env.reset()
+    env2.reset()
+    gen = torch.Generator().manual_seed(1000 + rank)
+    a_host = [(torch.rand((n_local, benv.act_dim), generator=gen) * 2 - 1).pin_memory() for _ in range(K + W)]
     if args.actions == "settled":  # SURVEY.md 8d "settled" variant: zero arm action, gripper open, no connect request
-        for a in acts:
+        for a in a_host:
             a.zero_()
             a[:, -2:] = -1.0
+    acts = [a.to(dev) for a in a_host]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2 (126 MB)
 
     def barrier():
@@ -188,47 +247,69 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- leg 1: device-resident actions, CUDA events per step
     for i in range(W):
         env.step(acts[i])
     barrier()
+    if world > 1:
+        env.timing = True
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches = 0
     for k in range(K):
         flush.fill_(float(k))  # evict L2 between timed iterations (not timed)
         ev[k][0].record()
         env.step(acts[W + k])
         ev[k][1].record()
-        launches += 2  # fe_env_step_kernel + fe_order_kernel (block packing for the next step)
     barrier()
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if dist is not None:
+    rank_ms = float(total_ms.item()) / K
+    per_rank = None
+    if world > 1:
+        km, gm = env.pop_timing()
+        env.timing = False
+        mine = torch.tensor([rank_ms, sum(km) / len(km), sum(gm) / len(gm)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "step_ms": float(t[0]), "kernel_ms": float(t[1]), "gather_wait_ms": float(t[2])} for r, t in enumerate(allr)]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = n_local * world * K / (total_ms * 1e-3)
+    # kernels launched by this repo inside the timed region, per step: fe_env_step_kernel + fe_order_kernel (block packing for
+    # the next step); N > 1 adds NCCL's all-gather kernel (a library kernel, not counted)
+    launches = 2 * K
 
-    # end to end through the public API with HOST buffers: pinned actions -> H2D -> step (-> all_gather) -> D2H results
-    Ke = max(3, min(K, 10))
-    a_host = [torch.rand((n_local, benv.act_dim)).mul_(2).sub_(1).pin_memory() for _ in range(Ke)]
-    obs_host = torch.empty((n_local * world if world > 1 else n_local, benv.obs_dim)).pin_memory()
-    rew_host = torch.empty(n_local * world if world > 1 else n_local).pin_memory()
-    done_host = torch.empty(n_local * world if world > 1 else n_local, dtype=torch.bool if world > 1 else torch.uint8).pin_memory()
+    # ---- leg 2: end to end through the public API with HOST buffers, same actions and step range on the twin env:
+    # pinned actions -> H2D -> step (-> all_gather) -> D2H of this rank's results
+    n_out = n_local
+    obs_host = torch.empty((n_out, benv2.obs_dim)).pin_memory()
+    rew_host = torch.empty(n_out).pin_memory()
+    done_host = torch.empty(n_out, dtype=torch.bool if world > 1 else torch.uint8).pin_memory()
+    for i in range(W):
+        env2.step(a_host[i])
     barrier()
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        od, rew, done, _ = env.step(a_host[k])
-        obs_host[:, : benv.object_ob_dim].copy_(od["object_ob"], non_blocking=True)
-        obs_host[:, benv.object_ob_dim :].copy_(od["robot_ob"], non_blocking=True)
+    e2e_s = 0.0
+    for k in range(K):
+        flush.fill_(float(k))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        od, rew, done, _ = env2.step(a_host[W + k])
+        if world > 1:  # every rank holds the gathered tensors on the device; its host side reads its own shard
+            ob_o, ob_r, rew, done = env2.local_slice(od["object_ob"]), env2.local_slice(od["robot_ob"]), env2.local_slice(rew), env2.local_slice(done)
+        else:
+            ob_o, ob_r = od["object_ob"], od["robot_ob"]
+        obs_host[:, : benv2.object_ob_dim].copy_(ob_o, non_blocking=True)
+        obs_host[:, benv2.object_ob_dim :].copy_(ob_r, non_blocking=True)
         rew_host.copy_(rew, non_blocking=True)
         done_host.copy_(done, non_blocking=True)
         torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        e2e_s += time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e = n_local * world * Ke / float(e2e_s.item())
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e = n_local * world * K / float(e2e_t.item())
     h2d = n_local * benv.act_dim * 4
     d2h = obs_host.numel() * 4 + rew_host.numel() * 4 + done_host.numel()
 
@@ -236,29 +317,53 @@ def run_ours(args):
         peaks, peak_src = load_peaks()
         kernel_ms = total_ms / K  # one env-step = one launch of fe_env_step_kernel (+ the all_gather when N > 1)
         benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim)
-        assert args.furniture != "table_lack_0825" or benv_bytes == B_ENV
+        assert args.furniture != "table_lack_0825" or args.agent != "Sawyer" or benv_bytes == B_ENV
         achieved = benv_bytes * n_local / (kernel_ms * 1e-3) / 1e9
-        workload = WORKLOAD if (args.furniture == "table_lack_0825" and args.actions == "random") else (
-            "FurnitureSawyerEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.furniture, "random actions U(-1,1)" if args.actions == "random" else "settled (zero arm action, gripper open)"))
-        default_case = args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU
-        traffic = None
+        act_txt = "random actions U(-1,1)" if args.actions == "random" else "settled (zero arm action, gripper open)"
+        default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU
+        workload = WORKLOAD if default_case else "Furniture%sEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.agent, args.furniture, act_txt)
+        # measured DRAM traffic and instruction counts come from an ncu capture of exactly this kernel build
+        # (tools/ncu_extract.py writes profiles/traffic.json with the build id); a stale capture is refused
+        traffic, secondary, prof_note = None, None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
+        bid = build_id()
         if os.path.exists(tp) and default_case:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            prof = json.load(open(tp))
+            if prof.get("build_id") == bid:
+                traffic = prof.get("dram_bytes_per_launch")
+                if prof.get("warp_instructions_per_launch") and clocks.get("sm_mhz"):
+                    slots = kernel_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * 148 * 4  # warp-issue slots of the chip during one launch
+                    ipc = prof["warp_instructions_per_launch"] / (kernel_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * 148)
+                    lanes = prof.get("lanes_active_per_instruction")
+                    secondary = {"bound": "fp32-issue", "ipc": ipc, "ipc_peak": 4.0, "lanes_active": lanes,
+                                 "frac": prof["warp_instructions_per_launch"] * lanes / 32.0 / slots,
+                                 "note": "warp instructions x active lanes of the ncu capture of this build (%s) over the lane-issue slots of the live launch" % prof.get("source", "profiles/")}
+            else:
+                prof_note = "profiles/traffic.json belongs to build %s, this is build %s: traffic not reported" % (prof.get("build_id"), bid)
         out = {
-            "metric": METRIC if default_case else "aggregate env-steps/sec, Sawyer+%s @%d envs/GPU (%s actions)" % (args.furniture, n_local, args.actions),
+            "metric": METRIC if default_case else "aggregate env-steps/sec, %s+%s @%d envs/GPU (%s actions)" % (args.agent, args.furniture, n_local, args.actions),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "envs_per_gpu": n_local, "global_envs": n_local * world, "parallelism": "env-shards x%d" % world,
-                       "l2": "flushed between timed steps (256 MiB write)", "timing": "CUDA events per step on the launch stream, max over ranks"},
+                       "l2": "flushed before every timed step of both legs (256 MiB write, not timed)",
+                       "timing": "value: CUDA events per step on the launch stream, max over ranks; e2e: wall clock per step around the public call with "
+                                 "host buffers, same actions and step range on a twin env", "build_id": bid},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                          "kernel": "fe_env_step_kernel", "algorithmic_bytes_per_launch": benv_bytes * n_local, "peak_source": peak_src,
                          "note": "state stays in shared memory for the 50 mj_steps of a launch; the path is latency/issue bound, not HBM bound (DESIGN.md)"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if secondary:
+            out["roofline_secondary"] = secondary
+        if prof_note:
+            out["roofline"]["traffic_note"] = prof_note
+        if per_rank:
+            out["per_rank"] = per_rank
         if world == 1 and not args.no_cpu_baseline and default_case:
+            for v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+                os.environ.setdefault(v, "1")
             v, n = cpu_env_rate(args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": "%d env.step() of one CPU oracle env (oracle/ref_env.py over oracle/fe_oracle.c) in %.0f s" % (n, args.cpu_seconds)}
@@ -278,6 +383,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--furniture", default="table_lack_0825", help="other furniture = parity-test configs timed for DESIGN.md, not the bench line")
+    ap.add_argument("--agent", default="Sawyer")
+    ap.add_argument("--ref-slice", type=float, default=1.0, help="--impl reference: seconds every worker runs free per bench step")
     ap.add_argument("--actions", default="random", choices=["random", "settled"])
     args = ap.parse_args()
     if args.warmup < 3:

@@ -234,6 +234,14 @@ int fe_env_step(fe_handle* h, const float* actions_dev, float* obs_dev, float* r
   if (obs_dev) plat_copy_d2d(h, obs_dev, h->es.obs, sizeof(float) * (size_t)h->N * h->hs.obs_dim, stream);
   return 0;
 }
+int fe_env_step_packed(fe_handle* h, const float* actions_dev, float* packed_dev, int32_t* info_dev, void* stream) {
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_env_step_packed: handle was created without a scene blob");
+  if (!actions_dev || !packed_dev) return fail(h, -1, "fe_env_step_packed: actions / packed is NULL");
+  h->es.packed = packed_dev;
+  int rc = plat_run_step(h, actions_dev, (float*)h->dev_rew, (uint8_t*)h->dev_done, info_dev ? info_dev : (int32_t*)h->dev_info, stream);
+  h->es.packed = nullptr;
+  return rc;
+}
 int fe_env_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
   if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_env_step_host: handle was created without a scene blob");
   return plat_step_host(h, actions, obs, reward, done, info);

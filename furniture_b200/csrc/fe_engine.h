@@ -1152,6 +1152,30 @@ FE_FN void fe_line_eval(FeWarp* w, float alpha, float g1, float g2, float* d1, f
   *d2 = fe_sum32(w->scr() + 32) + 2.f * g2;
 }
 
+// fe_cone, inlined (outputs stay in registers): zone, force, cost, and with WANTW the 3x3 weight (xx yy zz xy xz yz)
+template <bool WANTW>
+FE_HD int fe_cone_t(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
+  const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { f[0] = f[1] = f[2] = 0.f; if (WANTW) { W[0] = W[1] = W[2] = W[3] = W[4] = W[5] = 0.f; } return 0; }
+  if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
+    f[0] = -D0 * j0; f[1] = -D1 * j1; f[2] = -D1 * j2;
+    *cost += 0.5f * (D0 * j0 * j0 + D1 * (j1 * j1 + j2 * j2));
+    if (WANTW) { W[0] = D0; W[1] = D1; W[2] = D1; W[3] = W[4] = W[5] = 0.f; }
+    return 1;
+  }
+  const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+  *cost += 0.5f * Dm * NmT * NmT;
+  f[0] = -Dm * NmT * mu;
+  f[1] = -f[0] / T * U1 * fr;
+  f[2] = -f[0] / T * U2 * fr;
+  if (WANTW) {
+    const float iT = 1.f / T, a = Dm * mu * mu * iT * iT, b = Dm * NmT * mu * iT;
+    const float h11 = a * U1 * U1 - b * (1.f - U1 * U1 * iT * iT), h22 = a * U2 * U2 - b * (1.f - U2 * U2 * iT * iT), h12 = a * U1 * U2 + b * U1 * U2 * iT * iT;
+    const float h01 = -Dm * mu * U1 * iT, h02 = -Dm * mu * U2 * iT;
+    W[0] = mu * mu * Dm; W[1] = fr * fr * h11; W[2] = fr * fr * h22; W[3] = mu * fr * h01; W[4] = mu * fr * h02; W[5] = fr * fr * h12;
+  }
+  return 2;
+}
 // zone logic of one elliptic contact: forces f, cost, and (if W) the 3x3 weight (xx yy zz xy xz yz); returns state
 FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
   const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
@@ -1176,7 +1200,7 @@ FE_HDN int fe_cone(float j0, float j1, float j2, float mu, float fr, float D0, f
   return 2;
 }
 // rows of one part-vs-world contact in the part's coordinates: J[k] = sgn * [(r x F_k), F_k], r = pos - origin
-FE_HDN void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
+FE_HD void fe_part_rows(const FeWarp* w, int c, int l, float sgn, float* J) {
   float F[9];
       fe_frame_load(w, c, F);
   float r[3];
@@ -1879,8 +1903,8 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w, unsigned skipmask) {
           const float* q = PV(par_);
           const float* ar = w->c_aref() + 3 * c;
           const float* as = w->as() + z;
-          fe_cone(dot6(J, xw) - ar[0], dot6(J + 6, xw) - ar[1], dot6(J + 12, xw) - ar[2], q[2], q[3], q[0], q[1], f, &cw, nullptr);
-          fe_cone(dot6(J, as) - ar[0], dot6(J + 6, as) - ar[1], dot6(J + 12, as) - ar[2], q[2], q[3], q[0], q[1], f, &cs, nullptr);
+          fe_cone_t<false>(dot6(J, xw) - ar[0], dot6(J + 6, xw) - ar[1], dot6(J + 12, xw) - ar[2], q[2], q[3], q[0], q[1], f, &cw, nullptr);
+          fe_cone_t<false>(dot6(J, as) - ar[0], dot6(J + 6, as) - ar[1], dot6(J + 12, as) - ar[2], q[2], q[3], q[0], q[1], f, &cs, nullptr);
           PV(acc_)[0] = cw; PV(acc_)[1] = cs;
         }
       }
@@ -1910,7 +1934,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w, unsigned skipmask) {
           const float* ar = w->c_aref() + 3 * c;
           float f[3], W[6], cc = 0.f;
           PV(jx_)[0] = dot6(J, PV(x_)) - ar[0]; PV(jx_)[1] = dot6(J + 6, PV(x_)) - ar[1]; PV(jx_)[2] = dot6(J + 12, PV(x_)) - ar[2];
-          const int st = fe_cone(PV(jx_)[0], PV(jx_)[1], PV(jx_)[2], q[2], q[3], q[0], q[1], f, &cc, W);
+          const int st = fe_cone_t<true>(PV(jx_)[0], PV(jx_)[1], PV(jx_)[2], q[2], q[3], q[0], q[1], f, &cc, W);
           if (st != 0) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) { // column i of W J, then row i of the lower triangle of J^T W J (W symmetric)
@@ -2029,7 +2053,7 @@ FE_FN void fe_solve_parts_grouped(FeWarp* w, unsigned skipmask) {
         const float* q = PV(par_);
         const float* ar = w->c_aref() + 3 * c;
         float f[3], dummy = 0.f;
-        const int st = fe_cone(dot6(J, PV(x_)) - ar[0], dot6(J + 6, PV(x_)) - ar[1], dot6(J + 12, PV(x_)) - ar[2], q[2], q[3], q[0], q[1], f, &dummy, nullptr);
+        const int st = fe_cone_t<false>(dot6(J, PV(x_)) - ar[0], dot6(J + 6, PV(x_)) - ar[1], dot6(J + 12, PV(x_)) - ar[2], q[2], q[3], q[0], q[1], f, &dummy, nullptr);
         w->c_state()[c] = st;
         for (int k = 0; k < 3; ++k) w->c_f()[3 * c + k] = f[k];
         for (int i = 0; i < 6; ++i) PV(acc_)[i] = J[i] * f[0] + J[6 + i] * f[1] + J[12 + i] * f[2];

@@ -33,6 +33,8 @@ typedef struct fe_scene {
 
 struct FeEnvState {
   float* obs;                                  // [N][obs_dim]
+  float* packed;                               // optional second output of a step: rows [obs | reward | done] (float), stride obs_dim + 2 --
+                                               // the send buffer of the multi-GPU all-gather, written by the step kernel itself
   int *group, *site_connected;                 // [N][npart], [N][nsite]
   int *num_connected, *prev_num_connected, *touched, *picked, *episode_len, *done;
   uint32_t* mt;                                // [N][624] MT19937 state of the env's numpy RandomState(seed + env)
@@ -425,6 +427,8 @@ FE_FN void fe_write_obs(FeEnv* e) {
   const fe_scene* sc = e->sc;
   float* ob = e->es.obs + (size_t)e->env * sc->obs_dim;
   const int nrl = m->nrlink, np = m->npart;
+  for (int pass = 0; pass < (e->es.packed ? 2 : 1); ++pass) {
+  if (pass == 1) ob = e->es.packed + (size_t)e->env * (sc->obs_dim + 2);
   LANES_BEGIN
     for (int p = lane; p < np; p += 32) {
       for (int k = 0; k < 3; ++k) ob[7 * p + k] = w->lpos()[3 * (nrl + p) + k];
@@ -447,6 +451,7 @@ FE_FN void fe_write_obs(FeEnv* e) {
       v3cpy(o + 10, w->lvel() + 6 * l);
     }
   LANES_END
+  }
 }
 
 // FurnitureEnv._reset (furniture.py:1406-1663); the warp slice is (re)initialised here, caller stores it
@@ -637,6 +642,7 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       reward += penalty;
       reward_out[env] = reward;
       done_out[env] = (uint8_t)done;
+      if (e->es.packed) { float* pk = e->es.packed + (size_t)env * (sc->obs_dim + 2) + sc->obs_dim; pk[0] = reward; pk[1] = done ? 1.f : 0.f; }
       int32_t* info = info_out + (size_t)env * FE_INFO_DIM;
       info[0] = nc; info[1] = success; info[2] = fail; info[3] = len; info[4] = w->u()[0]; info[5] = w->u()[3];
       e->es.done[env] = done;

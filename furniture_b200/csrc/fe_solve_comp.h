@@ -21,28 +21,6 @@
 // 6x6 matrix K per pair of links in contact (the scheme of fe_newton_regs), factored and solved by shuffles.
 #pragma once
 
-// fe_cone, inlined (outputs stay in registers): zone, force, cost, 3x3 weight (xx yy zz xy xz yz)
-FE_HD int fe_cone_inl(float j0, float j1, float j2, float mu, float fr, float D0, float D1, float* f, float* cost, float* W) {
-  const float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
-  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { f[0] = f[1] = f[2] = 0.f; W[0] = W[1] = W[2] = W[3] = W[4] = W[5] = 0.f; return 0; }
-  if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
-    f[0] = -D0 * j0; f[1] = -D1 * j1; f[2] = -D1 * j2;
-    *cost += 0.5f * (D0 * j0 * j0 + D1 * (j1 * j1 + j2 * j2));
-    W[0] = D0; W[1] = D1; W[2] = D1; W[3] = W[4] = W[5] = 0.f;
-    return 1;
-  }
-  const float Dm = D0 / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
-  *cost += 0.5f * Dm * NmT * NmT;
-  f[0] = -Dm * NmT * mu;
-  f[1] = -f[0] / T * U1 * fr;
-  f[2] = -f[0] / T * U2 * fr;
-  const float iT = 1.f / T, a = Dm * mu * mu * iT * iT, b = Dm * NmT * mu * iT;
-  const float h11 = a * U1 * U1 - b * (1.f - U1 * U1 * iT * iT), h22 = a * U2 * U2 - b * (1.f - U2 * U2 * iT * iT), h12 = a * U1 * U2 + b * U1 * U2 * iT * iT;
-  const float h01 = -Dm * mu * U1 * iT, h02 = -Dm * mu * U2 * iT;
-  W[0] = mu * mu * Dm; W[1] = fr * fr * h11; W[2] = fr * fr * h22; W[3] = mu * fr * h01; W[4] = mu * fr * h02; W[5] = fr * fr * h12;
-  return 2;
-}
-
 template <int NMAX>
 FE_FN void fe_solve_comp(FeWarp* w, int nA, int ncc, unsigned cplmask, int robot_in) {
   const fe_model* m = w->m;
@@ -262,7 +240,7 @@ FE_FN void fe_solve_comp(FeWarp* w, int nA, int ncc, unsigned cplmask, int robot
 #define COMP_COST(jarr_, wjar, xv_, dst)                                                                                         \
   REGS_BEGIN                                                                                                                       \
     float cc = 0.f;                                                                                                                \
-    if (PV(c_) >= 0) { float ff[3]; fe_cone(PV(jarr_)[0], PV(jarr_)[1], PV(jarr_)[2], PV(par_)[2], PV(par_)[3], PV(par_)[0], PV(par_)[1], ff, &cc, nullptr); } \
+    if (PV(c_) >= 0) { float ff[3]; fe_cone_t<false>(PV(jarr_)[0], PV(jarr_)[1], PV(jarr_)[2], PV(par_)[2], PV(par_)[3], PV(par_)[0], PV(par_)[1], ff, &cc, nullptr); } \
     if (anyweld)                                                                                                                   \
       for (int e = lane; e < ne; e += 32) {                                                                                        \
         if (!w->eq_active()[e]) continue;                                                                                          \
@@ -314,7 +292,7 @@ FE_FN void fe_solve_comp(FeWarp* w, int nA, int ncc, unsigned cplmask, int robot
       if (c >= 0) {
         float W[6], F[9];
         float f3[3];
-        const int st = fe_cone_inl(PV(jar_)[0], PV(jar_)[1], PV(jar_)[2], PV(par_)[2], PV(par_)[3], PV(par_)[0], PV(par_)[1], f3, &cc, W);
+        const int st = fe_cone_t<true>(PV(jar_)[0], PV(jar_)[1], PV(jar_)[2], PV(par_)[2], PV(par_)[3], PV(par_)[0], PV(par_)[1], f3, &cc, W);
         PV(st_) = st;
         PV(f_)[0] = f3[0]; PV(f_)[1] = f3[1]; PV(f_)[2] = f3[2];
         float fw[3] = {0.f, 0.f, 0.f};

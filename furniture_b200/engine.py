@@ -252,6 +252,10 @@ class Engine:
         self._chk(self.L.fe_env_step(self.h, C.c_void_p(actions_dev), C.c_void_p(obs_dev or 0), C.c_void_p(reward_dev or 0), C.c_void_p(done_dev or 0),
                                      C.c_void_p(info_dev or 0), C.c_void_p(stream or 0)))
 
+    def env_step_packed(self, actions_dev, packed_dev, info_dev=None, stream=None):
+        """fe_env_step_packed: the kernel writes rows [obs | reward | done] straight into `packed_dev` (the all-gather send buffer)"""
+        self._chk(self.L.fe_env_step_packed(self.h, C.c_void_p(actions_dev), C.c_void_p(packed_dev), C.c_void_p(info_dev or 0), C.c_void_p(stream or 0)))
+
     def env_step_host(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float32)
         assert a.shape == (self.N, self.act_dim), a.shape

@@ -229,27 +229,63 @@ class ShardedFurnitureEnv:
         self.pack_dim = self.env.obs_dim + 2
         self._pack = torch.empty((envs_per_gpu, self.pack_dim), dtype=torch.float32, device=self.env.device)
         self._all = torch.empty((self.num_envs, self.pack_dim), dtype=torch.float32, device=self.env.device)
+        self.timing, self._events = False, []
 
     @staticmethod
     def shard_seed(seed, rank, envs_per_gpu):
         """env e of rank r is seeded seed + r * envs_per_gpu + e: the reference's seed + rank per env (env/base.py:77)"""
         return seed + rank * envs_per_gpu
 
-    def _gather(self, obs, rew=None, done=None):
-        p = self._pack
-        p[:, : self.env.obs_dim] = obs
-        p[:, self.env.obs_dim] = rew if rew is not None else 0
-        p[:, self.env.obs_dim + 1] = done.float() if done is not None else 0
-        self.dist.all_gather_into_tensor(self._all, p)
+    def _gather(self):
+        self.dist.all_gather_into_tensor(self._all, self._pack)
         return self._all
 
     def reset(self):
         self.env.reset()
-        allp = self._gather(self.env._obs)
+        p = self._pack  # resets are rare: packed on the host side of the stream (the step kernel writes its own rows)
+        p[:, : self.env.obs_dim] = self.env._obs
+        p[:, self.env.obs_dim :] = 0
+        allp = self._gather()
         return self.env._obs_dict(allp[:, : self.env.obs_dim])
 
     def step(self, local_actions):
-        _, rew, done, info = self.env.step(local_actions)
-        allp = self._gather(self.env._obs, rew, done)
-        od = self.env.obs_dim
-        return self.env._obs_dict(allp[:, :od]), allp[:, od], allp[:, od + 1] > 0.5, info
+        """One env step of the local shard, then the single collective of the data path.  The step kernel writes
+        [obs | reward | done] rows into the registered send buffer itself (fe_env_step_packed); with `timing` set, CUDA events
+        separate the kernel from the time spent in the all-gather (which includes waiting for the slowest rank)."""
+        env, t = self.env, self.torch
+        a = t.as_tensor(local_actions["default"] if isinstance(local_actions, dict) else local_actions)
+        if a.device != env.device or a.dtype != t.float32 or not a.is_contiguous():
+            env._act.copy_(a, non_blocking=True)
+            a = env._act
+        assert a.shape == (env.num_envs, env.act_dim), tuple(a.shape)
+        if self.timing:
+            ev = [t.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+        if hasattr(env, "_stream"):
+            env.engine.env_step_packed(a.data_ptr(), self._pack.data_ptr(), env._info.data_ptr(), stream=env._stream())
+            info = env._info
+        else:  # stand-in shard of the gloo tests
+            od_, rew, done, info = env.step(a)
+            self._pack[:, : env.obs_dim] = env._obs
+            self._pack[:, env.obs_dim] = rew
+            self._pack[:, env.obs_dim + 1] = done.float()
+        if self.timing:
+            ev[1].record()
+        allp = self._gather()
+        if self.timing:
+            ev[2].record()
+            self._events.append(ev)
+        od = env.obs_dim
+        return env._obs_dict(allp[:, :od]), allp[:, od], allp[:, od + 1] > 0.5, info
+
+    def local_slice(self, gathered):
+        """rows of this rank's own shard in a gathered (num_envs, ...) tensor"""
+        return gathered[self.rank * self.envs_per_gpu : (self.rank + 1) * self.envs_per_gpu]
+
+    def pop_timing(self):
+        """(kernel_ms, gather_ms) lists of the steps since the last call (needs timing=True; synchronises)"""
+        self.torch.cuda.synchronize()
+        k = [e[0].elapsed_time(e[1]) for e in self._events]
+        g = [e[1].elapsed_time(e[2]) for e in self._events]
+        self._events = []
+        return k, g

@@ -81,6 +81,10 @@ int fe_set_state(fe_handle* h, const float* qpos_host, const float* qvel_host);
 int fe_env_reset(fe_handle* h, const uint8_t* env_mask_dev /* NULL = all */, float* obs_dev, void* stream);
 int fe_env_step(fe_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, int32_t* info_dev,
                 void* stream);
+/* same step, results written by the kernel as rows [obs | reward | done] of (obs_dim + 2) floats: the send buffer of the
+   observation all-gather over env shards (the reference's counterpart is the pipe of
+   util/subproc_vec_env.py:100-113 that carries (ob, reward, done, info) of every worker back to the caller) */
+int fe_env_step_packed(fe_handle* h, const float* actions_dev, float* packed_dev, int32_t* info_dev, void* stream);
 /* same call with host buffers: H2D of the actions and D2H of the results happen inside (pinned staging) */
 int fe_env_step_host(fe_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host, int32_t* info_host);
 /* device pointer of the internal obs buffer after the last step/reset: (n_envs, obs_dim) float32 */

@@ -18,16 +18,22 @@ dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 n = 64
 env = ShardedFurnitureEnv(n)
+env.timing = True
+# the same envs run alone with the same seed and actions are the truth for this rank's slice (no cross-rank coupling)
+alone = BatchedFurnitureEnv("Sawyer", "table_lack_0825", n, device=local, seed=ShardedFurnitureEnv.shard_seed(123, rank, n))
 od = env.reset()
+alone.reset()
 assert od["object_ob"].shape == (n * world, 35) and od["robot_ob"].shape == (n * world, 29)
+assert torch.equal(torch.cat([od["object_ob"], od["robot_ob"]], 1)[rank * n : (rank + 1) * n], alone._obs)
 gen = torch.Generator(device=dev).manual_seed(rank)
 for k in range(3):
     a = torch.rand((n, env.env.act_dim), device=dev, generator=gen) * 2 - 1
     od, rew, done, info = env.step(a)
+    alone.step(a)
     full = torch.cat([od["object_ob"], od["robot_ob"]], 1)
     mine = full[rank * n : (rank + 1) * n]
-    assert torch.equal(mine, env.env._obs), "my slice of the gathered tensor is not my shard"
-    assert torch.equal(rew[rank * n : (rank + 1) * n], env.env._rew)
+    assert torch.equal(mine, alone._obs), "my slice of the gathered tensor is not my shard"
+    assert torch.equal(env.local_slice(rew), alone._rew) and torch.equal(env.local_slice(done), alone._done > 0)
     # every rank holds the same gathered tensor
     chk = [torch.zeros_like(full) for _ in range(world)]
     dist.all_gather(chk, full.contiguous())
@@ -36,15 +42,8 @@ for k in range(3):
     other = full[((rank + 1) % world) * n : ((rank + 1) % world + 1) * n]
     assert not torch.allclose(other[:, :2], mine[:, :2]), "shards with different seeds placed parts identically"
     assert torch.isfinite(full).all()
-# the shard equals the same envs run alone with the same seed and actions (no cross-rank coupling)
-alone = BatchedFurnitureEnv("Sawyer", "table_lack_0825", n, device=local, seed=ShardedFurnitureEnv.shard_seed(123, rank, n))
-alone.reset()
-gen = torch.Generator(device=dev).manual_seed(rank)
-for k in range(3):
-    a = torch.rand((n, alone.act_dim), device=dev, generator=gen) * 2 - 1
-    alone.step(a)
-torch.cuda.synchronize()
-assert torch.equal(alone._obs, env.env._obs), "shard differs from the same envs stepped alone"
+km, gm = env.pop_timing()
+assert len(km) == 3 and all(v > 0 for v in km + gm)
 dist.barrier()
 dist.destroy_process_group()
-print("rank %d of %d ok" % (rank, world))
+print("rank %d of %d ok (kernel %.2f ms, gather %.3f ms)" % (rank, world, sum(km) / 3, sum(gm) / 3))
