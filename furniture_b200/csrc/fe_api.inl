@@ -1,4 +1,4 @@
-// fe_api.inl -- host side of the C-ABI (include/furniture_b200.h), shared by the CUDA library (fe_cuda.cu) and the
+// fe_api.inl -- host side of the C-ABI (include/furniture_b200.h), shared by the CUDA library (fe_host.cpp) and the
 // lane-emulated test build (tests/emu/fe_emu.cpp).  The including file provides the plat_* functions.
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,6 +39,13 @@ struct fe_handle {
 };
 
 static std::string g_create_err;
+// the handle's device is made current for the duration of every entry point and the caller's restored afterwards
+struct FeDevScope {
+  fe_handle* h;
+  int prev;
+  explicit FeDevScope(fe_handle* h_) : h(h_), prev(plat_enter(h_)) {}
+  ~FeDevScope() { plat_leave(h, prev); }
+};
 
 template <typename T>
 static T* h_alloc(fe_handle* h, size_t count) {
@@ -101,6 +108,7 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   if (h->hm.ngeom > 255) { delete h; return fail(nullptr, -1, "fe_create: ngeom must be <= 255"); }
   int rc = plat_init(h);
   if (rc) { std::string e = h->err; delete h; return fail(nullptr, rc, e); }
+  FeDevScope dev_scope(h);
   const fe_model& m = h->hm;
   const size_t N = (size_t)n_envs;
   h->dm = (fe_model*)plat_alloc(sizeof(fe_model));
@@ -173,7 +181,10 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
 void fe_destroy(fe_handle* h) {
   if (!h) return;
   plat_fini(h);
-  for (void* p : h->allocs) plat_free(p);
+  {
+    FeDevScope dev_scope(h);
+    for (void* p : h->allocs) plat_free(p);
+  }
   delete h;
 }
 
@@ -189,6 +200,7 @@ int fe_get_field(fe_handle* h, const char* name, void* dst, size_t bytes) {
   if (!f) return fail(h, -3, std::string("unknown field ") + name);
   size_t want = (size_t)h->N * f->dim * f->elem;
   if (bytes != want) return fail(h, -4, std::string("size mismatch for field ") + name);
+  FeDevScope dev_scope(h);
   plat_sync(h);
   plat_download(dst, f->ptr, bytes);
   return 0;
@@ -199,6 +211,7 @@ int fe_set_field(fe_handle* h, const char* name, const void* src, size_t bytes) 
   if (!f->writable) return fail(h, -5, std::string("field is read-only: ") + name);
   size_t want = (size_t)h->N * f->dim * f->elem;
   if (bytes != want) return fail(h, -4, std::string("size mismatch for field ") + name);
+  FeDevScope dev_scope(h);
   plat_sync(h);
   plat_upload(f->ptr, src, bytes);
   return 0;
@@ -245,6 +258,12 @@ int fe_env_step_packed(fe_handle* h, const float* actions_dev, float* packed_dev
 int fe_env_step_host(fe_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int32_t* info) {
   if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_env_step_host: handle was created without a scene blob");
   return plat_step_host(h, actions, obs, reward, done, info);
+}
+
+int fe_set_max_episode_steps(fe_handle* h, int max_episode_steps) {
+  if (max_episode_steps <= 0) return fail(h, -1, "fe_set_max_episode_steps: must be positive");
+  h->cfg.max_episode_steps = max_episode_steps; // fe_config travels by value with every launch
+  return 0;
 }
 
 int fe_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles, const int32_t* nangles,

@@ -3,6 +3,9 @@
 #pragma once
 #include "fe_engine.h"
 
+#define FE_MAX_WPB 14      /* warps (= envs) per block of the sim / step / reset kernels */
+#define FE_EXTRA_BLOCKS 148 /* spare blocks of the step grid: heavy envs get half-empty blocks */
+
 struct FeState {
   int N;
   float *qpos, *qvel, *warm, *ctrl, *qfrc_applied, *gravcomp, *eq_data; // [N][nq|nv|nv|nu|nr|npart|7 neq]

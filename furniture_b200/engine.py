@@ -267,6 +267,10 @@ class Engine:
                                           done.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p)))
         return obs, rew, done, info
 
+    def set_max_episode_steps(self, n):
+        self._chk(self.L.fe_set_max_episode_steps(self.h, int(n)))
+        self.cfg.max_episode_steps = int(n)
+
     def obs_dev_ptr(self):
         return self.L.fe_obs_dev(self.h)
 

@@ -20,6 +20,38 @@ from .engine import INFO_DIM, Engine, default_config
 
 INFO_KEYS = ("num_connected", "episode_success", "episode_unstable", "episode_length", "ncon", "solver_iters")
 ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer"}
+# furniture_id -> name: the reference numbers the sorted objects/*.xml (furniture/env/models/__init__.py:11-19)
+FURNITURE_NAMES = (
+    "bed_dalselv_0270 bench_bjoderna_0208 bench_bjursta_0210 block bookcase_agerum_0006 bookcase_besta_0165 bookcase_besta_0170 bookcase_besta_0172 "
+    "bookcase_billy_0190 bookcase_billy_0191 bookcase_expedit_0373 bookcase_expedit_0374 bookcase_expedit_0376 bookcase_expedit_0385 bookcase_flaerke_0403 "
+    "bookcase_grevback_0484 bookcase_hensvik_0565 box_ivar_0666 box_lekman_0858 cabinet_akurum_0011 cabinet_akurum_0014 cabinet_akurum_0019 cabinet_akurum_0021 "
+    "cabinet_bjorken_0203 cabinet_lillagen_0933 chair_agam_0005 chair_agne_0007 chair_agne_0010 chair_balser_0115 chair_bernhard_0146 chair_bertil_0148 "
+    "chair_ingolf_0650 chair_ivar_0668 desk_fredrik_0430 desk_hannes_0529 desk_mikael_1064 shelf_ivar_0678 shelf_liden_0922 shelf_lillagen_0927 swivel_chair_0700 "
+    "table_benno_0141 table_billsta_round_0189 table_bjorkudden_0206 table_bjorkudden_0207 table_dalom_0267 table_dockstra_0279 table_expedit_0387 table_hemnes_0539 "
+    "table_hemnes_0541 table_jokkmokk_0694 table_klubbo_0740 table_klubbo_0743 table_lack_0825 table_liden_0919 table_liden_0920 table_liden_0921 table_torsby_1549 "
+    "three_blocks three_blocks_peg toy_table toy_table_flip tvunit_0406 tvunit_lack_0829 tvunit_lack_0830").split()
+
+
+def split_config(config):
+    """Reference-style config (argparse Namespace or dict, config/furniture.py) -> (furniture name, FeConfig overrides, ignored keys).
+    `furniture_name` wins over `furniture_id` as in furniture.py:157-161; keys the accelerated path has no use for (port, background,
+    camera and rendering options ...) are returned so that callers can report them instead of failing on them."""
+    from .engine import FeConfig
+
+    cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
+    if cfg.get("control_type", "impedance") != "impedance":
+        raise NotImplementedError("only control_type='impedance' is accelerated (got %r)" % cfg["control_type"])
+    for k in ("unity", "visual_ob", "depth_ob", "segmentation_ob", "record_demo", "record_vid"):
+        if cfg.get(k):
+            raise NotImplementedError("%s=True needs the renderer, which is outside the accelerated path" % k)
+    name = cfg.get("furniture_name")
+    if name is None and cfg.get("furniture_id") is not None:
+        name = FURNITURE_NAMES[int(cfg["furniture_id"])]
+    fields = {f[0] for f in FeConfig._fields_} - {"struct_bytes"}
+    renamed = {"furn_xyz_rand": "furn_xyz_rand", "furn_rot_rand": "furn_rot_rand", "agent_xyz_rand": "agent_xyz_rand", "alignment_pos_dist": "alignment_pos_dist"}
+    over = {renamed.get(k, k): v for k, v in cfg.items() if renamed.get(k, k) in fields and v is not None}
+    ignored = sorted(k for k in cfg if k not in over and k not in ("furniture_name", "furniture_id", "control_type"))
+    return name or "table_lack_0825", over, ignored
 
 
 class BatchedFurnitureEnv:
@@ -106,21 +138,23 @@ class BatchedFurnitureEnv:
 
 
 def make_vec_env(env_id="IKEASawyer-v0", num_env=1, config=None, device=0):
-    config = dict(config or {})
+    """make_vec_env(env_id, num_env, config) of furniture/env/base.py:55-80: `config` may be the reference's argparse
+    Namespace (config/furniture.py) or a dict; options outside the accelerated path are ignored (listed in `.ignored_config`)."""
     agent = ENV_IDS.get(env_id)
     if agent is None:
         raise ValueError("unknown env id %s (this build accelerates %s)" % (env_id, sorted(ENV_IDS)))
-    if config.pop("control_type", "impedance") != "impedance":
-        raise NotImplementedError("only control_type='impedance' is accelerated")
-    furniture = config.pop("furniture_name", "table_lack_0825")
-    return BatchedFurnitureEnv(agent, furniture, num_env, device=device, **config)
+    furniture, over, ignored = split_config(config)
+    env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, **over)
+    env.ignored_config = ignored
+    return env
 
 
 class MixedFurnitureEnv:
     """A batch over several furniture models at once (BASELINE.json config 5; the reference reaches other furniture through
     `furniture_name` / `furniture_id`, config/furniture.py:43-55, one model per env process).  Envs are bucketed by
-    furniture ("bucket by furniture id first"): one engine handle per model, all stepped from the same CUDA
-    stream, so switching the slice layout between buckets is a stream-ordered constant upload, not a device sync.
+    furniture ("bucket by furniture id first"): one engine handle per model, each with its own instance of the
+    kernels (its own slice-layout table, see csrc/fe_host.cpp) and its own CUDA stream, so the buckets of a step run
+    concurrently and fill the SMs together; the caller's stream waits for all of them at the end of the call.
     nq / nv / obs_dim differ per bucket; `object_ob` is returned zero-padded to the widest model, `robot_ob` is common.
 
       env = MixedFurnitureEnv(["table_lack_0825", "chair_ingolf_0650"], envs_per_model=64)
@@ -151,6 +185,18 @@ class MixedFurnitureEnv:
         self._done = torch.empty(off, dtype=torch.uint8, device=self.device)
         self._info = torch.empty((off, INFO_DIM), dtype=torch.int32, device=self.device)
         self._act = torch.empty((off, self.act_dim), dtype=torch.float32, device=self.device)
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in self.buckets]
+
+    def _fan_out(self, fn):
+        """run fn(bucket, offset) for every bucket on the bucket's own stream, ordered after the caller's stream; join at the end"""
+        t = self.torch
+        cur = t.cuda.current_stream(self.device)
+        for b, off, s in zip(self.buckets, self.offsets, self._streams):
+            s.wait_stream(cur)
+            with t.cuda.stream(s):
+                fn(b, off)
+        for s in self._streams:
+            cur.wait_stream(s)
 
     def bucket_of(self, env_index):
         """(furniture name, index inside its bucket) of a global env index"""
@@ -169,8 +215,7 @@ class MixedFurnitureEnv:
         return OrderedDict(object_ob=self._object_ob, robot_ob=self._robot_ob)
 
     def reset(self):
-        for b, off in zip(self.buckets, self.offsets):
-            self._collect(b, off, b.reset())
+        self._fan_out(lambda b, off: self._collect(b, off, b.reset()))
         return self._obs()
 
     def step(self, actions):
@@ -182,10 +227,12 @@ class MixedFurnitureEnv:
             self._act.copy_(a, non_blocking=True)
             a = self._act
         assert a.shape == (self.num_envs, self.act_dim), tuple(a.shape)
-        for b, off in zip(self.buckets, self.offsets):
+        def one(b, off):
             od, rew, done, info = b.step(a[off : off + b.num_envs])
             sl = self._collect(b, off, od)
             self._rew[sl].copy_(rew); self._done[sl].copy_(done); self._info[sl].copy_(info)
+
+        self._fan_out(one)
         return self._obs(), self._rew, self._done, self._info
 
     def close(self):

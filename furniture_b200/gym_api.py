@@ -29,13 +29,18 @@ AGENTS = {"FurnitureSawyerEnv": "Sawyer", "IKEASawyer-v0": "Sawyer", "Sawyer": "
 class FurnitureGymB200:
     metadata = {"render.modes": []}
 
-    def __init__(self, name="FurnitureSawyerEnv", furniture_name="table_lack_0825", device=0, lib_path=None, control_type="impedance", **config):
+    def __init__(self, name="FurnitureSawyerEnv", furniture_name=None, device=0, lib_path=None, id=None, **config):
+        """`id`, `name` and the remaining keywords are what gym passes from the registration (env/__init__.py:19-114: id, name,
+        furniture_name / furniture_id, background, port ...); options of the renderer are ignored, see env.split_config"""
+        from .env import split_config
+
         if name not in AGENTS:
             raise ValueError("unknown env %s (this build accelerates %s)" % (name, sorted(AGENTS)))
-        if control_type != "impedance":
-            raise NotImplementedError("only control_type='impedance' is accelerated")
+        if furniture_name is not None:
+            config["furniture_name"] = furniture_name
+        furniture_name, over, self.ignored_config = split_config(config)
         self.model = mjcf.load_scene(AGENTS[name], furniture_name)
-        self.cfg = default_config(**config)
+        self.cfg = default_config(**over)
         self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path)
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
@@ -83,6 +88,8 @@ class FurnitureGymB200:
         if isinstance(action, dict):
             action = np.concatenate([np.asarray(v, dtype=np.float32).ravel() for v in action.values()])
         a = np.asarray(action, dtype=np.float32).reshape(1, self.dof)
+        if self._pending_ob is not None:  # stepping on after `done` without reset(): the device is already in the next episode
+            self._pending_ob, self._episode_reward, self._episode_time = None, 0.0, time.time()
         obs, rew, done, info = self.engine.env_step_host(a)
         reward, done = float(rew[0]), bool(done[0])
         self._episode_reward += reward
@@ -101,7 +108,8 @@ class FurnitureGymB200:
 
     # ---- pass-throughs of FurnitureGym (furniture_gym.py:35-50)
     def set_max_episode_steps(self, max_episode_steps):
-        raise NotImplementedError("max_episode_steps is fixed at construction (fe_config.max_episode_steps)")
+        self._max_episode_steps = int(max_episode_steps)
+        self.engine.set_max_episode_steps(self._max_episode_steps)
 
     def get_env_state(self):
         q, v = self.engine.get_state()
@@ -117,3 +125,25 @@ class FurnitureGymB200:
 
     def close(self):
         self.engine.close()
+
+
+def register_gym_envs():
+    """Registers the accelerated counterpart of the reference's gym ids (furniture/env/__init__.py:19-114) when gym or
+    gymnasium is importable: `gym.make("IKEASawyer-v0")` then builds a FurnitureGymB200 with the reference's kwargs
+    (furniture_name="swivel_chair_0700").  Returns the ids registered (empty without gym)."""
+    try:
+        from gym.envs.registration import register
+    except Exception:
+        try:
+            from gymnasium.envs.registration import register
+        except Exception:
+            return []
+    specs = {"IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050}}
+    done = []
+    for env_id, kwargs in specs.items():
+        try:
+            register(id=env_id, entry_point="furniture_b200.gym_api:FurnitureGymB200", kwargs=kwargs)
+            done.append(env_id)
+        except Exception:  # already registered (e.g. by the reference package itself)
+            pass
+    return done

@@ -87,6 +87,9 @@ int fe_env_step(fe_handle* h, const float* actions_dev, float* obs_dev, float* r
 int fe_env_step_packed(fe_handle* h, const float* actions_dev, float* packed_dev, int32_t* info_dev, void* stream);
 /* same call with host buffers: H2D of the actions and D2H of the results happen inside (pinned staging) */
 int fe_env_step_host(fe_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host, int32_t* info_host);
+/* FurnitureGym.set_max_episode_steps -> FurnitureEnv.set_max_episode_steps (furniture_gym.py:35-37, furniture.py:271-272):
+   takes effect from the next step */
+int fe_set_max_episode_steps(fe_handle* h, int max_episode_steps);
 /* device pointer of the internal obs buffer after the last step/reset: (n_envs, obs_dim) float32 */
 const float* fe_obs_dev(const fe_handle* h);
 

@@ -1,5 +1,5 @@
 // fe_emu.cpp -- lane-emulated build of the engine (TEST HARNESS ONLY, never loaded by the package).
-// The same kernel source as furniture_b200/csrc/fe_cuda.cu, compiled by g++ with every lane region run as a 32-trip
+// The same kernel source as furniture_b200/csrc/fe_kernels.cu, compiled by g++ with every lane region run as a 32-trip
 // loop, behind the same C-ABI, so that `-m "not gpu"` tests can exercise the kernel logic without a GPU.
 #define FE_EMULATE 1
 #define PLAT_IS_CUDA 0
@@ -18,6 +18,8 @@ static void plat_download(void* h, const void* d, size_t n) { memcpy(h, d, n); }
 static int plat_init(fe_handle*) { return 0; }
 static void plat_fini(fe_handle*) {}
 static void plat_sync(fe_handle*) {}
+static int plat_enter(fe_handle*) { return -1; }
+static void plat_leave(fe_handle*, int) {}
 static int plat_run_sim(fe_handle* h, int nsub, int mode, void* stream);
 static int plat_run_reset(fe_handle* h, const uint8_t* mask, void* stream);
 static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, void* stream);

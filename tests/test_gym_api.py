@@ -37,3 +37,37 @@ def test_gym_surface_follows_the_reference_env_across_an_episode_boundary():
     st = env.get_env_state()
     assert st["qpos"].shape == (env.model.nq,) and st["qvel"].shape == (env.model.nv,)
     env.close()
+
+
+def test_reference_style_config_and_episode_length_passthrough():
+    """the reference hands its envs an argparse Namespace with dozens of keys (config/furniture.py) and a furniture_id; keys of the
+    renderer are ignored (and listed), physics keys map onto fe_config; set_max_episode_steps passes through (furniture_gym.py:35-37)"""
+    import argparse
+
+    from furniture_b200.env import FURNITURE_NAMES, split_config
+
+    assert len(FURNITURE_NAMES) == 64 and FURNITURE_NAMES[52] == "table_lack_0825" and FURNITURE_NAMES[39] == "swivel_chair_0700"  # SURVEY.md 8d ids
+    ns = argparse.Namespace(furniture_id=52, furniture_name=None, port=1050, background="Lab", unity=False, control_type="impedance",
+                            max_episode_steps=7, furn_xyz_rand=0.01, seed=5, robot_ob=True, object_ob=True, visual_ob=False)
+    name, over, ignored = split_config(ns)
+    assert name == "table_lack_0825" and over == {"max_episode_steps": 7, "furn_xyz_rand": 0.01, "seed": 5}
+    assert "port" in ignored and "background" in ignored
+    env = FurnitureGymB200(name="FurnitureSawyerEnv", lib_path=build_emu(), id="IKEASawyer-v0", nsub=2, **vars(ns))
+    assert env.cfg.max_episode_steps == 7 and env._max_episode_steps == 7
+    env.set_max_episode_steps(2)
+    env.reset()
+    a = np.zeros(env.dof); a[-1] = -1
+    _, _, done, _ = env.step(a)
+    assert not done
+    _, _, done, info = env.step(a)
+    assert done and info["episode_length"] == 2
+    # stepping on without reset(): the stale first observation is dropped, the next episode counts from 1
+    _, _, done, info = env.step(a)
+    assert not done and env._pending_ob is None
+    _, _, done, info = env.step(a)
+    assert done and info["episode_length"] == 2
+    env.close()
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        split_config({"control_type": "ik"})

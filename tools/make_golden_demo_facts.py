@@ -5,11 +5,31 @@ That number is an equilibrium of the soft-contact model (geom masses from densit
 solimp impedance), so it pins those parts of the physics oracle against MuJoCo itself.  The assembled relative poses at the
 end of the recording are NOT usable: they match neither the current XML sites nor its weld data (older model version).
 Needs /root/reference; writes tests/golden/demo_facts.json."""
+import io
 import json
 import os
 import pickle
 
 import numpy as np
+
+
+class _DataOnlyUnpickler(pickle.Unpickler):
+    """the demo files come from the untrusted reference tree: only numpy array reconstruction and builtin containers may be
+    instantiated; any other global in the stream (the hook arbitrary-code pickles rely on) is refused"""
+
+    _ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"), ("numpy", "dtype"),
+                ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("collections", "OrderedDict"),
+                ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"), ("builtins", "frozenset")}
+
+    def find_class(self, module, name):
+        if (module, name) not in self._ALLOWED:
+            raise pickle.UnpicklingError("refusing to load %s.%s from a demo file" % (module, name))
+        return super().find_class(module, name)
+
+
+def load_data_only(path):
+    with open(path, "rb") as f:
+        return _DataOnlyUnpickler(io.BytesIO(f.read())).load()
 
 REF = "/root/reference/demos/Sawyer_7.pkl"
 REF2 = "/root/reference/demos/Cursor_7.pkl"  # same furniture driven by the cursor agent; the base starts with no yaw
@@ -17,13 +37,13 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 
 
 def main():
-    q = pickle.load(open(REF, "rb"))["qpos"]
+    q = load_data_only(REF)["qpos"]
     z = np.array([s["1_chair_base"][2] for s in q])
     rest = z[:10]  # the base has not been touched yet in the first steps
     assert rest.std() < 1e-7
     facts = {"source": "demos/Sawyer_7.pkl of the reference, key 1_chair_base, first 10 recorded states (tools/make_golden_demo_facts.py)",
              "swivel_chair_base_rest_z": float(rest.mean()), "swivel_chair_base_rest_z_std": float(rest.std()), "n_states": int(len(q))}
-    q2 = pickle.load(open(REF2, "rb"))["qpos"]
+    q2 = load_data_only(REF2)["qpos"]
     base = np.array([s["1_chair_base"] for s in q2[:10]])
     assert base.std(0).max() < 1e-7 and abs(base[0, 2] - rest.mean()) < 1e-7  # same rest height in both recordings
     # at rest the base leans by 0.028 degrees about its x axis (its five cylinders are not arranged symmetrically about the
