@@ -220,9 +220,26 @@ def run_ours(args):
     n_local = args.envs_per_gpu
     K, W = args.steps, args.warmup
 
+    mixed = None
+    if args.furniture == "mixed":  # BASELINE.json config 5: every furniture model of the asset tree the compiler accepts, ragged nv / nefc
+        from furniture_b200 import mjcf
+        from furniture_b200.env import MixedFurnitureEnv, shard_furniture
+
+        cdir = os.path.join(ROOT, "furniture_b200", "compiled")
+        names = sorted(f[len(args.agent) + 1 : -4] for f in os.listdir(cdir) if f.startswith(args.agent + "_") and f.endswith(".npz"))
+        models = {n: mjcf.load_scene(args.agent, n) for n in names}
+        owned = shard_furniture(names, 1, world, nv=[models[n].nv for n in names], envs_per_rank=n_local)
+        wide = max(7 * len(models[n].meta["part_names"]) for n in names)
+        mixed = {"models": len(names), "per_rank": [len(o) for o in owned], "nv_range": [min(m.nv for m in models.values()), max(m.nv for m in models.values())]}
+
     def make_env():
         # the two timed legs (device-resident `value`, host-buffer `e2e`) run on two envs built alike -- same seeds, same
         # reset draws, same actions, same step range -- so that their numbers are comparable
+        if mixed is not None:
+            mine = owned[rank]
+            e = MixedFurnitureEnv([n for n, _ in mine], [c for _, c in mine], agent=args.agent, device=local, object_ob_dim=wide,
+                                  seed=ShardedFurnitureEnv.shard_seed(123, rank, n_local))
+            return (ShardedFurnitureEnv(n_local, env=e), e) if world > 1 else (e, e)
         if world > 1:
             e = ShardedFurnitureEnv(n_local, agent=args.agent, furniture_name=args.furniture)
             return e, e.env
@@ -279,7 +296,7 @@ def run_ours(args):
     value = n_local * world * K / (total_ms * 1e-3)
     # kernels launched by this repo inside the timed region, per step: fe_env_step_kernel + fe_order_kernel (block packing for
     # the next step); N > 1 adds NCCL's all-gather kernel (a library kernel, not counted)
-    launches = 2 * K
+    launches = 2 * K * (len(owned[rank]) if mixed is not None else 1)
 
     # ---- leg 2: end to end through the public API with HOST buffers, same actions and step range on the twin env:
     # pinned actions -> H2D -> step (-> all_gather) -> D2H of this rank's results
@@ -316,12 +333,18 @@ def run_ours(args):
     if rank == 0:
         peaks, peak_src = load_peaks()
         kernel_ms = total_ms / K  # one env-step = one launch of fe_env_step_kernel (+ the all_gather when N > 1)
-        benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim)
+        if mixed is not None:
+            benv_bytes = benv.algorithmic_bytes_per_step() / n_local  # mean over this rank's buckets
+        else:
+            benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim)
         assert args.furniture != "table_lack_0825" or args.agent != "Sawyer" or benv_bytes == B_ENV
         achieved = benv_bytes * n_local / (kernel_ms * 1e-3) / 1e9
         act_txt = "random actions U(-1,1)" if args.actions == "random" else "settled (zero arm action, gripper open)"
         default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU
         workload = WORKLOAD if default_case else "Furniture%sEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.agent, args.furniture, act_txt)
+        if mixed is not None:
+            workload = ("Furniture%sEnv, mixed-furniture batch: %d furniture models (nv %d..%d), whole buckets per GPU (%s models per rank), one kernel-module "
+                        "instance and stream per bucket, 50 mj_steps per env-step, %s" % (args.agent, mixed["models"], mixed["nv_range"][0], mixed["nv_range"][1], mixed["per_rank"], act_txt))
         # measured DRAM traffic and instruction counts come from an ncu capture of exactly this kernel build
         # (tools/ncu_extract.py writes profiles/traffic.json with the build id); a stale capture is refused
         traffic, secondary, prof_note = None, None, None

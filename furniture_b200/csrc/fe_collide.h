@@ -13,19 +13,19 @@ struct FeCon {
 
 FE_HD void fe_col(float* r, const float* R, int k) { r[0] = R[k]; r[1] = R[3 + k]; r[2] = R[6 + k]; }
 
-FE_HD int fe_plane_sphere(const float* pp, const float* pR, const float* c, float r, FeCon* out) {
+FE_HD int fe_plane_sphere(const float* pp, const float* pR, const float* c, float r, float margin, FeCon* out) {
   float n[3], t[3];
   fe_col(n, pR, 2);
   v3sub(t, c, pp);
   float dist = v3dot(t, n) - r;
-  if (dist >= 0.f) return 0;
+  if (dist >= margin) return 0;
   out->dist = dist;
   v3madd(out->pos, c, n, -(r + 0.5f * dist));
   v3cpy(out->n, n);
   return 1;
 }
 
-FE_HD int fe_plane_box(const float* pp, const float* pR, const float* c, const float* R, const float* s, FeCon* out) {
+FE_HD int fe_plane_box(const float* pp, const float* pR, const float* c, const float* R, const float* s, float margin, FeCon* out) {
   float n[3];
   fe_col(n, pR, 2);
   int cnt = 0;
@@ -35,7 +35,7 @@ FE_HD int fe_plane_box(const float* pp, const float* pR, const float* c, const f
     float t[3];
     v3sub(t, corner, pp);
     float dist = v3dot(t, n);
-    if (dist >= 0.f) continue;
+    if (dist >= margin) continue;
     out[cnt].dist = dist;
     v3madd(out[cnt].pos, corner, n, -0.5f * dist);
     v3cpy(out[cnt].n, n);
@@ -44,7 +44,7 @@ FE_HD int fe_plane_box(const float* pp, const float* pR, const float* c, const f
   return cnt;
 }
 
-FE_HD int fe_plane_cylinder(const float* pp, const float* pR, const float* c, const float* R, float r, float h, FeCon* out) {
+FE_HD int fe_plane_cylinder(const float* pp, const float* pR, const float* c, const float* R, float r, float h, float margin, FeCon* out) {
   float n[3], ax[3], vec[3], p[3], t[3];
   fe_col(n, pR, 2);
   fe_col(ax, R, 2);
@@ -57,29 +57,46 @@ FE_HD int fe_plane_cylinder(const float* pp, const float* pR, const float* c, co
   for (int k = 0; k < 3; ++k) p[k] = c[k] + ax[k] * h + vec[k];
   v3sub(t, p, pp);
   float dist = v3dot(t, n);
-  if (dist >= 0.f) return 0;
+  if (dist >= margin) return 0;
   int cnt = 0;
   out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt;
   for (int k = 0; k < 3; ++k) p[k] = c[k] - ax[k] * h + vec[k];
   v3sub(t, p, pp);
   dist = v3dot(t, n);
-  if (dist < 0.f) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
+  if (dist < margin) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
   float w[3];
   v3cross(w, vec, ax);
   for (int sg = -1; sg <= 1; sg += 2) {
     for (int k = 0; k < 3; ++k) p[k] = c[k] + ax[k] * h - 0.5f * vec[k] + (float)sg * 0.8660254037844386f * w[k];
     v3sub(t, p, pp);
     dist = v3dot(t, n);
-    if (dist < 0.f) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
+    if (dist < margin) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
   }
   return cnt;
 }
 
-FE_HD int fe_sphere_sphere(const float* c1, float r1, const float* c2, float r2, FeCon* out) {
+// plane - capsule: the two end spheres of the segment (mjc_PlaneCapsule)
+FE_HD int fe_plane_capsule(const float* pp, const float* pR, const float* c, const float* R, float r, float h, float margin, FeCon* out) {
+  float n[3], ax[3];
+  fe_col(n, pR, 2);
+  fe_col(ax, R, 2);
+  int cnt = 0;
+  for (int sg = 1; sg >= -1; sg -= 2) {
+    float e[3], t[3];
+    v3madd(e, c, ax, (float)sg * h);
+    v3sub(t, e, pp);
+    const float dist = v3dot(t, n) - r;
+    if (dist >= margin) continue;
+    out[cnt].dist = dist; v3madd(out[cnt].pos, e, n, -(r + 0.5f * dist)); v3cpy(out[cnt].n, n); ++cnt;
+  }
+  return cnt;
+}
+
+FE_HD int fe_sphere_sphere(const float* c1, float r1, const float* c2, float r2, float margin, FeCon* out) {
   float n[3];
   v3sub(n, c2, c1);
   float d = v3norm(n), dist = d - r1 - r2;
-  if (dist >= 0.f) return 0;
+  if (dist >= margin) return 0;
   if (d < 1e-20f) { n[0] = 1.f; n[1] = n[2] = 0.f; } else { float s = 1.f / d; n[0] *= s; n[1] *= s; n[2] *= s; }
   out->dist = dist;
   v3madd(out->pos, c1, n, r1 + 0.5f * dist);
@@ -87,7 +104,7 @@ FE_HD int fe_sphere_sphere(const float* c1, float r1, const float* c2, float r2,
   return 1;
 }
 
-FE_HD int fe_sphere_box(const float* c, float r, const float* bc, const float* R, const float* s, FeCon* out) {
+FE_HD int fe_sphere_box(const float* c, float r, const float* bc, const float* R, const float* s, float margin, FeCon* out) {
   float t[3], loc[3], cl[3], n[3];
   v3sub(t, c, bc);
   m3tmulv(loc, R, t);
@@ -101,7 +118,7 @@ FE_HD int fe_sphere_box(const float* c, float r, const float* bc, const float* R
     float dl[3] = {cl[0] - loc[0], cl[1] - loc[1], cl[2] - loc[2]};
     float d = v3norm(dl);
     dist = d - r;
-    if (dist >= 0.f) return 0;
+    if (dist >= margin) return 0;
     m3mulv(n, R, dl);
     float inv = 1.f / d;
     n[0] *= inv; n[1] *= inv; n[2] *= inv;
@@ -142,7 +159,7 @@ FE_HD int fe_clip(float (*poly)[3], int n, const float* cR, const float* ax, flo
   return m;
 }
 
-FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const float* cB, const float* RB, const float* b, FeCon* out) {
+FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const float* cB, const float* RB, const float* b, float margin, FeCon* out) {
   float A[3][3], B[3][3], d[3], Cm[3][3], AC[3][3], dA[3], dB[3];
   for (int k = 0; k < 3; ++k) { fe_col(A[k], RA, k); fe_col(B[k], RB, k); }
   v3sub(d, cB, cA);
@@ -153,12 +170,12 @@ FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const flo
   int face = -1;
   for (int i = 0; i < 3; ++i) {
     float sep = fabsf(dA[i]) - (a[i] + b[0] * AC[i][0] + b[1] * AC[i][1] + b[2] * AC[i][2]);
-    if (sep > 0.f) return 0;
+    if (sep > margin) return 0;
     if (sep > best_face) { best_face = sep; face = i; }
   }
   for (int j = 0; j < 3; ++j) {
     float sep = fabsf(dB[j]) - (b[j] + a[0] * AC[0][j] + a[1] * AC[1][j] + a[2] * AC[2][j]);
-    if (sep > 0.f) return 0;
+    if (sep > margin) return 0;
     if (sep > best_face) { best_face = sep; face = 3 + j; }
   }
   float best_edge = -1e30f;
@@ -173,7 +190,7 @@ FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const flo
       float ra = a[i1] * AC[i2][j] + a[i2] * AC[i1][j];
       float rb = b[j1] * AC[i][j2] + b[j2] * AC[i][j1];
       float sep = (fabsf(dl) - ra - rb) / l;
-      if (sep > 0.f) return 0;
+      if (sep > margin) return 0;
       if (sep > best_edge) { best_edge = sep; ei = i; ej = j; }
     }
   if (ei >= 0 && -best_edge < 0.95f * (-best_face) - 1e-5f) {
@@ -227,7 +244,7 @@ FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const flo
     float t[3];
     v3sub(t, poly[q], cR);
     float depth = hR[ri] - v3dot(t, nref);
-    if (depth <= 0.f) continue;
+    if (depth <= -margin) continue;
     out[cnt].dist = -depth;
     v3madd(out[cnt].pos, poly[q], nref, 0.5f * depth);
     for (int k = 0; k < 3; ++k) out[cnt].n[k] = refIsA ? nref[k] : -nref[k];
@@ -240,6 +257,7 @@ FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const flo
 struct FeCvx {
   int type;
   const float *pos, *mat, *size;
+  float inflate; // half the contact margin: the support function pushes the surface out by it (mjccd_support), fe_mpr takes it back
 };
 FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
   float l[3], p[3];
@@ -252,6 +270,10 @@ FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
     p[0] = l[0] >= 0.f ? g.size[0] : -g.size[0];
     p[1] = l[1] >= 0.f ? g.size[1] : -g.size[1];
     p[2] = l[2] >= 0.f ? g.size[2] : -g.size[2];
+  } else if (g.type == 3) { // capsule: a sphere swept along the local z segment
+    float n = v3norm(l);
+    float s = n > 1e-20f ? g.size[0] / n : 0.f;
+    p[0] = l[0] * s; p[1] = l[1] * s; p[2] = l[2] * s + (l[2] >= 0.f ? g.size[1] : -g.size[1]);
   } else {
     float n = sqrtf(l[0] * l[0] + l[1] * l[1]);
     float s = n > 1e-20f ? g.size[0] / n : 0.f;
@@ -260,6 +282,7 @@ FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
   }
   m3mulv(out, g.mat, p);
   v3add(out, out, g.pos);
+  if (g.inflate != 0.f) v3madd(out, out, dir, g.inflate);
 }
 struct FeSup {
   float v[3], v1[3], v2[3];
@@ -346,7 +369,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
     v3cpy(out->n, p[1].v);
     float depth = v3normalize(out->n);
     if (!(depth > 0.f)) return 0;
-    out->dist = -depth;
+    out->dist = -depth + g1.inflate + g2.inflate;
     for (int k = 0; k < 3; ++k) out->pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]);
     return 1;
   }
@@ -390,7 +413,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
       if (depth < 1e-9f) v3cpy(out->n, dir);
       else { float s = 1.f / depth; out->n[0] = w[0] * s; out->n[1] = w[1] * s; out->n[2] = w[2] * s; }
       if (!(depth > 0.f)) return 0;
-      out->dist = -depth;
+      out->dist = -depth + g1.inflate + g2.inflate;
       fe_find_pos(p, out->pos);
       return 1;
     }
@@ -398,17 +421,21 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
   }
 }
 
-// dispatch on the (ordered) type pair; geometry in world frame. Returns contact count (<= 8).
-FE_HDN int fe_narrowphase(int t1, const float* p1, const float* R1, const float* s1, int t2, const float* p2, const float* R2, const float* s2, FeCon* out) {
+// dispatch on the (ordered) type pair; geometry in world frame; contacts closer than `margin` are reported (mj_collision:
+// dist < margin, margin = max of the two geoms').  Returns contact count (<= 8).
+FE_HDN int fe_narrowphase(int t1, const float* p1, const float* R1, const float* s1, int t2, const float* p2, const float* R2, const float* s2, float margin, FeCon* out) {
   if (t1 == 0) {
-    if (t2 == 2) return fe_plane_sphere(p1, R1, p2, s2[0], out);
-    if (t2 == 5) return fe_plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], out);
-    if (t2 == 6) return fe_plane_box(p1, R1, p2, R2, s2, out);
+    if (t2 == 2) return fe_plane_sphere(p1, R1, p2, s2[0], margin, out);
+    if (t2 == 3) return fe_plane_capsule(p1, R1, p2, R2, s2[0], s2[1], margin, out);
+    if (t2 == 5) return fe_plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], margin, out);
+    if (t2 == 6) return fe_plane_box(p1, R1, p2, R2, s2, margin, out);
     return 0;
   }
-  if (t1 == 2 && t2 == 2) return fe_sphere_sphere(p1, s1[0], p2, s2[0], out);
-  if (t1 == 2 && t2 == 6) return fe_sphere_box(p1, s1[0], p2, R2, s2, out);
-  if (t1 == 6 && t2 == 6) return fe_box_box(p1, R1, s1, p2, R2, s2, out);
-  FeCvx a = {t1, p1, R1, s1}, b = {t2, p2, R2, s2};
+  if (t1 == 2 && t2 == 2) return fe_sphere_sphere(p1, s1[0], p2, s2[0], margin, out);
+  if (t1 == 2 && t2 == 6) return fe_sphere_box(p1, s1[0], p2, R2, s2, margin, out);
+  if (t1 == 6 && t2 == 6) return fe_box_box(p1, R1, s1, p2, R2, s2, margin, out);
+  // every other pair (a cylinder or a capsule on one side) goes through MPR; MuJoCo has analytic routines for the capsule
+  // pairs (mjc_CapsuleBox ...), which can return two points where MPR returns the deepest one
+  FeCvx a = {t1, p1, R1, s1, 0.5f * margin}, b = {t2, p2, R2, s2, 0.5f * margin};
   return fe_mpr(a, b, out);
 }

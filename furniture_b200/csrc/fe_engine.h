@@ -618,6 +618,7 @@ FE_FN void fe_kin_smooth(FeWarp* w) {
       inert_mulv(F, Ic, Sd);
       for (int a = d; a >= 0; a = m->link_parent[a]) {
         float v = dot6(w->S() + 6 * a, F);
+        if (a == d) v += m->rdof_armature[d];
         w->Mr()[d * nr + a] = v;
         w->Mr()[a * nr + d] = v;
       }
@@ -723,12 +724,13 @@ FE_FN void fe_collide(FeWarp* w) {
           float t[3];
           v3sub(t, w->gpos() + 3 * g2, w->gpos() + 3 * g1);
           bool hit;
+          const float mg = fmaxf(m->geom_margin[g1], m->geom_margin[g2]);
           if (m->geom_type[g1] == FE_GEOM_PLANE) {
             float n[3];
             fe_col(n, w->gmat() + 9 * g1, 2);
-            hit = v3dot(t, n) <= m->geom_rbound[g2];
+            hit = v3dot(t, n) <= m->geom_rbound[g2] + mg;
           } else {
-            const float bnd = m->geom_rbound[g1] + m->geom_rbound[g2];
+            const float bnd = m->geom_rbound[g1] + m->geom_rbound[g2] + mg;
             hit = v3dot(t, t) <= bnd * bnd;
           }
           if (hit) hits |= 1ull << (k - k0);
@@ -760,7 +762,7 @@ FE_FN void fe_collide(FeWarp* w) {
         const int k = w->cand()[ci];
         g1 = m->pair_g1[k]; g2 = m->pair_g2[k];
         n = fe_narrowphase(m->geom_type[g1], w->gpos() + 3 * g1, w->gmat() + 9 * g1, m->geom_size[g1], m->geom_type[g2], w->gpos() + 3 * g2, w->gmat() + 9 * g2,
-                           m->geom_size[g2], res);
+                           m->geom_size[g2], fmaxf(m->geom_margin[g1], m->geom_margin[g2]), res);
       }
       const int off = FE_SCAN(run, n);
       for (int i = 0; i < n; ++i) {
@@ -778,7 +780,7 @@ FE_FN void fe_collide(FeWarp* w) {
     LANES_BEGIN LANES_END
   }
   if (ncon > mc) { ncon = mc; LANES_BEGIN if (lane == 0) w->u()[2] |= 1; LANES_END }
-  // touch flags per part: bit0 left finger, bit1 right finger, bit2 floor (furniture.py:500-520, :1290-1322)
+  // touch flags per part: bit0 left finger, bit1 right finger, bit2 floor, bit3 / bit4 the fingers of a second arm (furniture.py:500-520, :1290-1322)
   LANES_BEGIN
     const int p = lane;
     if (p < m->npart) {
@@ -787,8 +789,8 @@ FE_FN void fe_collide(FeWarp* w) {
         const int g1 = w->c_geom()[c] & 255, g2 = w->c_geom()[c] >> 8;
         const int t1 = m->geom_tag[g1], t2 = m->geom_tag[g2];
         const int p1 = ((t1 >> FE_TAG_PART_SHIFT) & 0xff) - 1, p2 = ((t2 >> FE_TAG_PART_SHIFT) & 0xff) - 1;
-        if (p1 == p) bits |= ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0) | ((t2 & FE_TAG_FLOOR) ? 4 : 0);
-        if (p2 == p) bits |= ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0) | ((t1 & FE_TAG_FLOOR) ? 4 : 0);
+        if (p1 == p) bits |= ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0) | ((t2 & FE_TAG_FLOOR) ? 4 : 0) | ((t2 & FE_TAG_LFINGER2) ? 8 : 0) | ((t2 & FE_TAG_RFINGER2) ? 16 : 0);
+        if (p2 == p) bits |= ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0) | ((t1 & FE_TAG_FLOOR) ? 4 : 0) | ((t1 & FE_TAG_LFINGER2) ? 8 : 0) | ((t1 & FE_TAG_RFINGER2) ? 16 : 0);
       }
       w->touch()[p] = bits;
     }
@@ -873,7 +875,7 @@ FE_FN void fe_assemble(FeWarp* w) {
       if (s1[0] > 0.f && s2[0] > 0.f) { sr[0] = 0.5f * (s1[0] + s2[0]); sr[1] = 0.5f * (s1[1] + s2[1]); }
       else { sr[0] = fminf(s1[0], s2[0]); sr[1] = fminf(s1[1], s2[1]); }
       for (int k = 0; k < 3; ++k) si[k] = 0.5f * (m->geom_solimp[g1][k] + m->geom_solimp[g2][k]);
-      const float dist = w->c_dist()[c];
+      const float dist = w->c_dist()[c] - fmaxf(m->geom_margin[g1], m->geom_margin[g2]); // efc_pos - efc_margin (gap = 0: every contact is active)
       const float imp = fe_impedance(si, fabsf(dist));
       float kk, bb;
       fe_kb(sr, si[1], h, &kk, &bb);

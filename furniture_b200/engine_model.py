@@ -19,8 +19,8 @@ import numpy as np
 from . import mjcf
 
 MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU = 32, 20, 16, 116, 96, 2048, 256, 40, 20
-MAGIC = 0x46453031
-TAG_FLOOR, TAG_LFINGER, TAG_RFINGER, TAG_ROBOT, TAG_PART_SHIFT = 1, 2, 4, 8, 8
+MAGIC = 0x46453032
+TAG_FLOOR, TAG_LFINGER, TAG_RFINGER, TAG_ROBOT, TAG_LFINGER2, TAG_RFINGER2, TAG_PART_SHIFT = 1, 2, 4, 8, 16, 32, 8
 
 i32, f32 = C.c_int32, C.c_float
 
@@ -35,7 +35,7 @@ class FeModel(C.Structure):
         ("link_depth", i32 * MAXLINK), ("link_ancmask", i32 * MAXLINK),
         ("link_pos", (f32 * 3) * MAXLINK), ("link_quat", (f32 * 4) * MAXLINK), ("link_jaxis", (f32 * 3) * MAXLINK), ("link_jpos", (f32 * 3) * MAXLINK),
         ("link_mass", f32 * MAXLINK), ("link_com", (f32 * 3) * MAXLINK), ("link_inertia_c", (f32 * 6) * MAXLINK), ("link_inertia_o", (f32 * 6) * MAXLINK),
-        ("dof_damping", f32 * MAXDOF),
+        ("dof_damping", f32 * MAXDOF), ("rdof_armature", f32 * MAXRDOF),
         ("rdof_limited", i32 * MAXRDOF), ("rdof_range", (f32 * 2) * MAXRDOF), ("rdof_invweight", f32 * MAXRDOF),
         ("rdof_solref", (f32 * 2) * MAXRDOF), ("rdof_solimp", (f32 * 3) * MAXRDOF),
         ("act_type", i32 * MAXU), ("act_dof", i32 * MAXU), ("act_qadr", i32 * MAXU), ("act_ctrllimited", i32 * MAXU), ("act_forcelimited", i32 * MAXU),
@@ -43,6 +43,7 @@ class FeModel(C.Structure):
         ("geom_type", i32 * MAXGEOM), ("geom_link", i32 * MAXGEOM), ("geom_contype0", i32 * MAXGEOM), ("geom_conaffinity0", i32 * MAXGEOM), ("geom_tag", i32 * MAXGEOM),
         ("geom_pos", (f32 * 3) * MAXGEOM), ("geom_mat", (f32 * 9) * MAXGEOM), ("geom_size", (f32 * 3) * MAXGEOM), ("geom_rbound", f32 * MAXGEOM),
         ("geom_friction", f32 * MAXGEOM), ("geom_solref", (f32 * 2) * MAXGEOM), ("geom_solimp", (f32 * 3) * MAXGEOM), ("geom_invweight", f32 * MAXGEOM),
+        ("geom_margin", f32 * MAXGEOM),
         ("pair_g1", i32 * MAXPAIR), ("pair_g2", i32 * MAXPAIR),
         ("site_link", i32 * MAXSITE), ("site_pos", (f32 * 3) * MAXSITE), ("site_quat", (f32 * 4) * MAXSITE),
         ("eq_link1", i32 * MAXEQ), ("eq_link2", i32 * MAXEQ), ("eq_active0", i32 * MAXEQ),
@@ -133,6 +134,7 @@ class EngineModel:
             fm.dof_damping[d] = m.dof_damping[d]
         for i in range(nrl):
             j = int(m.body_jntadr[order[i]])
+            fm.rdof_armature[i] = m.dof_armature[i]
             fm.rdof_limited[i] = int(m.jnt_limited[j])
             fm.rdof_range[i][:] = list(m.jnt_range[j])
             fm.rdof_invweight[i] = m.dof_invweight0[i]
@@ -155,6 +157,7 @@ class EngineModel:
         # geoms that can ever collide
         meta = m.meta or {}
         lf, rf = set(meta.get("l_finger_geoms", [])), set(meta.get("r_finger_geoms", []))
+        lf2, rf2 = set(meta.get("l_finger_geoms2", [])), set(meta.get("r_finger_geoms2", []))  # second arm (Baxter's left gripper)
         robot_geoms = set(meta.get("robot_contact_geoms", []))
         part_names = list(meta.get("part_names", [m.names["body"][b] for b in parts]))
         keep = [g for g in range(m.ngeom) if m.geom_contype[g] != 0 or m.geom_conaffinity[g] != 0 or "collision" in m.names["geom"][g]]
@@ -167,7 +170,7 @@ class EngineModel:
             l = weld_link(b)
             name = m.names["geom"][g]
             fm.geom_type[i] = int(m.geom_type[g])
-            assert fm.geom_type[i] in (0, 2, 5, 6), "geom type not supported by the engine: %s" % name
+            assert fm.geom_type[i] in (0, 2, 3, 5, 6), "geom type not supported by the engine: %s" % name
             fm.geom_link[i] = l
             fm.geom_contype0[i] = int(m.geom_contype[g])
             fm.geom_conaffinity0[i] = int(m.geom_conaffinity[g])
@@ -178,6 +181,10 @@ class EngineModel:
                 tag |= TAG_LFINGER
             if name in rf:
                 tag |= TAG_RFINGER
+            if name in lf2:
+                tag |= TAG_LFINGER2
+            if name in rf2:
+                tag |= TAG_RFINGER2
             if name in robot_geoms:
                 tag |= TAG_ROBOT
             bname = m.names["body"][b]
@@ -205,7 +212,8 @@ class EngineModel:
             assert abs(m.geom_solimp[g][3] - 0.5) < 1e-12 and abs(m.geom_solimp[g][4] - 2) < 1e-12
             fm.geom_solimp[i][:] = list(m.geom_solimp[g][:3])
             fm.geom_invweight[i] = m.body_invweight0[b][0]
-            assert m.geom_condim[g] == 3 and m.geom_margin[g] == 0 and m.geom_gap[g] == 0, "engine assumes condim=3, margin=gap=0"
+            assert m.geom_condim[g] == 3 and m.geom_gap[g] == 0, "engine assumes condim=3 and gap=0 (every reported contact is active)"
+            fm.geom_margin[i] = m.geom_margin[g]
         pairs = []
         for g1, g2 in m.collision_pairs:
             if int(g1) in self.geom_map and int(g2) in self.geom_map:

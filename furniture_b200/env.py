@@ -161,7 +161,7 @@ class MixedFurnitureEnv:
       obs = env.reset(); obs, rew, done, info = env.step(actions)          # actions: (num_envs, dof)
     """
 
-    def __init__(self, furniture_names, envs_per_model, agent="Sawyer", device=0, **cfg_overrides):
+    def __init__(self, furniture_names, envs_per_model, agent="Sawyer", device=0, object_ob_dim=None, **cfg_overrides):
         import torch
 
         self.torch = torch
@@ -178,14 +178,24 @@ class MixedFurnitureEnv:
         b0 = self.buckets[0]
         self.device, self.act_dim, self.dof, self.robot_ob_dim = b0.device, b0.act_dim, b0.act_dim, b0.robot_ob_dim
         assert all(b.act_dim == self.act_dim and b.robot_ob_dim == self.robot_ob_dim for b in self.buckets)
-        self.object_ob_dim = max(b.object_ob_dim for b in self.buckets)
-        self._object_ob = torch.zeros((off, self.object_ob_dim), dtype=torch.float32, device=self.device)
-        self._robot_ob = torch.empty((off, self.robot_ob_dim), dtype=torch.float32, device=self.device)
+        # object_ob is zero-padded to the widest model of this batch, or to `object_ob_dim` (the widest of a sharded batch, so
+        # that every rank's rows have the same width)
+        self.object_ob_dim = max([b.object_ob_dim for b in self.buckets] + [object_ob_dim or 0])
+        self.obs_dim = self.object_ob_dim + self.robot_ob_dim
+        self._obs = torch.zeros((off, self.obs_dim), dtype=torch.float32, device=self.device)  # [object_ob (padded) | robot_ob]
+        self._object_ob, self._robot_ob = self._obs[:, : self.object_ob_dim], self._obs[:, self.object_ob_dim :]
         self._rew = torch.empty(off, dtype=torch.float32, device=self.device)
         self._done = torch.empty(off, dtype=torch.uint8, device=self.device)
         self._info = torch.empty((off, INFO_DIM), dtype=torch.int32, device=self.device)
         self._act = torch.empty((off, self.act_dim), dtype=torch.float32, device=self.device)
         self._streams = [torch.cuda.Stream(device=self.device) for _ in self.buckets]
+
+    def _obs_dict(self, obs):
+        return OrderedDict(object_ob=obs[:, : self.object_ob_dim], robot_ob=obs[:, self.object_ob_dim :])
+
+    def algorithmic_bytes_per_step(self, nsub=50):
+        """sum over the buckets of envs x (nsub x 4 (2 nq + 5 nv + nu) + 4 (obs + act) + 8)"""
+        return sum(b.num_envs * (nsub * 4 * (2 * b.model.nq + 5 * b.model.nv + b.model.nu) + 4 * (b.obs_dim + b.act_dim) + 8) for b in self.buckets)
 
     def _fan_out(self, fn):
         """run fn(bucket, offset) for every bucket on the bucket's own stream, ordered after the caller's stream; join at the end"""
@@ -211,12 +221,9 @@ class MixedFurnitureEnv:
         self._robot_ob[sl].copy_(od["robot_ob"])
         return sl
 
-    def _obs(self):
-        return OrderedDict(object_ob=self._object_ob, robot_ob=self._robot_ob)
-
     def reset(self):
         self._fan_out(lambda b, off: self._collect(b, off, b.reset()))
-        return self._obs()
+        return self._obs_dict(self._obs)
 
     def step(self, actions):
         t = self.torch
@@ -233,17 +240,19 @@ class MixedFurnitureEnv:
             self._rew[sl].copy_(rew); self._done[sl].copy_(done); self._info[sl].copy_(info)
 
         self._fan_out(one)
-        return self._obs(), self._rew, self._done, self._info
+        return self._obs_dict(self._obs), self._rew, self._done, self._info
 
     def close(self):
         for b in self.buckets:
             b.close()
 
 
-def shard_furniture(names, envs_per_model, world, nv=None):
+def shard_furniture(names, envs_per_model, world, nv=None, envs_per_rank=None):
     """Whole furniture buckets per GPU for a mixed batch ("bucket by furniture id first so each GPU gets
     whole buckets, balance by sum nv^3"): longest-processing-time greedy on envs * nv^3 (nv from the compiled tables unless
-    given).  Returns, per rank, the list of (name, envs) it owns; every rank computes the same answer."""
+    given).  Returns, per rank, the list of (name, envs) it owns; every rank computes the same answer.  With `envs_per_rank`
+    the env counts are then re-dealt inside each rank so that every rank holds exactly that many envs (the all-gather of the
+    step needs equal shards): its models share them evenly, the first ones taking the remainder."""
     counts = [envs_per_model] * len(names) if isinstance(envs_per_model, int) else list(envs_per_model)
     if nv is None:
         nv = [mjcf.load_scene("Sawyer", n).nv for n in names]
@@ -254,6 +263,11 @@ def shard_furniture(names, envs_per_model, world, nv=None):
         r = min(range(world), key=lambda k: (load[k], k))
         load[r] += cost[i]
         owned[r].append((names[i], counts[i]))
+    if envs_per_rank is not None:
+        for r in range(world):
+            k = len(owned[r])
+            assert 0 < k <= envs_per_rank, "rank %d owns %d models for %d envs" % (r, k, envs_per_rank)
+            owned[r] = [(nm, envs_per_rank // k + (1 if j < envs_per_rank % k else 0)) for j, (nm, _) in enumerate(owned[r])]
     return owned
 
 

@@ -553,7 +553,7 @@ void om_make_constraint(const om_model* m, om_data* d) {
       const double* fr = con->frame + 3 * k;
       for (int i = 0; i < nv; i++)
         row[i] = fr[0] * (jp2[i] - jp1[i]) + fr[1] * (jp2[nv + i] - jp1[nv + i]) + fr[2] * (jp2[2 * nv + i] - jp1[2 * nv + i]);
-      add_row(d, nv, dim == 1 ? OM_EFC_CONTACT_FRICTIONLESS : OM_EFC_CONTACT_ELLIPTIC, c, row, k == 0 ? con->dist : 0, 0, w);
+      add_row(d, nv, dim == 1 ? OM_EFC_CONTACT_FRICTIONLESS : OM_EFC_CONTACT_ELLIPTIC, c, row, k == 0 ? con->dist : 0, k == 0 ? con->margin : 0, w);
     }
   }
   d->nc = d->nefc - d->ne - d->nl;

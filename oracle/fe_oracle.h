@@ -69,6 +69,7 @@ typedef struct om_contact {
   double solref[2];
   double solimp[5];
   double mu; /* regularised cone mu */
+  double margin; /* max of the two geoms' margins; the constraint acts on dist - margin */
   int dim;
   int geom1, geom2;
   int efc_address;

@@ -56,17 +56,17 @@ static void set_contact(om_contact* c, double dist, const double* pos, const dou
 }
 
 /* ---------------------------------------------------------------- analytic pairs */
-static int plane_sphere(const double* pp, const double* pR, const double* c, double r, om_contact* out) {
+static int plane_sphere(const double* pp, const double* pR, const double* c, double r, double margin, om_contact* out) {
   double n[3], t[3], pos[3];
   col3(n, pR, 2);
   sub3(t, c, pp);
   double dist = dot3(t, n) - r;
-  if (dist >= 0) return 0;
+  if (dist >= margin) return 0;
   addscl3(pos, c, n, -(r + 0.5 * dist));
   set_contact(out, dist, pos, n);
   return 1;
 }
-static int plane_box(const double* pp, const double* pR, const double* c, const double* R, const double* s, om_contact* out) {
+static int plane_box(const double* pp, const double* pR, const double* c, const double* R, const double* s, double margin, om_contact* out) {
   double n[3];
   col3(n, pR, 2);
   int cnt = 0;
@@ -75,14 +75,14 @@ static int plane_box(const double* pp, const double* pR, const double* c, const 
     for (int k = 0; k < 3; k++) corner[k] = c[k] + R[3 * k] * loc[0] + R[3 * k + 1] * loc[1] + R[3 * k + 2] * loc[2];
     sub3(t, corner, pp);
     double dist = dot3(t, n);
-    if (dist >= 0) continue;
+    if (dist >= margin) continue;
     addscl3(pos, corner, n, -0.5 * dist);
     set_contact(out + cnt, dist, pos, n);
     cnt++;
   }
   return cnt;
 }
-static int plane_cylinder(const double* pp, const double* pR, const double* c, const double* R, double r, double h, om_contact* out) {
+static int plane_cylinder(const double* pp, const double* pR, const double* c, const double* R, double r, double h, double margin, om_contact* out) {
   double n[3], axis[3], vec[3], t[3], pos[3], p[3];
   col3(n, pR, 2);
   col3(axis, R, 2);
@@ -97,14 +97,14 @@ static int plane_cylinder(const double* pp, const double* pR, const double* c, c
   for (int k = 0; k < 3; k++) p[k] = c[k] + axis[k] * h + vec[k];
   sub3(t, p, pp);
   double dist = dot3(t, n);
-  if (dist >= 0) return 0;
+  if (dist >= margin) return 0;
   addscl3(pos, p, n, -0.5 * dist);
   set_contact(out + cnt++, dist, pos, n);
   /* 2: same side of the far disc (cylinder lying on its side) */
   for (int k = 0; k < 3; k++) p[k] = c[k] - axis[k] * h + vec[k];
   sub3(t, p, pp);
   dist = dot3(t, n);
-  if (dist < 0) { addscl3(pos, p, n, -0.5 * dist); set_contact(out + cnt++, dist, pos, n); }
+  if (dist < margin) { addscl3(pos, p, n, -0.5 * dist); set_contact(out + cnt++, dist, pos, n); }
   /* 3,4: triangle points on the near disc (cylinder standing on its cap) */
   double w[3];
   cross3(w, vec, axis);
@@ -112,22 +112,39 @@ static int plane_cylinder(const double* pp, const double* pR, const double* c, c
     for (int k = 0; k < 3; k++) p[k] = c[k] + axis[k] * h - 0.5 * vec[k] + sgn * 0.8660254037844386 * w[k];
     sub3(t, p, pp);
     dist = dot3(t, n);
-    if (dist < 0) { addscl3(pos, p, n, -0.5 * dist); set_contact(out + cnt++, dist, pos, n); }
+    if (dist < margin) { addscl3(pos, p, n, -0.5 * dist); set_contact(out + cnt++, dist, pos, n); }
   }
   return cnt;
 }
-static int sphere_sphere(const double* c1, double r1, const double* c2, double r2, om_contact* out) {
+/* plane - capsule: the two end spheres of the segment (mjc_PlaneCapsule) */
+static int plane_capsule(const double* pp, const double* pR, const double* c, const double* R, double r, double h, double margin, om_contact* out) {
+  double n[3], axis[3];
+  col3(n, pR, 2);
+  col3(axis, R, 2);
+  int cnt = 0;
+  for (int sg = 1; sg >= -1; sg -= 2) {
+    double e[3], t[3], pos[3];
+    addscl3(e, c, axis, sg * h);
+    sub3(t, e, pp);
+    double dist = dot3(t, n) - r;
+    if (dist >= margin) continue;
+    addscl3(pos, e, n, -(r + 0.5 * dist));
+    set_contact(out + cnt++, dist, pos, n);
+  }
+  return cnt;
+}
+static int sphere_sphere(const double* c1, double r1, const double* c2, double r2, double margin, om_contact* out) {
   double n[3], pos[3];
   sub3(n, c2, c1);
   double d = norm3(n);
   double dist = d - r1 - r2;
-  if (dist >= 0) return 0;
+  if (dist >= margin) return 0;
   if (d < MINVAL) { n[0] = 1; n[1] = n[2] = 0; } else { n[0] /= d; n[1] /= d; n[2] /= d; }
   addscl3(pos, c1, n, r1 + 0.5 * dist);
   set_contact(out, dist, pos, n);
   return 1;
 }
-static int sphere_box(const double* c, double r, const double* bc, const double* R, const double* s, om_contact* out) {
+static int sphere_box(const double* c, double r, const double* bc, const double* R, const double* s, double margin, om_contact* out) {
   double t[3], loc[3], cl[3], n[3], pos[3];
   sub3(t, c, bc);
   for (int k = 0; k < 3; k++) loc[k] = R[k] * t[0] + R[3 + k] * t[1] + R[6 + k] * t[2]; /* R^T t */
@@ -141,7 +158,7 @@ static int sphere_box(const double* c, double r, const double* bc, const double*
     double dl[3] = {cl[0] - loc[0], cl[1] - loc[1], cl[2] - loc[2]}; /* sphere centre -> closest point (box frame) */
     double d = norm3(dl);
     dist = d - r;
-    if (dist >= 0) return 0;
+    if (dist >= margin) return 0;
     for (int k = 0; k < 3; k++) n[k] = (R[3 * k] * dl[0] + R[3 * k + 1] * dl[1] + R[3 * k + 2] * dl[2]) / d;
   } else { /* centre inside the box: exit through the nearest face */
     int best = 0;
@@ -179,7 +196,7 @@ static int clip_poly(double (*poly)[3], int n, const double* cR, const double* a
   for (int i = 0; i < m; i++) memcpy(poly[i], outp[i], 3 * sizeof(double));
   return m;
 }
-static int box_box(const double* cA, const double* RA, const double* a, const double* cB, const double* RB, const double* b, om_contact* out) {
+static int box_box(const double* cA, const double* RA, const double* a, const double* cB, const double* RB, const double* b, double margin, om_contact* out) {
   double A[3][3], B[3][3], d[3], C[3][3], AC[3][3], dA[3], dB[3];
   for (int k = 0; k < 3; k++) { col3(A[k], RA, k); col3(B[k], RB, k); }
   sub3(d, cB, cA);
@@ -188,12 +205,12 @@ static int box_box(const double* cA, const double* RA, const double* a, const do
   double best_face = -1e300; int face = -1;
   for (int i = 0; i < 3; i++) {
     double sep = fabs(dA[i]) - (a[i] + b[0] * AC[i][0] + b[1] * AC[i][1] + b[2] * AC[i][2]);
-    if (sep > 0) return 0;
+    if (sep > margin) return 0;
     if (sep > best_face) { best_face = sep; face = i; }
   }
   for (int j = 0; j < 3; j++) {
     double sep = fabs(dB[j]) - (b[j] + a[0] * AC[0][j] + a[1] * AC[1][j] + a[2] * AC[2][j]);
-    if (sep > 0) return 0;
+    if (sep > margin) return 0;
     if (sep > best_face) { best_face = sep; face = 3 + j; }
   }
   double best_edge = -1e300; int ei = -1, ej = -1;
@@ -207,7 +224,7 @@ static int box_box(const double* cA, const double* RA, const double* a, const do
       double ra = a[i1] * AC[i2][j] + a[i2] * AC[i1][j];
       double rb = b[j1] * AC[i][j2] + b[j2] * AC[i][j1];
       double sep = (fabs(dl) - ra - rb) / l;
-      if (sep > 0) return 0;
+      if (sep > margin) return 0;
       if (sep > best_edge) { best_edge = sep; ei = i; ej = j; }
     }
   if (ei >= 0 && -best_edge < 0.95 * (-best_face) - 1e-5) {
@@ -262,7 +279,7 @@ static int box_box(const double* cA, const double* RA, const double* a, const do
     double t[3], pos[3];
     sub3(t, poly[q], cR);
     double depth = hR[ri] - dot3(t, nref);
-    if (depth <= 0) continue;
+    if (depth <= -margin) continue;
     addscl3(pos, poly[q], nref, 0.5 * depth);
     set_contact(out + cnt, -depth, pos, nrm);
     cnt++;
@@ -271,7 +288,7 @@ static int box_box(const double* cA, const double* RA, const double* a, const do
 }
 
 /* ---------------------------------------------------------------- MPR for convex pairs (sphere/cylinder/box) */
-typedef struct { int type; const double *pos, *mat, *size; } cvx;
+typedef struct { int type; const double *pos, *mat, *size; double inflate; /* half the contact margin, added along the query direction (mjccd_support) */ } cvx;
 static void support(const cvx* g, const double* dir, double* out) {
   double l[3] = {g->mat[0] * dir[0] + g->mat[3] * dir[1] + g->mat[6] * dir[2], g->mat[1] * dir[0] + g->mat[4] * dir[1] + g->mat[7] * dir[2],
                  g->mat[2] * dir[0] + g->mat[5] * dir[1] + g->mat[8] * dir[2]};
@@ -281,13 +298,17 @@ static void support(const cvx* g, const double* dir, double* out) {
     for (int k = 0; k < 3; k++) p[k] = n > MINVAL ? l[k] / n * g->size[0] : 0;
   } else if (g->type == G_BOX) {
     for (int k = 0; k < 3; k++) p[k] = l[k] >= 0 ? g->size[k] : -g->size[k];
+  } else if (g->type == G_CAPSULE) { /* sphere swept along the local z segment */
+    double n = norm3(l);
+    for (int k = 0; k < 3; k++) p[k] = n > MINVAL ? l[k] / n * g->size[0] : 0;
+    p[2] += l[2] >= 0 ? g->size[1] : -g->size[1];
   } else { /* cylinder */
     double n = sqrt(l[0] * l[0] + l[1] * l[1]);
     p[0] = n > MINVAL ? l[0] / n * g->size[0] : 0;
     p[1] = n > MINVAL ? l[1] / n * g->size[0] : 0;
     p[2] = l[2] >= 0 ? g->size[1] : -g->size[1];
   }
-  for (int k = 0; k < 3; k++) out[k] = g->pos[k] + g->mat[3 * k] * p[0] + g->mat[3 * k + 1] * p[1] + g->mat[3 * k + 2] * p[2];
+  for (int k = 0; k < 3; k++) out[k] = g->pos[k] + g->mat[3 * k] * p[0] + g->mat[3 * k + 1] * p[1] + g->mat[3 * k + 2] * p[2] + g->inflate * dir[k];
 }
 typedef struct { double v[3], v1[3], v2[3]; } sup;
 static void mink(const cvx* g1, const cvx* g2, const double* dir, sup* s) { /* point of (g1 - g2) furthest along dir */
@@ -425,7 +446,7 @@ static int convex_pair(const cvx* g1, const cvx* g2, om_contact* out) {
   double depth, dir[3], pos[3];
   if (!mpr_penetration(g1, g2, &depth, dir, pos)) return 0;
   if (depth <= 0) return 0;
-  set_contact(out, -depth, pos, dir);
+  set_contact(out, -depth + g1->inflate + g2->inflate, pos, dir);
   return 1;
 }
 
@@ -436,27 +457,29 @@ int om_collide_pair(const om_model* m, const om_data* d, int g1, int g2, om_cont
   const double *p1 = d->geom_xpos + 3 * g1, *R1 = d->geom_xmat + 9 * g1, *s1 = m->geom_size + 3 * g1;
   const double *p2 = d->geom_xpos + 3 * g2, *R2 = d->geom_xmat + 9 * g2, *s2 = m->geom_size + 3 * g2;
   int n = 0;
+  const double margin = m->geom_margin[g1] > m->geom_margin[g2] ? m->geom_margin[g1] : m->geom_margin[g2]; /* mj_contactParam: max */
   if (t1 == G_PLANE) {
     double t[3], nrm[3];
     col3(nrm, R1, 2);
     sub3(t, p2, p1);
-    if (dot3(t, nrm) > m->geom_rbound[g2]) return 0;
-    if (t2 == G_SPHERE) n = plane_sphere(p1, R1, p2, s2[0], out);
-    else if (t2 == G_CYLINDER) n = plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], out);
-    else if (t2 == G_BOX) n = plane_box(p1, R1, p2, R2, s2, out);
+    if (dot3(t, nrm) > m->geom_rbound[g2] + margin) return 0;
+    if (t2 == G_SPHERE) n = plane_sphere(p1, R1, p2, s2[0], margin, out);
+    else if (t2 == G_CAPSULE) n = plane_capsule(p1, R1, p2, R2, s2[0], s2[1], margin, out);
+    else if (t2 == G_CYLINDER) n = plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], margin, out);
+    else if (t2 == G_BOX) n = plane_box(p1, R1, p2, R2, s2, margin, out);
     else return 0;
   } else {
     double t[3];
     sub3(t, p2, p1);
-    double bound = m->geom_rbound[g1] + m->geom_rbound[g2];
+    double bound = m->geom_rbound[g1] + m->geom_rbound[g2] + margin;
     if (dot3(t, t) > bound * bound) return 0;
-    if (t1 == G_SPHERE && t2 == G_SPHERE) n = sphere_sphere(p1, s1[0], p2, s2[0], out);
-    else if (t1 == G_SPHERE && t2 == G_BOX) n = sphere_box(p1, s1[0], p2, R2, s2, out);
-    else if (t1 == G_BOX && t2 == G_BOX) n = box_box(p1, R1, s1, p2, R2, s2, out);
-    else if ((t1 == G_SPHERE || t1 == G_CYLINDER) && (t2 == G_CYLINDER || t2 == G_BOX)) {
-      cvx a = {t1, p1, R1, s1}, b = {t2, p2, R2, s2};
+    if (t1 == G_SPHERE && t2 == G_SPHERE) n = sphere_sphere(p1, s1[0], p2, s2[0], margin, out);
+    else if (t1 == G_SPHERE && t2 == G_BOX) n = sphere_box(p1, s1[0], p2, R2, s2, margin, out);
+    else if (t1 == G_BOX && t2 == G_BOX) n = box_box(p1, R1, s1, p2, R2, s2, margin, out);
+    else { /* a cylinder or a capsule on one side: MPR on shapes inflated by half the margin each */
+      cvx a = {t1, p1, R1, s1, 0.5 * margin}, b = {t2, p2, R2, s2, 0.5 * margin};
       n = convex_pair(&a, &b, out);
-    } else return 0;
+    }
   }
   /* mj_contactParam */
   for (int i = 0; i < n; i++) {
@@ -472,7 +495,7 @@ int om_collide_pair(const om_model* m, const om_data* d, int g1, int g2, om_cont
     if (sr1[0] > 0 && sr2[0] > 0) { c->solref[0] = 0.5 * (sr1[0] + sr2[0]); c->solref[1] = 0.5 * (sr1[1] + sr2[1]); }
     else { c->solref[0] = sr1[0] < sr2[0] ? sr1[0] : sr2[0]; c->solref[1] = sr1[1] < sr2[1] ? sr1[1] : sr2[1]; }
     for (int k = 0; k < 5; k++) c->solimp[k] = 0.5 * (m->geom_solimp[5 * g1 + k] + m->geom_solimp[5 * g2 + k]);
-    c->mu = 0; c->efc_address = -1;
+    c->mu = 0; c->efc_address = -1; c->margin = margin;
     for (int k = 0; k < 5; k++) if (c->friction[k] < 1e-5) c->friction[k] = 1e-5; /* mjMINMU */
     if (c->dim != 1) c->dim = 3; /* condim 1 and 3 only in these scenes */
   }

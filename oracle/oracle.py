@@ -34,7 +34,7 @@ DBL_ARRAYS = (
 class Contact(C.Structure):
     _fields_ = [
         ("dist", C.c_double), ("pos", C.c_double * 3), ("frame", C.c_double * 9), ("friction", C.c_double * 5),
-        ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double), ("dim", C.c_int),
+        ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double), ("margin", C.c_double), ("dim", C.c_int),
         ("geom1", C.c_int), ("geom2", C.c_int), ("efc_address", C.c_int),
     ]
 

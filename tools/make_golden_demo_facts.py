@@ -52,7 +52,7 @@ def main():
     # the whole first state of the Cursor recording: all three parts standing untouched (base flat, column and seat upright)
     facts["cursor7_rest_state"] = {k: [float(v) for v in np.mean([s[k] for s in q2[:10]], axis=0)] for k in ("1_chair_base", "2_chair_column", "3_chair_seat")}
     # demos/Baxter_0.pkl: the two boxes of the `block` furniture at rest (solref 0.001 < 2 h: the refsafe clamp is in play)
-    q3 = pickle.load(open("/root/reference/demos/Baxter_0.pkl", "rb"))["qpos"]
+    q3 = load_data_only("/root/reference/demos/Baxter_0.pkl")["qpos"]
     blocks = {k: np.array([s[k] for s in q3[:10]]) for k in ("1_block_l", "2_block_r")}
     assert all(v[:, 2:].std(0).max() < 1e-7 for v in blocks.values())  # height and orientation are still; x / y creep by 2e-7 per recorded step
     facts["baxter0_rest_state"] = {k: [float(x) for x in v[0]] for k, v in blocks.items()}
