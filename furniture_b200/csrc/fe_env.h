@@ -15,7 +15,8 @@
 
 typedef struct fe_scene {
   int32_t magic, struct_bytes;
-  int32_t obs_dim, act_dim, robot_ob_dim, nconn, npart, narm, ngrip;
+  int32_t obs_dim, act_dim, robot_ob_dim, nconn, npart, narm, ngrip; // narm / ngrip: arm / gripper joints of all arms together
+  int32_t narms;                                                      // 1 (Sawyer) or 2 (Baxter: right, left -- furniture.py:89-92)
   // action -> actuator map: ctrl[u] = bias_u + weight_u * sign_u * clip(action[src_u]) (furniture.py:3332-3367)
   int32_t act_src[FE_MAXU];
   float act_sign[FE_MAXU];
@@ -25,9 +26,12 @@ typedef struct fe_scene {
   double conn_cos[FE_MAXCONN][4], conn_sin[FE_MAXCONN][4]; // cos/sin(angle/180*pi) evaluated on the host in float64
   int32_t eq_part1[FE_MAXEQ], eq_part2[FE_MAXEQ];
   int32_t part_site_start[FE_MAXPART + 1], part_sites[FE_MAXSITE]; // sites per part for _get_bounding_box
-  int32_t eef_site, hand_link;
-  float hand_quat[4];
-  float robot_init_qpos[FE_MAXRDOF]; // arm then gripper, in robot dof order
+  int32_t eef_site[2], hand_link[2]; // per arm: grip site and the link that carries the "<arm>_hand" body
+  float hand_quat[2][4];
+  // robot dof of every arm joint (mujoco_robot.joints order: right arm, then left) and of every gripper joint (right gripper, then
+  // left); the other robot dofs (Baxter's head_pan) get neither gravity compensation nor a reset pose (furniture.py:3372-3377, :1761-1779)
+  int32_t arm_dof[FE_MAXRDOF], grip_dof[8];
+  float robot_init_qpos[FE_MAXRDOF]; // arm joints (arm_dof order), then gripper joints (grip_dof order)
   float part_init_pos[FE_MAXPART][3], part_init_quat[FE_MAXPART][4], part_radius[FE_MAXPART];
 } fe_scene;
 
@@ -435,20 +439,23 @@ FE_FN void fe_write_obs(FeEnv* e) {
       for (int k = 0; k < 4; ++k) ob[7 * p + 3 + k] = w->lquat()[4 * (nrl + p) + k];
     }
     float* rb = ob + 7 * np;
-    const int na = sc->narm, ngr = sc->ngrip;
-    for (int d = lane; d < na; d += 32) { rb[d] = w->qpos()[d]; rb[na + d] = w->qvel()[d]; }
-    for (int d = lane; d < ngr; d += 32) rb[2 * na + d] = w->qpos()[na + d];
-    if (lane == 0 && sc->eef_site >= 0) {
-      float* o = rb + 2 * na + ngr;
-      const int s = sc->eef_site, l = m->site_link[s], hl = sc->hand_link;
-      float t[3], sp[3], q[4];
-      m3mulv(t, w->lmat() + 9 * l, m->site_pos[s]);
-      v3add(sp, w->lpos() + 3 * l, t);
-      v3cpy(o, sp);
-      qmul(q, w->lquat() + 4 * hl, sc->hand_quat);
-      o[3] = q[1]; o[4] = q[2]; o[5] = q[3]; o[6] = q[0]; // xyzw
-      fe_point_vel(w, w->lvel(), l, sp, o + 7);
-      v3cpy(o + 10, w->lvel() + 6 * l);
+    const int nar = sc->narms > 0 ? sc->narms : 1, na = sc->narm / nar, ngr = sc->ngrip / nar, per = 2 * na + ngr + 13; // per arm: qpos, qvel, gripper, eef pos, quat, velp, velr
+    for (int arm = 0; arm < sc->narms; ++arm) {
+      float* r = rb + arm * per;
+      for (int d = lane; d < na; d += 32) { const int dof = sc->arm_dof[arm * na + d]; r[d] = w->qpos()[dof]; r[na + d] = w->qvel()[dof]; }
+      for (int d = lane; d < ngr; d += 32) r[2 * na + d] = w->qpos()[sc->grip_dof[arm * ngr + d]];
+      if (lane == 0 && sc->eef_site[arm] >= 0) {
+        float* o = r + 2 * na + ngr;
+        const int s = sc->eef_site[arm], l = m->site_link[s], hl = sc->hand_link[arm];
+        float t[3], sp[3], q[4];
+        m3mulv(t, w->lmat() + 9 * l, m->site_pos[s]);
+        v3add(sp, w->lpos() + 3 * l, t);
+        v3cpy(o, sp);
+        qmul(q, w->lquat() + 4 * hl, sc->hand_quat[arm]);
+        o[3] = q[1]; o[4] = q[2]; o[5] = q[3]; o[6] = q[0]; // xyzw
+        fe_point_vel(w, w->lvel(), l, sp, o + 7);
+        v3cpy(o + 10, w->lvel() + 6 * l);
+      }
     }
   LANES_END
   }
@@ -530,14 +537,17 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
   // gravity compensation, robot pose, one step with robot collisions still off (furniture.py:1569-1584)
   for (int phase = 0; phase < 101; ++phase) {
     LANES_BEGIN
-      if (phase <= 1) for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d];
+      if (phase <= 1) {
+        for (int i = lane; i < sc->narm; i += 32) w->qfrc_applied()[sc->arm_dof[i]] = w->bias()[sc->arm_dof[i]];
+        for (int i = lane; i < sc->ngrip; i += 32) w->qfrc_applied()[sc->grip_dof[i]] = w->bias()[sc->grip_dof[i]];
+      }
       if (phase == 1) for (int g = lane; g < ng; g += 32) if (m->geom_tag[g] & FE_TAG_ROBOT) { w->contype()[g] = rct[g]; w->conaff()[g] = rca[g]; } // :1586-1595
       if (lane == 0) { // _initialize_robot_pos (furniture.py:1761-1779): fresh noise on every call
         uint32_t* mt = e->es.mt + (size_t)e->env * FE_MT_N;
         int pos = e->es.mt_pos[e->env];
         const double r = (double)cfg->agent_xyz_rand; // _init_random(shape, "agent") = rng.uniform(-r, r, size=7), furniture.py:336-349
-        for (int d = 0; d < sc->narm; ++d) w->qpos()[d] = (float)ndadd((double)sc->robot_init_qpos[d], fe_mt_uniform(mt, &pos, -r, r));
-        for (int d = sc->narm; d < sc->narm + sc->ngrip; ++d) w->qpos()[d] = sc->robot_init_qpos[d];
+        for (int i = 0; i < sc->narm; ++i) w->qpos()[sc->arm_dof[i]] = (float)ndadd((double)sc->robot_init_qpos[i], fe_mt_uniform(mt, &pos, -r, r));
+        for (int i = 0; i < sc->ngrip; ++i) w->qpos()[sc->grip_dof[i]] = sc->robot_init_qpos[sc->narm + i];
         e->es.mt_pos[e->env] = pos;
       }
     LANES_END
@@ -551,7 +561,10 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
     for (int i = lane; i < m->nv; i += 32) w->warm()[i] = 0.f;
   LANES_END
   fe_forward(e->w);
-  LANES_BEGIN for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d]; LANES_END
+  LANES_BEGIN
+    for (int i = lane; i < sc->narm; i += 32) w->qfrc_applied()[sc->arm_dof[i]] = w->bias()[sc->arm_dof[i]];
+    for (int i = lane; i < sc->ngrip; i += 32) w->qfrc_applied()[sc->grip_dof[i]] = w->bias()[sc->grip_dof[i]];
+  LANES_END
   for (int i = 0; i < 100; ++i) fe_fwd_step(e);
   LANES_BEGIN
     if (lane == 0) { e->es.done[e->env] = 0; if (w->u()[2] & 8) { /* a reset that diverges is reported, not hidden */ } }
@@ -567,8 +580,8 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
   const fe_config* cfg = e->cfg;
   const int nr = m->nr, np = m->npart, env = e->env;
   const float* a = action + (size_t)env * sc->act_dim;
-  float grip = a[sc->grip_action_index];
-  if (cfg->discrete_grip) grip = grip < 0.f ? -1.f : 1.f; // furniture_sawyer.py:73-74
+  float grip = sc->grip_action_index >= 0 ? a[sc->grip_action_index] : 0.f;
+  if (cfg->discrete_grip) grip = grip < 0.f ? -1.f : 1.f; // FurnitureSawyerEnv._step only (furniture_sawyer.py:73-74); Baxter: index -1
   const float connect = a[sc->connect_action_index];
   LANES_BEGIN
     for (int u = lane; u < m->nu; u += 32) { // _setup_action, furniture.py:3332-3367
@@ -582,7 +595,8 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       }
       w->ctrl()[u] = v;
     }
-    for (int d = lane; d < nr; d += 32) w->qfrc_applied()[d] = w->bias()[d]; // gravity compensation, :3372-3377
+    for (int i = lane; i < sc->narm; i += 32) w->qfrc_applied()[sc->arm_dof[i]] = w->bias()[sc->arm_dof[i]]; // gravity compensation, :3372-3377
+    for (int i = lane; i < sc->ngrip; i += 32) w->qfrc_applied()[sc->grip_dof[i]] = w->bias()[sc->grip_dof[i]];
     if (lane == 0) { e->ei[0] = 0; e->ei[1] = -1; e->ei[6] = 0; w->u()[2] = 0; }
   LANES_END
   for (int i = 0; i < cfg->nsub; ++i) fe_substep_lockstep(w); // _do_simulation, furniture.py:2877-2879
@@ -591,12 +605,15 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
   if (fail) {
     fe_env_reset_one(e);
   } else {
-    if (connect > 0.f) { // furniture.py:1290-1322
-      int part = -1;
-      for (int p = 0; p < np; ++p) if ((w->touch()[p] & 3) == 3) { part = p; break; }
-      if (part >= 0) {
-        fe_try_connect_scan(e, part);
-        if (e->ei[0]) fe_connect(e);
+    if (connect > 0.f) { // furniture.py:1290-1322: per arm, the first part both of its fingers touch; stop at the first connection
+      for (int arm = 0; arm < sc->narms; ++arm) {
+        const int both = arm == 0 ? 3 : 24;
+        int part = -1;
+        for (int p = 0; p < np; ++p) if ((w->touch()[p] & both) == both) { part = p; break; }
+        if (part >= 0) {
+          fe_try_connect_scan(e, part);
+          if (e->ei[0]) { fe_connect(e); break; }
+        }
       }
     }
     const int repin = e->ei[1];
@@ -621,13 +638,14 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
       int* touched = e->es.touched + (size_t)env * np;
       int* picked = e->es.picked + (size_t)env * np;
       if (!fail)
-        for (int p = 0; p < np; ++p) {
-          const int t = w->touch()[p];
-          if ((t & 3) == 3) {
-            if (!touched[p]) { touched[p] = 1; touch_r += cfg->touch_reward; }
-            if (!(t & 4) && !picked[p]) { picked[p] = 1; pick_r += cfg->pick_reward; }
+        for (int arm = 0; arm < sc->narms; ++arm) // furniture.py:492-523: both fingers of the same arm
+          for (int p = 0; p < np; ++p) {
+            const int t = w->touch()[p], both = arm == 0 ? 3 : 24;
+            if ((t & both) == both) {
+              if (!touched[p]) { touched[p] = 1; touch_r += cfg->touch_reward; }
+              if (!(t & 4) && !picked[p]) { picked[p] = 1; pick_r += cfg->pick_reward; }
+            }
           }
-        }
       const int nc = e->es.num_connected[env];
       const float success_r = cfg->success_reward * (float)(nc - e->es.prev_num_connected[env]);
       e->es.prev_num_connected[env] = nc;

@@ -37,13 +37,14 @@ class FeConfig(C.Structure):
 class FeScene(C.Structure):
     _fields_ = [
         ("magic", i32), ("struct_bytes", i32),
-        ("obs_dim", i32), ("act_dim", i32), ("robot_ob_dim", i32), ("nconn", i32), ("npart", i32), ("narm", i32), ("ngrip", i32),
+        ("obs_dim", i32), ("act_dim", i32), ("robot_ob_dim", i32), ("nconn", i32), ("npart", i32), ("narm", i32), ("ngrip", i32), ("narms", i32),
         ("act_src", i32 * MAXU), ("act_sign", f32 * MAXU), ("grip_action_index", i32), ("connect_action_index", i32),
         ("conn_site", i32 * MAXCONN), ("conn_part", i32 * MAXCONN), ("conn_a", i32 * MAXCONN), ("conn_b", i32 * MAXCONN), ("conn_nangles", i32 * MAXCONN),
         ("conn_cos", (f64 * 4) * MAXCONN), ("conn_sin", (f64 * 4) * MAXCONN),
         ("eq_part1", i32 * MAXEQ), ("eq_part2", i32 * MAXEQ),
         ("part_site_start", i32 * (MAXPART + 1)), ("part_sites", i32 * MAXSITE),
-        ("eef_site", i32), ("hand_link", i32), ("hand_quat", f32 * 4),
+        ("eef_site", i32 * 2), ("hand_link", i32 * 2), ("hand_quat", (f32 * 4) * 2),
+        ("arm_dof", i32 * MAXRDOF), ("grip_dof", i32 * 8),
         ("robot_init_qpos", f32 * MAXRDOF),
         ("part_init_pos", (f32 * 3) * MAXPART), ("part_init_quat", (f32 * 4) * MAXPART), ("part_radius", f32 * MAXPART),
     ]
@@ -88,30 +89,47 @@ def build_scene(m: mjcf.Model, em: EngineModel) -> FeScene:
     narm, ngrip = len(meta.get("robot_joints", [])), len(meta.get("gripper_joints", []))
     sc.npart, sc.narm, sc.ngrip = npart, narm, ngrip
     has_robot = narm > 0
-    sc.robot_ob_dim = (2 * narm + ngrip + 3 + 4 + 3 + 3) if has_robot else 0  # furniture_sawyer.py:40
+    narms = (2 if meta.get("eef_site2") else 1) if has_robot else 0
+    sc.narms = narms
+    # per arm: qpos 7, qvel 7, gripper 2, eef pos 3, quat 4, velp 3, velr 3 (furniture_sawyer.py:40, furniture_baxter.py:36-42)
+    sc.robot_ob_dim = narms * (2 * (narm // narms) + ngrip // narms + 3 + 4 + 3 + 3) if has_robot else 0
     sc.obs_dim = 7 * npart + sc.robot_ob_dim
-    sc.act_dim = (narm + 2) if has_robot else 1
+    sc.act_dim = (narm + narms + 1) if has_robot else 1  # arm joints, one gripper action per arm, connect
+    sc.eef_site[0] = sc.eef_site[1] = -1
+    sc.hand_link[0] = sc.hand_link[1] = -1
     if has_robot:
-        # Sawyer: 7 arm actions, one gripper action fanned out as [g, -g] (two_finger_gripper.py:67-72)
+        jdof = lambda name: int(m.jnt_dofadr[m.names["jnt"].index(name)])
+        for i, jn in enumerate(meta["robot_joints"]):
+            sc.arm_dof[i] = jdof(jn)
+        for i, jn in enumerate(meta["gripper_joints"]):
+            sc.grip_dof[i] = jdof(jn)
+        # _setup_action (furniture.py:3332-3367): arm actions straight through; every gripper takes one action, fanned out over its
+        # two actuators as [g, -g] in actuator order (two_finger_gripper.py:67-72)
         assert m.nu == narm + ngrip
-        for u in range(narm):
-            sc.act_src[u], sc.act_sign[u] = u, 1.0
-        for k in range(ngrip):
-            sc.act_src[narm + k], sc.act_sign[narm + k] = narm, (1.0 if k == 0 else -1.0)
-        sc.grip_action_index, sc.connect_action_index = narm, narm + 1
-        assert list(m.actuator_jntid[:narm]) == list(range(narm))
+        seen = {}
+        for u in range(m.nu):
+            jn = m.names["jnt"][int(m.actuator_jntid[u])]
+            if jn in meta["robot_joints"]:
+                sc.act_src[u], sc.act_sign[u] = meta["robot_joints"].index(jn), 1.0
+            else:
+                g = meta["gripper_joints"].index(jn) // (ngrip // narms)  # which gripper: right first, then left
+                sc.act_src[u], sc.act_sign[u] = narm + g, (1.0 if seen.get(g, 0) == 0 else -1.0)
+                seen[g] = seen.get(g, 0) + 1
+        # FurnitureSawyerEnv._step discretises its gripper action (furniture_sawyer.py:73-74); FurnitureBaxterEnv does not
+        sc.grip_action_index = narm if narms == 1 else -1
+        sc.connect_action_index = narm + narms
         init = np.concatenate([meta["robot_init_qpos"], meta["gripper_init_qpos"]])
         for d, v in enumerate(init):
             sc.robot_init_qpos[d] = v
-        sc.eef_site = m.names["site"].index(meta["eef_site"])
-        hb = m.names["body"].index(meta["hand_body"])
-        hl = em.weld_link(hb)
         kin = mjcf.kinematics_np(m, m.qpos0)
-        lb = em.link_body[hl]
-        sc.hand_link = hl
-        sc.hand_quat[:] = list(mjcf.q_norm(mjcf.q_mul(mjcf.q_conj(kin["xquat"][lb]), kin["xquat"][hb])))
+        for arm, (sk, hk) in enumerate((("eef_site", "hand_body"), ("eef_site2", "hand_body2"))[:narms]):
+            sc.eef_site[arm] = m.names["site"].index(meta[sk])
+            hb = m.names["body"].index(meta[hk])
+            hl = em.weld_link(hb)
+            lb = em.link_body[hl]
+            sc.hand_link[arm] = hl
+            sc.hand_quat[arm][:] = list(mjcf.q_norm(mjcf.q_mul(mjcf.q_conj(kin["xquat"][lb]), kin["xquat"][hb])))
     else:
-        sc.eef_site, sc.hand_link = -1, -1
         sc.grip_action_index, sc.connect_action_index = 0, 0
     # connector sites (name contains "conn_site"), model site-id order
     names = {}

@@ -19,7 +19,7 @@ from . import mjcf
 from .engine import INFO_DIM, Engine, default_config
 
 INFO_KEYS = ("num_connected", "episode_success", "episode_unstable", "episode_length", "ncon", "solver_iters")
-ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer"}
+ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer", "IKEABaxter-v0": "Baxter", "FurnitureBaxterEnv": "Baxter"}
 # furniture_id -> name: the reference numbers the sorted objects/*.xml (furniture/env/models/__init__.py:11-19)
 FURNITURE_NAMES = (
     "bed_dalselv_0270 bench_bjoderna_0208 bench_bjursta_0210 block bookcase_agerum_0006 bookcase_besta_0165 bookcase_besta_0170 bookcase_besta_0172 "

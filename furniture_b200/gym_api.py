@@ -23,7 +23,7 @@ import numpy as np
 from . import mjcf
 from .engine import Engine, default_config
 
-AGENTS = {"FurnitureSawyerEnv": "Sawyer", "IKEASawyer-v0": "Sawyer", "Sawyer": "Sawyer"}
+AGENTS = {"FurnitureSawyerEnv": "Sawyer", "IKEASawyer-v0": "Sawyer", "Sawyer": "Sawyer", "FurnitureBaxterEnv": "Baxter", "IKEABaxter-v0": "Baxter", "Baxter": "Baxter"}
 
 
 class FurnitureGymB200:
@@ -138,7 +138,8 @@ def register_gym_envs():
             from gymnasium.envs.registration import register
         except Exception:
             return []
-    specs = {"IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050}}
+    specs = {"IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050},
+             "IKEABaxter-v0": {"id": "IKEABaxter-v0", "name": "FurnitureBaxterEnv", "furniture_id": 0, "background": "Interior", "port": 1050}}
     done = []
     for env_id, kwargs in specs.items():
         try:

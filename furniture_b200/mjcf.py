@@ -173,6 +173,8 @@ def _merge(dst_root, src_root, merge_body=True):
 
 SAWYER_INIT_QPOS = np.array([-0.28, -0.60, 0.00, 1.86, 0.00, 0.3, 1.57])  # robots/sawyer_robot.py:20
 SAWYER_BOTTOM_OFFSET = np.array([0.0, 0.0, -0.913])  # robots/sawyer_robot.py:17
+BAXTER_INIT_QPOS = np.array([0.814, -0.44, -0.07, 0.5, 0, 1.641, -1.57629266, -0.872, -0.39, 0.07, 0.5, 0, 1.641, -1.57629197])  # robots/baxter_robot.py:45-47
+BAXTER_BOTTOM_OFFSET = np.array([0.0, 0.0, -0.913])  # robots/baxter_robot.py:19
 GRIPPER_INIT_QPOS = np.array([0.020833, -0.020833])  # grippers/two_finger_gripper.py:22-23
 
 
@@ -247,11 +249,45 @@ def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None,
         )
         meta["eef_site"] = "grip_site"
         meta["hand_body"] = "right_hand"
+    elif agent == "Baxter":
+        # furniture.py:1925-1939 + baxter_robot.py + two_finger_gripper.py: right gripper on right_hand, left gripper on left_hand
+        robot = ET.parse(os.path.join(assets_root, "robots/baxter/robot_torque.xml" if use_torque else "robots/baxter/robot.xml")).getroot()
+        for a in _section(robot, "asset"):  # mesh files of the robot are relative to its own directory
+            if a.get("file") is not None:
+                a.set("file", os.path.join(assets_root, "robots", "baxter", a.get("file")))
+        for hand_name, gx in (("right_hand", "two_finger_gripper.xml"), ("left_hand", "left_two_finger_gripper.xml")):
+            gripper = ET.parse(os.path.join(assets_root, "grippers", gx)).getroot()
+            hand = robot.find("./worldbody//body[@name='%s']" % hand_name)
+            for body in list(_section(gripper, "worldbody")):
+                hand.append(body)
+            _merge(robot, gripper, merge_body=False)
+        base = robot.find("./worldbody/body[@name='base']")
+        pos = np.array([0, 0.65, -0.7]) - BAXTER_BOTTOM_OFFSET
+        base.set("pos", " ".join(str(x) for x in pos))
+        base.set("quat", "1 0 0 -1")
+        _merge(world, robot)
+        arm_j = ["s0", "s1", "e0", "e1", "w0", "w1", "w2"]
+        meta["robot_joints"] = ["right_" + a for a in arm_j] + ["left_" + a for a in arm_j]  # baxter_robot.py:38-42
+        meta["gripper_joints"] = ["r_gripper_l_finger_joint", "r_gripper_r_finger_joint", "l_gripper_l_finger_joint", "l_gripper_r_finger_joint"]
+        meta["robot_init_qpos"] = BAXTER_INIT_QPOS.copy()
+        meta["gripper_init_qpos"] = np.concatenate([GRIPPER_INIT_QPOS, GRIPPER_INIT_QPOS])
+        meta["l_finger_geoms"] = ["l_finger_g0", "l_finger_g1", "l_fingertip_g0"]          # arm "right"
+        meta["r_finger_geoms"] = ["r_finger_g0", "r_finger_g1", "r_fingertip_g0"]
+        meta["l_finger_geoms2"] = ["l_g_l_finger_g0", "l_g_l_finger_g1", "l_g_l_fingertip_g0"]  # arm "left"
+        meta["r_finger_geoms2"] = ["l_g_r_finger_g0", "l_g_r_finger_g1", "l_g_r_fingertip_g0"]
+        meta["robot_contact_geoms"] = (  # baxter_robot.py:71-86 + both grippers' contact_geoms
+            ["right_%s_collision" % n for n in ("upper_shoulder", "lower_shoulder", "upper_elbow", "lower_elbow", "upper_forearm", "lower_forearm", "wrist")]
+            + ["left_%s_collision" % n for n in ("upper_shoulder", "lower_shoulder", "upper_elbow", "lower_elbow", "upper_forearm", "lower_forearm")]
+            + ["r_finger_g0", "r_finger_g1", "l_finger_g0", "l_finger_g1", "r_fingertip_g0", "l_fingertip_g0", "right_gripper_base_collision"]
+            + ["l_g_r_finger_g0", "l_g_r_finger_g1", "l_g_l_finger_g0", "l_g_l_finger_g1", "l_g_r_fingertip_g0", "l_g_l_fingertip_g0", "left_gripper_base_collision"]
+        )
+        meta["eef_site"], meta["hand_body"] = "grip_site", "right_hand"
+        meta["eef_site2"], meta["hand_body2"] = "l_g_grip_site", "left_hand"
     elif agent == "None":
         meta.update(robot_joints=[], gripper_joints=[], robot_init_qpos=np.zeros(0), gripper_init_qpos=np.zeros(0),
                     l_finger_geoms=[], r_finger_geoms=[], robot_contact_geoms=[], eef_site=None, hand_body=None)
     else:
-        raise NotImplementedError("agent %s: only Sawyer (and None) are composed in this round" % agent)
+        raise NotImplementedError("agent %s: Sawyer, Baxter and None are composed" % agent)
 
     # furniture parts: furniture.py:1979-2001 + floor_task.py:55-72 + objects.py:186-206
     obj = ET.parse(os.path.join(assets_root, "objects", furniture + ".xml")).getroot()

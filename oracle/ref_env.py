@@ -1,5 +1,7 @@
 """CPU ORACLE of the env layer (TEST INFRASTRUCTURE, NOT PRODUCT CODE): a single-env restatement of
-FurnitureSawyerEnv (control_type="impedance") on top of the C physics oracle.
+FurnitureSawyerEnv and FurnitureBaxterEnv (control_type="impedance") on top of the C physics oracle.  Baxter: two arms
+(furniture.py:89-92), 17 actions (furniture_baxter.py:52-58), per-arm finger scans and observations (:98-155), no gripper
+discretisation, gravity compensation on the arm and gripper joints only (the head joint is left alone, furniture.py:3372-3377).
 
 Restates, with reference line cites:
   reset      FurnitureEnv._reset                      furniture/env/furniture.py:1406-1663
@@ -45,18 +47,22 @@ class OracleFurnitureEnv:
         self.part_qadr = [int(model.jnt_qposadr[model.names["jnt"].index(n)]) for n in self.parts]
         self.part_dadr = [int(model.jnt_dofadr[model.names["jnt"].index(n)]) for n in self.parts]
         self.narm, self.ngrip = len(meta["robot_joints"]), len(meta["gripper_joints"])
-        self.nr = self.narm + self.ngrip
-        self.dof = self.narm + 2
+        self.narms = 2 if meta.get("eef_site2") else 1
+        jq = lambda n: int(model.jnt_qposadr[model.names["jnt"].index(n)])  # robot joints are scalar: qpos index = dof index
+        self.arm_idx = [jq(n) for n in meta["robot_joints"]]
+        self.grip_idx = [jq(n) for n in meta["gripper_joints"]]
+        self.nr = int(sum(1 for j in range(model.njnt) if model.jnt_type[j] != 0))
+        self.dof = self.narm + self.narms + 1
         self.rng = np.random.RandomState(self.cfg.seed)
         g = model.names["geom"]
-        self.lf = [g.index(n) for n in meta["l_finger_geoms"]]
-        self.rf = [g.index(n) for n in meta["r_finger_geoms"]]
+        self.lf = [[g.index(n) for n in meta["l_finger_geoms"]]] + ([[g.index(n) for n in meta["l_finger_geoms2"]]] if self.narms == 2 else [])
+        self.rf = [[g.index(n) for n in meta["r_finger_geoms"]]] + ([[g.index(n) for n in meta["r_finger_geoms2"]]] if self.narms == 2 else [])
         self.floor = g.index("FLOOR")
         self.robot_geoms = [i for i, n in enumerate(g) if n in set(meta["robot_contact_geoms"])]
         self.part_col_geoms = [i for i, n in enumerate(g) if "collision" in n and model.names["body"][model.geom_bodyid[i]] in self.parts]
         self.conn_sites = [s for s, n in enumerate(model.names["site"]) if "conn_site" in n]
-        self.eef_site = model.names["site"].index(meta["eef_site"])
-        self.hand_body = model.names["body"].index(meta["hand_body"])
+        self.eef_site = [model.names["site"].index(meta[k]) for k in ("eef_site", "eef_site2")[: self.narms]]
+        self.hand_body = [model.names["body"].index(meta[k]) for k in ("hand_body", "hand_body2")[: self.narms]]
         self.nsub = int((1.0 / self.cfg.control_freq) / model.opt_timestep)
         self.group = list(range(self.npart))
         self.connected_sites = set()
@@ -95,13 +101,14 @@ class OracleFurnitureEnv:
         self.sim.forward()
         self.sim.step()
 
-    def _grav_comp(self):  # :3372-3377
-        self.sim.qfrc_applied[: self.nr] = self.sim.qfrc_bias[: self.nr]
+    def _grav_comp(self):  # :3372-3377: arm joints and gripper joints
+        idx = self.arm_idx + self.grip_idx
+        self.sim.qfrc_applied[idx] = self.sim.qfrc_bias[idx]
 
     def _init_robot(self):  # :1761-1779
         noise = self.rng.uniform(-self.cfg.agent_xyz_rand, self.cfg.agent_xyz_rand, self.narm)
-        self.sim.qpos[: self.narm] = self.m.meta["robot_init_qpos"] + noise
-        self.sim.qpos[self.narm : self.nr] = self.m.meta["gripper_init_qpos"]
+        self.sim.qpos[self.arm_idx] = self.m.meta["robot_init_qpos"] + noise
+        self.sim.qpos[self.grip_idx] = self.m.meta["gripper_init_qpos"]
 
     def _site_pose(self, s):  # _site_xpos_xquat :1044-1055
         b = self.m.site_bodyid[s]
@@ -179,7 +186,9 @@ class OracleFurnitureEnv:
                 b = self.m.geom_bodyid[gb]
                 if b in self.part_body:
                     p = self.part_body.index(b)
-                    bits[p] |= (1 if ga in self.lf else 0) | (2 if ga in self.rf else 0) | (4 if ga == self.floor else 0)
+                    bits[p] |= (1 if ga in self.lf[0] else 0) | (2 if ga in self.rf[0] else 0) | (4 if ga == self.floor else 0)
+                    if self.narms == 2:
+                        bits[p] |= (8 if ga in self.lf[1] else 0) | (16 if ga in self.rf[1] else 0)
         return bits
 
     def _move_group(self, obj, translation, target_quat, gravity=0):  # :1163-1176
@@ -272,21 +281,33 @@ class OracleFurnitureEnv:
         for p in range(self.npart):
             b = self.part_body[p]
             ob += list(sim.xpos[3 * b : 3 * b + 3]) + list(sim.xquat[4 * b : 4 * b + 4])
-        ob += list(sim.qpos[: self.narm]) + list(sim.qvel[: self.narm]) + list(sim.qpos[self.narm : self.nr])
-        s = self.eef_site
-        ob += list(sim.site_xpos[3 * s : 3 * s + 3])
-        hq = sim.xquat[4 * self.hand_body : 4 * self.hand_body + 4]
-        ob += [hq[1], hq[2], hq[3], hq[0]]
-        v = sim.site_velocity(s)
-        ob += list(v[:3]) + list(v[3:])
+        na, ng = self.narm // self.narms, self.ngrip // self.narms
+        for arm in range(self.narms):  # furniture_sawyer.py:103-155, furniture_baxter.py:98-155
+            ai, gi = self.arm_idx[arm * na : (arm + 1) * na], self.grip_idx[arm * ng : (arm + 1) * ng]
+            ob += list(sim.qpos[ai]) + list(sim.qvel[ai]) + list(sim.qpos[gi])
+            s = self.eef_site[arm]
+            ob += list(sim.site_xpos[3 * s : 3 * s + 3])
+            hq = sim.xquat[4 * self.hand_body[arm] : 4 * self.hand_body[arm] + 4]
+            ob += [hq[1], hq[2], hq[3], hq[0]]
+            v = sim.site_velocity(s)
+            ob += list(v[:3]) + list(v[3:])
         return np.array(ob)
 
     def set_controls(self, action):
         a = np.asarray(action, dtype=np.float64).copy()
-        if self.cfg.discrete_grip:
+        if self.cfg.discrete_grip and self.narms == 1:  # FurnitureSawyerEnv._step only
             a[-2] = -1 if a[-2] < 0 else 1
         act = np.clip(a[:-1], -1, 1) if self.cfg.rescale_actions else a[:-1]
-        full = np.concatenate([act[: self.narm], [act[self.narm], -act[self.narm]]])
+        full = np.zeros(self.m.nu)  # per actuator: arm joints straight through, each gripper's action as [g, -g] over its two actuators
+        seen = {}
+        for u in range(self.m.nu):
+            jn = self.m.names["jnt"][int(self.m.actuator_jntid[u])]
+            if jn in self.m.meta["robot_joints"]:
+                full[u] = act[self.m.meta["robot_joints"].index(jn)]
+            else:
+                gidx = self.m.meta["gripper_joints"].index(jn) // (self.ngrip // self.narms)
+                full[u] = act[self.narm + gidx] * (1 if seen.get(gidx, 0) == 0 else -1)
+                seen[gidx] = seen.get(gidx, 0) + 1
         cr = self.m.actuator_ctrlrange
         if self.cfg.rescale_actions:
             full = 0.5 * (cr[:, 1] + cr[:, 0]) + 0.5 * (cr[:, 1] - cr[:, 0]) * full
@@ -304,11 +325,12 @@ class OracleFurnitureEnv:
             self.sim.L.om_clear_warning(self.sim.d)
             self.reset()
         else:
-            if connect > 0:
+            if connect > 0:  # :1290-1322: per arm the first part both fingers touch; return at the first connection
                 bits = self.touch_bits()
-                for p in range(self.npart):
-                    if bits[p] & 3 == 3:
-                        self._try_connect(p)
+                for arm in range(self.narms):
+                    both = 3 if arm == 0 else 24
+                    hit = [p for p in range(self.npart) if bits[p] & both == both]
+                    if hit and self._try_connect(hit[0]):
                         break
             if self.connected_body1 is not None:
                 b1 = self.connected_body1
@@ -320,12 +342,14 @@ class OracleFurnitureEnv:
         touch_r = pick_r = 0.0
         if not fail:
             bits = self.touch_bits()
-            for p in range(self.npart):
-                if bits[p] & 3 == 3:
-                    if not self.touched[p]:
-                        self.touched[p] = True; touch_r += self.cfg.touch_reward
-                    if not (bits[p] & 4) and not self.picked[p]:
-                        self.picked[p] = True; pick_r += self.cfg.pick_reward
+            for arm in range(self.narms):
+                both = 3 if arm == 0 else 24
+                for p in range(self.npart):
+                    if bits[p] & both == both:
+                        if not self.touched[p]:
+                            self.touched[p] = True; touch_r += self.cfg.touch_reward
+                        if not (bits[p] & 4) and not self.picked[p]:
+                            self.picked[p] = True; pick_r += self.cfg.pick_reward
         success_r = self.cfg.success_reward * (self.num_connected - self.prev_num_connected)
         self.prev_num_connected = self.num_connected
         reward = success_r + touch_r + pick_r - self.cfg.ctrl_penalty_coef * float(np.square(raw).sum())
