@@ -5,6 +5,7 @@
 // MuJoCo 2.0 calls for cylinder pairs) for sphere/cylinder/box vs cylinder; box-box by SAT + reference-face clipping.
 // Contact convention: normal points from geom1 to geom2, dist < 0 is penetration, pos lies mid-way between surfaces.
 #pragma once
+#include "fe_model.h"
 #include "fe_warp.h"
 
 struct FeCon {
@@ -71,6 +72,36 @@ FE_HD int fe_plane_cylinder(const float* pp, const float* pR, const float* c, co
     v3sub(t, p, pp);
     dist = v3dot(t, n);
     if (dist < margin) { out[cnt].dist = dist; v3madd(out[cnt].pos, p, n, -0.5f * dist); v3cpy(out[cnt].n, n); ++cnt; }
+  }
+  return cnt;
+}
+
+// plane - mesh: hull vertices below the margin, the four deepest (ties: lowest index first)
+FE_HD int fe_plane_mesh(const float* pp, const float* pR, const float* c, const float* R, const float* verts, int nvert, float margin, FeCon* out) {
+  float n[3];
+  fe_col(n, pR, 2);
+  int i0 = -1, i1 = -1, i2 = -1, i3 = -1, cnt = 0; // kept in scalars: a sorted insertion without indexed local arrays
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  for (int i = 0; i < nvert; ++i) {
+    float w[3], t[3];
+    m3mulv(w, R, verts + 3 * i);
+    v3add(w, w, c);
+    v3sub(t, w, pp);
+    const float dist = v3dot(t, n);
+    if (dist >= margin) continue;
+    if (cnt < 1 || dist < d0) { d3 = d2; i3 = i2; d2 = d1; i2 = i1; d1 = d0; i1 = i0; d0 = dist; i0 = i; }
+    else if (cnt < 2 || dist < d1) { d3 = d2; i3 = i2; d2 = d1; i2 = i1; d1 = dist; i1 = i; }
+    else if (cnt < 3 || dist < d2) { d3 = d2; i3 = i2; d2 = dist; i2 = i; }
+    else if (cnt < 4 || dist < d3) { d3 = dist; i3 = i; }
+    if (cnt < 4) ++cnt;
+  }
+  for (int q = 0; q < cnt; ++q) {
+    const int iv = q == 0 ? i0 : (q == 1 ? i1 : (q == 2 ? i2 : i3));
+    const float dq = q == 0 ? d0 : (q == 1 ? d1 : (q == 2 ? d2 : d3));
+    float w[3];
+    m3mulv(w, R, verts + 3 * iv);
+    v3add(w, w, c);
+    out[q].dist = dq; v3madd(out[q].pos, w, n, -0.5f * dq); v3cpy(out[q].n, n);
   }
   return cnt;
 }
@@ -258,6 +289,8 @@ struct FeCvx {
   int type;
   const float *pos, *mat, *size;
   float inflate; // half the contact margin: the support function pushes the surface out by it (mjccd_support), fe_mpr takes it back
+  const float* verts; // mesh collider: convex-hull vertices in the geom frame
+  int nvert;
 };
 FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
   float l[3], p[3];
@@ -270,6 +303,11 @@ FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
     p[0] = l[0] >= 0.f ? g.size[0] : -g.size[0];
     p[1] = l[1] >= 0.f ? g.size[1] : -g.size[1];
     p[2] = l[2] >= 0.f ? g.size[2] : -g.size[2];
+  } else if (g.type == 7) { // mesh: hull vertex furthest along the direction (first one on ties)
+    int best = 0;
+    float bd = -1e30f;
+    for (int i = 0; i < g.nvert; ++i) { const float dd = l[0] * g.verts[3 * i] + l[1] * g.verts[3 * i + 1] + l[2] * g.verts[3 * i + 2]; if (dd > bd) { bd = dd; best = i; } }
+    p[0] = g.verts[3 * best]; p[1] = g.verts[3 * best + 1]; p[2] = g.verts[3 * best + 2];
   } else if (g.type == 3) { // capsule: a sphere swept along the local z segment
     float n = v3norm(l);
     float s = n > 1e-20f ? g.size[0] / n : 0.f;
@@ -423,19 +461,23 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
 
 // dispatch on the (ordered) type pair; geometry in world frame; contacts closer than `margin` are reported (mj_collision:
 // dist < margin, margin = max of the two geoms').  Returns contact count (<= 8).
-FE_HDN int fe_narrowphase(int t1, const float* p1, const float* R1, const float* s1, int t2, const float* p2, const float* R2, const float* s2, float margin, FeCon* out) {
+FE_HDN int fe_narrowphase(const fe_model* m, int g1, int g2, const float* p1, const float* R1, const float* p2, const float* R2, float margin, FeCon* out) {
+  const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  const float *s1 = m->geom_size[g1], *s2 = m->geom_size[g2];
   if (t1 == 0) {
     if (t2 == 2) return fe_plane_sphere(p1, R1, p2, s2[0], margin, out);
     if (t2 == 3) return fe_plane_capsule(p1, R1, p2, R2, s2[0], s2[1], margin, out);
     if (t2 == 5) return fe_plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], margin, out);
     if (t2 == 6) return fe_plane_box(p1, R1, p2, R2, s2, margin, out);
+    if (t2 == 7) return fe_plane_mesh(p1, R1, p2, R2, &m->mesh_vert[m->geom_meshadr[g2]][0], m->geom_meshnum[g2], margin, out);
     return 0;
   }
   if (t1 == 2 && t2 == 2) return fe_sphere_sphere(p1, s1[0], p2, s2[0], margin, out);
   if (t1 == 2 && t2 == 6) return fe_sphere_box(p1, s1[0], p2, R2, s2, margin, out);
   if (t1 == 6 && t2 == 6) return fe_box_box(p1, R1, s1, p2, R2, s2, margin, out);
-  // every other pair (a cylinder or a capsule on one side) goes through MPR; MuJoCo has analytic routines for the capsule
-  // pairs (mjc_CapsuleBox ...), which can return two points where MPR returns the deepest one
-  FeCvx a = {t1, p1, R1, s1, 0.5f * margin}, b = {t2, p2, R2, s2, 0.5f * margin};
+  // every other pair (a cylinder, a capsule or a mesh hull on one side) goes through MPR; MuJoCo has analytic routines for the
+  // capsule pairs (mjc_CapsuleBox ...), which can return two points where MPR returns the deepest one
+  FeCvx a = {t1, p1, R1, s1, 0.5f * margin, t1 == 7 ? &m->mesh_vert[m->geom_meshadr[g1]][0] : nullptr, t1 == 7 ? m->geom_meshnum[g1] : 0};
+  FeCvx b = {t2, p2, R2, s2, 0.5f * margin, t2 == 7 ? &m->mesh_vert[m->geom_meshadr[g2]][0] : nullptr, t2 == 7 ? m->geom_meshnum[g2] : 0};
   return fe_mpr(a, b, out);
 }

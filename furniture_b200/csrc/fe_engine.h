@@ -761,8 +761,7 @@ FE_FN void fe_collide(FeWarp* w) {
       if (ci < ncand) {
         const int k = w->cand()[ci];
         g1 = m->pair_g1[k]; g2 = m->pair_g2[k];
-        n = fe_narrowphase(m->geom_type[g1], w->gpos() + 3 * g1, w->gmat() + 9 * g1, m->geom_size[g1], m->geom_type[g2], w->gpos() + 3 * g2, w->gmat() + 9 * g2,
-                           m->geom_size[g2], fmaxf(m->geom_margin[g1], m->geom_margin[g2]), res);
+        n = fe_narrowphase(m, g1, g2, w->gpos() + 3 * g1, w->gmat() + 9 * g1, w->gpos() + 3 * g2, w->gmat() + 9 * g2, fmaxf(m->geom_margin[g1], m->geom_margin[g2]), res);
       }
       const int off = FE_SCAN(run, n);
       for (int i = 0; i < n; ++i) {

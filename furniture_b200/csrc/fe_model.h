@@ -7,7 +7,7 @@
 #pragma once
 #include <stdint.h>
 
-#define FE_MODEL_MAGIC 0x46453032 /* "FE02" */
+#define FE_MODEL_MAGIC 0x46453033 /* "FE03" */
 #define FE_MAXLINK 32
 #define FE_MAXRDOF 20
 #define FE_MAXPART 16
@@ -17,9 +17,10 @@
 #define FE_MAXSITE 256
 #define FE_MAXEQ 40
 #define FE_MAXU 20
+#define FE_MAXMESHVERT 512 /* convex-hull vertices of all mesh colliders of a scene */
 
 enum { FE_JNT_FREE = 0, FE_JNT_SLIDE = 2, FE_JNT_HINGE = 3 };
-enum { FE_GEOM_PLANE = 0, FE_GEOM_SPHERE = 2, FE_GEOM_CAPSULE = 3, FE_GEOM_CYLINDER = 5, FE_GEOM_BOX = 6 };
+enum { FE_GEOM_PLANE = 0, FE_GEOM_SPHERE = 2, FE_GEOM_CAPSULE = 3, FE_GEOM_CYLINDER = 5, FE_GEOM_BOX = 6, FE_GEOM_MESH = 7 };
 enum { FE_ACT_MOTOR = 0, FE_ACT_POSITION = 1, FE_ACT_VELOCITY = 2 };
 /* geom_tag bits */
 enum { FE_TAG_FLOOR = 1, FE_TAG_LFINGER = 2, FE_TAG_RFINGER = 4, FE_TAG_ROBOT = 8, FE_TAG_LFINGER2 = 16, FE_TAG_RFINGER2 = 32 /* fingers of a second arm */, FE_TAG_PART_SHIFT = 8 };
@@ -49,6 +50,8 @@ typedef struct fe_model {
   float geom_pos[FE_MAXGEOM][3], geom_mat[FE_MAXGEOM][9], geom_size[FE_MAXGEOM][3], geom_rbound[FE_MAXGEOM];
   float geom_friction[FE_MAXGEOM], geom_solref[FE_MAXGEOM][2], geom_solimp[FE_MAXGEOM][3], geom_invweight[FE_MAXGEOM];
   float geom_margin[FE_MAXGEOM]; /* contacts are generated below max(margin1, margin2); the constraint acts on dist - margin (gap = 0) */
+  int32_t geom_meshadr[FE_MAXGEOM], geom_meshnum[FE_MAXGEOM]; /* mesh colliders: their convex-hull vertices in mesh_vert (geom frame) */
+  float mesh_vert[FE_MAXMESHVERT][3];
   int32_t pair_g1[FE_MAXPAIR], pair_g2[FE_MAXPAIR]; /* type(g1) <= type(g2) */
   /* sites the env layer reads */
   int32_t site_link[FE_MAXSITE];

@@ -18,8 +18,8 @@ import numpy as np
 
 from . import mjcf
 
-MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU = 32, 20, 16, 116, 96, 2048, 256, 40, 20
-MAGIC = 0x46453032
+MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU, MAXMESHVERT = 32, 20, 16, 116, 96, 2048, 256, 40, 20, 512
+MAGIC = 0x46453033
 TAG_FLOOR, TAG_LFINGER, TAG_RFINGER, TAG_ROBOT, TAG_LFINGER2, TAG_RFINGER2, TAG_PART_SHIFT = 1, 2, 4, 8, 16, 32, 8
 
 i32, f32 = C.c_int32, C.c_float
@@ -44,6 +44,7 @@ class FeModel(C.Structure):
         ("geom_pos", (f32 * 3) * MAXGEOM), ("geom_mat", (f32 * 9) * MAXGEOM), ("geom_size", (f32 * 3) * MAXGEOM), ("geom_rbound", f32 * MAXGEOM),
         ("geom_friction", f32 * MAXGEOM), ("geom_solref", (f32 * 2) * MAXGEOM), ("geom_solimp", (f32 * 3) * MAXGEOM), ("geom_invweight", f32 * MAXGEOM),
         ("geom_margin", f32 * MAXGEOM),
+        ("geom_meshadr", i32 * MAXGEOM), ("geom_meshnum", i32 * MAXGEOM), ("mesh_vert", (f32 * 3) * MAXMESHVERT),
         ("pair_g1", i32 * MAXPAIR), ("pair_g2", i32 * MAXPAIR),
         ("site_link", i32 * MAXSITE), ("site_pos", (f32 * 3) * MAXSITE), ("site_quat", (f32 * 4) * MAXSITE),
         ("eq_link1", i32 * MAXEQ), ("eq_link2", i32 * MAXEQ), ("eq_active0", i32 * MAXEQ),
@@ -170,7 +171,8 @@ class EngineModel:
             l = weld_link(b)
             name = m.names["geom"][g]
             fm.geom_type[i] = int(m.geom_type[g])
-            assert fm.geom_type[i] in (0, 2, 3, 5, 6), "geom type not supported by the engine: %s" % name
+            assert fm.geom_type[i] in (0, 2, 3, 5, 6, 7), "geom type not supported by the engine: %s" % name
+            fm.geom_meshadr[i], fm.geom_meshnum[i] = int(m.geom_meshadr[g]), int(m.geom_meshnum[g])
             fm.geom_link[i] = l
             fm.geom_contype0[i] = int(m.geom_contype[g])
             fm.geom_conaffinity0[i] = int(m.geom_conaffinity[g])
@@ -214,6 +216,9 @@ class EngineModel:
             fm.geom_invweight[i] = m.body_invweight0[b][0]
             assert m.geom_condim[g] == 3 and m.geom_gap[g] == 0, "engine assumes condim=3 and gap=0 (every reported contact is active)"
             fm.geom_margin[i] = m.geom_margin[g]
+        assert len(m.mesh_vert) <= MAXMESHVERT, "too many mesh-collider hull vertices: %d" % len(m.mesh_vert)
+        for k, v in enumerate(m.mesh_vert):
+            fm.mesh_vert[k][:] = list(v)
         pairs = []
         for g1, g2 in m.collision_pairs:
             if int(g1) in self.geom_map and int(g2) in self.geom_map:

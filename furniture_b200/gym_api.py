@@ -139,7 +139,7 @@ def register_gym_envs():
         except Exception:
             return []
     specs = {"IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050},
-             "IKEABaxter-v0": {"id": "IKEABaxter-v0", "name": "FurnitureBaxterEnv", "furniture_id": 0, "background": "Interior", "port": 1050}}
+             "IKEABaxter-v0": {"id": "IKEABaxter-v0", "name": "FurnitureBaxterEnv", "furniture_id": 1, "background": "Interior", "port": 1050}}
     done = []
     for env_id, kwargs in specs.items():
         try:

@@ -109,7 +109,7 @@ def euler_xyz_to_q(e):
 # constants shared with the C oracle and the CUDA engine
 # --------------------------------------------------------------------------------------
 JNT_FREE, JNT_SLIDE, JNT_HINGE = 0, 2, 3  # numeric values follow mjtJoint (ball=1 unused)
-GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX = 0, 2, 3, 5, 6  # mjtGeom
+GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH = 0, 2, 3, 5, 6, 7  # mjtGeom
 GEOM_TYPES = {"plane": GEOM_PLANE, "sphere": GEOM_SPHERE, "capsule": GEOM_CAPSULE, "cylinder": GEOM_CYLINDER, "box": GEOM_BOX}
 ACT_MOTOR, ACT_POSITION, ACT_VELOCITY = 0, 1, 2
 
@@ -503,7 +503,9 @@ def compile_mjcf(xml_string, meta=None):
 
     B = dict(parent=[], pos=[], quat=[], ipos=[], iquat=[], mass=[], inertia=[], name=[], explicit=[])
     J = dict(type=[], body=[], pos=[], axis=[], limited=[], range=[], damping=[], name=[], solref=[], solimp=[], armature=[])
-    G = dict(type=[], body=[], pos=[], quat=[], size=[], contype=[], conaffinity=[], condim=[], friction=[], solref=[], solimp=[], margin=[], gap=[], name=[], density=[])
+    G = dict(type=[], body=[], pos=[], quat=[], size=[], contype=[], conaffinity=[], condim=[], friction=[], solref=[], solimp=[], margin=[], gap=[], name=[], density=[],
+             meshadr=[], meshnum=[])
+    mesh_verts = []  # convex-hull vertices of the mesh colliders, geom frame (one block per mesh geom)
     S = dict(body=[], pos=[], quat=[], name=[])
     meshes = {}
     asset = root.find("asset")
@@ -572,19 +574,47 @@ def compile_mjcf(xml_string, meta=None):
                 conaff = int(a.get("conaffinity", 1))
                 density = float(a.get("density", 1000))
                 if tname == "mesh":
-                    # visual meshes carry contype=conaffinity=0; with density 0 they are ignored (A.1), with a density
-                    # they still add their mass and inertia to the body (4 furniture models).  Mesh *colliders*
-                    # (3 furniture models: convex hull + MPR in MuJoCo) are not implemented.
-                    if contype != 0 or conaff != 0:
-                        raise NotImplementedError("mesh collider geom '%s'" % a.get("name"))
-                    if density != 0 and inert is None:
-                        mesh = meshes.get(a.get("mesh"))
-                        if mesh is None:
-                            raise NotImplementedError("mesh asset '%s' of geom '%s' not found" % (a.get("mesh"), a.get("name")))
+                    # visual meshes carry contype=conaffinity=0; with density 0 they are ignored (A.1), with a density they still
+                    # add their mass and inertia to the body (4 furniture models).  Mesh *colliders* (3 furniture models) collide
+                    # through the convex hull of their vertices, as in MuJoCo (mesh geoms are convexified for collision).
+                    mesh = meshes.get(a.get("mesh"))
+                    collider = contype != 0 or conaff != 0
+                    tri = None
+                    if mesh is not None and ((density != 0 and inert is None) or collider):
                         tri = load_stl(mesh["file"]) * mesh["scale"]
+                    elif (density != 0 and inert is None) or collider:
+                        raise NotImplementedError("mesh asset '%s' of geom '%s' not found" % (a.get("mesh"), a.get("name")))
+                    if density != 0 and inert is None:
                         m_, c_, I_ = mesh_mass_properties(tri, density)
                         Rg = q_to_mat(_orient(a))
                         mesh_inertia.setdefault(bid, []).append((m_, _floats(a.get("pos"), 3, [0, 0, 0]) + Rg @ c_, Rg @ I_ @ Rg.T))
+                    if not collider:
+                        continue
+                    try:
+                        from scipy.spatial import ConvexHull
+                    except Exception as e:  # pragma: no cover
+                        raise NotImplementedError("mesh collider geom '%s' needs scipy for its convex hull (%s)" % (a.get("name"), e))
+                    verts = np.unique(tri.reshape(-1, 3), axis=0)
+                    hv = verts[np.sort(ConvexHull(verts).vertices)]
+                    lo, hi = hv.min(0), hv.max(0)
+                    G["type"].append(GEOM_MESH)
+                    G["body"].append(bid)
+                    G["name"].append(a.get("name", ""))
+                    G["pos"].append(_floats(a.get("pos"), 3, [0, 0, 0]))
+                    G["quat"].append(_orient(a))
+                    G["size"].append(0.5 * (hi - lo))  # half extents of the hull's bounding box (informative; collision uses the vertices)
+                    G["contype"].append(contype)
+                    G["conaffinity"].append(conaff)
+                    G["condim"].append(int(a.get("condim", 3)))
+                    G["friction"].append(_floats(a.get("friction"), 3, [1, 0.005, 0.0001]))
+                    G["solref"].append(_floats(a.get("solref"), 2, [0.02, 1]))
+                    G["solimp"].append(_floats(a.get("solimp"), 5, [0.9, 0.95, 0.001, 0.5, 2]))
+                    G["margin"].append(float(a.get("margin", 0)))
+                    G["gap"].append(float(a.get("gap", 0)))
+                    G["density"].append(0.0)  # mass already taken from the triangle mesh above
+                    G["meshadr"].append(sum(len(v) for v in mesh_verts))
+                    G["meshnum"].append(len(hv))
+                    mesh_verts.append(hv)
                     continue
                 if tname not in GEOM_TYPES:
                     raise NotImplementedError("geom type " + tname)
@@ -604,6 +634,8 @@ def compile_mjcf(xml_string, meta=None):
                 G["margin"].append(float(a.get("margin", 0)))
                 G["gap"].append(float(a.get("gap", 0)))
                 G["density"].append(density)
+                G["meshadr"].append(-1)
+                G["meshnum"].append(0)
             elif child.tag == "site":
                 a = dfl.get("site", child, cc)
                 S["body"].append(bid)
@@ -639,7 +671,7 @@ def compile_mjcf(xml_string, meta=None):
     for b in range(nbody):
         if B["explicit"][b]:
             continue
-        gs = [i for i in range(ngeom) if G["body"][i] == b and G["density"][i] > 0 and G["type"][i] != GEOM_PLANE]
+        gs = [i for i in range(ngeom) if G["body"][i] == b and G["density"][i] > 0 and G["type"][i] not in (GEOM_PLANE, GEOM_MESH)]
         if not gs and b not in mesh_inertia:
             continue
         ms, cs, Is = [], [], []
@@ -832,10 +864,17 @@ def compile_mjcf(xml_string, meta=None):
     a["geom_margin"] = np.array(G["margin"], dtype=np.float64)
     a["geom_gap"] = np.array(G["gap"], dtype=np.float64)
     rb = np.zeros(ngeom)
+    mesh_verts_all = np.concatenate(mesh_verts, 0) if mesh_verts else np.zeros((0, 3))
     for i in range(ngeom):
         t, s = G["type"][i], G["size"][i]
-        rb[i] = {GEOM_PLANE: 0.0, GEOM_SPHERE: s[0], GEOM_CAPSULE: s[0] + s[1], GEOM_CYLINDER: math.hypot(s[0], s[1]), GEOM_BOX: float(np.linalg.norm(s))}[t]
+        if t == GEOM_MESH:
+            rb[i] = float(np.linalg.norm(mesh_verts_all[G["meshadr"][i] : G["meshadr"][i] + G["meshnum"][i]], axis=1).max())
+        else:
+            rb[i] = {GEOM_PLANE: 0.0, GEOM_SPHERE: s[0], GEOM_CAPSULE: s[0] + s[1], GEOM_CYLINDER: math.hypot(s[0], s[1]), GEOM_BOX: float(np.linalg.norm(s))}[t]
     a["geom_rbound"] = rb
+    a["geom_meshadr"] = np.array(G["meshadr"], dtype=np.int32)
+    a["geom_meshnum"] = np.array(G["meshnum"], dtype=np.int32)
+    a["mesh_vert"] = mesh_verts_all
     a["site_bodyid"] = np.array(S["body"], dtype=np.int32)
     a["site_pos"] = np.array(S["pos"]).reshape(nsite, 3)
     a["site_quat"] = np.array(S["quat"]).reshape(nsite, 4)

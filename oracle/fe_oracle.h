@@ -34,7 +34,7 @@ extern "C" {
   X(jnt_type) X(jnt_bodyid) X(jnt_qposadr) X(jnt_dofadr) X(jnt_limited) X(dof_bodyid) X(dof_jntid) X(dof_parentid)  \
   X(geom_type) X(geom_bodyid) X(geom_contype) X(geom_conaffinity) X(geom_condim) X(site_bodyid) X(actuator_type)    \
   X(actuator_jntid) X(actuator_ctrllimited) X(actuator_forcelimited) X(eq_obj1id) X(eq_obj2id) X(eq_active)         \
-  X(collision_pairs)
+  X(collision_pairs) X(geom_meshadr) X(geom_meshnum)
 
 #define OM_DBL_ARRAYS(X)                                                                                            \
   X(opt_gravity) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_inertia)                   \
@@ -42,7 +42,7 @@ extern "C" {
   X(dof_armature) X(dof_invweight0) X(qpos0) X(geom_size) X(geom_pos) X(geom_quat) X(geom_friction) X(geom_solref)  \
   X(geom_solimp) X(geom_margin) X(geom_gap) X(geom_rbound) X(site_pos) X(site_quat) X(actuator_gear)                \
   X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange) X(actuator_forcerange) X(eq_solref) X(eq_solimp)    \
-  X(eq_data)
+  X(eq_data) X(mesh_vert)
 
 typedef struct om_model {
 #define X(n) int n;

@@ -17,7 +17,7 @@
 #include "fe_oracle.h"
 
 #define MINVAL 1e-15
-enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_CYLINDER = 5, G_BOX = 6 };
+enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_CYLINDER = 5, G_BOX = 6, G_MESH = 7 };
 
 static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 static inline void cross3(double* r, const double* a, const double* b) {
@@ -113,6 +113,34 @@ static int plane_cylinder(const double* pp, const double* pR, const double* c, c
     sub3(t, p, pp);
     dist = dot3(t, n);
     if (dist < margin) { addscl3(pos, p, n, -0.5 * dist); set_contact(out + cnt++, dist, pos, n); }
+  }
+  return cnt;
+}
+/* plane - mesh: hull vertices below the margin, the four deepest (ties: lowest index first) */
+static int plane_mesh(const double* pp, const double* pR, const double* c, const double* R, const double* verts, int nvert, double margin, om_contact* out) {
+  double n[3];
+  col3(n, pR, 2);
+  int idx[4], cnt = 0;
+  double dep[4];
+  for (int i = 0; i < nvert; i++) {
+    double w[3], t[3];
+    for (int k = 0; k < 3; k++) w[k] = c[k] + R[3 * k] * verts[3 * i] + R[3 * k + 1] * verts[3 * i + 1] + R[3 * k + 2] * verts[3 * i + 2];
+    sub3(t, w, pp);
+    double dist = dot3(t, n);
+    if (dist >= margin) continue;
+    int pos = cnt < 4 ? cnt : 4;
+    while (pos > 0 && dist < dep[pos - 1]) --pos; /* insertion point in the ascending list of depths (strict: ties keep index order) */
+    if (pos >= 4) continue;
+    for (int j = (cnt < 4 ? cnt : 3); j > pos; --j) { dep[j] = dep[j - 1]; idx[j] = idx[j - 1]; }
+    dep[pos] = dist; idx[pos] = i;
+    if (cnt < 4) cnt++;
+  }
+  for (int q = 0; q < cnt; q++) {
+    double w[3], pos[3];
+    const double* v = verts + 3 * idx[q];
+    for (int k = 0; k < 3; k++) w[k] = c[k] + R[3 * k] * v[0] + R[3 * k + 1] * v[1] + R[3 * k + 2] * v[2];
+    addscl3(pos, w, n, -0.5 * dep[q]);
+    set_contact(out + q, dep[q], pos, n);
   }
   return cnt;
 }
@@ -288,7 +316,8 @@ static int box_box(const double* cA, const double* RA, const double* a, const do
 }
 
 /* ---------------------------------------------------------------- MPR for convex pairs (sphere/cylinder/box) */
-typedef struct { int type; const double *pos, *mat, *size; double inflate; /* half the contact margin, added along the query direction (mjccd_support) */ } cvx;
+typedef struct { int type; const double *pos, *mat, *size; double inflate; /* half the contact margin, added along the query direction (mjccd_support) */
+                 const double* verts; int nvert; /* convex-hull vertices of a mesh geom (geom frame) */ } cvx;
 static void support(const cvx* g, const double* dir, double* out) {
   double l[3] = {g->mat[0] * dir[0] + g->mat[3] * dir[1] + g->mat[6] * dir[2], g->mat[1] * dir[0] + g->mat[4] * dir[1] + g->mat[7] * dir[2],
                  g->mat[2] * dir[0] + g->mat[5] * dir[1] + g->mat[8] * dir[2]};
@@ -298,6 +327,11 @@ static void support(const cvx* g, const double* dir, double* out) {
     for (int k = 0; k < 3; k++) p[k] = n > MINVAL ? l[k] / n * g->size[0] : 0;
   } else if (g->type == G_BOX) {
     for (int k = 0; k < 3; k++) p[k] = l[k] >= 0 ? g->size[k] : -g->size[k];
+  } else if (g->type == G_MESH) { /* hull vertex furthest along the direction (first one on ties) */
+    int best = 0;
+    double bd = -1e300;
+    for (int i = 0; i < g->nvert; i++) { double dd = dot3(l, g->verts + 3 * i); if (dd > bd) { bd = dd; best = i; } }
+    for (int k = 0; k < 3; k++) p[k] = g->verts[3 * best + k];
   } else if (g->type == G_CAPSULE) { /* sphere swept along the local z segment */
     double n = norm3(l);
     for (int k = 0; k < 3; k++) p[k] = n > MINVAL ? l[k] / n * g->size[0] : 0;
@@ -467,6 +501,7 @@ int om_collide_pair(const om_model* m, const om_data* d, int g1, int g2, om_cont
     else if (t2 == G_CAPSULE) n = plane_capsule(p1, R1, p2, R2, s2[0], s2[1], margin, out);
     else if (t2 == G_CYLINDER) n = plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], margin, out);
     else if (t2 == G_BOX) n = plane_box(p1, R1, p2, R2, s2, margin, out);
+    else if (t2 == G_MESH) n = plane_mesh(p1, R1, p2, R2, m->mesh_vert + 3 * m->geom_meshadr[g2], m->geom_meshnum[g2], margin, out);
     else return 0;
   } else {
     double t[3];
@@ -477,7 +512,8 @@ int om_collide_pair(const om_model* m, const om_data* d, int g1, int g2, om_cont
     else if (t1 == G_SPHERE && t2 == G_BOX) n = sphere_box(p1, s1[0], p2, R2, s2, margin, out);
     else if (t1 == G_BOX && t2 == G_BOX) n = box_box(p1, R1, s1, p2, R2, s2, margin, out);
     else { /* a cylinder or a capsule on one side: MPR on shapes inflated by half the margin each */
-      cvx a = {t1, p1, R1, s1, 0.5 * margin}, b = {t2, p2, R2, s2, 0.5 * margin};
+      cvx a = {t1, p1, R1, s1, 0.5 * margin, t1 == G_MESH ? m->mesh_vert + 3 * m->geom_meshadr[g1] : NULL, t1 == G_MESH ? m->geom_meshnum[g1] : 0};
+      cvx b = {t2, p2, R2, s2, 0.5 * margin, t2 == G_MESH ? m->mesh_vert + 3 * m->geom_meshadr[g2] : NULL, t2 == G_MESH ? m->geom_meshnum[g2] : 0};
       n = convex_pair(&a, &b, out);
     }
   }

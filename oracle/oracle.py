@@ -21,13 +21,13 @@ INT_ARRAYS = (
     "body_parentid body_weldid body_rootid body_jntadr body_jntnum body_dofadr body_dofnum jnt_type jnt_bodyid "
     "jnt_qposadr jnt_dofadr jnt_limited dof_bodyid dof_jntid dof_parentid geom_type geom_bodyid geom_contype "
     "geom_conaffinity geom_condim site_bodyid actuator_type actuator_jntid actuator_ctrllimited actuator_forcelimited "
-    "eq_obj1id eq_obj2id eq_active collision_pairs"
+    "eq_obj1id eq_obj2id eq_active collision_pairs geom_meshadr geom_meshnum"
 ).split()
 DBL_ARRAYS = (
     "opt_gravity body_pos body_quat body_ipos body_iquat body_mass body_inertia body_invweight0 jnt_pos jnt_axis "
     "jnt_range jnt_solref jnt_solimp dof_damping dof_armature dof_invweight0 qpos0 geom_size geom_pos geom_quat "
     "geom_friction geom_solref geom_solimp geom_margin geom_gap geom_rbound site_pos site_quat actuator_gear "
-    "actuator_gainprm actuator_biasprm actuator_ctrlrange actuator_forcerange eq_solref eq_solimp eq_data"
+    "actuator_gainprm actuator_biasprm actuator_ctrlrange actuator_forcerange eq_solref eq_solimp eq_data mesh_vert"
 ).split()
 
 

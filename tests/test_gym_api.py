@@ -71,3 +71,43 @@ def test_reference_style_config_and_episode_length_passthrough():
 
     with pytest.raises(NotImplementedError):
         split_config({"control_type": "ik"})
+
+
+def test_demo_files_have_the_reference_recorder_format(tmp_path):
+    """BatchDemoRecorder writes what furniture/util/demo_recorder.py:58-87 writes: same keys, len(obs) = len(actions) + 1, the
+    connect action appended to every low-level action; load_init_states reads the states back"""
+    import pickle
+
+    import numpy as np
+
+    from furniture_b200.demo import BatchDemoRecorder, load_init_states
+    from furniture_b200.engine import Engine, default_config
+    from furniture_b200 import mjcf
+    from collections import OrderedDict
+
+    class Shard:  # minimal batched env over the lane-emulated engine
+        def __init__(self, n):
+            self.model = mjcf.load_scene("Sawyer", "table_lack_0825")
+            self.engine = Engine(self.model, n, config=default_config(nsub=2), lib_path=build_emu())
+            self.num_envs = n
+        def _od(self, o): return OrderedDict(object_ob=o[:, :35], robot_ob=o[:, 35:])
+        def reset(self): self.engine.env_reset(); return self._od(self.engine.get("obs"))
+        def step(self, a): o, r, d, i = self.engine.env_step_host(a); return self._od(o), r, d, i
+        def get_env_state(self): q, v = self.engine.get_state(); return {"qpos": q, "qvel": v}
+
+    env = Shard(2)
+    rec = BatchDemoRecorder(env, demo_dir=str(tmp_path), metadata={"furniture": "table_lack_0825"})
+    rec.add_reset(env.reset())
+    rng = np.random.RandomState(0)
+    for k in range(3):
+        a = rng.uniform(-1, 1, (2, 9)).astype(np.float32)
+        od, rew, done, info = env.step(a)
+        rec.add_step(a, od, rew)
+    paths = rec.save("Sawyer_table_lack_0825_")
+    assert [p[-8:] for p in paths] == ["0000.pkl", "0001.pkl"]
+    demo = pickle.load(open(paths[1], "rb"))
+    assert set(demo) == {"states", "obs", "actions", "rewards", "low_level_obs", "low_level_actions", "connect_actions", "metadata"}
+    assert len(demo["obs"]) == 4 and len(demo["actions"]) == 3 and len(demo["states"]) == 4 and demo["low_level_actions"][0].shape == (9,)
+    assert list(demo["obs"][0].keys()) == ["object_ob", "robot_ob"] and demo["states"][0]["qpos"].shape == (44,)
+    states = load_init_states(paths[0])
+    assert len(states) == 4 and states[3]["qvel"].shape == (39,)

@@ -1,6 +1,6 @@
-"""The mixed-furniture case (BASELINE.json config 5): FurnitureSawyerEnv over every furniture XML whose
-colliders the engine supports (61 of the 64 shipped models; the other 3 have mesh colliders) -- ragged nq/nv/nefc, 2 to 14
-parts, 1 to 37 welds, boxes and cylinders.  For each model: device reset (settle protocol of furniture.py:1406-1663), then
+"""The mixed-furniture case (BASELINE.json config 5): FurnitureSawyerEnv over every furniture XML of the asset
+tree (64 models; 3 of them with mesh colliders, which collide through their convex hulls) -- ragged nq/nv/nefc, 2 to 14
+parts, 1 to 37 welds, boxes, cylinders and hulls.  For each model: device reset (settle protocol of furniture.py:1406-1663), then
 env steps with random actions compared with the CPU env oracle started from the same post-reset state.
 
 `emu` = lane-emulated harness build of the kernel source (CPU); `cuda` = the sm_100a library (marked gpu, a subset that
@@ -26,7 +26,7 @@ NAMES = sorted(os.path.basename(p)[len("Sawyer_") : -len(".npz")] for p in glob.
 # always raise the overflow flag (the others may, depending on the draw); all seven come out of the reset still moving, so steps are compared loosely (chaotic contact).
 UNLISTED = {"bookcase_billy_0191", "bookcase_grevback_0484", "cabinet_akurum_0021", "chair_agam_0005", "table_hemnes_0539", "table_klubbo_0740", "table_liden_0921"}
 OVERFLOW = {"bookcase_billy_0191", "bookcase_grevback_0484", "table_hemnes_0539", "table_liden_0921"}
-GPU_SUBSET = ["bookcase_expedit_0376", "chair_ingolf_0650", "table_dockstra_0279", "toy_table_flip", "three_blocks_peg", "bookcase_hensvik_0565"]
+GPU_SUBSET = ["bookcase_expedit_0376", "chair_ingolf_0650", "table_dockstra_0279", "toy_table_flip", "three_blocks_peg", "bookcase_hensvik_0565", "chair_bertil_0148"]
 
 
 def _run(name, gpu, n=2, steps=2):
@@ -54,7 +54,7 @@ def _run(name, gpu, n=2, steps=2):
     rng = np.random.RandomState(5)
     # analytic pairs (plane/sphere/box) agree to fp32 round-off; cylinder pairs go through MPR (portal tolerance), as in
     # test_engine_parity; parts still in motion after the reset amplify round-off through contact (loose bound)
-    has_cyl = bool((np.asarray(m.geom_type) == 5).any())
+    has_cyl = bool(np.isin(np.asarray(m.geom_type), (5, 7)).any())  # cylinders and mesh hulls collide through MPR
     tol = 2e-2 if name in UNLISTED else (1e-3 if has_cyl else 5e-5)
     for k in range(steps):
         a = rng.uniform(-1, 1, (n, eng.act_dim)).astype(np.float32)
@@ -70,7 +70,9 @@ def _run(name, gpu, n=2, steps=2):
 
 
 def test_compiled_tables_cover_the_supported_models():
-    assert len(NAMES) == 61 and "toy_table" in NAMES and "table_lack_0825" in NAMES and "swivel_chair_0700" in NAMES
+    # all 64 furniture XMLs of the asset tree, the three with mesh colliders (convex hulls) included
+    assert len(NAMES) == 64 and "toy_table" in NAMES and "table_lack_0825" in NAMES and "swivel_chair_0700" in NAMES
+    assert {"chair_agne_0010", "chair_bertil_0148", "shelf_liden_0922"} <= set(NAMES)
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -295,3 +295,58 @@ def test_recorded_rest_state_of_the_blocks_is_an_equilibrium_of_the_oracle():
         assert abs(sim.qpos[qa + 2] - facts[n][2]) < 1e-7, n  # height (in the recording x / y creep by 2e-7 per step: not compared tightly)
         assert np.abs(sim.qpos[qa : qa + 2] - facts[n][:2]).max() < 1e-5, n
         assert np.abs(sim.qpos[qa + 3 : qa + 7] - facts[n][3:]).max() < 5e-7, n
+
+
+def test_margin_capsule_and_mesh_hull_contacts(tmp_path):
+    """Contact margin (dist < margin is reported, MuJoCo mj_collision), the capsule and the mesh-hull colliders, hand-checkable:
+    * a sphere 0.5 mm above a box with margin 1 mm: one contact at dist = +0.5 mm (none with margin 0);
+    * a capsule standing 2 mm inside the floor: plane-capsule contact at the lower end sphere only;
+    * the convex hull of a box-shaped STL on the floor gives the four bottom corners, like the box primitive, and against a
+      box through MPR the depth of the face contact."""
+    import struct
+
+    xml = """<mujoco><worldbody>
+      <geom name="floor" type="plane" size="1 1 0.1"/>
+      <body name="a" pos="0 0 0"><joint type="free"/><geom name="ga" type="%s" size="%s" margin="%s"/></body>
+      <body name="b" pos="0 0 1"><joint type="free"/><geom name="gb" type="box" size="0.2 0.2 0.2"/></body>
+    </worldbody></mujoco>"""
+    for margin, n in (("0.001", 1), ("0", 0)):
+        sim = OracleSim(mjcf.compile_mjcf(xml % ("sphere", "0.1", margin)))
+        sim.qpos[0:3] = [0, 0, 5.0]
+        sim.qpos[7:10] = [0, 0, 5.3005]
+        sim.stage("kinematics")
+        cs = sim.collide_pair(1, 2)
+        assert len(cs) == n
+        if n:
+            assert abs(cs[0].dist - 0.0005) < 1e-9 and abs(cs[0].margin - 0.001) < 1e-12
+    sim = OracleSim(mjcf.compile_mjcf(xml % ("capsule", "0.05 0.2", "0")))
+    sim.qpos[0:3] = [0, 0, 0.248]  # lower end sphere centre at 0.048: 2 mm inside the floor
+    sim.qpos[7:10] = [0, 0, 5.0]
+    sim.stage("kinematics")
+    cs = sim.collide_pair(0, 1)
+    assert len(cs) == 1 and abs(cs[0].dist + 0.002) < 1e-9 and np.allclose(list(cs[0].frame)[:3], [0, 0, 1])
+    # box-shaped STL (12 triangles) -> hull of 8 corners
+    h = np.array([0.1, 0.15, 0.05])
+    c = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * h
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    stl = tmp_path / "box.stl"
+    with open(stl, "wb") as f:
+        f.write(b"\0" * 80 + struct.pack("<I", 12))
+        for q in quads:
+            for tri in ((q[0], q[1], q[2]), (q[0], q[2], q[3])):
+                f.write(struct.pack("<12fH", 0, 0, 0, *c[tri[0]], *c[tri[1]], *c[tri[2]], 0))
+    xml2 = """<mujoco><asset><mesh name="bx" file="%s"/></asset><worldbody>
+      <geom name="floor" type="plane" size="1 1 0.1"/>
+      <body name="a" pos="0 0 0"><joint type="free"/><geom name="ga" type="mesh" mesh="bx" density="100"/></body>
+      <body name="b" pos="0 0 1"><joint type="free"/><geom name="gb" type="box" size="0.2 0.2 0.2"/></body>
+    </worldbody></mujoco>""" % stl
+    m = mjcf.compile_mjcf(xml2)
+    assert m.geom_meshnum[1] == 8 and abs(m.body_mass[1] - 100 * 8 * h.prod()) < 1e-6  # STL vertices are float32
+    sim = OracleSim(m)
+    sim.qpos[0:3] = [0, 0, 0.049]  # 1 mm inside the floor
+    sim.qpos[7:10] = [0, 0, 0.049 + 0.05 + 0.2 - 0.003]  # box b 3 mm into the hull's top face
+    sim.stage("kinematics")
+    cs = sim.collide_pair(0, 1)
+    assert len(cs) == 4 and all(abs(x.dist + 0.001) < 1e-7 for x in cs)
+    cs = sim.collide_pair(1, 2)
+    assert len(cs) == 1 and abs(cs[0].dist + 0.003) < 1e-5 and abs(abs(list(cs[0].frame)[2]) - 1) < 1e-5
