@@ -126,7 +126,7 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   if (nm) add_field(h, nm, dst, (dim), (int)sizeof(T), wr);
   ALLOC(s.qpos, float, m.nq, "qpos", true) ALLOC(s.qvel, float, m.nv, "qvel", true) ALLOC(s.warm, float, m.nv, "qacc_warmstart", true)
   ALLOC(s.ctrl, float, m.nu, "ctrl", true) ALLOC(s.qfrc_applied, float, m.nr, "qfrc_applied", true) ALLOC(s.gravcomp, float, m.npart, "gravcomp", true)
-  ALLOC(s.eq_data, float, 7 * m.neq, "eq_data", true) ALLOC(s.contype, int, m.ngeom, "geom_contype", true) ALLOC(s.conaff, int, m.ngeom, "geom_conaffinity", true)
+  ALLOC(s.eq_data, float, 7 * m.neq, "eq_data", true) ALLOC(s.mpos, float, 3 * m.nmov, "static_pos", true) ALLOC(s.contype, int, m.ngeom, "geom_contype", true) ALLOC(s.conaff, int, m.ngeom, "geom_conaffinity", true)
   ALLOC(s.eq_active, int, m.neq, "eq_active", true) ALLOC(s.bias, float, m.nr, "qfrc_bias", false)
   ALLOC(s.lpos, float, 3 * m.nlink, "link_xpos", false) ALLOC(s.lquat, float, 4 * m.nlink, "link_xquat", false) ALLOC(s.lvel, float, 6 * m.nlink, "link_vel", false)
   ALLOC(s.touch, int, m.npart, "touch", false) ALLOC(s.flags, int, 1, "flags", true) ALLOC(s.ncon, int, 1, "ncon", false) ALLOC(s.niter, int, 1, "niter", false) ALLOC(s.stats, int, FE_NSTAT, "stats", false) ALLOC(s.order, int, 1, "order", true)
@@ -156,6 +156,13 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
     plat_upload(s.contype, ct.data(), sizeof(int) * N * m.ngeom);
     plat_upload(s.conaff, ca.data(), sizeof(int) * N * m.ngeom);
     if (m.neq) { plat_upload(s.eq_active, ea.data(), sizeof(int) * N * m.neq); plat_upload(s.eq_data, ed.data(), sizeof(float) * N * 7 * m.neq); }
+    if (m.nmov > 0) { // movable static geoms start where the model puts them
+      std::vector<float> mp(N * 3 * m.nmov, 0.f);
+      for (size_t n = 0; n < N; ++n)
+        for (int g = 0; g < m.ngeom; ++g)
+          if (m.geom_mov[g]) for (int k = 0; k < 3; ++k) mp[(n * m.nmov + (m.geom_mov[g] - 1)) * 3 + k] = m.geom_pos[g][k];
+      plat_upload(s.mpos, mp.data(), sizeof(float) * mp.size());
+    }
     std::vector<int> ord(N);
     for (size_t n = 0; n < N; ++n) ord[n] = (int)n;
     plat_upload(s.order, ord.data(), sizeof(int) * N);

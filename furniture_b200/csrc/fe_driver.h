@@ -9,6 +9,7 @@
 struct FeState {
   int N;
   float *qpos, *qvel, *warm, *ctrl, *qfrc_applied, *gravcomp, *eq_data; // [N][nq|nv|nv|nu|nr|npart|7 neq]
+  float* mpos;                                                          // [N][3 nmov] world positions of the movable static geoms
   int *contype, *conaff, *eq_active;                                    // [N][ngeom|ngeom|neq]
   float *bias;                                                          // [N][nr]  qfrc_bias of the last forward pass
   float *lpos, *lquat, *lvel;                                           // [N][nlink][3|4|6] of the last forward pass
@@ -28,7 +29,7 @@ FE_FN void fe_load(FeWarp* w, const FeState& s, int env) {
   const fe_model* m = w->m;
 #define LD(field, n) for (int i = lane; i < (n); i += 32) w->field()[i] = s.field[(size_t)env * (n) + i];
   LANES_BEGIN
-    LD(qpos, m->nq) LD(qvel, m->nv) LD(warm, m->nv) LD(ctrl, m->nu) LD(qfrc_applied, m->nr) LD(gravcomp, m->npart) LD(eq_data, 7 * m->neq)
+    LD(qpos, m->nq) LD(qvel, m->nv) LD(warm, m->nv) LD(ctrl, m->nu) LD(qfrc_applied, m->nr) LD(gravcomp, m->npart) LD(eq_data, 7 * m->neq) LD(mpos, 3 * m->nmov)
     LD(contype, m->ngeom) LD(conaff, m->ngeom) LD(eq_active, m->neq) LD(bias, m->nr)
     w->u()[lane] = 0; // 4 + FE_NSTAT <= 32
   LANES_END
@@ -38,7 +39,7 @@ FE_FN void fe_store(FeWarp* w, const FeState& s, int env) {
   const fe_model* m = w->m;
 #define ST(field, n) for (int i = lane; i < (n); i += 32) s.field[(size_t)env * (n) + i] = w->field()[i];
   LANES_BEGIN
-    ST(qpos, m->nq) ST(qvel, m->nv) ST(warm, m->nv) ST(ctrl, m->nu) ST(qfrc_applied, m->nr) ST(gravcomp, m->npart) ST(eq_data, 7 * m->neq)
+    ST(qpos, m->nq) ST(qvel, m->nv) ST(warm, m->nv) ST(ctrl, m->nu) ST(qfrc_applied, m->nr) ST(gravcomp, m->npart) ST(eq_data, 7 * m->neq) ST(mpos, 3 * m->nmov)
     ST(contype, m->ngeom) ST(conaff, m->ngeom) ST(eq_active, m->neq)
     ST(bias, m->nr) ST(lpos, 3 * m->nlink) ST(lquat, 4 * m->nlink) ST(lvel, 6 * m->nlink) ST(touch, m->npart)
     if (lane == 0) { s.flags[env] |= w->u()[2]; s.ncon[env] = w->u()[0]; s.niter[env] = w->u()[3]; }

@@ -45,7 +45,7 @@ struct FeOpt {
 // where every thread reads the same entry -- and `w->qpos()` is header address + table entry: no per-thread pointer
 // table, no local-memory traffic to reach the slice.
 #define FE_SLICE_F(X) /* float arrays */ \
-  X(qpos) X(qvel) X(warm) X(ctrl) X(qfrc_applied) X(gravcomp) X(eq_data) /* persistent state */ \
+  X(qpos) X(qvel) X(warm) X(ctrl) X(qfrc_applied) X(gravcomp) X(eq_data) X(mpos) /* persistent state */ \
   X(lpos) X(lquat) X(lmat) X(S) X(lvel) X(lacc) X(lfrc) X(linert) X(lcrb) X(Mr) X(Lr) X(fs) X(as) X(bias) X(lacc2) /* kinematics / dynamics */ \
   X(gpos) X(gmat) /* collision */ \
   X(c_dist) X(c_pos) X(c_frame) X(c_aref) X(c_D) X(c_mu) X(c_fric) X(c_jar) X(c_jv) X(c_f) /* contacts (SoA, maxcon each) */ \
@@ -106,7 +106,7 @@ FE_BOTH int fe_layout_build(FeLayout* L, const fe_model* m, const FeOpt& opt) {
   int o = FE_WARP_HDR_WORDS;
   const int nq = m->nq, nv = m->nv, nu = m->nu, nl = m->nlink, nr = m->nr, np = m->npart, ng = m->ngeom, ne = m->neq, mc = opt.maxcon;
 #define CARVE(field, n) L->field = o; o += (n);
-  CARVE(qpos, nq) CARVE(qvel, nv) CARVE(warm, nv) CARVE(ctrl, nu) CARVE(qfrc_applied, nr) CARVE(gravcomp, np) CARVE(eq_data, 7 * ne)
+  CARVE(qpos, nq) CARVE(qvel, nv) CARVE(warm, nv) CARVE(ctrl, nu) CARVE(qfrc_applied, nr) CARVE(gravcomp, np) CARVE(eq_data, 7 * ne) CARVE(mpos, 3 * m->nmov)
   CARVE(contype, ng) CARVE(conaff, ng) CARVE(eq_active, ne)
   CARVE(lpos, 3 * nl) CARVE(lquat, 4 * nl) CARVE(lmat, 9 * nl) CARVE(S, 6 * nr) CARVE(lvel, 6 * nl) CARVE(lacc, 6 * nl) CARVE(lfrc, 6 * nl)
   L->lacc2 = L->lfrc; /* RNE wrench (smooth stage) and solver link accelerations are never live together */
@@ -699,7 +699,11 @@ FE_FN void fe_collide(FeWarp* w) {
       const int l = m->geom_link[gi];
       float* gp = w->gpos() + 3 * gi;
       float* gm = w->gmat() + 9 * gi;
-      if (l < 0) { v3cpy(gp, m->geom_pos[gi]); for (int k = 0; k < 9; ++k) gm[k] = m->geom_mat[gi][k]; }
+      if (l < 0) {
+        const int mv = m->geom_mov[gi];
+        v3cpy(gp, mv ? w->mpos() + 3 * (mv - 1) : m->geom_pos[gi]); // movable static geom: its world position is per-env state
+        for (int k = 0; k < 9; ++k) gm[k] = m->geom_mat[gi][k];
+      }
       else {
         float t[3];
         m3mulv(t, w->lmat() + 9 * l, m->geom_pos[gi]);
@@ -761,7 +765,27 @@ FE_FN void fe_collide(FeWarp* w) {
       if (ci < ncand) {
         const int k = w->cand()[ci];
         g1 = m->pair_g1[k]; g2 = m->pair_g2[k];
-        n = fe_narrowphase(m, g1, g2, w->gpos() + 3 * g1, w->gmat() + 9 * g1, w->gpos() + 3 * g2, w->gmat() + 9 * g2, fmaxf(m->geom_margin[g1], m->geom_margin[g2]), res);
+        const float mg = fmaxf(m->geom_margin[g1], m->geom_margin[g2]), gap = fmaxf(m->geom_gap[g1], m->geom_gap[g2]);
+        n = fe_narrowphase(m, g1, g2, w->gpos() + 3 * g1, w->gmat() + 9 * g1, w->gpos() + 3 * g2, w->gmat() + 9 * g2, mg, res);
+        if (gap > 0.f) { // sensor pair (mj_collision reports it, mj_makeConstraint skips dist >= margin - gap): touch flags only
+          bool touching = false;
+          for (int i = 0; i < n; ++i) touching |= res[i].dist >= mg - gap;
+          if (touching) {
+            const int t1 = m->geom_tag[g1], t2 = m->geom_tag[g2];
+            const int pa = ((t1 >> FE_TAG_PART_SHIFT) & 0xff) - 1, pb = ((t2 >> FE_TAG_PART_SHIFT) & 0xff) - 1;
+            const int bits1 = ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0), bits2 = ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0);
+#if FE_DEVICE_BUILD
+            if (pb >= 0 && bits1) atomicOr(w->touch() + pb, bits1);
+            if (pa >= 0 && bits2) atomicOr(w->touch() + pa, bits2);
+#else
+            if (pb >= 0 && bits1) w->touch()[pb] |= bits1;
+            if (pa >= 0 && bits2) w->touch()[pa] |= bits2;
+#endif
+          }
+          int keep = 0; // contacts below margin - gap stay active (never the case for gap = 10)
+          for (int i = 0; i < n; ++i) if (res[i].dist < mg - gap) res[keep++] = res[i];
+          n = keep;
+        }
       }
       const int off = FE_SCAN(run, n);
       for (int i = 0; i < n; ++i) {
@@ -791,7 +815,7 @@ FE_FN void fe_collide(FeWarp* w) {
         if (p1 == p) bits |= ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0) | ((t2 & FE_TAG_FLOOR) ? 4 : 0) | ((t2 & FE_TAG_LFINGER2) ? 8 : 0) | ((t2 & FE_TAG_RFINGER2) ? 16 : 0);
         if (p2 == p) bits |= ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0) | ((t1 & FE_TAG_FLOOR) ? 4 : 0) | ((t1 & FE_TAG_LFINGER2) ? 8 : 0) | ((t1 & FE_TAG_RFINGER2) ? 16 : 0);
       }
-      w->touch()[p] = bits;
+      w->touch()[p] |= bits; // sensor pairs have set their bits during the narrow phase
     }
     if (lane == 0) { w->u()[0] = ncon; w->u()[1] = ncand; }
   LANES_END

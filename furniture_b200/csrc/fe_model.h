@@ -7,7 +7,7 @@
 #pragma once
 #include <stdint.h>
 
-#define FE_MODEL_MAGIC 0x46453033 /* "FE03" */
+#define FE_MODEL_MAGIC 0x46453034 /* "FE04" */
 #define FE_MAXLINK 32
 #define FE_MAXRDOF 20
 #define FE_MAXPART 16
@@ -28,6 +28,7 @@ enum { FE_TAG_FLOOR = 1, FE_TAG_LFINGER = 2, FE_TAG_RFINGER = 4, FE_TAG_ROBOT = 
 typedef struct fe_model {
   int32_t magic, struct_bytes;
   int32_t nq, nv, nu, nlink, nrlink, nr, npart, ngeom, npair, nsite, neq, maxdepth;
+  int32_t nmov; /* static geoms whose world position is per-env state (the Cursor agent's two cursors, moved through sim.model.body_pos) */
   float timestep, gravity[3], impratio, meaninertia, robot_ref[3];
   /* links: robot links [0, nrlink) in parent-before-child order (one hinge/slide dof each), then parts (free joint) */
   int32_t link_parent[FE_MAXLINK]; /* -1 = world */
@@ -49,7 +50,9 @@ typedef struct fe_model {
   int32_t geom_type[FE_MAXGEOM], geom_link[FE_MAXGEOM], geom_contype0[FE_MAXGEOM], geom_conaffinity0[FE_MAXGEOM], geom_tag[FE_MAXGEOM];
   float geom_pos[FE_MAXGEOM][3], geom_mat[FE_MAXGEOM][9], geom_size[FE_MAXGEOM][3], geom_rbound[FE_MAXGEOM];
   float geom_friction[FE_MAXGEOM], geom_solref[FE_MAXGEOM][2], geom_solimp[FE_MAXGEOM][3], geom_invweight[FE_MAXGEOM];
-  float geom_margin[FE_MAXGEOM]; /* contacts are generated below max(margin1, margin2); the constraint acts on dist - margin (gap = 0) */
+  float geom_margin[FE_MAXGEOM]; /* contacts are generated below max(margin1, margin2); the constraint acts on dist - margin */
+  float geom_gap[FE_MAXGEOM];    /* a contact with dist >= margin - gap is reported (touch flags) but generates no force: gap > 0 marks sensor geoms */
+  int32_t geom_mov[FE_MAXGEOM];  /* 1 + slot of a movable static geom, 0 otherwise */
   int32_t geom_meshadr[FE_MAXGEOM], geom_meshnum[FE_MAXGEOM]; /* mesh colliders: their convex-hull vertices in mesh_vert (geom frame) */
   float mesh_vert[FE_MAXMESHVERT][3];
   int32_t pair_g1[FE_MAXPAIR], pair_g2[FE_MAXPAIR]; /* type(g1) <= type(g2) */

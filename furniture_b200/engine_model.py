@@ -19,7 +19,7 @@ import numpy as np
 from . import mjcf
 
 MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU, MAXMESHVERT = 32, 20, 16, 116, 96, 2048, 256, 40, 20, 512
-MAGIC = 0x46453033
+MAGIC = 0x46453034
 TAG_FLOOR, TAG_LFINGER, TAG_RFINGER, TAG_ROBOT, TAG_LFINGER2, TAG_RFINGER2, TAG_PART_SHIFT = 1, 2, 4, 8, 16, 32, 8
 
 i32, f32 = C.c_int32, C.c_float
@@ -29,7 +29,7 @@ class FeModel(C.Structure):
     _fields_ = [
         ("magic", i32), ("struct_bytes", i32),
         ("nq", i32), ("nv", i32), ("nu", i32), ("nlink", i32), ("nrlink", i32), ("nr", i32), ("npart", i32), ("ngeom", i32),
-        ("npair", i32), ("nsite", i32), ("neq", i32), ("maxdepth", i32),
+        ("npair", i32), ("nsite", i32), ("neq", i32), ("maxdepth", i32), ("nmov", i32),
         ("timestep", f32), ("gravity", f32 * 3), ("impratio", f32), ("meaninertia", f32), ("robot_ref", f32 * 3),
         ("link_parent", i32 * MAXLINK), ("link_jtype", i32 * MAXLINK), ("link_qadr", i32 * MAXLINK), ("link_dadr", i32 * MAXLINK),
         ("link_depth", i32 * MAXLINK), ("link_ancmask", i32 * MAXLINK),
@@ -43,7 +43,7 @@ class FeModel(C.Structure):
         ("geom_type", i32 * MAXGEOM), ("geom_link", i32 * MAXGEOM), ("geom_contype0", i32 * MAXGEOM), ("geom_conaffinity0", i32 * MAXGEOM), ("geom_tag", i32 * MAXGEOM),
         ("geom_pos", (f32 * 3) * MAXGEOM), ("geom_mat", (f32 * 9) * MAXGEOM), ("geom_size", (f32 * 3) * MAXGEOM), ("geom_rbound", f32 * MAXGEOM),
         ("geom_friction", f32 * MAXGEOM), ("geom_solref", (f32 * 2) * MAXGEOM), ("geom_solimp", (f32 * 3) * MAXGEOM), ("geom_invweight", f32 * MAXGEOM),
-        ("geom_margin", f32 * MAXGEOM),
+        ("geom_margin", f32 * MAXGEOM), ("geom_gap", f32 * MAXGEOM), ("geom_mov", i32 * MAXGEOM),
         ("geom_meshadr", i32 * MAXGEOM), ("geom_meshnum", i32 * MAXGEOM), ("mesh_vert", (f32 * 3) * MAXMESHVERT),
         ("pair_g1", i32 * MAXPAIR), ("pair_g2", i32 * MAXPAIR),
         ("site_link", i32 * MAXSITE), ("site_pos", (f32 * 3) * MAXSITE), ("site_quat", (f32 * 4) * MAXSITE),
@@ -161,6 +161,8 @@ class EngineModel:
         lf2, rf2 = set(meta.get("l_finger_geoms2", [])), set(meta.get("r_finger_geoms2", []))  # second arm (Baxter's left gripper)
         robot_geoms = set(meta.get("robot_contact_geoms", []))
         part_names = list(meta.get("part_names", [m.names["body"][b] for b in parts]))
+        movable = list(meta.get("movable_geoms", []))  # Cursor agent: the cursors are static bodies repositioned through model.body_pos
+        fm.nmov = len(movable)
         keep = [g for g in range(m.ngeom) if m.geom_contype[g] != 0 or m.geom_conaffinity[g] != 0 or "collision" in m.names["geom"][g]]
         self.geom_src = keep
         self.geom_map = {g: i for i, g in enumerate(keep)}
@@ -214,8 +216,11 @@ class EngineModel:
             assert abs(m.geom_solimp[g][3] - 0.5) < 1e-12 and abs(m.geom_solimp[g][4] - 2) < 1e-12
             fm.geom_solimp[i][:] = list(m.geom_solimp[g][:3])
             fm.geom_invweight[i] = m.body_invweight0[b][0]
-            assert m.geom_condim[g] == 3 and m.geom_gap[g] == 0, "engine assumes condim=3 and gap=0 (every reported contact is active)"
-            fm.geom_margin[i] = m.geom_margin[g]
+            assert m.geom_condim[g] == 3, "engine assumes condim=3"
+            fm.geom_margin[i], fm.geom_gap[i] = m.geom_margin[g], m.geom_gap[g]
+            if name in movable:
+                assert l < 0, "movable geoms sit on static bodies"
+                fm.geom_mov[i] = 1 + movable.index(name)
         assert len(m.mesh_vert) <= MAXMESHVERT, "too many mesh-collider hull vertices: %d" % len(m.mesh_vert)
         for k, v in enumerate(m.mesh_vert):
             fm.mesh_vert[k][:] = list(v)

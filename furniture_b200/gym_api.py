@@ -141,6 +141,12 @@ def register_gym_envs():
     specs = {"IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050},
              "IKEABaxter-v0": {"id": "IKEABaxter-v0", "name": "FurnitureBaxterEnv", "furniture_id": 1, "background": "Interior", "port": 1050}}
     done = []
+    try:  # the Cursor agent is host logic over the simulator surface (furniture_b200/cursor_env.py)
+        register(id="IKEACursor-v0", entry_point="furniture_b200.cursor_env:FurnitureCursorEnvB200",
+                 kwargs={"id": "IKEACursor-v0", "name": "FurnitureCursorEnv", "furniture_id": 0, "background": "Lab", "port": 1050})
+        done.append("IKEACursor-v0")
+    except Exception:
+        pass
     for env_id, kwargs in specs.items():
         try:
             register(id=env_id, entry_point="furniture_b200.gym_api:FurnitureGymB200", kwargs=kwargs)

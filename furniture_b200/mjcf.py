@@ -283,11 +283,24 @@ def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None,
         )
         meta["eef_site"], meta["hand_body"] = "grip_site", "right_hand"
         meta["eef_site2"], meta["hand_body2"] = "l_g_grip_site", "left_hand"
+    elif agent == "Cursor":
+        # furniture.py:1949-1954 + robots/cursor.py: two static cursor boxes, half size = margin = move_speed / 2 (default 0.1 / 2), gap 10
+        robot = ET.parse(os.path.join(assets_root, "robots", "cursor", "robot.xml")).getroot()
+        half = 0.05
+        for nm in ("cursor0", "cursor1"):
+            robot.find("./worldbody/body[@name='%s']" % nm).set("pos", "0 0 %s" % half)
+            g = robot.find("./worldbody/body/geom[@name='%s']" % nm)
+            g.set("size", "%s %s %s" % (half, half, half))
+            g.set("margin", str(half))
+        _merge(world, robot)
+        meta.update(robot_joints=[], gripper_joints=[], robot_init_qpos=np.zeros(0), gripper_init_qpos=np.zeros(0),
+                    l_finger_geoms=["cursor0"], r_finger_geoms=["cursor1"],  # touch bit 0 / 1 of a part = cursor0 / cursor1 on it
+                    robot_contact_geoms=["cursor0", "cursor1"], movable_geoms=["cursor0", "cursor1"], eef_site=None, hand_body=None)
     elif agent == "None":
         meta.update(robot_joints=[], gripper_joints=[], robot_init_qpos=np.zeros(0), gripper_init_qpos=np.zeros(0),
                     l_finger_geoms=[], r_finger_geoms=[], robot_contact_geoms=[], eef_site=None, hand_body=None)
     else:
-        raise NotImplementedError("agent %s: Sawyer, Baxter and None are composed" % agent)
+        raise NotImplementedError("agent %s: Sawyer, Baxter, Cursor and None are composed" % agent)
 
     # furniture parts: furniture.py:1979-2001 + floor_task.py:55-72 + objects.py:186-206
     obj = ET.parse(os.path.join(assets_root, "objects", furniture + ".xml")).getroot()

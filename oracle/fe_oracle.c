@@ -547,6 +547,7 @@ void om_make_constraint(const om_model* m, om_data* d) {
     jac_point(m, d, b1, con->pos, jp1, NULL);
     jac_point(m, d, b2, con->pos, jp2, NULL);
     double w = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
+    if (con->dist >= con->margin - con->gap) { con->efc_address = -1; continue; } /* reported but inactive (mj_makeConstraint: dist < margin - gap) */
     con->efc_address = d->nefc;
     int dim = con->dim == 1 ? 1 : 3;
     for (int k = 0; k < dim; k++) {

@@ -70,6 +70,7 @@ typedef struct om_contact {
   double solimp[5];
   double mu; /* regularised cone mu */
   double margin; /* max of the two geoms' margins; the constraint acts on dist - margin */
+  double gap;    /* max of the two geoms' gaps; a contact with dist >= margin - gap is reported but generates no force */
   int dim;
   int geom1, geom2;
   int efc_address;

@@ -532,6 +532,7 @@ int om_collide_pair(const om_model* m, const om_data* d, int g1, int g2, om_cont
     else { c->solref[0] = sr1[0] < sr2[0] ? sr1[0] : sr2[0]; c->solref[1] = sr1[1] < sr2[1] ? sr1[1] : sr2[1]; }
     for (int k = 0; k < 5; k++) c->solimp[k] = 0.5 * (m->geom_solimp[5 * g1 + k] + m->geom_solimp[5 * g2 + k]);
     c->mu = 0; c->efc_address = -1; c->margin = margin;
+    c->gap = m->geom_gap[g1] > m->geom_gap[g2] ? m->geom_gap[g1] : m->geom_gap[g2];
     for (int k = 0; k < 5; k++) if (c->friction[k] < 1e-5) c->friction[k] = 1e-5; /* mjMINMU */
     if (c->dim != 1) c->dim = 3; /* condim 1 and 3 only in these scenes */
   }

@@ -34,7 +34,7 @@ DBL_ARRAYS = (
 class Contact(C.Structure):
     _fields_ = [
         ("dist", C.c_double), ("pos", C.c_double * 3), ("frame", C.c_double * 9), ("friction", C.c_double * 5),
-        ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double), ("margin", C.c_double), ("dim", C.c_int),
+        ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double), ("margin", C.c_double), ("gap", C.c_double), ("dim", C.c_int),
         ("geom1", C.c_int), ("geom2", C.c_int), ("efc_address", C.c_int),
     ]
 
@@ -138,6 +138,11 @@ class OracleSim:
 
     def scalar(self, name):
         return self.L.om_data_scalar(self.d, name.encode())
+
+    def set_model(self, name, value):
+        """overwrite a float array of the model (sim.model.body_pos[...] = ... of the reference's _set_pos, furniture.py:3133-3145)"""
+        v = np.ascontiguousarray(value, dtype=np.float64).ravel()
+        assert self.L.om_model_set_dbl(self.m, name.encode(), v.ctypes.data, v.size) == 0, name
 
     @property
     def ncon(self):

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from furniture_b200 import mjcf  # noqa: E402
 
-SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer", "swivel_chair_0700"), ("Baxter", "chair_ingolf_0650"), ("Baxter", "table_lack_0825")]
+SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer", "swivel_chair_0700"), ("Baxter", "chair_ingolf_0650"), ("Baxter", "table_lack_0825"), ("Cursor", "toy_table"), ("Cursor", "table_lack_0825")]
 MIXED = True  # plus Sawyer + every furniture XML whose colliders the engine supports (BASELINE.json config 5, the mixed batch)
 
 
