@@ -185,6 +185,28 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
   return 0;
 }
 
+int fe_scene_file_write(const char* path, const void* model_blob, size_t model_bytes, const void* scene_blob, size_t scene_bytes) {
+  if (!path || !model_blob || model_bytes != sizeof(fe_model) || !scene_blob || scene_bytes != sizeof(fe_scene))
+    return fail(nullptr, -1, "fe_scene_file_write: blob size mismatch");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(nullptr, -7, std::string("fe_scene_file_write: cannot open ") + path);
+  const uint32_t hdr[4] = {0x31424546u /* "FEB1" */, (uint32_t)sizeof(fe_model), (uint32_t)sizeof(fe_scene), 0u};
+  const bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(model_blob, sizeof(fe_model), 1, f) == 1 && fwrite(scene_blob, sizeof(fe_scene), 1, f) == 1;
+  fclose(f);
+  return ok ? 0 : fail(nullptr, -7, std::string("fe_scene_file_write: short write to ") + path);
+}
+int fe_create_from_file(const char* path, const fe_config* cfg, int n_envs, int device, fe_handle** out) {
+  FILE* f = path ? fopen(path, "rb") : nullptr;
+  if (!f) return fail(nullptr, -7, std::string("fe_create_from_file: cannot open ") + (path ? path : "(null)"));
+  uint32_t hdr[4] = {0, 0, 0, 0};
+  std::vector<unsigned char> mb(sizeof(fe_model)), sb(sizeof(fe_scene));
+  const bool ok = fread(hdr, sizeof(hdr), 1, f) == 1 && hdr[0] == 0x31424546u && hdr[1] == sizeof(fe_model) && hdr[2] == sizeof(fe_scene) &&
+                  fread(mb.data(), sizeof(fe_model), 1, f) == 1 && fread(sb.data(), sizeof(fe_scene), 1, f) == 1;
+  fclose(f);
+  if (!ok) return fail(nullptr, -7, std::string("fe_create_from_file: not a scene file of this library version: ") + path);
+  return fe_create(mb.data(), mb.size(), sb.data(), sb.size(), cfg, n_envs, device, out);
+}
+
 void fe_destroy(fe_handle* h) {
   if (!h) return;
   plat_fini(h);

@@ -285,30 +285,33 @@ FE_HD int fe_box_box(const float* cA, const float* RA, const float* a, const flo
 }
 
 // ---- Minkowski portal refinement on (g1 - g2), v0 = c1 - c2; direction returned points from g1 to g2
+// `size` of a mesh collider (type 7 | nvert << 8) points to its convex-hull vertices (geom frame) instead of the size vector.
+// `infl` = half the contact margin: the support function pushes the surface out by it (mjccd_support), fe_mpr takes it back.
 struct FeCvx {
   int type;
   const float *pos, *mat, *size;
-  float inflate; // half the contact margin: the support function pushes the surface out by it (mjccd_support), fe_mpr takes it back
-  const float* verts; // mesh collider: convex-hull vertices in the geom frame
-  int nvert;
 };
-FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
+// FULL = false: sphere / cylinder / box only (the common scenes); FULL = true adds the mesh-hull and capsule supports
+template <bool FULL>
+FE_HD void fe_support(const FeCvx& g, const float* dir, float infl, float* out) {
   float l[3], p[3];
   m3tmulv(l, g.mat, dir);
-  if (g.type == 2) {
+  const int type = g.type & 255;
+  if (type == 2) {
     float n = v3norm(l);
     float s = n > 1e-20f ? g.size[0] / n : 0.f;
     p[0] = l[0] * s; p[1] = l[1] * s; p[2] = l[2] * s;
-  } else if (g.type == 6) {
+  } else if (type == 6) {
     p[0] = l[0] >= 0.f ? g.size[0] : -g.size[0];
     p[1] = l[1] >= 0.f ? g.size[1] : -g.size[1];
     p[2] = l[2] >= 0.f ? g.size[2] : -g.size[2];
-  } else if (g.type == 7) { // mesh: hull vertex furthest along the direction (first one on ties)
+  } else if (FULL && type == 7) { // mesh: hull vertex furthest along the direction (first one on ties)
+    const int nvert = g.type >> 8;
     int best = 0;
     float bd = -1e30f;
-    for (int i = 0; i < g.nvert; ++i) { const float dd = l[0] * g.verts[3 * i] + l[1] * g.verts[3 * i + 1] + l[2] * g.verts[3 * i + 2]; if (dd > bd) { bd = dd; best = i; } }
-    p[0] = g.verts[3 * best]; p[1] = g.verts[3 * best + 1]; p[2] = g.verts[3 * best + 2];
-  } else if (g.type == 3) { // capsule: a sphere swept along the local z segment
+    for (int i = 0; i < nvert; ++i) { const float dd = l[0] * g.size[3 * i] + l[1] * g.size[3 * i + 1] + l[2] * g.size[3 * i + 2]; if (dd > bd) { bd = dd; best = i; } }
+    p[0] = g.size[3 * best]; p[1] = g.size[3 * best + 1]; p[2] = g.size[3 * best + 2];
+  } else if (FULL && type == 3) { // capsule: a sphere swept along the local z segment
     float n = v3norm(l);
     float s = n > 1e-20f ? g.size[0] / n : 0.f;
     p[0] = l[0] * s; p[1] = l[1] * s; p[2] = l[2] * s + (l[2] >= 0.f ? g.size[1] : -g.size[1]);
@@ -320,15 +323,16 @@ FE_HD void fe_support(const FeCvx& g, const float* dir, float* out) {
   }
   m3mulv(out, g.mat, p);
   v3add(out, out, g.pos);
-  if (g.inflate != 0.f) v3madd(out, out, dir, g.inflate);
+  if (infl != 0.f) v3madd(out, out, dir, infl);
 }
 struct FeSup {
   float v[3], v1[3], v2[3];
 };
-FE_HD void fe_mink(const FeCvx& g1, const FeCvx& g2, const float* dir, FeSup* s) {
+template <bool FULL>
+FE_HD void fe_mink(const FeCvx& g1, const FeCvx& g2, const float* dir, float infl, FeSup* s) {
   float nd[3] = {-dir[0], -dir[1], -dir[2]};
-  fe_support(g1, dir, s->v1);
-  fe_support(g2, nd, s->v2);
+  fe_support<FULL>(g1, dir, infl, s->v1);
+  fe_support<FULL>(g2, nd, infl, s->v2);
   v3sub(s->v, s->v1, s->v2);
 }
 // Closest point of triangle (a, b, c) to the origin (Ericson's region tests); returns its squared distance.  Evaluated in
@@ -391,7 +395,8 @@ FE_HD void fe_find_pos(const FeSup* p, float* pos) {
     pos[k] = s * inv;
   }
 }
-FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
+template <bool FULL>
+FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, float infl, FeCon* out) {
   const float tol = 1e-6f, eps = 1e-9f;
   FeSup p[4], v4;
   float dir[3], va[3], vb[3];
@@ -400,19 +405,19 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
   if (v3norm(p[0].v) < 1e-7f) p[0].v[0] = 1e-5f;
   dir[0] = -p[0].v[0]; dir[1] = -p[0].v[1]; dir[2] = -p[0].v[2];
   v3normalize(dir);
-  fe_mink(g1, g2, dir, &p[1]);
+  fe_mink<FULL>(g1, g2, dir, infl, &p[1]);
   if (v3dot(p[1].v, dir) <= 0.f) return 0;
   v3cross(dir, p[0].v, p[1].v);
   if (v3dot(dir, dir) < eps * eps) {
     v3cpy(out->n, p[1].v);
     float depth = v3normalize(out->n);
     if (!(depth > 0.f)) return 0;
-    out->dist = -depth + g1.inflate + g2.inflate;
+    out->dist = -depth + 2.f * infl;
     for (int k = 0; k < 3; ++k) out->pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]);
     return 1;
   }
   v3normalize(dir);
-  fe_mink(g1, g2, dir, &p[2]);
+  fe_mink<FULL>(g1, g2, dir, infl, &p[2]);
   if (v3dot(p[2].v, dir) <= 0.f) return 0;
   v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v);
   v3cross(dir, va, vb);
@@ -420,7 +425,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
   if (v3dot(dir, p[0].v) > 0.f) { FeSup t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
   for (int it = 0;; ++it) {
     if (it > 100) return 0;
-    fe_mink(g1, g2, dir, &p[3]);
+    fe_mink<FULL>(g1, g2, dir, infl, &p[3]);
     if (v3dot(p[3].v, dir) <= 0.f) return 0;
     bool cont = false;
     v3cross(va, p[1].v, p[3].v);
@@ -434,7 +439,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
   for (int it = 0;; ++it) {
     fe_portal_dir(p, dir);
     if (v3dot(p[1].v, dir) >= 0.f) break;
-    fe_mink(g1, g2, dir, &v4);
+    fe_mink<FULL>(g1, g2, dir, infl, &v4);
     float dv4 = v3dot(v4.v, dir);
     float mn = fminf(fminf(dv4 - v3dot(p[1].v, dir), dv4 - v3dot(p[2].v, dir)), dv4 - v3dot(p[3].v, dir));
     if (dv4 < 0.f || mn <= tol || it > 50) return 0;
@@ -442,7 +447,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
   }
   for (int it = 0;; ++it) {
     fe_portal_dir(p, dir);
-    fe_mink(g1, g2, dir, &v4);
+    fe_mink<FULL>(g1, g2, dir, infl, &v4);
     float dv4 = v3dot(v4.v, dir);
     float mn = fminf(fminf(dv4 - v3dot(p[1].v, dir), dv4 - v3dot(p[2].v, dir)), dv4 - v3dot(p[3].v, dir));
     if (mn <= tol || it > 50) {
@@ -451,7 +456,7 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
       if (depth < 1e-9f) v3cpy(out->n, dir);
       else { float s = 1.f / depth; out->n[0] = w[0] * s; out->n[1] = w[1] * s; out->n[2] = w[2] * s; }
       if (!(depth > 0.f)) return 0;
-      out->dist = -depth + g1.inflate + g2.inflate;
+      out->dist = -depth + 2.f * infl;
       fe_find_pos(p, out->pos);
       return 1;
     }
@@ -459,25 +464,36 @@ FE_HD int fe_mpr(const FeCvx& g1, const FeCvx& g2, FeCon* out) {
   }
 }
 
+// the rarely used colliders (mesh hulls, capsules), kept out of the common dispatch so that its register budget stays small
+FE_HDN int fe_narrow_rare(const fe_model* m, int g1, int g2, const float* p1, const float* R1, const float* p2, const float* R2, float margin, FeCon* out) {
+  const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  const float *s1 = m->geom_size[g1], *s2 = m->geom_size[g2];
+  if (t1 == 0) {
+    if (t2 == 3) return fe_plane_capsule(p1, R1, p2, R2, s2[0], s2[1], margin, out);
+    return fe_plane_mesh(p1, R1, p2, R2, &m->mesh_vert[m->geom_meshadr[g2]][0], m->geom_meshnum[g2], margin, out);
+  }
+  // MuJoCo has analytic routines for the capsule pairs (mjc_CapsuleBox ...), which can return two points where MPR returns the deepest one
+  FeCvx a = {t1, p1, R1, s1}, b = {t2, p2, R2, s2};
+  if (t1 == 7) { a.type = 7 | (m->geom_meshnum[g1] << 8); a.size = &m->mesh_vert[m->geom_meshadr[g1]][0]; }
+  if (t2 == 7) { b.type = 7 | (m->geom_meshnum[g2] << 8); b.size = &m->mesh_vert[m->geom_meshadr[g2]][0]; }
+  return fe_mpr<true>(a, b, 0.5f * margin, out);
+}
+
 // dispatch on the (ordered) type pair; geometry in world frame; contacts closer than `margin` are reported (mj_collision:
 // dist < margin, margin = max of the two geoms').  Returns contact count (<= 8).
 FE_HDN int fe_narrowphase(const fe_model* m, int g1, int g2, const float* p1, const float* R1, const float* p2, const float* R2, float margin, FeCon* out) {
   const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  if (t1 == 3 || t2 == 3 || t2 == 7) return fe_narrow_rare(m, g1, g2, p1, R1, p2, R2, margin, out); // t1 <= t2: a mesh is always on side 2
   const float *s1 = m->geom_size[g1], *s2 = m->geom_size[g2];
   if (t1 == 0) {
     if (t2 == 2) return fe_plane_sphere(p1, R1, p2, s2[0], margin, out);
-    if (t2 == 3) return fe_plane_capsule(p1, R1, p2, R2, s2[0], s2[1], margin, out);
     if (t2 == 5) return fe_plane_cylinder(p1, R1, p2, R2, s2[0], s2[1], margin, out);
     if (t2 == 6) return fe_plane_box(p1, R1, p2, R2, s2, margin, out);
-    if (t2 == 7) return fe_plane_mesh(p1, R1, p2, R2, &m->mesh_vert[m->geom_meshadr[g2]][0], m->geom_meshnum[g2], margin, out);
     return 0;
   }
   if (t1 == 2 && t2 == 2) return fe_sphere_sphere(p1, s1[0], p2, s2[0], margin, out);
   if (t1 == 2 && t2 == 6) return fe_sphere_box(p1, s1[0], p2, R2, s2, margin, out);
   if (t1 == 6 && t2 == 6) return fe_box_box(p1, R1, s1, p2, R2, s2, margin, out);
-  // every other pair (a cylinder, a capsule or a mesh hull on one side) goes through MPR; MuJoCo has analytic routines for the
-  // capsule pairs (mjc_CapsuleBox ...), which can return two points where MPR returns the deepest one
-  FeCvx a = {t1, p1, R1, s1, 0.5f * margin, t1 == 7 ? &m->mesh_vert[m->geom_meshadr[g1]][0] : nullptr, t1 == 7 ? m->geom_meshnum[g1] : 0};
-  FeCvx b = {t2, p2, R2, s2, 0.5f * margin, t2 == 7 ? &m->mesh_vert[m->geom_meshadr[g2]][0] : nullptr, t2 == 7 ? m->geom_meshnum[g2] : 0};
-  return fe_mpr(a, b, out);
+  FeCvx a = {t1, p1, R1, s1}, b = {t2, p2, R2, s2}; // a cylinder on one side: MPR
+  return fe_mpr<false>(a, b, 0.5f * margin, out);
 }

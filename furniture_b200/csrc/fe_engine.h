@@ -691,16 +691,40 @@ FE_HD int fe_lane_excl_scan(int n) {
 #define FE_SCAN(run, n) ((run += (n)), (run - (n)))
 #endif
 
+// A pair with a sensor geom (gap > 0; mj_collision reports its contacts, mj_makeConstraint skips those with dist >= margin - gap):
+// the contacts at or beyond `active` only raise the touch flags; the (rare) closer ones stay.  Returns the contacts kept.
+FE_HDN int fe_sensor_pair(FeWarp* w, int g1, int g2, FeCon* res, int n, float active) {
+  const fe_model* m = w->m;
+  bool touching = false;
+  for (int i = 0; i < n; ++i) touching |= res[i].dist >= active;
+  if (touching) {
+    const int t1 = m->geom_tag[g1], t2 = m->geom_tag[g2];
+    const int pa = ((t1 >> FE_TAG_PART_SHIFT) & 0xff) - 1, pb = ((t2 >> FE_TAG_PART_SHIFT) & 0xff) - 1;
+    const int bits1 = ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0), bits2 = ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0);
+#if FE_DEVICE_BUILD
+    if (pb >= 0 && bits1) atomicOr(w->touch() + pb, bits1);
+    if (pa >= 0 && bits2) atomicOr(w->touch() + pa, bits2);
+#else
+    if (pb >= 0 && bits1) w->touch()[pb] |= bits1;
+    if (pa >= 0 && bits2) w->touch()[pa] |= bits2;
+#endif
+  }
+  int keep = 0;
+  for (int i = 0; i < n; ++i) if (res[i].dist < active) res[keep++] = res[i];
+  return keep;
+}
+
 FE_FN void fe_collide(FeWarp* w) {
   const fe_model* m = w->m;
   const int ng = m->ngeom, npair = m->npair, nrl = m->nrlink, mc = w->opt.maxcon;
+  const bool hasm = m->has_margin != 0;
   LANES_BEGIN
     for (int gi = lane; gi < ng; gi += 32) {
       const int l = m->geom_link[gi];
       float* gp = w->gpos() + 3 * gi;
       float* gm = w->gmat() + 9 * gi;
       if (l < 0) {
-        const int mv = m->geom_mov[gi];
+        const int mv = m->nmov > 0 ? m->geom_mov[gi] : 0;
         v3cpy(gp, mv ? w->mpos() + 3 * (mv - 1) : m->geom_pos[gi]); // movable static geom: its world position is per-env state
         for (int k = 0; k < 9; ++k) gm[k] = m->geom_mat[gi][k];
       }
@@ -728,7 +752,7 @@ FE_FN void fe_collide(FeWarp* w) {
           float t[3];
           v3sub(t, w->gpos() + 3 * g2, w->gpos() + 3 * g1);
           bool hit;
-          const float mg = fmaxf(m->geom_margin[g1], m->geom_margin[g2]);
+          const float mg = hasm ? fmaxf(m->geom_margin[g1], m->geom_margin[g2]) : 0.f;
           if (m->geom_type[g1] == FE_GEOM_PLANE) {
             float n[3];
             fe_col(n, w->gmat() + 9 * g1, 2);
@@ -765,27 +789,9 @@ FE_FN void fe_collide(FeWarp* w) {
       if (ci < ncand) {
         const int k = w->cand()[ci];
         g1 = m->pair_g1[k]; g2 = m->pair_g2[k];
-        const float mg = fmaxf(m->geom_margin[g1], m->geom_margin[g2]), gap = fmaxf(m->geom_gap[g1], m->geom_gap[g2]);
+        const float mg = hasm ? fmaxf(m->geom_margin[g1], m->geom_margin[g2]) : 0.f;
         n = fe_narrowphase(m, g1, g2, w->gpos() + 3 * g1, w->gmat() + 9 * g1, w->gpos() + 3 * g2, w->gmat() + 9 * g2, mg, res);
-        if (gap > 0.f) { // sensor pair (mj_collision reports it, mj_makeConstraint skips dist >= margin - gap): touch flags only
-          bool touching = false;
-          for (int i = 0; i < n; ++i) touching |= res[i].dist >= mg - gap;
-          if (touching) {
-            const int t1 = m->geom_tag[g1], t2 = m->geom_tag[g2];
-            const int pa = ((t1 >> FE_TAG_PART_SHIFT) & 0xff) - 1, pb = ((t2 >> FE_TAG_PART_SHIFT) & 0xff) - 1;
-            const int bits1 = ((t1 & FE_TAG_LFINGER) ? 1 : 0) | ((t1 & FE_TAG_RFINGER) ? 2 : 0), bits2 = ((t2 & FE_TAG_LFINGER) ? 1 : 0) | ((t2 & FE_TAG_RFINGER) ? 2 : 0);
-#if FE_DEVICE_BUILD
-            if (pb >= 0 && bits1) atomicOr(w->touch() + pb, bits1);
-            if (pa >= 0 && bits2) atomicOr(w->touch() + pa, bits2);
-#else
-            if (pb >= 0 && bits1) w->touch()[pb] |= bits1;
-            if (pa >= 0 && bits2) w->touch()[pa] |= bits2;
-#endif
-          }
-          int keep = 0; // contacts below margin - gap stay active (never the case for gap = 10)
-          for (int i = 0; i < n; ++i) if (res[i].dist < mg - gap) res[keep++] = res[i];
-          n = keep;
-        }
+        if (m->has_gap) { const float gap = fmaxf(m->geom_gap[g1], m->geom_gap[g2]); if (gap > 0.f) n = fe_sensor_pair(w, g1, g2, res, n, mg - gap); }
       }
       const int off = FE_SCAN(run, n);
       for (int i = 0; i < n; ++i) {
@@ -898,7 +904,7 @@ FE_FN void fe_assemble(FeWarp* w) {
       if (s1[0] > 0.f && s2[0] > 0.f) { sr[0] = 0.5f * (s1[0] + s2[0]); sr[1] = 0.5f * (s1[1] + s2[1]); }
       else { sr[0] = fminf(s1[0], s2[0]); sr[1] = fminf(s1[1], s2[1]); }
       for (int k = 0; k < 3; ++k) si[k] = 0.5f * (m->geom_solimp[g1][k] + m->geom_solimp[g2][k]);
-      const float dist = w->c_dist()[c] - fmaxf(m->geom_margin[g1], m->geom_margin[g2]); // efc_pos - efc_margin (gap = 0: every contact is active)
+      const float dist = w->c_dist()[c] - (m->has_margin ? fmaxf(m->geom_margin[g1], m->geom_margin[g2]) : 0.f); // efc_pos - efc_margin
       const float imp = fe_impedance(si, fabsf(dist));
       float kk, bb;
       fe_kb(sr, si[1], h, &kk, &bb);

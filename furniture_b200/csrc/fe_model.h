@@ -7,7 +7,7 @@
 #pragma once
 #include <stdint.h>
 
-#define FE_MODEL_MAGIC 0x46453034 /* "FE04" */
+#define FE_MODEL_MAGIC 0x46453035 /* "FE05" */
 #define FE_MAXLINK 32
 #define FE_MAXRDOF 20
 #define FE_MAXPART 16
@@ -28,6 +28,7 @@ enum { FE_TAG_FLOOR = 1, FE_TAG_LFINGER = 2, FE_TAG_RFINGER = 4, FE_TAG_ROBOT = 
 typedef struct fe_model {
   int32_t magic, struct_bytes;
   int32_t nq, nv, nu, nlink, nrlink, nr, npart, ngeom, npair, nsite, neq, maxdepth;
+  int32_t has_margin, has_gap; /* any geom with margin > 0 / gap > 0: scenes without skip the per-pair lookups */
   int32_t nmov; /* static geoms whose world position is per-env state (the Cursor agent's two cursors, moved through sim.model.body_pos) */
   float timestep, gravity[3], impratio, meaninertia, robot_ref[3];
   /* links: robot links [0, nrlink) in parent-before-child order (one hinge/slide dof each), then parts (free joint) */

@@ -198,7 +198,7 @@ class Engine:
                 raise RuntimeError("furniture_b200: %s = %d but python layout has %d bytes" % (fn, getattr(L, fn)(), C.sizeof(cls)))
         self.h = C.c_void_p()
         rc = L.fe_create(C.byref(self.em.fm), C.c_size_t(C.sizeof(self.em.fm)), C.byref(self.scene), C.c_size_t(C.sizeof(self.scene)), C.byref(self.cfg),
-                         int(n_envs), int(device), C.byref(self.h))
+                         int(n_envs), int(device), C.byref(self.h))  # (fe_create_from_file does the same from a compiled/*.feb scene file)
         if rc != 0:
             raise RuntimeError("fe_create failed (%d): %s" % (rc, L.fe_last_error(None).decode()))
         self.N = int(n_envs)

@@ -19,7 +19,7 @@ import numpy as np
 from . import mjcf
 
 MAXLINK, MAXRDOF, MAXPART, MAXDOF, MAXGEOM, MAXPAIR, MAXSITE, MAXEQ, MAXU, MAXMESHVERT = 32, 20, 16, 116, 96, 2048, 256, 40, 20, 512
-MAGIC = 0x46453034
+MAGIC = 0x46453035
 TAG_FLOOR, TAG_LFINGER, TAG_RFINGER, TAG_ROBOT, TAG_LFINGER2, TAG_RFINGER2, TAG_PART_SHIFT = 1, 2, 4, 8, 16, 32, 8
 
 i32, f32 = C.c_int32, C.c_float
@@ -29,7 +29,7 @@ class FeModel(C.Structure):
     _fields_ = [
         ("magic", i32), ("struct_bytes", i32),
         ("nq", i32), ("nv", i32), ("nu", i32), ("nlink", i32), ("nrlink", i32), ("nr", i32), ("npart", i32), ("ngeom", i32),
-        ("npair", i32), ("nsite", i32), ("neq", i32), ("maxdepth", i32), ("nmov", i32),
+        ("npair", i32), ("nsite", i32), ("neq", i32), ("maxdepth", i32), ("has_margin", i32), ("has_gap", i32), ("nmov", i32),
         ("timestep", f32), ("gravity", f32 * 3), ("impratio", f32), ("meaninertia", f32), ("robot_ref", f32 * 3),
         ("link_parent", i32 * MAXLINK), ("link_jtype", i32 * MAXLINK), ("link_qadr", i32 * MAXLINK), ("link_dadr", i32 * MAXLINK),
         ("link_depth", i32 * MAXLINK), ("link_ancmask", i32 * MAXLINK),
@@ -224,6 +224,8 @@ class EngineModel:
         assert len(m.mesh_vert) <= MAXMESHVERT, "too many mesh-collider hull vertices: %d" % len(m.mesh_vert)
         for k, v in enumerate(m.mesh_vert):
             fm.mesh_vert[k][:] = list(v)
+        fm.has_margin = int(any(fm.geom_margin[i] > 0 for i in range(fm.ngeom)))
+        fm.has_gap = int(any(fm.geom_gap[i] > 0 for i in range(fm.ngeom)))
         pairs = []
         for g1, g2 in m.collision_pairs:
             if int(g1) in self.geom_map and int(g2) in self.geom_map:

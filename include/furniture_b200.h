@@ -56,6 +56,12 @@ int fe_is_cuda(void);
 
 int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob, size_t scene_bytes, const fe_config* cfg, int n_envs,
               int device, fe_handle** out);
+/* Same, from a scene file: the two blobs as written by fe_scene_file_write (magic "FEB1", sizes, fe_model, fe_scene).  The
+   files furniture_b200/compiled/<agent>_<furniture>.feb are produced offline by tools/compile_models.py from the composed MJCF
+   (models/base.py:76-116 + load_model_from_xml), so that a binder in any language creates a handle with this one call and no
+   Python at run time. */
+int fe_create_from_file(const char* scene_file, const fe_config* cfg, int n_envs, int device, fe_handle** out);
+int fe_scene_file_write(const char* scene_file, const void* model_blob, size_t model_bytes, const void* scene_blob, size_t scene_bytes);
 void fe_destroy(fe_handle* h);
 const char* fe_last_error(const fe_handle* h); /* h may be NULL: last creation error */
 

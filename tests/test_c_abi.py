@@ -90,3 +90,41 @@ def test_get_and_set_state_round_trip(gpu):
     other.set("qpos", Q); other.set("qvel", V)
     other.forward(); other.step(5)
     assert np.array_equal(eng.get_state()[0], other.get("qpos")) and np.array_equal(eng.get_state()[1], other.get("qvel"))
+
+
+def test_scene_file_round_trip(tmp_path):
+    """fe_scene_file_write / fe_create_from_file: a handle created from the binary scene file (what a non-Python binder uses)
+    steps exactly like one created from the blobs (lane-emulated build; the CUDA library shares the code)"""
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from furniture_b200 import mjcf
+    from furniture_b200.engine import build_scene, default_config
+    from furniture_b200.engine_model import EngineModel
+    from parity_util import build_emu, make_engine
+
+    L = C.CDLL(build_emu())
+    L.fe_last_error.restype = C.c_char_p
+    L.fe_last_error.argtypes = [C.c_void_p]
+    m = mjcf.load_scene("Sawyer", "table_lack_0825")
+    em = EngineModel(m)
+    sc = build_scene(m, em)
+    path = str(tmp_path / "scene.feb").encode()
+    assert L.fe_scene_file_write(path, C.byref(em.fm), C.c_size_t(C.sizeof(em.fm)), C.byref(sc), C.c_size_t(C.sizeof(sc))) == 0
+    cfg = default_config(nsub=3, maxcon=44)
+    h = C.c_void_p()
+    assert L.fe_create_from_file(path, C.byref(cfg), 2, 0, C.byref(h)) == 0, L.fe_last_error(None)
+    assert L.fe_env_reset(h, None, None, None) == 0
+    a = np.random.RandomState(0).uniform(-1, 1, (2, 9)).astype(np.float32)
+    obs = np.empty((2, 64), np.float32)
+    assert L.fe_env_step_host(h, a.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p), None, None, None) == 0
+    eng = make_engine(m, 2, False, nsub=3, maxcon=44)
+    eng.env_reset()
+    obs2 = eng.env_step_host(a)[0]
+    assert np.array_equal(obs, obs2)
+    L.fe_destroy(h)
+    bad = tmp_path / "bad.feb"
+    bad.write_bytes(b"nope" * 100)
+    assert L.fe_create_from_file(str(bad).encode(), C.byref(cfg), 2, 0, C.byref(h)) < 0 and b"scene file" in L.fe_last_error(None)

@@ -13,6 +13,22 @@ SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer",
 MIXED = True  # plus Sawyer + every furniture XML whose colliders the engine supports (BASELINE.json config 5, the mixed batch)
 
 
+def write_feb(m, path):
+    """the binary scene file of fe_create_from_file (fe_model + fe_scene), written through the library itself"""
+    import ctypes as C
+
+    from furniture_b200.engine import DEFAULT_LIB, build_scene
+    from furniture_b200.engine_model import EngineModel
+
+    if not os.path.exists(DEFAULT_LIB):
+        return
+    L = C.CDLL(DEFAULT_LIB)
+    em = EngineModel(m)
+    sc = build_scene(m, em)
+    rc = L.fe_scene_file_write(path.encode(), C.byref(em.fm), C.c_size_t(C.sizeof(em.fm)), C.byref(sc), C.c_size_t(C.sizeof(sc)))
+    assert rc == 0, path
+
+
 def main():
     root = mjcf.default_assets_root()
     if root is None:
@@ -33,6 +49,7 @@ def main():
             continue
         path = os.path.join(out, "%s_%s.npz" % (agent, furn))
         m.save(path)
+        write_feb(m, os.path.join(out, "%s_%s.feb" % (agent, furn)))
         print("wrote", path, "nq=%d nv=%d" % (m.nq, m.nv))
     for furn, why in skipped:
         print("skipped", furn, "--", why)
