@@ -228,16 +228,24 @@ def run_ours(args):
         cdir = os.path.join(ROOT, "furniture_b200", "compiled")
         names = sorted(f[len(args.agent) + 1 : -4] for f in os.listdir(cdir) if f.startswith(args.agent + "_") and f.endswith(".npz"))
         models = {n: mjcf.load_scene(args.agent, n) for n in names}
-        owned = shard_furniture(names, 1, world, nv=[models[n].nv for n in names], envs_per_rank=n_local)
+        # the same number of envs of every furniture model; whole buckets per GPU, balanced on the measured cost of the models;
+        # ranks then own different numbers of envs and pad their shard to the largest (the all-gather wants equal shards)
+        from furniture_b200.env import model_costs
+
+        per_model = max(1, (n_local * world) // len(names))
+        owned = shard_furniture(names, per_model, world, nv=[models[n].nv for n in names], cost_per_env=model_costs() or None)
+        n_real = [sum(c for _, c in o) for o in owned]
+        n_local = max(n_real)
         wide = max(7 * len(models[n].meta["part_names"]) for n in names)
-        mixed = {"models": len(names), "per_rank": [len(o) for o in owned], "nv_range": [min(m.nv for m in models.values()), max(m.nv for m in models.values())]}
+        mixed = {"models": len(names), "per_rank": [len(o) for o in owned], "nv_range": [min(m.nv for m in models.values()), max(m.nv for m in models.values())],
+                 "envs_per_model": per_model, "envs_per_rank": n_real, "global_envs": sum(n_real)}
 
     def make_env():
         # the two timed legs (device-resident `value`, host-buffer `e2e`) run on two envs built alike -- same seeds, same
         # reset draws, same actions, same step range -- so that their numbers are comparable
         if mixed is not None:
             mine = owned[rank]
-            e = MixedFurnitureEnv([n for n, _ in mine], [c for _, c in mine], agent=args.agent, device=local, object_ob_dim=wide,
+            e = MixedFurnitureEnv([n for n, _ in mine], [c for _, c in mine], agent=args.agent, device=local, object_ob_dim=wide, pad_to=n_local,
                                   seed=ShardedFurnitureEnv.shard_seed(123, rank, n_local))
             return (ShardedFurnitureEnv(n_local, env=e), e) if world > 1 else (e, e)
         if world > 1:
@@ -293,7 +301,8 @@ def run_ours(args):
         per_rank = [{"rank": r, "step_ms": float(t[0]), "kernel_ms": float(t[1]), "gather_wait_ms": float(t[2])} for r, t in enumerate(allr)]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    value = n_local * world * K / (total_ms * 1e-3)
+    n_global = mixed["global_envs"] if mixed is not None else n_local * world  # padding rows of a mixed batch are not envs
+    value = n_global * K / (total_ms * 1e-3)
     # kernels launched by this repo inside the timed region, per step: fe_env_step_kernel + fe_order_kernel (block packing for
     # the next step); N > 1 adds NCCL's all-gather kernel (a library kernel, not counted)
     launches = 2 * K * (len(owned[rank]) if mixed is not None else 1)
@@ -326,7 +335,7 @@ def run_ours(args):
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e = n_local * world * K / float(e2e_t.item())
+    e2e = n_global * K / float(e2e_t.item())
     h2d = n_local * benv.act_dim * 4
     d2h = obs_host.numel() * 4 + rew_host.numel() * 4 + done_host.numel()
 
@@ -334,7 +343,7 @@ def run_ours(args):
         peaks, peak_src = load_peaks()
         kernel_ms = total_ms / K  # one env-step = one launch of fe_env_step_kernel (+ the all_gather when N > 1)
         if mixed is not None:
-            benv_bytes = benv.algorithmic_bytes_per_step() / n_local  # mean over this rank's buckets
+            benv_bytes = benv.algorithmic_bytes_per_step() / n_local  # this rank's buckets, per row of its (padded) shard
         else:
             benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim)
         assert args.furniture != "table_lack_0825" or args.agent != "Sawyer" or benv_bytes == B_ENV
@@ -343,8 +352,9 @@ def run_ours(args):
         default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU
         workload = WORKLOAD if default_case else "Furniture%sEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.agent, args.furniture, act_txt)
         if mixed is not None:
-            workload = ("Furniture%sEnv, mixed-furniture batch: %d furniture models (nv %d..%d), whole buckets per GPU (%s models per rank), one kernel-module "
-                        "instance and stream per bucket, 50 mj_steps per env-step, %s" % (args.agent, mixed["models"], mixed["nv_range"][0], mixed["nv_range"][1], mixed["per_rank"], act_txt))
+            workload = ("Furniture%sEnv, mixed-furniture batch: %d furniture models (nv %d..%d) x %d envs each, whole buckets per GPU balanced on measured model cost "
+                        "(%s models / %s envs per rank, shards padded to %d rows), one kernel-module instance and stream per bucket, 50 mj_steps per env-step, %s"
+                        % (args.agent, mixed["models"], mixed["nv_range"][0], mixed["nv_range"][1], mixed["envs_per_model"], mixed["per_rank"], mixed["envs_per_rank"], n_local, act_txt))
         # measured DRAM traffic and instruction counts come from an ncu capture of exactly this kernel build
         # (tools/ncu_extract.py writes profiles/traffic.json with the build id); a stale capture is refused
         traffic, secondary, prof_note = None, None, None
@@ -367,7 +377,7 @@ def run_ours(args):
             "metric": METRIC if default_case else "aggregate env-steps/sec, %s+%s @%d envs/GPU (%s actions)" % (args.agent, args.furniture, n_local, args.actions),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "envs_per_gpu": n_local, "global_envs": n_local * world, "parallelism": "env-shards x%d" % world,
+            "config": {"workload": workload, "envs_per_gpu": n_local, "global_envs": n_global, "parallelism": "env-shards x%d" % world,
                        "l2": "flushed before every timed step of both legs (256 MiB write, not timed)",
                        "timing": "value: CUDA events per step on the launch stream, max over ranks; e2e: wall clock per step around the public call with "
                                  "host buffers, same actions and step range on a twin env", "build_id": bid},

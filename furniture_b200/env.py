@@ -161,7 +161,7 @@ class MixedFurnitureEnv:
       obs = env.reset(); obs, rew, done, info = env.step(actions)          # actions: (num_envs, dof)
     """
 
-    def __init__(self, furniture_names, envs_per_model, agent="Sawyer", device=0, object_ob_dim=None, **cfg_overrides):
+    def __init__(self, furniture_names, envs_per_model, agent="Sawyer", device=0, object_ob_dim=None, pad_to=None, **cfg_overrides):
         import torch
 
         self.torch = torch
@@ -174,6 +174,8 @@ class MixedFurnitureEnv:
             self.buckets.append(BatchedFurnitureEnv(agent, name, n, device=device, seed=seed + off, **cfg_overrides))
             self.offsets.append(off)
             off += n
+        self.real_envs = off           # envs that exist; rows beyond them (up to pad_to) are padding for equal-sized shards
+        off = max(off, pad_to or 0)
         self.num_envs = off
         b0 = self.buckets[0]
         self.device, self.act_dim, self.dof, self.robot_ob_dim = b0.device, b0.act_dim, b0.act_dim, b0.robot_ob_dim
@@ -247,16 +249,34 @@ class MixedFurnitureEnv:
             b.close()
 
 
-def shard_furniture(names, envs_per_model, world, nv=None, envs_per_rank=None):
+def model_costs():
+    """measured GPU time per env-step per env (microseconds) of every compiled Sawyer scene: compiled/cost.json, written by
+    tools/calibrate_models.py on a B200; {} when absent"""
+    import json
+    import os
+
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compiled", "cost.json")
+    if not os.path.exists(p):
+        return {}
+    return {k: float(v["us_per_env_step"]) for k, v in json.load(open(p)).items()}
+
+
+def shard_furniture(names, envs_per_model, world, nv=None, envs_per_rank=None, cost_per_env=None):
     """Whole furniture buckets per GPU for a mixed batch ("bucket by furniture id first so each GPU gets
-    whole buckets, balance by sum nv^3"): longest-processing-time greedy on envs * nv^3 (nv from the compiled tables unless
-    given).  Returns, per rank, the list of (name, envs) it owns; every rank computes the same answer.  With `envs_per_rank`
-    the env counts are then re-dealt inside each rank so that every rank holds exactly that many envs (the all-gather of the
-    step needs equal shards): its models share them evenly, the first ones taking the remainder."""
+    whole buckets"): longest-processing-time greedy on the cost of each bucket = envs x cost per env, the cost per env being
+    the measured step time of the model (`cost_per_env`, e.g. model_costs(): the spread between furniture models is 40x and
+    follows contact count and overflow, not nv) or, without measurements, nv^3.  Returns, per rank, the list
+    of (name, envs) it owns; every rank computes the same answer.  With `envs_per_rank` the env counts are re-dealt inside
+    each rank so that every rank holds exactly that many envs (its models share them evenly); without it ranks may own
+    different numbers of envs and the caller pads the shards to the largest."""
     counts = [envs_per_model] * len(names) if isinstance(envs_per_model, int) else list(envs_per_model)
-    if nv is None:
-        nv = [mjcf.load_scene("Sawyer", n).nv for n in names]
-    cost = [c * float(v) ** 3 for c, v in zip(counts, nv)]
+    if cost_per_env is not None and all(n in cost_per_env for n in names):
+        per_env = [float(cost_per_env[n]) for n in names]
+    else:
+        if nv is None:
+            nv = [mjcf.load_scene("Sawyer", n).nv for n in names]
+        per_env = [float(v) ** 3 for v in nv]
+    cost = [c * w for c, w in zip(counts, per_env)]
     order = sorted(range(len(names)), key=lambda i: (-cost[i], names[i]))
     load, owned = [0.0] * world, [[] for _ in range(world)]
     for i in order:
