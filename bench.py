@@ -233,7 +233,7 @@ def run_ours(args):
         from furniture_b200.env import model_costs
 
         per_model = max(1, (n_local * world) // len(names))
-        owned = shard_furniture(names, per_model, world, nv=[models[n].nv for n in names], cost_per_env=model_costs() or None, chunk=256)
+        owned = shard_furniture(names, per_model, world, nv=[models[n].nv for n in names], cost_per_env=model_costs() or None)
         n_real = [sum(c for _, c in o) for o in owned]
         n_local = max(n_real)
         wide = max(7 * len(models[n].meta["part_names"]) for n in names)
@@ -352,7 +352,7 @@ def run_ours(args):
         default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU
         workload = WORKLOAD if default_case else "Furniture%sEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.agent, args.furniture, act_txt)
         if mixed is not None:
-            workload = ("Furniture%sEnv, mixed-furniture batch: %d furniture models (nv %d..%d) x %d envs each, buckets dealt to the GPUs in pieces of <= 256 envs, balanced on measured model cost "
+            workload = ("Furniture%sEnv, mixed-furniture batch: %d furniture models (nv %d..%d) x %d envs each, whole buckets per GPU balanced on measured model cost "
                         "(%s models / %s envs per rank, shards padded to %d rows), one kernel-module instance and stream per bucket, 50 mj_steps per env-step, %s"
                         % (args.agent, mixed["models"], mixed["nv_range"][0], mixed["nv_range"][1], mixed["envs_per_model"], mixed["per_rank"], mixed["envs_per_rank"], n_local, act_txt))
         # measured DRAM traffic and instruction counts come from an ncu capture of exactly this kernel build
