@@ -174,6 +174,8 @@ int fe_create(const void* model_blob, size_t model_bytes, const void* scene_blob
       s[0] = (uint32_t)((cfg->seed + n) & 0xffffffffu);
       for (uint32_t i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + i;
     }
+    if (cfg->furn_size_rand != 0.f) // the reference draws the size factor while loading the model (furniture.py:1989-1991): one double
+      for (size_t n = 0; n < N; ++n) { fe_mt_twist(mt.data() + n * 624); mpos[n] = 2; }
     plat_upload(e.mt, mt.data(), sizeof(uint32_t) * N * 624);
     plat_upload(e.mt_pos, mpos.data(), sizeof(int) * N);
   }

@@ -493,6 +493,7 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
     if (lane == 0) { // UniformRandomSampler.sample (placement_sampler.py:137-190): xy noise, z + 0.01, +furn_rot_rand deg about x
       uint32_t* mt = e->es.mt + (size_t)e->env * FE_MT_N;
       int pos = e->es.mt_pos[e->env];
+      if (cfg->furn_size_rand != 0.f) (void)fe_mt_double(mt, &pos); // _reset draws a size factor first (furniture.py:1428-1431; it only edits the XML tree)
       const double half = 0.5 * (double)cfg->furn_rot_rand * 3.14159265358979323846 / 180.0;
       const double qx[4] = {cos(half), sin(half), 0.0, 0.0};
       const double r_xy = (double)cfg->furn_xyz_rand, r_rot = (double)cfg->furn_rot_rand;

@@ -30,7 +30,7 @@ class FeConfig(C.Structure):
         ("max_episode_steps", i32), ("discrete_grip", i32), ("rescale_actions", i32), ("auto_align", i32),
         ("alignment_pos_dist", f64), ("alignment_rot_dist_up", f64), ("alignment_rot_dist_forward", f64), ("alignment_project_dist", f64),
         ("ctrl_penalty_coef", f32), ("unstable_penalty_coef", f32), ("success_reward", f32), ("touch_reward", f32), ("pick_reward", f32),
-        ("furn_xyz_rand", f32), ("furn_rot_rand", f32), ("agent_xyz_rand", f32), ("seed", C.c_uint64),
+        ("furn_xyz_rand", f32), ("furn_rot_rand", f32), ("agent_xyz_rand", f32), ("furn_size_rand", f32), ("seed", C.c_uint64),
     ]
 
 
@@ -59,7 +59,7 @@ def default_config(**kw):
     c.discrete_grip, c.rescale_actions, c.auto_align = 1, 1, 1
     c.alignment_pos_dist, c.alignment_rot_dist_up, c.alignment_rot_dist_forward, c.alignment_project_dist = 0.1, 0.9, 0.9, 0.3
     c.ctrl_penalty_coef, c.unstable_penalty_coef, c.success_reward, c.touch_reward, c.pick_reward = 1e-3, 100, 100, 10, 100
-    c.furn_xyz_rand, c.furn_rot_rand, c.agent_xyz_rand = 0.02, 3, 0.001
+    c.furn_xyz_rand, c.furn_rot_rand, c.agent_xyz_rand, c.furn_size_rand = 0.02, 3, 0.001, 0.0
     c.seed = 123
     for k, v in kw.items():
         if not hasattr(c, k):

@@ -64,8 +64,15 @@ class BatchedFurnitureEnv:
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         torch.zeros(1, device=self.device)  # make sure the primary context exists before the library binds to it
-        self.model = mjcf.load_scene(agent, furniture_name)
         self.cfg = default_config(**cfg_overrides)
+        # furn_size_rand (config/furniture.py:196-201): the reference draws one size factor per env process while loading the model.
+        # A handle shares one model: the batch takes env 0's factor (the first draw of RandomState(seed)); every env's generator
+        # still spends its draws like the reference's.  Different sizes side by side = several handles (MixedFurnitureEnv).
+        self.resize_factor = None
+        if self.cfg.furn_size_rand != 0:
+            r = float(self.cfg.furn_size_rand)
+            self.resize_factor = 1 + float(np.random.RandomState(int(self.cfg.seed)).uniform(-r, r, 1)[0])
+        self.model = mjcf.load_scene(agent, furniture_name, resize_factor=self.resize_factor)
         self.engine = Engine(self.model, num_envs, device=device, config=self.cfg)
         self.num_envs = num_envs
         self.obs_dim, self.act_dim = self.engine.obs_dim, self.engine.act_dim

@@ -204,7 +204,34 @@ def place_unlisted_parts(part_names, listed, radii, seed):
     return out
 
 
-def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, use_torque=False, placement_seed=123):
+def _rescale_objects(obj_root, mult):
+    """xml_adjusting/rescale.py:30-95 (`rescale`, used by MujocoXMLObject(resize=...), objects.py:136-147): mesh scales of the part
+    meshes, body positions, and every site / geom position and size under the part bodies are multiplied by `mult`; the
+    `*_initpos` numerics and the weld data are left alone, as in the reference."""
+    def mul(sv):
+        return " ".join(str(float(x) * mult) for x in sv.split())
+
+    asset = obj_root.find("asset")
+    if asset is not None:
+        for mesh in asset:
+            if mesh.tag == "mesh" and "part" in mesh.get("name", ""):
+                mesh.set("scale", mul(mesh.get("scale", "1 1 1")))
+    for body in obj_root.find("worldbody"):
+        if "_part" in body.get("name", ""):
+            body.set("pos", mul(body.get("pos", "0 0 0")))
+            for child in body.iter():
+                if child.tag == "site":
+                    child.set("pos", mul(child.get("pos", "0 0 0")))
+                    if child.get("size") is not None:
+                        child.set("size", mul(child.get("size")))
+                elif child.tag == "geom":
+                    if child.get("pos") is not None:
+                        child.set("pos", mul(child.get("pos")))
+                    if child.get("size") is not None:
+                        child.set("size", mul(child.get("size")))
+
+
+def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, use_torque=False, placement_seed=123, resize_factor=None):
     """Returns (xml_string, meta). meta carries what the env layer needs beyond the XML:
     part names in XML document order, *_initpos numerics, horizontal radii, robot/gripper joint names."""
     assets_root = assets_root or default_assets_root()
@@ -304,6 +331,9 @@ def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None,
 
     # furniture parts: furniture.py:1979-2001 + floor_task.py:55-72 + objects.py:186-206
     obj = ET.parse(os.path.join(assets_root, "objects", furniture + ".xml")).getroot()
+    if resize_factor:  # furn_size_rand / manual resize: furniture.py:1985-1992
+        _rescale_objects(obj, float(resize_factor))
+        meta["resize_factor"] = float(resize_factor)
     part_names = [b.get("name") for b in obj.iter("body")]  # base.py:159-167 (root.iter => document order)
     dst_asset = _section(world, "asset")
     for a in list(_section(obj, "asset")):
@@ -1056,13 +1086,15 @@ def _collision_pairs(m):
     return np.array(pairs, dtype=np.int32).reshape(len(pairs), 2)
 
 
-def load_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None):
+def load_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, resize_factor=None):
     """compose + compile if the asset tree is reachable, else the precompiled tables shipped in
-    furniture_b200/compiled/ (made by tools/compile_models.py)."""
+    furniture_b200/compiled/ (made by tools/compile_models.py; unit size only)."""
     root = assets_root or default_assets_root()
     if root is not None:
-        xml, meta = compose_scene(agent, furniture, root)
+        xml, meta = compose_scene(agent, furniture, root, resize_factor=resize_factor)
         return compile_mjcf(xml, meta)
+    if resize_factor:
+        raise FileNotFoundError("a resized scene (furn_size_rand) is composed from the MJCF asset tree: set FURNITURE_ASSETS")
     path = os.path.join(os.path.dirname(__file__), "compiled", "%s_%s.npz" % (agent, furniture))
     if not os.path.exists(path):
         raise FileNotFoundError("no asset tree and no compiled model at " + path)

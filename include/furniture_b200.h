@@ -43,6 +43,8 @@ typedef struct fe_config {
   double alignment_pos_dist, alignment_rot_dist_up, alignment_rot_dist_forward, alignment_project_dist; /* :203-226 */
   float ctrl_penalty_coef, unstable_penalty_coef, success_reward, touch_reward, pick_reward;            /* :291-295 */
   float furn_xyz_rand, furn_rot_rand, agent_xyz_rand; /* :177-194 */
+  float furn_size_rand;      /* :196-201; != 0: every env's generator gives one draw at creation and one per reset to the size factor
+                                (furniture.py:1989-1991, :1428-1431); the geometry itself is fixed by the scene handed to fe_create */
   uint64_t seed;             /* env i draws its resets from numpy's RandomState(seed + i) stream: MT19937 state per env
                                 (fields mt_state / mt_pos), the reference's draw order (furniture.py:72, env/base.py:77) */
 } fe_config;

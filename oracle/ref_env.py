@@ -32,6 +32,7 @@ class Cfg:
     alignment_pos_dist, alignment_rot_dist_up, alignment_rot_dist_forward, alignment_project_dist = 0.1, 0.9, 0.9, 0.3
     ctrl_penalty_coef, unstable_penalty_coef, success_reward, touch_reward, pick_reward = 1e-3, 100.0, 100.0, 10.0, 100.0
     furn_xyz_rand, furn_rot_rand, agent_xyz_rand = 0.02, 3.0, 0.001
+    furn_size_rand = 0.0
     seed = 123
 
 
@@ -54,6 +55,8 @@ class OracleFurnitureEnv:
         self.nr = int(sum(1 for j in range(model.njnt) if model.jnt_type[j] != 0))
         self.dof = self.narm + self.narms + 1
         self.rng = np.random.RandomState(self.cfg.seed)
+        if self.cfg.furn_size_rand != 0:  # _load_model_object draws the size factor first (furniture.py:1989-1991)
+            self.resize_factor = 1 + self.rng.uniform(-self.cfg.furn_size_rand, self.cfg.furn_size_rand, 1)[0]
         g = model.names["geom"]
         self.lf = [[g.index(n) for n in meta["l_finger_geoms"]]] + ([[g.index(n) for n in meta["l_finger_geoms2"]]] if self.narms == 2 else [])
         self.rf = [[g.index(n) for n in meta["r_finger_geoms"]]] + ([[g.index(n) for n in meta["r_finger_geoms2"]]] if self.narms == 2 else [])
@@ -139,6 +142,8 @@ class OracleFurnitureEnv:
 
     def reset(self):
         sim, m, cfg = self.sim, self.m, self.cfg
+        if cfg.furn_size_rand != 0:  # :1428-1431 (edits the XML tree only)
+            self.rng.uniform(-cfg.furn_size_rand, cfg.furn_size_rand, 1)
         sim.reset()
         saved = {g: (sim.geom_contype[g], sim.geom_conaffinity[g]) for g in self.robot_geoms}
         for g in self.robot_geoms:

@@ -139,3 +139,34 @@ def test_unstable_episode_resets_twice_like_the_reference_worker():
     assert np.isfinite(obs).all() and (eng.get("flags")[:, 0] & 8 == 0).all()
     obs, rew, done, info = eng.env_step_host(a)
     assert info[1][3] == 1 and info[0][3] == 2 and not done.any()
+
+
+def test_furn_size_rand_scales_the_scene_and_keeps_the_draw_order():
+    """furn_size_rand (config/furniture.py:196-201): the size factor is the first draw of the env's generator (furniture.py:1989-1991)
+    and every reset spends one more (:1428-1431); xml_adjusting/rescale.py scales geoms, sites and body offsets of the parts"""
+    r, seed = 0.1, 77
+    factor = 1 + np.random.RandomState(seed).uniform(-r, r, 1)[0]
+    m0 = mjcf.load_scene("Sawyer", "table_lack_0825")
+    m = mjcf.load_scene("Sawyer", "table_lack_0825", resize_factor=factor)
+    g0 = m0.names["geom"].index("noviz_collision_4_part4_0") if "noviz_collision_4_part4_0" in m0.names["geom"] else [i for i, n in enumerate(m0.names["geom"]) if "part4" in n][0]
+    assert np.allclose(m.geom_size[g0], m0.geom_size[g0] * factor) and np.allclose(m.geom_pos[g0], m0.geom_pos[g0] * factor)
+    s = [i for i, n in enumerate(m0.names["site"]) if "conn_site" in n][0]
+    assert np.allclose(m.site_pos[s], m0.site_pos[s] * factor)
+    assert np.allclose(m.meta["part_init_qpos"]["4_part4"], m0.meta["part_init_qpos"]["4_part4"])  # *_initpos numerics are not rescaled
+    assert np.array_equal(m.geom_size[m.names["geom"].index("FLOOR")], m0.geom_size[m0.names["geom"].index("FLOOR")])
+    n = 2
+    eng = make_engine(m, n, False, seed=seed, furn_size_rand=r)
+    envs = []
+    for i in range(n):
+        cfg = Cfg()
+        cfg.seed, cfg.furn_size_rand = seed + i, r
+        envs.append(OracleFurnitureEnv(m, cfg))
+    assert abs(envs[0].resize_factor - factor) < 1e-15
+    for k in range(2):
+        eng.env_reset()
+        for i, e in enumerate(envs):
+            e.reset()
+            st = e.rng.get_state()
+            assert eng.get("mt_pos")[i, 0] == st[2] and np.array_equal(eng.get("mt_state")[i], st[1]), (k, i)
+            assert np.abs(eng.get("qpos")[i] - e.sim.qpos).max() < 1e-5
+    eng.close()
