@@ -298,7 +298,7 @@ def shard_furniture(names, envs_per_model, world, nv=None, envs_per_rank=None, c
         r = min(range(world), key=lambda k: (load[k], k))
         load[r] += c * per_env[i]
         got[r][i] = got[r].get(i, 0) + c
-    owned = [[(names[i], c) for i, c in sorted(g.items())] for g in got]
+    owned = [[(names[i], c) for i, c in g.items()] for g in got]  # in the order the buckets were dealt (heaviest first)
     if envs_per_rank is not None:
         for r in range(world):
             k = len(owned[r])
