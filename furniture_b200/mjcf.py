@@ -368,6 +368,11 @@ def compose_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None,
     for eq in list(_section(obj, "equality")):
         _section(world, "equality").append(eq)
     meta["part_names"] = part_names
+    recipe = load_recipe(furniture, assets_root)
+    if recipe is not None:
+        import json
+
+        meta["recipe_json"] = json.dumps(recipe)
     init_qpos.update(place_unlisted_parts(part_names, init_qpos, radii, placement_seed))
     meta["part_init_qpos"] = init_qpos
     meta["part_radius"] = radii
@@ -1084,6 +1089,22 @@ def _collision_pairs(m):
                 continue
             pairs.append((g1, g2))
     return np.array(pairs, dtype=np.int32).reshape(len(pairs), 2)
+
+
+def load_recipe(furniture, assets_root):
+    """the assembly recipe of a furniture model (FurnitureEnv._load_recipe, furniture.py:2033-2044): assets/recipes/<name>.yaml with
+    python/tuple tags read as lists; None when the model has no recipe.  Kept in the compiled scene as JSON (meta["recipe_json"])."""
+    path = os.path.join(assets_root, "recipes", furniture + ".yaml")
+    if not os.path.exists(path):
+        return None
+    import yaml
+
+    class _Loader(yaml.SafeLoader):
+        pass
+
+    _Loader.add_constructor("tag:yaml.org,2002:python/tuple", lambda loader, node: loader.construct_sequence(node))
+    with open(path) as f:
+        return yaml.load(f, Loader=_Loader)
 
 
 def load_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, resize_factor=None):
