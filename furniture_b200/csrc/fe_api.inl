@@ -297,6 +297,46 @@ int fe_set_max_episode_steps(fe_handle* h, int max_episode_steps) {
   return 0;
 }
 
+int fe_dense_info_dim(void) { return FE_DENSE_INFO; }
+size_t fe_dense_recipe_sizeof(void) { return sizeof(fe_dense_recipe); }
+int fe_enable_dense_reward(fe_handle* h, const fe_dense_config* dc) {
+  if (!dc || dc->struct_bytes != (int32_t)sizeof(fe_dense_config)) return fail(h, -1, "fe_enable_dense_reward: fe_dense_config size mismatch");
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_enable_dense_reward: handle was created without a scene blob");
+  const fe_dense_recipe& rc = h->hs.dense;
+  if (rc.nsub <= 0 || rc.nsub > FE_DENSE_MAXSUB) return fail(h, -1, "fe_enable_dense_reward: the scene carries no assembly recipe");
+  if (h->hs.narms != 1) return fail(h, -1, "fe_enable_dense_reward: the dense reward is defined for the one-arm (Sawyer) env");
+  if ((dc->phase_ob != 0) != (h->hs.phase_ob != 0)) return fail(h, -1, "fe_enable_dense_reward: phase_ob disagrees with the scene's obs layout");
+  for (int s = 0; s < rc.nsub; ++s) {
+    const int ids[5] = {rc.leg_site[s], rc.table_site[s], rc.gl_site[s], rc.gr_site[s], rc.griptip_site};
+    for (int k = 0; k < 5; ++k) if (ids[k] < 0 || ids[k] >= h->hm.nsite) return fail(h, -1, "fe_enable_dense_reward: recipe names a site the model does not have");
+    if (rc.leg_part[s] < 0 || rc.leg_part[s] >= h->hm.npart) return fail(h, -1, "fe_enable_dense_reward: recipe names a part the model does not have");
+  }
+  if (rc.grip_site < 0 || rc.grip_site >= h->hm.nsite) return fail(h, -1, "fe_enable_dense_reward: grip_site missing");
+  FeDevScope dev_scope(h);
+  if (!h->es.dense) {
+    fe_dense_config* d = (fe_dense_config*)plat_alloc(sizeof(fe_dense_config));
+    FeDenseState* st = h_alloc<FeDenseState>(h, (size_t)h->N);
+    float* inf = h_alloc<float>(h, (size_t)h->N * FE_DENSE_INFO);
+    if (!d || !st || !inf) return fail(h, -2, "fe_enable_dense_reward: device allocation failed");
+    h->allocs.push_back(d);
+    h->es.dense = d; h->es.dstate = st; h->es.dinfo = inf;
+    add_field(h, "dense_info", inf, FE_DENSE_INFO, (int)sizeof(float), false);
+    add_field(h, "dense_state", st, (int)sizeof(FeDenseState), 1, true);
+  }
+  plat_upload((void*)h->es.dense, dc, sizeof(fe_dense_config));
+  return 0;
+}
+int fe_dense_eval(fe_handle* h, const fe_dense_config* dc, const void* recipe_blob, size_t recipe_bytes, const double* thr4, int n_goal, int n_episodes,
+                  const int32_t* first, const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* site_pos, const double* site_mat,
+                  const double* part_pos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward, uint8_t* done,
+                  double* info) {
+  if (!dc || dc->struct_bytes != (int32_t)sizeof(fe_dense_config)) return fail(h, -1, "fe_dense_eval: fe_dense_config size mismatch");
+  if (!recipe_blob || recipe_bytes != sizeof(fe_dense_recipe)) return fail(h, -1, "fe_dense_eval: recipe blob size mismatch");
+  if (n_episodes <= 0 || n_records <= 0) return 0;
+  return plat_dense_eval(h, dc, (const fe_dense_recipe*)recipe_blob, thr4, n_goal, n_episodes, first, count, n_records, nsite, npart, act_dim, site_pos, site_mat,
+                         part_pos, touch, reset, connected, ac, reward, done, info);
+}
+
 int fe_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles, const int32_t* nangles,
                   const double* thr, uint8_t* aligned, double* tq) {
   if (n <= 0) return 0;

@@ -8,8 +8,9 @@
 //   fe_is_aligned_d  : _is_aligned in float64 with numpy's exact arithmetic (float32 unit_vector, FMA-chain dots)
 #pragma once
 #include "fe_driver.h"
+#include "fe_dense_types.h"
 
-#define FE_SCENE_MAGIC 0x46455343 /* "FESC" */
+#define FE_SCENE_MAGIC 0x46455344 /* "FESD" */
 #define FE_MAXCONN 48
 #define FE_INFO_DIM 6
 
@@ -33,6 +34,8 @@ typedef struct fe_scene {
   int32_t arm_dof[FE_MAXRDOF], grip_dof[8];
   float robot_init_qpos[FE_MAXRDOF]; // arm joints (arm_dof order), then gripper joints (grip_dof order)
   float part_init_pos[FE_MAXPART][3], part_init_quat[FE_MAXPART][4], part_radius[FE_MAXPART];
+  int32_t phase_ob, pad_;      // 1: obs ends with the 8-way one-hot of the dense reward's phase (furniture_sawyer_dense.py:100-117); counted in obs_dim
+  fe_dense_recipe dense;       // assembly recipe for the dense reward (nsub = 0: the furniture has none)
 } fe_scene;
 
 struct FeEnvState {
@@ -45,6 +48,10 @@ struct FeEnvState {
   int* mt_pos;                                 // [N] position in the state (624 = regenerate before the next draw)
   int *robot_contype, *robot_conaff;           // [N][ngeom] saved robot masks during reset
   float* episode_reward;
+  // dense (phase-based) reward, fe_dense.h: NULL = the sparse reward of FurnitureEnv._compute_reward
+  const fe_dense_config* dense;
+  FeDenseState* dstate;                        // [N]
+  float* dinfo;                                // [N][FE_DENSE_INFO]
 };
 
 // ---------------------------------------------------------------- float64 helpers with numpy's arithmetic
@@ -153,6 +160,8 @@ FE_HDN bool fe_is_aligned_d(const double* p1, const double* m1, const double* p2
   return false;
 }
 
+#include "fe_dense.h"
+
 // ---- pyquaternion semantics in float64 (w,x,y,z), used by the connect path (transform_utils.py:633-664)
 FE_HD void dq_mul(double* r, const double* a, const double* b) {
   double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], x = a[1] * b[0] + a[0] * b[1] - a[3] * b[2] + a[2] * b[3];
@@ -244,6 +253,15 @@ FE_HDN void fe_site_pose_d(const FeWarp* w, int site, double* pos, double* mat, 
     for (int k = 0; k < 9; ++k) mat[k] = (double)Mx[k];
   }
 }
+
+// the dense reward's view of the env: poses of the last forward pass, as _get_obs and the connect scan see them
+struct FeSliceWorld {
+  const FeWarp* w;
+  FE_MEMBER void site_pos(int s, double* p) const { fe_site_pose_d(w, s, p, nullptr, nullptr); }
+  FE_MEMBER void site_pose(int s, double* p, double* m) const { fe_site_pose_d(w, s, p, m, nullptr); }
+  FE_MEMBER void part_pos(int q, double* p) const { const float* lp = w->lpos() + 3 * (w->m->nrlink + q); p[0] = (double)lp[0]; p[1] = (double)lp[1]; p[2] = (double)lp[2]; }
+  FE_MEMBER bool touch_both(int q) const { return (w->touch()[q] & 3) == 3; } // _finger_contact(leg): both fingers of the (only) arm
+};
 
 // _stop_object(obj, gravity=gc): xfrc_applied -> gravity-compensation factor, qvel = 0 (furniture.py:2778-2800)
 FE_HD void fe_stop_part(FeWarp* w, int p, float gc) {
@@ -457,6 +475,7 @@ FE_FN void fe_write_obs(FeEnv* e) {
         v3cpy(o + 10, w->lvel() + 6 * l);
       }
     }
+    if (sc->phase_ob && lane < 8) ob[sc->obs_dim - 8 + lane] = (e->es.dstate && e->es.dstate[e->env].phase == lane) ? 1.f : 0.f;
   LANES_END
   }
 }
@@ -568,7 +587,16 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
   LANES_END
   for (int i = 0; i < 100; ++i) fe_fwd_step(e);
   LANES_BEGIN
-    if (lane == 0) { e->es.done[e->env] = 0; if (w->u()[2] & 8) { /* a reset that diverges is reported, not hidden */ } }
+    if (lane == 0) {
+      e->es.done[e->env] = 0;
+      if (e->es.dense) { // FurnitureSawyerDenseRewardEnv._reset: _reset_reward_variables on the settled scene
+        FeSliceWorld world = {w};
+        fe_dense_begin_episode(world, e->es.dense, &sc->dense, e->es.dstate + e->env);
+        float* di = e->es.dinfo + (size_t)e->env * FE_DENSE_INFO;
+        for (int k = 0; k < FE_DENSE_INFO; ++k) di[k] = 0.f;
+        di[0] = (float)e->es.dstate[e->env].phase;
+      }
+    }
   LANES_END
   fe_write_obs(e);
 }
@@ -649,12 +677,27 @@ FE_FN void fe_env_step_one(FeEnv* e, const float* action, float* reward_out, uin
           }
       const int nc = e->es.num_connected[env];
       const float success_r = cfg->success_reward * (float)(nc - e->es.prev_num_connected[env]);
+      const int connected_now = nc != e->es.prev_num_connected[env]; // _connected: a connection was made during this step
       e->es.prev_num_connected[env] = nc;
       float sq = 0.f;
       for (int k = 0; k < sc->act_dim; ++k) sq += a[k] * a[k];
       float reward = success_r + touch_r + pick_r - cfg->ctrl_penalty_coef * sq;
-      const int success = (nc == np - 1 && np > 1) ? 1 : 0;
+      int success = (nc == np - 1 && np > 1) ? 1 : 0;
       int done = success;
+      if (e->es.dense) { // FurnitureSawyerEnv._step: reward, _done, info = _compute_reward(a); done = done or _done (furniture_sawyer.py:66-84)
+        FeSliceWorld world = {w};
+        const double thr[4] = {cfg->alignment_pos_dist, cfg->alignment_rot_dist_up, cfg->alignment_rot_dist_forward, cfg->alignment_project_dist};
+        double ad[FE_MAXU + 2], dr = 0.0, di[FE_DENSE_INFO];
+        for (int k = 0; k < sc->act_dim; ++k) ad[k] = (double)a[k];
+        int dd = 0;
+        FeDenseState* ds = e->es.dstate + env;
+        fe_dense_step(world, e->es.dense, &sc->dense, thr, np - 1, ds, ad, sc->act_dim, connected_now, &dr, &dd, di);
+        reward = (float)dr;
+        success = ds->success;
+        done = done || dd;
+        float* dinf = e->es.dinfo + (size_t)env * FE_DENSE_INFO;
+        for (int k = 0; k < FE_DENSE_INFO; ++k) dinf[k] = (float)di[k];
+      }
       const int len = ++e->es.episode_len[env];
       float penalty = 0.f;
       if (len == cfg->max_episode_steps || fail) { done = 1; if (fail) penalty = -cfg->unstable_penalty_coef; }

@@ -37,6 +37,10 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
 static void plat_copy_d2d(fe_handle* h, void* dst, const void* src, size_t n, void* stream);
 static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles,
                            const int32_t* nangles, const double* thr, uint8_t* aligned, double* tq);
+static int plat_dense_eval(fe_handle* h, const struct fe_dense_config* dc, const struct fe_dense_recipe* rc, const double* thr, int n_goal, int n_episodes,
+                           const int32_t* first, const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* spos, const double* smat,
+                           const double* ppos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward,
+                           uint8_t* done, double* info);
 
 #include "fe_api.inl"
 
@@ -86,7 +90,7 @@ struct FeModule {
   int device;
   FeLayout lay;
   CUmodule mod;
-  CUfunction f_sim, f_step, f_reset, f_order, f_aligned;
+  CUfunction f_sim, f_step, f_reset, f_order, f_aligned, f_dense;
   int users;
 };
 static std::vector<FeModule*> g_modules;
@@ -156,7 +160,7 @@ static int plat_module(fe_handle* h) {
   CUresult r = g_drv.ModuleLoadData(&m->mod, fe_cubin_start);
   if (r != CUDA_SUCCESS) { delete m; return fail(h, -10, "cuModuleLoadData(embedded sm_100a cubin): " + drv_err(r) + " (this library runs on B200 / sm_100a only)"); }
   struct { const char* name; CUfunction* f; } fn[] = {{"fe_sim_kernel", &m->f_sim}, {"fe_env_step_kernel", &m->f_step}, {"fe_env_reset_kernel", &m->f_reset},
-                                                      {"fe_order_kernel", &m->f_order}, {"fe_is_aligned_kernel", &m->f_aligned}};
+                                                      {"fe_order_kernel", &m->f_order}, {"fe_is_aligned_kernel", &m->f_aligned}, {"fe_dense_eval_kernel", &m->f_dense}};
   for (auto& f : fn) {
     r = g_drv.ModuleGetFunction(f.f, m->mod, f.name);
     if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(m->mod); delete m; return fail(h, -10, std::string("cuModuleGetFunction ") + f.name + ": " + drv_err(r)); }
@@ -337,4 +341,49 @@ static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* 
   }
   cudaFree(d_p1); cudaFree(d_m1); cudaFree(d_p2); cudaFree(d_m2); cudaFree(d_cs); cudaFree(d_sn); cudaFree(d_thr); cudaFree(d_tq); cudaFree(d_na); cudaFree(d_al);
   return rc;
+}
+static int plat_dense_eval(fe_handle* h, const fe_dense_config* dc, const fe_dense_recipe* rc, const double* thr, int n_goal, int n_episodes, const int32_t* first,
+                           const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* spos, const double* smat, const double* ppos,
+                           const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward, uint8_t* done, double* info) {
+  DevScope dev(h);
+  if (int rc_ = plat_prepare(h)) return rc_;
+  CudaPlat* p = (CudaPlat*)h->plat;
+  const size_t R = n_records, E = n_episodes;
+  std::vector<void*> bufs;
+  bool bad = false;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes ? bytes : 8) != cudaSuccess) { bad = true; return nullptr; }
+    bufs.push_back(d);
+    if (src && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) bad = true;
+    return d;
+  };
+  void* d_c = up(dc, sizeof(fe_dense_config));
+  void* d_rc = up(rc, sizeof(fe_dense_recipe));
+  void* d_thr = up(thr, 32);
+  void* d_first = up(first, 4 * E);
+  void* d_count = up(count, 4 * E);
+  void* d_spos = up(spos, 24 * R * nsite);
+  void* d_smat = up(smat, 72 * R * nsite);
+  void* d_ppos = up(ppos, 24 * R * npart);
+  void* d_touch = up(touch, R * npart);
+  void* d_reset = up(reset, R);
+  void* d_conn = up(connected, R);
+  void* d_ac = up(ac, 8 * R * act_dim);
+  void* d_rew = up(nullptr, 8 * R);
+  void* d_done = up(nullptr, R);
+  void* d_info = up(nullptr, 8 * R * FE_DENSE_INFO);
+  int rcode = bad ? fail(h, -2, "fe_dense_eval: device allocation / upload failed") : 0;
+  if (!rcode) {
+    void* a[] = {&d_c, &d_rc, &d_thr, &n_goal, &n_episodes, &d_first, &d_count, &nsite, &npart, &act_dim, &d_spos, &d_smat, &d_ppos, &d_touch, &d_reset, &d_conn, &d_ac,
+                 &d_rew, &d_done, &d_info};
+    rcode = launch(h, p->km->f_dense, (n_episodes + 31) / 32, 32, 0, nullptr, a);
+  }
+  if (!rcode) {
+    if (cudaMemcpy(reward, d_rew, 8 * R, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(done, d_done, R, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(info, d_info, 8 * R * FE_DENSE_INFO, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rcode = fail(h, -10, std::string("fe_dense_eval: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  for (void* b : bufs) cudaFree(b);
+  return rcode;
 }

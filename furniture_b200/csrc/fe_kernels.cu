@@ -105,3 +105,11 @@ extern "C" __global__ void fe_is_aligned_kernel(int n, const double* p1, const d
   for (int k = 0; k < 4; ++k) tq[4 * i + k] = set ? q[k] : nanv;
 }
 
+
+extern "C" __global__ void fe_dense_eval_kernel(const fe_dense_config* c, const fe_dense_recipe* rc, const double* thr, int n_goal, int n_episodes, const int32_t* first,
+                                     const int32_t* count, int nsite, int npart, int act_dim, const double* spos, const double* smat, const double* ppos,
+                                     const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward, uint8_t* done, double* info) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_episodes) return;
+  fe_dense_eval_episode(c, rc, thr, n_goal, first[e], count[e], nsite, npart, act_dim, spos, smat, ppos, touch, reset, connected, ac, reward, done, info);
+}

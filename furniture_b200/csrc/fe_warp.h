@@ -16,6 +16,7 @@
 #define FE_FN __device__ __noinline__
 #define FE_HDN __device__ __noinline__
 #define FE_BOTH __host__ __device__ __forceinline__
+#define FE_MEMBER __device__ __forceinline__ /* member functions of device-side helper structs */
 #define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u); (void)lane; {
 #define LANES_END } } __syncwarp();
 // register-only region: touches lane-private values only, so no barrier is needed after it
@@ -30,6 +31,7 @@
 #define FE_FN static
 #define FE_HDN static
 #define FE_BOTH static inline
+#define FE_MEMBER inline
 #define LANES_BEGIN for (int lane = 0; lane < 32; ++lane) { {
 #define LANES_END } }
 #define REGS_BEGIN LANES_BEGIN

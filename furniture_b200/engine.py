@@ -14,12 +14,13 @@ import os
 import numpy as np
 
 from . import mjcf
+from .dense import FeDenseConfig, FeDenseRecipe, dense_config, pack_dense_recipe
 from .engine_model import MAXEQ, MAXPART, MAXRDOF, MAXSITE, MAXU, EngineModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libfurniture_b200.so")
 MAXCONN = 48
-SCENE_MAGIC = 0x46455343
+SCENE_MAGIC = 0x46455344
 INFO_DIM = 6
 i32, f32, f64 = C.c_int32, C.c_float, C.c_double
 
@@ -47,6 +48,7 @@ class FeScene(C.Structure):
         ("arm_dof", i32 * MAXRDOF), ("grip_dof", i32 * 8),
         ("robot_init_qpos", f32 * MAXRDOF),
         ("part_init_pos", (f32 * 3) * MAXPART), ("part_init_quat", (f32 * 4) * MAXPART), ("part_radius", f32 * MAXPART),
+        ("phase_ob", i32), ("pad_", i32), ("dense", FeDenseRecipe),
     ]
 
 
@@ -78,9 +80,10 @@ def auto_maxcon(em: EngineModel) -> int:
     return int(min(128, max(44, 4 * part_geoms + 16)))
 
 
-def build_scene(m: mjcf.Model, em: EngineModel) -> FeScene:
+def build_scene(m: mjcf.Model, em: EngineModel, phase_ob: bool = False) -> FeScene:
     """Integer tables for the connect logic, pre-compiled from the site names, the obs layout and the
-    reset placements."""
+    reset placements; the assembly recipe of the dense reward when the furniture has one.  `phase_ob` appends the dense reward's
+    8-way one-hot phase to the observation (furniture_sawyer_dense.py:100-117)."""
     meta = m.meta
     sc = FeScene()
     sc.magic, sc.struct_bytes = SCENE_MAGIC, C.sizeof(FeScene)
@@ -166,11 +169,24 @@ def build_scene(m: mjcf.Model, em: EngineModel) -> FeScene:
         sc.part_init_quat[p][:] = list(q[3:7])
         sc.part_radius[p] = meta.get("part_radius", {}).get(name, 0.0)
     sc.part_site_start[npart] = k
+    if meta.get("recipe_json") and narms == 1:
+        import json
+
+        sites = m.names["site"]
+        sid = lambda name: sites.index(name) if name in sites else None
+        try:
+            sc.dense = pack_dense_recipe(json.loads(meta["recipe_json"]), sid, parts.index, sid("griptip_site"), sid("grip_site"))
+        except (KeyError, ValueError, TypeError):  # a recipe the scene cannot serve (no grasp-target sites ...): dense reward unavailable, nsub stays 0
+            sc.dense = FeDenseRecipe()
+    if phase_ob:
+        sc.phase_ob = 1
+        sc.obs_dim += 8
     return sc
 
 
 class Engine:
-    def __init__(self, model: mjcf.Model, n_envs: int, device: int = 0, config: FeConfig | None = None, lib_path: str | None = None):
+    def __init__(self, model: mjcf.Model, n_envs: int, device: int = 0, config: FeConfig | None = None, lib_path: str | None = None,
+                 dense: FeDenseConfig | None = None):
         path = lib_path or DEFAULT_LIB
         if not os.path.exists(path):
             raise RuntimeError(
@@ -189,7 +205,7 @@ class Engine:
             raise RuntimeError("furniture_b200: default library is not a CUDA build")
         self.model = model
         self.em = EngineModel(model)
-        self.scene = build_scene(model, self.em)
+        self.scene = build_scene(model, self.em, phase_ob=bool(dense is not None and dense.phase_ob))
         self.cfg = config or default_config()
         if self.cfg.maxcon <= 0:
             self.cfg.maxcon = auto_maxcon(self.em)
@@ -205,6 +221,9 @@ class Engine:
         self.obs_dim, self.act_dim = self.scene.obs_dim, self.scene.act_dim
         for f in ("fe_env_reset", "fe_env_step"):
             getattr(L, f).argtypes = None
+        self.dense = dense
+        if dense is not None:  # FurnitureSawyerDenseRewardEnv: the phase machine replaces the sparse reward inside fe_env_step
+            self._chk(L.fe_enable_dense_reward(self.h, C.byref(dense)))
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -288,6 +307,22 @@ class Engine:
     def set_max_episode_steps(self, n):
         self._chk(self.L.fe_set_max_episode_steps(self.h, int(n)))
         self.cfg.max_episode_steps = int(n)
+
+    def dense_eval(self, dc, recipe, thr, n_goal, first, count, site_pos, site_mat, part_pos, touch, reset, connected, ac):
+        """test hook fe_dense_eval: the device reward machine on explicit poses, episodes [first[e], first[e] + count[e])"""
+        R, nsite = site_pos.shape[:2]
+        npart, act_dim = part_pos.shape[1], ac.shape[1]
+        f = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        first, count = f(first, np.int32), f(count, np.int32)
+        arrs = [f(site_pos, np.float64), f(site_mat, np.float64), f(part_pos, np.float64), f(touch, np.uint8), f(reset, np.uint8), f(connected, np.uint8), f(ac, np.float64)]
+        thr = f(thr, np.float64)
+        rew = np.zeros(R, np.float64)
+        done = np.zeros(R, np.uint8)
+        info = np.zeros((R, self.L.fe_dense_info_dim()), np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._chk(self.L.fe_dense_eval(self.h, C.byref(dc), C.byref(recipe), C.c_size_t(C.sizeof(recipe)), p(thr), int(n_goal), len(first), p(first), p(count), int(R),
+                                       int(nsite), int(npart), int(act_dim), *[p(a) for a in arrs], p(rew), p(done), p(info)))
+        return rew, done, info
 
     def obs_dev_ptr(self):
         return self.L.fe_obs_dev(self.h)

@@ -14,6 +14,9 @@
  *                       _compute_reward, _after_step; VecEnv auto-reset) furniture.py:364-385, :405-449, :1260-1330,
  *                       :926-1153, :847-924, furniture_sawyer.py:66-155, util/subproc_vec_env.py:16-20
  *   fe_is_aligned    <- FurnitureEnv._is_aligned on explicit site poses (test hook)  furniture.py:1057-1153
+ *   fe_enable_dense_reward <- FurnitureSawyerDenseRewardEnv (env id IKEASawyerDense-v0): _compute_reward and the phase machine
+ *                       around it replace the sparse reward inside fe_env_step         furniture_sawyer_dense.py:18-1022
+ *   fe_dense_eval    <- the same reward machine on explicit poses (test hook)          furniture_sawyer_dense.py:225-586
  *
  * Conventions: every function returns 0 on success or a negative code and records a message retrievable with
  * fe_last_error(); a handle is bound to one CUDA device, is not thread-safe, and all work is issued on the stream
@@ -49,10 +52,22 @@ typedef struct fe_config {
                                 (fields mt_state / mt_pos), the reference's draw order (furniture.py:72, env/base.py:77) */
 } fe_config;
 
+/* coefficients of the dense reward: config/furniture_sawyer_dense.py:5-71 (defaults there), ctrl_penalty_coef of config/furniture.py:291 */
+typedef struct fe_dense_config {
+  int32_t struct_bytes; /* sizeof(fe_dense_config), checked */
+  int32_t diff_rew, early_termination, phase_ob, reset_robot_after_attach, pad_;
+  double phase_bonus, ctrl_penalty_coef, eef_forward_dist_coef, eef_up_dist_coef, eef_rot_threshold, gripper_penalty_coef, move_other_part_penalty_coef,
+      drop_penalty_coef, init_eef_pos_dist_coef, move_eef_pos_dist_coef, lower_eef_pos_dist_coef, grasp_dist_coef, lift_z_dist_coef, lift_xy_dist_coef,
+      lift_z_pos_threshold, lift_xy_pos_threshold, align_pos_dist_coef, align_rot_dist_coef, align_pos_threshold, align_rot_threshold, move_pos_dist_coef,
+      move_rot_dist_coef, move_pos_threshold, move_rot_threshold, move_fine_pos_exp_coef, move_fine_pos_dist_coef, move_fine_rot_dist_coef,
+      aligned_bonus_coef;
+} fe_dense_config;
+
 /* sizes of the blobs the host packs (furniture_b200/engine_model.py, furniture_b200/scene.py) */
 size_t fe_model_sizeof(void);
 size_t fe_scene_sizeof(void);
 size_t fe_config_sizeof(void);
+size_t fe_dense_recipe_sizeof(void); /* the recipe block inside the scene blob (fe_dense_recipe, csrc/fe_dense.h) */
 /* 1 if this library drives a CUDA device, 0 for the lane-emulated test build (never shipped) */
 int fe_is_cuda(void);
 
@@ -98,12 +113,27 @@ int fe_env_step_host(fe_handle* h, const float* actions_host, float* obs_host, f
 /* FurnitureGym.set_max_episode_steps -> FurnitureEnv.set_max_episode_steps (furniture_gym.py:35-37, furniture.py:271-272):
    takes effect from the next step */
 int fe_set_max_episode_steps(fe_handle* h, int max_episode_steps);
+/* Switch the handle to the dense reward; call before the first fe_env_reset.  The scene must carry a recipe, and dc->phase_ob must agree
+ * with the scene (the one-hot phase is part of obs_dim).  fe_env_step then returns the dense reward / done / success, and field
+ * "dense_info" holds (n_envs, fe_dense_info_dim()) float32 per step: phase, subtask, phase_bonus, ctrl_penalty, gripper_penalty,
+ * move_other_part_penalty, drop_penalty, touch, drop_leg, table_moved, stable_grip_succ, skips (bit 0 to lift_leg, bit 1 to move_leg_fine). */
+int fe_enable_dense_reward(fe_handle* h, const fe_dense_config* dc);
+int fe_dense_info_dim(void);
 /* device pointer of the internal obs buffer after the last step/reset: (n_envs, obs_dim) float32 */
 const float* fe_obs_dev(const fe_handle* h);
 
 /* ---- test hook: the device _is_aligned on explicit site poses (float64), n independent cases */
 int fe_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles /* (n,4) */,
                   const int32_t* nangles, const double* thr /* (n,4) */, uint8_t* aligned_host, double* target_quat_host /* (n,4) wxyz, NaN if unset */);
+
+/* ---- test hook: the device reward machine on explicit poses.  Records [first[e], first[e] + count[e]) form episode e and are walked in
+ * order by one thread; a record with reset != 0 starts the episode on the world it shows.  Per record: site_pos (nsite,3), site_mat
+ * (nsite,9 row-major), part_pos (npart,3), touch (npart: both fingers on the part), connected, ac (act_dim).  The ids inside the recipe
+ * blob index these arrays.  Outputs per record: reward, done (bit 0 done, bit 1 success), info (fe_dense_info_dim() doubles). */
+int fe_dense_eval(fe_handle* h, const fe_dense_config* dc, const void* recipe_blob, size_t recipe_bytes, const double* thr4, int n_goal, int n_episodes,
+                  const int32_t* first, const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* site_pos,
+                  const double* site_mat, const double* part_pos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac,
+                  double* reward_host, uint8_t* done_host, double* info_host);
 
 #ifdef __cplusplus
 }

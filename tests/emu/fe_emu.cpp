@@ -28,6 +28,11 @@ static void plat_copy_d2d(fe_handle*, void* dst, const void* src, size_t n, void
 static int plat_is_aligned(fe_handle* h, int n, const double* p1, const double* m1, const double* p2, const double* m2, const double* angles,
                            const int32_t* nangles, const double* thr, uint8_t* aligned, double* tq);
 
+static int plat_dense_eval(fe_handle* h, const struct fe_dense_config* dc, const struct fe_dense_recipe* rc, const double* thr, int n_goal, int n_episodes,
+                           const int32_t* first, const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* spos, const double* smat,
+                           const double* ppos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward,
+                           uint8_t* done, double* info);
+
 #include "../../furniture_b200/csrc/fe_api.inl"
 
 static int plat_run_sim(fe_handle* h, int nsub, int mode, void*) {
@@ -79,5 +84,12 @@ static int plat_is_aligned(fe_handle*, int n, const double* p1, const double* m1
     aligned[i] = fe_is_aligned_d(p1 + 3 * i, m1 + 9 * i, p2 + 3 * i, m2 + 9 * i, nangles[i], cs, sn, thr + 4 * i, q, &set) ? 1 : 0;
     for (int k = 0; k < 4; ++k) tq[4 * i + k] = set ? q[k] : NAN;
   }
+  return 0;
+}
+static int plat_dense_eval(fe_handle*, const fe_dense_config* dc, const fe_dense_recipe* rc, const double* thr, int n_goal, int n_episodes, const int32_t* first,
+                           const int32_t* count, int, int nsite, int npart, int act_dim, const double* spos, const double* smat, const double* ppos,
+                           const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward, uint8_t* done, double* info) {
+  for (int e = 0; e < n_episodes; ++e)
+    fe_dense_eval_episode(dc, rc, thr, n_goal, first[e], count[e], nsite, npart, act_dim, spos, smat, ppos, touch, reset, connected, ac, reward, done, info);
   return 0;
 }

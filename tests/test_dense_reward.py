@@ -102,3 +102,92 @@ def test_oracle_reproduces_the_reference_reward_machine(golden):
         assert orc.phase == int(g["phase"][t]), t
         assert orc.subtask == int(g["subtask"][t]), t
     assert int(np.sum(g["success"])) > 20 and len(set(g["phase"].tolist())) == 8  # the script did reach every phase and finish episodes
+
+
+# ------------------------------------------------------------------ the device machine on the same records
+def _device_inputs(g, recipes):
+    """golden records -> the arrays of fe_dense_eval; site ids: leg_site s, table_site 8+s, g_l 16+s, g_r 24+s, griptip 32, grip_site 33"""
+    n = len(g["reward"])
+    spos = np.zeros((n, 34, 3))
+    smat = np.zeros((n, 34, 9))
+    for k, (pk, mk) in enumerate((("leg_site_pos", "leg_site_mat"), ("table_site_pos", "table_site_mat"), ("gl", None), ("gr", None))):
+        spos[:, 8 * k : 8 * k + 4] = g[pk]
+        if mk:
+            smat[:, 8 * k : 8 * k + 4] = g[mk]
+    spos[:, 32] = g["eef"]
+    smat[:, 33] = g["grip_mat"]
+    touch = (g["touchL"] & g["touchR"]).astype(np.uint8)
+    return spos, smat, g["leg_pos"], touch
+
+
+def _packed_recipe(recipe):
+    from furniture_b200.dense import pack_dense_recipe
+
+    ids = {}
+    for s, (leg, _) in enumerate(recipe["recipe"]):
+        ids[recipe["site_recipe"][s][0]] = s
+        ids[recipe["site_recipe"][s][1]] = 8 + s
+        for k in range(len(recipe["recipe"])):
+            ids["%s_ltgt_site%d" % (leg, k)] = 16 + s
+            ids["%s_rtgt_site%d" % (leg, k)] = 24 + s
+    legs = [r[0] for r in recipe["recipe"]]
+    return pack_dense_recipe(recipe, ids.get, legs.index, 32, 33)
+
+
+def _check_device_machine(eng, golden):
+    from furniture_b200.dense import dense_config
+
+    g = {k: golden[k] for k in golden.files}
+    recipes = [json.loads(str(r)) for r in g["recipe_json"]]
+    spos, smat, ppos, touch = _device_inputs(g, recipes)
+    starts = np.flatnonzero(g["is_reset"])
+    ends = np.append(starts[1:], len(g["reward"]))
+    thr = [0.02, 0.99, 0.99, 0.0]
+    groups = {}
+    for e, (a, b) in enumerate(zip(starts, ends)):
+        key = (int(g["ep_recipe"][e]),) + tuple(bool(g["ep_" + k][e]) for k in ("diff_rew", "early_termination", "phase_ob", "reset_robot_after_attach"))
+        groups.setdefault(key, []).append((a, b - a))
+    checked = 0
+    for key, eps in groups.items():
+        recipe = recipes[key[0]]
+        cfg = golden_cfg(g, int(g["episode"][eps[0][0]]))
+        dc = dense_config(**{k: v for k, v in cfg.items() if not k.startswith("alignment")})
+        rc = _packed_recipe(recipe)
+        first, count = [a for a, _ in eps], [c for _, c in eps]
+        rew, done, info = eng.dense_eval(dc, rc, thr, len(recipe["recipe"]), first, count, spos, smat, ppos, touch, g["is_reset"], g["connected"], g["ac"])
+        for a, c in eps:
+            sl = slice(a, a + c)
+            assert np.array_equal(info[sl, 0].astype(int), g["phase"][sl]), key
+            assert np.array_equal(info[sl, 1].astype(int), g["subtask"][sl]), key
+            assert np.array_equal(done[sl] & 1, g["done"][sl].astype(np.uint8)), key
+            assert np.array_equal((done[sl] >> 1) & 1, g["success"][sl].astype(np.uint8)), key
+            ref = g["reward"][sl]
+            assert np.array_equal(np.isnan(ref), np.isnan(rew[sl])), key
+            ok = ~np.isnan(ref)
+            assert np.all(np.abs(rew[sl][ok] - ref[ok]) <= 1e-11 * np.maximum(1.0, np.abs(ref[ok]))), (key, np.max(np.abs(rew[sl][ok] - ref[ok])))
+            # info columns shared with the golden: phase_bonus ... stable_grip_succ, then the two skip flags as bits
+            gi = g["info"][sl]
+            step = ~g["is_reset"][sl]
+            for col, name in enumerate(D.INFO_KEYS[:9]):
+                want, got = gi[step, col], info[sl][step, 2 + col]
+                assert np.allclose(got, want, rtol=1e-11, atol=1e-11, equal_nan=True), (key, name)
+            assert np.array_equal(info[sl][step, 11].astype(int), (gi[step, 9] + 2 * gi[step, 10]).astype(int)), key
+            checked += c
+    assert checked == len(g["reward"])
+
+
+def test_device_reward_machine_matches_the_reference_emu(golden):
+    from furniture_b200 import mjcf
+    from parity_util import make_engine
+
+    eng = make_engine(mjcf.load_scene("None", "table_lack_0825"), 1, False)
+    _check_device_machine(eng, golden)
+
+
+@pytest.mark.gpu
+def test_device_reward_machine_matches_the_reference_cuda(golden):
+    from furniture_b200 import mjcf
+    from parity_util import make_engine
+
+    eng = make_engine(mjcf.load_scene("None", "table_lack_0825"), 1, True)
+    _check_device_machine(eng, golden)
