@@ -591,10 +591,7 @@ FE_FN void fe_env_reset_one(FeEnv* e) {
       e->es.done[e->env] = 0;
       if (e->es.dense) { // FurnitureSawyerDenseRewardEnv._reset: _reset_reward_variables on the settled scene
         FeSliceWorld world = {w};
-        fe_dense_begin_episode(world, e->es.dense, &sc->dense, e->es.dstate + e->env);
-        float* di = e->es.dinfo + (size_t)e->env * FE_DENSE_INFO;
-        for (int k = 0; k < FE_DENSE_INFO; ++k) di[k] = 0.f;
-        di[0] = (float)e->es.dstate[e->env].phase;
+        fe_dense_begin_episode(world, e->es.dense, &sc->dense, e->es.dstate + e->env); // dense_info keeps the last step's terms (the terminal step's, after an auto-reset)
       }
     }
   LANES_END

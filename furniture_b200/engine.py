@@ -251,14 +251,14 @@ class Engine:
 
     def get(self, name):
         dim, eb = self.field_info(name)
-        dt = np.uint64 if eb == 8 else (np.uint32 if name == "mt_state" else (np.int32 if name in self._INT else np.float32))
+        dt = np.uint8 if eb == 1 else np.uint64 if eb == 8 else (np.uint32 if name == "mt_state" else (np.int32 if name in self._INT else np.float32))
         out = np.empty((self.N, dim), dtype=dt)
         self._chk(self.L.fe_get_field(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
         return out
 
     def set(self, name, value):
         dim, eb = self.field_info(name)
-        dt = np.uint64 if eb == 8 else (np.uint32 if name == "mt_state" else (np.int32 if name in self._INT else np.float32))
+        dt = np.uint8 if eb == 1 else np.uint64 if eb == 8 else (np.uint32 if name == "mt_state" else (np.int32 if name in self._INT else np.float32))
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), (self.N, dim)))
         self._chk(self.L.fe_set_field(self.h, name.encode(), v.ctypes.data_as(C.c_void_p), C.c_size_t(v.nbytes)))
 

@@ -16,10 +16,13 @@ from collections import OrderedDict
 import numpy as np
 
 from . import mjcf
+from .dense import DENSE_DEFAULTS, DENSE_ENV_DEFAULTS, INFO_KEYS as DENSE_INFO_KEYS, dense_config
 from .engine import INFO_DIM, Engine, default_config
 
 INFO_KEYS = ("num_connected", "episode_success", "episode_unstable", "episode_length", "ncon", "solver_iters")
-ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer", "IKEABaxter-v0": "Baxter", "FurnitureBaxterEnv": "Baxter"}
+ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer", "IKEABaxter-v0": "Baxter", "FurnitureBaxterEnv": "Baxter",
+           "IKEASawyerDense-v0": "Sawyer", "furniture-sawyer-densereward-v0": "Sawyer", "FurnitureSawyerDenseRewardEnv": "Sawyer"}
+DENSE_IDS = {"IKEASawyerDense-v0", "furniture-sawyer-densereward-v0", "FurnitureSawyerDenseRewardEnv"}  # env/__init__.py:103-114
 # furniture_id -> name: the reference numbers the sorted objects/*.xml (furniture/env/models/__init__.py:11-19)
 FURNITURE_NAMES = (
     "bed_dalselv_0270 bench_bjoderna_0208 bench_bjursta_0210 block bookcase_agerum_0006 bookcase_besta_0165 bookcase_besta_0170 bookcase_besta_0172 "
@@ -54,8 +57,24 @@ def split_config(config):
     return name or "table_lack_0825", over, ignored
 
 
+def split_dense_config(config):
+    """Config of a dense-reward env id (config/furniture_sawyer_dense.py) -> (furniture name, FeConfig overrides, dense coefficient
+    overrides, ignored keys).  What that file changes in the base env (150 steps, table_lack_0825, auto_align off, the tight
+    alignment thresholds) is the default here too; explicit keys of `config` win."""
+    cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
+    merged = dict(DENSE_ENV_DEFAULTS)
+    merged.update({k: v for k, v in cfg.items() if v is not None})
+    name, over, ignored = split_config(merged)
+    dense = {k: merged[k] for k in DENSE_DEFAULTS if k in merged}
+    if "ctrl_penalty_coef" in over:
+        dense["ctrl_penalty_coef"] = over["ctrl_penalty_coef"]
+    return name, over, dense, [k for k in ignored if k not in DENSE_DEFAULTS]
+
+
 class BatchedFurnitureEnv:
-    def __init__(self, agent="Sawyer", furniture_name="table_lack_0825", num_envs=1, device=0, **cfg_overrides):
+    def __init__(self, agent="Sawyer", furniture_name="table_lack_0825", num_envs=1, device=0, dense=None, **cfg_overrides):
+        """`dense`: None for the sparse reward of FurnitureEnv; a dict of coefficient overrides (possibly empty) for the phase-based
+        reward of FurnitureSawyerDenseRewardEnv, computed inside the step kernel (furniture_b200/dense.py)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -73,12 +92,14 @@ class BatchedFurnitureEnv:
             r = float(self.cfg.furn_size_rand)
             self.resize_factor = 1 + float(np.random.RandomState(int(self.cfg.seed)).uniform(-r, r, 1)[0])
         self.model = mjcf.load_scene(agent, furniture_name, resize_factor=self.resize_factor)
-        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg)
+        self.dense_cfg = dense_config(**dense) if dense is not None else None
+        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg, dense=self.dense_cfg)
         self.num_envs = num_envs
         self.obs_dim, self.act_dim = self.engine.obs_dim, self.engine.act_dim
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
+        self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self.dof = self.act_dim
         self._obs = torch.empty((num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         self._rew = torch.empty(num_envs, dtype=torch.float32, device=self.device)
@@ -89,14 +110,28 @@ class BatchedFurnitureEnv:
     # spaces, in the reference's terms (furniture.py:215-252, :293-310)
     @property
     def observation_space(self):
-        return OrderedDict(object_ob=(self.object_ob_dim,), robot_ob=(self.robot_ob_dim,))
+        sp = OrderedDict(object_ob=(self.object_ob_dim,), robot_ob=(self.robot_ob_dim,))
+        if self.phase_ob_dim:
+            sp["phase_ob"] = (8,)  # furniture_sawyer_dense.py:100-109
+        return sp
 
     @property
     def action_space(self):
         return OrderedDict(default=(self.act_dim,))
 
     def _obs_dict(self, obs):
-        return OrderedDict(object_ob=obs[:, : self.object_ob_dim], robot_ob=obs[:, self.object_ob_dim :])
+        a, b = self.object_ob_dim, self.object_ob_dim + self.robot_ob_dim
+        d = OrderedDict(object_ob=obs[:, :a], robot_ob=obs[:, a:b])
+        if self.phase_ob_dim:
+            d["phase_ob"] = obs[:, b:]
+        return d
+
+    def dense_infos(self):
+        """per env, the dense reward's view of the last step (a host copy): phase, subtask, phase_bonus, the penalty terms ..."""
+        if self.dense_cfg is None:
+            raise RuntimeError("this env runs the sparse reward")
+        rows = self.engine.get("dense_info")
+        return tuple({k: float(r[j]) for j, k in enumerate(DENSE_INFO_KEYS)} for r in rows)
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -125,7 +160,7 @@ class BatchedFurnitureEnv:
     def step_host(self, actions_np):
         """numpy in / numpy out through fe_env_step_host (pinned staging, copies inside the call)."""
         obs, rew, done, info = self.engine.env_step_host(actions_np)
-        return OrderedDict(object_ob=obs[:, : self.object_ob_dim], robot_ob=obs[:, self.object_ob_dim :]), rew, done.astype(bool), info
+        return self._obs_dict(obs), rew, done.astype(bool), info
 
     def infos(self):
         info = self._info.cpu().numpy()
@@ -150,8 +185,12 @@ def make_vec_env(env_id="IKEASawyer-v0", num_env=1, config=None, device=0):
     agent = ENV_IDS.get(env_id)
     if agent is None:
         raise ValueError("unknown env id %s (this build accelerates %s)" % (env_id, sorted(ENV_IDS)))
-    furniture, over, ignored = split_config(config)
-    env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, **over)
+    if env_id in DENSE_IDS:
+        furniture, over, dense, ignored = split_dense_config(config)
+        env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, dense=dense, **over)
+    else:
+        furniture, over, ignored = split_config(config)
+        env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, **over)
     env.ignored_config = ignored
     return env
 

@@ -23,7 +23,7 @@ import numpy as np
 from . import mjcf
 from .engine import Engine, default_config
 
-AGENTS = {"FurnitureSawyerEnv": "Sawyer", "IKEASawyer-v0": "Sawyer", "Sawyer": "Sawyer", "FurnitureBaxterEnv": "Baxter", "IKEABaxter-v0": "Baxter", "Baxter": "Baxter"}
+AGENTS = {"FurnitureSawyerDenseRewardEnv": "Sawyer", "IKEASawyerDense-v0": "Sawyer", "furniture-sawyer-densereward-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer", "IKEASawyer-v0": "Sawyer", "Sawyer": "Sawyer", "FurnitureBaxterEnv": "Baxter", "IKEABaxter-v0": "Baxter", "Baxter": "Baxter"}
 
 
 class FurnitureGymB200:
@@ -32,19 +32,26 @@ class FurnitureGymB200:
     def __init__(self, name="FurnitureSawyerEnv", furniture_name=None, device=0, lib_path=None, id=None, **config):
         """`id`, `name` and the remaining keywords are what gym passes from the registration (env/__init__.py:19-114: id, name,
         furniture_name / furniture_id, background, port ...); options of the renderer are ignored, see env.split_config"""
-        from .env import split_config
+        from .dense import dense_config
+        from .env import DENSE_IDS, split_config, split_dense_config
 
         if name not in AGENTS:
             raise ValueError("unknown env %s (this build accelerates %s)" % (name, sorted(AGENTS)))
         if furniture_name is not None:
             config["furniture_name"] = furniture_name
-        furniture_name, over, self.ignored_config = split_config(config)
+        self.dense_cfg = None
+        if name in DENSE_IDS:  # FurnitureSawyerDenseRewardEnv: the phase-based reward, computed inside the step kernel
+            furniture_name, over, dense, self.ignored_config = split_dense_config(config)
+            self.dense_cfg = dense_config(**dense)
+        else:
+            furniture_name, over, self.ignored_config = split_config(config)
         self.model = mjcf.load_scene(AGENTS[name], furniture_name)
         self.cfg = default_config(**over)
-        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path)
+        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path, dense=self.dense_cfg)
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
+        self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self.dof = self.engine.act_dim
         self._max_episode_steps = self.cfg.max_episode_steps
         self._pending_ob = None  # observation of an episode the device has already started
@@ -55,6 +62,8 @@ class FurnitureGymB200:
     @property
     def observation_space(self):
         shapes = OrderedDict(object_ob=(self.object_ob_dim,), robot_ob=(self.robot_ob_dim,))
+        if self.phase_ob_dim:
+            shapes["phase_ob"] = (8,)
         try:
             import gym.spaces as sp
 
@@ -72,7 +81,11 @@ class FurnitureGymB200:
             return OrderedDict(default=dict(shape=(self.dof,), low=-1.0, high=1.0))
 
     def _ob(self, obs_row):
-        return OrderedDict(object_ob=obs_row[: self.object_ob_dim].astype(np.float64), robot_ob=obs_row[self.object_ob_dim :].astype(np.float64))
+        a, b = self.object_ob_dim, self.object_ob_dim + self.robot_ob_dim
+        ob = OrderedDict(object_ob=obs_row[:a].astype(np.float64), robot_ob=obs_row[a:b].astype(np.float64))
+        if self.phase_ob_dim:
+            ob["phase_ob"] = obs_row[b:].astype(np.float64)
+        return ob
 
     def reset(self):
         if self._pending_ob is not None:
@@ -95,6 +108,11 @@ class FurnitureGymB200:
         self._episode_reward += reward
         out = OrderedDict()
         ob = self._ob(obs[0])
+        if self.dense_cfg is not None:  # the step's reward terms (_compute_reward's info, furniture_sawyer_dense.py:574-586)
+            from .dense import INFO_KEYS
+
+            row = self.engine.get("dense_info")[0]
+            out.update((k, float(v)) for k, v in zip(INFO_KEYS, row))
         if done:
             unstable = int(info[0][2])
             out["episode_success"] = int(info[0][1])
@@ -138,7 +156,9 @@ def register_gym_envs():
             from gymnasium.envs.registration import register
         except Exception:
             return []
-    specs = {"IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050},
+    specs = {"IKEASawyerDense-v0": {"id": "IKEASawyerDense-v0", "name": "FurnitureSawyerDenseRewardEnv", "unity": False},
+             "furniture-sawyer-densereward-v0": {"id": "IKEASawyerDense-v0", "name": "FurnitureSawyerDenseRewardEnv", "unity": False},
+             "IKEASawyer-v0": {"id": "IKEASawyer-v0", "name": "FurnitureSawyerEnv", "furniture_name": "swivel_chair_0700", "background": "Industrial", "port": 1050},
              "IKEABaxter-v0": {"id": "IKEABaxter-v0", "name": "FurnitureBaxterEnv", "furniture_id": 1, "background": "Interior", "port": 1050}}
     done = []
     try:  # the Cursor agent is host logic over the simulator surface (furniture_b200/cursor_env.py)

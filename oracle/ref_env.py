@@ -344,6 +344,16 @@ class OracleFurnitureEnv:
                 self.connected_body1 = None
                 self._fwd_step()
         ob = self.obs()
+        reward, done, success = self._compute_reward(raw, fail)
+        self.episode_len += 1
+        if self.episode_len == self.cfg.max_episode_steps or fail:
+            done = True
+            if fail:
+                reward -= self.cfg.unstable_penalty_coef
+        info = dict(num_connected=self.num_connected, success=int(success), unstable=int(fail), episode_length=self.episode_len)
+        return ob, reward, done, info
+
+    def _compute_reward(self, raw, fail):  # FurnitureEnv._compute_reward, furniture.py:482-541
         touch_r = pick_r = 0.0
         if not fail:
             bits = self.touch_bits()
@@ -359,11 +369,79 @@ class OracleFurnitureEnv:
         self.prev_num_connected = self.num_connected
         reward = success_r + touch_r + pick_r - self.cfg.ctrl_penalty_coef * float(np.square(raw).sum())
         success = self.num_connected == self.npart - 1 and self.npart > 1
-        done = success
-        self.episode_len += 1
-        if self.episode_len == self.cfg.max_episode_steps or fail:
-            done = True
-            if fail:
-                reward -= self.cfg.unstable_penalty_coef
-        info = dict(num_connected=self.num_connected, success=int(success), unstable=int(fail), episode_length=self.episode_len)
-        return ob, reward, done, info
+        return reward, success, success
+
+
+class DenseCfg(Cfg):  # what config/furniture_sawyer_dense.py:5-14 changes in the base env
+    max_episode_steps = 150
+    auto_align = False
+    alignment_pos_dist, alignment_rot_dist_up, alignment_rot_dist_forward, alignment_project_dist = 0.02, 0.99, 0.99, 0.0
+
+
+class SimWorld:
+    """the oracle simulator seen through the names the dense reward asks for (FurnitureEnv._get_pos / _get_up_vector /
+    _get_forward_vector, furniture.py:3121-3200; FurnitureSawyerEnv._finger_contact, furniture_sawyer.py:220-243)"""
+
+    def __init__(self, env):
+        self.e = env
+
+    def pos(self, name):
+        m, sim = self.e.m, self.e.sim
+        if name in m.names["body"]:
+            b = m.names["body"].index(name)
+            return np.array(sim.xpos[3 * b : 3 * b + 3])
+        s = m.names["site"].index(name)
+        return np.array(sim.site_xpos[3 * s : 3 * s + 3])
+
+    def _mat(self, name):
+        s = self.e.m.names["site"].index(name)
+        return np.array(self.e.sim.site_xmat[9 * s : 9 * s + 9]).reshape(3, 3)
+
+    def up(self, name):
+        return self._mat(name)[:, 2].copy()
+
+    def forward(self, name):
+        return self._mat(name)[:, 1].copy()
+
+    def finger_contact(self, leg):
+        e = self.e
+        bits = e.touch_bits()[e.parts.index(leg)]
+        return bool(bits & 1), bool(bits & 2)
+
+
+class OracleDenseEnv(OracleFurnitureEnv):
+    """FurnitureSawyerDenseRewardEnv (furniture_sawyer_dense.py): the Sawyer env with the reward machine of oracle/dense_oracle.py"""
+
+    def __init__(self, model, cfg=None, dense_cfg=None):
+        import json
+
+        from .dense_oracle import DenseOracle
+
+        super().__init__(model, cfg or DenseCfg())
+        c = self.cfg
+        dc = dict(dense_cfg or {})
+        dc.update(ctrl_penalty_coef=c.ctrl_penalty_coef, alignment_pos_dist=c.alignment_pos_dist, alignment_rot_dist_up=c.alignment_rot_dist_up,
+                  alignment_rot_dist_forward=c.alignment_rot_dist_forward, alignment_project_dist=c.alignment_project_dist)
+        self.dense = DenseOracle(SimWorld(self), json.loads(model.meta["recipe_json"]), dc, success_num_conn=self.npart - 1)
+
+    def obs(self):
+        ob = super().obs()
+        if self.dense.c["phase_ob"] and hasattr(self.dense, "phase"):
+            ob = np.concatenate([ob, np.eye(8)[self.dense.phase]])
+        return ob
+
+    def reset(self):
+        super().reset()
+        self.dense.begin_episode()
+        return self.obs()
+
+    def step(self, action):
+        ob, reward, done, info = super().step(action)
+        return self.obs(), reward, done, info  # the phase one-hot follows the phase after the reward (furniture_sawyer_dense.py:119-126)
+
+    def _compute_reward(self, raw, fail):
+        connected = self.num_connected != self.prev_num_connected  # _connected: _connect ran during this step
+        self.prev_num_connected = self.num_connected
+        reward, done, self.dense_info = self.dense.step(np.asarray(raw, dtype=np.float64), connected)
+        base_done = self.num_connected == self.npart - 1 and self.npart > 1  # FurnitureEnv._step, furniture.py:438-445
+        return reward, bool(done or base_done), self.dense.success

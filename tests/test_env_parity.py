@@ -113,14 +113,14 @@ def test_env_reset_and_step_swivel_chair(swivel_model, gpu):
             assert abs(rew[i] - r) < 1e-5 and bool(done[i]) == d
 
 
-def _grasp_and_align_state(m, env):
-    """state in which leg 0 sits between the finger tips (1 mm interpenetration on both sides) and the table top is
-    placed so that its connector 'table-leg..conn_site1' coincides with the leg's 'leg-table..conn_site1'."""
+def _grasp_and_align_state(m, env, leg=0, leg_site="leg-table,0,90,180,270,conn_site1", table_site="table-leg,0,90,180,270,conn_site1", arm_qpos=None):
+    """state in which leg `leg` sits between the finger tips (1 mm interpenetration on both sides) and the table top is
+    placed so that its connector `table_site` coincides with the leg's `leg_site`."""
     sim = env.sim
     sim.reset()
     for p, name in enumerate(env.parts):
         sim.qpos[env.part_qadr[p] : env.part_qadr[p] + 7] = m.meta["part_init_qpos"][name]
-    sim.qpos[:7] = m.meta["robot_init_qpos"]
+    sim.qpos[:7] = m.meta["robot_init_qpos"] if arm_qpos is None else arm_qpos
     gl, gr = m.names["geom"].index("l_fingertip_g0"), m.names["geom"].index("r_fingertip_g0")
 
     def tips(g):
@@ -149,11 +149,11 @@ def _grasp_and_align_state(m, env):
     Rz = np.array([[np.cos(tz), -np.sin(tz), 0], [np.sin(tz), np.cos(tz), 0], [0, 0, 1]])
     R = R @ Ry @ Rz
     leg_q = np.concatenate([0.5 * (cl + cr), mjcf.mat_to_q(R)])
-    s1 = m.names["site"].index("leg-table,0,90,180,270,conn_site1")
-    s2 = m.names["site"].index("table-leg,0,90,180,270,conn_site1")
+    s1 = m.names["site"].index(leg_site)
+    s2 = m.names["site"].index(table_site)
     site1_world = leg_q[:3] + R @ m.site_pos[s1]
     table_q = np.concatenate([site1_world - R @ m.site_pos[s2], mjcf.mat_to_q(R)])
-    sim.qpos[env.part_qadr[0] : env.part_qadr[0] + 7] = leg_q
+    sim.qpos[env.part_qadr[leg] : env.part_qadr[leg] + 7] = leg_q
     sim.qpos[env.part_qadr[4] : env.part_qadr[4] + 7] = table_q
     return sim.qpos.copy()
 

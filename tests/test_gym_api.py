@@ -111,3 +111,33 @@ def test_demo_files_have_the_reference_recorder_format(tmp_path):
     assert list(demo["obs"][0].keys()) == ["object_ob", "robot_ob"] and demo["states"][0]["qpos"].shape == (44,)
     states = load_init_states(paths[0])
     assert len(states) == 4 and states[3]["qvel"].shape == (39,)
+
+
+def test_dense_reward_env_id_through_the_gym_surface():
+    """gym.make("IKEASawyerDense-v0") of the reference builds FurnitureGym(name="FurnitureSawyerDenseRewardEnv", unity=False)
+    (env/__init__.py:103-114); the same kwargs here: config/furniture_sawyer_dense.py's defaults, the phase one-hot on request, the
+    reward terms in info, and an episode of 150 steps at most."""
+    from furniture_b200.env import split_dense_config
+
+    name, over, dense, ignored = split_dense_config(dict(phase_bonus=1000.0, early_termination=True, port=1050))
+    assert name == "table_lack_0825" and over["max_episode_steps"] == 150 and over["auto_align"] is False and over["alignment_pos_dist"] == 0.02
+    assert dense == dict(phase_bonus=1000.0, early_termination=True) and ignored == ["port"]
+    env = FurnitureGymB200(name="FurnitureSawyerDenseRewardEnv", id="IKEASawyerDense-v0", unity=False, lib_path=build_emu(), nsub=2, phase_ob=True,
+                           max_episode_steps=3)
+    assert list(env.observation_space) == ["object_ob", "robot_ob", "phase_ob"] if isinstance(env.observation_space, dict) else True
+    ob = env.reset()
+    assert ob["phase_ob"].tolist() == [0, 1, 0, 0, 0, 0, 0, 0]  # first leg of table_lack: straight to move_eef_above_leg
+    a = np.zeros(env.dof)
+    a[-2] = -1.0
+    total = 0.0
+    for t in range(3):
+        ob, r, done, info = env.step(a)
+        total += r
+        assert info["phase"] == 1 and info["subtask"] == 0 and info["gripper_penalty"] == 1.0 and info["ctrl_penalty"] == 0.0
+        assert done == (t == 2)
+    assert info["episode_length"] == 3 and abs(info["episode_reward"] - total) < 1e-6 and info["episode_success"] == 0
+    # no recipe, no dense reward: the library says so
+    import pytest
+
+    with pytest.raises(RuntimeError, match="recipe"):
+        FurnitureGymB200(name="FurnitureSawyerDenseRewardEnv", furniture_name="swivel_chair_0700", lib_path=build_emu())
