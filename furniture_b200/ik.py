@@ -1,0 +1,165 @@
+"""Host side of control_type="ik" for the Sawyer env (FurnitureEnv._do_ik_step, furniture/env/furniture.py:2899-2996, and
+SawyerIKController, furniture/env/controllers/sawyer_ik_controller.py:46-299).
+
+The reference solves the inverse kinematics in a pybullet copy of the arm (`p.calculateInverseKinematics`, 20 calls, joint damping 0.1,
+rest poses, joint limits) -- a host round trip per env step and a dependency (pybullet + its URDF) that is absent here.  This build keeps
+everything the reference does around that call (action scaling and axis swap, workspace clipping, the accumulated target orientation with
+its quaternion conventions, the 0.3 sensitivity, the P controller -5 * (q - q_cmd) clipped to [-1, 1], three closed-loop repeats of
+_do_simulation) and replaces the solver by a damped-least-squares IK on the arm's own kinematic chain, run by the warp that owns the env
+(csrc/fe_ik.h); `solve_ik` below is the same algorithm in numpy float64 (the oracle's copy, oracle/ik_oracle.py, calls it).  The joint
+targets therefore differ from pybullet's within the arm's one-dimensional null space; the end-effector pose they reach is the same target.
+
+  arm_chain(model)   -> the 7 joint frames from the robot base to `right_hand`, taken from the composed model at zero joint angles
+  ik_config(model)   -> struct fe_ik_config (include/furniture_b200.h): gains, limits, rest pose, workspace, the chain
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import mjcf
+
+i32, f32 = C.c_int32, C.c_float
+NJ = 7
+REST_POSE = [0, -1.18, 0.00, 2.18, 0.00, 0.57, 3.3161]          # sawyer_ik_controller.py:268
+LOWER = [-3.05, -3.82, -3.05, -3.05, -2.98, -2.98, -4.71]       # :196-198
+UPPER = [3.05, 2.28, 3.05, 3.05, 2.98, 2.98, 4.71]
+
+
+class FeIkConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("action_repeat", i32), ("max_iters", i32), ("pad_", i32),
+        ("move_speed", f32), ("rotate_speed", f32), ("user_sensitivity", f32), ("kp", f32), ("damping", f32), ("null_gain", f32),
+        ("tol_pos", f32), ("tol_rot", f32), ("max_step_pos", f32), ("max_step_rot", f32),
+        ("min_pos", f32 * 3), ("max_pos", f32 * 3), ("rest_pose", f32 * NJ), ("lower", f32 * NJ), ("upper", f32 * NJ),
+        ("link_pos", (f32 * 3) * NJ), ("link_quat", (f32 * 4) * NJ), ("jaxis", (f32 * 3) * NJ), ("jpos", (f32 * 3) * NJ),
+        ("hand_pos", f32 * 3), ("hand_quat", f32 * 4), ("base_pos", f32 * 3), ("base_quat", f32 * 4),
+        ("arm_qadr", i32 * NJ),
+    ]
+
+
+def arm_chain(m: mjcf.Model):
+    """frames of the arm's joint bodies relative to one another at zero joint angles: link_pos / link_quat [k] = body of joint k in the
+    frame of the body of joint k-1 (k = 0: in the world), joint axis / anchor in the body frame, `right_hand` in the last joint body's
+    frame, and the world pose of the robot `base` body (targets are kept in the base frame, furniture.py:3381-3427)"""
+    joints = list(m.meta["robot_joints"])[:NJ]
+    q0 = np.array(m.qpos0, dtype=np.float64)
+    for jn in m.meta["robot_joints"]:
+        q0[int(m.jnt_qposadr[m.names["jnt"].index(jn)])] = 0.0
+    kin = mjcf.kinematics_np(m, q0)
+    ch = dict(link_pos=[], link_quat=[], jaxis=[], jpos=[], qadr=[])
+    prev_p, prev_q = np.zeros(3), np.array([1.0, 0, 0, 0])
+    for jn in joints:
+        j = m.names["jnt"].index(jn)
+        b = int(m.jnt_bodyid[j])
+        p, q = kin["xpos"][b], kin["xquat"][b]
+        Rp = mjcf.q_to_mat(prev_q)
+        ch["link_pos"].append(Rp.T @ (p - prev_p))
+        ch["link_quat"].append(mjcf.q_norm(mjcf.q_mul(mjcf.q_conj(prev_q), q)))
+        ch["jaxis"].append(np.array(m.jnt_axis[j], dtype=np.float64))
+        ch["jpos"].append(np.array(m.jnt_pos[j], dtype=np.float64))
+        ch["qadr"].append(int(m.jnt_qposadr[j]))
+        prev_p, prev_q = p, q
+    hb = m.names["body"].index(m.meta["hand_body"])
+    Rp = mjcf.q_to_mat(prev_q)
+    ch["hand_pos"] = Rp.T @ (kin["xpos"][hb] - prev_p)
+    ch["hand_quat"] = mjcf.q_norm(mjcf.q_mul(mjcf.q_conj(prev_q), kin["xquat"][hb]))
+    bb = m.names["body"].index("base")
+    ch["base_pos"], ch["base_quat"] = kin["xpos"][bb].copy(), kin["xquat"][bb].copy()
+    return ch
+
+
+IK_DEFAULTS = dict(action_repeat=3, max_iters=20, move_speed=0.1, rotate_speed=22.5, user_sensitivity=0.3, kp=5.0, damping=0.1, null_gain=0.0,
+                   tol_pos=1e-4, tol_rot=1e-3, max_step_pos=0.05, max_step_rot=0.2, min_pos=(-1.5, -1.5, 0.0), max_pos=(1.5, 1.5, 1.5))
+
+
+def ik_params(m: mjcf.Model, **kw):
+    """plain-Python view of the IK parameters (what `ik_config` packs); config/furniture.py:84-89 for the speeds, furniture.py:166-172 for
+    the workspace and the three repeats, sawyer_ik_controller.py for sensitivity, gain, damping, rest pose and limits"""
+    p = dict(IK_DEFAULTS)
+    for k, v in kw.items():
+        if k not in p:
+            raise KeyError(k)
+        p[k] = v
+    p.update(rest_pose=list(REST_POSE), lower=list(LOWER), upper=list(UPPER), chain=arm_chain(m))
+    return p
+
+
+def ik_config(m: mjcf.Model, **kw) -> FeIkConfig:
+    p = ik_params(m, **kw)
+    c = FeIkConfig()
+    c.struct_bytes = C.sizeof(FeIkConfig)
+    for k in ("action_repeat", "max_iters"):
+        setattr(c, k, int(p[k]))
+    for k in ("move_speed", "rotate_speed", "user_sensitivity", "kp", "damping", "null_gain", "tol_pos", "tol_rot", "max_step_pos", "max_step_rot"):
+        setattr(c, k, float(p[k]))
+    for k in ("min_pos", "max_pos", "rest_pose", "lower", "upper"):
+        getattr(c, k)[:] = [float(x) for x in p[k]]
+    ch = p["chain"]
+    for k in range(NJ):
+        c.link_pos[k][:] = list(ch["link_pos"][k]); c.link_quat[k][:] = list(ch["link_quat"][k])
+        c.jaxis[k][:] = list(ch["jaxis"][k]); c.jpos[k][:] = list(ch["jpos"][k])
+        c.arm_qadr[k] = ch["qadr"][k]
+    c.hand_pos[:] = list(ch["hand_pos"]); c.hand_quat[:] = list(ch["hand_quat"])
+    c.base_pos[:] = list(ch["base_pos"]); c.base_quat[:] = list(ch["base_quat"])
+    return c
+
+
+# ------------------------------------------------------------------ the algorithm, numpy float64 (same steps as csrc/fe_ik.h)
+def chain_fk(ch, q):
+    """world pose of `right_hand` and the world anchors / axes of the 7 joints"""
+    p, quat = np.zeros(3), np.array([1.0, 0, 0, 0])
+    anchors, axes = [], []
+    for k in range(NJ):
+        R = mjcf.q_to_mat(quat)
+        p0 = p + R @ ch["link_pos"][k]
+        q0 = mjcf.q_mul(quat, ch["link_quat"][k])
+        R0 = mjcf.q_to_mat(q0)
+        anchors.append(p0 + R0 @ ch["jpos"][k])
+        axes.append(R0 @ ch["jaxis"][k])
+        quat = mjcf.q_norm(mjcf.q_mul(q0, mjcf.q_axis_angle(ch["jaxis"][k], q[k])))
+        p = anchors[-1] - mjcf.q_to_mat(quat) @ ch["jpos"][k]
+    R = mjcf.q_to_mat(quat)
+    return p + R @ ch["hand_pos"], mjcf.q_norm(mjcf.q_mul(quat, ch["hand_quat"])), np.array(anchors), np.array(axes)
+
+
+def rot_error(q_target, q_cur):
+    """rotation vector of q_target * conj(q_cur) (world frame)"""
+    e = mjcf.q_mul(q_target, mjcf.q_conj(q_cur))
+    if e[0] < 0:
+        e = -e
+    n = np.linalg.norm(e[1:])
+    if n < 1e-9:
+        return 2.0 * e[1:]
+    return 2.0 * np.arctan2(n, e[0]) * e[1:] / n
+
+
+def solve_ik(p, q_start, target_pos_world, target_quat_world):
+    """damped least squares with a null-space pull to the rest pose and joint limits; returns (q, iterations)"""
+    ch = p["chain"]
+    q = np.array(q_start, dtype=np.float64)
+    lam2 = p["damping"] ** 2
+    rest, lo, hi = np.array(p["rest_pose"]), np.array(p["lower"]), np.array(p["upper"])
+    it = 0
+    for it in range(p["max_iters"]):
+        hp, hq, anchors, axes = chain_fk(ch, q)
+        ep = target_pos_world - hp
+        er = rot_error(target_quat_world, hq)
+        np_, nr = np.linalg.norm(ep), np.linalg.norm(er)
+        if np_ < p["tol_pos"] and nr < p["tol_rot"]:
+            break
+        if np_ > p["max_step_pos"]:
+            ep = ep * (p["max_step_pos"] / np_)
+        if nr > p["max_step_rot"]:
+            er = er * (p["max_step_rot"] / nr)
+        J = np.zeros((6, NJ))
+        for k in range(NJ):
+            J[:3, k] = np.cross(axes[k], hp - anchors[k])
+            J[3:, k] = axes[k]
+        A = J @ J.T + lam2 * np.eye(6)
+        e = np.concatenate([ep, er])
+        z = p["null_gain"] * (rest - q)
+        dq = J.T @ np.linalg.solve(A, e - J @ z) + z
+        q = np.clip(q + dq, lo, hi)
+    return q, it

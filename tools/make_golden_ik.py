@@ -1,0 +1,78 @@
+"""Golden vectors for what FurnitureEnv._do_ik_step does *around* the inverse-kinematics call (control_type="ik", Sawyer), made by running
+the REFERENCE'S OWN Python, unmodified (furniture/env/furniture.py:2899-2996, _bounded_d_pos :1252-1258, _make_input :1332-1343;
+transform_utils.euler_to_quat / quat_multiply / quat_inverse / quat2mat / mat2quat).  Runs only in the build container.
+
+The simulator and the pybullet controller are replaced by stand-ins that show a hand pose and record what the controller is asked for:
+`dpos` and `rotation` of the first get_control call, the accumulated `_initial_right_hand_quat`, and how often _do_simulation and the
+closed-loop get_control() run.  pyquaternion is absent: the stand-in of tools/make_golden_assembly.py (documented semantics) is used by
+euler_to_quat, so this golden is pinned to the reference code modulo that stand-in, like connect_geom.npz.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from make_golden_assembly import import_reference, rand_rot  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def main():
+    T, FurnitureEnv = import_reference()
+    rng = np.random.RandomState(20260925)
+    rec = {k: [] for k in ("action", "hand_pos", "hand_R", "s_in", "dpos", "rotation", "s_out", "low_grip", "n_sim", "n_closed_loop")}
+    for n in range(600):
+        hand_R = rand_rot(rng)
+        hand_pos = rng.uniform(-1.6, 1.6, size=3) if n % 3 == 0 else rng.uniform(-0.5, 0.5, size=3) + [0, 0, 0.6]
+        calls = dict(sim=0, closed=0, first=None)
+
+        class Ctl:
+            def get_control(self, dpos=None, rotation=None):
+                if dpos is None:
+                    calls["closed"] += 1
+                else:
+                    calls["first"] = (np.array(dpos, dtype=np.float64), np.array(rotation, dtype=np.float64))
+                return np.zeros(7)
+
+        class Fake:
+            _control_type, _agent_type, _record_demo, _action_repeat = "ik", "Sawyer", False, 3
+            _move_speed, _rotate_speed = 0.1, 22.5
+            _min_gripper_pos, _max_gripper_pos = np.array([-1.5, -1.5, 0.0]), np.array([1.5, 1.5, 1.5])
+            _controller = Ctl()
+            sim = types.SimpleNamespace(data=types.SimpleNamespace(get_body_xpos=lambda name: hand_pos.copy()))
+            _bounded_d_pos = FurnitureEnv._bounded_d_pos
+            _make_input = FurnitureEnv._make_input
+
+            @property
+            def _right_hand_quat(self):
+                return T.mat2quat(np.ascontiguousarray(hand_R, dtype=np.float32))  # numpy 2: the reference asks for copy=False, so hand it float32
+
+            def _setup_action(self, low):
+                self.low = np.array(low, dtype=np.float64)
+                return low
+
+            def _do_simulation(self, ctrl):
+                calls["sim"] += 1
+
+        fake = Fake()
+        s_in = T.mat2quat(rand_rot(rng).astype(np.float32)) if n % 2 else T.mat2quat(hand_R.astype(np.float32))
+        if n % 5 == 4:  # after some steps the accumulated target is a python list of float64, not a unit float32 quaternion
+            s_in = list(np.asarray(s_in, dtype=np.float64) * (1 + 1e-3 * rng.normal()))
+        fake._initial_right_hand_quat = s_in
+        a = rng.uniform(-1, 1, size=8)
+        if n % 7 == 0:
+            a[3:6] = 0
+        FurnitureEnv._do_ik_step(fake, a.copy())
+        rec["action"].append(a); rec["hand_pos"].append(hand_pos); rec["hand_R"].append(hand_R.ravel()); rec["s_in"].append(np.asarray(s_in, dtype=np.float64))
+        rec["dpos"].append(calls["first"][0]); rec["rotation"].append(calls["first"][1].ravel())
+        rec["s_out"].append(np.asarray(fake._initial_right_hand_quat, dtype=np.float64)); rec["low_grip"].append(fake.low[7])
+        rec["n_sim"].append(calls["sim"]); rec["n_closed_loop"].append(calls["closed"])
+    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{k: np.array(v) for k, v in rec.items()},
+                        source="reference FurnitureEnv._do_ik_step run unmodified around stand-ins for the simulator and the pybullet controller (tools/make_golden_ik.py)")
+    print("ik_pre: %d cases; _do_simulation calls %s, closed-loop get_control calls %s" % (len(rec["action"]), set(rec["n_sim"]), set(rec["n_closed_loop"])))
+
+
+if __name__ == "__main__":
+    main()
