@@ -79,16 +79,10 @@ class ClockSampler(threading.Thread):
 
 
 def build_id():
-    """identifies the kernel build a profile belongs to: sha256 over the kernel sources and the nvcc flags"""
-    import hashlib
-
+    """identifies the kernel build a profile belongs to: sha256 over the SASS of the stock kernels' cubin (__graft_entry__.sass_id)"""
     import __graft_entry__ as ge
 
-    h = hashlib.sha256(" ".join(ge.NVCC_FLAGS).encode())
-    csrc = os.path.join(ROOT, "furniture_b200", "csrc")
-    for f in sorted(os.listdir(csrc)) + ["../../include/furniture_b200.h"]:
-        h.update(open(os.path.join(csrc, f), "rb").read())
-    return h.hexdigest()[:16]
+    return ge.sass_id()
 
 
 def host_cores():

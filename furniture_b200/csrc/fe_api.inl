@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "../../include/furniture_b200.h"
-#include "fe_env.h"
+#include "fe_ik.h"
 
 struct FeField {
   std::string name;
@@ -28,6 +28,7 @@ struct fe_handle {
   FeState st;
   FeDebug dbg;
   FeEnvState es;
+  FeIkArgs ik = {nullptr, nullptr}; // control_type="ik" when ik.c is set (fe_enable_ik)
   int slice_words = 0;
   FeLayout lay;       // where each array of an env's slice starts (same for every env of the handle)
   std::vector<FeField> fields;
@@ -78,7 +79,7 @@ int fe_is_cuda(void) { return PLAT_IS_CUDA; }
 const char* fe_last_error(const fe_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int fe_num_envs(const fe_handle* h) { return h->N; }
 int fe_obs_dim(const fe_handle* h) { return h->hs.obs_dim; }
-int fe_action_dim(const fe_handle* h) { return h->hs.act_dim; }
+int fe_action_dim(const fe_handle* h) { return h->ik.c ? 8 : h->hs.act_dim; }
 int fe_info_dim(const fe_handle* h) { return FE_INFO_DIM; }
 int fe_smem_bytes_per_env(const fe_handle* h) { return (h->slice_words + FE_ENV_EXTRA_WORDS) * 4; }
 const float* fe_obs_dev(const fe_handle* h) { return h->es.obs; }
@@ -297,6 +298,24 @@ int fe_set_max_episode_steps(fe_handle* h, int max_episode_steps) {
   return 0;
 }
 
+int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc) {
+  if (!ikc || ikc->struct_bytes != (int32_t)sizeof(fe_ik_config)) return fail(h, -1, "fe_enable_ik: fe_ik_config size mismatch");
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_enable_ik: handle was created without a scene blob");
+  if (h->hs.narms != 1 || h->hs.narm != 7 || h->hs.hand_link[0] < 0 || h->hs.act_dim != 9) return fail(h, -1, "fe_enable_ik: the IK control type is built for the one-arm 7-joint (Sawyer) env");
+  if (ikc->action_repeat < 1 || ikc->action_repeat > 16 || ikc->max_iters < 1 || ikc->max_iters > 1000) return fail(h, -1, "fe_enable_ik: action_repeat / max_iters out of range");
+  for (int k = 0; k < 7; ++k) if (ikc->arm_qadr[k] < 0 || ikc->arm_qadr[k] >= h->hm.nq) return fail(h, -1, "fe_enable_ik: arm_qadr outside qpos");
+  FeDevScope dev_scope(h);
+  if (!h->ik.c) {
+    fe_ik_config* d = (fe_ik_config*)plat_alloc(sizeof(fe_ik_config));
+    FeIkState* st = h_alloc<FeIkState>(h, (size_t)h->N);
+    if (!d || !st) return fail(h, -2, "fe_enable_ik: device allocation failed");
+    h->allocs.push_back(d);
+    h->ik.c = d; h->ik.st = st;
+    add_field(h, "ik_state", st, (int)sizeof(FeIkState), 1, true);
+  }
+  plat_upload((void*)h->ik.c, ikc, sizeof(fe_ik_config));
+  return 0;
+}
 int fe_dense_info_dim(void) { return FE_DENSE_INFO; }
 size_t fe_dense_recipe_sizeof(void) { return sizeof(fe_dense_recipe); }
 int fe_enable_dense_reward(fe_handle* h, const fe_dense_config* dc) {

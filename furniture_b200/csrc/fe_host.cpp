@@ -47,6 +47,9 @@ static int plat_dense_eval(fe_handle* h, const struct fe_dense_config* dc, const
 // ---------------------------------------------------------------- embedded cubin + driver entry points
 __asm__(".section .rodata\n.balign 16\n.global fe_cubin_start\nfe_cubin_start:\n.incbin \"" FE_CUBIN_FILE "\"\n.global fe_cubin_end\nfe_cubin_end:\n.byte 0\n.previous\n");
 extern "C" const unsigned char fe_cubin_start[];
+// the IK step kernel is a module of its own (fe_kernels_ik.cu): the stock kernels stay the binary they were profiled as
+__asm__(".section .rodata\n.balign 16\n.global fe_cubin_ik_start\nfe_cubin_ik_start:\n.incbin \"" FE_CUBIN_IK_FILE "\"\n.global fe_cubin_ik_end\nfe_cubin_ik_end:\n.byte 0\n.previous\n");
+extern "C" const unsigned char fe_cubin_ik_start[];
 
 struct DriverApi {
   CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
@@ -91,6 +94,8 @@ struct FeModule {
   FeLayout lay;
   CUmodule mod;
   CUfunction f_sim, f_step, f_reset, f_order, f_aligned, f_dense;
+  CUmodule mod_ik = nullptr;     // loaded when a handle of this (device, layout) first steps with control_type="ik"
+  CUfunction f_ik_step = nullptr;
   int users;
 };
 static std::vector<FeModule*> g_modules;
@@ -229,6 +234,7 @@ static void plat_fini(fe_handle* h) {
       for (size_t i = 0; i < g_modules.size(); ++i)
         if (g_modules[i] == p->km) { g_modules.erase(g_modules.begin() + i); break; }
       g_drv.ModuleUnload(p->km->mod);
+      if (p->km->mod_ik) g_drv.ModuleUnload(p->km->mod_ik);
       delete p->km;
     }
   }
@@ -246,12 +252,39 @@ static int launch(fe_handle* h, CUfunction f, unsigned grid, unsigned block, siz
   DRV_OK(g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr));
   return 0;
 }
+// the IK module of this handle's (device, layout): its own copy of the slice layout table
+static int plat_module_ik(fe_handle* h) {
+  CudaPlat* p = (CudaPlat*)h->plat;
+  std::lock_guard<std::mutex> lock(g_mu);
+  FeModule* m = p->km;
+  if (m->f_ik_step) return 0;
+  CUmodule mod = nullptr;
+  CUfunction f = nullptr;
+  CUresult r = g_drv.ModuleLoadData(&mod, fe_cubin_ik_start);
+  if (r != CUDA_SUCCESS) return fail(h, -10, "cuModuleLoadData(embedded IK cubin): " + drv_err(r));
+  r = g_drv.ModuleGetFunction(&f, mod, "fe_env_ik_step_kernel");
+  CUdeviceptr sym = 0;
+  size_t bytes = 0;
+  if (r == CUDA_SUCCESS) r = g_drv.ModuleGetGlobal(&sym, &bytes, mod, "fe_c_lay");
+  if (r == CUDA_SUCCESS && bytes != sizeof(FeLayout)) r = CUDA_ERROR_INVALID_VALUE;
+  if (r == CUDA_SUCCESS) r = g_drv.MemcpyHtoD(sym, &h->lay, sizeof(FeLayout));
+  if (r == CUDA_SUCCESS) r = g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 227 * 1024);
+  if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(mod); return fail(h, -10, "IK module set-up: " + drv_err(r)); }
+  m->mod_ik = mod; m->f_ik_step = f;
+  return 0;
+}
 static int launch_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, cudaStream_t stream) {
   CudaPlat* p = (CudaPlat*)h->plat;
   int slice_words = h->slice_words;
   const int* slots = p->slots;
+  if (h->ik.c) { // control_type="ik": same launch shape, the IK kernel of the second module
+    if (int rc = plat_module_ik(h)) return rc;
+    void* a[] = {&h->st, &h->es, &h->ik, &h->dm, &h->ds, &h->cfg, &h->opt, &actions, &reward, &done, &info, &slice_words, &slots};
+    if (int rc = launch(h, p->km->f_ik_step, p->nblocks, 32 * p->wpb, p->smem_env, stream, a)) return rc;
+  } else {
   void* a[] = {&h->st, &h->es, &h->dm, &h->ds, &h->cfg, &h->opt, &actions, &reward, &done, &info, &slice_words, &slots};
   if (int rc = launch(h, p->km->f_step, p->nblocks, 32 * p->wpb, p->smem_env, stream, a)) return rc;
+  }
   if (p->reorder) {
     int N = h->N, nslots = p->nblocks * p->wpb, wpb = p->wpb;
     const int* stats = h->st.stats;
@@ -292,7 +325,7 @@ static int plat_step_host(fe_handle* h, const float* actions, float* obs, float*
   DevScope dev(h);
   if (int rc = plat_prepare(h)) return rc;
   CudaPlat* p = (CudaPlat*)h->plat;
-  const size_t N = h->N, ab = sizeof(float) * N * h->hs.act_dim, ob = sizeof(float) * N * h->hs.obs_dim, rb = sizeof(float) * N, ib = sizeof(int32_t) * N * FE_INFO_DIM;
+  const size_t N = h->N, ab = sizeof(float) * N * fe_action_dim(h), ob = sizeof(float) * N * h->hs.obs_dim, rb = sizeof(float) * N, ib = sizeof(int32_t) * N * FE_INFO_DIM;
   memcpy(p->pin_act, actions, ab);
   // The private stream is ordered behind whatever the caller last launched for this handle on another stream
   // (fe_sim_forward, fe_env_reset ...) with an event, not with a device-wide synchronisation.

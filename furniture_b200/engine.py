@@ -186,7 +186,7 @@ def build_scene(m: mjcf.Model, em: EngineModel, phase_ob: bool = False) -> FeSce
 
 class Engine:
     def __init__(self, model: mjcf.Model, n_envs: int, device: int = 0, config: FeConfig | None = None, lib_path: str | None = None,
-                 dense: FeDenseConfig | None = None):
+                 dense: FeDenseConfig | None = None, ik=None):
         path = lib_path or DEFAULT_LIB
         if not os.path.exists(path):
             raise RuntimeError(
@@ -221,6 +221,10 @@ class Engine:
         self.obs_dim, self.act_dim = self.scene.obs_dim, self.scene.act_dim
         for f in ("fe_env_reset", "fe_env_step"):
             getattr(L, f).argtypes = None
+        self.ik = ik
+        if ik is not None:  # control_type="ik" (furniture_b200/ik.py: FeIkConfig): actions become (move 3, rotate 3, gripper, connect)
+            self._chk(L.fe_enable_ik(self.h, C.byref(ik)))
+            self.act_dim = int(L.fe_action_dim(self.h))
         self.dense = dense
         if dense is not None:  # FurnitureSawyerDenseRewardEnv: the phase machine replaces the sparse reward inside fe_env_step
             self._chk(L.fe_enable_dense_reward(self.h, C.byref(dense)))

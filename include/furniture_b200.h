@@ -135,6 +135,24 @@ int fe_dense_eval(fe_handle* h, const fe_dense_config* dc, const void* recipe_bl
                   const double* site_mat, const double* part_pos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac,
                   double* reward_host, uint8_t* done_host, double* info_host);
 
+/* ---- control_type="ik" for the one-arm env: FurnitureEnv._do_ik_step (furniture.py:2899-2996) + SawyerIKController
+ * (controllers/sawyer_ik_controller.py) with the pybullet solve replaced by a damped-least-squares IK on the arm's own chain, run inside
+ * the step kernel.  Speeds: config/furniture.py:84-89; workspace and the three repeats: furniture.py:166-172; sensitivity 0.3, gain 5,
+ * joint damping 0.1, rest pose, limits: sawyer_ik_controller.py.  The chain (host: furniture_b200/ik.py: arm_chain) lists, per arm joint,
+ * its body frame in the previous joint body's frame at zero angle and the hinge (anchor, axis) in its body frame. */
+typedef struct fe_ik_config {
+  int32_t struct_bytes, action_repeat, max_iters, pad_;
+  float move_speed, rotate_speed, user_sensitivity, kp, damping, null_gain, tol_pos, tol_rot, max_step_pos, max_step_rot;
+  float min_pos[3], max_pos[3], rest_pose[7], lower[7], upper[7];
+  float link_pos[7][3], link_quat[7][4], jaxis[7][3], jpos[7][3];
+  float hand_pos[3], hand_quat[4], base_pos[3], base_quat[4]; /* right_hand in the last joint body's frame; the robot base in the world */
+  int32_t arm_qadr[7];                                           /* qpos index of every arm joint */
+} fe_ik_config;
+/* Switch the handle to control_type="ik": fe_env_step then takes (n_envs, 8) actions (move 3, rotate 3, gripper, connect) and
+ * fe_action_dim() returns 8.  Field "ik_state" holds per env: accumulated target quaternion (4), target position in the base frame (3),
+ * commanded joints (7), last low-level action (8) as float32, then the iteration count of the last solve (int32) and a pad. */
+int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc);
+
 #ifdef __cplusplus
 }
 #endif

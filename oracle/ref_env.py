@@ -320,14 +320,26 @@ class OracleFurnitureEnv:
         self._grav_comp()
         return a[-1]
 
-    def step(self, action):
-        raw = np.asarray(action, dtype=np.float64)
-        connect = self.set_controls(raw)
+    def _do_simulation(self):
+        """forward + nsub mj_steps with the controls in place; True if the solver blew up (furniture.py:2877-2897)"""
         self.sim.forward()
         self.sim.step(self.nsub)
         fail = bool(self.sim.scalar("warning") & 2)
         if fail:
             self.sim.L.om_clear_warning(self.sim.d)
+        return fail
+
+    def _simulate(self, raw):
+        """_step_continuous up to the connect scan -> (some _do_simulation failed, the env still has to be reset for it)"""
+        self.set_controls(raw)
+        fail = self._do_simulation()
+        return fail, fail
+
+    def step(self, action):
+        raw = np.asarray(action, dtype=np.float64)
+        connect = raw[-1]
+        fail, reset_now = self._simulate(raw)
+        if reset_now:
             self.reset()
         else:
             if connect > 0:  # :1290-1322: per arm the first part both fingers touch; return at the first connection
@@ -370,6 +382,59 @@ class OracleFurnitureEnv:
         reward = success_r + touch_r + pick_r - self.cfg.ctrl_penalty_coef * float(np.square(raw).sum())
         success = self.num_connected == self.npart - 1 and self.npart > 1
         return reward, success, success
+
+
+class IKMixin:
+    """control_type="ik" (FurnitureEnv._do_ik_step, furniture.py:2899-2996) over the oracle simulator; the solver is the
+    damped-least-squares IK of oracle/ik_oracle.py (pybullet's is not available)"""
+
+    def _ik_setup(self, **ik_kw):
+        from furniture_b200 import ik as IK
+        from .ik_oracle import IKOracle
+
+        self.ikp = IK.ik_params(self.m, **ik_kw)
+        self.ik = IKOracle(self.ikp)
+        self.hand = self.m.names["body"].index("right_hand")
+        self.dof = 8  # move 3, rotate 3, gripper, connect (furniture_sawyer.py:60-61)
+
+    def _hand(self):
+        b = self.hand
+        return np.array(self.sim.xpos[3 * b : 3 * b + 3]), np.array(self.sim.xquat[4 * b : 4 * b + 4])
+
+    def _ik_sync(self):  # _reset's tail, furniture.py:1643-1650
+        self.ik.sync(*self._hand())
+
+    def _simulate(self, raw):
+        a = raw.copy()
+        if self.cfg.discrete_grip:
+            a[-2] = -1 if a[-2] < 0 else 1
+        jpos = lambda: np.array(self.sim.qpos[self.arm_idx])
+        vel, grip = self.ik.command(a, *self._hand(), jpos())
+        fail = reset_now = False
+        R = self.ikp["action_repeat"]
+        for r in range(R):
+            if r > 0:
+                vel = self.ik.velocities(jpos())
+            self.low_action = np.concatenate([vel, [grip]])
+            self.set_controls(np.concatenate([self.low_action, [raw[-1]]]))
+            if self._do_simulation():
+                fail = True
+                if r + 1 < R:
+                    self.reset()
+                else:
+                    reset_now = True
+        return fail, reset_now
+
+
+class OracleIKEnv(IKMixin, OracleFurnitureEnv):
+    def __init__(self, model, cfg=None, **ik_kw):
+        super().__init__(model, cfg)
+        self._ik_setup(**ik_kw)
+
+    def reset(self):
+        ob = super().reset()
+        self._ik_sync()
+        return ob
 
 
 class DenseCfg(Cfg):  # what config/furniture_sawyer_dense.py:5-14 changes in the base env

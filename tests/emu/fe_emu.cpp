@@ -64,7 +64,8 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
     fe_env_bind(&e, (float*)slice.data(), h->dm, h->ds, &h->cfg, h->opt, h->st, h->es, env, h->slice_words);
     fe_load(e.w, h->st, env);
     fe_env_load_groups(&e);
-    fe_env_step_one(&e, actions, reward, done, info);
+    if (h->ik.c) fe_env_ik_step_one(&e, h->ik, actions, reward, done, info);
+    else fe_env_step_one(&e, actions, reward, done, info);
     fe_env_store_groups(&e);
     fe_store(e.w, h->st, env);
   }

@@ -50,3 +50,97 @@ def test_chain_and_solver_reach_the_commanded_hand_pose(sawyer):
         a, b, _, _ = IK.chain_fk(p["chain"], qs)
         assert it < p["max_iters"] - 1 and np.linalg.norm(a - tp) < p["tol_pos"] and np.linalg.norm(IK.rot_error(tq, b)) < p["tol_rot"]
         assert (qs >= np.array(p["lower"]) - 1e-12).all() and (qs <= np.array(p["upper"]) + 1e-12).all()
+
+
+# ------------------------------------------------------------------ the IK env: device step against the CPU env
+def _ik_engine(m, n, gpu, **cfg):
+    from furniture_b200.engine import Engine, default_config
+    from parity_util import build_emu
+
+    c = default_config(**cfg)
+    ikc = IK.ik_config(m)
+    return Engine(m, n, device=0, config=c, ik=ikc) if gpu else Engine(m, n, config=c, lib_path=build_emu(), ik=ikc)
+
+
+def _ik_state(eng, i):
+    raw = eng.get("ik_state")[i].tobytes()
+    f = np.frombuffer(raw[: 22 * 4], np.float32)
+    return dict(s=f[0:4], target_pos=f[4:7], q_cmd=f[7:14], low=f[14:22], iters=int(np.frombuffer(raw[22 * 4 : 23 * 4], np.int32)[0]))
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_ik_env_steps_match_the_cpu_env(sawyer, gpu):
+    """reset + 3 env steps with control_type="ik" (8-number actions, three closed-loop repeats of 50 mj_steps): targets, joint command,
+    low-level action, observation, reward of the device equal the CPU env (oracle physics + the float64 copy of the solver)"""
+    from oracle.ref_env import OracleIKEnv
+    from test_env_parity import _sync_oracle_from_engine
+
+    m = sawyer
+    n = 2
+    eng = _ik_engine(m, n, gpu)
+    assert eng.act_dim == 8
+    eng.env_reset()
+    envs = [OracleIKEnv(m) for _ in range(n)]
+    lpos, lquat = eng.get("link_xpos"), eng.get("link_xquat")
+    for i, e in enumerate(envs):
+        e.reset()
+        _sync_oracle_from_engine(e, eng, i)
+        e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[i]
+        # the targets start from the hand pose of the reset's last forward pass (what sim.data holds in the reference): hand it to the oracle
+        hl = eng.scene.hand_link[0]
+        ikc = eng.ik
+        R = mjcf.q_to_mat(lquat[i][4 * hl : 4 * hl + 4].astype(np.float64))
+        hp = lpos[i][3 * hl : 3 * hl + 3].astype(np.float64) + R @ np.array(ikc.hand_pos[:])
+        hq = mjcf.q_norm(mjcf.q_mul(lquat[i][4 * hl : 4 * hl + 4].astype(np.float64), np.array(ikc.hand_quat[:], dtype=np.float64)))
+        e.ik.sync(hp, hq)
+        e._hand0 = (hp, hq)
+    rng = np.random.RandomState(3)
+    for k in range(3):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        a[:, -1] = -0.5
+        if k == 0:  # first step: the oracle's sim.data would be one integration newer than the device's stored kinematics; show it the same hand pose
+            for e in envs:
+                e._hand = lambda hp_hq=e._hand0: hp_hq
+        obs, rew, done, info = eng.env_step_host(a)
+        for i, e in enumerate(envs):
+            ob, r, d, inf = e.step(a[i].astype(np.float64))
+            if k == 0:
+                del e._hand
+            st = _ik_state(eng, i)
+            assert np.abs(st["target_pos"] - e.ik.target_pos).max() < 2e-6, (k, i)
+            assert min(np.abs(st["s"] - e.ik.s).max(), np.abs(st["s"] + e.ik.s).max()) < 1e-5, (k, i)
+            assert np.abs(st["q_cmd"] - e.ik.q_cmd).max() < 2e-4, (k, i, st["q_cmd"], e.ik.q_cmd)
+            assert np.abs(st["low"] - e.low_action).max() < 2e-3, (k, i, st["low"], e.low_action)
+            assert np.abs(obs[i] - ob).max() < 1e-3, (k, i, np.abs(obs[i] - ob).max())
+            assert abs(rew[i] - r) < 1e-5 and bool(done[i]) == d and info[i][3] == inf["episode_length"] == k + 1
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_ik_control_moves_the_hand_where_the_actions_say(sawyer, gpu):
+    """four steps of "move" along one action axis, then four of zero action: the hand follows the accumulated target (0.3 x move_speed per
+    step along the swapped axes of furniture.py:2912-2913) and keeps its orientation"""
+    m = sawyer
+    eng = _ik_engine(m, 1, gpu)
+    eng.env_reset()
+    hl = eng.scene.hand_link[0]
+
+    def hand():
+        lp, lq = eng.get("link_xpos")[0], eng.get("link_xquat")[0]
+        R = mjcf.q_to_mat(lq[4 * hl : 4 * hl + 4].astype(np.float64))
+        return lp[3 * hl : 3 * hl + 3] + R @ np.array(eng.ik.hand_pos[:]), mjcf.q_mul(lq[4 * hl : 4 * hl + 4].astype(np.float64), np.array(eng.ik.hand_quat[:], dtype=np.float64))
+
+    p0, q0 = hand()
+    a = np.zeros((1, 8), np.float32)
+    a[0, 1], a[0, 6], a[0, 7] = 1.0, -1.0, -1.0  # action[1] -> -x after the swap
+    for _ in range(4):
+        eng.env_step_host(a)
+    a[0, 1] = 0.0
+    for _ in range(4):
+        eng.env_step_host(a)
+    p1, q1 = hand()
+    Rb = mjcf.q_to_mat(np.array(eng.ik.base_quat[:], dtype=np.float64))  # the displacement is added to the target in the robot's base frame
+    want = p0 + Rb @ np.array([-4 * 0.1 * 0.3, 0.0, 0.0])
+    assert np.linalg.norm(p1 - want) < 0.012, (p1 - p0, want - p0)
+    assert abs(abs(np.dot(mjcf.q_norm(q0), mjcf.q_norm(q1))) - 1) < 2e-3
+    st = _ik_state(eng, 0)
+    assert st["iters"] <= 3 and np.abs(st["low"][:7]).max() < 0.2  # at rest on the target: the solve is immediate, the velocities small
