@@ -249,9 +249,9 @@ def run_ours(args):
             from furniture_b200.env import split_dense_config
 
             _, over, dense, _ = split_dense_config(dict(furniture_name=args.furniture, seed=123))
-            e = BatchedFurnitureEnv(args.agent, args.furniture, n_local, device=local, dense=dense, **over)
+            e = BatchedFurnitureEnv(args.agent, args.furniture, n_local, device=local, dense=dense, control_type=args.control_type, **over)
         else:
-            e = BatchedFurnitureEnv(args.agent, args.furniture, n_local, device=local, seed=123)
+            e = BatchedFurnitureEnv(args.agent, args.furniture, n_local, device=local, seed=123, control_type=args.control_type)
         return e, e
 
     env, benv = make_env()
@@ -349,10 +349,12 @@ def run_ours(args):
         assert args.furniture != "table_lack_0825" or args.agent != "Sawyer" or benv_bytes == B_ENV
         achieved = benv_bytes * n_local / (kernel_ms * 1e-3) / 1e9
         act_txt = "random actions U(-1,1)" if args.actions == "random" else "settled (zero arm action, gripper open)"
-        default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU and args.reward == "sparse"
+        default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU and args.reward == "sparse" and args.control_type == "impedance"
         workload = WORKLOAD if default_case else "Furniture%sEnv + %s, control_type=impedance, 50 mj_steps per env-step, %s" % (args.agent, args.furniture, act_txt)
         if args.reward == "dense":
             workload = "FurnitureSawyerDenseRewardEnv (IKEASawyerDense-v0) + %s, phase-based reward inside the step kernel, episodes of 150 steps, %s" % (args.furniture, act_txt)
+        if args.control_type == "ik":
+            workload = workload.replace("control_type=impedance, 50 mj_steps per env-step", "control_type=ik (in-kernel inverse kinematics), 3 x 50 mj_steps per env-step") + " [control_type=ik]"
         if mixed is not None:
             workload = ("Furniture%sEnv, mixed-furniture batch: %d furniture models (nv %d..%d) x %d envs each, whole buckets per GPU balanced on measured model cost "
                         "(%s models / %s envs per rank, shards padded to %d rows), one kernel-module instance and stream per bucket, 50 mj_steps per env-step, %s"
@@ -419,6 +421,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--furniture", default="table_lack_0825", help="other furniture = parity-test configs timed for DESIGN.md, not the bench line")
     ap.add_argument("--agent", default="Sawyer")
+    ap.add_argument("--control-type", default="impedance", choices=["impedance", "ik"], help="ik = the reference's default control type: inverse kinematics + 3 x 50 mj_steps "
+                    "per env step inside the kernel; one GPU, not the bench line")
     ap.add_argument("--reward", default="sparse", choices=["sparse", "dense"], help="dense = FurnitureSawyerDenseRewardEnv (IKEASawyerDense-v0), one GPU, not the bench line")
     ap.add_argument("--ref-slice", type=float, default=1.0, help="--impl reference: seconds every worker runs free per bench step")
     ap.add_argument("--actions", default="random", choices=["random", "settled"])

@@ -42,8 +42,8 @@ def split_config(config):
     from .engine import FeConfig
 
     cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
-    if cfg.get("control_type", "impedance") != "impedance":
-        raise NotImplementedError("only control_type='impedance' is accelerated (got %r)" % cfg["control_type"])
+    if cfg.get("control_type", "impedance") not in ("impedance", "ik"):
+        raise NotImplementedError("control_type 'impedance' and 'ik' are accelerated (got %r)" % cfg["control_type"])
     for k in ("unity", "visual_ob", "depth_ob", "segmentation_ob", "record_demo", "record_vid"):
         if cfg.get(k):
             raise NotImplementedError("%s=True needs the renderer, which is outside the accelerated path" % k)
@@ -55,6 +55,16 @@ def split_config(config):
     over = {renamed.get(k, k): v for k, v in cfg.items() if renamed.get(k, k) in fields and v is not None}
     ignored = sorted(k for k in cfg if k not in over and k not in ("furniture_name", "furniture_id", "control_type"))
     return name or "table_lack_0825", over, ignored
+
+
+def control_options(config):
+    """control_type and, for "ik", the speeds of config/furniture.py:84-89 -> keywords of BatchedFurnitureEnv"""
+    cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
+    ct = cfg.get("control_type") or "impedance"
+    out = dict(control_type=ct)
+    if ct == "ik":
+        out["ik"] = {k: cfg[k] for k in ("move_speed", "rotate_speed") if cfg.get(k) is not None}
+    return out
 
 
 def split_dense_config(config):
@@ -72,9 +82,13 @@ def split_dense_config(config):
 
 
 class BatchedFurnitureEnv:
-    def __init__(self, agent="Sawyer", furniture_name="table_lack_0825", num_envs=1, device=0, dense=None, **cfg_overrides):
+    def __init__(self, agent="Sawyer", furniture_name="table_lack_0825", num_envs=1, device=0, dense=None, control_type="impedance", ik=None,
+                 **cfg_overrides):
         """`dense`: None for the sparse reward of FurnitureEnv; a dict of coefficient overrides (possibly empty) for the phase-based
-        reward of FurnitureSawyerDenseRewardEnv, computed inside the step kernel (furniture_b200/dense.py)."""
+        reward of FurnitureSawyerDenseRewardEnv, computed inside the step kernel (furniture_b200/dense.py).
+        `control_type`: "impedance" (joint velocities, dof 9) or "ik" (move 3, rotate 3, gripper, connect: dof 8; the inverse kinematics
+        and its three closed-loop repeats run inside the step kernel, furniture_b200/ik.py); `ik`: overrides of ik.IK_DEFAULTS
+        (move_speed, rotate_speed, action_repeat ...)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -93,7 +107,17 @@ class BatchedFurnitureEnv:
             self.resize_factor = 1 + float(np.random.RandomState(int(self.cfg.seed)).uniform(-r, r, 1)[0])
         self.model = mjcf.load_scene(agent, furniture_name, resize_factor=self.resize_factor)
         self.dense_cfg = dense_config(**dense) if dense is not None else None
-        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg, dense=self.dense_cfg)
+        self.control_type = control_type
+        self.ik_cfg = None
+        if control_type == "ik":
+            if agent != "Sawyer":
+                raise NotImplementedError("control_type='ik' is built for the Sawyer env")
+            from .ik import ik_config
+
+            self.ik_cfg = ik_config(self.model, **(ik or {}))
+        elif control_type != "impedance":
+            raise NotImplementedError("control_type 'impedance' and 'ik' are accelerated (got %r)" % control_type)
+        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg, dense=self.dense_cfg, ik=self.ik_cfg)
         self.num_envs = num_envs
         self.obs_dim, self.act_dim = self.engine.obs_dim, self.engine.act_dim
         self.n_objects = self.engine.scene.npart
@@ -185,12 +209,14 @@ def make_vec_env(env_id="IKEASawyer-v0", num_env=1, config=None, device=0):
     agent = ENV_IDS.get(env_id)
     if agent is None:
         raise ValueError("unknown env id %s (this build accelerates %s)" % (env_id, sorted(ENV_IDS)))
+    ctl = control_options(config)
     if env_id in DENSE_IDS:
         furniture, over, dense, ignored = split_dense_config(config)
-        env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, dense=dense, **over)
+        env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, dense=dense, **ctl, **over)
     else:
         furniture, over, ignored = split_config(config)
-        env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, **over)
+        env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, **ctl, **over)
+    ignored = [k for k in ignored if k not in ("move_speed", "rotate_speed")] if ctl["control_type"] == "ik" else ignored
     env.ignored_config = ignored
     return env
 

@@ -33,7 +33,7 @@ class FurnitureGymB200:
         """`id`, `name` and the remaining keywords are what gym passes from the registration (env/__init__.py:19-114: id, name,
         furniture_name / furniture_id, background, port ...); options of the renderer are ignored, see env.split_config"""
         from .dense import dense_config
-        from .env import DENSE_IDS, split_config, split_dense_config
+        from .env import DENSE_IDS, control_options, split_config, split_dense_config
 
         if name not in AGENTS:
             raise ValueError("unknown env %s (this build accelerates %s)" % (name, sorted(AGENTS)))
@@ -47,7 +47,15 @@ class FurnitureGymB200:
             furniture_name, over, self.ignored_config = split_config(config)
         self.model = mjcf.load_scene(AGENTS[name], furniture_name)
         self.cfg = default_config(**over)
-        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path, dense=self.dense_cfg)
+        ctl = control_options(config)
+        self.control_type, self.ik_cfg = ctl["control_type"], None
+        if self.control_type == "ik":  # the reference's default control type (config/furniture.py:57): move / rotate / gripper / connect
+            if AGENTS[name] != "Sawyer":
+                raise NotImplementedError("control_type='ik' is built for the Sawyer env")
+            from .ik import ik_config
+
+            self.ik_cfg = ik_config(self.model, **ctl["ik"])
+        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path, dense=self.dense_cfg, ik=self.ik_cfg)
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim

@@ -70,7 +70,7 @@ def test_reference_style_config_and_episode_length_passthrough():
     import pytest
 
     with pytest.raises(NotImplementedError):
-        split_config({"control_type": "ik"})
+        split_config({"control_type": "joint_torque"})  # the five NEW_CONTROLLERS are not built ("impedance" and "ik" are)
 
 
 def test_demo_files_have_the_reference_recorder_format(tmp_path):
@@ -141,3 +141,28 @@ def test_dense_reward_env_id_through_the_gym_surface():
 
     with pytest.raises(RuntimeError, match="recipe"):
         FurnitureGymB200(name="FurnitureSawyerDenseRewardEnv", furniture_name="swivel_chair_0700", lib_path=build_emu())
+
+
+def test_ik_control_type_through_the_gym_surface():
+    """control_type="ik" is the reference's default (config/furniture.py:57): dof 8 = move 3 + rotate 3 + gripper + connect
+    (furniture_sawyer.py:60-61); move_speed / rotate_speed come from the config"""
+    from furniture_b200.env import control_options, split_config
+
+    assert control_options(dict(control_type="ik", move_speed=0.05, rotate_speed=10.0)) == dict(control_type="ik", ik=dict(move_speed=0.05, rotate_speed=10.0))
+    assert control_options(None) == dict(control_type="impedance")
+    split_config(dict(control_type="ik"))  # accepted
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        split_config(dict(control_type="position_orientation"))
+    env = FurnitureGymB200(name="FurnitureSawyerEnv", lib_path=build_emu(), control_type="ik", move_speed=0.05, nsub=5, max_episode_steps=2)
+    assert env.dof == 8 and abs(env.ik_cfg.move_speed - 0.05) < 1e-9 and env.ik_cfg.action_repeat == 3
+    env.reset()
+    a = np.zeros(8)
+    a[0], a[-2], a[-1] = 1.0, -1.0, -1.0
+    ob, r, done, info = env.step(a)
+    assert abs(r + 1e-3 * 3) < 1e-7 and not done  # ctrl penalty on the policy's 8 numbers
+    ob, r, done, info = env.step(a)
+    assert done and info["episode_length"] == 2
+    with pytest.raises(NotImplementedError):
+        FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik")
