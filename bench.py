@@ -345,8 +345,8 @@ def run_ours(args):
         if mixed is not None:
             benv_bytes = benv.algorithmic_bytes_per_step() / n_local  # this rank's buckets, per row of its (padded) shard
         else:
-            benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim)
-        assert args.furniture != "table_lack_0825" or args.agent != "Sawyer" or benv_bytes == B_ENV
+            benv_bytes = b_env(benv.model, benv.obs_dim, benv.act_dim, nsub=150 if args.control_type == "ik" else 50)  # ik: three _do_simulation per env step
+        assert args.furniture != "table_lack_0825" or args.agent != "Sawyer" or args.control_type != "impedance" or args.reward != "sparse" or benv_bytes == B_ENV
         achieved = benv_bytes * n_local / (kernel_ms * 1e-3) / 1e9
         act_txt = "random actions U(-1,1)" if args.actions == "random" else "settled (zero arm action, gripper open)"
         default_case = args.agent == "Sawyer" and args.furniture == "table_lack_0825" and args.actions == "random" and n_local == ENVS_PER_GPU and args.reward == "sparse" and args.control_type == "impedance"
