@@ -144,3 +144,26 @@ def test_ik_control_moves_the_hand_where_the_actions_say(sawyer, gpu):
     assert abs(abs(np.dot(mjcf.q_norm(q0), mjcf.q_norm(q1))) - 1) < 2e-3
     st = _ik_state(eng, 0)
     assert st["iters"] <= 3 and np.abs(st["low"][:7]).max() < 0.2  # at rest on the target: the solve is immediate, the velocities small
+
+
+def test_enable_ik_and_dense_refuse_what_they_cannot_serve(sawyer):
+    """the C-ABI answers with a code and a message: IK on a two-arm scene, the dense reward on a furniture without a recipe, a config
+    struct of the wrong size"""
+    import ctypes as C
+
+    from furniture_b200.dense import dense_config
+    from furniture_b200.engine import Engine, default_config
+    from parity_util import build_emu
+
+    ikc = IK.ik_config(sawyer)
+    baxter = mjcf.load_scene("Baxter", "chair_ingolf_0650")
+    with pytest.raises(RuntimeError, match="one-arm"):
+        Engine(baxter, 1, config=default_config(), lib_path=build_emu(), ik=ikc)
+    with pytest.raises(RuntimeError, match="recipe"):
+        Engine(mjcf.load_scene("Sawyer", "swivel_chair_0700"), 1, config=default_config(), lib_path=build_emu(), dense=dense_config())
+    eng = Engine(sawyer, 1, config=default_config(), lib_path=build_emu())
+    bad = IK.ik_config(sawyer)
+    bad.struct_bytes = 12
+    assert eng.L.fe_enable_ik(eng.h, C.byref(bad)) < 0 and b"size mismatch" in eng.L.fe_last_error(eng.h)
+    assert eng.L.fe_action_dim(eng.h) == 9  # still the impedance handle
+    assert eng.L.fe_enable_ik(eng.h, C.byref(ikc)) == 0 and eng.L.fe_action_dim(eng.h) == 8
