@@ -123,6 +123,10 @@ class BatchedFurnitureEnv:
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
+        # control_type="ik": robot_ob is gripper_qpos, eef_pos, eef_quat, eef_velp, eef_velr only -- no joint positions / velocities
+        # (furniture_sawyer.py:110-125); the device row always holds all of it, the 15 numbers are its tail
+        self._robot_skip = 14 if control_type == "ik" else 0
+        self.robot_ob_dim -= self._robot_skip
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self.dof = self.act_dim
         self._obs = torch.empty((num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
@@ -144,8 +148,8 @@ class BatchedFurnitureEnv:
         return OrderedDict(default=(self.act_dim,))
 
     def _obs_dict(self, obs):
-        a, b = self.object_ob_dim, self.object_ob_dim + self.robot_ob_dim
-        d = OrderedDict(object_ob=obs[:, :a], robot_ob=obs[:, a:b])
+        a, b = self.object_ob_dim, self.object_ob_dim + self._robot_skip + self.robot_ob_dim
+        d = OrderedDict(object_ob=obs[:, :a], robot_ob=obs[:, a + self._robot_skip : b])
         if self.phase_ob_dim:
             d["phase_ob"] = obs[:, b:]
         return d

@@ -60,6 +60,8 @@ class FurnitureGymB200:
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
+        self._robot_skip = 14 if self.control_type == "ik" else 0  # ik: robot_ob has no joint positions / velocities (furniture_sawyer.py:110-125)
+        self.robot_ob_dim -= self._robot_skip
         self.dof = self.engine.act_dim
         self._max_episode_steps = self.cfg.max_episode_steps
         self._pending_ob = None  # observation of an episode the device has already started
@@ -89,8 +91,8 @@ class FurnitureGymB200:
             return OrderedDict(default=dict(shape=(self.dof,), low=-1.0, high=1.0))
 
     def _ob(self, obs_row):
-        a, b = self.object_ob_dim, self.object_ob_dim + self.robot_ob_dim
-        ob = OrderedDict(object_ob=obs_row[:a].astype(np.float64), robot_ob=obs_row[a:b].astype(np.float64))
+        a, b = self.object_ob_dim, self.object_ob_dim + self._robot_skip + self.robot_ob_dim
+        ob = OrderedDict(object_ob=obs_row[:a].astype(np.float64), robot_ob=obs_row[a + self._robot_skip : b].astype(np.float64))
         if self.phase_ob_dim:
             ob["phase_ob"] = obs_row[b:].astype(np.float64)
         return ob

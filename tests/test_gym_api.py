@@ -157,7 +157,9 @@ def test_ik_control_type_through_the_gym_surface():
         split_config(dict(control_type="position_orientation"))
     env = FurnitureGymB200(name="FurnitureSawyerEnv", lib_path=build_emu(), control_type="ik", move_speed=0.05, nsub=5, max_episode_steps=2)
     assert env.dof == 8 and abs(env.ik_cfg.move_speed - 0.05) < 1e-9 and env.ik_cfg.action_repeat == 3
-    env.reset()
+    ob = env.reset()
+    full = env.engine.get("obs")[0]
+    assert ob["robot_ob"].shape == (15,) and np.allclose(ob["robot_ob"], full[35 + 14 : 64])  # gripper_qpos, eef pos / quat / velp / velr (furniture_sawyer.py:43-48)
     a = np.zeros(8)
     a[0], a[-2], a[-1] = 1.0, -1.0, -1.0
     ob, r, done, info = env.step(a)
