@@ -29,6 +29,7 @@ struct fe_handle {
   FeDebug dbg;
   FeEnvState es;
   FeIkArgs ik = {nullptr, nullptr}; // control_type="ik" when ik.c is set (fe_enable_ik)
+  int ik_act_dim = 8;               // 9 for "ik_quaternion"
   int slice_words = 0;
   FeLayout lay;       // where each array of an env's slice starts (same for every env of the handle)
   std::vector<FeField> fields;
@@ -79,7 +80,7 @@ int fe_is_cuda(void) { return PLAT_IS_CUDA; }
 const char* fe_last_error(const fe_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int fe_num_envs(const fe_handle* h) { return h->N; }
 int fe_obs_dim(const fe_handle* h) { return h->hs.obs_dim; }
-int fe_action_dim(const fe_handle* h) { return h->ik.c ? 8 : h->hs.act_dim; }
+int fe_action_dim(const fe_handle* h) { return h->ik.c ? h->ik_act_dim : h->hs.act_dim; }
 int fe_info_dim(const fe_handle* h) { return FE_INFO_DIM; }
 int fe_smem_bytes_per_env(const fe_handle* h) { return (h->slice_words + FE_ENV_EXTRA_WORDS) * 4; }
 const float* fe_obs_dev(const fe_handle* h) { return h->es.obs; }
@@ -314,6 +315,7 @@ int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc) {
     add_field(h, "ik_state", st, (int)sizeof(FeIkState), 1, true);
   }
   plat_upload((void*)h->ik.c, ikc, sizeof(fe_ik_config));
+  h->ik_act_dim = ikc->quaternion_mode ? 9 : 8;
   return 0;
 }
 int fe_dense_info_dim(void) { return FE_DENSE_INFO; }

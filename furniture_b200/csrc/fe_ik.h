@@ -282,22 +282,28 @@ FE_HDN void fe_ik_command(FeEnv* e, const FeIkArgs& ik, const float* a, float gr
   const float mv[3] = {-a[1] * c->move_speed, a[0] * c->move_speed, a[2] * c->move_speed};
   float dpos[3];
   for (int k = 0; k < 3; ++k) dpos[k] = fminf(fmaxf(mv[k], c->min_pos[k] - hand_p[k]), c->max_pos[k] - hand_p[k]);
-  // euler_to_quat(action[3:6] * rotate_speed, s): q3 q2 q1 about z, y, x; s read as if (w, x, y, z)
-  float qe[4], t4[4], s_new[4];
-  {
-    const float hx = 0.5f * a[3] * c->rotate_speed * 0.017453292519943295f, hy = 0.5f * a[4] * c->rotate_speed * 0.017453292519943295f,
-                hz = 0.5f * a[5] * c->rotate_speed * 0.017453292519943295f;
-    const float q1[4] = {cosf(hx), sinf(hx), 0.f, 0.f}, q2[4] = {cosf(hy), 0.f, sinf(hy), 0.f}, q3[4] = {cosf(hz), 0.f, 0.f, sinf(hz)};
-    ik_hamilton(t4, q3, q2);
-    ik_hamilton(qe, t4, q1);
+  float rq[4], rot[9], Rw[9], tq[4], tp[3];
+  if (c->quaternion_mode) { // "ik_quaternion": rotation = quat2mat(cur * convert_quat(action[3:7])), furniture.py:3013, :3027 (_make_input)
+    const float aq[4] = {a[4], a[5], a[6], a[3]};
+    ik_xyzw_mul(rq, cur, aq);
+  } else {
+    // euler_to_quat(action[3:6] * rotate_speed, s): q3 q2 q1 about z, y, x; s read as if (w, x, y, z)
+    float qe[4], t4[4], s_new[4];
+    {
+      const float hx = 0.5f * a[3] * c->rotate_speed * 0.017453292519943295f, hy = 0.5f * a[4] * c->rotate_speed * 0.017453292519943295f,
+                  hz = 0.5f * a[5] * c->rotate_speed * 0.017453292519943295f;
+      const float q1[4] = {cosf(hx), sinf(hx), 0.f, 0.f}, q2[4] = {cosf(hy), 0.f, sinf(hy), 0.f}, q3[4] = {cosf(hz), 0.f, 0.f, sinf(hz)};
+      ik_hamilton(t4, q3, q2);
+      ik_hamilton(qe, t4, q1);
+    }
+    ik_hamilton(s_new, st->s, qe);
+    for (int k = 0; k < 4; ++k) st->s[k] = s_new[k];
+    // d_quat = quat_inverse(cur) * s; rotation = quat2mat(cur * d_quat)  (all (x, y, z, w))
+    float inv[4], dq[4];
+    { const float n = cur[0] * cur[0] + cur[1] * cur[1] + cur[2] * cur[2] + cur[3] * cur[3]; inv[0] = -cur[0] / n; inv[1] = -cur[1] / n; inv[2] = -cur[2] / n; inv[3] = cur[3] / n; }
+    ik_xyzw_mul(dq, inv, s_new);
+    ik_xyzw_mul(rq, cur, dq);
   }
-  ik_hamilton(s_new, st->s, qe);
-  for (int k = 0; k < 4; ++k) st->s[k] = s_new[k];
-  // d_quat = quat_inverse(cur) * s; rotation = quat2mat(cur * d_quat)  (all (x, y, z, w))
-  float inv[4], dq[4], rq[4], rot[9], Rw[9], tq[4], tp[3];
-  { const float n = cur[0] * cur[0] + cur[1] * cur[1] + cur[2] * cur[2] + cur[3] * cur[3]; inv[0] = -cur[0] / n; inv[1] = -cur[1] / n; inv[2] = -cur[2] / n; inv[3] = cur[3] / n; }
-  ik_xyzw_mul(dq, inv, s_new);
-  ik_xyzw_mul(rq, cur, dq);
   ik_xyzw_to_mat(rot, rq);
   for (int k = 0; k < 3; ++k) st->target_pos[k] += dpos[k] * c->user_sensitivity;
   m3mulv(t, Rb, st->target_pos);
@@ -315,11 +321,11 @@ FE_HDN void fe_ik_command(FeEnv* e, const FeIkArgs& ik, const float* a, float gr
 FE_FN void fe_env_ik_step_one(FeEnv* e, FeIkArgs ik, const float* action, float* reward_out, uint8_t* done_out, int32_t* info_out) {
   FeWarp* w = e->w;
   const fe_ik_config* c = ik.c;
-  const int act_dim = 8; // move 3, rotate 3, select (gripper), connect (furniture_sawyer.py:60-61)
+  const int act_dim = c->quaternion_mode ? 9 : 8; // move 3, rotate 3 (or a quaternion), select (gripper), connect (furniture_sawyer.py:60-63)
   const float* a = action + (size_t)e->env * act_dim;
-  float grip = a[6];
+  float grip = a[act_dim - 2];
   if (e->cfg->discrete_grip) grip = grip < 0.f ? -1.f : 1.f; // furniture_sawyer.py:73-74
-  const float connect = a[7];
+  const float connect = a[act_dim - 1];
   FeIkState* st = ik.st + e->env;
   LANES_BEGIN
     if (lane == 0) fe_ik_command(e, ik, a, grip);

@@ -42,8 +42,8 @@ def split_config(config):
     from .engine import FeConfig
 
     cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
-    if cfg.get("control_type", "impedance") not in ("impedance", "ik"):
-        raise NotImplementedError("control_type 'impedance' and 'ik' are accelerated (got %r)" % cfg["control_type"])
+    if cfg.get("control_type", "impedance") not in ("impedance", "ik", "ik_quaternion"):
+        raise NotImplementedError("control_type 'impedance', 'ik' and 'ik_quaternion' are accelerated (got %r)" % cfg["control_type"])
     for k in ("unity", "visual_ob", "depth_ob", "segmentation_ob", "record_demo", "record_vid"):
         if cfg.get(k):
             raise NotImplementedError("%s=True needs the renderer, which is outside the accelerated path" % k)
@@ -62,7 +62,7 @@ def control_options(config):
     cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
     ct = cfg.get("control_type") or "impedance"
     out = dict(control_type=ct)
-    if ct == "ik":
+    if ct in ("ik", "ik_quaternion"):
         out["ik"] = {k: cfg[k] for k in ("move_speed", "rotate_speed") if cfg.get(k) is not None}
     return out
 
@@ -86,8 +86,9 @@ class BatchedFurnitureEnv:
                  **cfg_overrides):
         """`dense`: None for the sparse reward of FurnitureEnv; a dict of coefficient overrides (possibly empty) for the phase-based
         reward of FurnitureSawyerDenseRewardEnv, computed inside the step kernel (furniture_b200/dense.py).
-        `control_type`: "impedance" (joint velocities, dof 9) or "ik" (move 3, rotate 3, gripper, connect: dof 8; the inverse kinematics
-        and its three closed-loop repeats run inside the step kernel, furniture_b200/ik.py); `ik`: overrides of ik.IK_DEFAULTS
+        `control_type`: "impedance" (joint velocities, dof 9), "ik" (move 3, rotate 3, gripper, connect: dof 8) or "ik_quaternion" (the
+        rotation as a quaternion relative to the hand: dof 9); the inverse kinematics and its three closed-loop repeats run inside the
+        step kernel (furniture_b200/ik.py); `ik`: overrides of ik.IK_DEFAULTS
         (move_speed, rotate_speed, action_repeat ...)."""
         import torch
 
@@ -109,14 +110,14 @@ class BatchedFurnitureEnv:
         self.dense_cfg = dense_config(**dense) if dense is not None else None
         self.control_type = control_type
         self.ik_cfg = None
-        if control_type == "ik":
+        if control_type in ("ik", "ik_quaternion"):
             if agent != "Sawyer":
-                raise NotImplementedError("control_type='ik' is built for the Sawyer env")
+                raise NotImplementedError("control_type='%s' is built for the Sawyer env" % control_type)
             from .ik import ik_config
 
-            self.ik_cfg = ik_config(self.model, **(ik or {}))
+            self.ik_cfg = ik_config(self.model, **dict(ik or {}, quaternion_mode=int(control_type == "ik_quaternion")))
         elif control_type != "impedance":
-            raise NotImplementedError("control_type 'impedance' and 'ik' are accelerated (got %r)" % control_type)
+            raise NotImplementedError("control_type 'impedance', 'ik' and 'ik_quaternion' are accelerated (got %r)" % control_type)
         self.engine = Engine(self.model, num_envs, device=device, config=self.cfg, dense=self.dense_cfg, ik=self.ik_cfg)
         self.num_envs = num_envs
         self.obs_dim, self.act_dim = self.engine.obs_dim, self.engine.act_dim
@@ -125,7 +126,7 @@ class BatchedFurnitureEnv:
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
         # control_type="ik": robot_ob is gripper_qpos, eef_pos, eef_quat, eef_velp, eef_velr only -- no joint positions / velocities
         # (furniture_sawyer.py:110-125); the device row always holds all of it, the 15 numbers are its tail
-        self._robot_skip = 14 if control_type == "ik" else 0
+        self._robot_skip = 14 if control_type in ("ik", "ik_quaternion") else 0
         self.robot_ob_dim -= self._robot_skip
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self.dof = self.act_dim
@@ -220,7 +221,7 @@ def make_vec_env(env_id="IKEASawyer-v0", num_env=1, config=None, device=0):
     else:
         furniture, over, ignored = split_config(config)
         env = BatchedFurnitureEnv(agent, furniture, num_env, device=device, **ctl, **over)
-    ignored = [k for k in ignored if k not in ("move_speed", "rotate_speed")] if ctl["control_type"] == "ik" else ignored
+    ignored = [k for k in ignored if k not in ("move_speed", "rotate_speed")] if "ik" in ctl else ignored
     env.ignored_config = ignored
     return env
 

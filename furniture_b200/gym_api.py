@@ -49,18 +49,18 @@ class FurnitureGymB200:
         self.cfg = default_config(**over)
         ctl = control_options(config)
         self.control_type, self.ik_cfg = ctl["control_type"], None
-        if self.control_type == "ik":  # the reference's default control type (config/furniture.py:57): move / rotate / gripper / connect
+        if self.control_type in ("ik", "ik_quaternion"):  # "ik" is the reference's default control type (config/furniture.py:57)
             if AGENTS[name] != "Sawyer":
-                raise NotImplementedError("control_type='ik' is built for the Sawyer env")
+                raise NotImplementedError("control_type='%s' is built for the Sawyer env" % self.control_type)
             from .ik import ik_config
 
-            self.ik_cfg = ik_config(self.model, **ctl["ik"])
+            self.ik_cfg = ik_config(self.model, **dict(ctl["ik"], quaternion_mode=int(self.control_type == "ik_quaternion")))
         self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path, dense=self.dense_cfg, ik=self.ik_cfg)
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
-        self._robot_skip = 14 if self.control_type == "ik" else 0  # ik: robot_ob has no joint positions / velocities (furniture_sawyer.py:110-125)
+        self._robot_skip = 14 if self.control_type in ("ik", "ik_quaternion") else 0  # ik: robot_ob has no joint positions / velocities (furniture_sawyer.py:110-125)
         self.robot_ob_dim -= self._robot_skip
         self.dof = self.engine.act_dim
         self._max_episode_steps = self.cfg.max_episode_steps

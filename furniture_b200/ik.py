@@ -9,6 +9,9 @@ _do_simulation) and replaces the solver by a damped-least-squares IK on the arm'
 (csrc/fe_ik.h); `solve_ik` below is the same algorithm in numpy float64 (the oracle's copy, oracle/ik_oracle.py, calls it).  The joint
 targets therefore differ from pybullet's within the arm's one-dimensional null space; the end-effector pose they reach is the same target.
 
+`quaternion_mode=1` is control_type="ik_quaternion" (furniture.py:2998-3058): move 3, a quaternion (w, x, y, z) relative to the hand's
+current orientation, gripper, connect -- 9 numbers, nothing accumulated.
+
   arm_chain(model)   -> the 7 joint frames from the robot base to `right_hand`, taken from the composed model at zero joint angles
   ik_config(model)   -> struct fe_ik_config (include/furniture_b200.h): gains, limits, rest pose, workspace, the chain
 """
@@ -29,7 +32,7 @@ UPPER = [3.05, 2.28, 3.05, 3.05, 2.98, 2.98, 4.71]
 
 class FeIkConfig(C.Structure):
     _fields_ = [
-        ("struct_bytes", i32), ("action_repeat", i32), ("max_iters", i32), ("pad_", i32),
+        ("struct_bytes", i32), ("action_repeat", i32), ("max_iters", i32), ("quaternion_mode", i32),
         ("move_speed", f32), ("rotate_speed", f32), ("user_sensitivity", f32), ("kp", f32), ("damping", f32), ("null_gain", f32),
         ("tol_pos", f32), ("tol_rot", f32), ("max_step_pos", f32), ("max_step_rot", f32),
         ("min_pos", f32 * 3), ("max_pos", f32 * 3), ("rest_pose", f32 * NJ), ("lower", f32 * NJ), ("upper", f32 * NJ),
@@ -70,7 +73,7 @@ def arm_chain(m: mjcf.Model):
     return ch
 
 
-IK_DEFAULTS = dict(action_repeat=3, max_iters=20, move_speed=0.1, rotate_speed=22.5, user_sensitivity=0.3, kp=5.0, damping=0.1, null_gain=0.0,
+IK_DEFAULTS = dict(quaternion_mode=0, action_repeat=3, max_iters=20, move_speed=0.1, rotate_speed=22.5, user_sensitivity=0.3, kp=5.0, damping=0.1, null_gain=0.0,
                    tol_pos=1e-4, tol_rot=1e-3, max_step_pos=0.05, max_step_rot=0.2, min_pos=(-1.5, -1.5, 0.0), max_pos=(1.5, 1.5, 1.5))
 
 
@@ -90,7 +93,7 @@ def ik_config(m: mjcf.Model, **kw) -> FeIkConfig:
     p = ik_params(m, **kw)
     c = FeIkConfig()
     c.struct_bytes = C.sizeof(FeIkConfig)
-    for k in ("action_repeat", "max_iters"):
+    for k in ("action_repeat", "max_iters", "quaternion_mode"):
         setattr(c, k, int(p[k]))
     for k in ("move_speed", "rotate_speed", "user_sensitivity", "kp", "damping", "null_gain", "tol_pos", "tol_rot", "max_step_pos", "max_step_rot"):
         setattr(c, k, float(p[k]))

@@ -141,7 +141,8 @@ int fe_dense_eval(fe_handle* h, const fe_dense_config* dc, const void* recipe_bl
  * joint damping 0.1, rest pose, limits: sawyer_ik_controller.py.  The chain (host: furniture_b200/ik.py: arm_chain) lists, per arm joint,
  * its body frame in the previous joint body's frame at zero angle and the hinge (anchor, axis) in its body frame. */
 typedef struct fe_ik_config {
-  int32_t struct_bytes, action_repeat, max_iters, pad_;
+  int32_t struct_bytes, action_repeat, max_iters;
+  int32_t quaternion_mode; /* 1: control_type="ik_quaternion" (furniture.py:2998-3058): actions are move 3, quaternion (w,x,y,z) relative to the hand, gripper, connect */
   float move_speed, rotate_speed, user_sensitivity, kp, damping, null_gain, tol_pos, tol_rot, max_step_pos, max_step_rot;
   float min_pos[3], max_pos[3], rest_pose[7], lower[7], upper[7];
   float link_pos[7][3], link_quat[7][4], jaxis[7][3], jpos[7][3];

@@ -78,6 +78,17 @@ def ik_pre(action, hand_pos_world, hand_quat_base, s, p):
     return d_pos, rotation, s_new, a[-2]
 
 
+def ik_pre_quaternion(action, hand_pos_world, hand_quat_base, p):
+    """control_type="ik_quaternion" (furniture.py:2998-3058): action = move 3, quaternion (w, x, y, z) relative to the hand's current
+    orientation, gripper, connect -> (dpos, rotation in the base frame, gripper action)"""
+    a = np.array(action, dtype=np.float64)
+    d = a[:3] * p["move_speed"]
+    d_pos = np.clip([-d[1], d[0], d[2]], np.asarray(p["min_pos"]) - hand_pos_world, np.asarray(p["max_pos"]) - hand_pos_world)
+    arm_quat = a[3:7][[1, 2, 3, 0]]  # T.convert_quat(..., to="xyzw")
+    rotation = quat2mat(quat_multiply(hand_quat_base, arm_quat))
+    return d_pos, rotation, a[7]
+
+
 class IKOracle:
     """one arm: the accumulated orientation target, the position target in the base frame, the commanded joints"""
 
@@ -100,7 +111,10 @@ class IKOracle:
     def command(self, action, hand_pos_world, hand_quat_world_wxyz, jpos):
         """first get_control of an env step: new targets, IK from the current joints, then the P controller"""
         _, Rb = self.to_base(hand_pos_world, hand_quat_world_wxyz)
-        d_pos, rotation, self.s, grip = ik_pre(action, hand_pos_world, mat2quat(Rb), self.s, self.p)
+        if self.p.get("quaternion_mode"):
+            d_pos, rotation, grip = ik_pre_quaternion(action, hand_pos_world, mat2quat(Rb), self.p)
+        else:
+            d_pos, rotation, self.s, grip = ik_pre(action, hand_pos_world, mat2quat(Rb), self.s, self.p)
         self.target_pos = self.target_pos + d_pos * self.p["user_sensitivity"]
         tp = self.base_p + self.base_R @ self.target_pos
         tq = mjcf.mat_to_q(self.base_R @ rotation)

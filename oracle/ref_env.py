@@ -395,7 +395,7 @@ class IKMixin:
         self.ikp = IK.ik_params(self.m, **ik_kw)
         self.ik = IKOracle(self.ikp)
         self.hand = self.m.names["body"].index("right_hand")
-        self.dof = 8  # move 3, rotate 3, gripper, connect (furniture_sawyer.py:60-61)
+        self.dof = 9 if self.ikp.get("quaternion_mode") else 8  # move 3, rotate 3 (or a quaternion), gripper, connect (furniture_sawyer.py:60-63)
 
     def _hand(self):
         b = self.hand

@@ -32,6 +32,17 @@ def test_ik_step_preamble_equals_the_reference_code():
         assert grip == g["low_grip"][i]
 
 
+def test_ik_quaternion_preamble_equals_the_reference_code():
+    g = np.load(os.path.join(HERE, "golden", "ik_pre.npz"))
+    p = dict(IK.IK_DEFAULTS)
+    assert set(g["q_n_sim"]) == {3} and set(g["q_n_closed_loop"]) == {2}
+    for i in range(len(g["q_action"])):
+        hq = O.mat2quat(g["q_hand_R"][i].reshape(3, 3))
+        d_pos, rot, grip = O.ik_pre_quaternion(g["q_action"][i], g["q_hand_pos"][i], hq, p)
+        assert np.array_equal(d_pos, g["q_dpos"][i]) and grip == g["q_low_grip"][i], i
+        assert np.abs(rot - g["q_rotation"][i].reshape(3, 3)).max() < 2e-6, i
+
+
 def test_chain_and_solver_reach_the_commanded_hand_pose(sawyer):
     m = sawyer
     p = IK.ik_params(m)
@@ -53,12 +64,12 @@ def test_chain_and_solver_reach_the_commanded_hand_pose(sawyer):
 
 
 # ------------------------------------------------------------------ the IK env: device step against the CPU env
-def _ik_engine(m, n, gpu, **cfg):
+def _ik_engine(m, n, gpu, quaternion_mode=0, **cfg):
     from furniture_b200.engine import Engine, default_config
     from parity_util import build_emu
 
     c = default_config(**cfg)
-    ikc = IK.ik_config(m)
+    ikc = IK.ik_config(m, quaternion_mode=quaternion_mode)
     return Engine(m, n, device=0, config=c, ik=ikc) if gpu else Engine(m, n, config=c, lib_path=build_emu(), ik=ikc)
 
 
@@ -68,7 +79,10 @@ def _ik_state(eng, i):
     return dict(s=f[0:4], target_pos=f[4:7], q_cmd=f[7:14], low=f[14:22], iters=int(np.frombuffer(raw[22 * 4 : 23 * 4], np.int32)[0]))
 
 
-@pytest.mark.parametrize("gpu", BACKENDS)
+QUAT_BACKENDS = BACKENDS + [pytest.param("emu-quaternion", id="emu-ik_quaternion")]  # the quaternion variant: lane-emulated build only
+
+
+@pytest.mark.parametrize("gpu", QUAT_BACKENDS)
 def test_ik_env_steps_match_the_cpu_env(sawyer, gpu):
     """reset + 3 env steps with control_type="ik" (8-number actions, three closed-loop repeats of 50 mj_steps): targets, joint command,
     low-level action, observation, reward of the device equal the CPU env (oracle physics + the float64 copy of the solver)"""
@@ -77,10 +91,13 @@ def test_ik_env_steps_match_the_cpu_env(sawyer, gpu):
 
     m = sawyer
     n = 2
-    eng = _ik_engine(m, n, gpu)
-    assert eng.act_dim == 8
+    quat = gpu == "emu-quaternion"
+    gpu = False if quat else gpu
+    eng = _ik_engine(m, n, gpu, quaternion_mode=int(quat))
+    dof = 9 if quat else 8
+    assert eng.act_dim == dof
     eng.env_reset()
-    envs = [OracleIKEnv(m) for _ in range(n)]
+    envs = [OracleIKEnv(m, quaternion_mode=int(quat)) for _ in range(n)]
     lpos, lquat = eng.get("link_xpos"), eng.get("link_xquat")
     for i, e in enumerate(envs):
         e.reset()
@@ -96,8 +113,12 @@ def test_ik_env_steps_match_the_cpu_env(sawyer, gpu):
         e._hand0 = (hp, hq)
     rng = np.random.RandomState(3)
     for k in range(3):
-        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        a = rng.uniform(-1, 1, (n, dof)).astype(np.float32)
         a[:, -1] = -0.5
+        if quat:  # a small rotation relative to the hand, (w, x, y, z)
+            v = rng.normal(size=(n, 3)) * 0.05
+            a[:, 3], a[:, 4:7] = 1.0, v
+            a[:, 3:7] /= np.linalg.norm(a[:, 3:7], axis=1, keepdims=True)
         if k == 0:  # first step: the oracle's sim.data would be one integration newer than the device's stored kinematics; show it the same hand pose
             for e in envs:
                 e._hand = lambda hp_hq=e._hand0: hp_hq
@@ -108,7 +129,7 @@ def test_ik_env_steps_match_the_cpu_env(sawyer, gpu):
                 del e._hand
             st = _ik_state(eng, i)
             assert np.abs(st["target_pos"] - e.ik.target_pos).max() < 2e-6, (k, i)
-            assert min(np.abs(st["s"] - e.ik.s).max(), np.abs(st["s"] + e.ik.s).max()) < 1e-5, (k, i)
+            assert quat or min(np.abs(st["s"] - e.ik.s).max(), np.abs(st["s"] + e.ik.s).max()) < 1e-5, (k, i)
             assert np.abs(st["q_cmd"] - e.ik.q_cmd).max() < 2e-4, (k, i, st["q_cmd"], e.ik.q_cmd)
             assert np.abs(st["low"] - e.low_action).max() < 2e-3, (k, i, st["low"], e.low_action)
             assert np.abs(obs[i] - ob).max() < 1e-3, (k, i, np.abs(obs[i] - ob).max())

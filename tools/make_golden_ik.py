@@ -69,7 +69,52 @@ def main():
         rec["dpos"].append(calls["first"][0]); rec["rotation"].append(calls["first"][1].ravel())
         rec["s_out"].append(np.asarray(fake._initial_right_hand_quat, dtype=np.float64)); rec["low_grip"].append(fake.low[7])
         rec["n_sim"].append(calls["sim"]); rec["n_closed_loop"].append(calls["closed"])
-    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{k: np.array(v) for k, v in rec.items()},
+    # ---- control_type="ik_quaternion" (furniture.py:2998-3058): displacement as above, the rotation given as a quaternion (w, x, y, z)
+    # relative to the hand's current orientation; nothing is accumulated
+    rq = {k: [] for k in ("action", "hand_pos", "hand_R", "dpos", "rotation", "low_grip", "n_sim", "n_closed_loop")}
+    for n in range(300):
+        hand_R = rand_rot(rng)
+        hand_pos = rng.uniform(-1.6, 1.6, size=3) if n % 3 == 0 else rng.uniform(-0.5, 0.5, size=3) + [0, 0, 0.6]
+        calls = dict(sim=0, closed=0, first=None)
+
+        class CtlQ:
+            def get_control(self, dpos=None, rotation=None):
+                if dpos is None:
+                    calls["closed"] += 1
+                else:
+                    calls["first"] = (np.array(dpos, dtype=np.float64), np.array(rotation, dtype=np.float64))
+                return np.zeros(7)
+
+        class FakeQ:
+            _control_type, _agent_type, _record_demo, _action_repeat, _arms = "ik_quaternion", "Sawyer", False, 3, ["right"]
+            _move_speed, _rotate_speed = 0.1, 22.5
+            _min_gripper_pos, _max_gripper_pos = np.array([-1.5, -1.5, 0.0]), np.array([1.5, 1.5, 1.5])
+            _controller = CtlQ()
+            sim = types.SimpleNamespace(data=types.SimpleNamespace(get_body_xpos=lambda name: hand_pos.copy()))
+            _bounded_d_pos = FurnitureEnv._bounded_d_pos
+            _make_input = FurnitureEnv._make_input
+
+            @property
+            def _right_hand_quat(self):
+                return T.mat2quat(np.ascontiguousarray(hand_R, dtype=np.float32))
+
+            def _setup_action(self, low):
+                self.low = np.array(low, dtype=np.float64)
+                return low
+
+            def _do_simulation(self, ctrl):
+                calls["sim"] += 1
+
+        fq = FakeQ()
+        a = rng.uniform(-1, 1, size=9)
+        q = rng.normal(size=4)
+        a[3:7] = q / np.linalg.norm(q) * (1.0 if n % 4 else 1.3)  # now and then not a unit quaternion: quat2mat normalises
+        FurnitureEnv._do_ik_step(fq, a.copy())
+        rq["action"].append(a); rq["hand_pos"].append(hand_pos); rq["hand_R"].append(hand_R.ravel())
+        rq["dpos"].append(calls["first"][0]); rq["rotation"].append(calls["first"][1].ravel()); rq["low_grip"].append(fq.low[7])
+        rq["n_sim"].append(calls["sim"]); rq["n_closed_loop"].append(calls["closed"])
+    print("ik_quaternion: %d cases" % len(rq["action"]))
+    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{"q_" + k: np.array(v) for k, v in rq.items()}, **{k: np.array(v) for k, v in rec.items()},
                         source="reference FurnitureEnv._do_ik_step run unmodified around stand-ins for the simulator and the pybullet controller (tools/make_golden_ik.py)")
     print("ik_pre: %d cases; _do_simulation calls %s, closed-loop get_control calls %s" % (len(rec["action"]), set(rec["n_sim"]), set(rec["n_closed_loop"])))
 
