@@ -510,3 +510,17 @@ class OracleDenseEnv(OracleFurnitureEnv):
         reward, done, self.dense_info = self.dense.step(np.asarray(raw, dtype=np.float64), connected)
         base_done = self.num_connected == self.npart - 1 and self.npart > 1  # FurnitureEnv._step, furniture.py:438-445
         return reward, bool(done or base_done), self.dense.success
+
+
+class OracleDenseIKEnv(IKMixin, OracleDenseEnv):
+    """the dense-reward env driven through control_type="ik" (the combination the reference's training scripts use: env id
+    IKEASawyerDense-v0 with the default control type)"""
+
+    def __init__(self, model, cfg=None, dense_cfg=None, **ik_kw):
+        OracleDenseEnv.__init__(self, model, cfg, dense_cfg)
+        self._ik_setup(**ik_kw)
+
+    def reset(self):
+        ob = OracleDenseEnv.reset(self)
+        self._ik_sync()
+        return ob

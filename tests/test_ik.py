@@ -188,3 +188,44 @@ def test_enable_ik_and_dense_refuse_what_they_cannot_serve(sawyer):
     assert eng.L.fe_enable_ik(eng.h, C.byref(bad)) < 0 and b"size mismatch" in eng.L.fe_last_error(eng.h)
     assert eng.L.fe_action_dim(eng.h) == 9  # still the impedance handle
     assert eng.L.fe_enable_ik(eng.h, C.byref(ikc)) == 0 and eng.L.fe_action_dim(eng.h) == 8
+
+
+def test_dense_reward_under_ik_control_matches_the_cpu_env(sawyer):
+    """IKEASawyerDense-v0 with the reference's default control type: the phase machine reads the policy's 8-number action (gripper = ac[-2],
+    connect = ac[-1], control penalty on ac[:-2]) while the arm is driven by the IK's joint velocities -- device vs CPU env, emulated build"""
+    from furniture_b200.dense import dense_config
+    from furniture_b200.engine import Engine, default_config
+    from oracle.ref_env import DenseCfg, OracleDenseIKEnv
+    from parity_util import build_emu
+    from test_dense_reward import DENSE_BASE, _adopt_device_anchors, _assert_same_machine, _dense_state
+    from test_env_parity import _sync_oracle_from_engine
+
+    m = sawyer
+    eng = Engine(m, 1, config=default_config(**DENSE_BASE), lib_path=build_emu(), dense=dense_config(), ik=IK.ik_config(m))
+    eng.env_reset()
+    e = OracleDenseIKEnv(m, DenseCfg())
+    e.reset()
+    _sync_oracle_from_engine(e, eng, 0)
+    e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[0]
+    hl = eng.scene.hand_link[0]
+    lp, lq = eng.get("link_xpos")[0], eng.get("link_xquat")[0]
+    R = mjcf.q_to_mat(lq[4 * hl : 4 * hl + 4].astype(np.float64))
+    hand0 = (lp[3 * hl : 3 * hl + 3].astype(np.float64) + R @ np.array(eng.ik.hand_pos[:]),
+             mjcf.q_norm(mjcf.q_mul(lq[4 * hl : 4 * hl + 4].astype(np.float64), np.array(eng.ik.hand_quat[:], dtype=np.float64))))
+    e.ik.sync(*hand0)
+    e.dense.begin_episode()
+    _adopt_device_anchors(e.dense, _dense_state(eng, 0))
+    rng = np.random.RandomState(4)
+    for k in range(2):
+        a = rng.uniform(-1, 1, (1, 8)).astype(np.float32)
+        a[0, -1] = -0.5
+        if k == 0:
+            e._hand = lambda: hand0
+        obs, rew, done, info = eng.env_step_host(a)
+        ob, r, d, inf = e.step(a[0].astype(np.float64))
+        if k == 0:
+            del e._hand
+        assert abs(rew[0] - r) < 5e-2 + 1e-5 * abs(r), (k, rew[0], r)
+        assert abs(eng.get("dense_info")[0][3] - e.dense_info["ctrl_penalty"]) < 1e-6  # -coef * |ac[:-2]| over six numbers
+        _assert_same_machine(_dense_state(eng, 0), e.dense, k, tol=5e-4)
+        assert np.abs(obs[0] - ob).max() < 1e-3 and bool(done[0]) == d
