@@ -229,3 +229,37 @@ def test_dense_reward_under_ik_control_matches_the_cpu_env(sawyer):
         assert abs(eng.get("dense_info")[0][3] - e.dense_info["ctrl_penalty"]) < 1e-6  # -coef * |ac[:-2]| over six numbers
         _assert_same_machine(_dense_state(eng, 0), e.dense, k, tol=5e-4)
         assert np.abs(obs[0] - ob).max() < 1e-3 and bool(done[0]) == d
+
+
+def test_unstable_ik_step_resets_mid_step_and_once_more_at_the_end(sawyer):
+    """a _do_simulation that blows up inside _do_ik_step resets the env on the spot and the remaining repeats run on the new episode
+    (furniture.py:2889-2897 inside the loop of :2977-2995); the step then ends the episode with the unstable penalty and the VecEnv worker
+    resets again: three resets' worth of random draws in all, like the impedance path"""
+    from oracle.ref_env import Cfg, OracleFurnitureEnv
+
+    m, seed = sawyer, 99
+    eng = _ik_engine(m, 2, False, seed=seed, nsub=2)
+    eng.env_reset()
+    v = eng.get("qvel").copy()
+    v[1, 0] = 1e8
+    eng.set("qvel", v)
+    a = np.zeros((2, 8), np.float32)
+    a[:, -1] = -1
+    obs, rew, done, info = eng.env_step_host(a)
+    assert not done[0] and done[1] and info[1][2] == 1 and info[0][2] == 0 and rew[1] < -50
+    ln, pos, st = eng.get("episode_length")[:, 0], eng.get("mt_pos")[:, 0], eng.get("mt_state")
+    assert ln[0] == 1 and ln[1] == 0
+    for i, nreset in ((0, 1), (1, 3)):
+        cfg = Cfg()
+        cfg.seed = seed + i
+        e = OracleFurnitureEnv(m, cfg)
+        for _ in range(nreset):
+            e.place()
+            for _ in range(101):
+                e.rng.uniform(-cfg.agent_xyz_rand, cfg.agent_xyz_rand, e.narm)
+        s = e.rng.get_state()
+        assert s[2] == pos[i] and np.array_equal(s[1], st[i]), i
+    assert np.isfinite(obs).all() and (eng.get("flags")[:, 0] & 8 == 0).all()
+    obs, rew, done, info = eng.env_step_host(a)
+    assert info[1][3] == 1 and info[0][3] == 2 and not done.any()
+    assert np.isfinite(eng.get("ik_state")[1].view(np.float32)[:22]).all()  # the new episode's targets were re-synchronised from a sane pose
