@@ -9,6 +9,7 @@
 
 #include "../../include/furniture_b200.h"
 #include "fe_ik.h"
+#include "fe_ctl.h"
 
 struct FeField {
   std::string name;
@@ -30,6 +31,8 @@ struct fe_handle {
   FeEnvState es;
   FeIkArgs ik = {nullptr, nullptr}; // control_type="ik" when ik.c is set (fe_enable_ik)
   int ik_act_dim = 8;               // 9 for "ik_quaternion"
+  FeCtlArgs ctl = {nullptr, nullptr}; // one of the NEW_CONTROLLERS when ctl.c is set (fe_enable_controller)
+  int ctl_act_dim = 0;
   int slice_words = 0;
   FeLayout lay;       // where each array of an env's slice starts (same for every env of the handle)
   std::vector<FeField> fields;
@@ -80,7 +83,7 @@ int fe_is_cuda(void) { return PLAT_IS_CUDA; }
 const char* fe_last_error(const fe_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int fe_num_envs(const fe_handle* h) { return h->N; }
 int fe_obs_dim(const fe_handle* h) { return h->hs.obs_dim; }
-int fe_action_dim(const fe_handle* h) { return h->ik.c ? h->ik_act_dim : h->hs.act_dim; }
+int fe_action_dim(const fe_handle* h) { return h->ctl.c ? h->ctl_act_dim : (h->ik.c ? h->ik_act_dim : h->hs.act_dim); }
 int fe_info_dim(const fe_handle* h) { return FE_INFO_DIM; }
 int fe_smem_bytes_per_env(const fe_handle* h) { return (h->slice_words + FE_ENV_EXTRA_WORDS) * 4; }
 const float* fe_obs_dev(const fe_handle* h) { return h->es.obs; }
@@ -303,6 +306,7 @@ int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc) {
   if (!ikc || ikc->struct_bytes != (int32_t)sizeof(fe_ik_config)) return fail(h, -1, "fe_enable_ik: fe_ik_config size mismatch");
   if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_enable_ik: handle was created without a scene blob");
   if (h->hs.narms != 1 || h->hs.narm != 7 || h->hs.hand_link[0] < 0 || h->hs.act_dim != 9) return fail(h, -1, "fe_enable_ik: the IK control type is built for the one-arm 7-joint (Sawyer) env");
+  if (h->ctl.c) return fail(h, -1, "fe_enable_ik: the handle already runs a torque controller");
   if (ikc->action_repeat < 1 || ikc->action_repeat > 16 || ikc->max_iters < 1 || ikc->max_iters > 1000) return fail(h, -1, "fe_enable_ik: action_repeat / max_iters out of range");
   for (int k = 0; k < 7; ++k) if (ikc->arm_qadr[k] < 0 || ikc->arm_qadr[k] >= h->hm.nq) return fail(h, -1, "fe_enable_ik: arm_qadr outside qpos");
   FeDevScope dev_scope(h);
@@ -317,6 +321,36 @@ int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc) {
   plat_upload((void*)h->ik.c, ikc, sizeof(fe_ik_config));
   h->ik_act_dim = ikc->quaternion_mode ? 9 : 8;
   return 0;
+}
+int fe_enable_controller(fe_handle* h, const fe_ctl_config* cc) {
+  if (!cc || cc->struct_bytes != (int32_t)sizeof(fe_ctl_config)) return fail(h, -1, "fe_enable_controller: fe_ctl_config size mismatch");
+  if (cc->mode < 0 || cc->mode > FE_CTL_POS || cc->control_dim < 1 || cc->control_dim > 7 || !(cc->ramp_steps >= 1.0)) return fail(h, -1, "fe_enable_controller: bad controller parameters");
+  if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_enable_controller: handle was created without a scene blob");
+  if (h->hs.narms != 1 || h->hs.narm != 7 || h->hs.hand_link[0] < 0) return fail(h, -1, "fe_enable_controller: built for the one-arm 7-joint (Sawyer) env");
+  if (h->ik.c) return fail(h, -1, "fe_enable_controller: the handle already runs the IK control type");
+  for (int u = 0; u < h->hm.nu; ++u) // ctrl = qfrc_bias + torques only means torques on motor actuators (robot_torque.xml)
+    if (h->hs.act_src[u] < h->hs.narm && (h->hm.act_gain[u] != 1.f || h->hm.act_bias[u][1] != 0.f || h->hm.act_bias[u][2] != 0.f))
+      return fail(h, -1, "fe_enable_controller: the arm's actuators are not motors (compose the scene with the torque-actuated robot)");
+  FeDevScope dev_scope(h);
+  if (!h->ctl.c) {
+    fe_ctl_config* d = (fe_ctl_config*)plat_alloc(sizeof(fe_ctl_config));
+    FeCtlState* st = h_alloc<FeCtlState>(h, (size_t)h->N);
+    if (!d || !st) return fail(h, -2, "fe_enable_controller: device allocation failed");
+    h->allocs.push_back(d);
+    h->ctl.c = d; h->ctl.st = st;
+    add_field(h, "ctl_state", st, (int)sizeof(FeCtlState), 1, true);
+  }
+  plat_upload((void*)h->ctl.c, cc, sizeof(fe_ctl_config));
+  h->ctl_act_dim = cc->control_dim + 2;
+  return 0;
+}
+int fe_ctl_eval(fe_handle* h, const fe_ctl_config* cc, int n_episodes, const int32_t* first, const int32_t* count, int n_records, const uint8_t* reset,
+                const uint8_t* policy_step, const double* action, const double* readings, double* torques) {
+  if (!cc || cc->struct_bytes != (int32_t)sizeof(fe_ctl_config)) return fail(h, -1, "fe_ctl_eval: fe_ctl_config size mismatch");
+  if (cc->mode < 0 || cc->mode > FE_CTL_POS || cc->control_dim < 1 || cc->control_dim > 7 || !(cc->ramp_steps >= 1.0)) return fail(h, -1, "fe_ctl_eval: bad controller parameters");
+  static_assert(sizeof(FeCtlIn) == 123 * sizeof(double), "FeCtlIn is the 123-double reading record of the C-ABI");
+  if (n_episodes <= 0 || n_records <= 0) return 0;
+  return plat_ctl_eval(h, cc, n_episodes, first, count, n_records, reset, policy_step, action, (const FeCtlIn*)readings, torques);
 }
 int fe_dense_info_dim(void) { return FE_DENSE_INFO; }
 size_t fe_dense_recipe_sizeof(void) { return sizeof(fe_dense_recipe); }

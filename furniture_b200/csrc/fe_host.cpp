@@ -41,6 +41,8 @@ static int plat_dense_eval(fe_handle* h, const struct fe_dense_config* dc, const
                            const int32_t* first, const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* spos, const double* smat,
                            const double* ppos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward,
                            uint8_t* done, double* info);
+static int plat_ctl_eval(fe_handle* h, const struct fe_ctl_config* cc, int n_episodes, const int32_t* first, const int32_t* count, int n_records, const uint8_t* reset,
+                         const uint8_t* policy_step, const double* action, const struct FeCtlIn* in, double* torques);
 
 #include "fe_api.inl"
 
@@ -50,6 +52,9 @@ extern "C" const unsigned char fe_cubin_start[];
 // the IK step kernel is a module of its own (fe_kernels_ik.cu): the stock kernels stay the binary they were profiled as
 __asm__(".section .rodata\n.balign 16\n.global fe_cubin_ik_start\nfe_cubin_ik_start:\n.incbin \"" FE_CUBIN_IK_FILE "\"\n.global fe_cubin_ik_end\nfe_cubin_ik_end:\n.byte 0\n.previous\n");
 extern "C" const unsigned char fe_cubin_ik_start[];
+// likewise the torque controllers (fe_kernels_ctl.cu)
+__asm__(".section .rodata\n.balign 16\n.global fe_cubin_ctl_start\nfe_cubin_ctl_start:\n.incbin \"" FE_CUBIN_CTL_FILE "\"\n.global fe_cubin_ctl_end\nfe_cubin_ctl_end:\n.byte 0\n.previous\n");
+extern "C" const unsigned char fe_cubin_ctl_start[];
 
 struct DriverApi {
   CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
@@ -96,6 +101,8 @@ struct FeModule {
   CUfunction f_sim, f_step, f_reset, f_order, f_aligned, f_dense;
   CUmodule mod_ik = nullptr;     // loaded when a handle of this (device, layout) first steps with control_type="ik"
   CUfunction f_ik_step = nullptr;
+  CUmodule mod_ctl = nullptr;    // the torque controllers' module, loaded on first use
+  CUfunction f_ctl_step = nullptr, f_ctl_eval = nullptr;
   int users;
 };
 static std::vector<FeModule*> g_modules;
@@ -235,6 +242,7 @@ static void plat_fini(fe_handle* h) {
         if (g_modules[i] == p->km) { g_modules.erase(g_modules.begin() + i); break; }
       g_drv.ModuleUnload(p->km->mod);
       if (p->km->mod_ik) g_drv.ModuleUnload(p->km->mod_ik);
+      if (p->km->mod_ctl) g_drv.ModuleUnload(p->km->mod_ctl);
       delete p->km;
     }
   }
@@ -273,11 +281,36 @@ static int plat_module_ik(fe_handle* h) {
   m->mod_ik = mod; m->f_ik_step = f;
   return 0;
 }
+static int plat_module_ctl(fe_handle* h) {
+  CudaPlat* p = (CudaPlat*)h->plat;
+  std::lock_guard<std::mutex> lock(g_mu);
+  FeModule* m = p->km;
+  if (m->f_ctl_step) return 0;
+  CUmodule mod = nullptr;
+  CUfunction f = nullptr, fe = nullptr;
+  CUresult r = g_drv.ModuleLoadData(&mod, fe_cubin_ctl_start);
+  if (r != CUDA_SUCCESS) return fail(h, -10, "cuModuleLoadData(embedded controller cubin): " + drv_err(r));
+  r = g_drv.ModuleGetFunction(&f, mod, "fe_env_ctl_step_kernel");
+  if (r == CUDA_SUCCESS) r = g_drv.ModuleGetFunction(&fe, mod, "fe_ctl_eval_kernel");
+  CUdeviceptr sym = 0;
+  size_t bytes = 0;
+  if (r == CUDA_SUCCESS) r = g_drv.ModuleGetGlobal(&sym, &bytes, mod, "fe_c_lay");
+  if (r == CUDA_SUCCESS && bytes != sizeof(FeLayout)) r = CUDA_ERROR_INVALID_VALUE;
+  if (r == CUDA_SUCCESS) r = g_drv.MemcpyHtoD(sym, &h->lay, sizeof(FeLayout));
+  if (r == CUDA_SUCCESS) r = g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 227 * 1024);
+  if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(mod); return fail(h, -10, "controller module set-up: " + drv_err(r)); }
+  m->mod_ctl = mod; m->f_ctl_step = f; m->f_ctl_eval = fe;
+  return 0;
+}
 static int launch_step(fe_handle* h, const float* actions, float* reward, uint8_t* done, int32_t* info, cudaStream_t stream) {
   CudaPlat* p = (CudaPlat*)h->plat;
   int slice_words = h->slice_words;
   const int* slots = p->slots;
-  if (h->ik.c) { // control_type="ik": same launch shape, the IK kernel of the second module
+  if (h->ctl.c) { // one of the NEW_CONTROLLERS: same launch shape, the kernel of the controllers' module
+    if (int rc = plat_module_ctl(h)) return rc;
+    void* a[] = {&h->st, &h->es, &h->ctl, &h->dm, &h->ds, &h->cfg, &h->opt, &actions, &reward, &done, &info, &slice_words, &slots};
+    if (int rc = launch(h, p->km->f_ctl_step, p->nblocks, 32 * p->wpb, p->smem_env, stream, a)) return rc;
+  } else if (h->ik.c) { // control_type="ik": same launch shape, the IK kernel of the second module
     if (int rc = plat_module_ik(h)) return rc;
     void* a[] = {&h->st, &h->es, &h->ik, &h->dm, &h->ds, &h->cfg, &h->opt, &actions, &reward, &done, &info, &slice_words, &slots};
     if (int rc = launch(h, p->km->f_ik_step, p->nblocks, 32 * p->wpb, p->smem_env, stream, a)) return rc;
@@ -417,6 +450,39 @@ static int plat_dense_eval(fe_handle* h, const fe_dense_config* dc, const fe_den
         cudaMemcpy(info, d_info, 8 * R * FE_DENSE_INFO, cudaMemcpyDeviceToHost) != cudaSuccess)
       rcode = fail(h, -10, std::string("fe_dense_eval: ") + cudaGetErrorString(cudaGetLastError()));
   }
+  for (void* b : bufs) cudaFree(b);
+  return rcode;
+}
+static int plat_ctl_eval(fe_handle* h, const fe_ctl_config* cc, int n_episodes, const int32_t* first, const int32_t* count, int n_records, const uint8_t* reset,
+                         const uint8_t* policy_step, const double* action, const FeCtlIn* in, double* torques) {
+  DevScope dev(h);
+  if (int rc_ = plat_prepare(h)) return rc_;
+  if (int rc_ = plat_module_ctl(h)) return rc_;
+  CudaPlat* p = (CudaPlat*)h->plat;
+  const size_t R = n_records, E = n_episodes;
+  std::vector<void*> bufs;
+  bool bad = false;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes ? bytes : 8) != cudaSuccess) { bad = true; return nullptr; }
+    bufs.push_back(d);
+    if (src && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) bad = true;
+    return d;
+  };
+  void* d_c = up(cc, sizeof(fe_ctl_config));
+  void* d_first = up(first, 4 * E);
+  void* d_count = up(count, 4 * E);
+  void* d_reset = up(reset, R);
+  void* d_pol = up(policy_step, R);
+  void* d_act = up(action, 56 * R);
+  void* d_in = up(in, sizeof(FeCtlIn) * R);
+  void* d_tau = up(nullptr, 56 * R);
+  int rcode = bad ? fail(h, -2, "fe_ctl_eval: device allocation / upload failed") : 0;
+  if (!rcode) {
+    void* a[] = {&d_c, &n_episodes, &d_first, &d_count, &d_reset, &d_pol, &d_act, &d_in, &d_tau};
+    rcode = launch(h, p->km->f_ctl_eval, (n_episodes + 31) / 32, 32, 0, nullptr, a);
+  }
+  if (!rcode && cudaMemcpy(torques, d_tau, 56 * R, cudaMemcpyDeviceToHost) != cudaSuccess) rcode = fail(h, -10, std::string("fe_ctl_eval: ") + cudaGetErrorString(cudaGetLastError()));
   for (void* b : bufs) cudaFree(b);
   return rcode;
 }

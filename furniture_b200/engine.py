@@ -186,7 +186,7 @@ def build_scene(m: mjcf.Model, em: EngineModel, phase_ob: bool = False) -> FeSce
 
 class Engine:
     def __init__(self, model: mjcf.Model, n_envs: int, device: int = 0, config: FeConfig | None = None, lib_path: str | None = None,
-                 dense: FeDenseConfig | None = None, ik=None):
+                 dense: FeDenseConfig | None = None, ik=None, controller=None):
         path = lib_path or DEFAULT_LIB
         if not os.path.exists(path):
             raise RuntimeError(
@@ -224,6 +224,10 @@ class Engine:
         self.ik = ik
         if ik is not None:  # control_type="ik" (furniture_b200/ik.py: FeIkConfig): actions become (move 3, rotate 3, gripper, connect)
             self._chk(L.fe_enable_ik(self.h, C.byref(ik)))
+            self.act_dim = int(L.fe_action_dim(self.h))
+        self.controller = controller
+        if controller is not None:  # one of the NEW_CONTROLLERS (furniture_b200/controllers.py: FeCtlConfig) on the torque-actuated robot
+            self._chk(L.fe_enable_controller(self.h, C.byref(controller)))
             self.act_dim = int(L.fe_action_dim(self.h))
         self.dense = dense
         if dense is not None:  # FurnitureSawyerDenseRewardEnv: the phase machine replaces the sparse reward inside fe_env_step
@@ -327,6 +331,17 @@ class Engine:
         self._chk(self.L.fe_dense_eval(self.h, C.byref(dc), C.byref(recipe), C.c_size_t(C.sizeof(recipe)), p(thr), int(n_goal), len(first), p(first), p(count), int(R),
                                        int(nsite), int(npart), int(act_dim), *[p(a) for a in arrs], p(rew), p(done), p(info)))
         return rew, done, info
+
+    def ctl_eval(self, cc, first, count, reset, policy_step, action, readings):
+        """test hook fe_ctl_eval: the device controller arithmetic on explicit simulator readings (R, 123), episodes [first[e], first[e] + count[e])"""
+        f = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        first, count, reset, policy_step = f(first, np.int32), f(count, np.int32), f(reset, np.uint8), f(policy_step, np.uint8)
+        action, readings = f(action, np.float64), f(readings, np.float64)
+        assert readings.shape[1] == 123 and action.shape[1] == 7
+        tau = np.zeros((len(readings), 7), np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._chk(self.L.fe_ctl_eval(self.h, C.byref(cc), len(first), p(first), p(count), len(readings), p(reset), p(policy_step), p(action), p(readings), p(tau)))
+        return tau
 
     def obs_dev_ptr(self):
         return self.L.fe_obs_dev(self.h)

@@ -1107,12 +1107,22 @@ def load_recipe(furniture, assets_root):
         return yaml.load(f, Loader=_Loader)
 
 
+def compose_agent(agent, furniture, assets_root, resize_factor=None):
+    """compose_scene with the agent names of the compiled tables: "SawyerTorque" is the Sawyer on torque (motor) actuators,
+    robots/sawyer/robot_torque.xml -- what the reference loads for control_type "torque" and the NEW_CONTROLLERS (furniture.py:1893-1899)"""
+    if agent == "SawyerTorque":
+        xml, meta = compose_scene("Sawyer", furniture, assets_root, resize_factor=resize_factor, use_torque=True)
+        meta["agent"] = "SawyerTorque"
+        return xml, meta
+    return compose_scene(agent, furniture, assets_root, resize_factor=resize_factor)
+
+
 def load_scene(agent="Sawyer", furniture="table_lack_0825", assets_root=None, resize_factor=None):
     """compose + compile if the asset tree is reachable, else the precompiled tables shipped in
     furniture_b200/compiled/ (made by tools/compile_models.py; unit size only)."""
     root = assets_root or default_assets_root()
     if root is not None:
-        xml, meta = compose_scene(agent, furniture, root, resize_factor=resize_factor)
+        xml, meta = compose_agent(agent, furniture, root, resize_factor=resize_factor)
         return compile_mjcf(xml, meta)
     if resize_factor:
         raise FileNotFoundError("a resized scene (furn_size_rand) is composed from the MJCF asset tree: set FURNITURE_ASSETS")

@@ -154,6 +154,27 @@ typedef struct fe_ik_config {
  * commanded joints (7), last low-level action (8) as float32, then the iteration count of the last solve (int32) and a pad. */
 int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc);
 
+/* ---- the torque controllers of controllers/arm_controller.py (NEW_CONTROLLERS): parameters of one controller (host: furniture_b200/
+ * controllers.py from controllers/controller_config.hjson).  mode: 0 joint_torque, 1 joint_velocity, 2 joint_impedance, 3 position_orientation,
+ * 4 position.  ramp_steps = floor(0.2 * control_freq / model timestep) as the reference computes it (arm_controller.py:111). */
+typedef struct fe_ctl_config {
+  int32_t struct_bytes, mode, control_dim, pad_;
+  double move_speed;                              /* _do_controller_step scales and swaps action[:3] for every controller (furniture.py:3069-3071) */
+  double control_max[7], kp[7], damping[7], kv[7];
+  double ramp_steps;
+  float hand_pos[3], hand_quat[4];                /* right_hand in the frame of the link that carries it */
+} fe_ctl_config;
+/* Switch the handle (one-arm env on the torque-actuated robot, robots/sawyer/robot_torque.xml) to one of these controllers: fe_env_step then
+ * takes (n_envs, control_dim + 2) actions -- the controller's command, the gripper, connect -- and runs _do_controller_step
+ * (furniture.py:3065-3093): sim.forward(), then before every mj_step the controller turns the hand pose / velocity, the hand Jacobian and
+ * the arm block of the joint-space inertia of the last forward pass into joint torques, ctrl = qfrc_bias + torques (_pre_action :1706-1759). */
+int fe_enable_controller(fe_handle* h, const fe_ctl_config* cc);
+/* test hook: the device controller arithmetic on explicit simulator readings.  Records [first[e], first[e] + count[e]) form episode e; per
+ * record: reset / policy_step flags, action (7 doubles, the first control_dim used) and the readings as 123 doubles: pos 3, R 9 (row-major),
+ * velp 3, velr 3, q 7, qvel 7, Jx 21, Jr 21 (3 x 7 row-major), M 49.  Output: torques (7 doubles per record). */
+int fe_ctl_eval(fe_handle* h, const fe_ctl_config* cc, int n_episodes, const int32_t* first, const int32_t* count, int n_records, const uint8_t* reset,
+                const uint8_t* policy_step, const double* action, const double* readings, double* torques_host);
+
 #ifdef __cplusplus
 }
 #endif

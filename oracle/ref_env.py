@@ -524,3 +524,72 @@ class OracleDenseIKEnv(IKMixin, OracleDenseEnv):
         ob = OracleDenseEnv.reset(self)
         self._ik_sync()
         return ob
+
+
+class OracleControllerEnv(OracleFurnitureEnv):
+    """the one-arm env under one of the NEW_CONTROLLERS (FurnitureEnv._do_controller_step, furniture.py:3065-3093, with _pre_action
+    :1706-1759 before every mj_step) on the torque-actuated robot; the controller is oracle/controller_oracle.py"""
+
+    def __init__(self, model, name, cfg=None, move_speed=0.1):
+        from .controller_oracle import ArmController
+
+        super().__init__(model, cfg)
+        self.ctl = ArmController(name, timestep=float(model.opt_timestep))
+        self.move_speed = move_speed
+        self.hand = model.names["body"].index("right_hand")
+        self.arm_jnt = [model.names["jnt"].index(n) for n in model.meta["robot_joints"]]
+        self.dof = self.ctl.control_dim + 2
+
+    def reset(self):
+        ob = super().reset()
+        self.ctl.reset()  # furniture.py:1885-1887
+        return ob
+
+    def readings(self):
+        sim, b = self.sim, self.hand
+        pos = np.array(sim.xpos[3 * b : 3 * b + 3])
+        R = np.array(sim.xmat[9 * b : 9 * b + 9]).reshape(3, 3)
+        Jx, Jr = np.zeros((3, 7)), np.zeros((3, 7))
+        for k, j in enumerate(self.arm_jnt):
+            axis, anchor = np.array(sim.xaxis[3 * j : 3 * j + 3]), np.array(sim.xanchor[3 * j : 3 * j + 3])
+            Jx[:, k], Jr[:, k] = np.cross(axis, pos - anchor), axis
+        q, qv = np.array(sim.qpos[self.arm_idx]), np.array(sim.qvel[self.arm_idx])
+        M = np.array(sim.qM).reshape(self.m.nv, self.m.nv)[np.ix_(self.arm_idx, self.arm_idx)]
+        # body_xvelp / body_xvelr come from the velocities of the last forward pass (cvel), i.e. from the joint velocities before the
+        # last integration, like the Jacobian; qpos / qvel themselves are the integrated ones
+        return pos, R, Jx @ self._qvel_fwd, Jr @ self._qvel_fwd, q, qv, Jx, Jr, M
+
+    def _simulate(self, raw):
+        a = raw.copy()
+        if self.cfg.discrete_grip:
+            a[-2] = -1 if a[-2] < 0 else 1
+        n = self.ctl.control_dim
+        arm = np.zeros(7)
+        arm[:n] = a[:n]
+        arm[:3] = arm[:3] * self.move_speed
+        arm[:3] = [-arm[1], arm[0], arm[2]]
+        m, sim = self.m, self.sim
+        cr = m.actuator_ctrlrange
+        sim.forward()
+        self.torques = []
+        for i in range(self.nsub):
+            if i == 0:
+                self._qvel_fwd = np.array(sim.qvel[self.arm_idx])
+            tau = self.ctl.torques(arm, i == 0, *self.readings())
+            self.torques.append(tau)
+            seen = 0
+            for u in range(m.nu):
+                jn = m.names["jnt"][int(m.actuator_jntid[u])]
+                if jn in m.meta["robot_joints"]:
+                    k = m.meta["robot_joints"].index(jn)
+                    sim.ctrl[u] = sim.qfrc_bias[self.arm_idx[k]] + tau[k]
+                else:
+                    g = a[-2] * (1 if seen == 0 else -1)
+                    seen += 1
+                    sim.ctrl[u] = 0.5 * (cr[u, 1] + cr[u, 0]) + 0.5 * (cr[u, 1] - cr[u, 0]) * g
+            self._qvel_fwd = np.array(sim.qvel[self.arm_idx])
+            sim.step(1)
+        fail = bool(sim.scalar("warning") & 2)
+        if fail:
+            sim.L.om_clear_warning(sim.d)
+        return fail, fail

@@ -32,6 +32,8 @@ static int plat_dense_eval(fe_handle* h, const struct fe_dense_config* dc, const
                            const int32_t* first, const int32_t* count, int n_records, int nsite, int npart, int act_dim, const double* spos, const double* smat,
                            const double* ppos, const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward,
                            uint8_t* done, double* info);
+static int plat_ctl_eval(fe_handle* h, const struct fe_ctl_config* cc, int n_episodes, const int32_t* first, const int32_t* count, int n_records, const uint8_t* reset,
+                         const uint8_t* policy_step, const double* action, const struct FeCtlIn* in, double* torques);
 
 #include "../../furniture_b200/csrc/fe_api.inl"
 
@@ -64,7 +66,8 @@ static int plat_run_step(fe_handle* h, const float* actions, float* reward, uint
     fe_env_bind(&e, (float*)slice.data(), h->dm, h->ds, &h->cfg, h->opt, h->st, h->es, env, h->slice_words);
     fe_load(e.w, h->st, env);
     fe_env_load_groups(&e);
-    if (h->ik.c) fe_env_ik_step_one(&e, h->ik, actions, reward, done, info);
+    if (h->ctl.c) fe_env_ctl_step_one(&e, h->ctl, actions, reward, done, info);
+    else if (h->ik.c) fe_env_ik_step_one(&e, h->ik, actions, reward, done, info);
     else fe_env_step_one(&e, actions, reward, done, info);
     fe_env_store_groups(&e);
     fe_store(e.w, h->st, env);
@@ -92,5 +95,10 @@ static int plat_dense_eval(fe_handle*, const fe_dense_config* dc, const fe_dense
                            const uint8_t* touch, const uint8_t* reset, const uint8_t* connected, const double* ac, double* reward, uint8_t* done, double* info) {
   for (int e = 0; e < n_episodes; ++e)
     fe_dense_eval_episode(dc, rc, thr, n_goal, first[e], count[e], nsite, npart, act_dim, spos, smat, ppos, touch, reset, connected, ac, reward, done, info);
+  return 0;
+}
+static int plat_ctl_eval(fe_handle*, const fe_ctl_config* cc, int n_episodes, const int32_t* first, const int32_t* count, int, const uint8_t* reset,
+                         const uint8_t* policy_step, const double* action, const FeCtlIn* in, double* torques) {
+  for (int e = 0; e < n_episodes; ++e) fe_ctl_eval_episode(cc, first[e], count[e], reset, policy_step, action, in, torques);
   return 0;
 }

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from furniture_b200 import mjcf  # noqa: E402
 
-SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer", "swivel_chair_0700"), ("Baxter", "chair_ingolf_0650"), ("Baxter", "table_lack_0825"), ("Cursor", "toy_table"), ("Cursor", "table_lack_0825")]
+SCENES = [("Sawyer", "table_lack_0825"), ("None", "table_lack_0825"), ("Sawyer", "swivel_chair_0700"), ("Baxter", "chair_ingolf_0650"), ("Baxter", "table_lack_0825"), ("Cursor", "toy_table"), ("Cursor", "table_lack_0825"), ("SawyerTorque", "table_lack_0825")]
 MIXED = True  # plus Sawyer + every furniture XML whose colliders the engine supports (BASELINE.json config 5, the mixed batch)
 
 
@@ -41,7 +41,7 @@ def main():
         scenes += [("Sawyer", n) for n in mjcf.furniture_names(root) if ("Sawyer", n) not in scenes]
     skipped = []
     for agent, furn in scenes:
-        xml, meta = mjcf.compose_scene(agent, furn, root)
+        xml, meta = mjcf.compose_agent(agent, furn, root)
         try:
             m = mjcf.compile_mjcf(xml, meta)
         except NotImplementedError as e:  # mesh colliders (7 of the 64 furniture models)
