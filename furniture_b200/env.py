@@ -22,6 +22,7 @@ from .engine import INFO_DIM, Engine, default_config
 INFO_KEYS = ("num_connected", "episode_success", "episode_unstable", "episode_length", "ncon", "solver_iters")
 ENV_IDS = {"IKEASawyer-v0": "Sawyer", "FurnitureSawyerEnv": "Sawyer", "IKEABaxter-v0": "Baxter", "FurnitureBaxterEnv": "Baxter",
            "IKEASawyerDense-v0": "Sawyer", "furniture-sawyer-densereward-v0": "Sawyer", "FurnitureSawyerDenseRewardEnv": "Sawyer"}
+NEW_CONTROLLERS = ("position", "position_orientation", "joint_impedance", "joint_torque", "joint_velocity")  # furniture.py:41-47
 DENSE_IDS = {"IKEASawyerDense-v0", "furniture-sawyer-densereward-v0", "FurnitureSawyerDenseRewardEnv"}  # env/__init__.py:103-114
 # furniture_id -> name: the reference numbers the sorted objects/*.xml (furniture/env/models/__init__.py:11-19)
 FURNITURE_NAMES = (
@@ -42,8 +43,8 @@ def split_config(config):
     from .engine import FeConfig
 
     cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
-    if cfg.get("control_type", "impedance") not in ("impedance", "ik", "ik_quaternion"):
-        raise NotImplementedError("control_type 'impedance', 'ik' and 'ik_quaternion' are accelerated (got %r)" % cfg["control_type"])
+    if cfg.get("control_type", "impedance") not in ("impedance", "ik", "ik_quaternion") + NEW_CONTROLLERS:
+        raise NotImplementedError("control_type %r is not built ('torque' drives nine actuators with eight numbers in the reference)" % cfg["control_type"])
     for k in ("unity", "visual_ob", "depth_ob", "segmentation_ob", "record_demo", "record_vid"):
         if cfg.get(k):
             raise NotImplementedError("%s=True needs the renderer, which is outside the accelerated path" % k)
@@ -64,6 +65,8 @@ def control_options(config):
     out = dict(control_type=ct)
     if ct in ("ik", "ik_quaternion"):
         out["ik"] = {k: cfg[k] for k in ("move_speed", "rotate_speed") if cfg.get(k) is not None}
+    elif ct in NEW_CONTROLLERS and cfg.get("move_speed") is not None:
+        out["ik"] = {"move_speed": cfg["move_speed"]}  # _do_controller_step scales action[:3] with it as well (furniture.py:3069-3071)
     return out
 
 
@@ -88,7 +91,9 @@ class BatchedFurnitureEnv:
         reward of FurnitureSawyerDenseRewardEnv, computed inside the step kernel (furniture_b200/dense.py).
         `control_type`: "impedance" (joint velocities, dof 9), "ik" (move 3, rotate 3, gripper, connect: dof 8) or "ik_quaternion" (the
         rotation as a quaternion relative to the hand: dof 9); the inverse kinematics and its three closed-loop repeats run inside the
-        step kernel (furniture_b200/ik.py); `ik`: overrides of ik.IK_DEFAULTS
+        step kernel (furniture_b200/ik.py); or one of the NEW_CONTROLLERS ("position", "position_orientation", "joint_impedance",
+        "joint_torque", "joint_velocity": the command of the controller, gripper, connect), which switch the scene to the torque-actuated
+        robot and evaluate the controller before every mj_step inside the step kernel (furniture_b200/controllers.py); `ik`: overrides of ik.IK_DEFAULTS
         (move_speed, rotate_speed, action_repeat ...)."""
         import torch
 
@@ -106,6 +111,10 @@ class BatchedFurnitureEnv:
         if self.cfg.furn_size_rand != 0:
             r = float(self.cfg.furn_size_rand)
             self.resize_factor = 1 + float(np.random.RandomState(int(self.cfg.seed)).uniform(-r, r, 1)[0])
+        if control_type in NEW_CONTROLLERS:
+            if agent != "Sawyer":
+                raise NotImplementedError("the torque controllers are built for the Sawyer env")
+            agent = "SawyerTorque"  # robots/sawyer/robot_torque.xml (furniture.py:1893-1899)
         self.model = mjcf.load_scene(agent, furniture_name, resize_factor=self.resize_factor)
         self.dense_cfg = dense_config(**dense) if dense is not None else None
         self.control_type = control_type
@@ -116,9 +125,14 @@ class BatchedFurnitureEnv:
             from .ik import ik_config
 
             self.ik_cfg = ik_config(self.model, **dict(ik or {}, quaternion_mode=int(control_type == "ik_quaternion")))
-        elif control_type != "impedance":
-            raise NotImplementedError("control_type 'impedance', 'ik' and 'ik_quaternion' are accelerated (got %r)" % control_type)
-        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg, dense=self.dense_cfg, ik=self.ik_cfg)
+        self.ctl_cfg = None
+        if control_type in NEW_CONTROLLERS:
+            from .controllers import ctl_config
+
+            self.ctl_cfg = ctl_config(control_type, model=self.model, move_speed=(ik or {}).get("move_speed", 0.1))
+        elif control_type not in ("impedance", "ik", "ik_quaternion"):
+            raise NotImplementedError("control_type %r is not built" % control_type)
+        self.engine = Engine(self.model, num_envs, device=device, config=self.cfg, dense=self.dense_cfg, ik=self.ik_cfg, controller=self.ctl_cfg)
         self.num_envs = num_envs
         self.obs_dim, self.act_dim = self.engine.obs_dim, self.engine.act_dim
         self.n_objects = self.engine.scene.npart
@@ -126,7 +140,7 @@ class BatchedFurnitureEnv:
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
         # control_type="ik": robot_ob is gripper_qpos, eef_pos, eef_quat, eef_velp, eef_velr only -- no joint positions / velocities
         # (furniture_sawyer.py:110-125); the device row always holds all of it, the 15 numbers are its tail
-        self._robot_skip = 14 if control_type in ("ik", "ik_quaternion") else 0
+        self._robot_skip = 0 if control_type == "impedance" else 14
         self.robot_ob_dim -= self._robot_skip
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self.dof = self.act_dim

@@ -33,7 +33,7 @@ class FurnitureGymB200:
         """`id`, `name` and the remaining keywords are what gym passes from the registration (env/__init__.py:19-114: id, name,
         furniture_name / furniture_id, background, port ...); options of the renderer are ignored, see env.split_config"""
         from .dense import dense_config
-        from .env import DENSE_IDS, control_options, split_config, split_dense_config
+        from .env import DENSE_IDS, NEW_CONTROLLERS, control_options, split_config, split_dense_config
 
         if name not in AGENTS:
             raise ValueError("unknown env %s (this build accelerates %s)" % (name, sorted(AGENTS)))
@@ -45,22 +45,31 @@ class FurnitureGymB200:
             self.dense_cfg = dense_config(**dense)
         else:
             furniture_name, over, self.ignored_config = split_config(config)
-        self.model = mjcf.load_scene(AGENTS[name], furniture_name)
-        self.cfg = default_config(**over)
         ctl = control_options(config)
-        self.control_type, self.ik_cfg = ctl["control_type"], None
+        self.control_type, self.ik_cfg, self.ctl_cfg = ctl["control_type"], None, None
+        agent = AGENTS[name]
+        if self.control_type in NEW_CONTROLLERS:  # the torque controllers run on the torque-actuated robot (furniture.py:1893-1899)
+            if agent != "Sawyer":
+                raise NotImplementedError("the torque controllers are built for the Sawyer env")
+            agent = "SawyerTorque"
+        self.model = mjcf.load_scene(agent, furniture_name)
+        self.cfg = default_config(**over)
+        if self.control_type in NEW_CONTROLLERS:
+            from .controllers import ctl_config
+
+            self.ctl_cfg = ctl_config(self.control_type, model=self.model, move_speed=ctl.get("ik", {}).get("move_speed", 0.1))
         if self.control_type in ("ik", "ik_quaternion"):  # "ik" is the reference's default control type (config/furniture.py:57)
             if AGENTS[name] != "Sawyer":
                 raise NotImplementedError("control_type='%s' is built for the Sawyer env" % self.control_type)
             from .ik import ik_config
 
             self.ik_cfg = ik_config(self.model, **dict(ctl["ik"], quaternion_mode=int(self.control_type == "ik_quaternion")))
-        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path, dense=self.dense_cfg, ik=self.ik_cfg)
+        self.engine = Engine(self.model, 1, device=device, config=self.cfg, lib_path=lib_path, dense=self.dense_cfg, ik=self.ik_cfg, controller=self.ctl_cfg)
         self.n_objects = self.engine.scene.npart
         self.object_ob_dim = 7 * self.n_objects
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
-        self._robot_skip = 14 if self.control_type in ("ik", "ik_quaternion") else 0  # ik: robot_ob has no joint positions / velocities (furniture_sawyer.py:110-125)
+        self._robot_skip = 0 if self.control_type == "impedance" else 14  # ik: robot_ob has no joint positions / velocities (furniture_sawyer.py:110-125)
         self.robot_ob_dim -= self._robot_skip
         self.dof = self.engine.act_dim
         self._max_episode_steps = self.cfg.max_episode_steps

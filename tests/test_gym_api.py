@@ -70,7 +70,7 @@ def test_reference_style_config_and_episode_length_passthrough():
     import pytest
 
     with pytest.raises(NotImplementedError):
-        split_config({"control_type": "joint_torque"})  # the five NEW_CONTROLLERS are not built ("impedance" and "ik" are)
+        split_config({"control_type": "torque"})  # eight numbers for nine actuators in the reference; not built
 
 
 def test_demo_files_have_the_reference_recorder_format(tmp_path):
@@ -153,8 +153,7 @@ def test_ik_control_type_through_the_gym_surface():
     split_config(dict(control_type="ik"))  # accepted
     import pytest
 
-    with pytest.raises(NotImplementedError):
-        split_config(dict(control_type="position_orientation"))
+    split_config(dict(control_type="position_orientation"))  # the five NEW_CONTROLLERS are accepted as well
     env = FurnitureGymB200(name="FurnitureSawyerEnv", lib_path=build_emu(), control_type="ik", move_speed=0.05, nsub=5, max_episode_steps=2)
     assert env.dof == 8 and abs(env.ik_cfg.move_speed - 0.05) < 1e-9 and env.ik_cfg.action_repeat == 3
     ob = env.reset()
@@ -168,3 +167,20 @@ def test_ik_control_type_through_the_gym_surface():
     assert done and info["episode_length"] == 2
     with pytest.raises(NotImplementedError):
         FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik")
+
+
+def test_torque_controllers_through_the_gym_surface():
+    """control_type in NEW_CONTROLLERS (furniture.py:41-47): the scene switches to the torque-actuated Sawyer, the action is the controller's
+    command + gripper + connect, robot_ob the 15-number proprioception of every non-impedance control type (furniture_sawyer.py:110-155)"""
+    for ct, dof in (("position_orientation", 8), ("position", 5), ("joint_impedance", 9), ("joint_velocity", 9), ("joint_torque", 9)):
+        env = FurnitureGymB200(name="FurnitureSawyerEnv", lib_path=build_emu(), control_type=ct, nsub=3, max_episode_steps=2, move_speed=0.05)
+        assert env.dof == dof and env.model.meta["agent"] == "SawyerTorque" and abs(env.ctl_cfg.move_speed - 0.05) < 1e-12
+        ob = env.reset()
+        assert ob["robot_ob"].shape == (15,)
+        a = np.zeros(dof)
+        a[-1] = -1.0
+        ob, r, done, info = env.step(a)
+        assert np.isfinite(ob["robot_ob"]).all() and abs(r + 1e-3) < 1e-7 and not done
+        ob, r, done, info = env.step(a)
+        assert done and info["episode_length"] == 2
+        env.close()
