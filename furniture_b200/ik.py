@@ -6,7 +6,7 @@ rest poses, joint limits) -- a host round trip per env step and a dependency (py
 everything the reference does around that call (action scaling and axis swap, workspace clipping, the accumulated target orientation with
 its quaternion conventions, the 0.3 sensitivity, the P controller -5 * (q - q_cmd) clipped to [-1, 1], three closed-loop repeats of
 _do_simulation) and replaces the solver by a damped-least-squares IK on the arm's own kinematic chain, run by the warp that owns the env
-(csrc/fe_ik.h); `solve_ik` below is the same algorithm in numpy float64 (the oracle's copy, oracle/ik_oracle.py, calls it).  The joint
+(csrc/fe_ik.h); the same algorithm in numpy float64 is test infrastructure (oracle/ik_oracle.py: solve_ik).  The joint
 targets therefore differ from pybullet's within the arm's one-dimensional null space; the end-effector pose they reach is the same target.
 
 `quaternion_mode=1` is control_type="ik_quaternion" (furniture.py:2998-3058): move 3, a quaternion (w, x, y, z) relative to the hand's
@@ -107,62 +107,3 @@ def ik_config(m: mjcf.Model, **kw) -> FeIkConfig:
     c.hand_pos[:] = list(ch["hand_pos"]); c.hand_quat[:] = list(ch["hand_quat"])
     c.base_pos[:] = list(ch["base_pos"]); c.base_quat[:] = list(ch["base_quat"])
     return c
-
-
-# ------------------------------------------------------------------ the algorithm, numpy float64 (same steps as csrc/fe_ik.h)
-def chain_fk(ch, q):
-    """world pose of `right_hand` and the world anchors / axes of the 7 joints"""
-    p, quat = np.zeros(3), np.array([1.0, 0, 0, 0])
-    anchors, axes = [], []
-    for k in range(NJ):
-        R = mjcf.q_to_mat(quat)
-        p0 = p + R @ ch["link_pos"][k]
-        q0 = mjcf.q_mul(quat, ch["link_quat"][k])
-        R0 = mjcf.q_to_mat(q0)
-        anchors.append(p0 + R0 @ ch["jpos"][k])
-        axes.append(R0 @ ch["jaxis"][k])
-        quat = mjcf.q_norm(mjcf.q_mul(q0, mjcf.q_axis_angle(ch["jaxis"][k], q[k])))
-        p = anchors[-1] - mjcf.q_to_mat(quat) @ ch["jpos"][k]
-    R = mjcf.q_to_mat(quat)
-    return p + R @ ch["hand_pos"], mjcf.q_norm(mjcf.q_mul(quat, ch["hand_quat"])), np.array(anchors), np.array(axes)
-
-
-def rot_error(q_target, q_cur):
-    """rotation vector of q_target * conj(q_cur) (world frame)"""
-    e = mjcf.q_mul(q_target, mjcf.q_conj(q_cur))
-    if e[0] < 0:
-        e = -e
-    n = np.linalg.norm(e[1:])
-    if n < 1e-9:
-        return 2.0 * e[1:]
-    return 2.0 * np.arctan2(n, e[0]) * e[1:] / n
-
-
-def solve_ik(p, q_start, target_pos_world, target_quat_world):
-    """damped least squares with a null-space pull to the rest pose and joint limits; returns (q, iterations)"""
-    ch = p["chain"]
-    q = np.array(q_start, dtype=np.float64)
-    lam2 = p["damping"] ** 2
-    rest, lo, hi = np.array(p["rest_pose"]), np.array(p["lower"]), np.array(p["upper"])
-    it = 0
-    for it in range(p["max_iters"]):
-        hp, hq, anchors, axes = chain_fk(ch, q)
-        ep = target_pos_world - hp
-        er = rot_error(target_quat_world, hq)
-        np_, nr = np.linalg.norm(ep), np.linalg.norm(er)
-        if np_ < p["tol_pos"] and nr < p["tol_rot"]:
-            break
-        if np_ > p["max_step_pos"]:
-            ep = ep * (p["max_step_pos"] / np_)
-        if nr > p["max_step_rot"]:
-            er = er * (p["max_step_rot"] / nr)
-        J = np.zeros((6, NJ))
-        for k in range(NJ):
-            J[:3, k] = np.cross(axes[k], hp - anchors[k])
-            J[3:, k] = axes[k]
-        A = J @ J.T + lam2 * np.eye(6)
-        e = np.concatenate([ep, er])
-        z = p["null_gain"] * (rest - q)
-        dq = J.T @ np.linalg.solve(A, e - J @ z) + z
-        q = np.clip(q + dq, lo, hi)
-    return q, it

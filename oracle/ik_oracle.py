@@ -5,7 +5,7 @@
                    quat2mat :207-229 (float32 where the reference computes in float32)
   IKOracle      <- SawyerIKController.get_control / sync_state / joint_positions_for_eef_command
                    furniture/env/controllers/sawyer_ik_controller.py:46-118, :248-281 -- with the pybullet solve replaced by
-                   furniture_b200.ik.solve_ik (damped least squares on the arm's own chain, float64), which is the algorithm the device
+                   solve_ik below (damped least squares on the arm's own chain, float64), which is the algorithm the device
                    runs in float32 (csrc/fe_ik.h)
 
 ik_pre is pinned against tests/golden/ik_pre.npz (the reference's own _do_ik_step run around stand-ins, tools/make_golden_ik.py).
@@ -18,6 +18,65 @@ import numpy as np
 
 from furniture_b200 import ik as IK
 from furniture_b200 import mjcf
+
+
+# ------------------------------------------------------------------ the solver, numpy float64 (same steps as csrc/fe_ik.h: fe_ik_fk, fe_ik_solve)
+def chain_fk(ch, q):
+    """world pose of `right_hand` and the world anchors / axes of the 7 joints"""
+    p, quat = np.zeros(3), np.array([1.0, 0, 0, 0])
+    anchors, axes = [], []
+    for k in range(IK.NJ):
+        R = mjcf.q_to_mat(quat)
+        p0 = p + R @ ch["link_pos"][k]
+        q0 = mjcf.q_mul(quat, ch["link_quat"][k])
+        R0 = mjcf.q_to_mat(q0)
+        anchors.append(p0 + R0 @ ch["jpos"][k])
+        axes.append(R0 @ ch["jaxis"][k])
+        quat = mjcf.q_norm(mjcf.q_mul(q0, mjcf.q_axis_angle(ch["jaxis"][k], q[k])))
+        p = anchors[-1] - mjcf.q_to_mat(quat) @ ch["jpos"][k]
+    R = mjcf.q_to_mat(quat)
+    return p + R @ ch["hand_pos"], mjcf.q_norm(mjcf.q_mul(quat, ch["hand_quat"])), np.array(anchors), np.array(axes)
+
+
+def rot_error(q_target, q_cur):
+    """rotation vector of q_target * conj(q_cur) (world frame)"""
+    e = mjcf.q_mul(q_target, mjcf.q_conj(q_cur))
+    if e[0] < 0:
+        e = -e
+    n = np.linalg.norm(e[1:])
+    if n < 1e-9:
+        return 2.0 * e[1:]
+    return 2.0 * np.arctan2(n, e[0]) * e[1:] / n
+
+
+def solve_ik(p, q_start, target_pos_world, target_quat_world):
+    """damped least squares with a null-space pull to the rest pose and joint limits; returns (q, iterations)"""
+    ch = p["chain"]
+    q = np.array(q_start, dtype=np.float64)
+    lam2 = p["damping"] ** 2
+    rest, lo, hi = np.array(p["rest_pose"]), np.array(p["lower"]), np.array(p["upper"])
+    it = 0
+    for it in range(p["max_iters"]):
+        hp, hq, anchors, axes = chain_fk(ch, q)
+        ep = target_pos_world - hp
+        er = rot_error(target_quat_world, hq)
+        np_, nr = np.linalg.norm(ep), np.linalg.norm(er)
+        if np_ < p["tol_pos"] and nr < p["tol_rot"]:
+            break
+        if np_ > p["max_step_pos"]:
+            ep = ep * (p["max_step_pos"] / np_)
+        if nr > p["max_step_rot"]:
+            er = er * (p["max_step_rot"] / nr)
+        J = np.zeros((6, IK.NJ))
+        for k in range(IK.NJ):
+            J[:3, k] = np.cross(axes[k], hp - anchors[k])
+            J[3:, k] = axes[k]
+        A = J @ J.T + lam2 * np.eye(6)
+        e = np.concatenate([ep, er])
+        z = p["null_gain"] * (rest - q)
+        dq = J.T @ np.linalg.solve(A, e - J @ z) + z
+        q = np.clip(q + dq, lo, hi)
+    return q, it
 
 
 def _hamilton(a, b):  # (w, x, y, z)
@@ -118,7 +177,7 @@ class IKOracle:
         self.target_pos = self.target_pos + d_pos * self.p["user_sensitivity"]
         tp = self.base_p + self.base_R @ self.target_pos
         tq = mjcf.mat_to_q(self.base_R @ rotation)
-        self.q_cmd, self.iters = IK.solve_ik(self.p, jpos, tp, tq)
+        self.q_cmd, self.iters = solve_ik(self.p, jpos, tp, tq)
         return self.velocities(jpos), grip
 
     def velocities(self, jpos):

@@ -51,15 +51,15 @@ def test_chain_and_solver_reach_the_commanded_hand_pose(sawyer):
     full[p["chain"]["qadr"]] = q
     kin = mjcf.kinematics_np(m, full)
     hb = m.names["body"].index("right_hand")
-    hp, hq, _, _ = IK.chain_fk(p["chain"], q)
+    hp, hq, _, _ = O.chain_fk(p["chain"], q)
     assert np.abs(hp - kin["xpos"][hb]).max() < 1e-12 and np.abs(hq - kin["xquat"][hb]).max() < 1e-12  # the chain is the model's arm
     rng = np.random.RandomState(0)
     for _ in range(20):
         tp = hp + rng.uniform(-0.06, 0.06, 3)
         tq = mjcf.q_norm(mjcf.q_mul(mjcf.q_axis_angle(rng.normal(size=3), rng.uniform(0, 0.3)), hq))
-        qs, it = IK.solve_ik(p, q, tp, tq)
-        a, b, _, _ = IK.chain_fk(p["chain"], qs)
-        assert it < p["max_iters"] - 1 and np.linalg.norm(a - tp) < p["tol_pos"] and np.linalg.norm(IK.rot_error(tq, b)) < p["tol_rot"]
+        qs, it = O.solve_ik(p, q, tp, tq)
+        a, b, _, _ = O.chain_fk(p["chain"], qs)
+        assert it < p["max_iters"] - 1 and np.linalg.norm(a - tp) < p["tol_pos"] and np.linalg.norm(O.rot_error(tq, b)) < p["tol_rot"]
         assert (qs >= np.array(p["lower"]) - 1e-12).all() and (qs <= np.array(p["upper"]) + 1e-12).all()
 
 
