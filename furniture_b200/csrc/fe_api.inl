@@ -305,10 +305,12 @@ int fe_set_max_episode_steps(fe_handle* h, int max_episode_steps) {
 int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc) {
   if (!ikc || ikc->struct_bytes != (int32_t)sizeof(fe_ik_config)) return fail(h, -1, "fe_enable_ik: fe_ik_config size mismatch");
   if (h->hs.magic != FE_SCENE_MAGIC) return fail(h, -6, "fe_enable_ik: handle was created without a scene blob");
-  if (h->hs.narms != 1 || h->hs.narm != 7 || h->hs.hand_link[0] < 0 || h->hs.act_dim != 9) return fail(h, -1, "fe_enable_ik: the IK control type is built for the one-arm 7-joint (Sawyer) env");
+  if (ikc->narms != h->hs.narms || ikc->narms < 1 || ikc->narms > 2 || h->hs.narm != 7 * ikc->narms || h->hs.hand_link[0] < 0 || (ikc->narms == 2 && h->hs.hand_link[1] < 0))
+    return fail(h, -1, "fe_enable_ik: the IK control type is built for arms of 7 joints (one arm: Sawyer, two: Baxter) and the config must name as many arms as the scene has");
   if (h->ctl.c) return fail(h, -1, "fe_enable_ik: the handle already runs a torque controller");
   if (ikc->action_repeat < 1 || ikc->action_repeat > 16 || ikc->max_iters < 1 || ikc->max_iters > 1000) return fail(h, -1, "fe_enable_ik: action_repeat / max_iters out of range");
-  for (int k = 0; k < 7; ++k) if (ikc->arm_qadr[k] < 0 || ikc->arm_qadr[k] >= h->hm.nq) return fail(h, -1, "fe_enable_ik: arm_qadr outside qpos");
+  for (int a = 0; a < ikc->narms; ++a)
+    for (int k = 0; k < 7; ++k) if (ikc->arm[a].arm_qadr[k] < 0 || ikc->arm[a].arm_qadr[k] >= h->hm.nq) return fail(h, -1, "fe_enable_ik: arm_qadr outside qpos");
   FeDevScope dev_scope(h);
   if (!h->ik.c) {
     fe_ik_config* d = (fe_ik_config*)plat_alloc(sizeof(fe_ik_config));
@@ -319,7 +321,7 @@ int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc) {
     add_field(h, "ik_state", st, (int)sizeof(FeIkState), 1, true);
   }
   plat_upload((void*)h->ik.c, ikc, sizeof(fe_ik_config));
-  h->ik_act_dim = ikc->quaternion_mode ? 9 : 8;
+  h->ik_act_dim = ikc->narms * (ikc->quaternion_mode ? 7 : 6) + ikc->narms + 1;
   return 0;
 }
 int fe_enable_controller(fe_handle* h, const fe_ctl_config* cc) {

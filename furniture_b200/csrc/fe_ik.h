@@ -15,12 +15,12 @@
 #pragma once
 #include "fe_env.h"
 
-struct FeIkState { // per env, in HBM
-  float s[4];          // _initial_right_hand_quat: the accumulated orientation target, components as the reference stores them
-  float target_pos[3]; // ik_robot_target_pos, base frame
-  float q_cmd[7];      // commanded_joint_positions
-  float low[8];        // low-level action of the current repeat: 7 joint velocities + gripper
-  int32_t iters, pad_;
+struct FeIkState { // per env, in HBM; [arm]: right, left
+  float s[2][4];          // _initial_<arm>_hand_quat: the accumulated orientation target, components as the reference stores them
+  float target_pos[2][3]; // ik_robot_target_pos_<arm>, base frame
+  float q_cmd[14];        // commanded_joint_positions (right arm, then left)
+  float low[16];          // low-level action of the current repeat: the joint velocities of every arm, then one gripper action per arm
+  int32_t iters[2];
 };
 struct FeIkArgs {
   const fe_ik_config* c;
@@ -56,7 +56,7 @@ FE_HD void ik_mat_to_wxyz(float* q, const float* R) { // rotation matrix -> unit
 }
 
 // ---- the arm: joint k's body frame in the frame of joint k-1's body at zero angle (fe_ik_config), hinge about (jpos, jaxis)
-FE_HD void fe_ik_fk(const fe_ik_config* c, const float* q, float* hp, float* hq, float* anchors, float* axes) {
+FE_HD void fe_ik_fk(const fe_ik_arm* c, const float* q, float* hp, float* hq, float* anchors, float* axes) {
   float p[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
   for (int k = 0; k < 7; ++k) {
     float R[9], t[3], p0[3], q0[4], R0[9], ql[4], R1[9];
@@ -85,12 +85,12 @@ FE_HD void fe_ik_fk(const fe_ik_config* c, const float* q, float* hp, float* hq,
 }
 
 // damped least squares from q (in / out) to the world target (tp, tq wxyz); returns the number of iterations used
-FE_HDN int fe_ik_solve(const fe_ik_config* c, float* q, const float* tp, const float* tq) {
+FE_HDN int fe_ik_solve(const fe_ik_config* c, const fe_ik_arm* arm, float* q, const float* tp, const float* tq) {
   const float lam2 = c->damping * c->damping;
   int it = 0;
   for (; it < c->max_iters; ++it) {
     float hp[3], hq[4], an[21], ax[21], e[6], J[42];
-    fe_ik_fk(c, q, hp, hq, an, ax);
+    fe_ik_fk(arm, q, hp, hq, an, ax);
     v3sub(e, tp, hp);
     { // rotation vector of tq * conj(hq)
       const float cq[4] = {hq[0], -hq[1], -hq[2], -hq[3]};
@@ -118,14 +118,14 @@ FE_HDN int fe_ik_solve(const fe_ik_config* c, float* q, const float* tp, const f
         for (int k = 0; k < 7; ++k) s += J[7 * i + k] * J[7 * j + k];
         A[i * (i + 1) / 2 + j] = s;
       }
-    for (int k = 0; k < 7; ++k) z[k] = c->null_gain * (c->rest_pose[k] - q[k]);
+    for (int k = 0; k < 7; ++k) z[k] = c->null_gain * (arm->rest_pose[k] - q[k]);
     for (int i = 0; i < 6; ++i) { float s = e[i]; for (int k = 0; k < 7; ++k) s -= J[7 * i + k] * z[k]; rhs[i] = s; }
     fe_chol6(A);
     fe_chol6_solve(A, rhs);
     for (int k = 0; k < 7; ++k) {
       float dq = z[k];
       for (int i = 0; i < 6; ++i) dq += J[7 * i + k] * rhs[i];
-      q[k] = fminf(fmaxf(q[k] + dq, c->lower[k]), c->upper[k]);
+      q[k] = fminf(fmaxf(q[k] + dq, arm->lower[k]), arm->upper[k]);
     }
   }
   return it;
@@ -251,32 +251,36 @@ FE_HD void fe_ik_finish(FeEnv* e, const float* a, int act_dim, float connect, in
   if (e->ei[6]) fe_env_reset_one(e); else fe_write_obs(e);
 }
 
-// first get_control of the step (lane 0): hand pose of the last forward pass -> targets -> joint command -> first low-level action
-FE_HDN void fe_ik_command(FeEnv* e, const FeIkArgs& ik, const float* a, float grip) {
+// first get_control of the step (lane 0), one arm: hand pose of the last forward pass -> targets -> joint command -> first velocities.
+// `a` points at this arm's (move, rotate) numbers
+FE_HDN void fe_ik_command(FeEnv* e, const FeIkArgs& ik, int arm_i, const float* a) {
   FeWarp* w = e->w;
   const fe_model* m = w->m;
   const fe_ik_config* c = ik.c;
+  const fe_ik_arm* arm = &c->arm[arm_i];
   FeIkState* st = ik.st + e->env;
-  const int hl = e->sc->hand_link[0];
+  const int hl = e->sc->hand_link[arm_i];
   const float* lp = e->st.lpos + ((size_t)e->env * m->nlink + hl) * 3;  // sim.data.body_xpos / body_xmat: kinematics of the last forward pass
   const float* lq = e->st.lquat + ((size_t)e->env * m->nlink + hl) * 4;
   float Rl[9], t[3], hand_p[3], hand_q[4], Rh[9], Rb[9], hb[3], Rhb[9], cur[4], cw[4];
   const float lqv[4] = {lq[0], lq[1], lq[2], lq[3]};
   q2mat(Rl, lqv);
-  m3mulv(t, Rl, c->hand_pos);
+  m3mulv(t, Rl, arm->hand_pos);
   hand_p[0] = lp[0] + t[0]; hand_p[1] = lp[1] + t[1]; hand_p[2] = lp[2] + t[2];
-  qmul(hand_q, lqv, c->hand_quat);
+  qmul(hand_q, lqv, arm->hand_quat);
   qnormalize(hand_q);
   q2mat(Rh, hand_q);
   q2mat(Rb, c->base_quat);
   v3sub(t, hand_p, c->base_pos);
-  m3tmulv(hb, Rb, t);                                      // pose_in_base_from_name("right_hand"), furniture.py:3381-3398
+  m3tmulv(hb, Rb, t);                                      // pose_in_base_from_name("<arm>_hand"), furniture.py:3381-3398
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rhb[3 * i + j] = Rb[i] * Rh[j] + Rb[3 + i] * Rh[3 + j] + Rb[6 + i] * Rh[6 + j];
   ik_mat_to_wxyz(cw, Rhb);
-  cur[0] = cw[1]; cur[1] = cw[2]; cur[2] = cw[3]; cur[3] = cw[0]; // _right_hand_quat, (x, y, z, w)
-  if (e->es.episode_len[e->env] == 0) {                     // _reset's tail: _initial_right_hand_quat = _right_hand_quat; controller.sync_state()
-    for (int k = 0; k < 4; ++k) st->s[k] = cur[k];
-    v3cpy(st->target_pos, hb);
+  cur[0] = cw[1]; cur[1] = cw[2]; cur[2] = cw[3]; cur[3] = cw[0]; // _<arm>_hand_quat, (x, y, z, w)
+  float* s_acc = st->s[arm_i];
+  float* target = st->target_pos[arm_i];
+  if (e->es.episode_len[e->env] == 0) {                     // _reset's tail: _initial_<arm>_hand_quat = _<arm>_hand_quat; controller.sync_state()
+    for (int k = 0; k < 4; ++k) s_acc[k] = cur[k];
+    v3cpy(target, hb);
   }
   // action[:3] * move_speed, axes swapped, clipped to the workspace (world position of the hand)
   const float mv[3] = {-a[1] * c->move_speed, a[0] * c->move_speed, a[2] * c->move_speed};
@@ -296,8 +300,8 @@ FE_HDN void fe_ik_command(FeEnv* e, const FeIkArgs& ik, const float* a, float gr
       ik_hamilton(t4, q3, q2);
       ik_hamilton(qe, t4, q1);
     }
-    ik_hamilton(s_new, st->s, qe);
-    for (int k = 0; k < 4; ++k) st->s[k] = s_new[k];
+    ik_hamilton(s_new, s_acc, qe);
+    for (int k = 0; k < 4; ++k) s_acc[k] = s_new[k];
     // d_quat = quat_inverse(cur) * s; rotation = quat2mat(cur * d_quat)  (all (x, y, z, w))
     float inv[4], dq[4];
     { const float n = cur[0] * cur[0] + cur[1] * cur[1] + cur[2] * cur[2] + cur[3] * cur[3]; inv[0] = -cur[0] / n; inv[1] = -cur[1] / n; inv[2] = -cur[2] / n; inv[3] = cur[3] / n; }
@@ -305,36 +309,41 @@ FE_HDN void fe_ik_command(FeEnv* e, const FeIkArgs& ik, const float* a, float gr
     ik_xyzw_mul(rq, cur, dq);
   }
   ik_xyzw_to_mat(rot, rq);
-  for (int k = 0; k < 3; ++k) st->target_pos[k] += dpos[k] * c->user_sensitivity;
-  m3mulv(t, Rb, st->target_pos);
+  for (int k = 0; k < 3; ++k) target[k] += dpos[k] * c->user_sensitivity;
+  m3mulv(t, Rb, target);
   v3add(tp, c->base_pos, t);
   m3mul(Rw, Rb, rot);
   ik_mat_to_wxyz(tq, Rw);
   float q[7];
-  for (int k = 0; k < 7; ++k) q[k] = w->qpos()[c->arm_qadr[k]];
-  st->iters = fe_ik_solve(c, q, tp, tq);
-  for (int k = 0; k < 7; ++k) { st->q_cmd[k] = q[k]; st->low[k] = fminf(fmaxf(-c->kp * (w->qpos()[c->arm_qadr[k]] - q[k]), -1.f), 1.f); }
-  st->low[7] = grip;
+  for (int k = 0; k < 7; ++k) q[k] = w->qpos()[arm->arm_qadr[k]];
+  st->iters[arm_i] = fe_ik_solve(c, arm, q, tp, tq);
+  for (int k = 0; k < 7; ++k) { st->q_cmd[7 * arm_i + k] = q[k]; st->low[7 * arm_i + k] = fminf(fmaxf(-c->kp * (w->qpos()[arm->arm_qadr[k]] - q[k]), -1.f), 1.f); }
 }
 
-// FurnitureEnv.step with control_type="ik" for one env
+// FurnitureEnv.step with control_type="ik" / "ik_quaternion" for one env.  Actions: per arm (move 3, rotate 3 or a quaternion), then one
+// gripper action per arm, then connect (furniture_sawyer.py:60-63, furniture_baxter.py:52-62)
 FE_FN void fe_env_ik_step_one(FeEnv* e, FeIkArgs ik, const float* action, float* reward_out, uint8_t* done_out, int32_t* info_out) {
   FeWarp* w = e->w;
   const fe_ik_config* c = ik.c;
-  const int act_dim = c->quaternion_mode ? 9 : 8; // move 3, rotate 3 (or a quaternion), select (gripper), connect (furniture_sawyer.py:60-63)
+  const int na = c->narms, per = c->quaternion_mode ? 7 : 6, act_dim = na * per + na + 1;
   const float* a = action + (size_t)e->env * act_dim;
   float grip = a[act_dim - 2];
-  if (e->cfg->discrete_grip) grip = grip < 0.f ? -1.f : 1.f; // furniture_sawyer.py:73-74
+  if (e->cfg->discrete_grip) grip = grip < 0.f ? -1.f : 1.f; // FurnitureSawyerEnv._step only (furniture_sawyer.py:73-74); unused with two arms
   const float connect = a[act_dim - 1];
   FeIkState* st = ik.st + e->env;
   LANES_BEGIN
-    if (lane == 0) fe_ik_command(e, ik, a, grip);
+    if (lane == 0) {
+      for (int arm = 0; arm < na; ++arm) {
+        fe_ik_command(e, ik, arm, a + arm * per);
+        st->low[7 * na + arm] = na == 1 ? grip : a[na * per + arm];
+      }
+    }
   LANES_END
   int fail = 0, reset_now = 0;
   for (int r = 0; r < c->action_repeat; ++r) {
     if (r > 0) { // closed loop: get_control() without arguments, furniture.py:2988-2995
       LANES_BEGIN
-        if (lane < 7) st->low[lane] = fminf(fmaxf(-c->kp * (w->qpos()[c->arm_qadr[lane]] - st->q_cmd[lane]), -1.f), 1.f);
+        if (lane < 7 * na) st->low[lane] = fminf(fmaxf(-c->kp * (w->qpos()[c->arm[lane / 7].arm_qadr[lane % 7]] - st->q_cmd[lane]), -1.f), 1.f);
       LANES_END
     }
     fe_ik_controls(e, st->low, grip);

@@ -120,8 +120,8 @@ class BatchedFurnitureEnv:
         self.control_type = control_type
         self.ik_cfg = None
         if control_type in ("ik", "ik_quaternion"):
-            if agent != "Sawyer":
-                raise NotImplementedError("control_type='%s' is built for the Sawyer env" % control_type)
+            if agent not in ("Sawyer", "Baxter") or (agent == "Baxter" and control_type != "ik"):
+                raise NotImplementedError("control_type='%s' is built for the Sawyer env ('ik' for Baxter as well)" % control_type)
             from .ik import ik_config
 
             self.ik_cfg = ik_config(self.model, **dict(ik or {}, quaternion_mode=int(control_type == "ik_quaternion")))
@@ -141,7 +141,13 @@ class BatchedFurnitureEnv:
         # control_type="ik": robot_ob is gripper_qpos, eef_pos, eef_quat, eef_velp, eef_velr only -- no joint positions / velocities
         # (furniture_sawyer.py:110-125); the device row always holds all of it, the 15 numbers are its tail
         self._robot_skip = 0 if control_type == "impedance" else 14
-        self.robot_ob_dim -= self._robot_skip
+        self._narms = max(1, int(self.engine.scene.narms))
+        self.robot_ob_dim -= self._robot_skip * self._narms
+        self._robot_cols = None
+        if self._robot_skip and self._narms > 1:  # two arms: the 15-number tail of each arm's block (furniture_baxter.py:137-160)
+            per = self.engine.scene.robot_ob_dim // self._narms
+            cols = [self.object_ob_dim + a * per + k for a in range(self._narms) for k in range(self._robot_skip, per)]
+            self._robot_cols = torch.tensor(cols, dtype=torch.long, device=self.device)
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self.dof = self.act_dim
         self._obs = torch.empty((num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
@@ -163,8 +169,12 @@ class BatchedFurnitureEnv:
         return OrderedDict(default=(self.act_dim,))
 
     def _obs_dict(self, obs):
-        a, b = self.object_ob_dim, self.object_ob_dim + self._robot_skip + self.robot_ob_dim
-        d = OrderedDict(object_ob=obs[:, :a], robot_ob=obs[:, a + self._robot_skip : b])
+        a, b = self.object_ob_dim, self.object_ob_dim + self._robot_skip * self._narms + self.robot_ob_dim
+        if self._robot_cols is not None:
+            cols = self._robot_cols if hasattr(obs, "index_select") else self._robot_cols.cpu().numpy()
+            d = OrderedDict(object_ob=obs[:, :a], robot_ob=obs.index_select(1, cols) if hasattr(obs, "index_select") else obs[:, cols])
+        else:
+            d = OrderedDict(object_ob=obs[:, :a], robot_ob=obs[:, a + self._robot_skip : b])
         if self.phase_ob_dim:
             d["phase_ob"] = obs[:, b:]
         return d

@@ -59,8 +59,8 @@ class FurnitureGymB200:
 
             self.ctl_cfg = ctl_config(self.control_type, model=self.model, move_speed=ctl.get("ik", {}).get("move_speed", 0.1))
         if self.control_type in ("ik", "ik_quaternion"):  # "ik" is the reference's default control type (config/furniture.py:57)
-            if AGENTS[name] != "Sawyer":
-                raise NotImplementedError("control_type='%s' is built for the Sawyer env" % self.control_type)
+            if AGENTS[name] not in ("Sawyer", "Baxter") or (AGENTS[name] == "Baxter" and self.control_type != "ik"):
+                raise NotImplementedError("control_type='%s' is built for the Sawyer env ('ik' for Baxter as well)" % self.control_type)
             from .ik import ik_config
 
             self.ik_cfg = ik_config(self.model, **dict(ctl["ik"], quaternion_mode=int(self.control_type == "ik_quaternion")))
@@ -70,7 +70,10 @@ class FurnitureGymB200:
         self.robot_ob_dim = self.engine.scene.robot_ob_dim
         self.phase_ob_dim = 8 if self.engine.scene.phase_ob else 0
         self._robot_skip = 0 if self.control_type == "impedance" else 14  # ik: robot_ob has no joint positions / velocities (furniture_sawyer.py:110-125)
-        self.robot_ob_dim -= self._robot_skip
+        self._narms = max(1, int(self.engine.scene.narms))
+        per = self.robot_ob_dim // self._narms
+        self._robot_cols = np.array([self.object_ob_dim + a * per + k for a in range(self._narms) for k in range(self._robot_skip, per)])
+        self.robot_ob_dim -= self._robot_skip * self._narms
         self.dof = self.engine.act_dim
         self._max_episode_steps = self.cfg.max_episode_steps
         self._pending_ob = None  # observation of an episode the device has already started
@@ -100,8 +103,8 @@ class FurnitureGymB200:
             return OrderedDict(default=dict(shape=(self.dof,), low=-1.0, high=1.0))
 
     def _ob(self, obs_row):
-        a, b = self.object_ob_dim, self.object_ob_dim + self._robot_skip + self.robot_ob_dim
-        ob = OrderedDict(object_ob=obs_row[:a].astype(np.float64), robot_ob=obs_row[a + self._robot_skip : b].astype(np.float64))
+        a, b = self.object_ob_dim, self.object_ob_dim + self._robot_skip * self._narms + self.robot_ob_dim
+        ob = OrderedDict(object_ob=obs_row[:a].astype(np.float64), robot_ob=obs_row[self._robot_cols].astype(np.float64))
         if self.phase_ob_dim:
             ob["phase_ob"] = obs_row[b:].astype(np.float64)
         return ob

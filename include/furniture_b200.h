@@ -138,20 +138,28 @@ int fe_dense_eval(fe_handle* h, const fe_dense_config* dc, const void* recipe_bl
 /* ---- control_type="ik" for the one-arm env: FurnitureEnv._do_ik_step (furniture.py:2899-2996) + SawyerIKController
  * (controllers/sawyer_ik_controller.py) with the pybullet solve replaced by a damped-least-squares IK on the arm's own chain, run inside
  * the step kernel.  Speeds: config/furniture.py:84-89; workspace and the three repeats: furniture.py:166-172; sensitivity 0.3, gain 5,
- * joint damping 0.1, rest pose, limits: sawyer_ik_controller.py.  The chain (host: furniture_b200/ik.py: arm_chain) lists, per arm joint,
+ * joint damping 0.1, rest pose, limits: sawyer_ik_controller.py (Baxter: 1.0, 2, 0.7, baxter_ik_controller.py).  The chain (host: furniture_b200/ik.py: arm_chain) lists, per arm joint,
  * its body frame in the previous joint body's frame at zero angle and the hinge (anchor, axis) in its body frame. */
+typedef struct fe_ik_arm {
+  float rest_pose[7], lower[7], upper[7];
+  float link_pos[7][3], link_quat[7][4], jaxis[7][3], jpos[7][3];
+  float hand_pos[3], hand_quat[4]; /* "<arm>_hand" in the last joint body's frame */
+  int32_t arm_qadr[7];             /* qpos index of every joint of this arm */
+  int32_t pad_;
+} fe_ik_arm;
 typedef struct fe_ik_config {
   int32_t struct_bytes, action_repeat, max_iters;
   int32_t quaternion_mode; /* 1: control_type="ik_quaternion" (furniture.py:2998-3058): actions are move 3, quaternion (w,x,y,z) relative to the hand, gripper, connect */
   float move_speed, rotate_speed, user_sensitivity, kp, damping, null_gain, tol_pos, tol_rot, max_step_pos, max_step_rot;
-  float min_pos[3], max_pos[3], rest_pose[7], lower[7], upper[7];
-  float link_pos[7][3], link_quat[7][4], jaxis[7][3], jpos[7][3];
-  float hand_pos[3], hand_quat[4], base_pos[3], base_quat[4]; /* right_hand in the last joint body's frame; the robot base in the world */
-  int32_t arm_qadr[7];                                           /* qpos index of every arm joint */
+  float min_pos[3], max_pos[3];
+  float base_pos[3], base_quat[4]; /* the robot base in the world: targets are kept in its frame */
+  int32_t narms, pad_;             /* 1 (Sawyer) or 2 (Baxter: right, then left; actions (move, rotate) per arm, then the grippers, then connect) */
+  fe_ik_arm arm[2];
 } fe_ik_config;
 /* Switch the handle to control_type="ik": fe_env_step then takes (n_envs, 8) actions (move 3, rotate 3, gripper, connect) and
- * fe_action_dim() returns 8.  Field "ik_state" holds per env: accumulated target quaternion (4), target position in the base frame (3),
- * commanded joints (7), last low-level action (8) as float32, then the iteration count of the last solve (int32) and a pad. */
+ * fe_action_dim() returns 8.  Field "ik_state" holds per env, for two arms (the second unused with one): accumulated target quaternions
+ * (2 x 4), target positions in the base frame (2 x 3), commanded joints (14), last low-level action (16) as float32, then the iteration counts
+ * of the last solves (2 x int32). */
 int fe_enable_ik(fe_handle* h, const fe_ik_config* ikc);
 
 /* ---- the torque controllers of controllers/arm_controller.py (NEW_CONTROLLERS): parameters of one controller (host: furniture_b200/

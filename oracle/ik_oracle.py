@@ -49,12 +49,12 @@ def rot_error(q_target, q_cur):
     return 2.0 * np.arctan2(n, e[0]) * e[1:] / n
 
 
-def solve_ik(p, q_start, target_pos_world, target_quat_world):
-    """damped least squares with a null-space pull to the rest pose and joint limits; returns (q, iterations)"""
-    ch = p["chain"]
+def solve_ik(p, q_start, target_pos_world, target_quat_world, ch=None):
+    """damped least squares with a null-space pull to the rest pose and joint limits; returns (q, iterations); `ch`: the arm's chain"""
+    ch = ch or p["chain"]
     q = np.array(q_start, dtype=np.float64)
     lam2 = p["damping"] ** 2
-    rest, lo, hi = np.array(p["rest_pose"]), np.array(p["lower"]), np.array(p["upper"])
+    rest, lo, hi = np.array(ch.get("rest_pose", p["rest_pose"])), np.array(ch.get("lower", p["lower"])), np.array(ch.get("upper", p["upper"]))
     it = 0
     for it in range(p["max_iters"]):
         hp, hq, anchors, axes = chain_fk(ch, q)
@@ -151,9 +151,9 @@ def ik_pre_quaternion(action, hand_pos_world, hand_quat_base, p):
 class IKOracle:
     """one arm: the accumulated orientation target, the position target in the base frame, the commanded joints"""
 
-    def __init__(self, params):
+    def __init__(self, params, arm=0):
         self.p = params
-        ch = params["chain"]
+        ch = self.ch = params["chains"][arm] if "chains" in params else params["chain"]
         self.base_R = mjcf.q_to_mat(ch["base_quat"])
         self.base_p = np.asarray(ch["base_pos"], dtype=np.float64)
 
@@ -177,7 +177,7 @@ class IKOracle:
         self.target_pos = self.target_pos + d_pos * self.p["user_sensitivity"]
         tp = self.base_p + self.base_R @ self.target_pos
         tq = mjcf.mat_to_q(self.base_R @ rotation)
-        self.q_cmd, self.iters = solve_ik(self.p, jpos, tp, tq)
+        self.q_cmd, self.iters = solve_ik(self.p, jpos, tp, tq, self.ch)
         return self.velocities(jpos), grip
 
     def velocities(self, jpos):

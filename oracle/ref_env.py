@@ -385,37 +385,47 @@ class OracleFurnitureEnv:
 
 
 class IKMixin:
-    """control_type="ik" (FurnitureEnv._do_ik_step, furniture.py:2899-2996) over the oracle simulator; the solver is the
-    damped-least-squares IK of oracle/ik_oracle.py (pybullet's is not available)"""
+    """control_type="ik" / "ik_quaternion" (FurnitureEnv._do_ik_step, furniture.py:2899-3063) over the oracle simulator, one or two arms; the
+    solver is the damped-least-squares IK of oracle/ik_oracle.py (pybullet's is not available)"""
 
     def _ik_setup(self, **ik_kw):
         from furniture_b200 import ik as IK
         from .ik_oracle import IKOracle
 
         self.ikp = IK.ik_params(self.m, **ik_kw)
-        self.ik = IKOracle(self.ikp)
-        self.hand = self.m.names["body"].index("right_hand")
-        self.dof = 9 if self.ikp.get("quaternion_mode") else 8  # move 3, rotate 3 (or a quaternion), gripper, connect (furniture_sawyer.py:60-63)
+        na = self.ikp["narms"]
+        self.iks = [IKOracle(self.ikp, a) for a in range(na)]
+        self.ik = self.iks[0]
+        self.hands = [self.m.names["body"].index(n) for n in ("right_hand", "left_hand")[:na]]
+        self.per = 7 if self.ikp.get("quaternion_mode") else 6
+        self.dof = na * self.per + na + 1  # per arm: move 3, rotate 3 (or a quaternion); a gripper per arm; connect (furniture_sawyer.py:60-63, furniture_baxter.py:52-62)
 
-    def _hand(self):
-        b = self.hand
+    def _hand(self, arm=0):
+        b = self.hands[arm]
         return np.array(self.sim.xpos[3 * b : 3 * b + 3]), np.array(self.sim.xquat[4 * b : 4 * b + 4])
 
     def _ik_sync(self):  # _reset's tail, furniture.py:1643-1650
-        self.ik.sync(*self._hand())
+        for a, ik in enumerate(self.iks):
+            ik.sync(*self._hand(a))
 
     def _simulate(self, raw):
         a = raw.copy()
-        if self.cfg.discrete_grip:
+        na, per = len(self.iks), self.per
+        if self.cfg.discrete_grip and na == 1:
             a[-2] = -1 if a[-2] < 0 else 1
-        jpos = lambda: np.array(self.sim.qpos[self.arm_idx])
-        vel, grip = self.ik.command(a, *self._hand(), jpos())
+        jpos = lambda arm: np.array(self.sim.qpos[self.arm_idx[7 * arm : 7 * arm + 7]])
+        vel, grips = [], []
+        for arm, ik in enumerate(self.iks):
+            arm_action = np.concatenate([a[arm * per : (arm + 1) * per], [a[na * per + arm], a[-1]]])
+            v, g = ik.command(arm_action, *self._hand(arm), jpos(arm))
+            vel.append(v)
+            grips.append(g)
         fail = reset_now = False
         R = self.ikp["action_repeat"]
         for r in range(R):
             if r > 0:
-                vel = self.ik.velocities(jpos())
-            self.low_action = np.concatenate([vel, [grip]])
+                vel = [ik.velocities(jpos(arm)) for arm, ik in enumerate(self.iks)]
+            self.low_action = np.concatenate(vel + [grips])
             self.set_controls(np.concatenate([self.low_action, [raw[-1]]]))
             if self._do_simulation():
                 fail = True

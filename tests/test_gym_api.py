@@ -165,8 +165,16 @@ def test_ik_control_type_through_the_gym_surface():
     assert abs(r + 1e-3 * 3) < 1e-7 and not done  # ctrl penalty on the policy's 8 numbers
     ob, r, done, info = env.step(a)
     assert done and info["episode_length"] == 2
+    bx = FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik", nsub=3)
+    assert bx.dof == 15 and bx.ik_cfg.narms == 2  # (move, rotate) x 2, two grippers, connect (furniture_baxter.py:56-57)
+    ob = bx.reset()
+    full = bx.engine.get("obs")[0]
+    n = bx.object_ob_dim
+    assert ob["robot_ob"].shape == (30,) and np.allclose(ob["robot_ob"][:15], full[n + 14 : n + 29]) and np.allclose(ob["robot_ob"][15:], full[n + 29 + 14 : n + 58])
+    ob, r, done, info = bx.step(np.zeros(15))
+    assert np.isfinite(ob["robot_ob"]).all() and r == 0.0
     with pytest.raises(NotImplementedError):
-        FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik")
+        FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik_quaternion")
 
 
 def test_torque_controllers_through_the_gym_surface():

@@ -43,6 +43,21 @@ def test_ik_quaternion_preamble_equals_the_reference_code():
         assert np.abs(rot - g["q_rotation"][i].reshape(3, 3)).max() < 2e-6, i
 
 
+def test_baxter_ik_preamble_equals_the_reference_code():
+    """the two-arm branch of _do_ik_step (furniture.py:2933-2970): each arm like the one-arm case, both gripper actions passed through"""
+    g = np.load(os.path.join(HERE, "golden", "ik_pre.npz"))
+    p = dict(IK.IK_DEFAULTS)
+    for i in range(len(g["b_action"])):
+        a = g["b_action"][i]
+        for arm in range(2):
+            hq = O.mat2quat(g["b_hand_R"][i][arm].reshape(3, 3))
+            arm_action = np.concatenate([a[6 * arm : 6 * arm + 6], [a[12 + arm], a[14]]])
+            d_pos, rot, s_new, grip = O.ik_pre(arm_action, g["b_hand_pos"][i][arm], hq, g["b_s_in"][i][arm], p)
+            assert np.array_equal(d_pos, g["b_dpos"][i][arm]), (i, arm)
+            assert np.allclose(s_new, g["b_s_out"][i][arm], rtol=0, atol=1e-15) and np.abs(rot - g["b_rotation"][i][arm].reshape(3, 3)).max() < 2e-6, (i, arm)
+            assert grip == g["b_low_grips"][i][arm]
+
+
 def test_chain_and_solver_reach_the_commanded_hand_pose(sawyer):
     m = sawyer
     p = IK.ik_params(m)
@@ -75,8 +90,10 @@ def _ik_engine(m, n, gpu, quaternion_mode=0, **cfg):
 
 def _ik_state(eng, i):
     raw = eng.get("ik_state")[i].tobytes()
-    f = np.frombuffer(raw[: 22 * 4], np.float32)
-    return dict(s=f[0:4], target_pos=f[4:7], q_cmd=f[7:14], low=f[14:22], iters=int(np.frombuffer(raw[22 * 4 : 23 * 4], np.int32)[0]))
+    f = np.frombuffer(raw[: 44 * 4], np.float32)  # s[2][4], target_pos[2][3], q_cmd[14], low[16], then iters[2]
+    it = np.frombuffer(raw[44 * 4 : 46 * 4], np.int32)
+    return dict(s=f[0:4], target_pos=f[8:11], q_cmd=f[14:21], low=np.concatenate([f[28:35], f[35:36]]), iters=int(it[0]),
+                s2=f[4:8], target_pos2=f[11:14], q_cmd2=f[21:28], low_all=f[28:44], iters2=int(it[1]))
 
 
 QUAT_BACKENDS = BACKENDS + [pytest.param("emu-quaternion", id="emu-ik_quaternion")]  # the quaternion variant: lane-emulated build only
@@ -121,7 +138,7 @@ def test_ik_env_steps_match_the_cpu_env(sawyer, gpu):
             a[:, 3:7] /= np.linalg.norm(a[:, 3:7], axis=1, keepdims=True)
         if k == 0:  # first step: the oracle's sim.data would be one integration newer than the device's stored kinematics; show it the same hand pose
             for e in envs:
-                e._hand = lambda hp_hq=e._hand0: hp_hq
+                e._hand = lambda arm=0, hp_hq=e._hand0: hp_hq
         obs, rew, done, info = eng.env_step_host(a)
         for i, e in enumerate(envs):
             ob, r, d, inf = e.step(a[i].astype(np.float64))
@@ -178,8 +195,8 @@ def test_enable_ik_and_dense_refuse_what_they_cannot_serve(sawyer):
 
     ikc = IK.ik_config(sawyer)
     baxter = mjcf.load_scene("Baxter", "chair_ingolf_0650")
-    with pytest.raises(RuntimeError, match="one-arm"):
-        Engine(baxter, 1, config=default_config(), lib_path=build_emu(), ik=ikc)
+    with pytest.raises(RuntimeError, match="as many arms"):
+        Engine(baxter, 1, config=default_config(), lib_path=build_emu(), ik=ikc)  # a one-arm IK config on the two-arm scene
     with pytest.raises(RuntimeError, match="recipe"):
         Engine(mjcf.load_scene("Sawyer", "swivel_chair_0700"), 1, config=default_config(), lib_path=build_emu(), dense=dense_config())
     eng = Engine(sawyer, 1, config=default_config(), lib_path=build_emu())
@@ -220,7 +237,7 @@ def test_dense_reward_under_ik_control_matches_the_cpu_env(sawyer):
         a = rng.uniform(-1, 1, (1, 8)).astype(np.float32)
         a[0, -1] = -0.5
         if k == 0:
-            e._hand = lambda: hand0
+            e._hand = lambda arm=0: hand0
         obs, rew, done, info = eng.env_step_host(a)
         ob, r, d, inf = e.step(a[0].astype(np.float64))
         if k == 0:
@@ -262,4 +279,48 @@ def test_unstable_ik_step_resets_mid_step_and_once_more_at_the_end(sawyer):
     assert np.isfinite(obs).all() and (eng.get("flags")[:, 0] & 8 == 0).all()
     obs, rew, done, info = eng.env_step_host(a)
     assert info[1][3] == 1 and info[0][3] == 2 and not done.any()
-    assert np.isfinite(eng.get("ik_state")[1].view(np.float32)[:22]).all()  # the new episode's targets were re-synchronised from a sane pose
+    assert np.isfinite(eng.get("ik_state")[1].view(np.float32)[:44]).all()  # the new episode's targets were re-synchronised from a sane pose
+
+
+def test_baxter_ik_env_steps_match_the_cpu_env():
+    """control_type="ik" on the two-arm env (15-number actions: move / rotate per arm, two grippers, connect): both arms' targets, joint
+    commands and low-level actions, observation and reward of the device equal the CPU env -- emulated build"""
+    from furniture_b200.engine import Engine, default_config
+    from oracle.ref_env import OracleIKEnv
+    from parity_util import build_emu
+    from test_env_parity import _sync_oracle_from_engine
+
+    m = mjcf.load_scene("Baxter", "chair_ingolf_0650")
+    ikc = IK.ik_config(m)
+    assert ikc.narms == 2 and abs(ikc.kp - 2.0) < 1e-9 and abs(ikc.user_sensitivity - 1.0) < 1e-9 and abs(ikc.damping - 0.7) < 1e-7
+    eng = Engine(m, 1, config=default_config(), lib_path=build_emu(), ik=ikc)
+    assert eng.act_dim == 15
+    eng.env_reset()
+    e = OracleIKEnv(m)
+    e.reset()
+    _sync_oracle_from_engine(e, eng, 0)
+    e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[0]
+    lpos, lquat = eng.get("link_xpos")[0], eng.get("link_xquat")[0]
+    hands = []
+    for arm in range(2):
+        hl = eng.scene.hand_link[arm]
+        R = mjcf.q_to_mat(lquat[4 * hl : 4 * hl + 4].astype(np.float64))
+        hp = lpos[3 * hl : 3 * hl + 3].astype(np.float64) + R @ np.array(ikc.arm[arm].hand_pos[:])
+        hq = mjcf.q_norm(mjcf.q_mul(lquat[4 * hl : 4 * hl + 4].astype(np.float64), np.array(ikc.arm[arm].hand_quat[:], dtype=np.float64)))
+        e.iks[arm].sync(hp, hq)
+        hands.append((hp, hq))
+    rng = np.random.RandomState(6)
+    for k in range(2):
+        a = rng.uniform(-1, 1, (1, 15)).astype(np.float32)
+        a[0, -1] = -0.5
+        if k == 0:
+            e._hand = lambda arm=0: hands[arm]
+        obs, rew, done, info = eng.env_step_host(a)
+        ob, r, d, inf = e.step(a[0].astype(np.float64))
+        if k == 0:
+            del e._hand
+        st = _ik_state(eng, 0)
+        for arm, (tp, qc) in enumerate(((st["target_pos"], st["q_cmd"]), (st["target_pos2"], st["q_cmd2"]))):
+            assert np.abs(tp - e.iks[arm].target_pos).max() < 2e-6 and np.abs(qc - e.iks[arm].q_cmd).max() < 3e-4, (k, arm, qc, e.iks[arm].q_cmd)
+        assert np.abs(st["low_all"] - e.low_action).max() < 2e-3, (k, st["low_all"], e.low_action)
+        assert np.abs(obs[0] - ob).max() < 1e-3 and abs(rew[0] - r) < 1e-5 and bool(done[0]) == d

@@ -114,7 +114,49 @@ def main():
         rq["dpos"].append(calls["first"][0]); rq["rotation"].append(calls["first"][1].ravel()); rq["low_grip"].append(fq.low[7])
         rq["n_sim"].append(calls["sim"]); rq["n_closed_loop"].append(calls["closed"])
     print("ik_quaternion: %d cases" % len(rq["action"]))
-    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{"q_" + k: np.array(v) for k, v in rq.items()}, **{k: np.array(v) for k, v in rec.items()},
+    # ---- Baxter, control_type="ik" (furniture.py:2933-2970): the same per arm, right then left; both grippers pass through
+    rb = {k: [] for k in ("action", "hand_pos", "hand_R", "s_in", "dpos", "rotation", "s_out", "low_grips")}
+    for n in range(200):
+        hand_R = [rand_rot(rng), rand_rot(rng)]
+        hand_pos = [rng.uniform(-0.5, 0.5, size=3) + [0, 0, 0.6], rng.uniform(-1.6, 1.6, size=3)]
+        got = {}
+
+        class CtlB:
+            def get_control(self, right=None, left=None):
+                if right is not None:
+                    got["right"], got["left"] = right, left
+                return np.zeros(14)
+
+        class FakeB:
+            _control_type, _agent_type, _record_demo, _action_repeat = "ik", "Baxter", False, 3
+            _move_speed, _rotate_speed = 0.1, 22.5
+            _min_gripper_pos, _max_gripper_pos = np.array([-1.5, -1.5, 0.0]), np.array([1.5, 1.5, 1.5])
+            _controller = CtlB()
+            sim = types.SimpleNamespace(data=types.SimpleNamespace(get_body_xpos=lambda name: hand_pos[0 if name == "right_hand" else 1].copy()))
+            _bounded_d_pos = FurnitureEnv._bounded_d_pos
+            _make_input = FurnitureEnv._make_input
+            _right_hand_quat = property(lambda self: T.mat2quat(np.ascontiguousarray(hand_R[0], dtype=np.float32)))
+            _left_hand_quat = property(lambda self: T.mat2quat(np.ascontiguousarray(hand_R[1], dtype=np.float32)))
+
+            def _setup_action(self, low):
+                self.low = np.array(low, dtype=np.float64)
+                return low
+
+            def _do_simulation(self, ctrl):
+                pass
+
+        fb = FakeB()
+        s_in = [T.mat2quat(rand_rot(rng).astype(np.float32)), T.mat2quat(hand_R[1].astype(np.float32))]
+        fb._initial_right_hand_quat, fb._initial_left_hand_quat = s_in
+        a = rng.uniform(-1, 1, size=15)
+        FurnitureEnv._do_ik_step(fb, a.copy())
+        rb["action"].append(a); rb["hand_pos"].append(np.array(hand_pos)); rb["hand_R"].append(np.array([r.ravel() for r in hand_R]))
+        rb["s_in"].append(np.array(s_in, dtype=np.float64))
+        rb["dpos"].append(np.array([got["right"]["dpos"], got["left"]["dpos"]], dtype=np.float64))
+        rb["rotation"].append(np.array([np.asarray(got["right"]["rotation"]).ravel(), np.asarray(got["left"]["rotation"]).ravel()], dtype=np.float64))
+        rb["s_out"].append(np.array([fb._initial_right_hand_quat, fb._initial_left_hand_quat], dtype=np.float64)); rb["low_grips"].append(fb.low[14:16])
+    print("baxter ik: %d cases" % len(rb["action"]))
+    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{"q_" + k: np.array(v) for k, v in rq.items()}, **{"b_" + k: np.array(v) for k, v in rb.items()}, **{k: np.array(v) for k, v in rec.items()},
                         source="reference FurnitureEnv._do_ik_step run unmodified around stand-ins for the simulator and the pybullet controller (tools/make_golden_ik.py)")
     print("ik_pre: %d cases; _do_simulation calls %s, closed-loop get_control calls %s" % (len(rec["action"]), set(rec["n_sim"]), set(rec["n_closed_loop"])))
 
