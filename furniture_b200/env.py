@@ -120,8 +120,8 @@ class BatchedFurnitureEnv:
         self.control_type = control_type
         self.ik_cfg = None
         if control_type in ("ik", "ik_quaternion"):
-            if agent not in ("Sawyer", "Baxter") or (agent == "Baxter" and control_type != "ik"):
-                raise NotImplementedError("control_type='%s' is built for the Sawyer env ('ik' for Baxter as well)" % control_type)
+            if agent not in ("Sawyer", "Baxter"):
+                raise NotImplementedError("control_type='%s' is built for the Sawyer and Baxter envs" % control_type)
             from .ik import ik_config
 
             self.ik_cfg = ik_config(self.model, **dict(ik or {}, quaternion_mode=int(control_type == "ik_quaternion")))

@@ -59,8 +59,8 @@ class FurnitureGymB200:
 
             self.ctl_cfg = ctl_config(self.control_type, model=self.model, move_speed=ctl.get("ik", {}).get("move_speed", 0.1))
         if self.control_type in ("ik", "ik_quaternion"):  # "ik" is the reference's default control type (config/furniture.py:57)
-            if AGENTS[name] not in ("Sawyer", "Baxter") or (AGENTS[name] == "Baxter" and self.control_type != "ik"):
-                raise NotImplementedError("control_type='%s' is built for the Sawyer env ('ik' for Baxter as well)" % self.control_type)
+            if AGENTS[name] not in ("Sawyer", "Baxter"):
+                raise NotImplementedError("control_type='%s' is built for the Sawyer and Baxter envs" % self.control_type)
             from .ik import ik_config
 
             self.ik_cfg = ik_config(self.model, **dict(ctl["ik"], quaternion_mode=int(self.control_type == "ik_quaternion")))

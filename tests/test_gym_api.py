@@ -173,8 +173,10 @@ def test_ik_control_type_through_the_gym_surface():
     assert ob["robot_ob"].shape == (30,) and np.allclose(ob["robot_ob"][:15], full[n + 14 : n + 29]) and np.allclose(ob["robot_ob"][15:], full[n + 29 + 14 : n + 58])
     ob, r, done, info = bx.step(np.zeros(15))
     assert np.isfinite(ob["robot_ob"]).all() and r == 0.0
+    bq = FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik_quaternion", nsub=3)
+    assert bq.dof == 17  # (move 3, quaternion 4) x 2, two grippers, connect
     with pytest.raises(NotImplementedError):
-        FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="ik_quaternion")
+        FurnitureGymB200(name="FurnitureBaxterEnv", furniture_name="chair_ingolf_0650", lib_path=build_emu(), control_type="position")
 
 
 def test_torque_controllers_through_the_gym_surface():

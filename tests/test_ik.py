@@ -58,6 +58,19 @@ def test_baxter_ik_preamble_equals_the_reference_code():
             assert grip == g["b_low_grips"][i][arm]
 
 
+def test_baxter_ik_quaternion_preamble_equals_the_reference_code():
+    g = np.load(os.path.join(HERE, "golden", "ik_pre.npz"))
+    p = dict(IK.IK_DEFAULTS)
+    for i in range(len(g["bq_action"])):
+        a = g["bq_action"][i]
+        for arm in range(2):
+            hq = O.mat2quat(g["bq_hand_R"][i][arm].reshape(3, 3))
+            arm_action = np.concatenate([a[7 * arm : 7 * arm + 7], [a[14 + arm], a[16]]])
+            d_pos, rot, grip = O.ik_pre_quaternion(arm_action, g["bq_hand_pos"][i][arm], hq, p)
+            assert np.array_equal(d_pos, g["bq_dpos"][i][arm]) and grip == g["bq_low_grips"][i][arm], (i, arm)
+            assert np.abs(rot - g["bq_rotation"][i][arm].reshape(3, 3)).max() < 2e-6, (i, arm)
+
+
 def test_chain_and_solver_reach_the_commanded_hand_pose(sawyer):
     m = sawyer
     p = IK.ik_params(m)
@@ -282,21 +295,23 @@ def test_unstable_ik_step_resets_mid_step_and_once_more_at_the_end(sawyer):
     assert np.isfinite(eng.get("ik_state")[1].view(np.float32)[:44]).all()  # the new episode's targets were re-synchronised from a sane pose
 
 
-def test_baxter_ik_env_steps_match_the_cpu_env():
-    """control_type="ik" on the two-arm env (15-number actions: move / rotate per arm, two grippers, connect): both arms' targets, joint
-    commands and low-level actions, observation and reward of the device equal the CPU env -- emulated build"""
+@pytest.mark.parametrize("quat", [0, 1], ids=["ik", "ik_quaternion"])
+def test_baxter_ik_env_steps_match_the_cpu_env(quat):
+    """control_type="ik" / "ik_quaternion" on the two-arm env (15 / 17-number actions: move / rotate per arm, two grippers, connect): both
+    arms' targets, joint commands and low-level actions, observation and reward of the device equal the CPU env -- emulated build"""
     from furniture_b200.engine import Engine, default_config
     from oracle.ref_env import OracleIKEnv
     from parity_util import build_emu
     from test_env_parity import _sync_oracle_from_engine
 
     m = mjcf.load_scene("Baxter", "chair_ingolf_0650")
-    ikc = IK.ik_config(m)
+    ikc = IK.ik_config(m, quaternion_mode=quat)
     assert ikc.narms == 2 and abs(ikc.kp - 2.0) < 1e-9 and abs(ikc.user_sensitivity - 1.0) < 1e-9 and abs(ikc.damping - 0.7) < 1e-7
     eng = Engine(m, 1, config=default_config(), lib_path=build_emu(), ik=ikc)
-    assert eng.act_dim == 15
+    dof = 17 if quat else 15
+    assert eng.act_dim == dof
     eng.env_reset()
-    e = OracleIKEnv(m)
+    e = OracleIKEnv(m, quaternion_mode=quat)
     e.reset()
     _sync_oracle_from_engine(e, eng, 0)
     e.sim.qfrc_bias[: e.nr] = eng.get("qfrc_bias")[0]
@@ -311,8 +326,12 @@ def test_baxter_ik_env_steps_match_the_cpu_env():
         hands.append((hp, hq))
     rng = np.random.RandomState(6)
     for k in range(2):
-        a = rng.uniform(-1, 1, (1, 15)).astype(np.float32)
+        a = rng.uniform(-1, 1, (1, dof)).astype(np.float32)
         a[0, -1] = -0.5
+        if quat:
+            for off in (3, 10):
+                a[0, off], a[0, off + 1 : off + 4] = 1.0, rng.normal(size=3) * 0.05
+                a[0, off : off + 4] /= np.linalg.norm(a[0, off : off + 4])
         if k == 0:
             e._hand = lambda arm=0: hands[arm]
         obs, rew, done, info = eng.env_step_host(a)

@@ -37,7 +37,7 @@ def main():
     checks = [("controller arithmetic %s" % m, lambda m=m: TC.test_device_controllers_reproduce_the_reference_emu.__wrapped__(golden, m)
                if hasattr(TC.test_device_controllers_reproduce_the_reference_emu, "__wrapped__") else TC.test_device_controllers_reproduce_the_reference_emu(golden, m)) for m in TC.MODES]
     checks += [("controller env %s" % m, lambda m=m: TC.test_controller_env_steps_match_the_cpu_env(torque, m)) for m in TC.MODES]
-    checks += [("baxter ik env", lambda: TI.test_baxter_ik_env_steps_match_the_cpu_env()),
+    checks += [("baxter ik env", lambda: TI.test_baxter_ik_env_steps_match_the_cpu_env(0)), ("baxter ik_quaternion env", lambda: TI.test_baxter_ik_env_steps_match_the_cpu_env(1)),
                ("ik_quaternion env", lambda: TI.test_ik_env_steps_match_the_cpu_env(sawyer, "emu-quaternion")),
                ("ik + dense env", lambda: TI.test_dense_reward_under_ik_control_matches_the_cpu_env(sawyer)),
                ("ik unstable step", lambda: TI.test_unstable_ik_step_resets_mid_step_and_once_more_at_the_end(sawyer))]

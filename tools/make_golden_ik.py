@@ -156,7 +156,38 @@ def main():
         rb["rotation"].append(np.array([np.asarray(got["right"]["rotation"]).ravel(), np.asarray(got["left"]["rotation"]).ravel()], dtype=np.float64))
         rb["s_out"].append(np.array([fb._initial_right_hand_quat, fb._initial_left_hand_quat], dtype=np.float64)); rb["low_grips"].append(fb.low[14:16])
     print("baxter ik: %d cases" % len(rb["action"]))
-    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{"q_" + k: np.array(v) for k, v in rq.items()}, **{"b_" + k: np.array(v) for k, v in rb.items()}, **{k: np.array(v) for k, v in rec.items()},
+    # ---- Baxter, control_type="ik_quaternion" (furniture.py:2998-3058 with two arms): 17 numbers
+    rbq = {k: [] for k in ("action", "hand_pos", "hand_R", "dpos", "rotation", "low_grips")}
+    for n in range(100):
+        hand_R = [rand_rot(rng), rand_rot(rng)]
+        hand_pos = [rng.uniform(-0.5, 0.5, size=3) + [0, 0, 0.6], rng.uniform(-1.6, 1.6, size=3)]
+        got = {}
+
+        class CtlBQ:
+            def get_control(self, right=None, left=None):
+                if right is not None:
+                    got["right"], got["left"] = right, left
+                return np.zeros(14)
+
+        class FakeBQ(FakeB):
+            _control_type, _arms = "ik_quaternion", ["right", "left"]
+            _controller = CtlBQ()
+            sim = types.SimpleNamespace(data=types.SimpleNamespace(get_body_xpos=lambda name: hand_pos[0 if name == "right_hand" else 1].copy()))
+            _right_hand_quat = property(lambda self: T.mat2quat(np.ascontiguousarray(hand_R[0], dtype=np.float32)))
+            _left_hand_quat = property(lambda self: T.mat2quat(np.ascontiguousarray(hand_R[1], dtype=np.float32)))
+
+        fbq = FakeBQ()
+        a = rng.uniform(-1, 1, size=17)
+        for off in (3, 10):
+            q = rng.normal(size=4)
+            a[off : off + 4] = q / np.linalg.norm(q)
+        FurnitureEnv._do_ik_step(fbq, a.copy())
+        rbq["action"].append(a); rbq["hand_pos"].append(np.array(hand_pos)); rbq["hand_R"].append(np.array([r.ravel() for r in hand_R]))
+        rbq["dpos"].append(np.array([got["right"]["dpos"], got["left"]["dpos"]], dtype=np.float64))
+        rbq["rotation"].append(np.array([np.asarray(got["right"]["rotation"]).ravel(), np.asarray(got["left"]["rotation"]).ravel()], dtype=np.float64))
+        rbq["low_grips"].append(fbq.low[14:16])
+    print("baxter ik_quaternion: %d cases" % len(rbq["action"]))
+    np.savez_compressed(os.path.join(OUT, "ik_pre.npz"), **{"q_" + k: np.array(v) for k, v in rq.items()}, **{"b_" + k: np.array(v) for k, v in rb.items()}, **{"bq_" + k: np.array(v) for k, v in rbq.items()}, **{k: np.array(v) for k, v in rec.items()},
                         source="reference FurnitureEnv._do_ik_step run unmodified around stand-ins for the simulator and the pybullet controller (tools/make_golden_ik.py)")
     print("ik_pre: %d cases; _do_simulation calls %s, closed-loop get_control calls %s" % (len(rec["action"]), set(rec["n_sim"]), set(rec["n_closed_loop"])))
 
